@@ -1,0 +1,122 @@
+// fcl_oracle.hpp — CPU ORACLE (test infrastructure, NOT product code).
+//
+// A dependency-free, scalar, double-precision restatement of the reference's
+// BVHModel<OBBRSS<double>> mesh-mesh collide()/distance() path.  Only tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+// may build, link or call anything in this directory.  The shipped library
+// (fcl_b200/) never includes or links it.
+//
+// PARITY STATUS: the reference cannot be compiled here (it needs Eigen3 and
+// libccd, neither is on the image), so this restatement is pinned against the
+// reference's own known-answer tests and invariants (see tests/test_oracle_*.py):
+//   * test/test_fcl_math.cpp:256-291   RSS distance known answers 2, 1, sqrt(6)-1, 1
+//   * test/test_fcl_collision.cpp:792-886  contact-pair sets equal across split
+//     methods and equal to brute-force all-pairs triangle intersection
+//   * test/test_fcl_distance.cpp:177-298  distance equal across split methods,
+//     qsize 2 vs 20, and equal to brute-force all-pairs triangle distance
+//   * test/test_fcl_shape_mesh_consistency.cpp:57-80  tessellated spheres
+//   * test/test_fcl_collision.cpp:271-311  OBB overlap == AABB overlap
+// At the ULP level (Eigen's internal association order of 3-term sums) parity
+// is UNPINNED; this file fixes one canonical order, documented at each helper:
+// every 3-term sum is evaluated left to right, (a0*b0 + a1*b1) + a2*b2, with
+// separately rounded multiplies and adds (compile with -ffp-contract=off,
+// matching the reference's default non-FMA x86-64 build, CMakeLists.txt:82-116).
+//
+// All file:line citations are relative to /root/reference/.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace oracle {
+
+struct Vec3 {
+  double v[3];
+  double& operator[](int i) { return v[i]; }
+  double operator[](int i) const { return v[i]; }
+};
+
+// Row-major storage: m[r][c].  "axis.col(i)" of the reference is (m[0][i], m[1][i], m[2][i]).
+struct Mat3 {
+  double m[3][3];
+};
+
+struct Tri {
+  int v[3];
+};
+
+// One BVNode<OBBRSS<double>>  (include/fcl/geometry/bvh/BV_node.h:50-72,
+// BV_node_base.h:48-63, math/bv/OBB.h:56-68, RSS.h:63-82, OBBRSS.h:52-60).
+struct Node {
+  int first_child;      // <0 => leaf holding primitive -(first_child+1)
+  int first_primitive;  // build bookkeeping
+  int num_primitives;
+  Mat3 axis;            // shared by obb and rss (BV_fitter-inl.h:464)
+  Vec3 obb_To, obb_ext;
+  Vec3 rss_To;
+  double rss_l[2], rss_r;
+};
+
+enum SplitMethod { SPLIT_MEAN = 0, SPLIT_MEDIAN = 1, SPLIT_BV_CENTER = 2 };
+
+struct Model {
+  std::vector<Vec3> verts;
+  std::vector<Tri> tris;
+  std::vector<Node> nodes;
+};
+
+// rigid pose: p_world = R * p + t
+struct Pose {
+  Mat3 R;
+  Vec3 t;
+};
+
+struct Contact {
+  int b1, b2;
+  Vec3 normal, pos;
+  double depth;
+};
+
+struct CollideStats {
+  long long n_bv = 0, n_leaf = 0;
+};
+
+struct DistanceOut {
+  double min_distance;
+  Vec3 p1, p2;  // world frame (valid when nearest points requested)
+  int b1, b2;
+};
+
+// ---- inputs ----------------------------------------------------------------
+bool load_obj(const std::string& path, std::vector<Vec3>& pts, std::vector<Tri>& tris);
+void build_model(Model& m, const std::vector<Vec3>& pts, const std::vector<Tri>& tris,
+                 SplitMethod split = SPLIT_MEAN);
+
+// ---- BV / leaf kernels -------------------------------------------------------
+bool obb_disjoint(const Mat3& B, const Vec3& T, const Vec3& a, const Vec3& b);
+bool obb_overlap(const Mat3& R0, const Vec3& T0, const Node& n1, const Node& n2);
+double rect_distance(const Mat3& Rab, const Vec3& Tab, const double a[2], const double b[2]);
+double rss_distance(const Mat3& R0, const Vec3& T0, const Node& n1, const Node& n2);
+bool tri_intersect(const Vec3 P[3], const Vec3 Qin[3], const Mat3& R, const Vec3& T,
+                   Vec3* contact_points, unsigned* num_contact_points, double* depth,
+                   Vec3* normal);
+double tri_distance(const Vec3 S[3], const Vec3 T[3], Vec3& P, Vec3& Q);
+
+// ---- queries -----------------------------------------------------------------
+// collide(): contacts appended in the reference's DFS order; returns numContacts.
+size_t collide(const Model& m1, const Pose& tf1, const Model& m2, const Pose& tf2,
+               size_t num_max_contacts, bool enable_contact, std::vector<Contact>& out,
+               CollideStats* stats = nullptr);
+// distance(): qsize<=2 recursive, else queue variant.
+double distance(const Model& m1, const Pose& tf1, const Model& m2, const Pose& tf2,
+                bool enable_nearest_points, DistanceOut& out, int qsize = 2,
+                CollideStats* stats = nullptr);
+
+// brute force over all triangle pairs (for the invariants)
+void brute_collide_pairs(const Model& m1, const Pose& tf1, const Model& m2, const Pose& tf2,
+                         std::vector<std::pair<int, int>>& pairs);
+double brute_distance(const Model& m1, const Pose& tf1, const Model& m2, const Pose& tf2,
+                      DistanceOut& out);
+
+}  // namespace oracle

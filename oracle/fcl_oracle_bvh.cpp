@@ -1,0 +1,688 @@
+// fcl_oracle_bvh.cpp — CPU ORACLE (test infrastructure, NOT product code).
+// OBJ loading, BVHModel<OBBRSS> construction and the collide / distance
+// traversals.  See fcl_oracle.hpp for the parity statement.
+// Citations are relative to /root/reference/.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <queue>
+
+#include "fcl_oracle.hpp"
+#include "fcl_oracle_vec.hpp"
+
+namespace oracle {
+
+// -----------------------------------------------------------------------------
+// OBJ loader with the semantics of test/test_fcl_utility.h:194-280: the first
+// whitespace token selects the record; 'v' (not vn/vt) adds a vertex, 'f' adds a
+// triangle fan with 1-based indices ("a/b/c" -> atoi reads a); anything else
+// (including the "6540 2180" first line of env.obj) is ignored.
+// -----------------------------------------------------------------------------
+bool load_obj(const std::string& path, std::vector<Vec3>& pts, std::vector<Tri>& tris) {
+  FILE* f = std::fopen(path.c_str(), "rb");
+  if (!f) return false;
+  char line[2000];
+  while (std::fgets(line, sizeof line, f)) {
+    char* tok = std::strtok(line, "\r\n\t ");
+    if (!tok || tok[0] == '#' || tok[0] == 0) continue;
+    if (tok[0] == 'v') {
+      if (tok[1] == 'n' || tok[1] == 't') continue;
+      double c[3] = {0, 0, 0};
+      for (int k = 0; k < 3; ++k) {
+        char* s = std::strtok(nullptr, "\t ");
+        c[k] = s ? std::atof(s) : 0.0;
+      }
+      pts.push_back(Vec3{{c[0], c[1], c[2]}});
+    } else if (tok[0] == 'f') {
+      int idx[30];
+      int n = 0;
+      char* s;
+      while (n < 30 && (s = std::strtok(nullptr, "\t \r\n")) != nullptr)
+        if (std::strlen(s)) idx[n++] = std::atoi(s) - 1;
+      // fan: (0, t+1, t+2).  (For plain "f a b c" records the reference emits the
+      // same triangle; its no-normal branch only differs for polygons, :250-255.)
+      for (int t = 0; t < n - 2; ++t) tris.push_back(Tri{{idx[0], idx[t + 1], idx[t + 2]}});
+    }
+  }
+  std::fclose(f);
+  return true;
+}
+
+// -----------------------------------------------------------------------------
+// Fitting — include/fcl/geometry/bvh/detail/BV_fitter-inl.h:449-477
+// -----------------------------------------------------------------------------
+namespace {
+
+struct Builder {
+  Model& m;
+  SplitMethod split;
+  std::vector<unsigned> prim;
+  int num_bvs = 0;
+
+  // getCovariance — include/fcl/math/geometry-inl.h:1335-1425 (triangle branch)
+  void covariance(const unsigned* idx, int n, double M[3][3]) const {
+    double S1[3] = {0, 0, 0};
+    double S2[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int i = 0; i < n; ++i) {
+      const Tri& t = m.tris[idx[i]];
+      const Vec3& p1 = m.verts[t.v[0]];
+      const Vec3& p2 = m.verts[t.v[1]];
+      const Vec3& p3 = m.verts[t.v[2]];
+      for (int k = 0; k < 3; ++k) S1[k] += ((p1[k] + p2[k]) + p3[k]);
+      S2[0][0] += (p1[0] * p1[0] + p2[0] * p2[0] + p3[0] * p3[0]);
+      S2[1][1] += (p1[1] * p1[1] + p2[1] * p2[1] + p3[1] * p3[1]);
+      S2[2][2] += (p1[2] * p1[2] + p2[2] * p2[2] + p3[2] * p3[2]);
+      S2[0][1] += (p1[0] * p1[1] + p2[0] * p2[1] + p3[0] * p3[1]);
+      S2[0][2] += (p1[0] * p1[2] + p2[0] * p2[2] + p3[0] * p3[2]);
+      S2[1][2] += (p1[1] * p1[2] + p2[1] * p2[2] + p3[1] * p3[2]);
+    }
+    int n_points = 3 * n;
+    M[0][0] = S2[0][0] - S1[0] * S1[0] / n_points;
+    M[1][1] = S2[1][1] - S1[1] * S1[1] / n_points;
+    M[2][2] = S2[2][2] - S1[2] * S1[2] / n_points;
+    M[0][1] = S2[0][1] - S1[0] * S1[1] / n_points;
+    M[1][2] = S2[1][2] - S1[1] * S1[2] / n_points;
+    M[0][2] = S2[0][2] - S1[0] * S1[2] / n_points;
+    M[1][0] = M[0][1];
+    M[2][0] = M[0][2];
+    M[2][1] = M[1][2];
+  }
+
+  // eigen_old — include/fcl/math/geometry-inl.h:477-558 (cyclic Jacobi, <=50 sweeps).
+  // On return evec[k] is the k-th eigenvector (the reference's vout.col(k) written
+  // from v[k][*] and read back with eigenV.row(), :503-505 and :590-591).
+  static void jacobi(const double Min[3][3], double dout[3], double v[3][3]) {
+    double R[3][3];
+    std::memcpy(R, Min, sizeof R);
+    const int n = 3;
+    double b[3], z[3], d[3];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) v[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int ip = 0; ip < n; ++ip) {
+      b[ip] = d[ip] = R[ip][ip];
+      z[ip] = 0;
+    }
+    for (int i = 0; i < 50; ++i) {
+      double sm = 0;
+      for (int ip = 0; ip < n; ++ip)
+        for (int iq = ip + 1; iq < n; ++iq) sm += std::abs(R[ip][iq]);
+      if (sm == 0.0) {
+        dout[0] = d[0]; dout[1] = d[1]; dout[2] = d[2];
+        return;
+      }
+      double tresh = (i < 3) ? 0.2 * sm / (n * n) : 0.0;
+      for (int ip = 0; ip < n; ++ip) {
+        for (int iq = ip + 1; iq < n; ++iq) {
+          double g = 100.0 * std::abs(R[ip][iq]);
+          if (i > 3 && std::abs(d[ip]) + g == std::abs(d[ip]) && std::abs(d[iq]) + g == std::abs(d[iq]))
+            R[ip][iq] = 0.0;
+          else if (std::abs(R[ip][iq]) > tresh) {
+            double h = d[iq] - d[ip], t;
+            if (std::abs(h) + g == std::abs(h)) t = (R[ip][iq]) / h;
+            else {
+              double theta = 0.5 * h / (R[ip][iq]);
+              t = 1.0 / (std::abs(theta) + std::sqrt(1.0 + theta * theta));
+              if (theta < 0.0) t = -t;
+            }
+            double c = 1.0 / std::sqrt(1 + t * t);
+            double s = t * c;
+            double tau = s / (1.0 + c);
+            h = t * R[ip][iq];
+            z[ip] -= h; z[iq] += h; d[ip] -= h; d[iq] += h;
+            R[ip][iq] = 0.0;
+            auto rot = [&](double& x, double& y) {
+              double gg = x, hh = y;
+              x = gg - s * (hh + gg * tau);
+              y = hh + s * (gg - hh * tau);
+            };
+            for (int j = 0; j < ip; ++j) rot(R[j][ip], R[j][iq]);
+            for (int j = ip + 1; j < iq; ++j) rot(R[ip][j], R[j][iq]);
+            for (int j = iq + 1; j < n; ++j) rot(R[ip][j], R[iq][j]);
+            for (int j = 0; j < n; ++j) rot(v[j][ip], v[j][iq]);
+          }
+        }
+      }
+      for (int ip = 0; ip < n; ++ip) {
+        b[ip] += z[ip];
+        d[ip] = b[ip];
+        z[ip] = 0.0;
+      }
+    }
+    std::fprintf(stderr, "oracle: too many iterations in Jacobi transform.\n");
+    dout[0] = d[0]; dout[1] = d[1]; dout[2] = d[2];
+  }
+
+  // axisFromEigen — include/fcl/math/geometry-inl.h:563-597
+  static void axis_from_eigen(const double v[3][3], const double s[3], Mat3& axis) {
+    int mn, mid, mx;
+    if (s[0] > s[1]) { mx = 0; mn = 1; } else { mn = 0; mx = 1; }
+    if (s[2] < s[mn]) { mid = mn; mn = 2; }
+    else if (s[2] > s[mx]) { mid = mx; mx = 2; }
+    else { mid = 2; }
+    (void)mn;
+    for (int r = 0; r < 3; ++r) {
+      axis.m[r][0] = v[r][mx];
+      axis.m[r][1] = v[r][mid];
+    }
+    Vec3 c2 = cross(col(axis, 0), col(axis, 1));
+    for (int r = 0; r < 3; ++r) axis.m[r][2] = c2[r];
+  }
+
+  // getExtentAndCenter_mesh — include/fcl/math/geometry-inl.h:294-362
+  void extent_and_center(const unsigned* idx, int n, const Mat3& axis, Vec3& center, Vec3& extent) const {
+    const double real_max = std::numeric_limits<double>::max();
+    double mn[3] = {real_max, real_max, real_max}, mx[3] = {-real_max, -real_max, -real_max};
+    for (int i = 0; i < n; ++i) {
+      const Tri& t = m.tris[idx[i]];
+      for (int j = 0; j < 3; ++j) {
+        const Vec3& p = m.verts[t.v[j]];
+        for (int k = 0; k < 3; ++k) {
+          double proj = dot(col(axis, k), p);
+          if (proj > mx[k]) mx[k] = proj;
+          if (proj < mn[k]) mn[k] = proj;
+        }
+      }
+    }
+    Vec3 o{{(mx[0] + mn[0]) / 2, (mx[1] + mn[1]) / 2, (mx[2] + mn[2]) / 2}};
+    center = mul(axis, o);
+    extent = Vec3{{(mx[0] - mn[0]) / 2, (mx[1] - mn[1]) / 2, (mx[2] - mn[2]) / 2}};
+  }
+
+  // getRadiusAndOriginAndRectangleSize — include/fcl/math/geometry-inl.h:709-988
+  void rss_fit(const unsigned* idx, int n, const Mat3& axis, Vec3& origin, double l[2], double& r) const {
+    const int size_P = 3 * n;
+    std::vector<Vec3> P(size_P);
+    int id = 0;
+    for (int i = 0; i < n; ++i) {
+      const Tri& t = m.tris[idx[i]];
+      for (int j = 0; j < 3; ++j) {
+        const Vec3& p = m.verts[t.v[j]];
+        P[id][0] = dot(col(axis, 0), p);
+        P[id][1] = dot(col(axis, 1), p);
+        P[id][2] = dot(col(axis, 2), p);
+        id++;
+      }
+    }
+    double minx, maxx, miny, maxy, minz, maxz, cz, radsqr;
+    minz = maxz = P[0][2];
+    for (int i = 1; i < size_P; ++i) {
+      double zv = P[i][2];
+      if (zv < minz) minz = zv;
+      else if (zv > maxz) maxz = zv;
+    }
+    r = 0.5 * (maxz - minz);
+    radsqr = r * r;
+    cz = 0.5 * (maxz + minz);
+
+    auto cap = [&](int i) {  // sqrt(max(radsqr - dz*dz, 0)) for point i
+      double dz = P[i][2] - cz;
+      return std::sqrt(std::max<double>(radsqr - dz * dz, 0));
+    };
+    auto extreme = [&](int c, int& minindex, int& maxindex) {
+      minindex = maxindex = 0;
+      double mintmp = P[0][c], maxtmp = P[0][c];
+      for (int i = 1; i < size_P; ++i) {
+        double val = P[i][c];
+        if (val < mintmp) { minindex = i; mintmp = val; }
+        else if (val > maxtmp) { maxindex = i; maxtmp = val; }
+      }
+    };
+    int minindex, maxindex;
+    extreme(0, minindex, maxindex);
+    minx = P[minindex][0] + cap(minindex);
+    maxx = P[maxindex][0] - cap(maxindex);
+    for (int i = 0; i < size_P; ++i)
+      if (P[i][0] < minx) { double x = P[i][0] + cap(i); if (x < minx) minx = x; }
+    for (int i = 0; i < size_P; ++i)
+      if (P[i][0] > maxx) { double x = P[i][0] - cap(i); if (x > maxx) maxx = x; }
+
+    extreme(1, minindex, maxindex);
+    miny = P[minindex][1] + cap(minindex);
+    maxy = P[maxindex][1] - cap(maxindex);
+    for (int i = 0; i < size_P; ++i)
+      if (P[i][1] < miny) { double y = P[i][1] + cap(i); if (y < miny) miny = y; }
+    for (int i = 0; i < size_P; ++i)
+      if (P[i][1] > maxy) { double y = P[i][1] - cap(i); if (y > maxy) maxy = y; }
+
+    // corner growth (:883-965)
+    double dx, dy, u, t;
+    const double a = std::sqrt(0.5);
+    for (int i = 0; i < size_P; ++i) {
+      if (P[i][0] > maxx) {
+        if (P[i][1] > maxy) {
+          dx = P[i][0] - maxx; dy = P[i][1] - maxy;
+          u = dx * a + dy * a;
+          t = (a * u - dx) * (a * u - dx) + (a * u - dy) * (a * u - dy) + (cz - P[i][2]) * (cz - P[i][2]);
+          u = u - std::sqrt(std::max<double>(radsqr - t, 0));
+          if (u > 0) { maxx += u * a; maxy += u * a; }
+        } else if (P[i][1] < miny) {
+          dx = P[i][0] - maxx; dy = P[i][1] - miny;
+          u = dx * a - dy * a;
+          t = (a * u - dx) * (a * u - dx) + (-a * u - dy) * (-a * u - dy) + (cz - P[i][2]) * (cz - P[i][2]);
+          u = u - std::sqrt(std::max<double>(radsqr - t, 0));
+          if (u > 0) { maxx += u * a; miny -= u * a; }
+        }
+      } else if (P[i][0] < minx) {
+        if (P[i][1] > maxy) {
+          dx = P[i][0] - minx; dy = P[i][1] - maxy;
+          u = dy * a - dx * a;
+          t = (-a * u - dx) * (-a * u - dx) + (a * u - dy) * (a * u - dy) + (cz - P[i][2]) * (cz - P[i][2]);
+          u = u - std::sqrt(std::max<double>(radsqr - t, 0));
+          if (u > 0) { minx -= u * a; maxy += u * a; }
+        } else if (P[i][1] < miny) {
+          dx = P[i][0] - minx; dy = P[i][1] - miny;
+          u = -dx * a - dy * a;
+          t = (-a * u - dx) * (-a * u - dx) + (-a * u - dy) * (-a * u - dy) + (cz - P[i][2]) * (cz - P[i][2]);
+          u = u - std::sqrt(std::max<double>(radsqr - t, 0));
+          if (u > 0) { minx -= u * a; miny -= u * a; }
+        }
+      }
+    }
+    for (int k = 0; k < 3; ++k) origin[k] = (axis.m[k][0] * minx + axis.m[k][1] * miny) + axis.m[k][2] * cz;
+    l[0] = maxx - minx; if (l[0] < 0) l[0] = 0;
+    l[1] = maxy - miny; if (l[1] < 0) l[1] = 0;
+  }
+
+  void fit(const unsigned* idx, int n, Node& nd) const {
+    double M[3][3], s[3], E[3][3];
+    covariance(idx, n, M);
+    jacobi(M, s, E);
+    axis_from_eigen(E, s, nd.axis);
+    extent_and_center(idx, n, nd.axis, nd.obb_To, nd.obb_ext);
+    rss_fit(idx, n, nd.axis, nd.rss_To, nd.rss_l, nd.rss_r);
+  }
+
+  // split rule — include/fcl/geometry/bvh/detail/BV_splitter-inl.h:422-451 (OBBRSS
+  // specialisations), :540-547 (split vector = obb.axis.col(0)), :550-555,
+  // :558-599 (mean), :603-657 (median); apply(): :492-500.
+  double split_value(const Node& nd, const unsigned* idx, int n, const Vec3& sv) const {
+    if (split == SPLIT_BV_CENTER) return nd.obb_To[0];
+    if (split == SPLIT_MEAN) {
+      double c[3] = {0.0, 0.0, 0.0};
+      for (int i = 0; i < n; ++i) {
+        const Tri& t = m.tris[idx[i]];
+        const Vec3& p1 = m.verts[t.v[0]];
+        const Vec3& p2 = m.verts[t.v[1]];
+        const Vec3& p3 = m.verts[t.v[2]];
+        c[0] += (p1[0] + p2[0] + p3[0]);
+        c[1] += (p1[1] + p2[1] + p3[1]);
+        c[2] += (p1[2] + p2[2] + p3[2]);
+      }
+      return (c[0] * sv[0] + c[1] * sv[1] + c[2] * sv[2]) / (3 * n);
+    }
+    std::vector<double> proj(n);
+    for (int i = 0; i < n; ++i) {
+      const Tri& t = m.tris[idx[i]];
+      const Vec3& p1 = m.verts[t.v[0]];
+      const Vec3& p2 = m.verts[t.v[1]];
+      const Vec3& p3 = m.verts[t.v[2]];
+      Vec3 c3{{p1[0] + p2[0] + p3[0], p1[1] + p2[1] + p3[1], p1[2] + p2[2] + p3[2]}};
+      proj[i] = dot(c3, sv) / 3;
+    }
+    std::sort(proj.begin(), proj.end());
+    if (n % 2 == 1) return proj[(n - 1) / 2];
+    return (proj[n / 2] + proj[n / 2 - 1]) / 2;
+  }
+
+  // recursiveBuildTree — include/fcl/geometry/bvh/BVH_model-inl.h:868-938
+  void recurse(int bv_id, int first, int n) {
+    unsigned* cur = prim.data() + first;
+    Node nd;
+    fit(cur, n, nd);
+    Vec3 sv = col(nd.axis, 0);
+    double sval = split_value(nd, cur, n, sv);
+    nd.first_primitive = first;
+    nd.num_primitives = n;
+    if (n == 1) {
+      nd.first_child = -((int)cur[0] + 1);
+      m.nodes[bv_id] = nd;
+      return;
+    }
+    nd.first_child = num_bvs;
+    num_bvs += 2;
+    m.nodes[bv_id] = nd;
+
+    int c1 = 0;
+    for (int i = 0; i < n; ++i) {
+      const Tri& t = m.tris[cur[i]];
+      const Vec3& p1 = m.verts[t.v[0]];
+      const Vec3& p2 = m.verts[t.v[1]];
+      const Vec3& p3 = m.verts[t.v[2]];
+      Vec3 p{{((p1[0] + p2[0]) + p3[0]) / 3.0, ((p1[1] + p2[1]) + p3[1]) / 3.0, ((p1[2] + p2[2]) + p3[2]) / 3.0}};
+      if (dot(sv, p) > sval) {
+        // right side: stays
+      } else {
+        std::swap(cur[i], cur[c1]);
+        c1++;
+      }
+    }
+    if ((c1 == 0) || (c1 == n)) c1 = n / 2;
+    recurse(nd.first_child, first, c1);
+    recurse(nd.first_child + 1, first + c1, n - c1);
+  }
+};
+
+}  // namespace
+
+// beginModel/addSubModel/endModel/buildTree — BVH_model-inl.h:207-253,383-517,833-864
+void build_model(Model& m, const std::vector<Vec3>& pts, const std::vector<Tri>& tris, SplitMethod split) {
+  m.verts = pts;
+  m.tris = tris;
+  const int nt = (int)tris.size();
+  m.nodes.assign(nt > 0 ? 2 * nt - 1 : 0, Node{});
+  if (nt == 0) return;
+  Builder b{m, split, {}, 1};
+  b.prim.resize(nt);
+  for (int i = 0; i < nt; ++i) b.prim[i] = i;
+  b.recurse(0, 0, nt);
+}
+
+// -----------------------------------------------------------------------------
+// Collision traversal
+// -----------------------------------------------------------------------------
+namespace {
+
+inline double node_size(const Node& n) {  // OBB::size() = extent.squaredNorm(), OBB-inl.h:206-209
+  return sqnorm(n.obb_ext);
+}
+
+// firstOverSecond — bvh_collision_traversal_node-inl.h:78-90 (same in distance: bvh_distance_…:78-90)
+inline bool first_over_second(const Node& n1, const Node& n2) {
+  bool l1 = n1.first_child < 0, l2 = n2.first_child < 0;
+  return l2 || (!l1 && (node_size(n1) > node_size(n2)));
+}
+
+struct CollideCtx {
+  const Model& m1;
+  const Model& m2;
+  Pose tf1;
+  Mat3 R;  // relative rotation  R1^T R2
+  Vec3 T;  // relative translation R1^T (t2 - t1)
+  size_t max_contacts;
+  bool enable_contact;
+  std::vector<Contact>& out;
+  long long n_bv = 0, n_leaf = 0;
+
+  bool can_stop() const {  // collision_request-inl.h:77-82 (enable_cost == false)
+    return !out.empty() && max_contacts <= out.size();
+  }
+
+  // meshCollisionOrientedNodeLeafTesting — mesh_collision_traversal_node-inl.h:527-620
+  void leaf(int b1, int b2) {
+    n_leaf++;
+    int id1 = -(m1.nodes[b1].first_child + 1);
+    int id2 = -(m2.nodes[b2].first_child + 1);
+    const Tri& t1 = m1.tris[id1];
+    const Tri& t2 = m2.tris[id2];
+    Vec3 P[3] = {m1.verts[t1.v[0]], m1.verts[t1.v[1]], m1.verts[t1.v[2]]};
+    Vec3 Q[3] = {m2.verts[t2.v[0]], m2.verts[t2.v[1]], m2.verts[t2.v[2]]};
+    if (!enable_contact) {
+      if (tri_intersect(P, Q, R, T, nullptr, nullptr, nullptr, nullptr)) {
+        if (out.size() < max_contacts) {
+          Contact c{};
+          c.b1 = id1;
+          c.b2 = id2;
+          out.push_back(c);
+        }
+      }
+    } else {
+      double penetration;
+      Vec3 normal;
+      unsigned n_contacts;
+      Vec3 contacts[2];
+      if (tri_intersect(P, Q, R, T, contacts, &n_contacts, &penetration, &normal)) {
+        if (max_contacts < out.size() + n_contacts)
+          n_contacts = (max_contacts > out.size()) ? (unsigned)(max_contacts - out.size()) : 0;
+        for (unsigned i = 0; i < n_contacts; ++i) {
+          Contact c;
+          c.b1 = id1;
+          c.b2 = id2;
+          c.pos = add(mul(tf1.R, contacts[i]), tf1.t);  // tf1 * p
+          c.normal = mul(tf1.R, normal);                // tf1.linear() * n
+          c.depth = penetration;
+          out.push_back(c);
+        }
+      }
+    }
+  }
+
+  bool bv_disjoint(int b1, int b2) {  // MeshCollisionTraversalNodeOBBRSS::BVTesting, :495-500
+    n_bv++;
+    return !obb_overlap(R, T, m1.nodes[b1], m2.nodes[b2]);
+  }
+
+  // collisionRecurse — traversal/traversal_recurse-inl.h:84-130 (front_list == nullptr)
+  void recurse(int b1, int b2) {
+    const Node& n1 = m1.nodes[b1];
+    const Node& n2 = m2.nodes[b2];
+    bool l1 = n1.first_child < 0, l2 = n2.first_child < 0;
+    if (l1 && l2) {
+      if (bv_disjoint(b1, b2)) return;
+      leaf(b1, b2);
+      return;
+    }
+    if (bv_disjoint(b1, b2)) return;
+    if (first_over_second(n1, n2)) {
+      int c1 = n1.first_child, c2 = n1.first_child + 1;
+      recurse(c1, b2);
+      if (can_stop()) return;
+      recurse(c2, b2);
+    } else {
+      int c1 = n2.first_child, c2 = n2.first_child + 1;
+      recurse(b1, c1);
+      if (can_stop()) return;
+      recurse(b1, c2);
+    }
+  }
+};
+
+}  // namespace
+
+// fcl::collide → BVHCollide → orientedMeshCollide — collision-inl.h:95-150,
+// detail/collision_func_matrix-inl.h:571-590; setup: mesh_collision_traversal_node-inl.h:716-745
+// and relativeTransform, math/geometry-inl.h:681-682.
+size_t collide(const Model& m1, const Pose& tf1, const Model& m2, const Pose& tf2,
+               size_t num_max_contacts, bool enable_contact, std::vector<Contact>& out,
+               CollideStats* stats) {
+  if (num_max_contacts == 0) return 0;                              // collision-inl.h:111-115
+  if (!out.empty() && num_max_contacts <= out.size()) return out.size();  // isSatisfied on entry
+  if (m1.nodes.empty() || m2.nodes.empty()) return out.size();
+  CollideCtx ctx{m1, m2, tf1, mulTN(tf1.R, tf2.R), mulTv(tf1.R, sub(tf2.t, tf1.t)),
+                 num_max_contacts, enable_contact, out};
+  ctx.recurse(0, 0);
+  if (stats) {
+    stats->n_bv += ctx.n_bv;
+    stats->n_leaf += ctx.n_leaf;
+  }
+  return out.size();
+}
+
+void brute_collide_pairs(const Model& m1, const Pose& tf1, const Model& m2, const Pose& tf2,
+                         std::vector<std::pair<int, int>>& pairs) {
+  Mat3 R = mulTN(tf1.R, tf2.R);
+  Vec3 T = mulTv(tf1.R, sub(tf2.t, tf1.t));
+  for (int i = 0; i < (int)m1.tris.size(); ++i) {
+    const Tri& t1 = m1.tris[i];
+    Vec3 P[3] = {m1.verts[t1.v[0]], m1.verts[t1.v[1]], m1.verts[t1.v[2]]};
+    for (int j = 0; j < (int)m2.tris.size(); ++j) {
+      const Tri& t2 = m2.tris[j];
+      Vec3 Q[3] = {m2.verts[t2.v[0]], m2.verts[t2.v[1]], m2.verts[t2.v[2]]};
+      if (tri_intersect(P, Q, R, T, nullptr, nullptr, nullptr, nullptr)) pairs.emplace_back(i, j);
+    }
+  }
+}
+
+// -----------------------------------------------------------------------------
+// Distance traversal
+// -----------------------------------------------------------------------------
+namespace {
+
+struct DistCtx {
+  const Model& m1;
+  const Model& m2;
+  Mat3 R;  // tf = tf1^-1 * tf2  (mesh_distance_traversal_node-inl.h:630)
+  Vec3 T;
+  bool nearest;
+  double min_distance = std::numeric_limits<double>::max();  // distance_result.h:94
+  Vec3 p1{{0, 0, 0}}, p2{{0, 0, 0}};
+  int rb1 = -1, rb2 = -1;
+  long long n_bv = 0, n_leaf = 0;
+
+  void update(double d, int id1, int id2, const Vec3& P1, const Vec3& P2) {  // distance_result-inl.h:66-103
+    if (min_distance > d) {
+      min_distance = d;
+      rb1 = id1;
+      rb2 = id2;
+      if (nearest) { p1 = P1; p2 = P2; }
+    }
+  }
+
+  // triDistance(S1,S2,S3,T1,T2,T3,tf,P,Q) — triangle_distance-inl.h:453-462; tf*p = R p + T
+  void tri_pair(int id1, int id2) {
+    const Tri& t1 = m1.tris[id1];
+    const Tri& t2 = m2.tris[id2];
+    Vec3 S[3] = {m1.verts[t1.v[0]], m1.verts[t1.v[1]], m1.verts[t1.v[2]]};
+    Vec3 Tt[3];
+    for (int k = 0; k < 3; ++k) Tt[k] = add(mul(R, m2.verts[t2.v[k]]), T);
+    Vec3 P1, P2;
+    double d = tri_distance(S, Tt, P1, P2);
+    update(d, id1, id2, P1, P2);
+  }
+
+  void leaf(int b1, int b2) {  // meshDistanceOrientedNodeLeafTesting, :453-499
+    n_leaf++;
+    tri_pair(-(m1.nodes[b1].first_child + 1), -(m2.nodes[b2].first_child + 1));
+  }
+
+  double bv(int b1, int b2) {  // mesh_distance_traversal_node.h:188-193
+    n_bv++;
+    return rss_distance(R, T, m1.nodes[b1], m2.nodes[b2]);
+  }
+
+  // MeshDistanceTraversalNode::canStop with rel_err = abs_err = 0 (latched from a
+  // default request in the constructor, mesh_distance_traversal_node-inl.h:96-105,148-153)
+  bool can_stop(double c) const { return (c >= min_distance - 0.0) && (c * (1 + 0.0) >= min_distance); }
+
+  // distanceRecurse — traversal_recurse-inl.h:259-316
+  void recurse(int b1, int b2) {
+    const Node& n1 = m1.nodes[b1];
+    const Node& n2 = m2.nodes[b2];
+    bool l1 = n1.first_child < 0, l2 = n2.first_child < 0;
+    if (l1 && l2) {
+      leaf(b1, b2);
+      return;
+    }
+    int a1, a2, c1, c2;
+    if (first_over_second(n1, n2)) {
+      a1 = n1.first_child; a2 = b2; c1 = n1.first_child + 1; c2 = b2;
+    } else {
+      a1 = b1; a2 = n2.first_child; c1 = b1; c2 = n2.first_child + 1;
+    }
+    double d1 = bv(a1, a2);
+    double d2 = bv(c1, c2);
+    if (d2 < d1) {
+      if (!can_stop(d2)) recurse(c1, c2);
+      if (!can_stop(d1)) recurse(a1, a2);
+    } else {
+      if (!can_stop(d1)) recurse(a1, a2);
+      if (!can_stop(d2)) recurse(c1, c2);
+    }
+  }
+
+  // distanceQueueRecurse — traversal_recurse-inl.h:321-460
+  struct BVT {
+    double d;
+    int b1, b2;
+  };
+  struct Cmp {
+    bool operator()(const BVT& l, const BVT& r) const { return l.d > r.d; }
+  };
+  void queue_recurse(int b1, int b2, unsigned qsize) {
+    std::priority_queue<BVT, std::vector<BVT>, Cmp> pq;
+    BVT cur{0, b1, b2};
+    while (true) {
+      const Node& n1 = m1.nodes[cur.b1];
+      const Node& n2 = m2.nodes[cur.b2];
+      bool l1 = n1.first_child < 0, l2 = n2.first_child < 0;
+      if (l1 && l2) {
+        leaf(cur.b1, cur.b2);
+      } else if (pq.size() + 1 >= qsize) {
+        queue_recurse(cur.b1, cur.b2, qsize);
+      } else {
+        BVT x, y;
+        if (first_over_second(n1, n2)) {
+          x.b1 = n1.first_child; x.b2 = cur.b2;
+          x.d = bv(x.b1, x.b2);
+          y.b1 = n1.first_child + 1; y.b2 = cur.b2;
+          y.d = bv(y.b1, y.b2);
+        } else {
+          x.b1 = cur.b1; x.b2 = n2.first_child;
+          x.d = bv(x.b1, x.b2);
+          y.b1 = cur.b1; y.b2 = n2.first_child + 1;
+          y.d = bv(y.b1, y.b2);
+        }
+        pq.push(x);
+        pq.push(y);
+      }
+      if (pq.empty()) break;
+      cur = pq.top();
+      pq.pop();
+      if (can_stop(cur.d)) break;
+    }
+  }
+};
+
+inline void relative_for_distance(const Pose& tf1, const Pose& tf2, Mat3& R, Vec3& T) {
+  // tf1.inverse(Isometry) * tf2:  linear = R1^T R2,  translation = R1^T t2 + (-(R1^T t1))
+  R = mulTN(tf1.R, tf2.R);
+  Vec3 inv_t = mulTv(tf1.R, tf1.t);
+  inv_t = Vec3{{-inv_t[0], -inv_t[1], -inv_t[2]}};
+  T = add(mulTv(tf1.R, tf2.t), inv_t);
+}
+
+}  // namespace
+
+// fcl::distance → BVHDistance → orientedMeshDistance — distance-inl.h:92-190,
+// detail/distance_func_matrix-inl.h:386-403; driver collision_node-inl.h:137-146.
+double distance(const Model& m1, const Pose& tf1, const Model& m2, const Pose& tf2,
+                bool enable_nearest_points, DistanceOut& out, int qsize, CollideStats* stats) {
+  DistCtx ctx{m1, m2, Mat3{}, Vec3{}, enable_nearest_points};
+  relative_for_distance(tf1, tf2, ctx.R, ctx.T);
+  // preprocess: seed with triangle 0 / triangle 0 (:352-366 → :546-586)
+  ctx.tri_pair(0, 0);
+  if (qsize <= 2) ctx.recurse(0, 0);
+  else ctx.queue_recurse(0, 0, (unsigned)qsize);
+  // postprocess: both points are in model1's frame → world with tf1 (:590-603)
+  out.min_distance = ctx.min_distance;
+  out.b1 = ctx.rb1;
+  out.b2 = ctx.rb2;
+  if (enable_nearest_points) {
+    out.p1 = add(mul(tf1.R, ctx.p1), tf1.t);
+    out.p2 = add(mul(tf1.R, ctx.p2), tf1.t);
+  } else {
+    out.p1 = out.p2 = Vec3{{0, 0, 0}};
+  }
+  if (stats) {
+    stats->n_bv += ctx.n_bv;
+    stats->n_leaf += ctx.n_leaf;
+  }
+  return out.min_distance;
+}
+
+double brute_distance(const Model& m1, const Pose& tf1, const Model& m2, const Pose& tf2, DistanceOut& out) {
+  DistCtx ctx{m1, m2, Mat3{}, Vec3{}, true};
+  relative_for_distance(tf1, tf2, ctx.R, ctx.T);
+  for (int i = 0; i < (int)m1.tris.size(); ++i)
+    for (int j = 0; j < (int)m2.tris.size(); ++j) ctx.tri_pair(i, j);
+  out.min_distance = ctx.min_distance;
+  out.b1 = ctx.rb1;
+  out.b2 = ctx.rb2;
+  out.p1 = add(mul(tf1.R, ctx.p1), tf1.t);
+  out.p2 = add(mul(tf1.R, ctx.p2), tf1.t);
+  return out.min_distance;
+}
+
+}  // namespace oracle

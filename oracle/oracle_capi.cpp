@@ -1,0 +1,315 @@
+// oracle_capi.cpp — CPU ORACLE (test infrastructure, NOT product code).
+// extern "C" surface over the oracle so that tests/, smoke() and bench.py's
+// cpu_baseline leg can drive it through ctypes.  Nothing under fcl_b200/ links
+// or loads this library.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstring>
+#include <thread>
+
+#include "fcl_oracle.hpp"
+
+using namespace oracle;
+
+namespace {
+
+// pose record at the boundary: 12 doubles, R row-major (9) then t (3)
+inline Pose pose_from(const double* p) {
+  Pose q;
+  if (!p) {
+    q.R = Mat3{{{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}};
+    q.t = Vec3{{0, 0, 0}};
+    return q;
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) q.R.m[i][j] = p[3 * i + j];
+  q.t = Vec3{{p[9], p[10], p[11]}};
+  return q;
+}
+
+struct OrcContact {  // 64 bytes, same layout as fclgpu_contact
+  int32_t b1, b2;
+  double normal[3], pos[3], depth;
+};
+
+struct CollideBatch {
+  std::vector<int32_t> counts;
+  std::vector<std::vector<Contact>> per_pose;
+  std::vector<long long> n_bv, n_leaf;
+  double seconds = 0;
+};
+
+template <class F>
+void parallel_for(long long n, int nthreads, F f) {
+  if (nthreads <= 1 || n < 2) {
+    for (long long i = 0; i < n; ++i) f(i);
+    return;
+  }
+  // dynamic chunks: per-pose cost varies by >100x
+  std::atomic<long long> next{0};
+  const long long chunk = std::max<long long>(1, std::min<long long>(256, n / (nthreads * 8)));
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; ++t)
+    th.emplace_back([&] {
+      while (true) {
+        long long s = next.fetch_add(chunk);
+        if (s >= n) break;
+        long long e = std::min(n, s + chunk);
+        for (long long i = s; i < e; ++i) f(i);
+      }
+    });
+  for (auto& x : th) x.join();
+}
+
+}  // namespace
+
+extern "C" {
+
+void* orc_model_from_obj(const char* path, int split) {
+  std::vector<Vec3> pts;
+  std::vector<Tri> tris;
+  if (!load_obj(path, pts, tris)) return nullptr;
+  Model* m = new Model;
+  build_model(*m, pts, tris, (SplitMethod)split);
+  return m;
+}
+
+void* orc_model_from_arrays(const double* verts, int nv, const int32_t* tris, int nt, int split) {
+  std::vector<Vec3> pts(nv);
+  std::vector<Tri> ts(nt);
+  for (int i = 0; i < nv; ++i) pts[i] = Vec3{{verts[3 * i], verts[3 * i + 1], verts[3 * i + 2]}};
+  for (int i = 0; i < nt; ++i) ts[i] = Tri{{tris[3 * i], tris[3 * i + 1], tris[3 * i + 2]}};
+  Model* m = new Model;
+  build_model(*m, pts, ts, (SplitMethod)split);
+  return m;
+}
+
+void orc_model_free(void* h) { delete (Model*)h; }
+
+void orc_model_counts(void* h, int* nv, int* nt, int* nn) {
+  Model* m = (Model*)h;
+  *nv = (int)m->verts.size();
+  *nt = (int)m->tris.size();
+  *nn = (int)m->nodes.size();
+}
+
+// axis is written row-major 9 per node (axis[3*r+c]; column c = c-th box axis)
+void orc_model_get(void* h, double* verts, int32_t* tris, int32_t* first_child, double* axis9,
+                   double* obb_To, double* obb_ext, double* rss_To, double* rss_l, double* rss_r) {
+  Model* m = (Model*)h;
+  if (verts)
+    for (size_t i = 0; i < m->verts.size(); ++i)
+      for (int k = 0; k < 3; ++k) verts[3 * i + k] = m->verts[i][k];
+  if (tris)
+    for (size_t i = 0; i < m->tris.size(); ++i)
+      for (int k = 0; k < 3; ++k) tris[3 * i + k] = m->tris[i].v[k];
+  for (size_t i = 0; i < m->nodes.size(); ++i) {
+    const Node& n = m->nodes[i];
+    if (first_child) first_child[i] = n.first_child;
+    if (axis9)
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) axis9[9 * i + 3 * r + c] = n.axis.m[r][c];
+    for (int k = 0; k < 3; ++k) {
+      if (obb_To) obb_To[3 * i + k] = n.obb_To[k];
+      if (obb_ext) obb_ext[3 * i + k] = n.obb_ext[k];
+      if (rss_To) rss_To[3 * i + k] = n.rss_To[k];
+    }
+    if (rss_l) { rss_l[2 * i] = n.rss_l[0]; rss_l[2 * i + 1] = n.rss_l[1]; }
+    if (rss_r) rss_r[i] = n.rss_r;
+  }
+}
+
+// ---- batched queries (tf arrays: n x 12 doubles, or NULL = identity for all) ----
+void* orc_collide_batch(void* h1, void* h2, long long n, const double* tf1, const double* tf2,
+                        long long num_max_contacts, int enable_contact, int nthreads) {
+  Model* m1 = (Model*)h1;
+  Model* m2 = (Model*)h2;
+  CollideBatch* b = new CollideBatch;
+  b->counts.assign(n, 0);
+  b->per_pose.resize(n);
+  b->n_bv.assign(n, 0);
+  b->n_leaf.assign(n, 0);
+  auto t0 = std::chrono::steady_clock::now();
+  parallel_for(n, nthreads, [&](long long i) {
+    Pose a = pose_from(tf1 ? tf1 + 12 * i : nullptr);
+    Pose c = pose_from(tf2 ? tf2 + 12 * i : nullptr);
+    CollideStats st;
+    collide(*m1, a, *m2, c, (size_t)num_max_contacts, enable_contact != 0, b->per_pose[i], &st);
+    b->counts[i] = (int32_t)b->per_pose[i].size();
+    b->n_bv[i] = st.n_bv;
+    b->n_leaf[i] = st.n_leaf;
+  });
+  b->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return b;
+}
+
+double orc_collide_seconds(void* hb) { return ((CollideBatch*)hb)->seconds; }
+
+long long orc_collide_total(void* hb) {
+  CollideBatch* b = (CollideBatch*)hb;
+  long long t = 0;
+  for (auto c : b->counts) t += c;
+  return t;
+}
+
+// counts[n], contacts[total] (DFS order per pose, poses concatenated), n_bv[n], n_leaf[n]
+void orc_collide_copy(void* hb, int32_t* counts, void* contacts, long long* n_bv, long long* n_leaf) {
+  CollideBatch* b = (CollideBatch*)hb;
+  OrcContact* out = (OrcContact*)contacts;
+  size_t k = 0;
+  for (size_t i = 0; i < b->counts.size(); ++i) {
+    if (counts) counts[i] = b->counts[i];
+    if (n_bv) n_bv[i] = b->n_bv[i];
+    if (n_leaf) n_leaf[i] = b->n_leaf[i];
+    if (out)
+      for (const Contact& c : b->per_pose[i]) {
+        OrcContact& o = out[k++];
+        o.b1 = c.b1;
+        o.b2 = c.b2;
+        for (int d = 0; d < 3; ++d) {
+          o.normal[d] = c.normal[d];
+          o.pos[d] = c.pos[d];
+        }
+        o.depth = c.depth;
+      }
+  }
+}
+
+void orc_collide_free(void* hb) { delete (CollideBatch*)hb; }
+
+// returns wall seconds of the batch
+double orc_distance_batch(void* h1, void* h2, long long n, const double* tf1, const double* tf2,
+                          int enable_nearest_points, int qsize, int nthreads, double* dist,
+                          double* p1, double* p2, int32_t* b1, int32_t* b2, long long* n_bv,
+                          long long* n_leaf) {
+  Model* m1 = (Model*)h1;
+  Model* m2 = (Model*)h2;
+  auto t0 = std::chrono::steady_clock::now();
+  parallel_for(n, nthreads, [&](long long i) {
+    Pose a = pose_from(tf1 ? tf1 + 12 * i : nullptr);
+    Pose c = pose_from(tf2 ? tf2 + 12 * i : nullptr);
+    CollideStats st;
+    DistanceOut o;
+    distance(*m1, a, *m2, c, enable_nearest_points != 0, o, qsize, &st);
+    if (dist) dist[i] = o.min_distance;
+    for (int k = 0; k < 3; ++k) {
+      if (p1) p1[3 * i + k] = o.p1[k];
+      if (p2) p2[3 * i + k] = o.p2[k];
+    }
+    if (b1) b1[i] = o.b1;
+    if (b2) b2[i] = o.b2;
+    if (n_bv) n_bv[i] = st.n_bv;
+    if (n_leaf) n_leaf[i] = st.n_leaf;
+  });
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// ---- brute force --------------------------------------------------------------
+long long orc_brute_collide(void* h1, void* h2, const double* tf1, const double* tf2, int32_t* pairs,
+                            long long cap_pairs) {
+  std::vector<std::pair<int, int>> v;
+  brute_collide_pairs(*(Model*)h1, pose_from(tf1), *(Model*)h2, pose_from(tf2), v);
+  for (long long i = 0; i < (long long)v.size() && i < cap_pairs; ++i) {
+    pairs[2 * i] = v[i].first;
+    pairs[2 * i + 1] = v[i].second;
+  }
+  return (long long)v.size();
+}
+
+double orc_brute_distance(void* h1, void* h2, const double* tf1, const double* tf2, double* p1,
+                          double* p2, int32_t* b12) {
+  DistanceOut o;
+  brute_distance(*(Model*)h1, pose_from(tf1), *(Model*)h2, pose_from(tf2), o);
+  for (int k = 0; k < 3; ++k) {
+    if (p1) p1[k] = o.p1[k];
+    if (p2) p2[k] = o.p2[k];
+  }
+  if (b12) { b12[0] = o.b1; b12[1] = o.b2; }
+  return o.min_distance;
+}
+
+// ---- unit-level kernels (row-major 3x3) ---------------------------------------
+static Mat3 mat_from(const double* r) {
+  Mat3 M;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) M.m[i][j] = r[3 * i + j];
+  return M;
+}
+static Vec3 vec_from(const double* v) { return Vec3{{v[0], v[1], v[2]}}; }
+
+int orc_obb_disjoint(const double* B9, const double* T3, const double* a3, const double* b3) {
+  return obb_disjoint(mat_from(B9), vec_from(T3), vec_from(a3), vec_from(b3)) ? 1 : 0;
+}
+
+static Node node_from(const double* axis9, const double* To, const double* ext_or_l, double r, bool rss) {
+  Node n{};
+  n.axis = mat_from(axis9);
+  if (rss) {
+    n.rss_To = vec_from(To);
+    n.rss_l[0] = ext_or_l[0];
+    n.rss_l[1] = ext_or_l[1];
+    n.rss_r = r;
+  } else {
+    n.obb_To = vec_from(To);
+    n.obb_ext = vec_from(ext_or_l);
+  }
+  return n;
+}
+
+int orc_obb_overlap(const double* R0, const double* T0, const double* axis1, const double* To1,
+                    const double* ext1, const double* axis2, const double* To2, const double* ext2) {
+  Node n1 = node_from(axis1, To1, ext1, 0, false), n2 = node_from(axis2, To2, ext2, 0, false);
+  return obb_overlap(mat_from(R0), vec_from(T0), n1, n2) ? 1 : 0;
+}
+
+double orc_rect_distance(const double* R9, const double* T3, const double* a2, const double* b2) {
+  return rect_distance(mat_from(R9), vec_from(T3), a2, b2);
+}
+
+double orc_rss_distance(const double* R0, const double* T0, const double* axis1, const double* To1,
+                        const double* l1, double r1, const double* axis2, const double* To2,
+                        const double* l2, double r2) {
+  Node n1 = node_from(axis1, To1, l1, r1, true), n2 = node_from(axis2, To2, l2, r2, true);
+  return rss_distance(mat_from(R0), vec_from(T0), n1, n2);
+}
+
+// P9/Q9: three vertices each; returns hit; out: n_contacts, contacts(6), depth, normal(3)
+int orc_tri_intersect(const double* P9, const double* Q9, const double* R9, const double* T3,
+                      int want_contacts, uint32_t* n_contacts, double* contacts6, double* depth,
+                      double* normal3) {
+  Vec3 P[3] = {vec_from(P9), vec_from(P9 + 3), vec_from(P9 + 6)};
+  Vec3 Q[3] = {vec_from(Q9), vec_from(Q9 + 3), vec_from(Q9 + 6)};
+  if (!want_contacts)
+    return tri_intersect(P, Q, mat_from(R9), vec_from(T3), nullptr, nullptr, nullptr, nullptr) ? 1 : 0;
+  Vec3 c[2] = {Vec3{{0, 0, 0}}, Vec3{{0, 0, 0}}}, nrm{{0, 0, 0}};
+  unsigned nc = 0;
+  double d = 0;
+  bool hit = tri_intersect(P, Q, mat_from(R9), vec_from(T3), c, &nc, &d, &nrm);
+  if (hit) {
+    *n_contacts = nc;
+    *depth = d;
+    for (int k = 0; k < 3; ++k) {
+      contacts6[k] = c[0][k];
+      contacts6[3 + k] = c[1][k];
+      normal3[k] = nrm[k];
+    }
+  }
+  return hit ? 1 : 0;
+}
+
+double orc_tri_distance(const double* S9, const double* T9, double* P3, double* Q3) {
+  Vec3 S[3] = {vec_from(S9), vec_from(S9 + 3), vec_from(S9 + 6)};
+  Vec3 T[3] = {vec_from(T9), vec_from(T9 + 3), vec_from(T9 + 6)};
+  Vec3 P{{0, 0, 0}}, Q{{0, 0, 0}};
+  double d = tri_distance(S, T, P, Q);
+  for (int k = 0; k < 3; ++k) {
+    P3[k] = P[k];
+    Q3[k] = Q[k];
+  }
+  return d;
+}
+
+int orc_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
+
+}  // extern "C"

@@ -1,0 +1,254 @@
+"""ctypes front-end of the CPU ORACLE (test infrastructure, NOT product code).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.  Nothing under fcl_b200/ does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+
+SPLIT_MEAN, SPLIT_MEDIAN, SPLIT_BV_CENTER = 0, 1, 2
+
+CONTACT_DTYPE = np.dtype(
+    [("b1", "<i4"), ("b2", "<i4"), ("normal", "<f8", (3,)), ("pos", "<f8", (3,)), ("depth", "<f8")]
+)
+assert CONTACT_DTYPE.itemsize == 64
+
+
+def build(force=False):
+    """Compile the oracle with its Makefile (g++ -O2 -ffp-contract=off)."""
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".hpp"))]
+    stale = (not os.path.exists(_LIB_PATH)) or any(
+        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs
+    )
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = C.CDLL(_LIB_PATH)
+        vp, dp, ip, lp = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_longlong)
+        L.orc_model_from_obj.restype = vp
+        L.orc_model_from_obj.argtypes = [C.c_char_p, C.c_int]
+        L.orc_model_from_arrays.restype = vp
+        L.orc_model_from_arrays.argtypes = [dp, C.c_int, ip, C.c_int, C.c_int]
+        L.orc_model_free.argtypes = [vp]
+        L.orc_model_counts.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_model_get.argtypes = [vp, dp, ip, ip, dp, dp, dp, dp, dp, dp]
+        L.orc_collide_batch.restype = vp
+        L.orc_collide_batch.argtypes = [vp, vp, C.c_longlong, dp, dp, C.c_longlong, C.c_int, C.c_int]
+        L.orc_collide_seconds.restype = C.c_double
+        L.orc_collide_seconds.argtypes = [vp]
+        L.orc_collide_total.restype = C.c_longlong
+        L.orc_collide_total.argtypes = [vp]
+        L.orc_collide_copy.argtypes = [vp, ip, vp, lp, lp]
+        L.orc_collide_free.argtypes = [vp]
+        L.orc_distance_batch.restype = C.c_double
+        L.orc_distance_batch.argtypes = [vp, vp, C.c_longlong, dp, dp, C.c_int, C.c_int, C.c_int,
+                                         dp, dp, dp, ip, ip, lp, lp]
+        L.orc_brute_collide.restype = C.c_longlong
+        L.orc_brute_collide.argtypes = [vp, vp, dp, dp, ip, C.c_longlong]
+        L.orc_brute_distance.restype = C.c_double
+        L.orc_brute_distance.argtypes = [vp, vp, dp, dp, dp, dp, ip]
+        L.orc_obb_disjoint.restype = C.c_int
+        L.orc_obb_disjoint.argtypes = [dp, dp, dp, dp]
+        L.orc_obb_overlap.restype = C.c_int
+        L.orc_obb_overlap.argtypes = [dp] * 8
+        L.orc_rect_distance.restype = C.c_double
+        L.orc_rect_distance.argtypes = [dp, dp, dp, dp]
+        L.orc_rss_distance.restype = C.c_double
+        L.orc_rss_distance.argtypes = [dp, dp, dp, dp, dp, C.c_double, dp, dp, dp, C.c_double]
+        L.orc_tri_intersect.restype = C.c_int
+        L.orc_tri_intersect.argtypes = [dp, dp, dp, dp, C.c_int, C.POINTER(C.c_uint32), dp, dp, dp]
+        L.orc_tri_distance.restype = C.c_double
+        L.orc_tri_distance.argtypes = [dp, dp, dp, dp]
+        L.orc_hardware_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _d(a):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _lp(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_longlong))
+
+
+def hardware_threads():
+    return int(lib().orc_hardware_threads())
+
+
+class Model:
+    """Oracle BVHModel<OBBRSS<double>>."""
+
+    def __init__(self, verts, tris, split=SPLIT_MEAN):
+        self.verts = np.ascontiguousarray(verts, dtype=np.float64).reshape(-1, 3)
+        self.tris = np.ascontiguousarray(tris, dtype=np.int32).reshape(-1, 3)
+        self.h = lib().orc_model_from_arrays(_dp(self.verts), len(self.verts), _ip(self.tris), len(self.tris), split)
+        nv, nt, nn = C.c_int(), C.c_int(), C.c_int()
+        lib().orc_model_counts(self.h, C.byref(nv), C.byref(nt), C.byref(nn))
+        self.num_vertices, self.num_tris, self.num_bvs = nv.value, nt.value, nn.value
+
+    @classmethod
+    def from_npz(cls, path, split=SPLIT_MEAN):
+        z = np.load(path)
+        return cls(z["verts"], z["tris"], split)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib().orc_model_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def arrays(self):
+        """Flattened node tree: dict of numpy arrays (axis row-major 9 per node)."""
+        n = self.num_bvs
+        out = dict(
+            first_child=np.empty(n, np.int32), axis=np.empty((n, 9)), obb_To=np.empty((n, 3)),
+            obb_ext=np.empty((n, 3)), rss_To=np.empty((n, 3)), rss_l=np.empty((n, 2)), rss_r=np.empty(n),
+        )
+        lib().orc_model_get(self.h, None, None, _ip(out["first_child"]), _dp(out["axis"]), _dp(out["obb_To"]),
+                            _dp(out["obb_ext"]), _dp(out["rss_To"]), _dp(out["rss_l"]), _dp(out["rss_r"]))
+        return out
+
+
+def _poses(tf, n=None):
+    if tf is None:
+        return None
+    tf = np.ascontiguousarray(tf, dtype=np.float64).reshape(-1, 12)
+    return tf
+
+
+def collide_batch(m1, m2, tf1, tf2=None, num_max_contacts=1, enable_contact=False, nthreads=1):
+    """Returns dict(counts[n], contacts[total] (CONTACT_DTYPE), offsets[n+1], n_bv[n], n_leaf[n], seconds)."""
+    tf1 = _poses(tf1)
+    tf2 = _poses(tf2)
+    n = len(tf1) if tf1 is not None else len(tf2)
+    L = lib()
+    hb = L.orc_collide_batch(m1.h, m2.h, n, _dp(tf1), _dp(tf2), int(num_max_contacts), int(enable_contact), nthreads)
+    try:
+        total = L.orc_collide_total(hb)
+        counts = np.empty(n, np.int32)
+        contacts = np.zeros(total, CONTACT_DTYPE)
+        n_bv = np.empty(n, np.int64)
+        n_leaf = np.empty(n, np.int64)
+        L.orc_collide_copy(hb, _ip(counts), contacts.ctypes.data_as(C.c_void_p), _lp(n_bv), _lp(n_leaf))
+        secs = L.orc_collide_seconds(hb)
+    finally:
+        L.orc_collide_free(hb)
+    offsets = np.zeros(n + 1, np.int64)
+    np.cumsum(counts, out=offsets[1:])
+    return dict(counts=counts, contacts=contacts, offsets=offsets, n_bv=n_bv, n_leaf=n_leaf, seconds=secs)
+
+
+def distance_batch(m1, m2, tf1, tf2=None, enable_nearest_points=True, qsize=2, nthreads=1):
+    tf1 = _poses(tf1)
+    tf2 = _poses(tf2)
+    n = len(tf1) if tf1 is not None else len(tf2)
+    dist = np.empty(n)
+    p1 = np.empty((n, 3))
+    p2 = np.empty((n, 3))
+    b1 = np.empty(n, np.int32)
+    b2 = np.empty(n, np.int32)
+    n_bv = np.empty(n, np.int64)
+    n_leaf = np.empty(n, np.int64)
+    secs = lib().orc_distance_batch(m1.h, m2.h, n, _dp(tf1), _dp(tf2), int(enable_nearest_points), qsize, nthreads,
+                                    _dp(dist), _dp(p1), _dp(p2), _ip(b1), _ip(b2), _lp(n_bv), _lp(n_leaf))
+    return dict(min_distance=dist, p1=p1, p2=p2, b1=b1, b2=b2, n_bv=n_bv, n_leaf=n_leaf, seconds=secs)
+
+
+def brute_collide(m1, m2, tf1, tf2=None):
+    tf1 = None if tf1 is None else np.ascontiguousarray(tf1, dtype=np.float64).reshape(12)
+    tf2 = None if tf2 is None else np.ascontiguousarray(tf2, dtype=np.float64).reshape(12)
+    cap = 1 << 16
+    while True:
+        pairs = np.empty((cap, 2), np.int32)
+        k = lib().orc_brute_collide(m1.h, m2.h, _dp(tf1), _dp(tf2), _ip(pairs), cap)
+        if k <= cap:
+            return pairs[:k].copy()
+        cap = int(k)
+
+
+def brute_distance(m1, m2, tf1, tf2=None):
+    tf1 = None if tf1 is None else np.ascontiguousarray(tf1, dtype=np.float64).reshape(12)
+    tf2 = None if tf2 is None else np.ascontiguousarray(tf2, dtype=np.float64).reshape(12)
+    p1 = np.empty(3)
+    p2 = np.empty(3)
+    b = np.empty(2, np.int32)
+    d = lib().orc_brute_distance(m1.h, m2.h, _dp(tf1), _dp(tf2), _dp(p1), _dp(p2), _ip(b))
+    return d, p1, p2, b
+
+
+def _c9(a):
+    return np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+
+
+def obb_disjoint(B, T, a, b):
+    B, T, a, b = _c9(B), _c9(T), _c9(a), _c9(b)
+    return bool(lib().orc_obb_disjoint(_dp(B), _dp(T), _dp(a), _dp(b)))
+
+
+def obb_overlap(R0, T0, axis1, To1, ext1, axis2, To2, ext2):
+    args = [_c9(x) for x in (R0, T0, axis1, To1, ext1, axis2, To2, ext2)]
+    return bool(lib().orc_obb_overlap(*[_dp(x) for x in args]))
+
+
+def rect_distance(R, T, a, b):
+    R, T, a, b = _c9(R), _c9(T), _c9(a), _c9(b)
+    return float(lib().orc_rect_distance(_dp(R), _dp(T), _dp(a), _dp(b)))
+
+
+def rss_distance(R0, T0, axis1, To1, l1, r1, axis2, To2, l2, r2):
+    R0, T0, axis1, To1, l1, axis2, To2, l2 = [_c9(x) for x in (R0, T0, axis1, To1, l1, axis2, To2, l2)]
+    return float(lib().orc_rss_distance(_dp(R0), _dp(T0), _dp(axis1), _dp(To1), _dp(l1), float(r1),
+                                        _dp(axis2), _dp(To2), _dp(l2), float(r2)))
+
+
+def tri_intersect(P, Q, R=None, T=None, want_contacts=False):
+    P, Q = _c9(P), _c9(Q)
+    R = _c9(np.eye(3) if R is None else R)
+    T = _c9(np.zeros(3) if T is None else T)
+    nc = C.c_uint32(0)
+    contacts = np.zeros(6)
+    depth = np.zeros(1)
+    normal = np.zeros(3)
+    hit = lib().orc_tri_intersect(_dp(P), _dp(Q), _dp(R), _dp(T), int(want_contacts), C.byref(nc),
+                                  _dp(contacts), _dp(depth), _dp(normal))
+    if not want_contacts:
+        return bool(hit)
+    return bool(hit), int(nc.value), contacts.reshape(2, 3), float(depth[0]), normal
+
+
+def tri_distance(S, T):
+    S, T = _c9(S), _c9(T)
+    P = np.zeros(3)
+    Q = np.zeros(3)
+    d = lib().orc_tri_distance(_dp(S), _dp(T), _dp(P), _dp(Q))
+    return float(d), P, Q
