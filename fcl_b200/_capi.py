@@ -1,0 +1,138 @@
+"""ctypes binding of the C ABI in include/fclgpu.h (fcl_b200/lib/libfclgpu.so).
+
+There is no CPU fallback: if the shared library is missing this module raises at import
+time with the build command, and every compute call fails with FCLGPU_ERR_NO_DEVICE when no
+CUDA device is present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfclgpu.so")
+
+OK = 0
+ERR_BUILD_OUT_OF_SEQUENCE = -2
+ERR_BUILD_EMPTY_MODEL = -3
+ERR_UNSUPPORTED_FUNCTION = -5
+ERR_INCORRECT_DATA = -7
+ERR_INVALID_ARGUMENT = -20
+ERR_NO_DEVICE = -21
+ERR_CUDA = -22
+ERR_CONTACT_OVERFLOW = -23
+ERR_STACK_OVERFLOW = -24
+
+CONTACT_DTYPE = np.dtype(
+    [("b1", "<i4"), ("b2", "<i4"), ("normal", "<f8", (3,)), ("pos", "<f8", (3,)), ("penetration_depth", "<f8")]
+)
+assert CONTACT_DTYPE.itemsize == 64
+
+
+class CollisionRequestC(C.Structure):
+    _fields_ = [("num_max_contacts", C.c_int64), ("enable_contact", C.c_int32), ("enable_cost", C.c_int32)]
+
+
+class DistanceRequestC(C.Structure):
+    _fields_ = [("enable_nearest_points", C.c_int32), ("enable_signed_distance", C.c_int32),
+                ("rel_err", C.c_double), ("abs_err", C.c_double)]
+
+
+class FclGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"fclgpu error {code}: {msg}")
+        self.code = code
+
+
+# every symbol include/fclgpu.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "fclgpu_bvh_build_obbrss", "fclgpu_bvh_destroy", "fclgpu_bvh_num_nodes", "fclgpu_bvh_num_tris", "fclgpu_bvh_get",
+    "fclgpu_model_create_obbrss", "fclgpu_model_from_bvh", "fclgpu_model_destroy", "fclgpu_model_num_nodes",
+    "fclgpu_model_num_tris", "fclgpu_model_device", "fclgpu_collide_batch", "fclgpu_collide_batch_host",
+    "fclgpu_distance_batch", "fclgpu_distance_batch_host", "fclgpu_abi_version", "fclgpu_device_count",
+    "fclgpu_last_error", "fclgpu_pose_from_colmajor4x4", "fclgpu_sync_status", "fclgpu_set_option",
+    "fclgpu_get_option", "fclgpu_launch_count", "fclgpu_microbench",
+]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build the CUDA library first (python -c 'import __graft_entry__ as g; g.build()' "
+            "or make -C fcl_b200/csrc). fcl_b200 has no CPU fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    vp, dp, ip, up = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p  # raw addresses (host or device)
+    L.fclgpu_bvh_build_obbrss.argtypes = [vp, C.c_int32, vp, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+    L.fclgpu_bvh_destroy.argtypes = [vp]
+    L.fclgpu_bvh_destroy.restype = None
+    L.fclgpu_bvh_num_nodes.argtypes = [vp]
+    L.fclgpu_bvh_num_tris.argtypes = [vp]
+    L.fclgpu_bvh_get.argtypes = [vp] * 9
+    L.fclgpu_model_create_obbrss.argtypes = [C.c_int, C.c_int32, vp, vp, vp, vp, vp, vp, vp, C.c_int32, vp,
+                                             C.POINTER(C.c_void_p)]
+    L.fclgpu_model_from_bvh.argtypes = [C.c_int, vp, C.POINTER(C.c_void_p)]
+    L.fclgpu_model_destroy.argtypes = [vp]
+    L.fclgpu_model_num_nodes.argtypes = [vp]
+    L.fclgpu_model_num_tris.argtypes = [vp]
+    L.fclgpu_model_device.argtypes = [vp]
+    L.fclgpu_collide_batch.argtypes = [vp, vp, C.c_int64, dp, dp, C.POINTER(CollisionRequestC), ip, vp, C.c_int64,
+                                       vp, up, up, vp]
+    L.fclgpu_collide_batch_host.argtypes = [vp, vp, C.c_int64, dp, dp, C.POINTER(CollisionRequestC), ip, vp,
+                                            C.c_int64, vp, up, up]
+    L.fclgpu_distance_batch.argtypes = [vp, vp, C.c_int64, dp, dp, C.POINTER(DistanceRequestC), dp, dp, dp, ip, ip,
+                                        up, up, vp]
+    L.fclgpu_distance_batch_host.argtypes = [vp, vp, C.c_int64, dp, dp, C.POINTER(DistanceRequestC), dp, dp, dp, ip,
+                                             ip, up, up]
+    L.fclgpu_last_error.restype = C.c_char_p
+    L.fclgpu_pose_from_colmajor4x4.argtypes = [vp, vp]
+    L.fclgpu_pose_from_colmajor4x4.restype = None
+    L.fclgpu_sync_status.argtypes = [C.c_int, vp]
+    L.fclgpu_set_option.argtypes = [C.c_char_p, C.c_int64]
+    L.fclgpu_get_option.argtypes = [C.c_char_p]
+    L.fclgpu_get_option.restype = C.c_int64
+    L.fclgpu_launch_count.restype = C.c_int64
+    L.fclgpu_microbench.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
+    _lib = L
+    return L
+
+
+def check(code):
+    if code != OK:
+        raise FclGpuError(code, lib().fclgpu_last_error().decode("utf-8", "replace"))
+
+
+def addr(a):
+    """Address of a numpy array (host) or torch tensor (host or device); None -> NULL."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()
+
+
+def set_option(name, value):
+    check(lib().fclgpu_set_option(name.encode(), int(value)))
+
+
+def get_option(name):
+    return int(lib().fclgpu_get_option(name.encode()))
+
+
+def launch_count():
+    return int(lib().fclgpu_launch_count())
+
+
+def device_count():
+    return int(lib().fclgpu_device_count())
+
+
+def microbench(kind, device=0):
+    out = C.c_double(0)
+    check(lib().fclgpu_microbench(device, kind, C.byref(out)))
+    return out.value

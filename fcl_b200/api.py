@@ -1,0 +1,496 @@
+"""Host-side mirror of the reference's interface for the OBBRSS mesh-mesh path.
+
+Names, argument meaning and error behaviour follow the reference
+(/root/reference/include/fcl/...):
+  BVHModel            geometry/bvh/BVH_model.h:62-330 (beginModel/addSubModel/addTriangle/endModel)
+  CollisionRequest    narrowphase/collision_request.h:52-106
+  CollisionResult     narrowphase/collision_result.h:52-93
+  Contact             narrowphase/contact.h:48-91
+  DistanceRequest     narrowphase/distance_request.h:52-113
+  DistanceResult      narrowphase/distance_result.h:51-107
+  collide / distance  narrowphase/collision-inl.h:95-207, narrowphase/distance-inl.h:92-246
+plus the batched entry points (new API beside them) which are the product: one call
+evaluates n pose pairs on the GPU through the C ABI (include/fclgpu.h).
+"""
+import ctypes as C
+import sys
+
+import numpy as np
+
+from . import _capi
+from ._capi import CONTACT_DTYPE, FclGpuError, check, addr
+
+# BVHReturnCode (geometry/bvh/BVH_internal.h:61-72)
+BVH_OK = 0
+BVH_ERR_MODEL_OUT_OF_MEMORY = -1
+BVH_ERR_BUILD_OUT_OF_SEQUENCE = -2
+BVH_ERR_BUILD_EMPTY_MODEL = -3
+BVH_ERR_BUILD_EMPTY_PREVIOUS_FRAME = -4
+BVH_ERR_UNSUPPORTED_FUNCTION = -5
+BVH_ERR_UNUPDATED_MODEL = -6
+BVH_ERR_INCORRECT_DATA = -7
+BVH_ERR_UNKNOWN = -8
+
+# BVHBuildState (BVH_internal.h:48-57)
+BVH_BUILD_STATE_EMPTY, BVH_BUILD_STATE_BEGUN, BVH_BUILD_STATE_PROCESSED = 0, 1, 2
+
+SPLIT_METHOD_MEAN, SPLIT_METHOD_MEDIAN, SPLIT_METHOD_BV_CENTER = 0, 1, 2
+
+DBL_MAX = sys.float_info.max
+
+
+class Transform3:
+    """Rigid transform p -> R p + t (the reference's Transform3<double>, an Eigen Isometry)."""
+
+    __slots__ = ("R", "t")
+
+    def __init__(self, R=None, t=None):
+        self.R = np.eye(3) if R is None else np.asarray(R, dtype=np.float64).reshape(3, 3).copy()
+        self.t = np.zeros(3) if t is None else np.asarray(t, dtype=np.float64).reshape(3).copy()
+
+    @staticmethod
+    def Identity():
+        return Transform3()
+
+    def linear(self):
+        return self.R
+
+    def translation(self):
+        return self.t
+
+    def to_pose12(self):
+        return np.concatenate([self.R.reshape(9), self.t])
+
+    @staticmethod
+    def from_pose12(p):
+        p = np.asarray(p, dtype=np.float64).reshape(12)
+        return Transform3(p[:9].reshape(3, 3), p[9:])
+
+    @staticmethod
+    def from_matrix4_colmajor(m16):
+        m16 = np.ascontiguousarray(m16, dtype=np.float64).reshape(16)
+        out = np.empty(12)
+        _capi.lib().fclgpu_pose_from_colmajor4x4(addr(m16), addr(out))
+        return Transform3.from_pose12(out)
+
+
+def _poses(tf, n=None):
+    """Accepts None (identity), a Transform3, an (n,12) array or a torch tensor; returns (array_or_tensor, n)."""
+    if tf is None:
+        return None, n
+    if isinstance(tf, Transform3):
+        return tf.to_pose12().reshape(1, 12), 1
+    if isinstance(tf, np.ndarray) or isinstance(tf, (list, tuple)):
+        a = np.ascontiguousarray(tf, dtype=np.float64).reshape(-1, 12)
+        return a, len(a)
+    # torch tensor
+    if tf.dtype != _torch().float64 or not tf.is_contiguous():
+        raise ValueError("pose tensors must be contiguous float64 of shape (n, 12)")
+    return tf, tf.numel() // 12
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+class BVHModel:
+    """BVHModel<OBBRSS<double>> (triangle meshes only).
+
+    Build protocol and return codes as the reference: beginModel() -> addSubModel()/
+    addTriangle()* -> endModel() (BVH_model-inl.h:207-253, 256-446, 450-517).  endModel()
+    builds the OBBRSS tree on the host; the flattened tree is uploaded to a GPU on first use.
+    """
+
+    def __init__(self, split_method=SPLIT_METHOD_MEAN):
+        self.split_method = split_method
+        self.build_state = BVH_BUILD_STATE_EMPTY
+        self._verts = []
+        self._tris = []
+        self.vertices = np.zeros((0, 3))
+        self.tri_indices = np.zeros((0, 3), np.int32)
+        self.num_vertices = 0
+        self.num_tris = 0
+        self._bvh = None
+        self._dev = {}
+        # CollisionGeometry defaults (geometry/collision_geometry.h): always "occupied"
+        self.cost_density = 1.0
+        self.threshold_occupied = 1.0
+        self.threshold_free = 0.0
+
+    # -- CollisionGeometry surface used by the dispatch --
+    def getObjectType(self):
+        return "OT_BVH"
+
+    def getNodeType(self):
+        return "BV_OBBRSS"
+
+    def isOccupied(self):
+        return self.cost_density >= self.threshold_occupied
+
+    def isFree(self):
+        return self.cost_density <= self.threshold_free
+
+    # -- build protocol --
+    def beginModel(self, num_tris=0, num_vertices=0):
+        if self.build_state != BVH_BUILD_STATE_EMPTY:
+            self._release()
+            self._verts, self._tris = [], []
+            self.num_vertices = self.num_tris = 0
+        if self.build_state != BVH_BUILD_STATE_EMPTY:
+            sys.stderr.write("BVH Warning! Call beginModel() on a BVHModel that is not empty. This model was cleared "
+                             "and previous triangles/vertices were lost.\n")
+            self.build_state = BVH_BUILD_STATE_EMPTY
+            return BVH_ERR_BUILD_OUT_OF_SEQUENCE
+        self.build_state = BVH_BUILD_STATE_BEGUN
+        return BVH_OK
+
+    def addSubModel(self, ps, ts=None):
+        if self.build_state == BVH_BUILD_STATE_PROCESSED:
+            sys.stderr.write("BVH Warning! Call addSubModel() in a wrong order. addSubModel() was ignored. Must do a "
+                             "beginModel() to clear the model for addition of new vertices.\n")
+            return BVH_ERR_BUILD_OUT_OF_SEQUENCE
+        ps = np.asarray(ps, dtype=np.float64).reshape(-1, 3)
+        offset = self.num_vertices
+        self._verts.append(ps)
+        self.num_vertices += len(ps)
+        if ts is not None:
+            ts = np.asarray(ts, dtype=np.int64).reshape(-1, 3) + offset
+            self._tris.append(ts.astype(np.int32))
+            self.num_tris += len(ts)
+        return BVH_OK
+
+    def addTriangle(self, p1, p2, p3):
+        if self.build_state == BVH_BUILD_STATE_PROCESSED:
+            sys.stderr.write("BVH Warning! Call addTriangle() in a wrong order. addTriangle() was ignored. Must do a "
+                             "beginModel() to clear the model for addition of new triangles.\n")
+            return BVH_ERR_BUILD_OUT_OF_SEQUENCE
+        return self.addSubModel(np.array([p1, p2, p3], dtype=np.float64), np.array([[0, 1, 2]]))
+
+    def endModel(self):
+        if self.build_state != BVH_BUILD_STATE_BEGUN:
+            sys.stderr.write("BVH Warning! Call endModel() in wrong order. endModel() was ignored.\n")
+            return BVH_ERR_BUILD_OUT_OF_SEQUENCE
+        if self.num_tris == 0 and self.num_vertices == 0:
+            sys.stderr.write("BVH Error! endModel() called on model with no triangles and vertices.\n")
+            return BVH_ERR_BUILD_EMPTY_MODEL
+        if self.num_tris == 0:
+            sys.stderr.write("BVH Error! point-cloud models are not supported on the OBBRSS mesh-mesh path.\n")
+            return BVH_ERR_UNSUPPORTED_FUNCTION
+        self.vertices = np.ascontiguousarray(np.concatenate(self._verts), dtype=np.float64)
+        self.tri_indices = np.ascontiguousarray(np.concatenate(self._tris), dtype=np.int32)
+        h = C.c_void_p()
+        rc = _capi.lib().fclgpu_bvh_build_obbrss(addr(self.vertices), self.num_vertices, addr(self.tri_indices),
+                                                 self.num_tris, self.split_method, C.byref(h))
+        if rc != 0:
+            return rc
+        self._bvh = h
+        self.build_state = BVH_BUILD_STATE_PROCESSED
+        return BVH_OK
+
+    @classmethod
+    def from_arrays(cls, verts, tris, split_method=SPLIT_METHOD_MEAN):
+        m = cls(split_method)
+        m.beginModel()
+        m.addSubModel(verts, tris)
+        rc = m.endModel()
+        if rc != BVH_OK:
+            raise FclGpuError(rc, "endModel failed")
+        return m
+
+    def getNumBVs(self):
+        return 0 if self._bvh is None else int(_capi.lib().fclgpu_bvh_num_nodes(self._bvh))
+
+    def node_arrays(self):
+        """The flattened node tree as numpy arrays (what the upload step sends to HBM)."""
+        n, nt = self.getNumBVs(), self.num_tris
+        out = dict(first_child=np.empty(n, np.int32), axis=np.empty((n, 9)), obb_To=np.empty((n, 3)),
+                   obb_ext=np.empty((n, 3)), rss_To=np.empty((n, 3)), rss_l=np.empty((n, 2)), rss_r=np.empty(n),
+                   tri_verts=np.empty((nt, 9)))
+        check(_capi.lib().fclgpu_bvh_get(self._bvh, addr(out["first_child"]), addr(out["axis"]), addr(out["obb_To"]),
+                                         addr(out["obb_ext"]), addr(out["rss_To"]), addr(out["rss_l"]),
+                                         addr(out["rss_r"]), addr(out["tri_verts"])))
+        return out
+
+    def device_model(self, device=None):
+        """Upload (once per device) and return the fclgpu_model handle."""
+        if self.build_state != BVH_BUILD_STATE_PROCESSED:
+            raise FclGpuError(BVH_ERR_BUILD_OUT_OF_SEQUENCE, "model is not built (call endModel())")
+        if device is None:
+            device = _current_device()
+        h = self._dev.get(device)
+        if h is None:
+            h = C.c_void_p()
+            check(_capi.lib().fclgpu_model_from_bvh(int(device), self._bvh, C.byref(h)))
+            self._dev[device] = h
+        return h
+
+    def _release(self):
+        L = _capi.lib()
+        for h in self._dev.values():
+            L.fclgpu_model_destroy(h)
+        self._dev = {}
+        if self._bvh is not None:
+            L.fclgpu_bvh_destroy(self._bvh)
+            self._bvh = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+
+def _current_device():
+    try:
+        torch = _torch()
+        if torch.cuda.is_available():
+            return torch.cuda.current_device()
+    except ImportError:
+        pass
+    return 0
+
+
+class CollisionRequest:
+    def __init__(self, num_max_contacts=1, enable_contact=False, num_max_cost_sources=1, enable_cost=False,
+                 use_approximate_cost=True, gjk_solver_type="GST_LIBCCD", gjk_tolerance=1e-6):
+        self.num_max_contacts = num_max_contacts
+        self.enable_contact = enable_contact
+        self.num_max_cost_sources = num_max_cost_sources
+        self.enable_cost = enable_cost
+        self.use_approximate_cost = use_approximate_cost
+        self.gjk_solver_type = gjk_solver_type
+        self.gjk_tolerance = gjk_tolerance
+
+    def isSatisfied(self, result):
+        return (not self.enable_cost) and result.isCollision() and self.num_max_contacts <= result.numContacts()
+
+    def _c(self):
+        return _capi.CollisionRequestC(int(min(self.num_max_contacts, 2**62)), int(bool(self.enable_contact)),
+                                       int(bool(self.enable_cost)))
+
+
+class Contact:
+    __slots__ = ("o1", "o2", "b1", "b2", "normal", "pos", "penetration_depth")
+
+    def __init__(self, o1=None, o2=None, b1=-1, b2=-1, pos=None, normal=None, depth=0.0):
+        self.o1, self.o2, self.b1, self.b2 = o1, o2, b1, b2
+        self.pos, self.normal, self.penetration_depth = pos, normal, depth
+
+    def __lt__(self, other):  # contact-inl.h:98-104
+        if self.b1 == other.b1:
+            return self.b2 < other.b2
+        return self.b1 < other.b1
+
+
+class CollisionResult:
+    def __init__(self):
+        self.contacts = []
+
+    def addContact(self, c):
+        self.contacts.append(c)
+
+    def isCollision(self):
+        return len(self.contacts) > 0
+
+    def numContacts(self):
+        return len(self.contacts)
+
+    def getContact(self, i):
+        return self.contacts[i] if i < len(self.contacts) else self.contacts[-1]
+
+    def getContacts(self):
+        return list(self.contacts)
+
+    def clear(self):
+        self.contacts = []
+
+
+class DistanceRequest:
+    def __init__(self, enable_nearest_points=False, enable_signed_distance=False, rel_err=0.0, abs_err=0.0,
+                 distance_tolerance=1e-6, gjk_solver_type="GST_LIBCCD"):
+        self.enable_nearest_points = enable_nearest_points
+        self.enable_signed_distance = enable_signed_distance
+        self.rel_err = rel_err  # ignored on this path, like the reference (see include/fclgpu.h)
+        self.abs_err = abs_err
+        self.distance_tolerance = distance_tolerance
+        self.gjk_solver_type = gjk_solver_type
+
+    def isSatisfied(self, result):
+        return result.min_distance <= 0
+
+    def _c(self):
+        return _capi.DistanceRequestC(int(bool(self.enable_nearest_points)), int(bool(self.enable_signed_distance)),
+                                      float(self.rel_err), float(self.abs_err))
+
+
+class DistanceResult:
+    def __init__(self, min_distance=DBL_MAX):
+        self.min_distance = min_distance
+        self.nearest_points = [np.zeros(3), np.zeros(3)]
+        self.o1 = self.o2 = None
+        self.b1 = self.b2 = -1  # DistanceResult::NONE
+
+    def update(self, distance, o1, o2, b1, b2, p1=None, p2=None):  # distance_result-inl.h:66-103
+        if self.min_distance > distance:
+            self.min_distance = distance
+            self.o1, self.o2, self.b1, self.b2 = o1, o2, b1, b2
+            if p1 is not None:
+                self.nearest_points = [np.array(p1), np.array(p2)]
+
+    def clear(self):
+        self.__init__()
+
+
+# ------------------------------------------------------------------------------------------------
+# batched entry points (the product)
+# ------------------------------------------------------------------------------------------------
+class BatchCollisionResult:
+    """num_contacts[n]; contacts (structured array / tensor view) with offsets[n+1]; optional counters."""
+
+    def __init__(self, num_contacts, contacts, offsets, n_bv=None, n_leaf=None):
+        self.num_contacts = num_contacts
+        self.contacts = contacts
+        self.offsets = offsets
+        self.n_bv = n_bv
+        self.n_leaf = n_leaf
+
+    def contacts_of(self, i):
+        return self.contacts[self.offsets[i]:self.offsets[i + 1]]
+
+
+class BatchDistanceResult:
+    def __init__(self, min_distance, p1, p2, b1, b2, n_bv=None, n_leaf=None):
+        self.min_distance, self.nearest_p1, self.nearest_p2, self.b1, self.b2 = min_distance, p1, p2, b1, b2
+        self.n_bv, self.n_leaf = n_bv, n_leaf
+
+
+def collide_batch(o1, tf1, o2, tf2, request, contact_capacity=None, want_contacts=True, stats=False, device=None):
+    """Host arrays in, host arrays out (copies inside): n independent fcl::collide() calls.
+
+    tf1 / tf2: (n,12) float64 pose records, a Transform3, or None (identity)."""
+    tf1, n1 = _poses(tf1)
+    tf2, n2 = _poses(tf2)
+    n = n1 if n1 is not None else n2
+    if n is None:
+        raise ValueError("at least one of tf1/tf2 must be given")
+    if n1 is not None and n2 is not None and n1 != n2:
+        raise ValueError("tf1 and tf2 must have the same length")
+    m1, m2 = o1.device_model(device), o2.device_model(device)
+    req = request._c()
+    counts = np.zeros(n, np.int32)
+    if want_contacts:
+        if contact_capacity is None:
+            contact_capacity = int(min(max(request.num_max_contacts, 0), 64)) * n
+        contact_capacity = max(int(contact_capacity), 1)
+        contacts = np.zeros(contact_capacity, CONTACT_DTYPE)
+        offsets = np.zeros(n + 1, np.int64)
+    else:
+        contact_capacity, contacts, offsets = 0, None, None
+    n_bv = np.zeros(n, np.uint32) if stats else None
+    n_leaf = np.zeros(n, np.uint32) if stats else None
+    check(_capi.lib().fclgpu_collide_batch_host(m1, m2, n, addr(tf1), addr(tf2), C.byref(req), addr(counts),
+                                                addr(contacts), contact_capacity, addr(offsets), addr(n_bv),
+                                                addr(n_leaf)))
+    if want_contacts:
+        contacts = contacts[: offsets[n]]
+    return BatchCollisionResult(counts, contacts, offsets, n_bv, n_leaf)
+
+
+def distance_batch(o1, tf1, o2, tf2, request, stats=False, device=None):
+    tf1, n1 = _poses(tf1)
+    tf2, n2 = _poses(tf2)
+    n = n1 if n1 is not None else n2
+    if n is None:
+        raise ValueError("at least one of tf1/tf2 must be given")
+    m1, m2 = o1.device_model(device), o2.device_model(device)
+    req = request._c()
+    dist = np.zeros(n)
+    p1 = np.zeros((n, 3))
+    p2 = np.zeros((n, 3))
+    b1 = np.zeros(n, np.int32)
+    b2 = np.zeros(n, np.int32)
+    n_bv = np.zeros(n, np.uint32) if stats else None
+    n_leaf = np.zeros(n, np.uint32) if stats else None
+    check(_capi.lib().fclgpu_distance_batch_host(m1, m2, n, addr(tf1), addr(tf2), C.byref(req), addr(dist), addr(p1),
+                                                 addr(p2), addr(b1), addr(b2), addr(n_bv), addr(n_leaf)))
+    return BatchDistanceResult(dist, p1, p2, b1, b2, n_bv, n_leaf)
+
+
+def collide_batch_device(o1, tf1, o2, tf2, request, num_contacts, contacts=None, contact_offsets=None, n_bv=None,
+                         n_leaf=None, stream=None):
+    """Device-resident variant: every argument is a CUDA torch tensor (or None); asynchronous on
+    `stream` (default: torch's current stream).  contacts: uint8/any tensor of capacity*64 bytes."""
+    torch = _torch()
+    n = (tf1 if tf1 is not None else tf2).numel() // 12
+    dev = num_contacts.device.index
+    m1, m2 = o1.device_model(dev), o2.device_model(dev)
+    req = request._c()
+    cap = 0 if contacts is None else (contacts.numel() * contacts.element_size()) // 64
+    st = (stream or torch.cuda.current_stream(dev)).cuda_stream
+    check(_capi.lib().fclgpu_collide_batch(m1, m2, n, addr(tf1), addr(tf2), C.byref(req), addr(num_contacts),
+                                           addr(contacts), cap, addr(contact_offsets), addr(n_bv), addr(n_leaf), st))
+
+
+def distance_batch_device(o1, tf1, o2, tf2, request, min_distance, p1=None, p2=None, b1=None, b2=None, n_bv=None,
+                          n_leaf=None, stream=None):
+    torch = _torch()
+    n = (tf1 if tf1 is not None else tf2).numel() // 12
+    dev = min_distance.device.index
+    m1, m2 = o1.device_model(dev), o2.device_model(dev)
+    req = request._c()
+    st = (stream or torch.cuda.current_stream(dev)).cuda_stream
+    check(_capi.lib().fclgpu_distance_batch(m1, m2, n, addr(tf1), addr(tf2), C.byref(req), addr(min_distance),
+                                            addr(p1), addr(p2), addr(b1), addr(b2), addr(n_bv), addr(n_leaf), st))
+
+
+def sync_status(device=None, stream=None):
+    torch = _torch()
+    dev = _current_device() if device is None else device
+    st = (stream or torch.cuda.current_stream(dev)).cuda_stream
+    check(_capi.lib().fclgpu_sync_status(dev, st))
+
+
+# ------------------------------------------------------------------------------------------------
+# single-query entry points with the reference's signatures
+# ------------------------------------------------------------------------------------------------
+def collide(o1, tf1, o2, tf2, request, result):
+    """fcl::collide(o1, tf1, o2, tf2, request, result) for two BVHModel<OBBRSS> (collision-inl.h:95-207).
+    Appends to `result` (results accumulate across calls unless cleared) and returns numContacts()."""
+    if request.num_max_contacts == 0:
+        sys.stderr.write(f"Warning: should stop early as num_max_contact is {request.num_max_contacts} !\n")
+        return 0
+    if not (isinstance(o1, BVHModel) and isinstance(o2, BVHModel)):
+        sys.stderr.write("Warning: collision function between these node types is not supported\n")
+        return 0
+    if request.isSatisfied(result):  # orientedMeshCollide, collision_func_matrix-inl.h:580
+        return result.numContacts()
+    if request.enable_cost:
+        raise FclGpuError(BVH_ERR_UNSUPPORTED_FUNCTION, "cost sources are not supported on this path")
+    # a non-empty result consumes part of the contact budget
+    budget = request.num_max_contacts - result.numContacts()
+    sub = CollisionRequest(budget, request.enable_contact)
+    r = collide_batch(o1, tf1, o2, tf2, sub, contact_capacity=None if budget > 4096 else budget)
+    for c in r.contacts_of(0):
+        if request.enable_contact:
+            result.addContact(Contact(o1, o2, int(c["b1"]), int(c["b2"]), c["pos"].copy(), c["normal"].copy(),
+                                      float(c["penetration_depth"])))
+        else:
+            result.addContact(Contact(o1, o2, int(c["b1"]), int(c["b2"])))
+    return result.numContacts()
+
+
+def distance(o1, tf1, o2, tf2, request, result):
+    """fcl::distance(o1, tf1, o2, tf2, request, result) (distance-inl.h:92-246); returns min_distance."""
+    if not (isinstance(o1, BVHModel) and isinstance(o2, BVHModel)):
+        sys.stderr.write("Warning: distance function between these node types is not supported\n")
+        return DBL_MAX
+    if request.isSatisfied(result):  # orientedMeshDistance, distance_func_matrix-inl.h:395
+        return result.min_distance
+    r = distance_batch(o1, tf1, o2, tf2, request)
+    if request.enable_nearest_points:
+        result.update(float(r.min_distance[0]), o1, o2, int(r.b1[0]), int(r.b2[0]), r.nearest_p1[0], r.nearest_p2[0])
+    else:
+        result.update(float(r.min_distance[0]), o1, o2, int(r.b1[0]), int(r.b2[0]))
+    return result.min_distance

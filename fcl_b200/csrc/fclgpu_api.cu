@@ -1,0 +1,745 @@
+// fclgpu_api.cu — C ABI (include/fclgpu.h): model upload, batched collide / distance,
+// contact compaction, host-pointer wrappers and micro-benchmarks.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/fclgpu.h"
+#include "bvh_build.hpp"
+#include "traversal.cuh"
+
+using namespace fclgpu;
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return fail(e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver            \
+                      ? FCLGPU_ERR_NO_DEVICE                                                \
+                      : (e__ == cudaErrorMemoryAllocation ? FCLGPU_ERR_MODEL_OUT_OF_MEMORY  \
+                                                          : FCLGPU_ERR_CUDA),               \
+                  "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+// options
+std::mutex g_opt_mu;
+std::map<std::string, long long> g_opts = {
+    {"traversal", 0},          // 0 = thread per query (persistent lanes), 1 = warp per query front traversal
+    {"contact_stride", 1024},  // per-query contact scratch slots when num_max_contacts is larger
+    {"scratch_bytes", 2ll << 30},
+    {"blocks_per_sm", 0},      // 0 = occupancy query
+    {"stats", 1},
+};
+long long opt(const char* k) {
+  std::lock_guard<std::mutex> g(g_opt_mu);
+  auto it = g_opts.find(k);
+  return it == g_opts.end() ? 0 : it->second;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-device workspace: work counters, sticky status, scan temporaries, contact scratch
+// ------------------------------------------------------------------------------------------
+struct Workspace {
+  int device = -1;
+  int sm_count = 0;
+  unsigned long long* counters = nullptr;  // ring of work counters (one per launch in flight)
+  int counter_slots = 0, counter_next = 0;
+  int* status = nullptr;
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  void* scan_tmp = nullptr;
+  size_t scan_bytes = 0;
+  long long* scan_base = nullptr;  // running contact offset across chunks
+  // host-API staging (device side)
+  void* dev_io = nullptr;
+  size_t dev_io_bytes = 0;
+  std::mutex mu;
+};
+
+std::mutex g_ws_mu;
+std::map<int, Workspace*> g_ws;
+
+int get_ws(int device, Workspace** out) {
+  std::lock_guard<std::mutex> g(g_ws_mu);
+  auto it = g_ws.find(device);
+  if (it != g_ws.end()) {
+    *out = it->second;
+    return 0;
+  }
+  CUDA_TRY(cudaSetDevice(device));
+  Workspace* w = new Workspace;
+  w->device = device;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  w->sm_count = prop.multiProcessorCount;
+  w->counter_slots = 4096;
+  CUDA_TRY(cudaMalloc(&w->counters, sizeof(unsigned long long) * w->counter_slots));
+  CUDA_TRY(cudaMemset(w->counters, 0, sizeof(unsigned long long) * w->counter_slots));
+  CUDA_TRY(cudaMalloc(&w->status, sizeof(int)));
+  CUDA_TRY(cudaMemset(w->status, 0, sizeof(int)));
+  CUDA_TRY(cudaMalloc(&w->scan_base, sizeof(long long)));
+  g_ws[device] = w;
+  *out = w;
+  return 0;
+}
+
+int ensure(void** p, size_t* have, size_t want) {
+  if (*have >= want) return 0;
+  if (*p) CUDA_TRY(cudaFree(*p));
+  *p = nullptr;
+  *have = 0;
+  CUDA_TRY(cudaMalloc(p, want));
+  *have = want;
+  return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// model
+// ------------------------------------------------------------------------------------------
+struct fclgpu_model {
+  int device;
+  DeviceModel d;
+  double *obb, *rss, *tri;
+  int32_t* fc;
+  int depth;
+};
+
+namespace {
+int tree_depth(const int32_t* fc, int n) {
+  std::vector<std::pair<int, int>> st;
+  st.emplace_back(0, 0);
+  int mx = 0;
+  while (!st.empty()) {
+    auto [i, d] = st.back();
+    st.pop_back();
+    mx = std::max(mx, d);
+    if (fc[i] >= 0) {
+      if (fc[i] + 1 >= n) return -1;
+      st.emplace_back(fc[i], d + 1);
+      st.emplace_back(fc[i] + 1, d + 1);
+    }
+  }
+  return mx;
+}
+}  // namespace
+
+extern "C" int fclgpu_model_create_obbrss(int device, int32_t n_nodes, const int32_t* first_child,
+                                          const double* axis9, const double* obb_To3,
+                                          const double* obb_extent3, const double* rss_To3,
+                                          const double* rss_l2, const double* rss_r, int32_t n_tris,
+                                          const double* tri_verts9, fclgpu_model** out) {
+  if (!out) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  if (n_nodes <= 0 || n_tris <= 0) return fail(FCLGPU_ERR_BUILD_EMPTY_MODEL, "empty model");
+  if (!first_child || !axis9 || !obb_To3 || !obb_extent3 || !rss_To3 || !rss_l2 || !rss_r || !tri_verts9)
+    return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL node array");
+  if (n_nodes != 2 * n_tris - 1) return fail(FCLGPU_ERR_INCORRECT_DATA, "n_nodes != 2*n_tris-1");
+  for (int i = 0; i < n_nodes; ++i) {
+    const int fc = first_child[i];
+    if (fc >= 0 ? (fc + 1 >= n_nodes || fc <= i) : (-(fc + 1) >= n_tris))
+      return fail(FCLGPU_ERR_INCORRECT_DATA, "first_child[%d]=%d out of range", i, fc);
+  }
+  const int depth = tree_depth(first_child, n_nodes);
+  if (depth < 0) return fail(FCLGPU_ERR_INCORRECT_DATA, "malformed tree");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(FCLGPU_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "device %d out of range", device);
+  CUDA_TRY(cudaSetDevice(device));
+
+  // pack the 128-byte node records and 80-byte triangle records
+  std::vector<double> obb((size_t)n_nodes * kNodeDoubles), rss((size_t)n_nodes * kNodeDoubles);
+  for (int i = 0; i < n_nodes; ++i) {
+    double* o = &obb[(size_t)i * kNodeDoubles];
+    double* r = &rss[(size_t)i * kNodeDoubles];
+    for (int k = 0; k < 9; ++k) o[k] = r[k] = axis9[9 * (size_t)i + k];
+    for (int k = 0; k < 3; ++k) {
+      o[9 + k] = obb_To3[3 * (size_t)i + k];
+      o[12 + k] = obb_extent3[3 * (size_t)i + k];
+      r[9 + k] = rss_To3[3 * (size_t)i + k];
+    }
+    r[12] = rss_l2[2 * (size_t)i];
+    r[13] = rss_l2[2 * (size_t)i + 1];
+    r[14] = rss_r[i];
+    // OBB::size() = extent.squaredNorm(), summed left to right
+    const double size = (o[12] * o[12] + o[13] * o[13]) + o[14] * o[14];
+    o[15] = r[15] = size;
+  }
+  std::vector<double> tri((size_t)n_tris * kTriDoubles, 0.0);
+  for (int t = 0; t < n_tris; ++t)
+    for (int k = 0; k < 9; ++k) tri[(size_t)t * kTriDoubles + k] = tri_verts9[9 * (size_t)t + k];
+
+  fclgpu_model* m = new fclgpu_model{};
+  m->device = device;
+  m->depth = depth;
+  auto up = [&](double** dst, const std::vector<double>& src) -> int {
+    CUDA_TRY(cudaMalloc((void**)dst, src.size() * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(*dst, src.data(), src.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+  };
+  int rc;
+  if ((rc = up(&m->obb, obb)) || (rc = up(&m->rss, rss)) || (rc = up(&m->tri, tri))) {
+    fclgpu_model_destroy(m);
+    return rc;
+  }
+  if (cudaMalloc((void**)&m->fc, sizeof(int32_t) * n_nodes) != cudaSuccess ||
+      cudaMemcpy(m->fc, first_child, sizeof(int32_t) * n_nodes, cudaMemcpyHostToDevice) != cudaSuccess) {
+    fclgpu_model_destroy(m);
+    return fail(FCLGPU_ERR_MODEL_OUT_OF_MEMORY, "first_child upload failed");
+  }
+  m->d = DeviceModel{m->obb, m->rss, m->fc, m->tri, n_nodes, n_tris};
+  *out = m;
+  return FCLGPU_OK;
+}
+
+extern "C" int fclgpu_model_from_bvh(int device, const fclgpu_bvh* bvh, fclgpu_model** out) {
+  if (!bvh) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "bvh is NULL");
+  const int nn = fclgpu_bvh_num_nodes(bvh), nt = fclgpu_bvh_num_tris(bvh);
+  std::vector<int32_t> fc(nn);
+  std::vector<double> axis(9 * (size_t)nn), oT(3 * (size_t)nn), oe(3 * (size_t)nn), rT(3 * (size_t)nn), rl(2 * (size_t)nn),
+      rr(nn), tv(9 * (size_t)nt);
+  fclgpu_bvh_get(bvh, fc.data(), axis.data(), oT.data(), oe.data(), rT.data(), rl.data(), rr.data(), tv.data());
+  return fclgpu_model_create_obbrss(device, nn, fc.data(), axis.data(), oT.data(), oe.data(), rT.data(), rl.data(),
+                                    rr.data(), nt, tv.data(), out);
+}
+
+extern "C" int fclgpu_model_destroy(fclgpu_model* m) {
+  if (!m) return FCLGPU_OK;
+  cudaSetDevice(m->device);
+  cudaFree(m->obb);
+  cudaFree(m->rss);
+  cudaFree(m->tri);
+  cudaFree(m->fc);
+  delete m;
+  return FCLGPU_OK;
+}
+extern "C" int32_t fclgpu_model_num_nodes(const fclgpu_model* m) { return m ? m->d.n_nodes : 0; }
+extern "C" int32_t fclgpu_model_num_tris(const fclgpu_model* m) { return m ? m->d.n_tris : 0; }
+extern "C" int fclgpu_model_device(const fclgpu_model* m) { return m ? m->device : -1; }
+
+// ------------------------------------------------------------------------------------------
+// contact compaction: exclusive scan of per-query counts -> offsets, then gather from the
+// fixed-stride scratch into the dense pool (deterministic: query order, DFS order inside)
+// ------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kScanBlock = 1024;
+
+// pass 1: per-block inclusive scan (counts clipped to `stride` = what was actually stored)
+__global__ void scan_block_kernel(const int32_t* __restrict__ counts, long long n, long long stride,
+                                  long long* __restrict__ local, long long* __restrict__ block_sums) {
+  __shared__ long long warp_sums[32];
+  const long long i = (long long)blockIdx.x * kScanBlock + threadIdx.x;
+  long long v = 0;
+  if (i < n) {
+    v = counts[i];
+    if (v > stride) v = stride;
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  long long x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    long long y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_sums[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    long long w = warp_sums[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      long long y = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += y;
+    }
+    warp_sums[lane] = w;
+  }
+  __syncthreads();
+  const long long prefix = (wid > 0 ? warp_sums[wid - 1] : 0) + x;  // inclusive
+  if (i < n) local[i] = prefix - v;                                // exclusive within block
+  if (threadIdx.x == kScanBlock - 1) block_sums[blockIdx.x] = prefix;
+}
+
+// pass 2: one block scans the block sums in place (exclusive), adds the running base
+__global__ void scan_sums_kernel(long long* __restrict__ block_sums, int nblocks, long long* __restrict__ base,
+                                 long long* __restrict__ total_out) {
+  __shared__ long long carry;
+  __shared__ long long warp_sums[32];
+  if (threadIdx.x == 0) carry = *base;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int s = 0; s < nblocks; s += kScanBlock) {
+    const int i = s + threadIdx.x;
+    const long long v = (i < nblocks) ? block_sums[i] : 0;
+    long long x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      long long y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      long long w = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        long long y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const long long incl = (wid > 0 ? warp_sums[wid - 1] : 0) + x;
+    if (i < nblocks) block_sums[i] = carry + incl - v;
+    __syncthreads();
+    if (threadIdx.x == kScanBlock - 1) carry += incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *base = carry;
+    if (total_out) *total_out = carry;
+  }
+}
+
+// pass 3: offsets[i] = block offset + local; gather contacts (one warp per query, 16-byte copies)
+__global__ void compact_kernel(const int32_t* __restrict__ counts, long long n, long long stride,
+                               const long long* __restrict__ local, const long long* __restrict__ block_sums,
+                               const fclgpu_contact* __restrict__ scratch, fclgpu_contact* __restrict__ pool,
+                               long long capacity, long long* __restrict__ offsets, int* status) {
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const long long off = block_sums[warp / kScanBlock] + local[warp];
+  long long c = counts[warp];
+  if (c > stride) c = stride;
+  if (lane == 0 && offsets) offsets[warp] = off;
+  if (pool == nullptr) return;
+  if (off + c > capacity) {
+    if (lane == 0) atomicMin(status, (int)FCLGPU_ERR_CONTACT_OVERFLOW);
+    c = capacity > off ? capacity - off : 0;
+  }
+  const int4* src = reinterpret_cast<const int4*>(scratch + warp * stride);
+  int4* dst = reinterpret_cast<int4*>(pool + off);
+  for (long long k = lane; k < c * 4; k += 32) dst[k] = src[k];
+}
+
+__global__ void write_total_kernel(const long long* base, long long* offsets_n) { *offsets_n = *base; }
+
+template <typename K, typename Pm>
+int launch_persistent(K kernel, const Pm& params, Workspace* w, int block, cudaStream_t st) {
+  int per_sm = (int)opt("blocks_per_sm");
+  if (per_sm <= 0) {
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0));
+    if (per_sm < 1) per_sm = 1;
+  }
+  const int grid = w->sm_count * per_sm;
+  kernel<<<grid, block, 0, st>>>(params);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+unsigned long long* next_counter(Workspace* w, cudaStream_t st) {
+  unsigned long long* c = w->counters + w->counter_next;
+  w->counter_next = (w->counter_next + 1) % w->counter_slots;
+  cudaMemsetAsync(c, 0, sizeof(unsigned long long), st);
+  return c;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// collide
+// ------------------------------------------------------------------------------------------
+extern "C" int fclgpu_collide_batch(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1,
+                                    const double* tf2, const fclgpu_collision_request* request,
+                                    int32_t* num_contacts, fclgpu_contact* contacts, int64_t contact_capacity,
+                                    int64_t* contact_offsets, uint32_t* n_bv, uint32_t* n_leaf, void* stream) {
+  if (!m1 || !m2 || !request || n < 0) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL model/request or n<0");
+  if (m1->device != m2->device) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "models live on different devices");
+  if (request->enable_cost) return fail(FCLGPU_ERR_UNSUPPORTED_FUNCTION, "cost sources are not supported on this path");
+  if (!num_contacts) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "num_contacts is NULL");
+  if (m1->depth + m2->depth + 2 > kStackCap)
+    return fail(FCLGPU_ERR_STACK_OVERFLOW, "tree depths %d+%d exceed the traversal stack", m1->depth, m2->depth);
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaSetDevice(m1->device));
+  Workspace* w;
+  int rc = get_ws(m1->device, &w);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lock(w->mu);
+  if (n == 0) {
+    if (contact_offsets) CUDA_TRY(cudaMemsetAsync(contact_offsets, 0, sizeof(int64_t), st));
+    return FCLGPU_OK;
+  }
+  if (request->num_max_contacts <= 0) {  // collision-inl.h:111-115: warn and return 0
+    CUDA_TRY(cudaMemsetAsync(num_contacts, 0, sizeof(int32_t) * n, st));
+    if (contact_offsets) CUDA_TRY(cudaMemsetAsync(contact_offsets, 0, sizeof(int64_t) * (n + 1), st));
+    if (n_bv) CUDA_TRY(cudaMemsetAsync(n_bv, 0, sizeof(uint32_t) * n, st));
+    if (n_leaf) CUDA_TRY(cudaMemsetAsync(n_leaf, 0, sizeof(uint32_t) * n, st));
+    return FCLGPU_OK;
+  }
+  const bool want_contacts = contacts != nullptr || contact_offsets != nullptr;
+  const bool stats = (n_bv || n_leaf);
+
+  long long stride = 0, chunk = n;
+  if (want_contacts) {
+    stride = std::min<long long>(request->num_max_contacts, std::max<long long>(1, opt("contact_stride")));
+    const long long budget = std::max<long long>(opt("scratch_bytes"), stride * (long long)sizeof(fclgpu_contact));
+    chunk = std::max<long long>(1, std::min<long long>(n, budget / (stride * (long long)sizeof(fclgpu_contact))));
+    rc = ensure(&w->scratch, &w->scratch_bytes, (size_t)(chunk * stride) * sizeof(fclgpu_contact));
+    if (rc) return rc;
+    const long long nblk = (chunk + kScanBlock - 1) / kScanBlock;
+    rc = ensure(&w->scan_tmp, &w->scan_bytes, (size_t)(chunk + nblk) * sizeof(long long));
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(w->scan_base, 0, sizeof(long long), st));
+  }
+
+  for (long long s = 0; s < n; s += chunk) {
+    const long long cn = std::min(chunk, n - s);
+    CollideParams P;
+    P.m1 = m1->d;
+    P.m2 = m2->d;
+    P.tf1 = tf1 ? tf1 + 12 * s : nullptr;
+    P.tf2 = tf2 ? tf2 + 12 * s : nullptr;
+    P.n = cn;
+    P.max_contacts = request->num_max_contacts;
+    P.enable_contact = request->enable_contact ? 1 : 0;
+    P.num_contacts = num_contacts + s;
+    P.scratch = want_contacts ? (fclgpu_contact*)w->scratch : nullptr;
+    P.stride = stride;
+    P.n_bv = n_bv ? n_bv + s : nullptr;
+    P.n_leaf = n_leaf ? n_leaf + s : nullptr;
+    P.work_counter = next_counter(w, st);
+    P.status = w->status;
+    rc = stats ? launch_persistent(collide_thread_kernel<true>, P, w, 128, st)
+               : launch_persistent(collide_thread_kernel<false>, P, w, 128, st);
+    if (rc) return rc;
+    if (want_contacts) {
+      long long* local = (long long*)w->scan_tmp;
+      long long* bsums = local + cn;
+      const int nblk = (int)((cn + kScanBlock - 1) / kScanBlock);
+      scan_block_kernel<<<nblk, kScanBlock, 0, st>>>(num_contacts + s, cn, stride, local, bsums);
+      scan_sums_kernel<<<1, kScanBlock, 0, st>>>(bsums, nblk, w->scan_base, nullptr);
+      const long long threads = cn * 32;
+      compact_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
+          num_contacts + s, cn, stride, local, bsums, (const fclgpu_contact*)w->scratch, contacts, contact_capacity,
+          contact_offsets ? (long long*)contact_offsets + s : nullptr, w->status);
+      g_launches += 3;
+      CUDA_TRY(cudaGetLastError());
+    }
+  }
+  if (want_contacts && contact_offsets) {
+    write_total_kernel<<<1, 1, 0, st>>>(w->scan_base, (long long*)contact_offsets + n);
+    g_launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return FCLGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// distance
+// ------------------------------------------------------------------------------------------
+extern "C" int fclgpu_distance_batch(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1,
+                                     const double* tf2, const fclgpu_distance_request* request,
+                                     double* min_distance, double* nearest_p1, double* nearest_p2, int32_t* b1,
+                                     int32_t* b2, uint32_t* n_bv, uint32_t* n_leaf, void* stream) {
+  if (!m1 || !m2 || !request || n < 0) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL model/request or n<0");
+  if (m1->device != m2->device) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "models live on different devices");
+  if (m1->depth + m2->depth + 2 > kStackCap)
+    return fail(FCLGPU_ERR_STACK_OVERFLOW, "tree depths %d+%d exceed the traversal stack", m1->depth, m2->depth);
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaSetDevice(m1->device));
+  Workspace* w;
+  int rc = get_ws(m1->device, &w);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lock(w->mu);
+  if (n == 0) return FCLGPU_OK;
+  DistanceParams P;
+  P.m1 = m1->d;
+  P.m2 = m2->d;
+  P.tf1 = tf1;
+  P.tf2 = tf2;
+  P.n = n;
+  P.enable_nearest_points = request->enable_nearest_points ? 1 : 0;
+  P.min_distance = min_distance;
+  P.p1 = nearest_p1;
+  P.p2 = nearest_p2;
+  P.b1 = b1;
+  P.b2 = b2;
+  P.n_bv = n_bv;
+  P.n_leaf = n_leaf;
+  P.work_counter = next_counter(w, st);
+  P.status = w->status;
+  const bool stats = (n_bv || n_leaf);
+  rc = stats ? launch_persistent(distance_thread_kernel<true>, P, w, 128, st)
+             : launch_persistent(distance_thread_kernel<false>, P, w, 128, st);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// status / host-pointer wrappers
+// ------------------------------------------------------------------------------------------
+extern "C" int fclgpu_sync_status(int device, void* stream) {
+  Workspace* w;
+  int rc = get_ws(device, &w);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  int s = 0;
+  CUDA_TRY(cudaMemcpy(&s, w->status, sizeof(int), cudaMemcpyDeviceToHost));
+  if (s != 0) {
+    CUDA_TRY(cudaMemset(w->status, 0, sizeof(int)));
+    return fail(s, s == FCLGPU_ERR_CONTACT_OVERFLOW ? "contact capacity exceeded (counts are exact; raise contact "
+                                                      "capacity or the contact_stride option)"
+                                                    : "traversal stack overflow");
+  }
+  return FCLGPU_OK;
+}
+
+namespace {
+struct DevBuf {  // carve typed sub-buffers out of one device allocation (256-byte aligned)
+  char* base;
+  size_t off = 0;
+  template <typename T>
+  T* take(size_t count) {
+    T* p = reinterpret_cast<T*>(base + off);
+    off += (count * sizeof(T) + 255) & ~size_t(255);
+    return p;
+  }
+};
+size_t padded(size_t bytes) { return (bytes + 255) & ~size_t(255); }
+}  // namespace
+
+extern "C" int fclgpu_collide_batch_host(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1,
+                                         const double* tf2, const fclgpu_collision_request* request,
+                                         int32_t* num_contacts, fclgpu_contact* contacts, int64_t contact_capacity,
+                                         int64_t* contact_offsets, uint32_t* n_bv, uint32_t* n_leaf) {
+  if (!m1 || !m2 || !request || n < 0 || !num_contacts)
+    return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL model/request/num_contacts or n<0");
+  CUDA_TRY(cudaSetDevice(m1->device));
+  Workspace* w;
+  int rc = get_ws(m1->device, &w);
+  if (rc) return rc;
+  const bool want = contacts != nullptr || contact_offsets != nullptr;
+  if (contacts == nullptr) contact_capacity = 0;
+  size_t bytes = (tf1 ? padded(96 * (size_t)n) : 0) + (tf2 ? padded(96 * (size_t)n) : 0) + padded(4 * (size_t)n) +
+                 (want ? padded(8 * (size_t)(n + 1)) + padded(64 * (size_t)contact_capacity) : 0) +
+                 (n_bv ? padded(4 * (size_t)n) : 0) + (n_leaf ? padded(4 * (size_t)n) : 0) + 256;
+  {
+    std::lock_guard<std::mutex> lock(w->mu);
+    rc = ensure(&w->dev_io, &w->dev_io_bytes, bytes);
+    if (rc) return rc;
+  }
+  DevBuf B{(char*)w->dev_io};
+  double* d_tf1 = tf1 ? B.take<double>(12 * (size_t)n) : nullptr;
+  double* d_tf2 = tf2 ? B.take<double>(12 * (size_t)n) : nullptr;
+  int32_t* d_cnt = B.take<int32_t>((size_t)n);
+  int64_t* d_off = want ? B.take<int64_t>((size_t)n + 1) : nullptr;
+  fclgpu_contact* d_con = (want && contact_capacity > 0) ? B.take<fclgpu_contact>((size_t)contact_capacity) : nullptr;
+  uint32_t* d_bv = n_bv ? B.take<uint32_t>((size_t)n) : nullptr;
+  uint32_t* d_leaf = n_leaf ? B.take<uint32_t>((size_t)n) : nullptr;
+  cudaStream_t st = 0;
+  if (tf1) CUDA_TRY(cudaMemcpyAsync(d_tf1, tf1, 96 * (size_t)n, cudaMemcpyHostToDevice, st));
+  if (tf2) CUDA_TRY(cudaMemcpyAsync(d_tf2, tf2, 96 * (size_t)n, cudaMemcpyHostToDevice, st));
+  rc = fclgpu_collide_batch(m1, m2, n, d_tf1, d_tf2, request, d_cnt, d_con, contact_capacity, d_off, d_bv, d_leaf, st);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(num_contacts, d_cnt, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  if (n_bv) CUDA_TRY(cudaMemcpyAsync(n_bv, d_bv, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  if (n_leaf) CUDA_TRY(cudaMemcpyAsync(n_leaf, d_leaf, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  int64_t total = 0;
+  if (want && n > 0 && request->num_max_contacts > 0) {
+    if (contact_offsets) CUDA_TRY(cudaMemcpyAsync(contact_offsets, d_off, 8 * (size_t)(n + 1), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpy(&total, d_off + n, 8, cudaMemcpyDeviceToHost));
+    if (contacts && total > 0)
+      CUDA_TRY(cudaMemcpyAsync(contacts, d_con, 64 * (size_t)std::min<int64_t>(total, contact_capacity),
+                               cudaMemcpyDeviceToHost, st));
+  } else if (contact_offsets) {
+    std::memset(contact_offsets, 0, 8 * (size_t)(n + 1));
+  }
+  return fclgpu_sync_status(m1->device, st);
+}
+
+extern "C" int fclgpu_distance_batch_host(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n,
+                                          const double* tf1, const double* tf2,
+                                          const fclgpu_distance_request* request, double* min_distance,
+                                          double* nearest_p1, double* nearest_p2, int32_t* b1, int32_t* b2,
+                                          uint32_t* n_bv, uint32_t* n_leaf) {
+  if (!m1 || !m2 || !request || n < 0) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL model/request or n<0");
+  CUDA_TRY(cudaSetDevice(m1->device));
+  Workspace* w;
+  int rc = get_ws(m1->device, &w);
+  if (rc) return rc;
+  const size_t N = (size_t)n;
+  size_t bytes = (tf1 ? padded(96 * N) : 0) + (tf2 ? padded(96 * N) : 0) + padded(8 * N) + 2 * padded(24 * N) +
+                 4 * padded(4 * N) + 256;
+  {
+    std::lock_guard<std::mutex> lock(w->mu);
+    rc = ensure(&w->dev_io, &w->dev_io_bytes, bytes);
+    if (rc) return rc;
+  }
+  DevBuf B{(char*)w->dev_io};
+  double* d_tf1 = tf1 ? B.take<double>(12 * N) : nullptr;
+  double* d_tf2 = tf2 ? B.take<double>(12 * N) : nullptr;
+  double* d_dist = B.take<double>(N);
+  double* d_p1 = nearest_p1 ? B.take<double>(3 * N) : nullptr;
+  double* d_p2 = nearest_p2 ? B.take<double>(3 * N) : nullptr;
+  int32_t* d_b1 = b1 ? B.take<int32_t>(N) : nullptr;
+  int32_t* d_b2 = b2 ? B.take<int32_t>(N) : nullptr;
+  uint32_t* d_bv = n_bv ? B.take<uint32_t>(N) : nullptr;
+  uint32_t* d_leaf = n_leaf ? B.take<uint32_t>(N) : nullptr;
+  cudaStream_t st = 0;
+  if (tf1) CUDA_TRY(cudaMemcpyAsync(d_tf1, tf1, 96 * N, cudaMemcpyHostToDevice, st));
+  if (tf2) CUDA_TRY(cudaMemcpyAsync(d_tf2, tf2, 96 * N, cudaMemcpyHostToDevice, st));
+  rc = fclgpu_distance_batch(m1, m2, n, d_tf1, d_tf2, request, d_dist, d_p1, d_p2, d_b1, d_b2, d_bv, d_leaf, st);
+  if (rc) return rc;
+  if (min_distance) CUDA_TRY(cudaMemcpyAsync(min_distance, d_dist, 8 * N, cudaMemcpyDeviceToHost, st));
+  if (nearest_p1 && request->enable_nearest_points) CUDA_TRY(cudaMemcpyAsync(nearest_p1, d_p1, 24 * N, cudaMemcpyDeviceToHost, st));
+  if (nearest_p2 && request->enable_nearest_points) CUDA_TRY(cudaMemcpyAsync(nearest_p2, d_p2, 24 * N, cudaMemcpyDeviceToHost, st));
+  if (b1) CUDA_TRY(cudaMemcpyAsync(b1, d_b1, 4 * N, cudaMemcpyDeviceToHost, st));
+  if (b2) CUDA_TRY(cudaMemcpyAsync(b2, d_b2, 4 * N, cudaMemcpyDeviceToHost, st));
+  if (n_bv) CUDA_TRY(cudaMemcpyAsync(n_bv, d_bv, 4 * N, cudaMemcpyDeviceToHost, st));
+  if (n_leaf) CUDA_TRY(cudaMemcpyAsync(n_leaf, d_leaf, 4 * N, cudaMemcpyDeviceToHost, st));
+  return fclgpu_sync_status(m1->device, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// utilities
+// ------------------------------------------------------------------------------------------
+extern "C" int fclgpu_abi_version(void) { return FCLGPU_ABI_VERSION; }
+
+extern "C" int fclgpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+extern "C" const char* fclgpu_last_error(void) { return g_err; }
+
+extern "C" void fclgpu_pose_from_colmajor4x4(const double* m, double* p) {
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) p[3 * r + c] = m[4 * c + r];
+    p[9 + r] = m[12 + r];
+  }
+}
+
+extern "C" int fclgpu_set_option(const char* name, int64_t value) {
+  if (!name) return FCLGPU_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(g_opt_mu);
+  auto it = g_opts.find(name);
+  if (it == g_opts.end()) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "unknown option %s", name);
+  it->second = value;
+  return FCLGPU_OK;
+}
+extern "C" int64_t fclgpu_get_option(const char* name) { return name ? opt(name) : 0; }
+extern "C" int64_t fclgpu_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------
+// micro-benchmarks for the roofline denominators
+// ------------------------------------------------------------------------------------------
+namespace {
+template <int MODE>
+__global__ void fp64_peak_kernel(double* out, int iters, double seed) {
+  // 8 independent dependency chains per thread
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    if (MODE == 0) {  // separately rounded multiply then add
+      a0 = __dadd_rn(__dmul_rn(a0, m), c); a1 = __dadd_rn(__dmul_rn(a1, m), c);
+      a2 = __dadd_rn(__dmul_rn(a2, m), c); a3 = __dadd_rn(__dmul_rn(a3, m), c);
+      a4 = __dadd_rn(__dmul_rn(a4, m), c); a5 = __dadd_rn(__dmul_rn(a5, m), c);
+      a6 = __dadd_rn(__dmul_rn(a6, m), c); a7 = __dadd_rn(__dmul_rn(a7, m), c);
+    } else {
+      a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+      a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+__global__ void l2_read_kernel(const double2* __restrict__ buf, size_t n16, int reps, double* out) {
+  double acc = 0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (int r = 0; r < reps; ++r)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+      double2 v = __ldcg(buf + i);  // L2-cached, bypass L1
+      acc += v.x + v.y;
+    }
+  if (acc == 123.456) out[0] = acc;
+}
+}  // namespace
+
+extern "C" int fclgpu_microbench(int device, int kind, double* result) {
+  if (!result) return FCLGPU_ERR_INVALID_ARGUMENT;
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  float ms = 0;
+  if (kind == 0 || kind == 1) {
+    const int block = 256, grid = prop.multiProcessorCount * 8, iters = 20000;
+    double* out;
+    CUDA_TRY(cudaMalloc(&out, sizeof(double) * grid * block));
+    for (int rep = 0; rep < 3; ++rep) {
+      CUDA_TRY(cudaEventRecord(e0));
+      if (kind == 0) fp64_peak_kernel<0><<<grid, block>>>(out, iters, 1.0);
+      else fp64_peak_kernel<1><<<grid, block>>>(out, iters, 1.0);
+      CUDA_TRY(cudaEventRecord(e1));
+      CUDA_TRY(cudaEventSynchronize(e1));
+      CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    }
+    const double ops = (double)grid * block * iters * 8.0 * (kind == 0 ? 2.0 : 1.0);
+    *result = ops / (ms * 1e-3);
+    cudaFree(out);
+  } else if (kind == 2) {
+    const size_t bytes = 32ull << 20;  // 32 MiB: L2 resident
+    double2* buf;
+    double* out;
+    CUDA_TRY(cudaMalloc(&buf, bytes));
+    CUDA_TRY(cudaMalloc(&out, 8));
+    CUDA_TRY(cudaMemset(buf, 0, bytes));
+    const int reps = 50;
+    for (int rep = 0; rep < 3; ++rep) {
+      CUDA_TRY(cudaEventRecord(e0));
+      l2_read_kernel<<<prop.multiProcessorCount * 8, 256>>>(buf, bytes / 16, reps, out);
+      CUDA_TRY(cudaEventRecord(e1));
+      CUDA_TRY(cudaEventSynchronize(e1));
+      CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    }
+    *result = (double)bytes * reps / (ms * 1e-3) / 1e9;
+    cudaFree(buf);
+    cudaFree(out);
+  } else {
+    return fail(FCLGPU_ERR_INVALID_ARGUMENT, "unknown microbench kind %d", kind);
+  }
+  g_launches += 3;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return FCLGPU_OK;
+}

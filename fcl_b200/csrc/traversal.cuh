@@ -1,0 +1,396 @@
+// traversal.cuh — BVTT traversal kernels for BVHModel<OBBRSS<double>> pairs.
+//
+// Reference semantics implemented here (file:line under /root/reference/include/fcl):
+//   collisionRecurse        narrowphase/detail/traversal/traversal_recurse-inl.h:84-130
+//   distanceRecurse         narrowphase/detail/traversal/traversal_recurse-inl.h:259-316
+//   firstOverSecond         narrowphase/detail/traversal/collision/bvh_collision_traversal_node-inl.h:78-90
+//   leaf tests              .../collision/mesh_collision_traversal_node-inl.h:527-620,
+//                           .../distance/mesh_distance_traversal_node-inl.h:453-499, 546-603
+//   relative pose           math/geometry-inl.h:681-682 (collide), mesh_distance_traversal_node-inl.h:630 (distance)
+#pragma once
+#include <cstdint>
+
+#include "../../include/fclgpu.h"
+#include "device_math.cuh"
+
+namespace fclgpu {
+
+// ---------------------------------------------------------------------------------------
+// HBM layout.  Every record is a multiple of 16 bytes and 16-byte aligned,
+// fetched with LDG.128:
+//   obb[i]  16 doubles = 128 B (one cache line): axis[9] row-major, To[3], extent[3], size
+//   rss[i]  16 doubles = 128 B:                  axis[9] row-major, To[3], l[2], r, size
+//   first_child[i] int32  (<0: leaf holding triangle -(fc+1))
+//   tri[t]  10 doubles = 80 B: p1 p2 p3 (de-indexed vertices), pad
+// size = extent.squaredNorm() (OBB::size(), OBB-inl.h:206-209) precomputed at upload.
+// ---------------------------------------------------------------------------------------
+struct DeviceModel {
+  const double* obb;
+  const double* rss;
+  const int32_t* first_child;
+  const double* tri;
+  int32_t n_nodes, n_tris;
+};
+
+constexpr int kNodeDoubles = 16;
+constexpr int kTriDoubles = 10;
+constexpr int kStackCap = 128;  // per-query DFS stack entries; host checks depth1+depth2+2 <= cap
+
+struct NodeRec {
+  M3 axis;
+  V3 To;
+  double e0, e1, e2;  // obb: extent xyz          | rss: l0, l1, r
+  double size;
+};
+
+__device__ __forceinline__ NodeRec load_node(const double* __restrict__ base, int idx) {
+  const double2* p = reinterpret_cast<const double2*>(base + (size_t)idx * kNodeDoubles);
+  double2 v0 = __ldg(p + 0), v1 = __ldg(p + 1), v2 = __ldg(p + 2), v3 = __ldg(p + 3);
+  double2 v4 = __ldg(p + 4), v5 = __ldg(p + 5), v6 = __ldg(p + 6), v7 = __ldg(p + 7);
+  NodeRec n;
+  n.axis.m[0] = v0.x; n.axis.m[1] = v0.y; n.axis.m[2] = v1.x; n.axis.m[3] = v1.y;
+  n.axis.m[4] = v2.x; n.axis.m[5] = v2.y; n.axis.m[6] = v3.x; n.axis.m[7] = v3.y;
+  n.axis.m[8] = v4.x;
+  n.To = mk(v4.y, v5.x, v5.y);
+  n.e0 = v6.x; n.e1 = v6.y; n.e2 = v7.x;
+  n.size = v7.y;
+  return n;
+}
+
+__device__ __forceinline__ void load_tri(const double* __restrict__ base, int t, V3 out[3]) {
+  const double2* p = reinterpret_cast<const double2*>(base + (size_t)t * kTriDoubles);
+  double2 v0 = __ldg(p + 0), v1 = __ldg(p + 1), v2 = __ldg(p + 2), v3 = __ldg(p + 3), v4 = __ldg(p + 4);
+  out[0] = mk(v0.x, v0.y, v1.x);
+  out[1] = mk(v1.y, v2.x, v2.y);
+  out[2] = mk(v3.x, v3.y, v4.x);
+}
+
+struct PoseRT {
+  M3 R;
+  V3 t;
+};
+
+__device__ __forceinline__ PoseRT load_pose(const double* __restrict__ tf, long long i) {
+  PoseRT p;
+  if (tf == nullptr) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) p.R.m[k] = (k % 4 == 0) ? 1.0 : 0.0;
+    p.t = mk(0, 0, 0);
+  } else {
+    const double2* q = reinterpret_cast<const double2*>(tf + 12 * i);  // 96 B records, 16-B aligned
+    double2 v0 = __ldg(q + 0), v1 = __ldg(q + 1), v2 = __ldg(q + 2), v3 = __ldg(q + 3), v4 = __ldg(q + 4), v5 = __ldg(q + 5);
+    p.R.m[0] = v0.x; p.R.m[1] = v0.y; p.R.m[2] = v1.x; p.R.m[3] = v1.y; p.R.m[4] = v2.x;
+    p.R.m[5] = v2.y; p.R.m[6] = v3.x; p.R.m[7] = v3.y; p.R.m[8] = v4.x;
+    p.t = mk(v4.y, v5.x, v5.y);
+  }
+  return p;
+}
+
+// warp-aggregated fetch of the next unprocessed query index (persistent lanes)
+__device__ __forceinline__ long long fetch_work(bool need, unsigned long long* counter) {
+  const unsigned mask = __ballot_sync(0xffffffffu, need);
+  if (mask == 0) return -1;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(mask) - 1;
+  unsigned long long base = 0;
+  if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(mask));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return need ? (long long)(base + __popc(mask & ((1u << lane) - 1u))) : -1;
+}
+
+struct CollideParams {
+  DeviceModel m1, m2;
+  const double* tf1;
+  const double* tf2;
+  long long n;
+  long long max_contacts;
+  int enable_contact;
+  int32_t* num_contacts;      // [n]
+  fclgpu_contact* scratch;    // [n * stride] or nullptr
+  long long stride;           // slots per query in scratch
+  uint32_t* n_bv;             // optional
+  uint32_t* n_leaf;           // optional
+  unsigned long long* work_counter;
+  int* status;                // sticky device status (0 ok)
+};
+
+// ---------------------------------------------------------------------------------------
+// Variant T (thread per query, persistent lanes): every lane runs the reference's depth-first
+// recursion for its own query with an explicit stack, so the visiting order, the early stop
+// (canStop) and therefore contact order / truncation are the reference's by construction.
+// Lanes that finish pull the next query with one warp-aggregated atomic.
+// ---------------------------------------------------------------------------------------
+template <bool kStats>
+__global__ void __launch_bounds__(128) collide_thread_kernel(CollideParams P) {
+  uint2 stk[kStackCap];
+  int sp = 0;
+  long long q = -1;
+  PoseRT tf1;
+  M3 R;
+  V3 T;
+  long long count = 0;
+  uint32_t bv_tests = 0, leaf_tests = 0;
+  bool exhausted = false;
+
+  while (true) {
+    // ---- refill idle lanes ----
+    const bool need = (sp == 0) && !exhausted;
+    if (need && q >= 0) {  // retire the finished query
+      P.num_contacts[q] = (int32_t)count;
+      if (kStats) {
+        if (P.n_bv) P.n_bv[q] = bv_tests;
+        if (P.n_leaf) P.n_leaf[q] = leaf_tests;
+      }
+      q = -1;
+    }
+    const long long nq = fetch_work(need, P.work_counter);
+    if (need) {
+      if (nq < P.n) {
+        q = nq;
+        tf1 = load_pose(P.tf1, q);
+        const PoseRT tf2 = load_pose(P.tf2, q);
+        R = mulTM(tf1.R, tf2.R);                    // R1^T R2
+        T = mulTv(tf1.R, tf2.t - tf1.t);            // R1^T (t2 - t1)
+        count = 0;
+        bv_tests = leaf_tests = 0;
+        stk[0] = make_uint2(0u, 0u);
+        sp = 1;
+      } else {
+        exhausted = true;
+      }
+    }
+    if (__all_sync(0xffffffffu, exhausted && sp == 0)) break;
+    if (sp == 0) continue;
+
+    // ---- one BVTT node ----
+    const uint2 e = stk[--sp];
+    const int b1 = (int)e.x, b2 = (int)e.y;
+    const NodeRec n1 = load_node(P.m1.obb, b1);
+    const NodeRec n2 = load_node(P.m2.obb, b2);
+    const int fc1 = __ldg(P.m1.first_child + b1);
+    const int fc2 = __ldg(P.m2.first_child + b2);
+    if (kStats) bv_tests++;
+    if (obb_pair_disjoint(R, T, n1.axis, n1.To, mk(n1.e0, n1.e1, n1.e2), n2.axis, n2.To, mk(n2.e0, n2.e1, n2.e2)))
+      continue;
+    const bool l1 = fc1 < 0, l2 = fc2 < 0;
+    if (l1 && l2) {
+      if (kStats) leaf_tests++;
+      const int id1 = -(fc1 + 1), id2 = -(fc2 + 1);
+      V3 Pt[3], Qt[3];
+      load_tri(P.m1.tri, id1, Pt);
+      load_tri(P.m2.tri, id2, Qt);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) Qt[k] = mulv(R, Qt[k]) + T;
+      if (tri_intersect(Pt[0], Pt[1], Pt[2], Qt[0], Qt[1], Qt[2])) {
+        if (!P.enable_contact) {
+          if (count < P.max_contacts) {
+            if (P.scratch) {
+              if (count < P.stride) {
+                fclgpu_contact* c = P.scratch + q * P.stride + count;
+                c->b1 = id1;
+                c->b2 = id2;
+              } else {
+                atomicMin(P.status, (int)FCLGPU_ERR_CONTACT_OVERFLOW);
+              }
+            }
+            count++;
+          }
+        } else {
+          V3 cp[2], nrm;
+          unsigned nc;
+          double depth;
+          tri_contact_info(Pt, Qt, cp, nc, depth, nrm);
+          if (P.max_contacts < count + (long long)nc)
+            nc = (P.max_contacts > count) ? (unsigned)(P.max_contacts - count) : 0u;
+          for (unsigned k = 0; k < nc; ++k) {
+            if (P.scratch) {
+              if (count < P.stride) {
+                fclgpu_contact* c = P.scratch + q * P.stride + count;
+                const V3 pw = mulv(tf1.R, cp[k]) + tf1.t;  // tf1 * p
+                const V3 nw = mulv(tf1.R, nrm);            // tf1.linear() * n
+                c->b1 = id1;
+                c->b2 = id2;
+                c->normal[0] = nw.x; c->normal[1] = nw.y; c->normal[2] = nw.z;
+                c->pos[0] = pw.x; c->pos[1] = pw.y; c->pos[2] = pw.z;
+                c->penetration_depth = depth;
+              } else {
+                atomicMin(P.status, (int)FCLGPU_ERR_CONTACT_OVERFLOW);
+              }
+            }
+            count++;
+          }
+        }
+        // canStop(): isCollision && num_max_contacts <= numContacts -> every pending sibling is skipped
+        if (count > 0 && P.max_contacts <= count) sp = 0;
+      }
+      continue;
+    }
+    // firstOverSecond: descend model1 iff l2 || (!l1 && size1 > size2)
+    uint2 left, right;
+    if (l2 || (!l1 && (n1.size > n2.size))) {
+      left = make_uint2((unsigned)fc1, (unsigned)b2);
+      right = make_uint2((unsigned)fc1 + 1u, (unsigned)b2);
+    } else {
+      left = make_uint2((unsigned)b1, (unsigned)fc2);
+      right = make_uint2((unsigned)b1, (unsigned)fc2 + 1u);
+    }
+    if (sp + 2 > kStackCap) {
+      atomicMin(P.status, (int)FCLGPU_ERR_STACK_OVERFLOW);
+      sp = 0;
+      continue;
+    }
+    stk[sp++] = right;
+    stk[sp++] = left;
+  }
+}
+
+struct DistanceParams {
+  DeviceModel m1, m2;
+  const double* tf1;
+  const double* tf2;
+  long long n;
+  int enable_nearest_points;
+  double* min_distance;
+  double* p1;
+  double* p2;
+  int32_t* b1;
+  int32_t* b2;
+  uint32_t* n_bv;
+  uint32_t* n_leaf;
+  unsigned long long* work_counter;
+  int* status;
+};
+
+struct DistState {
+  double min_d;
+  V3 p1, p2;
+  int b1, b2;
+};
+
+__device__ __forceinline__ void dist_leaf(const DeviceModel& m1, const DeviceModel& m2, const M3& R, const V3& T,
+                                          int id1, int id2, DistState& s) {
+  V3 S[3], Tt[3];
+  load_tri(m1.tri, id1, S);
+  load_tri(m2.tri, id2, Tt);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) Tt[k] = mulv(R, Tt[k]) + T;  // tf * p
+  V3 Pn, Qn;
+  const double d = tri_distance(S, Tt, Pn, Qn);
+  if (s.min_d > d) {  // DistanceResult::update keeps strictly smaller (distance_result-inl.h:66-103)
+    s.min_d = d;
+    s.b1 = id1;
+    s.b2 = id2;
+    s.p1 = Pn;
+    s.p2 = Qn;
+  }
+}
+
+template <bool kStats>
+__global__ void __launch_bounds__(128) distance_thread_kernel(DistanceParams P) {
+  uint2 stk[kStackCap];
+  double stk_d[kStackCap];
+  int sp = 0;
+  long long q = -1;
+  PoseRT tf1;
+  M3 R;
+  V3 T;
+  DistState s;
+  uint32_t bv_tests = 0, leaf_tests = 0;
+  bool exhausted = false;
+
+  while (true) {
+    const bool need = (sp == 0) && !exhausted;
+    if (need && q >= 0) {
+      // postprocess: nearest points (model1 frame) -> world with tf1
+      if (P.min_distance) P.min_distance[q] = s.min_d;
+      if (P.b1) P.b1[q] = s.b1;
+      if (P.b2) P.b2[q] = s.b2;
+      if (P.enable_nearest_points) {
+        const V3 w1 = mulv(tf1.R, s.p1) + tf1.t, w2 = mulv(tf1.R, s.p2) + tf1.t;
+        if (P.p1) { P.p1[3 * q] = w1.x; P.p1[3 * q + 1] = w1.y; P.p1[3 * q + 2] = w1.z; }
+        if (P.p2) { P.p2[3 * q] = w2.x; P.p2[3 * q + 1] = w2.y; P.p2[3 * q + 2] = w2.z; }
+      }
+      if (kStats) {
+        if (P.n_bv) P.n_bv[q] = bv_tests;
+        if (P.n_leaf) P.n_leaf[q] = leaf_tests;
+      }
+      q = -1;
+    }
+    const long long nq = fetch_work(need, P.work_counter);
+    if (need) {
+      if (nq < P.n) {
+        q = nq;
+        tf1 = load_pose(P.tf1, q);
+        const PoseRT tf2 = load_pose(P.tf2, q);
+        // tf = tf1.inverse(Isometry) * tf2: linear R1^T R2, translation R1^T t2 + (-(R1^T t1))
+        R = mulTM(tf1.R, tf2.R);
+        const V3 it = mulTv(tf1.R, tf1.t);
+        T = mulTv(tf1.R, tf2.t) + mk(-it.x, -it.y, -it.z);
+        s.min_d = 1.7976931348623157e308;
+        s.b1 = s.b2 = -1;
+        s.p1 = s.p2 = mk(0, 0, 0);
+        bv_tests = leaf_tests = 0;
+        dist_leaf(P.m1, P.m2, R, T, 0, 0, s);  // preprocess: seed with triangle 0 / triangle 0
+        stk[0] = make_uint2(0u, 0u);
+        stk_d[0] = -1.0;  // the root pair is never bound-tested
+        sp = 1;
+      } else {
+        exhausted = true;
+      }
+    }
+    if (__all_sync(0xffffffffu, exhausted && sp == 0)) break;
+    if (sp == 0) continue;
+
+    --sp;
+    const uint2 e = stk[sp];
+    const double bound = stk_d[sp];
+    if (bound >= s.min_d) continue;  // canStop(c) with rel_err = abs_err = 0
+    const int b1 = (int)e.x, b2 = (int)e.y;
+    const int fc1 = __ldg(P.m1.first_child + b1);
+    const int fc2 = __ldg(P.m2.first_child + b2);
+    const bool l1 = fc1 < 0, l2 = fc2 < 0;
+    if (l1 && l2) {
+      if (kStats) leaf_tests++;
+      dist_leaf(P.m1, P.m2, R, T, -(fc1 + 1), -(fc2 + 1), s);
+      continue;
+    }
+    // firstOverSecond needs both sizes (OBB extents' squared norm, stored in the rss record too)
+    const double size1 = __ldg(P.m1.rss + (size_t)b1 * kNodeDoubles + 15);
+    const double size2 = __ldg(P.m2.rss + (size_t)b2 * kNodeDoubles + 15);
+    int a1, a2, c1, c2;
+    if (l2 || (!l1 && (size1 > size2))) {
+      a1 = fc1; a2 = b2; c1 = fc1 + 1; c2 = b2;
+    } else {
+      a1 = b1; a2 = fc2; c1 = b1; c2 = fc2 + 1;
+    }
+    double d1, d2;
+    {
+      const NodeRec na1 = load_node(P.m1.rss, a1);
+      const NodeRec na2 = load_node(P.m2.rss, a2);
+      const double la[2] = {na1.e0, na1.e1}, lb[2] = {na2.e0, na2.e1};
+      d1 = rss_pair_distance(R, T, na1.axis, na1.To, la, na1.e2, na2.axis, na2.To, lb, na2.e2);
+    }
+    {
+      const NodeRec nc1 = load_node(P.m1.rss, c1);
+      const NodeRec nc2 = load_node(P.m2.rss, c2);
+      const double la[2] = {nc1.e0, nc1.e1}, lb[2] = {nc2.e0, nc2.e1};
+      d2 = rss_pair_distance(R, T, nc1.axis, nc1.To, la, nc1.e2, nc2.axis, nc2.To, lb, nc2.e2);
+    }
+    if (kStats) bv_tests += 2;
+    if (sp + 2 > kStackCap) {
+      atomicMin(P.status, (int)FCLGPU_ERR_STACK_OVERFLOW);
+      sp = 0;
+      continue;
+    }
+    // visit the nearer child first: it goes on top of the stack
+    if (d2 < d1) {
+      stk[sp] = make_uint2((unsigned)a1, (unsigned)a2); stk_d[sp] = d1; ++sp;
+      stk[sp] = make_uint2((unsigned)c1, (unsigned)c2); stk_d[sp] = d2; ++sp;
+    } else {
+      stk[sp] = make_uint2((unsigned)c1, (unsigned)c2); stk_d[sp] = d2; ++sp;
+      stk[sp] = make_uint2((unsigned)a1, (unsigned)a2); stk_d[sp] = d1; ++sp;
+    }
+  }
+}
+
+}  // namespace fclgpu

@@ -1,0 +1,198 @@
+/* fclgpu.h — C ABI of the B200-native batched BVHModel<OBBRSS<double>> mesh-mesh
+ * collide()/distance() path.
+ *
+ * This is the drop-in boundary for ONE cell of the reference's dispatch tables:
+ *   collision_matrix[BV_OBBRSS][BV_OBBRSS]  (include/fcl/narrowphase/detail/collision_func_matrix-inl.h:851)
+ *   distance_matrix [BV_OBBRSS][BV_OBBRSS]  (include/fcl/narrowphase/detail/distance_func_matrix-inl.h:663)
+ * evaluated over a batch of pose pairs.  All citations are relative to the
+ * reference tree (flexible-collision-library/fcl).
+ *
+ * Conventions
+ *  - plain C types, caller-owned buffers, no exceptions; every entry point
+ *    returns an int status (0 = ok, negative = error, see fclgpu_status).
+ *  - a pose ("tf") is 12 doubles: rotation R row-major (9) then translation t (3),
+ *    p_world = R p + t.  (The reference's Transform3d is a 4x4 column-major
+ *    Eigen::Isometry, include/fcl/common/types.h:70-92; fclgpu_pose_from_colmajor4x4
+ *    converts.)  A NULL tf array means identity for every query.
+ *  - *_batch entry points take DEVICE pointers (memory resident on the model's
+ *    device) and enqueue on `stream` (a cudaStream_t passed as void*; NULL = the
+ *    legacy default stream) without synchronising.
+ *  - *_batch_host entry points take HOST pointers, stage through pinned memory,
+ *    copy, launch, copy back and return when the results are in the caller's
+ *    buffers (this is what a single fcl::collide()/fcl::distance() call maps to).
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point
+ *    fails with FCLGPU_ERR_NO_DEVICE.
+ */
+#ifndef FCLGPU_H_
+#define FCLGPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FCLGPU_ABI_VERSION 1
+
+/* Status codes.  -1..-8 mirror the reference's BVHReturnCode
+ * (include/fcl/geometry/bvh/BVH_internal.h:61-72). */
+typedef enum fclgpu_status {
+  FCLGPU_OK = 0,
+  FCLGPU_ERR_MODEL_OUT_OF_MEMORY = -1,
+  FCLGPU_ERR_BUILD_OUT_OF_SEQUENCE = -2,
+  FCLGPU_ERR_BUILD_EMPTY_MODEL = -3,
+  FCLGPU_ERR_BUILD_EMPTY_PREVIOUS_FRAME = -4,
+  FCLGPU_ERR_UNSUPPORTED_FUNCTION = -5,
+  FCLGPU_ERR_UNUPDATED_MODEL = -6,
+  FCLGPU_ERR_INCORRECT_DATA = -7,
+  FCLGPU_ERR_UNKNOWN = -8,
+  FCLGPU_ERR_INVALID_ARGUMENT = -20,
+  FCLGPU_ERR_NO_DEVICE = -21,
+  FCLGPU_ERR_CUDA = -22,
+  FCLGPU_ERR_CONTACT_OVERFLOW = -23, /* per-pose or pool capacity too small; counts are still exact */
+  FCLGPU_ERR_STACK_OVERFLOW = -24    /* traversal stack exhausted (tree deeper than supported) */
+} fclgpu_status;
+
+/* Split rules of the reference's BVSplitter (include/fcl/geometry/bvh/detail/BV_splitter.h). */
+typedef enum fclgpu_split_method {
+  FCLGPU_SPLIT_METHOD_MEAN = 0,
+  FCLGPU_SPLIT_METHOD_MEDIAN = 1,
+  FCLGPU_SPLIT_METHOD_BV_CENTER = 2
+} fclgpu_split_method;
+
+/* One contact; field meaning as fcl::Contact<double> (include/fcl/narrowphase/contact.h:48-91)
+ * with b1/b2 = triangle ids in model1/model2.  In binary mode (enable_contact == 0) only
+ * b1/b2 are defined, as in the reference.  64 bytes. */
+typedef struct fclgpu_contact {
+  int32_t b1, b2;
+  double normal[3];
+  double pos[3];
+  double penetration_depth;
+} fclgpu_contact;
+
+/* Honoured fields of fcl::CollisionRequest (include/fcl/narrowphase/collision_request.h:52-106).
+ * enable_cost must be 0 (cost sources are not on this path: FCLGPU_ERR_UNSUPPORTED_FUNCTION). */
+typedef struct fclgpu_collision_request {
+  int64_t num_max_contacts; /* default 1; 0 -> every query returns 0 contacts (collision-inl.h:111-115) */
+  int32_t enable_contact;   /* default 0 */
+  int32_t enable_cost;      /* must be 0 */
+} fclgpu_collision_request;
+
+/* Honoured fields of fcl::DistanceRequest (include/fcl/narrowphase/distance_request.h:52-113).
+ * rel_err / abs_err are accepted for source compatibility and ignored, exactly as the
+ * reference does on this path (mesh_distance_traversal_node-inl.h:96-105 vs :606-633). */
+typedef struct fclgpu_distance_request {
+  int32_t enable_nearest_points;
+  int32_t enable_signed_distance; /* no effect for meshes (triDistance >= 0) */
+  double rel_err, abs_err;        /* ignored */
+} fclgpu_distance_request;
+
+/* ---------------------------------------------------------------------------------------
+ * Host-side BVH construction: BVHModel<OBBRSS<double>>::beginModel/addSubModel/endModel
+ * (include/fcl/geometry/bvh/BVH_model-inl.h:207-253, 383-517, 833-938) with
+ * FitImpl<OBBRSS> (detail/BV_fitter-inl.h:449-477) and BVSplitter (detail/BV_splitter-inl.h).
+ * The result is the flattened node tree the upload step consumes.
+ * ------------------------------------------------------------------------------------- */
+typedef struct fclgpu_bvh fclgpu_bvh; /* host object */
+
+int fclgpu_bvh_build_obbrss(const double* vertices /* nv x 3 */, int32_t num_vertices,
+                            const int32_t* triangles /* nt x 3 */, int32_t num_tris,
+                            int32_t split_method, fclgpu_bvh** out);
+void fclgpu_bvh_destroy(fclgpu_bvh* bvh);
+int32_t fclgpu_bvh_num_nodes(const fclgpu_bvh* bvh);
+int32_t fclgpu_bvh_num_tris(const fclgpu_bvh* bvh);
+/* Copies the node arrays out (any pointer may be NULL).  axis9 is row-major: axis9[3*r+c],
+ * column c = c-th box axis.  tri_verts9 = de-indexed triangle vertices (p1 p2 p3). */
+int fclgpu_bvh_get(const fclgpu_bvh* bvh, int32_t* first_child, double* axis9, double* obb_To3,
+                   double* obb_extent3, double* rss_To3, double* rss_l2, double* rss_r,
+                   double* tri_verts9);
+
+/* ---------------------------------------------------------------------------------------
+ * Upload: flattens BVNode<OBBRSS<double>>[] (include/fcl/geometry/bvh/BV_node.h:50-72,
+ * BVH_model.h:160-203) + triangles into device records ("HBM layout").
+ * The arrays are exactly what a BVHModel<OBBRSS<double>> holds: getBV(i).first_child,
+ * .bv.obb.{axis,To,extent}, .bv.rss.{To,l,r} (rss.axis == obb.axis by construction,
+ * BV_fitter-inl.h:464) and vertices[tri_indices[t][k]].
+ * ------------------------------------------------------------------------------------- */
+typedef struct fclgpu_model fclgpu_model; /* device-resident model */
+
+int fclgpu_model_create_obbrss(int device, int32_t n_nodes, const int32_t* first_child,
+                               const double* axis9, const double* obb_To3, const double* obb_extent3,
+                               const double* rss_To3, const double* rss_l2, const double* rss_r,
+                               int32_t n_tris, const double* tri_verts9, fclgpu_model** out);
+int fclgpu_model_from_bvh(int device, const fclgpu_bvh* bvh, fclgpu_model** out);
+int fclgpu_model_destroy(fclgpu_model* m);
+int32_t fclgpu_model_num_nodes(const fclgpu_model* m);
+int32_t fclgpu_model_num_tris(const fclgpu_model* m);
+int fclgpu_model_device(const fclgpu_model* m);
+
+/* ---------------------------------------------------------------------------------------
+ * Batched collide: query i evaluates fcl::collide(m1, tf1[i], m2, tf2[i], request, result_i)
+ * with a fresh result_i (collision-inl.h:95-207 -> orientedMeshCollide,
+ * collision_func_matrix-inl.h:571-590).
+ *   num_contacts[i]  = result_i.numContacts()
+ *   contacts         : query i's contacts, in the reference's DFS order, at
+ *                      contacts[contact_offsets[i] .. contact_offsets[i+1]) (compacted).
+ *   contact_offsets  : n+1 entries (exclusive prefix sum of num_contacts); may be NULL
+ *                      together with contacts when only counts/verdicts are wanted.
+ *   contact_capacity : slots available in `contacts`.
+ *   n_bv / n_leaf    : optional per-query counters (num_bv_tests / num_leaf_tests of the
+ *                      reference's traversal node, bvh_collision_traversal_node.h:92-94).
+ * ------------------------------------------------------------------------------------- */
+int fclgpu_collide_batch(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n,
+                         const double* tf1, const double* tf2,
+                         const fclgpu_collision_request* request, int32_t* num_contacts,
+                         fclgpu_contact* contacts, int64_t contact_capacity,
+                         int64_t* contact_offsets, uint32_t* n_bv, uint32_t* n_leaf, void* stream);
+
+int fclgpu_collide_batch_host(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n,
+                              const double* tf1, const double* tf2,
+                              const fclgpu_collision_request* request, int32_t* num_contacts,
+                              fclgpu_contact* contacts, int64_t contact_capacity,
+                              int64_t* contact_offsets, uint32_t* n_bv, uint32_t* n_leaf);
+
+/* ---------------------------------------------------------------------------------------
+ * Batched distance: query i evaluates fcl::distance(m1, tf1[i], m2, tf2[i], request, result_i)
+ * (distance-inl.h:92-246 -> orientedMeshDistance, distance_func_matrix-inl.h:386-403;
+ * recursive traversal, qsize = 2, traversal/collision_node.h:67).
+ *   min_distance[i]; nearest_p1/p2 (n x 3, world frame, only written when
+ *   enable_nearest_points); b1/b2 = closest triangle ids.  Any output may be NULL.
+ * ------------------------------------------------------------------------------------- */
+int fclgpu_distance_batch(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n,
+                          const double* tf1, const double* tf2,
+                          const fclgpu_distance_request* request, double* min_distance,
+                          double* nearest_p1, double* nearest_p2, int32_t* b1, int32_t* b2,
+                          uint32_t* n_bv, uint32_t* n_leaf, void* stream);
+
+int fclgpu_distance_batch_host(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n,
+                               const double* tf1, const double* tf2,
+                               const fclgpu_distance_request* request, double* min_distance,
+                               double* nearest_p1, double* nearest_p2, int32_t* b1, int32_t* b2,
+                               uint32_t* n_bv, uint32_t* n_leaf);
+
+/* ---------------------------------------------------------------------------------------
+ * Utilities
+ * ------------------------------------------------------------------------------------- */
+int fclgpu_abi_version(void);
+int fclgpu_device_count(void);
+const char* fclgpu_last_error(void); /* thread-local, human readable */
+/* Eigen::Transform<double,3,Isometry> (4x4 column-major, 16 doubles) -> 12-double pose */
+void fclgpu_pose_from_colmajor4x4(const double* m16, double* pose12);
+/* The *_batch entry points are asynchronous; errors detected on the device (contact
+ * capacity, traversal stack) are sticky.  This synchronises `stream` and returns and clears
+ * that status. */
+int fclgpu_sync_status(int device, void* stream);
+/* Tuning knob: select the traversal kernel variant (0 = default).  See DESIGN.md. */
+int fclgpu_set_option(const char* name, int64_t value);
+int64_t fclgpu_get_option(const char* name);
+/* Kernel launches issued by this library since process start (bench.py's gpu_launches). */
+int64_t fclgpu_launch_count(void);
+/* FP64 pipe / L2 micro-benchmarks used for the roofline denominators:
+ * kind 0: unfused DMUL+DADD ops/s, 1: DFMA ops/s (counted as 1 op), 2: L2-resident read GB/s */
+int fclgpu_microbench(int device, int kind, double* result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FCLGPU_H_ */

@@ -1,0 +1,60 @@
+// Test-only: compiles the product's device math header for the HOST so that the CPU test
+// suite can compare it bit-for-bit with the oracle without a GPU.  Not part of the product.
+#include "../../fcl_b200/csrc/device_math.cuh"
+using namespace fclgpu;
+
+static M3 m3(const double* r) { M3 M; for (int i = 0; i < 9; ++i) M.m[i] = r[i]; return M; }
+static V3 v3(const double* v) { return mk(v[0], v[1], v[2]); }
+
+extern "C" {
+int hm_obb_disjoint(const double* B9, const double* T3, const double* a3, const double* b3) {
+  return obb_disjoint(m3(B9), v3(T3), v3(a3), v3(b3)) ? 1 : 0;
+}
+double hm_rect_distance(const double* R9, const double* T3, const double* a2, const double* b2) {
+  return rect_distance(m3(R9), v3(T3), a2, b2);
+}
+// n pairs: nodes given as arrays; idx1/idx2 select nodes; R0/T0 per pair (12 doubles)
+void hm_obb_pairs(long long n, const double* pose12, const int* idx1, const int* idx2,
+                  const double* axis1, const double* To1, const double* ext1,
+                  const double* axis2, const double* To2, const double* ext2, int* out) {
+  for (long long k = 0; k < n; ++k) {
+    int i = idx1[k], j = idx2[k];
+    out[k] = obb_pair_disjoint(m3(pose12 + 12 * k), v3(pose12 + 12 * k + 9), m3(axis1 + 9 * i), v3(To1 + 3 * i),
+                               v3(ext1 + 3 * i), m3(axis2 + 9 * j), v3(To2 + 3 * j), v3(ext2 + 3 * j));
+  }
+}
+void hm_rss_pairs(long long n, const double* pose12, const int* idx1, const int* idx2,
+                  const double* axis1, const double* To1, const double* l1, const double* r1,
+                  const double* axis2, const double* To2, const double* l2, const double* r2, double* out) {
+  for (long long k = 0; k < n; ++k) {
+    int i = idx1[k], j = idx2[k];
+    out[k] = rss_pair_distance(m3(pose12 + 12 * k), v3(pose12 + 12 * k + 9), m3(axis1 + 9 * i), v3(To1 + 3 * i),
+                               l1 + 2 * i, r1[i], m3(axis2 + 9 * j), v3(To2 + 3 * j), l2 + 2 * j, r2[j]);
+  }
+}
+// triangles: P9/Q9 per pair, pose per pair (Q' = R Q + T done here like the kernels do)
+int hm_tri_intersect(const double* P9, const double* Q9, const double* pose12, int want, unsigned* nc,
+                     double* contacts6, double* depth, double* normal3) {
+  M3 R = m3(pose12); V3 T = v3(pose12 + 9);
+  V3 P[3] = {v3(P9), v3(P9 + 3), v3(P9 + 6)};
+  V3 Q[3] = {mulv(R, v3(Q9)) + T, mulv(R, v3(Q9 + 3)) + T, mulv(R, v3(Q9 + 6)) + T};
+  bool hit = tri_intersect(P[0], P[1], P[2], Q[0], Q[1], Q[2]);
+  if (hit && want) {
+    V3 c[2]; unsigned n; double d; V3 nrm;
+    tri_contact_info(P, Q, c, n, d, nrm);
+    *nc = n; *depth = d;
+    contacts6[0] = c[0].x; contacts6[1] = c[0].y; contacts6[2] = c[0].z;
+    contacts6[3] = c[1].x; contacts6[4] = c[1].y; contacts6[5] = c[1].z;
+    normal3[0] = nrm.x; normal3[1] = nrm.y; normal3[2] = nrm.z;
+  }
+  return hit ? 1 : 0;
+}
+double hm_tri_distance(const double* S9, const double* T9, double* P3, double* Q3) {
+  V3 S[3] = {v3(S9), v3(S9 + 3), v3(S9 + 6)};
+  V3 T[3] = {v3(T9), v3(T9 + 3), v3(T9 + 6)};
+  V3 P = mk(0, 0, 0), Q = mk(0, 0, 0);
+  double d = tri_distance(S, T, P, Q);
+  P3[0] = P.x; P3[1] = P.y; P3[2] = P.z; Q3[0] = Q.x; Q3[1] = Q.y; Q3[2] = Q.z;
+  return d;
+}
+}

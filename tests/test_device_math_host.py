@@ -1,0 +1,142 @@
+"""The product's device math header, compiled for the host, must agree with the oracle
+bit for bit (CPU only; the same header is what the CUDA kernels inline)."""
+import ctypes as C
+import shutil
+
+import numpy as np
+import pytest
+
+from fcl_b200.poses import random_poses
+
+pytestmark = pytest.mark.skipif(shutil.which("nvcc") is None, reason="nvcc not available")
+
+
+@pytest.fixture(scope="module")
+def hm():
+    from tests import hostcheck
+
+    return hostcheck
+
+
+def _rel_pose(P):
+    """(R, T) of identity model2 in posed model1's frame, same arithmetic as collide setup."""
+    n = len(P)
+    R1 = P[:, :9].reshape(n, 3, 3)
+    t1 = P[:, 9:]
+    out = np.empty((n, 12))
+    out[:, :9] = np.transpose(R1, (0, 2, 1)).reshape(n, 9)  # R1^T * I
+    d = 0.0 - t1
+    RT = np.transpose(R1, (0, 2, 1))
+    out[:, 9:] = np.stack([(RT[:, i, 0] * d[:, 0] + RT[:, i, 1] * d[:, 1]) + RT[:, i, 2] * d[:, 2] for i in range(3)], 1)
+    return out
+
+
+def test_obb_and_rss_pairs_match_oracle(hm, oracle, oracle_env_rob):
+    env, rob = oracle_env_rob
+    a1, a2 = env.arrays(), rob.arrays()
+    rng = np.random.default_rng(11)
+    n = 200000
+    rel = _rel_pose(random_poses(n, seed=9))
+    # bias towards deep nodes being near each other: also shrink translations for half of them
+    rel[: n // 2, 9:] *= rng.uniform(0, 0.3, size=(n // 2, 1))
+    i1 = rng.integers(0, env.num_bvs, n).astype(np.int32)
+    i2 = rng.integers(0, rob.num_bvs, n).astype(np.int32)
+    got = np.empty(n, np.int32)
+    L = hm.lib()
+    L.hm_obb_pairs(n, hm.dptr(rel), hm.iptr(i1), hm.iptr(i2), hm.dptr(a1["axis"]), hm.dptr(a1["obb_To"]),
+                   hm.dptr(a1["obb_ext"]), hm.dptr(a2["axis"]), hm.dptr(a2["obb_To"]), hm.dptr(a2["obb_ext"]), hm.iptr(got))
+    dist = np.empty(n)
+    L.hm_rss_pairs(n, hm.dptr(rel), hm.iptr(i1), hm.iptr(i2), hm.dptr(a1["axis"]), hm.dptr(a1["rss_To"]),
+                   hm.dptr(a1["rss_l"]), hm.dptr(a1["rss_r"]), hm.dptr(a2["axis"]), hm.dptr(a2["rss_To"]),
+                   hm.dptr(a2["rss_l"]), hm.dptr(a2["rss_r"]), hm.dptr(dist))
+    step = 7
+    n_dis = 0
+    n_pos = 0
+    for k in range(0, n, step):
+        R0, T0 = rel[k, :9], rel[k, 9:]
+        i, j = i1[k], i2[k]
+        ov = oracle.obb_overlap(R0, T0, a1["axis"][i], a1["obb_To"][i], a1["obb_ext"][i], a2["axis"][j], a2["obb_To"][j], a2["obb_ext"][j])
+        assert bool(got[k]) == (not ov)
+        n_dis += got[k]
+        d = oracle.rss_distance(R0, T0, a1["axis"][i], a1["rss_To"][i], a1["rss_l"][i], a1["rss_r"][i],
+                                a2["axis"][j], a2["rss_To"][j], a2["rss_l"][j], a2["rss_r"][j])
+        assert d == dist[k], (k, d, dist[k])
+        n_pos += d > 0
+    assert 0 < n_dis < n // step and n_pos > 100
+
+
+def test_rect_distance_random_configs_match_oracle(hm, oracle):
+    """Synthetic rectangles in general position exercise all 16 edge cases + the face fallback."""
+    rng = np.random.default_rng(5)
+    from fcl_b200.poses import euler_to_matrix
+
+    L = hm.lib()
+    n = 60000
+    ang = rng.uniform(0, 2 * np.pi, size=(n, 3))
+    # a third of the rotations nearly axis aligned (exercises the 1e-7 parallel thresholds)
+    ang[: n // 3] = np.round(ang[: n // 3] / (np.pi / 2)) * (np.pi / 2) + rng.normal(0, 1e-8, size=(n // 3, 3))
+    R = euler_to_matrix(ang[:, 0], ang[:, 1], ang[:, 2]).reshape(n, 9)
+    T = rng.uniform(-3, 3, size=(n, 3))
+    a = rng.uniform(0, 2, size=(n, 2))
+    b = rng.uniform(0, 2, size=(n, 2))
+    a[::17] = 0.0  # degenerate (segment / point) rectangles
+    vals = set()
+    for k in range(n):
+        g = L.hm_rect_distance(hm.dptr(R[k]), hm.dptr(T[k]), hm.dptr(a[k]), hm.dptr(b[k]))
+        o = oracle.rect_distance(R[k], T[k], a[k], b[k])
+        assert g == o, (k, g, o)
+        vals.add(g > 0)
+    assert vals == {True, False}
+
+
+def _tri_pairs(rng, n, spread):
+    P = rng.normal(0, 1, size=(n, 3, 3))
+    Q = rng.normal(0, 1, size=(n, 3, 3)) + rng.normal(0, spread, size=(n, 1, 3))
+    return P.reshape(n, 9), Q.reshape(n, 9)
+
+
+def test_tri_intersect_and_contacts_match_oracle(hm, oracle):
+    rng = np.random.default_rng(3)
+    L = hm.lib()
+    n = 40000
+    P, Q = _tri_pairs(rng, n, 0.8)
+    # shared-vertex / coplanar cases (touching counts as intersecting)
+    Q[:2000, :3] = P[:2000, :3]
+    Q[2000:3000, 2::3] = 0.0
+    P[2000:3000, 2::3] = 0.0
+    poses = random_poses(n, seed=21)
+    poses[:, 9:] *= 1e-4
+    poses[: n // 2, :9] = np.eye(3).reshape(9)
+    hits = 0
+    for k in range(n):
+        nc = C.c_uint32(0)
+        c6, dep, nrm = np.zeros(6), np.zeros(1), np.zeros(3)
+        g = L.hm_tri_intersect(hm.dptr(P[k]), hm.dptr(Q[k]), hm.dptr(poses[k]), 1, C.byref(nc), hm.dptr(c6), hm.dptr(dep), hm.dptr(nrm))
+        o = oracle.tri_intersect(P[k], Q[k], poses[k, :9], poses[k, 9:], want_contacts=True)
+        assert bool(g) == o[0]
+        if g:
+            hits += 1
+            assert nc.value == o[1]
+            assert dep[0] == o[3]
+            assert nrm.tobytes() == o[4].tobytes()
+            assert c6[: 3 * nc.value].tobytes() == o[2].reshape(-1)[: 3 * nc.value].tobytes()
+    assert n // 20 < hits < n
+
+
+def test_tri_distance_matches_oracle(hm, oracle):
+    rng = np.random.default_rng(4)
+    L = hm.lib()
+    n = 40000
+    S, T = _tri_pairs(rng, n, 2.5)
+    T[:1500, :3] = S[:1500, :3]          # shared vertex
+    S[1500:2500, 3:6] = S[1500:2500, :3]  # degenerate (zero-length edge -> NaN guards)
+    T[2500:3500] = S[2500:3500] + np.tile(rng.normal(0, 2, size=(1000, 1, 3)), (1, 3, 1)).reshape(1000, 9)  # parallel
+    zero = 0
+    for k in range(n):
+        Pg, Qg = np.zeros(3), np.zeros(3)
+        g = L.hm_tri_distance(hm.dptr(S[k]), hm.dptr(T[k]), hm.dptr(Pg), hm.dptr(Qg))
+        o, Po, Qo = oracle.tri_distance(S[k], T[k])
+        assert g == o or (np.isnan(g) and np.isnan(o)), (k, g, o)
+        assert Pg.tobytes() == Po.tobytes() and Qg.tobytes() == Qo.tobytes(), k
+        zero += g == 0
+    assert 0 < zero < n

@@ -1,0 +1,257 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on
+the same seeded inputs.  Bit-exact for verdicts, contact lists (ids, positions, normals, depths,
+in the reference's DFS order) and minimum distances; nearest points / closest ids are exact for
+the thread-per-query traversal and within 1e-6 relative for the warp-front traversal."""
+import numpy as np
+import pytest
+
+import fcl_b200 as F
+from fcl_b200 import _capi
+from fcl_b200.poses import identity_poses, random_poses
+from tests.meshes import box_mesh, random_soup, uv_sphere
+
+pytestmark = pytest.mark.gpu
+
+INT_MAX = 2**31 - 1
+REL_TOL = 1e-6  # north_star: minimum distance and nearest points within 1e-6 relative
+
+
+@pytest.fixture(scope="module")
+def models(env_rob_npz, oracle):
+    (ev, et), (rv, rt) = env_rob_npz
+    return (F.BVHModel.from_arrays(ev, et), F.BVHModel.from_arrays(rv, rt)), (oracle.Model(ev, et), oracle.Model(rv, rt))
+
+
+@pytest.fixture(params=[0, 1], ids=["thread", "warp"])
+def traversal(request):
+    _capi.set_option("traversal", request.param)
+    yield request.param
+    _capi.set_option("traversal", 0)
+
+
+def _contacts_equal(got, ref):
+    assert np.array_equal(got.num_contacts, ref["counts"])
+    assert np.array_equal(got.offsets, ref["offsets"])
+    g, r = got.contacts, ref["contacts"]
+    assert len(g) == len(r)
+    assert np.array_equal(g["b1"], r["b1"]) and np.array_equal(g["b2"], r["b2"])
+    return g, r
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5])
+def test_cfg1_binary_verdict_10k(models, oracle, traversal, seed):
+    (env, rob), (oenv, orob) = models
+    P = random_poses(10000, seed=seed)
+    got = F.collide_batch(env, P, rob, None, F.CollisionRequest(), want_contacts=False, stats=True)
+    ref = oracle.collide_batch(oenv, orob, P, None, 1, False, nthreads=8)
+    assert np.array_equal(got.num_contacts, ref["counts"])
+    assert 3000 < got.num_contacts.sum() < 5000
+    if traversal == 0:  # same visiting order as the reference => same work counters
+        assert np.array_equal(got.n_bv, ref["n_bv"]) and np.array_equal(got.n_leaf, ref["n_leaf"])
+
+
+def test_cfg1_first_contact_pair_ids(models, oracle, traversal):
+    (env, rob), (oenv, orob) = models
+    P = random_poses(10000, seed=6)
+    got = F.collide_batch(env, P, rob, None, F.CollisionRequest(1, False), contact_capacity=len(P))
+    ref = oracle.collide_batch(oenv, orob, P, None, 1, False, nthreads=8)
+    _contacts_equal(got, ref)
+
+
+def test_cfg3_contacts_max100(models, oracle, traversal):
+    (env, rob), (oenv, orob) = models
+    P = random_poses(20000, seed=7)
+    got = F.collide_batch(env, P, rob, None, F.CollisionRequest(100, True), contact_capacity=100 * len(P))
+    ref = oracle.collide_batch(oenv, orob, P, None, 100, True, nthreads=8)
+    g, r = _contacts_equal(got, ref)
+    assert g.tobytes() == r.tobytes()  # positions, normals, depths bit-exact, DFS order, truncated at 100
+    assert (got.num_contacts == 100).sum() > 100  # truncation is exercised
+
+
+def test_exhaustive_contact_pair_sets(models, oracle, traversal):
+    (env, rob), (oenv, orob) = models
+    P = random_poses(4000, seed=8)
+    got = F.collide_batch(env, P, rob, None, F.CollisionRequest(INT_MAX, True), contact_capacity=1024 * len(P) // 4)
+    ref = oracle.collide_batch(oenv, orob, P, None, INT_MAX, True, nthreads=8)
+    g, r = _contacts_equal(got, ref)
+    assert g.tobytes() == r.tobytes()
+    assert got.num_contacts.max() > 300
+    # and the pair set of a few poses equals brute force over all 2180 x 216 triangle pairs
+    for i in np.flatnonzero(got.num_contacts > 0)[:5]:
+        c = got.contacts_of(i)
+        brute = set(map(tuple, oracle.brute_collide(oenv, orob, P[i]).tolist()))
+        assert set(zip(c["b1"].tolist(), c["b2"].tolist())) == brute
+
+
+def test_binary_mode_many_contacts(models, oracle, traversal):
+    (env, rob), (oenv, orob) = models
+    P = random_poses(3000, seed=9)
+    got = F.collide_batch(env, P, rob, None, F.CollisionRequest(50, False), contact_capacity=50 * len(P))
+    ref = oracle.collide_batch(oenv, orob, P, None, 50, False, nthreads=8)
+    _contacts_equal(got, ref)
+
+
+def test_cfg2_distance_nearest_points(models, oracle, traversal):
+    (env, rob), (oenv, orob) = models
+    P = random_poses(20000, seed=10)
+    got = F.distance_batch(env, P, rob, None, F.DistanceRequest(True), stats=True)
+    ref = oracle.distance_batch(oenv, orob, P, None, True, 2, nthreads=8)
+    assert np.array_equal(got.min_distance, ref["min_distance"])  # bit-exact minimum distance
+    pos = ref["min_distance"] > 0
+    assert pos.sum() > 5000 and (~pos).sum() > 5000
+    scale = np.maximum(1.0, np.abs(ref["p1"][pos]).max(axis=1, keepdims=True))
+    assert (np.abs(got.nearest_p1[pos] - ref["p1"][pos]) <= REL_TOL * scale).all()
+    assert (np.abs(got.nearest_p2[pos] - ref["p2"][pos]) <= REL_TOL * scale).all()
+    if traversal == 0:  # identical visiting order: ids, points and counters are identical too
+        assert np.array_equal(got.b1, ref["b1"]) and np.array_equal(got.b2, ref["b2"])
+        assert got.nearest_p1.tobytes() == ref["p1"].tobytes() and got.nearest_p2.tobytes() == ref["p2"].tobytes()
+        assert np.array_equal(got.n_bv, ref["n_bv"]) and np.array_equal(got.n_leaf, ref["n_leaf"])
+
+
+def test_distance_without_nearest_points(models, oracle, traversal):
+    (env, rob), (oenv, orob) = models
+    P = random_poses(2000, seed=11)
+    got = F.distance_batch(env, P, rob, None, F.DistanceRequest(False))
+    ref = oracle.distance_batch(oenv, orob, P, None, False, 2, nthreads=8)
+    assert np.array_equal(got.min_distance, ref["min_distance"])
+
+
+def test_both_objects_posed(models, oracle, traversal):
+    """General (tf1, tf2): the collide and distance paths build the relative pose with different
+    rounding sequences (SURVEY 8 a3 vs a11); both must match."""
+    (env, rob), (oenv, orob) = models
+    P1 = random_poses(3000, seed=12)
+    P2 = random_poses(3000, seed=13)
+    P2[:, 9:] = P1[:, 9:] + 0.2 * (P2[:, 9:] - 1500.0)
+    got = F.collide_batch(env, P1, rob, P2, F.CollisionRequest(20, True), contact_capacity=20 * len(P1))
+    ref = oracle.collide_batch(oenv, orob, P1, P2, 20, True, nthreads=8)
+    g, r = _contacts_equal(got, ref)
+    assert g.tobytes() == r.tobytes()
+    assert got.num_contacts.sum() > 1000
+    gd = F.distance_batch(env, P1, rob, P2, F.DistanceRequest(True))
+    rd = oracle.distance_batch(oenv, orob, P1, P2, True, 2, nthreads=8)
+    assert np.array_equal(gd.min_distance, rd["min_distance"])
+    # model2 posed, model1 identity
+    got = F.collide_batch(env, None, rob, P2, F.CollisionRequest(5, True), contact_capacity=5 * len(P2))
+    ref = oracle.collide_batch(oenv, orob, None, P2, 5, True, nthreads=8)
+    g, r = _contacts_equal(got, ref)
+    assert g.tobytes() == r.tobytes()
+
+
+def test_edge_cases(oracle, traversal):
+    """Single-triangle models (the root pair is a leaf pair), n = 1, n = 0, num_max_contacts = 0."""
+    tri = ([[0, 0, 0], [1, 0, 0], [0, 1, 0]], [[0, 1, 2]])
+    a, b = F.BVHModel.from_arrays(*tri), F.BVHModel.from_arrays(*tri)
+    oa, ob = oracle.Model(*tri), oracle.Model(*tri)
+    P = identity_poses(3)
+    P[1, 9:] = [0.2, 0.2, 0.0]   # coplanar overlap
+    P[2, 9:] = [0.0, 0.0, 3.0]   # apart
+    got = F.collide_batch(a, P, b, None, F.CollisionRequest(10, True), contact_capacity=30)
+    ref = oracle.collide_batch(oa, ob, P, None, 10, True)
+    g, r = _contacts_equal(got, ref)
+    assert g.tobytes() == r.tobytes()
+    gd = F.distance_batch(a, P, b, None, F.DistanceRequest(True))
+    rd = oracle.distance_batch(oa, ob, P, None, True)
+    assert np.array_equal(gd.min_distance, rd["min_distance"]) and gd.min_distance[2] == 3.0
+    one = F.collide_batch(a, P[2:], b, None, F.CollisionRequest(), want_contacts=False)
+    assert one.num_contacts.tolist() == [0]
+    zero = F.collide_batch(a, P, b, None, F.CollisionRequest(0, True), contact_capacity=8)
+    assert zero.num_contacts.sum() == 0 and zero.offsets.tolist() == [0, 0, 0, 0]
+    empty = F.collide_batch(a, np.zeros((0, 12)), b, None, F.CollisionRequest(), want_contacts=False)
+    assert len(empty.num_contacts) == 0
+    assert len(F.distance_batch(a, np.zeros((0, 12)), b, None, F.DistanceRequest()).min_distance) == 0
+
+
+def test_contact_capacity_overflow_is_reported(models):
+    (env, rob), _ = models
+    P = random_poses(2000, seed=14)
+    with pytest.raises(F.FclGpuError) as ei:
+        F.collide_batch(env, P, rob, None, F.CollisionRequest(100, True), contact_capacity=10)
+    assert ei.value.code == _capi.ERR_CONTACT_OVERFLOW
+
+
+def test_synthetic_meshes(oracle, traversal):
+    """Tessellated spheres (test_fcl_shape_mesh_consistency.cpp:57-80 analytic check) and random soups."""
+    v, t = uv_sphere(20, 16, 16)
+    s1, s2 = F.BVHModel.from_arrays(v, t), F.BVHModel.from_arrays(v, t)
+    tf2 = identity_poses(2)
+    tf2[0, 9] = 50.0
+    tf2[1, 9] = 30.0
+    d = F.distance_batch(s1, identity_poses(2), s2, tf2, F.DistanceRequest(True))
+    assert abs(d.min_distance[0] - 10.0) < 1.5 and d.min_distance[1] == 0.0
+    c = F.collide_batch(s1, identity_poses(2), s2, tf2, F.CollisionRequest(), want_contacts=False)
+    assert c.num_contacts.tolist() == [0, 1]
+    va, ta = random_soup(700, 1, scale=3.0)
+    vb, tb = random_soup(300, 2, scale=1.0)
+    A, B = F.BVHModel.from_arrays(va, ta), F.BVHModel.from_arrays(vb, tb)
+    OA, OB = oracle.Model(va, ta), oracle.Model(vb, tb)
+    P = random_poses(3000, seed=15, extents=(-4, -4, -4, 4, 4, 4))
+    got = F.collide_batch(A, P, B, None, F.CollisionRequest(INT_MAX, True), contact_capacity=600 * len(P))
+    ref = oracle.collide_batch(OA, OB, P, None, INT_MAX, True, nthreads=8)
+    g, r = _contacts_equal(got, ref)
+    assert g.tobytes() == r.tobytes()
+    gd = F.distance_batch(A, P, B, None, F.DistanceRequest(True))
+    rd = oracle.distance_batch(OA, OB, P, None, True, 2, nthreads=8)
+    assert np.array_equal(gd.min_distance, rd["min_distance"])
+
+
+def test_single_query_api_reads_like_the_reference(models, oracle):
+    """test/test_fcl_collision.cpp:1107-1150 (test_collide_func) and test_fcl_distance.cpp style."""
+    (env, rob), (oenv, orob) = models
+    P = random_poses(40, seed=16)
+    for i in range(len(P)):
+        pose = F.Transform3.from_pose12(P[i])
+        request = F.CollisionRequest(INT_MAX, True)
+        result = F.CollisionResult()
+        n = F.collide(env, pose, rob, F.Transform3.Identity(), request, result)
+        ref = oracle.collide_batch(oenv, orob, P[i:i + 1], None, INT_MAX, True)
+        assert n == ref["counts"][0] == result.numContacts()
+        pairs = sorted((c.b1, c.b2) for c in result.getContacts())
+        assert pairs == sorted(zip(ref["contacts"]["b1"].tolist(), ref["contacts"]["b2"].tolist()))
+        # results accumulate; a satisfied request returns early
+        assert F.collide(env, pose, rob, F.Transform3.Identity(), F.CollisionRequest(1), result) == n or n == 0
+        dres = F.DistanceResult()
+        d = F.distance(env, pose, rob, F.Transform3.Identity(), F.DistanceRequest(True), dres)
+        rd = oracle.distance_batch(oenv, orob, P[i:i + 1], None, True)
+        assert d == rd["min_distance"][0]
+        if d > 0:
+            assert abs(np.linalg.norm(dres.nearest_points[0] - dres.nearest_points[1]) - d) < 1e-6 * max(1, d)
+
+
+def test_full_size_properties_1m(models, oracle):
+    """BASELINE full size (1M poses): device-resident API; shard-additivity, idempotence,
+    and a random sample checked against the oracle."""
+    import torch
+
+    (env, rob), (oenv, orob) = models
+    n = 1_000_000
+    P = random_poses(n, seed=1)
+    dP = torch.from_numpy(P).cuda()
+    cnt = torch.zeros(n, dtype=torch.int32, device="cuda")
+    cnt2 = torch.zeros(n, dtype=torch.int32, device="cuda")
+    req = F.CollisionRequest()
+    F.collide_batch_device(env, dP, rob, None, req, cnt)
+    h = n // 2
+    F.collide_batch_device(env, dP[:h], rob, None, req, cnt2[:h])
+    F.collide_batch_device(env, dP[h:], rob, None, req, cnt2[h:])
+    F.sync_status()
+    assert torch.equal(cnt, cnt2)
+    dist = torch.zeros(n, dtype=torch.float64, device="cuda")
+    dist2 = torch.zeros(n, dtype=torch.float64, device="cuda")
+    p1 = torch.zeros(n, 3, dtype=torch.float64, device="cuda")
+    p2 = torch.zeros(n, 3, dtype=torch.float64, device="cuda")
+    F.distance_batch_device(env, dP, rob, None, F.DistanceRequest(True), dist, p1, p2)
+    F.distance_batch_device(env, dP, rob, None, F.DistanceRequest(False), dist2)
+    F.sync_status()
+    assert torch.equal(dist, dist2)
+    sep = (p1 - p2).norm(dim=1)
+    pos = dist > 0
+    assert torch.allclose(sep[pos], dist[pos], rtol=1e-9, atol=1e-9)
+    # colliding (triangle intersection) implies zero triangle distance for the overwhelming majority
+    col = cnt > 0
+    assert ((dist[col] == 0).float().mean() > 0.999) and ((cnt[dist > 1e-6] == 0).all())
+    idx = np.random.default_rng(0).choice(n, 3000, replace=False)
+    ref = oracle.collide_batch(oenv, orob, P[idx], None, 1, False, nthreads=8)
+    assert np.array_equal(cnt.cpu().numpy()[idx], ref["counts"])
+    rd = oracle.distance_batch(oenv, orob, P[idx], None, True, 2, nthreads=8)
+    assert np.array_equal(dist.cpu().numpy()[idx], rd["min_distance"])
