@@ -366,7 +366,8 @@ class BatchDistanceResult:
         self.n_bv, self.n_leaf = n_bv, n_leaf
 
 
-def collide_batch(o1, tf1, o2, tf2, request, contact_capacity=None, want_contacts=True, stats=False, device=None):
+def collide_batch(o1, tf1, o2, tf2, request, contact_capacity=None, want_contacts=True, stats=False, device=None,
+                  grow_on_overflow=False):
     """Host arrays in, host arrays out (copies inside): n independent fcl::collide() calls.
 
     tf1 / tf2: (n,12) float64 pose records, a Transform3, or None (identity)."""
@@ -390,9 +391,17 @@ def collide_batch(o1, tf1, o2, tf2, request, contact_capacity=None, want_contact
         contact_capacity, contacts, offsets = 0, None, None
     n_bv = np.zeros(n, np.uint32) if stats else None
     n_leaf = np.zeros(n, np.uint32) if stats else None
-    check(_capi.lib().fclgpu_collide_batch_host(m1, m2, n, addr(tf1), addr(tf2), C.byref(req), addr(counts),
-                                                addr(contacts), contact_capacity, addr(offsets), addr(n_bv),
-                                                addr(n_leaf)))
+    rc = _capi.lib().fclgpu_collide_batch_host(m1, m2, n, addr(tf1), addr(tf2), C.byref(req), addr(counts),
+                                               addr(contacts), contact_capacity, addr(offsets), addr(n_bv),
+                                               addr(n_leaf))
+    if rc == _capi.ERR_CONTACT_OVERFLOW and grow_on_overflow:
+        # counts are exact even when the pool / per-query scratch was too small: size both and rerun
+        need_stride = int(counts.max())
+        if need_stride > _capi.get_option("contact_stride"):
+            _capi.set_option("contact_stride", 1 << int(need_stride - 1).bit_length())
+        return collide_batch(o1, tf1, o2, tf2, request, contact_capacity=int(counts.sum(dtype=np.int64)),
+                             want_contacts=True, stats=stats, device=device, grow_on_overflow=False)
+    check(rc)
     if want_contacts:
         contacts = contacts[: offsets[n]]
     return BatchCollisionResult(counts, contacts, offsets, n_bv, n_leaf)
@@ -471,7 +480,7 @@ def collide(o1, tf1, o2, tf2, request, result):
     # a non-empty result consumes part of the contact budget
     budget = request.num_max_contacts - result.numContacts()
     sub = CollisionRequest(budget, request.enable_contact)
-    r = collide_batch(o1, tf1, o2, tf2, sub, contact_capacity=None if budget > 4096 else budget)
+    r = collide_batch(o1, tf1, o2, tf2, sub, contact_capacity=min(budget, 256), grow_on_overflow=True)
     for c in r.contacts_of(0):
         if request.enable_contact:
             result.addContact(Contact(o1, o2, int(c["b1"]), int(c["b2"]), c["pos"].copy(), c["normal"].copy(),
