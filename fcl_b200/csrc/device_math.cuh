@@ -128,13 +128,19 @@ FD bool obb_disjoint(const M3& B, const V3& T, const V3& a, const V3& b) {
 // Rectangle-rectangle distance (PQP RectDist).  Rab row-major, Tab, a[2] = sides of
 // rectangle A, b[2] = sides of B.
 //
-// Structure (differs from the reference's 16 hand-unrolled blocks, same arithmetic): the
-// 16 (edge of A, edge of B) candidates are 4 groups (ia, jb) = (1,1), (1,0), (0,1), (0,0)
-// -- A's edges parallel to A-axis ia against B's edges parallel to B-axis jb -- times the
-// 4 (upper/lower A edge, upper/lower B edge) combinations.  rect_group<> evaluates one
-// group; the first candidate whose Voronoi conditions hold yields the segment-segment
-// parameters, and ONE shared tail computes the closest-point vector, so lanes that stop
-// at different candidates re-converge for the divisions / sqrt.
+// Same arithmetic as the reference's 16 hand-unrolled blocks (RSS-inl.h:513-1225), different
+// control structure, chosen so that the 32 lanes of a warp -- each working on a different BV
+// pair -- stay converged:
+//   1. all 16 (edge of A, edge of B) candidates are classified at once from the projected
+//      corner coordinates: a 16-bit mask of open gates and two masks of interval shortcuts
+//      (straight-line code, no divisions);
+//   2. the first open candidate whose Voronoi conditions hold is found by walking the gate
+//      mask; the (rare, ~0.6 per call) in_voronoi evaluations use parameters selected from
+//      the candidate index, so lanes on different candidates share the same instructions;
+//   3. one shared tail computes the segment-segment closest points and the norm.
+// Candidate index k = 4*g + c: group g = (ia,jb) in the reference's order (1,1),(1,0),(0,1),
+// (0,0) -- A's edges parallel to A-axis ia against B's edges parallel to B-axis jb -- and
+// c = (upper A, upper B), (upper A, lower B), (lower A, upper B), (lower A, lower B).
 // ---------------------------------------------------------------------------------------
 FD void clip_to_range(double& v, double lo, double hi) {
   if (v < lo) v = lo;
@@ -157,173 +163,171 @@ FD bool in_voronoi(double a, double b, double Anorm_dot_B, double Anorm_dot_T, d
   return false;
 }
 
-struct RectHit {
-  int ia, jb;     // edge axes
-  bool ua, ub;    // upper A edge / upper B edge
-  double AdT, BdT;  // segment parameters' right-hand sides
-};
+FD int first_set_bit(unsigned m) {
+#ifdef __CUDA_ARCH__
+  return __ffs((int)m) - 1;
+#else
+  return __builtin_ctz(m);
+#endif
+}
 
-// One group.  R = Rab (row-major), Tab, Tba = Rab^T Tab.  Returns true and fills `h` when
-// one of the 4 candidates of the group contains the closest points.
-template <int IA, int JB>
-FD bool rect_group(const double* R, const double* Tab, const double* Tba, const double* a,
-                   const double* b, RectHit& h) {
-  constexpr int P = 1 - IA;  // A's other axis: index into a[], Tab[], rows of R
-  constexpr int Q = 1 - JB;  // B's other axis: index into b[], Tba[], cols of R
-  const double RiaQ = R[3 * IA + Q];    // A_ia . B_q
-  const double RiaJ = R[3 * IA + JB];   // A_ia . B_jb
-  const double RpJ = R[3 * P + JB];     // A_p  . B_jb
-  const double RpQ = R[3 * P + Q];      // A_p  . B_q
-  const double aPQ = a[P] * RpQ;        // a[p]  * (A_p . B_q)
-  const double aPJ = a[P] * RpJ;        // a[p]  * (A_p . B_jb)
-  const double aIQ = a[IA] * RiaQ;      // a[ia] * (A_ia . B_q)
-  const double bQiQ = b[Q] * RiaQ;      // b[q]  * (A_ia . B_q)
-  const double bQpQ = b[Q] * RpQ;       // b[q]  * (A_p . B_q)
-  const double bJpJ = b[JB] * RpJ;      // b[jb] * (A_p . B_jb)
-
-  // A's four corners projected on B-axis q (origin of B at 0), B's on A-axis p.
-  // Corner naming: first letter = position along axis 0 (L/U), second along axis 1.
-  const double ALL = -Tba[Q];
-  const double A_step1 = a[1] * R[3 * 1 + Q], A_step0 = a[0] * R[3 * 0 + Q];
-  const double ALU = ALL + A_step1, AUL = ALL + A_step0, AUU = ALU + A_step0;
-  const double BLL = Tab[P];
-  const double B_step1 = b[1] * R[3 * P + 1], B_step0 = b[0] * R[3 * P + 0];
-  const double BLU = BLL + B_step1, BUL = BLL + B_step0, BUU = BLU + B_step0;
-
-  // lower / upper edge of A parallel to axis IA, each as an ordered interval [l,u]
-  double LA_l, LA_u, UA_l, UA_u;
-  {
-    const double lo0 = ALL, lo1 = (IA == 1) ? ALU : AUL;  // the lower edge's two endpoints
-    const double up0 = (IA == 1) ? AUL : ALU, up1 = AUU;
-    if (lo0 < lo1) { LA_l = lo0; LA_u = lo1; UA_l = up0; UA_u = up1; }
-    else           { LA_l = lo1; LA_u = lo0; UA_l = up1; UA_u = up0; }
-  }
-  double LB_l, LB_u, UB_l, UB_u;
-  {
-    const double lo0 = BLL, lo1 = (JB == 1) ? BLU : BUL;
-    const double up0 = (JB == 1) ? BUL : BLU, up1 = BUU;
-    if (lo0 < lo1) { LB_l = lo0; LB_u = lo1; UB_l = up0; UB_u = up1; }
-    else           { LB_l = lo1; LB_u = lo0; UB_l = up1; UB_u = up0; }
-  }
-
-  const double la = a[IA], lb = b[JB];
-  const double AdT_U = Tab[IA] + bQiQ;  // B's upper edge: origin shifted by b[q] along B_q
-  const double AdT_L = Tab[IA];
-  const double BdT_U = Tba[JB] - aPJ;   // A's upper edge: origin shifted by a[p] along A_p
-  const double BdT_L = Tba[JB];
-
-  h.ia = IA;
-  h.jb = JB;
-  // (upper A, upper B)
-  if ((UA_u > b[Q]) && (UB_u > a[P])) {
-    // group (1,1) associates these two sums differently from the other three groups
-    // (RSS-inl.h:588,592 vs :742,746 / :896,900 / :1041,1045)
-    const double x1 = (IA == 1 && JB == 1) ? (aPQ - b[Q] - Tba[Q]) : (aPQ - Tba[Q] - b[Q]);
-    const double x2 = (IA == 1 && JB == 1) ? (Tab[P] + bQpQ - a[P]) : (Tab[P] - a[P] + bQpQ);
-    if (((UA_l > b[Q]) || in_voronoi(lb, la, RiaQ, x1, RiaJ, aPJ - Tba[JB], -Tab[IA] - bQiQ)) &&
-        ((UB_l > a[P]) || in_voronoi(la, lb, RpJ, x2, RiaJ, AdT_U, BdT_U))) {
-      h.ua = true; h.ub = true; h.AdT = AdT_U; h.BdT = BdT_U;
-      return true;
-    }
-  }
-  // (upper A, lower B)
-  if ((UA_l < 0) && (LB_u > a[P])) {
-    if (((UA_u < 0) || in_voronoi(lb, la, -RiaQ, Tba[Q] - aPQ, RiaJ, aPJ - Tba[JB], -Tab[IA])) &&
-        ((LB_l > a[P]) || in_voronoi(la, lb, RpJ, Tab[P] - a[P], RiaJ, AdT_L, BdT_U))) {
-      h.ua = true; h.ub = false; h.AdT = AdT_L; h.BdT = BdT_U;
-      return true;
-    }
-  }
-  // (lower A, upper B)
-  if ((LA_u > b[Q]) && (UB_l < 0)) {
-    if (((LA_l > b[Q]) || in_voronoi(lb, la, RiaQ, -Tba[Q] - b[Q], RiaJ, -Tba[JB], -Tab[IA] - bQiQ)) &&
-        ((UB_u < 0) || in_voronoi(la, lb, -RpJ, -Tab[P] - bQpQ, RiaJ, AdT_U, BdT_L))) {
-      h.ua = false; h.ub = true; h.AdT = AdT_U; h.BdT = BdT_L;
-      return true;
-    }
-  }
-  // (lower A, lower B)
-  if ((LA_l < 0) && (LB_l < 0)) {
-    if (((LA_u < 0) || in_voronoi(lb, la, -RiaQ, Tba[Q], RiaJ, -Tba[JB], -Tab[IA])) &&
-        ((LB_u < 0) || in_voronoi(la, lb, -RpJ, -Tab[P], RiaJ, AdT_L, BdT_L))) {
-      h.ua = false; h.ub = false; h.AdT = AdT_L; h.BdT = BdT_L;
-      return true;
-    }
-  }
-  (void)aIQ; (void)bJpJ;
-  return false;
+// gates / shortcuts of the four candidates of one group, packed into bits [shift, shift+4)
+FD void rect_group_masks(double lo0, double lo1, double up0, double up1,      // A: lower edge ends, upper edge ends
+                         double blo0, double blo1, double bup0, double bup1,  // B likewise
+                         double bq, double ap, int shift, unsigned& gate, unsigned& sc1, unsigned& sc2) {
+  double LA_l, LA_u, UA_l, UA_u, LB_l, LB_u, UB_l, UB_u;
+  if (lo0 < lo1) { LA_l = lo0; LA_u = lo1; UA_l = up0; UA_u = up1; }
+  else           { LA_l = lo1; LA_u = lo0; UA_l = up1; UA_u = up0; }
+  if (blo0 < blo1) { LB_l = blo0; LB_u = blo1; UB_l = bup0; UB_u = bup1; }
+  else             { LB_l = blo1; LB_u = blo0; UB_l = bup1; UB_u = bup0; }
+  const unsigned g = (((UA_u > bq) && (UB_u > ap)) ? 1u : 0u) | (((UA_l < 0) && (LB_u > ap)) ? 2u : 0u) |
+                     (((LA_u > bq) && (UB_l < 0)) ? 4u : 0u) | (((LA_l < 0) && (LB_l < 0)) ? 8u : 0u);
+  const unsigned s1 = ((UA_l > bq) ? 1u : 0u) | ((UA_u < 0) ? 2u : 0u) | ((LA_l > bq) ? 4u : 0u) | ((LA_u < 0) ? 8u : 0u);
+  const unsigned s2 = ((UB_l > ap) ? 1u : 0u) | ((LB_l > ap) ? 2u : 0u) | ((UB_u < 0) ? 4u : 0u) | ((LB_u < 0) ? 8u : 0u);
+  gate |= g << shift;
+  sc1 |= s1 << shift;
+  sc2 |= s2 << shift;
 }
 
 FD double rect_distance(const M3& Rab, const V3& Tabv, const double a[2], const double b[2]) {
-  const double* R = Rab.m;
-  const double Tab[3] = {Tabv.x, Tabv.y, Tabv.z};
+  const double R00 = Rab.m[0], R01 = Rab.m[1], R02 = Rab.m[2];
+  const double R10 = Rab.m[3], R11 = Rab.m[4], R12 = Rab.m[5];
+  const double R20 = Rab.m[6], R21 = Rab.m[7];
+  const double a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
+  const double Tab0 = Tabv.x, Tab1 = Tabv.y, Tab2 = Tabv.z;
   const V3 Tbav = mulTv(Rab, Tabv);
-  const double Tba[3] = {Tbav.x, Tbav.y, Tbav.z};
+  const double Tba0 = Tbav.x, Tba1 = Tbav.y, Tba2 = Tbav.z;
 
-  RectHit h;
-  bool found = rect_group<1, 1>(R, Tab, Tba, a, b, h);
-  if (!found) found = rect_group<1, 0>(R, Tab, Tba, a, b, h);
-  if (!found) found = rect_group<0, 1>(R, Tab, Tba, a, b, h);
-  if (!found) found = rect_group<0, 0>(R, Tab, Tba, a, b, h);
+  const double aA0B0 = a0 * R00, aA0B1 = a0 * R01, aA1B0 = a1 * R10, aA1B1 = a1 * R11;
+  const double bA0B0 = b0 * R00, bA1B0 = b0 * R10, bA0B1 = b1 * R01, bA1B1 = b1 * R11;
 
-  if (found) {
-    // shared tail: closest points of the two edge segments (segCoords, RSS-inl.h:458-482)
-    const int ia = h.ia, jb = h.jb, p = 1 - ia, q = 1 - jb;
-    const double la = a[ia], lb = b[jb];
-    const double A_dot_B = R[3 * ia + jb];
-    double t, u;
-    const double denom = 1 - A_dot_B * A_dot_B;
-    if (denom == 0) t = 0;
-    else {
-      t = (h.AdT - h.BdT * A_dot_B) / denom;
-      clip_to_range(t, 0.0, la);
+  // corners of A on B's axes (x: B-axis 0, y: B-axis 1) and of B on A's axes; first letter =
+  // position along the rectangle's axis 0 (Lower/Upper), second along its axis 1
+  const double ALL_x = -Tba0, ALU_x = ALL_x + aA1B0, AUL_x = ALL_x + aA0B0, AUU_x = ALU_x + aA0B0;
+  const double ALL_y = -Tba1, ALU_y = ALL_y + aA1B1, AUL_y = ALL_y + aA0B1, AUU_y = ALU_y + aA0B1;
+  const double BLL_x = Tab0, BLU_x = BLL_x + bA0B1, BUL_x = BLL_x + bA0B0, BUU_x = BLU_x + bA0B0;
+  const double BLL_y = Tab1, BLU_y = BLL_y + bA1B1, BUL_y = BLL_y + bA1B0, BUU_y = BLU_y + bA1B0;
+
+  unsigned gate = 0, sc1 = 0, sc2 = 0;
+  rect_group_masks(ALL_x, ALU_x, AUL_x, AUU_x, BLL_x, BLU_x, BUL_x, BUU_x, b0, a0, 0, gate, sc1, sc2);   // (1,1)
+  rect_group_masks(ALL_y, ALU_y, AUL_y, AUU_y, BLL_x, BUL_x, BLU_x, BUU_x, b1, a0, 4, gate, sc1, sc2);   // (1,0)
+  rect_group_masks(ALL_x, AUL_x, ALU_x, AUU_x, BLL_y, BLU_y, BUL_y, BUU_y, b0, a1, 8, gate, sc1, sc2);   // (0,1)
+  rect_group_masks(ALL_y, AUL_y, ALU_y, AUU_y, BLL_y, BUL_y, BLU_y, BUU_y, b1, a1, 12, gate, sc1, sc2);  // (0,0)
+
+  // candidate-indexed parameters (selects, no memory indexing)
+  int hit = -1;
+  bool ia = true, jb = true, ua = true, ub = true;
+  double la = a1, lb = b1, ap = a0, bq = b0, RiaJ = R11, AdT_U = 0, AdT_L = 0, BdT_U = 0, BdT_L = 0;
+  unsigned m = gate;
+  while (m != 0u) {
+    const int k = first_set_bit(m);
+    const int g = k >> 2, c = k & 3;
+    ia = g < 2;
+    jb = (g & 1) == 0;
+    ua = c < 2;
+    ub = (c & 1) == 0;
+    la = ia ? a1 : a0;
+    lb = jb ? b1 : b0;
+    ap = ia ? a0 : a1;
+    bq = jb ? b0 : b1;
+    RiaJ = ia ? (jb ? R11 : R10) : (jb ? R01 : R00);
+    const double RiaQ = ia ? (jb ? R10 : R11) : (jb ? R00 : R01);
+    const double RpJ = ia ? (jb ? R01 : R00) : (jb ? R11 : R10);
+    const double RpQ = ia ? (jb ? R00 : R01) : (jb ? R10 : R11);
+    const double Tab_ia = ia ? Tab1 : Tab0, Tab_p = ia ? Tab0 : Tab1;
+    const double Tba_jb = jb ? Tba1 : Tba0, Tba_q = jb ? Tba0 : Tba1;
+    const double aPQ = ap * RpQ, aPJ = ap * RpJ, bQiQ = bq * RiaQ, bQpQ = bq * RpQ;
+    AdT_U = Tab_ia + bQiQ;
+    AdT_L = Tab_ia;
+    BdT_U = Tba_jb - aPJ;
+    BdT_L = Tba_jb;
+    bool ok1 = ((sc1 >> k) & 1u) != 0u, ok2 = ((sc2 >> k) & 1u) != 0u;
+    if (!ok1) {
+      double n_dot_T;
+      if (c == 0) n_dot_T = (g == 0) ? (aPQ - bq - Tba_q) : (aPQ - Tba_q - bq);  // RSS-inl.h:588 vs :742,896,1041
+      else if (c == 1) n_dot_T = Tba_q - aPQ;
+      else if (c == 2) n_dot_T = -Tba_q - bq;
+      else n_dot_T = Tba_q;
+      ok1 = in_voronoi(lb, la, (c & 1) ? -RiaQ : RiaQ, n_dot_T, RiaJ, ua ? (aPJ - Tba_jb) : (-Tba_jb),
+                       ub ? (-Tab_ia - bQiQ) : (-Tab_ia));
     }
-    u = t * A_dot_B - h.BdT;
-    if (u < 0) {
-      u = 0;
-      t = h.AdT;
-      clip_to_range(t, 0.0, la);
-    } else if (u > lb) {
-      u = lb;
-      t = u * A_dot_B + h.AdT;
-      clip_to_range(t, 0.0, la);
+    if (ok1 && !ok2) {
+      double n_dot_T;
+      if (c == 0) n_dot_T = (g == 0) ? (Tab_p + bQpQ - ap) : (Tab_p - ap + bQpQ);  // RSS-inl.h:592 vs :746,900,1045
+      else if (c == 1) n_dot_T = Tab_p - ap;
+      else if (c == 2) n_dot_T = -Tab_p - bQpQ;
+      else n_dot_T = -Tab_p;
+      ok2 = in_voronoi(la, lb, ua ? RpJ : -RpJ, n_dot_T, RiaJ, ub ? AdT_U : AdT_L, ua ? BdT_U : BdT_L);
     }
-    // D_k = Tab[k] (+ R[k][q]*b[q] if upper B) + R[k][jb]*u - (point on A)_k
-    double D[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      double d = Tab[k];
-      if (h.ub) d = d + R[3 * k + q] * b[q];
-      d = d + R[3 * k + jb] * u;
-      D[k] = d;
+    if (ok1 && ok2) {
+      hit = k;
+      break;
     }
-    D[ia] = D[ia] - t;
-    if (h.ua) D[p] = D[p] - a[p];
-    return sqrt((D[0] * D[0] + D[1] * D[1]) + D[2] * D[2]);
+    m &= m - 1u;
   }
+
+  // shared tail: closest points of the two edge segments (segCoords, RSS-inl.h:458-482) and
+  // their difference vector; executed by every lane (lanes without a hit discard the result)
+  const double AdT = ub ? AdT_U : AdT_L, BdT = ua ? BdT_U : BdT_L;
+  double t, u;
+  const double denom = 1 - RiaJ * RiaJ;
+  if (denom == 0) t = 0;
+  else {
+    t = (AdT - BdT * RiaJ) / denom;
+    clip_to_range(t, 0.0, la);
+  }
+  u = t * RiaJ - BdT;
+  if (u < 0) {
+    u = 0;
+    t = AdT;
+    clip_to_range(t, 0.0, la);
+  } else if (u > lb) {
+    u = lb;
+    t = u * RiaJ + AdT;
+    clip_to_range(t, 0.0, la);
+  }
+  // D_k = Tab[k] (+ R[k][q]*b[q] if upper B) + R[k][jb]*u - (point on A)_k
+  double D0 = Tab0, D1 = Tab1, D2 = Tab2;
+  if (ub) {
+    D0 = D0 + (jb ? R00 : R01) * bq;
+    D1 = D1 + (jb ? R10 : R11) * bq;
+    D2 = D2 + (jb ? R20 : R21) * bq;
+  }
+  D0 = D0 + (jb ? R01 : R00) * u;
+  D1 = D1 + (jb ? R11 : R10) * u;
+  D2 = D2 + (jb ? R21 : R20) * u;
+  if (ia) {
+    D1 = D1 - t;
+    if (ua) D0 = D0 - ap;
+  } else {
+    D0 = D0 - t;
+    if (ua) D1 = D1 - ap;
+  }
+  const double edge_dist = sqrt((D0 * D0 + D1 * D1) + D2 * D2);
 
   // no edge pair: separation along the two face normals (RSS-inl.h:1152-1224)
   double sep1, sep2;
-  if (Tab[2] > 0.0) {
-    sep1 = Tab[2];
-    if (R[6] < 0.0) sep1 += b[0] * R[6];
-    if (R[7] < 0.0) sep1 += b[1] * R[7];
+  if (Tab2 > 0.0) {
+    sep1 = Tab2;
+    if (R20 < 0.0) sep1 += b0 * R20;
+    if (R21 < 0.0) sep1 += b1 * R21;
   } else {
-    sep1 = -Tab[2];
-    if (R[6] > 0.0) sep1 -= b[0] * R[6];
-    if (R[7] > 0.0) sep1 -= b[1] * R[7];
+    sep1 = -Tab2;
+    if (R20 > 0.0) sep1 -= b0 * R20;
+    if (R21 > 0.0) sep1 -= b1 * R21;
   }
-  if (Tba[2] < 0) {
-    sep2 = -Tba[2];
-    if (R[2] < 0.0) sep2 += a[0] * R[2];
-    if (R[5] < 0.0) sep2 += a[1] * R[5];
+  if (Tba2 < 0) {
+    sep2 = -Tba2;
+    if (R02 < 0.0) sep2 += a0 * R02;
+    if (R12 < 0.0) sep2 += a1 * R12;
   } else {
-    sep2 = Tba[2];
-    if (R[2] > 0.0) sep2 -= a[0] * R[2];
-    if (R[5] > 0.0) sep2 -= a[1] * R[5];
+    sep2 = Tba2;
+    if (R02 > 0.0) sep2 -= a0 * R02;
+    if (R12 > 0.0) sep2 -= a1 * R12;
   }
   const double sep = (sep1 > sep2 ? sep1 : sep2);
-  return (sep > 0 ? sep : 0);
+  const double face_dist = (sep > 0 ? sep : 0);
+  return hit >= 0 ? edge_dist : face_dist;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -53,6 +53,7 @@ std::map<std::string, long long> g_opts = {
     {"scratch_bytes", 2ll << 30},
     {"blocks_per_sm", 0},      // 0 = occupancy query
     {"stats", 1},
+    {"leaf_trigger", 20},      // collide variant D: lanes with queued triangle pairs that trigger a leaf round
 };
 long long opt(const char* k) {
   std::lock_guard<std::mutex> g(g_opt_mu);
@@ -350,15 +351,17 @@ __global__ void compact_kernel(const int32_t* __restrict__ counts, long long n, 
 
 __global__ void write_total_kernel(const long long* base, long long* offsets_n) { *offsets_n = *base; }
 
-template <typename K, typename Pm>
-int launch_persistent(K kernel, const Pm& params, Workspace* w, int block, cudaStream_t st) {
+template <typename K, typename Pm, typename... Extra>
+int launch_persistent(K kernel, const Pm& params, Workspace* w, int block, cudaStream_t st, size_t smem = 0,
+                      Extra... extra) {
+  if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = (int)opt("blocks_per_sm");
   if (per_sm <= 0) {
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
     if (per_sm < 1) per_sm = 1;
   }
   const int grid = w->sm_count * per_sm;
-  kernel<<<grid, block, 0, st>>>(params);
+  kernel<<<grid, block, smem, st>>>(params, extra...);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -436,8 +439,14 @@ extern "C" int fclgpu_collide_batch(const fclgpu_model* m1, const fclgpu_model* 
     P.n_leaf = n_leaf ? n_leaf + s : nullptr;
     P.work_counter = next_counter(w, st);
     P.status = w->status;
-    rc = stats ? launch_persistent(collide_thread_kernel<true>, P, w, 128, st)
-               : launch_persistent(collide_thread_kernel<false>, P, w, 128, st);
+    if (opt("traversal") == 1) {
+      const int trig = (int)opt("leaf_trigger");
+      rc = stats ? launch_persistent(collide_deferred_kernel<true>, P, w, 128, st, 0, trig)
+                 : launch_persistent(collide_deferred_kernel<false>, P, w, 128, st, 0, trig);
+    } else {
+      rc = stats ? launch_persistent(collide_thread_kernel<true>, P, w, 128, st)
+                 : launch_persistent(collide_thread_kernel<false>, P, w, 128, st);
+    }
     if (rc) return rc;
     if (want_contacts) {
       long long* local = (long long*)w->scan_tmp;
@@ -496,8 +505,13 @@ extern "C" int fclgpu_distance_batch(const fclgpu_model* m1, const fclgpu_model*
   P.work_counter = next_counter(w, st);
   P.status = w->status;
   const bool stats = (n_bv || n_leaf);
-  rc = stats ? launch_persistent(distance_thread_kernel<true>, P, w, 128, st)
-             : launch_persistent(distance_thread_kernel<false>, P, w, 128, st);
+  if (opt("traversal") == 1) {
+    rc = stats ? launch_persistent(distance_warp_kernel<true>, P, w, kDistWarps * 32, st, sizeof(WarpFront) * kDistWarps)
+               : launch_persistent(distance_warp_kernel<false>, P, w, kDistWarps * 32, st, sizeof(WarpFront) * kDistWarps);
+  } else {
+    rc = stats ? launch_persistent(distance_thread_kernel<true>, P, w, 128, st)
+               : launch_persistent(distance_thread_kernel<false>, P, w, 128, st);
+  }
   return rc;
 }
 
