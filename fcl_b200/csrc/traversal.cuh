@@ -416,9 +416,9 @@ namespace fclgpu {
 // 0.5x the leaf tests (nearest-first expansion tightens the bound sooner).
 // ---------------------------------------------------------------------------------------
 constexpr int kDistPop = 16;         // entries expanded per BV round (2 lanes each)
-constexpr int kDistStackCap = 640;   // entries per warp
+constexpr int kDistStackCap = 512;   // entries per warp
 constexpr int kLeafCap = 64;
-constexpr int kLeafTrigger = 16;
+constexpr int kLeafTrigger = 32;
 constexpr int kDistWarps = 4;        // warps per block
 
 struct __align__(16) WarpFront {
@@ -426,6 +426,7 @@ struct __align__(16) WarpFront {
   uint2 pair[kDistStackCap];
   double leaf_bound[kLeafCap];
   uint2 leaf_pair[kLeafCap];  // triangle ids
+  uint2 expand[32];           // child pairs handed from the entry's holder lane to the two testing lanes
   double best[6];
   int best_id[2];
 };
@@ -436,33 +437,35 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
   hi = __shfl_xor_sync(0xffffffffu, hi, m);
   return ((unsigned long long)hi << 32) | lo;
 }
+__device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int src) {
+  unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
+  lo = __shfl_sync(0xffffffffu, lo, src);
+  hi = __shfl_sync(0xffffffffu, hi, src);
+  return ((unsigned long long)hi << 32) | lo;
+}
 
-// ascending bitonic sort of (key, payload) across the 32 lanes; ties broken by payload
-__device__ __forceinline__ void warp_sort(unsigned long long& key, unsigned long long& val, int lane) {
+// Ascending bitonic sort of one 32-bit key per lane.  The keys only steer the visiting order
+// (nearest candidates first), so a rounded-down float image of the bound with the lane id in
+// the low 5 bits is enough: keys are unique and the winner's payload is fetched afterwards.
+__device__ __forceinline__ unsigned warp_sort_keys(unsigned key, int lane) {
 #pragma unroll
   for (int k = 2; k <= 32; k <<= 1) {
 #pragma unroll
     for (int j = k >> 1; j > 0; j >>= 1) {
-      const unsigned long long ok = shfl_xor_u64(key, j), ov = shfl_xor_u64(val, j);
-      const bool up = ((lane & k) == 0);          // ascending block
-      const bool lower = ((lane & j) == 0);       // this lane keeps the smaller element if ascending
-      const bool other_less = (ok < key) || (ok == key && ov < val);
-      const bool take = (lower == up) ? other_less : !other_less && !(ok == key && ov == val);
-      if (take) {
-        key = ok;
-        val = ov;
-      }
+      const unsigned other = __shfl_xor_sync(0xffffffffu, key, j);
+      const bool keep_min = (((lane & j) == 0) == ((lane & k) == 0));
+      key = keep_min ? min(key, other) : max(key, other);
     }
   }
+  return key;
 }
 
 template <bool kStats>
-__global__ void __launch_bounds__(kDistWarps * 32) distance_warp_kernel(DistanceParams P) {
+__global__ void __launch_bounds__(kDistWarps * 32, 4) distance_warp_kernel(DistanceParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WarpFront& S = reinterpret_cast<WarpFront*>(smem_raw)[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const unsigned long long kDead = 0xffffffffffffffffull;
 
   while (true) {
     long long q = 0;
@@ -470,18 +473,22 @@ __global__ void __launch_bounds__(kDistWarps * 32) distance_warp_kernel(Distance
     q = __shfl_sync(0xffffffffu, q, 0);
     if (q >= P.n) break;
 
-    const PoseRT tf1 = load_pose(P.tf1, q);
-    const PoseRT tf2 = load_pose(P.tf2, q);
-    const M3 R = mulTM(tf1.R, tf2.R);
-    const V3 it = mulTv(tf1.R, tf1.t);
-    const V3 T = mulTv(tf1.R, tf2.t) + mk(-it.x, -it.y, -it.z);
+    M3 R;
+    V3 T;
+    {
+      const PoseRT tf1 = load_pose(P.tf1, q);
+      const PoseRT tf2 = load_pose(P.tf2, q);
+      R = mulTM(tf1.R, tf2.R);
+      const V3 it = mulTv(tf1.R, tf1.t);
+      T = mulTv(tf1.R, tf2.t) + mk(-it.x, -it.y, -it.z);
+    }
 
     double min_d = 1.7976931348623157e308;
     int sp = 1, nleaf = 1;
     uint32_t bv_tests = 0, leaf_tests = 0;
     if (lane == 0) {
       S.pair[0] = make_uint2(0u, 0u);
-      S.bound[0] = -1.0;           // the root pair is never bound-tested
+      S.bound[0] = -1.0;                    // the root pair is never bound-tested
       S.leaf_pair[0] = make_uint2(0u, 0u);  // preprocess: triangle 0 / triangle 0 seeds the result
       S.leaf_bound[0] = -1.0;
       S.best_id[0] = S.best_id[1] = -1;
@@ -514,11 +521,11 @@ __global__ void __launch_bounds__(kDistWarps * 32) distance_warp_kernel(Distance
         }
         // warp arg-min (distances are >= 0, so the bit pattern orders like the value); ties -> lowest lane
         unsigned long long key = (unsigned long long)__double_as_longlong(d);
-        unsigned long long who = (unsigned long long)lane;
+        int who = lane;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           const unsigned long long ok = shfl_xor_u64(key, o);
-          const unsigned long long ow = shfl_xor_u64(who, o);
+          const int ow = __shfl_xor_sync(0xffffffffu, who, o);
           if (ok < key || (ok == key && ow < who)) {
             key = ok;
             who = ow;
@@ -527,7 +534,7 @@ __global__ void __launch_bounds__(kDistWarps * 32) distance_warp_kernel(Distance
         const double dmin = __longlong_as_double((long long)key);
         if (dmin < min_d) {  // strictly smaller, like DistanceResult::update
           min_d = dmin;
-          if (lane == (int)who) {
+          if (lane == who) {
             S.best[0] = Pn.x; S.best[1] = Pn.y; S.best[2] = Pn.z;
             S.best[3] = Qn.x; S.best[4] = Qn.y; S.best[5] = Qn.z;
             S.best_id[0] = (int)ids.x;
@@ -540,23 +547,18 @@ __global__ void __launch_bounds__(kDistWarps * 32) distance_warp_kernel(Distance
       if (sp == 0) break;
 
       // ---- BV round ----
-      int k = sp < kDistPop ? sp : kDistPop;
-      const int room = kDistStackCap - sp;  // popping k and pushing <= 2k needs room >= k
-      if (room < k) k = room;
-      if (k <= 0) {
-        if (lane == 0) atomicMin(P.status, (int)FCLGPU_ERR_STACK_OVERFLOW);
-        sp = 0;
-        nleaf = 0;
-        break;
-      }
-      const int e = lane >> 1, c = lane & 1;
-      bool alive = e < k;
+      // every lane pops one entry; dead entries (bound no longer beats the minimum) vanish, leaf
+      // pairs move to the leaf queue, the first kDistPop internal entries (nearest first) are
+      // expanded by two lanes each and the remaining internal entries go back on the stack.
+      const int k = sp < 32 ? sp : 32;
       uint2 pr = make_uint2(0u, 0u);
+      double bd = 0.0;
+      bool alive = lane < k;
       if (alive) {
-        pr = S.pair[sp - 1 - e];
-        alive = S.bound[sp - 1 - e] < min_d;  // canStop(c): bound >= min_distance -> skip
+        pr = S.pair[sp - 1 - lane];
+        bd = S.bound[sp - 1 - lane];
+        alive = bd < min_d;  // canStop(c): bound >= min_distance -> skip
       }
-      sp -= k;
       int fc1 = 0, fc2 = 0;
       if (alive) {
         fc1 = __ldg(P.m1.first_child + pr.x);
@@ -564,46 +566,69 @@ __global__ void __launch_bounds__(kDistWarps * 32) distance_warp_kernel(Distance
       }
       const bool l1 = fc1 < 0, l2 = fc2 < 0;
       const bool leafpair = alive && l1 && l2;
-      {
-        const unsigned lm = __ballot_sync(0xffffffffu, leafpair && c == 0);
-        if (leafpair && c == 0) {
-          const int pos = nleaf + __popc(lm & lt_mask);
-          S.leaf_pair[pos] = make_uint2((unsigned)(-(fc1 + 1)), (unsigned)(-(fc2 + 1)));
-          S.leaf_bound[pos] = S.bound[sp + k - 1 - e];
-        }
-        nleaf += __popc(lm);
+      const unsigned lm = __ballot_sync(0xffffffffu, leafpair);
+      if (leafpair) {
+        const int pos = nleaf + __popc(lm & lt_mask);
+        S.leaf_pair[pos] = make_uint2((unsigned)(-(fc1 + 1)), (unsigned)(-(fc2 + 1)));
+        S.leaf_bound[pos] = bd;
       }
-      const bool expand = alive && !leafpair;
-      unsigned long long key = kDead, val = 0;
+      nleaf += __popc(lm);
+      const bool internal = alive && !leafpair;
+      const unsigned im = __ballot_sync(0xffffffffu, internal);
+      const int n_int = __popc(im), rank = __popc(im & lt_mask);
+      sp -= k;
+      int n_exp = n_int < kDistPop ? n_int : kDistPop;
+      const int room = kDistStackCap - sp - n_int;  // after re-pushing the leftovers, 2*n_exp children minus n_exp must fit
+      if (n_exp > room) n_exp = room;
+      if (n_int > 0 && n_exp <= 0) {
+        if (lane == 0) atomicMin(P.status, (int)FCLGPU_ERR_STACK_OVERFLOW);
+        sp = 0;
+        nleaf = 0;
+        break;
+      }
+      __syncwarp();  // every lane has read its popped entry before slots are overwritten
+      if (internal) {
+        if (rank < n_exp) {
+          const double size1 = __ldg(P.m1.rss + (size_t)pr.x * kNodeDoubles + 15);
+          const double size2 = __ldg(P.m2.rss + (size_t)pr.y * kNodeDoubles + 15);
+          if (l2 || (!l1 && (size1 > size2))) {  // firstOverSecond
+            S.expand[2 * rank] = make_uint2((unsigned)fc1, pr.y);
+            S.expand[2 * rank + 1] = make_uint2((unsigned)fc1 + 1u, pr.y);
+          } else {
+            S.expand[2 * rank] = make_uint2(pr.x, (unsigned)fc2);
+            S.expand[2 * rank + 1] = make_uint2(pr.x, (unsigned)fc2 + 1u);
+          }
+        } else {  // leftover: back on the stack, order preserved (rank n_exp nearest -> top)
+          const int pos = sp + (n_int - 1 - rank);
+          S.pair[pos] = pr;
+          S.bound[pos] = bd;
+        }
+      }
+      sp += n_int - n_exp;
+      __syncwarp();
+      const bool expand = lane < 2 * n_exp;
+      unsigned key = 0xffffffffu;
+      uint2 xy = make_uint2(0u, 0u);
+      double d = 0.0;
       if (expand) {
-        const double size1 = __ldg(P.m1.rss + (size_t)pr.x * kNodeDoubles + 15);
-        const double size2 = __ldg(P.m2.rss + (size_t)pr.y * kNodeDoubles + 15);
-        unsigned x, y;
-        if (l2 || (!l1 && (size1 > size2))) {
-          x = (unsigned)fc1 + (unsigned)c;
-          y = pr.y;
-        } else {
-          x = pr.x;
-          y = (unsigned)fc2 + (unsigned)c;
-        }
-        const NodeRec n1 = load_node(P.m1.rss, (int)x);
-        const NodeRec n2 = load_node(P.m2.rss, (int)y);
+        xy = S.expand[lane];
+        const NodeRec n1 = load_node(P.m1.rss, (int)xy.x);
+        const NodeRec n2 = load_node(P.m2.rss, (int)xy.y);
         const double la[2] = {n1.e0, n1.e1}, lb[2] = {n2.e0, n2.e1};
-        const double d = rss_pair_distance(R, T, n1.axis, n1.To, la, n1.e2, n2.axis, n2.To, lb, n2.e2);
-        if (d < min_d) {
-          key = (unsigned long long)__double_as_longlong(d);
-          val = ((unsigned long long)x << 32) | y;
-        }
+        d = rss_pair_distance(R, T, n1.axis, n1.To, la, n1.e2, n2.axis, n2.To, lb, n2.e2);
+        if (d < min_d) key = (__float_as_uint(__double2float_rd(d)) & ~31u) | (unsigned)lane;
       }
-      if (kStats) bv_tests += __popc(__ballot_sync(0xffffffffu, expand));
-      const int nkeep = __popc(__ballot_sync(0xffffffffu, key != kDead));
-      __syncwarp();  // every lane has read its popped entry before the slots are overwritten
+      if (kStats) bv_tests += 2 * n_exp;
+      const int nkeep = __popc(__ballot_sync(0xffffffffu, key != 0xffffffffu));
       if (nkeep > 0) {
-        warp_sort(key, val, lane);  // ascending: lane 0 = nearest
-        if (lane < nkeep) {         // nearest ends on top of the stack
+        key = warp_sort_keys(key, lane);  // ascending: lane 0 = nearest
+        const int src = (int)(key & 31u);
+        const unsigned long long v = shfl_u64(((unsigned long long)xy.x << 32) | xy.y, src);
+        const double dv = __longlong_as_double((long long)shfl_u64((unsigned long long)__double_as_longlong(d), src));
+        if (lane < nkeep) {  // nearest ends on top of the stack
           const int pos = sp + (nkeep - 1 - lane);
-          S.pair[pos] = make_uint2((unsigned)(val >> 32), (unsigned)val);
-          S.bound[pos] = __longlong_as_double((long long)key);
+          S.pair[pos] = make_uint2((unsigned)(v >> 32), (unsigned)v);
+          S.bound[pos] = dv;
         }
         sp += nkeep;
       }
@@ -616,6 +641,7 @@ __global__ void __launch_bounds__(kDistWarps * 32) distance_warp_kernel(Distance
       if (P.b1) P.b1[q] = S.best_id[0];
       if (P.b2) P.b2[q] = S.best_id[1];
       if (P.enable_nearest_points) {
+        const PoseRT tf1 = load_pose(P.tf1, q);
         const V3 w1 = mulv(tf1.R, mk(S.best[0], S.best[1], S.best[2])) + tf1.t;
         const V3 w2 = mulv(tf1.R, mk(S.best[3], S.best[4], S.best[5])) + tf1.t;
         if (P.p1) { P.p1[3 * q] = w1.x; P.p1[3 * q + 1] = w1.y; P.p1[3 * q + 2] = w1.z; }
