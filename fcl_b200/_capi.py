@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libfclgpu.so")
+LIB_PATH = os.environ.get("FCLGPU_LIB_PATH") or os.path.join(_HERE, "lib", "libfclgpu.so")  # override: A/B builds
 
 OK = 0
 ERR_BUILD_OUT_OF_SEQUENCE = -2

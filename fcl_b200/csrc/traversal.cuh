@@ -460,8 +460,11 @@ __device__ __forceinline__ unsigned warp_sort_keys(unsigned key, int lane) {
   return key;
 }
 
+#ifndef FCLGPU_DIST_MINBLOCKS
+#define FCLGPU_DIST_MINBLOCKS 4
+#endif
 template <bool kStats>
-__global__ void __launch_bounds__(kDistWarps * 32, 4) distance_warp_kernel(DistanceParams P) {
+__global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distance_warp_kernel(DistanceParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WarpFront& S = reinterpret_cast<WarpFront*>(smem_raw)[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
@@ -678,8 +681,11 @@ namespace fclgpu {
 // ---------------------------------------------------------------------------------------
 constexpr int kLeafFifo = 8;  // deferred pairs per lane (power of two)
 
+#ifndef FCLGPU_COLLIDE_MINBLOCKS
+#define FCLGPU_COLLIDE_MINBLOCKS 3
+#endif
 template <bool kStats>
-__global__ void __launch_bounds__(128) collide_deferred_kernel(CollideParams P, int leaf_trigger) {
+__global__ void __launch_bounds__(128, FCLGPU_COLLIDE_MINBLOCKS) collide_deferred_kernel(CollideParams P, int leaf_trigger) {
   __shared__ uint2 fifo[4][kLeafFifo][32];  // [warp][slot][lane]
   uint2 stk[kStackCap];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
