@@ -153,7 +153,7 @@ def main():
     ap.add_argument("--workload", default="distance", choices=sorted(WORKLOADS))
     ap.add_argument("--poses", type=int, default=1_000_000, help="poses per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=20000)
-    ap.add_argument("--traversal", type=int, default=None, help="kernel variant (fclgpu option 'traversal')")
+    ap.add_argument("--traversal", type=int, default=1, help="kernel variant (fclgpu option 'traversal', see DESIGN.md)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -173,6 +173,7 @@ def main():
 
     import fcl_b200 as F
     from fcl_b200 import _capi
+    from fcl_b200.sharding import all_gather_records
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
@@ -181,8 +182,7 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    if args.traversal is not None:
-        _capi.set_option("traversal", args.traversal)
+    _capi.set_option("traversal", args.traversal)
 
     (ev, et), (rv, rt) = load_meshes()
     env, rob = F.BVHModel.from_arrays(ev, et), F.BVHModel.from_arrays(rv, rt)
@@ -204,11 +204,8 @@ def main():
         o_p2 = torch.empty(n, 3, dtype=torch.float64, device=dev)
         o_b1 = torch.empty(n, dtype=torch.int32, device=dev)
         o_b2 = torch.empty(n, dtype=torch.int32, device=dev)
-        g_dist = torch.empty(world * n, dtype=torch.float64, device=dev) if world > 1 else None
-        g_pts = torch.empty(world * n, 6, dtype=torch.float64, device=dev) if world > 1 else None
     else:
         o_cnt = torch.empty(n, dtype=torch.int32, device=dev)
-        g_cnt = torch.empty(world * n, dtype=torch.int32, device=dev) if world > 1 else None
         if wl == "contacts":
             cap = 64 * n
             o_con = torch.empty(cap * 64, dtype=torch.uint8, device=dev)
@@ -218,16 +215,16 @@ def main():
         if wl == "distance":
             F.distance_batch_device(env, dP, rob, None, dreq, o_dist, o_p1, o_p2, o_b1, o_b2)
             if world > 1:  # per-GPU results gathered with NCCL allgather over NVLink
-                dist.all_gather_into_tensor(g_dist, o_dist)
-                dist.all_gather_into_tensor(g_pts, torch.cat([o_p1, o_p2], dim=1))
+                all_gather_records(o_dist, world * n)
+                all_gather_records(torch.cat([o_p1, o_p2], dim=1), world * n)
         elif wl == "collide":
             F.collide_batch_device(env, dP, rob, None, creq, o_cnt)
             if world > 1:
-                dist.all_gather_into_tensor(g_cnt, o_cnt)
+                all_gather_records(o_cnt, world * n)
         else:
             F.collide_batch_device(env, dP, rob, None, creq, o_cnt, o_con, o_off)
             if world > 1:
-                dist.all_gather_into_tensor(g_cnt, o_cnt)
+                all_gather_records(o_cnt, world * n)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
@@ -265,8 +262,7 @@ def main():
     else:
         F.collide_batch_device(env, dP, rob, None, creq, o_cnt, None, None, nbv, nleaf)
     F.sync_status(local)
-    if args.traversal is not None:
-        _capi.set_option("traversal", args.traversal)
+    _capi.set_option("traversal", args.traversal)
     h_nbv, h_nleaf = nbv.cpu().numpy().astype(np.int64), nleaf.cpu().numpy().astype(np.int64)
 
     # ---- device-resident throughput (value) ----

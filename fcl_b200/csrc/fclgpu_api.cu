@@ -48,7 +48,9 @@ int fail(int code, const char* fmt, ...) {
 // options
 std::mutex g_opt_mu;
 std::map<std::string, long long> g_opts = {
-    {"traversal", 0},          // 0 = thread per query (persistent lanes), 1 = warp per query front traversal
+    // 1 (default): collide = thread per query with deferred leaf rounds, distance = warp per query sorted front
+    // 0: thread per query, the reference's visiting order exactly (work counters match the reference's)
+    {"traversal", 1},
     {"contact_stride", 1024},  // per-query contact scratch slots when num_max_contacts is larger
     {"scratch_bytes", 2ll << 30},
     {"blocks_per_sm", 0},      // 0 = occupancy query

@@ -26,7 +26,7 @@ def models(env_rob_npz, oracle):
 def traversal(request):
     _capi.set_option("traversal", request.param)
     yield request.param
-    _capi.set_option("traversal", 0)
+    _capi.set_option("traversal", 1)  # library default
 
 
 def _contacts_equal(got, ref):
