@@ -1,0 +1,135 @@
+// bounds_f32.cuh — conservative single-precision BV tests that only STEER the traversal.
+//
+// The reference prunes the BVTT with double-precision RSS distances / OBB overlap tests
+// (math/bv/RSS-inl.h:1957-1974, math/bv/OBB-inl.h:384-523).  A pruning test does not have to
+// reproduce those numbers: any test that never discards a node pair whose subtree could matter
+// gives the same result, because results are produced only by the exact FP64 leaf routines
+// (triDistance / intersect_Triangle):
+//   * distance: a VALID LOWER BOUND lb <= dist(RSS1, RSS2) prunes (lb >= current minimum) only
+//     pairs that cannot improve the minimum, so the final minimum is the minimum over all
+//     triangle pairs, which is the reference's value;
+//   * collide: a test that answers "disjoint" only when the two boxes are certainly disjoint
+//     visits a superset of the reference's BVTT nodes in the same depth-first order, so the
+//     same triangle pairs intersect in the same order.
+// The bounds below are evaluated in FP32 (the FP32 pipe is otherwise idle on this path and
+// issues twice as fast as FP64), are branch-free so all 32 lanes stay converged, and subtract
+// a slack that dominates the worst-case rounding error (derivation in DESIGN.md §4.5):
+//   every intermediate has magnitude <= M = s1 + s2 + |T0|_1 (s = |To|_1 + l0 + l1 + r per
+//   node), inputs are rounded once (relative 2^-24), accumulated absolute error of every
+//   candidate gap <= 1000 u M with u = 2^-24; slack = 1536 u M plus 0.1 % of the bound.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cmath>
+
+namespace fclgpu {
+
+#ifndef FD
+#define FD __host__ __device__ __forceinline__
+#endif
+
+// 64-byte single-precision RSS record: axis[9] row-major, rectangle CENTRE c[3] (not the
+// corner), half side lengths h[2] (rounded up), radius r (rounded up), magnitude scale s
+// (rounded up).
+struct RssRec32 {
+  float a[9];
+  float c[3];
+  float h0, h1, r, s;
+};
+
+FD float f32_rsqrt(float x) {
+#ifdef __CUDA_ARCH__
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+
+// lower bound on the distance between two RSS; R0 (row-major), T0: pose of model2 in model1's
+// frame, t0_l1 >= |T0|_1.  Valid for any inputs: every candidate is the support-function gap
+// along some direction, which never exceeds the true distance between the rectangles.
+FD float rss_lower_bound_f32(const float* R0, const float* T0, float t0_l1, const RssRec32& n1, const RssRec32& n2) {
+  // B = R0 * A2 (columns = B's axes in model1's frame), cB = T0 + R0 * c2
+  float B[9], D[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      B[3 * r + c] = fmaf(R0[3 * r + 2], n2.a[6 + c], fmaf(R0[3 * r + 1], n2.a[3 + c], R0[3 * r] * n2.a[c]));
+    const float cb = fmaf(R0[3 * r + 2], n2.c[2], fmaf(R0[3 * r + 1], n2.c[1], fmaf(R0[3 * r], n2.c[0], T0[r])));
+    D[r] = cb - n1.c[r];
+  }
+  // C[i][j] = a_i . b_j ; DA = A1^T D ; DB = B^T D
+  float C[9], DA[3], DB[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) C[3 * i + j] = fmaf(n1.a[6 + i], B[6 + j], fmaf(n1.a[3 + i], B[3 + j], n1.a[i] * B[j]));
+    DA[i] = fmaf(n1.a[6 + i], D[2], fmaf(n1.a[3 + i], D[1], n1.a[i] * D[0]));
+    DB[i] = fmaf(B[6 + i], D[2], fmaf(B[3 + i], D[1], B[i] * D[0]));
+  }
+  const float hA[3] = {n1.h0, n1.h1, 0.0f}, hB[3] = {n2.h0, n2.h1, 0.0f};
+  float best = 0.0f;
+  // A's three axes, B's three axes
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float ga = fabsf(DA[i]) - hA[i] - fmaf(hB[1], fabsf(C[3 * i + 1]), hB[0] * fabsf(C[3 * i]));
+    const float gb = fabsf(DB[i]) - hB[i] - fmaf(hA[1], fabsf(C[3 + i]), hA[0] * fabsf(C[i]));
+    best = fmaxf(best, fmaxf(ga, gb));
+  }
+  // nine edge-direction cross products a_i x b_j (skipped when nearly parallel: |a_i x b_j|^2 < 1/16)
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      const float len2 = fmaf(-C[3 * i + j], C[3 * i + j], 1.0f);
+      const float num = fabsf(fmaf(DA[i2], C[3 * i1 + j], -(DA[i1] * C[3 * i2 + j])));
+      const float ra = fmaf(hA[i2], fabsf(C[3 * i1 + j]), hA[i1] * fabsf(C[3 * i2 + j]));
+      const float rb = fmaf(hB[j2], fabsf(C[3 * i + j1]), hB[j1] * fabsf(C[3 * i + j2]));
+      const float g = (num - ra - rb) * f32_rsqrt(fmaxf(len2, 0.0625f));
+      best = fmaxf(best, len2 >= 0.0625f ? g : 0.0f);
+    }
+  }
+  const float M = n1.s + n2.s + t0_l1;
+  // centre-to-centre direction (skipped when the centres are close relative to the scale)
+  {
+    const float len2 = fmaf(D[2], D[2], fmaf(D[1], D[1], D[0] * D[0]));
+    const float ra = fmaf(hA[1], fabsf(DA[1]), hA[0] * fabsf(DA[0]));
+    const float rb = fmaf(hB[1], fabsf(DB[1]), hB[0] * fabsf(DB[0]));
+    const float lim = M * (1.0f / 128.0f);
+    const bool ok = len2 >= lim * lim;
+    const float g = (len2 - ra - rb) * f32_rsqrt(ok ? len2 : 1.0f);
+    best = fmaxf(best, ok ? g : 0.0f);
+  }
+  // one refined direction: between the point of rectangle A nearest to B's centre and the point of
+  // rectangle B nearest to A's centre (any direction gives a valid bound; this one is usually tight)
+  {
+    const float pa0 = fminf(fmaxf(DA[0], -hA[0]), hA[0]), pa1 = fminf(fmaxf(DA[1], -hA[1]), hA[1]);
+    const float pb0 = fminf(fmaxf(-DB[0], -hB[0]), hB[0]), pb1 = fminf(fmaxf(-DB[1], -hB[1]), hB[1]);
+    float L[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      L[r] = fmaf(-pa1, n1.a[3 * r + 1], fmaf(-pa0, n1.a[3 * r], fmaf(pb1, B[3 * r + 1], fmaf(pb0, B[3 * r], D[r]))));
+    const float len2 = fmaf(L[2], L[2], fmaf(L[1], L[1], L[0] * L[0]));
+    const float dl = fmaf(L[2], D[2], fmaf(L[1], D[1], L[0] * D[0]));
+    float ra = 0.0f, rb = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float la = fmaf(L[2], n1.a[6 + i], fmaf(L[1], n1.a[3 + i], L[0] * n1.a[i]));
+      const float lb = fmaf(L[2], B[6 + i], fmaf(L[1], B[3 + i], L[0] * B[i]));
+      ra = fmaf(hA[i], fabsf(la), ra);
+      rb = fmaf(hB[i], fabsf(lb), rb);
+    }
+    const float lim = M * (1.0f / 128.0f);
+    const bool ok = len2 >= lim * lim;
+    const float g = (fabsf(dl) - ra - rb) * f32_rsqrt(ok ? len2 : 1.0f);
+    best = fmaxf(best, ok ? g : 0.0f);
+  }
+  const float slack = 9.1552734375e-05f * M;  // 1536 * 2^-24 * M
+  const float lb = fmaf(best, 0.999f, -slack) - (n1.r + n2.r) * 1.000001f;
+  return fmaxf(lb, 0.0f);
+}
+
+}  // namespace fclgpu

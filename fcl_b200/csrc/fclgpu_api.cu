@@ -14,6 +14,7 @@
 
 #include "../../include/fclgpu.h"
 #include "bvh_build.hpp"
+#include "records.hpp"
 #include "traversal.cuh"
 
 using namespace fclgpu;
@@ -129,6 +130,7 @@ struct fclgpu_model {
   int device;
   DeviceModel d;
   double *obb, *rss, *tri;
+  RssRec32* rss32;
   int32_t* fc;
   int depth;
 };
@@ -211,12 +213,22 @@ extern "C" int fclgpu_model_create_obbrss(int device, int32_t n_nodes, const int
     fclgpu_model_destroy(m);
     return rc;
   }
+  {
+    std::vector<RssRec32> r32(n_nodes);
+    for (int i = 0; i < n_nodes; ++i)
+      pack_rss32(axis9 + 9 * (size_t)i, rss_To3 + 3 * (size_t)i, rss_l2 + 2 * (size_t)i, rss_r[i], r32[i]);
+    if (cudaMalloc((void**)&m->rss32, sizeof(RssRec32) * n_nodes) != cudaSuccess ||
+        cudaMemcpy(m->rss32, r32.data(), sizeof(RssRec32) * n_nodes, cudaMemcpyHostToDevice) != cudaSuccess) {
+      fclgpu_model_destroy(m);
+      return fail(FCLGPU_ERR_MODEL_OUT_OF_MEMORY, "rss32 upload failed");
+    }
+  }
   if (cudaMalloc((void**)&m->fc, sizeof(int32_t) * n_nodes) != cudaSuccess ||
       cudaMemcpy(m->fc, first_child, sizeof(int32_t) * n_nodes, cudaMemcpyHostToDevice) != cudaSuccess) {
     fclgpu_model_destroy(m);
     return fail(FCLGPU_ERR_MODEL_OUT_OF_MEMORY, "first_child upload failed");
   }
-  m->d = DeviceModel{m->obb, m->rss, m->fc, m->tri, n_nodes, n_tris};
+  m->d = DeviceModel{m->obb, m->rss, m->fc, m->tri, m->rss32, n_nodes, n_tris};
   *out = m;
   return FCLGPU_OK;
 }
@@ -239,6 +251,7 @@ extern "C" int fclgpu_model_destroy(fclgpu_model* m) {
   cudaFree(m->rss);
   cudaFree(m->tri);
   cudaFree(m->fc);
+  cudaFree(m->rss32);
   delete m;
   return FCLGPU_OK;
 }
@@ -441,7 +454,7 @@ extern "C" int fclgpu_collide_batch(const fclgpu_model* m1, const fclgpu_model* 
     P.n_leaf = n_leaf ? n_leaf + s : nullptr;
     P.work_counter = next_counter(w, st);
     P.status = w->status;
-    if (opt("traversal") == 1) {
+    if (opt("traversal") >= 1) {
       const int trig = (int)opt("leaf_trigger");
       rc = stats ? launch_persistent(collide_deferred_kernel<true>, P, w, 128, st, 0, trig)
                  : launch_persistent(collide_deferred_kernel<false>, P, w, 128, st, 0, trig);
@@ -507,9 +520,14 @@ extern "C" int fclgpu_distance_batch(const fclgpu_model* m1, const fclgpu_model*
   P.work_counter = next_counter(w, st);
   P.status = w->status;
   const bool stats = (n_bv || n_leaf);
-  if (opt("traversal") == 1) {
-    rc = stats ? launch_persistent(distance_warp_kernel<true>, P, w, kDistWarps * 32, st, sizeof(WarpFront) * kDistWarps)
-               : launch_persistent(distance_warp_kernel<false>, P, w, kDistWarps * 32, st, sizeof(WarpFront) * kDistWarps);
+  const long long trav = opt("traversal");
+  const size_t front_smem = sizeof(WarpFront) * kDistWarps;
+  if (trav >= 2) {
+    rc = stats ? launch_persistent(distance_warp_kernel<true, true>, P, w, kDistWarps * 32, st, front_smem)
+               : launch_persistent(distance_warp_kernel<false, true>, P, w, kDistWarps * 32, st, front_smem);
+  } else if (trav == 1) {
+    rc = stats ? launch_persistent(distance_warp_kernel<true, false>, P, w, kDistWarps * 32, st, front_smem)
+               : launch_persistent(distance_warp_kernel<false, false>, P, w, kDistWarps * 32, st, front_smem);
   } else {
     rc = stats ? launch_persistent(distance_thread_kernel<true>, P, w, 128, st)
                : launch_persistent(distance_thread_kernel<false>, P, w, 128, st);

@@ -11,6 +11,7 @@
 #include <cstdint>
 
 #include "../../include/fclgpu.h"
+#include "bounds_f32.cuh"
 #include "device_math.cuh"
 
 namespace fclgpu {
@@ -29,6 +30,7 @@ struct DeviceModel {
   const double* rss;
   const int32_t* first_child;
   const double* tri;
+  const RssRec32* rss32;  // single-precision steering records (bounds_f32.cuh), 64 B per node
   int32_t n_nodes, n_tris;
 };
 
@@ -54,6 +56,17 @@ __device__ __forceinline__ NodeRec load_node(const double* __restrict__ base, in
   n.To = mk(v4.y, v5.x, v5.y);
   n.e0 = v6.x; n.e1 = v6.y; n.e2 = v7.x;
   n.size = v7.y;
+  return n;
+}
+
+__device__ __forceinline__ RssRec32 load_rss32(const RssRec32* __restrict__ base, int idx) {
+  const float4* p = reinterpret_cast<const float4*>(base + idx);
+  const float4 v0 = __ldg(p + 0), v1 = __ldg(p + 1), v2 = __ldg(p + 2), v3 = __ldg(p + 3);
+  RssRec32 n;
+  n.a[0] = v0.x; n.a[1] = v0.y; n.a[2] = v0.z; n.a[3] = v0.w;
+  n.a[4] = v1.x; n.a[5] = v1.y; n.a[6] = v1.z; n.a[7] = v1.w;
+  n.a[8] = v2.x; n.c[0] = v2.y; n.c[1] = v2.z; n.c[2] = v2.w;
+  n.h0 = v3.x; n.h1 = v3.y; n.r = v3.z; n.s = v3.w;
   return n;
 }
 
@@ -422,9 +435,9 @@ constexpr int kLeafTrigger = 32;
 constexpr int kDistWarps = 4;        // warps per block
 
 struct __align__(16) WarpFront {
-  double bound[kDistStackCap];
+  float bound[kDistStackCap];   // lower bounds are stored in single precision, rounded down
   uint2 pair[kDistStackCap];
-  double leaf_bound[kLeafCap];
+  float leaf_bound[kLeafCap];
   uint2 leaf_pair[kLeafCap];  // triangle ids
   uint2 expand[32];           // child pairs handed from the entry's holder lane to the two testing lanes
   double best[6];
@@ -463,7 +476,7 @@ __device__ __forceinline__ unsigned warp_sort_keys(unsigned key, int lane) {
 #ifndef FCLGPU_DIST_MINBLOCKS
 #define FCLGPU_DIST_MINBLOCKS 4
 #endif
-template <bool kStats>
+template <bool kStats, bool kBound32>
 __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distance_warp_kernel(DistanceParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WarpFront& S = reinterpret_cast<WarpFront*>(smem_raw)[threadIdx.x >> 5];
@@ -485,15 +498,22 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
       const V3 it = mulTv(tf1.R, tf1.t);
       T = mulTv(tf1.R, tf2.t) + mk(-it.x, -it.y, -it.z);
     }
+    float Rf[9], Tf[3], t_l1 = 0.0f;
+    if (kBound32) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) Rf[k] = (float)R.m[k];
+      Tf[0] = (float)T.x; Tf[1] = (float)T.y; Tf[2] = (float)T.z;
+      t_l1 = __double2float_ru((fabs(T.x) + fabs(T.y)) + fabs(T.z));
+    }
 
     double min_d = 1.7976931348623157e308;
     int sp = 1, nleaf = 1;
     uint32_t bv_tests = 0, leaf_tests = 0;
     if (lane == 0) {
       S.pair[0] = make_uint2(0u, 0u);
-      S.bound[0] = -1.0;                    // the root pair is never bound-tested
+      S.bound[0] = -1.0f;                   // the root pair is never bound-tested
       S.leaf_pair[0] = make_uint2(0u, 0u);  // preprocess: triangle 0 / triangle 0 seeds the result
-      S.leaf_bound[0] = -1.0;
+      S.leaf_bound[0] = -1.0f;
       S.best_id[0] = S.best_id[1] = -1;
 #pragma unroll
       for (int k = 0; k < 6; ++k) S.best[k] = 0.0;
@@ -511,7 +531,7 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
         bool mine = lane < k;
         if (mine) {
           ids = S.leaf_pair[nleaf + lane];
-          mine = S.leaf_bound[nleaf + lane] < min_d;
+          mine = (double)S.leaf_bound[nleaf + lane] < min_d;
         }
         if (kStats) leaf_tests += __popc(__ballot_sync(0xffffffffu, mine));
         if (mine) {
@@ -555,12 +575,12 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
       // expanded by two lanes each and the remaining internal entries go back on the stack.
       const int k = sp < 32 ? sp : 32;
       uint2 pr = make_uint2(0u, 0u);
-      double bd = 0.0;
+      float bd = 0.0f;
       bool alive = lane < k;
       if (alive) {
         pr = S.pair[sp - 1 - lane];
         bd = S.bound[sp - 1 - lane];
-        alive = bd < min_d;  // canStop(c): bound >= min_distance -> skip
+        alive = (double)bd < min_d;  // canStop(c): bound >= min_distance -> skip
       }
       int fc1 = 0, fc2 = 0;
       if (alive) {
@@ -612,14 +632,20 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
       const bool expand = lane < 2 * n_exp;
       unsigned key = 0xffffffffu;
       uint2 xy = make_uint2(0u, 0u);
-      double d = 0.0;
+      float d = 0.0f;  // lower bound on the distance between the two child BVs
       if (expand) {
         xy = S.expand[lane];
-        const NodeRec n1 = load_node(P.m1.rss, (int)xy.x);
-        const NodeRec n2 = load_node(P.m2.rss, (int)xy.y);
-        const double la[2] = {n1.e0, n1.e1}, lb[2] = {n2.e0, n2.e1};
-        d = rss_pair_distance(R, T, n1.axis, n1.To, la, n1.e2, n2.axis, n2.To, lb, n2.e2);
-        if (d < min_d) key = (__float_as_uint(__double2float_rd(d)) & ~31u) | (unsigned)lane;
+        if (kBound32) {
+          const RssRec32 n1 = load_rss32(P.m1.rss32, (int)xy.x);
+          const RssRec32 n2 = load_rss32(P.m2.rss32, (int)xy.y);
+          d = rss_lower_bound_f32(Rf, Tf, t_l1, n1, n2);
+        } else {
+          const NodeRec n1 = load_node(P.m1.rss, (int)xy.x);
+          const NodeRec n2 = load_node(P.m2.rss, (int)xy.y);
+          const double la[2] = {n1.e0, n1.e1}, lb[2] = {n2.e0, n2.e1};
+          d = __double2float_rd(rss_pair_distance(R, T, n1.axis, n1.To, la, n1.e2, n2.axis, n2.To, lb, n2.e2));
+        }
+        if ((double)d < min_d) key = (__float_as_uint(d) & ~31u) | (unsigned)lane;
       }
       if (kStats) bv_tests += 2 * n_exp;
       const int nkeep = __popc(__ballot_sync(0xffffffffu, key != 0xffffffffu));
@@ -627,7 +653,7 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
         key = warp_sort_keys(key, lane);  // ascending: lane 0 = nearest
         const int src = (int)(key & 31u);
         const unsigned long long v = shfl_u64(((unsigned long long)xy.x << 32) | xy.y, src);
-        const double dv = __longlong_as_double((long long)shfl_u64((unsigned long long)__double_as_longlong(d), src));
+        const float dv = __shfl_sync(0xffffffffu, d, src);
         if (lane < nkeep) {  // nearest ends on top of the stack
           const int pos = sp + (nkeep - 1 - lane);
           S.pair[pos] = make_uint2((unsigned)(v >> 32), (unsigned)v);

@@ -7,12 +7,14 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "devmath_host.cu")
-_HDR = os.path.join(_HERE, "..", "..", "fcl_b200", "csrc", "device_math.cuh")
+_CSRC = os.path.join(_HERE, "..", "..", "fcl_b200", "csrc")
+_HDR = os.path.join(_CSRC, "device_math.cuh")
+_HDRS = [os.path.join(_CSRC, f) for f in ("device_math.cuh", "bounds_f32.cuh", "records.hpp")]
 _OUT = os.path.join(_HERE, "_build", "libdevmath_host.so")
 
 
 def build():
-    stale = (not os.path.exists(_OUT)) or any(os.path.getmtime(s) > os.path.getmtime(_OUT) for s in (_SRC, _HDR))
+    stale = (not os.path.exists(_OUT)) or any(os.path.getmtime(s) > os.path.getmtime(_OUT) for s in [_SRC] + _HDRS)
     if stale:
         os.makedirs(os.path.dirname(_OUT), exist_ok=True)
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler",
@@ -38,6 +40,7 @@ def lib():
         L.hm_tri_intersect.argtypes = [dp, dp, dp, C.c_int, C.POINTER(C.c_uint32), dp, dp, dp]
         L.hm_tri_distance.restype = C.c_double
         L.hm_tri_distance.argtypes = [dp, dp, dp, dp]
+        L.hm_rss_lb32_pairs.argtypes = [C.c_longlong, dp, ip, ip, dp, dp, dp, dp, dp, dp, dp, dp, C.POINTER(C.c_float)]
         _lib = L
     return _lib
 

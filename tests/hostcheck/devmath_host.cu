@@ -1,6 +1,8 @@
 // Test-only: compiles the product's device math header for the HOST so that the CPU test
 // suite can compare it bit-for-bit with the oracle without a GPU.  Not part of the product.
 #include "../../fcl_b200/csrc/device_math.cuh"
+#include "../../fcl_b200/csrc/bounds_f32.cuh"
+#include "../../fcl_b200/csrc/records.hpp"
 using namespace fclgpu;
 
 static M3 m3(const double* r) { M3 M; for (int i = 0; i < 9; ++i) M.m[i] = r[i]; return M; }
@@ -56,5 +58,19 @@ double hm_tri_distance(const double* S9, const double* T9, double* P3, double* Q
   double d = tri_distance(S, T, P, Q);
   P3[0] = P.x; P3[1] = P.y; P3[2] = P.z; Q3[0] = Q.x; Q3[1] = Q.y; Q3[2] = Q.z;
   return d;
+}
+// conservative FP32 RSS lower bound on n node pairs (records packed exactly like the upload step does)
+void hm_rss_lb32_pairs(long long n, const double* pose12, const int* idx1, const int* idx2,
+                       const double* axis1, const double* To1, const double* l1, const double* r1,
+                       const double* axis2, const double* To2, const double* l2, const double* r2, float* out) {
+  for (long long k = 0; k < n; ++k) {
+    int i = idx1[k], j = idx2[k];
+    RssRec32 a, b;
+    pack_rss32(axis1 + 9 * i, To1 + 3 * i, l1 + 2 * i, r1[i], a);
+    pack_rss32(axis2 + 9 * j, To2 + 3 * j, l2 + 2 * j, r2[j], b);
+    float R0[9], T0[3], t1;
+    pack_pose32(pose12 + 12 * k, pose12 + 12 * k + 9, R0, T0, t1);
+    out[k] = rss_lower_bound_f32(R0, T0, t1, a, b);
+  }
 }
 }

@@ -140,3 +140,39 @@ def test_tri_distance_matches_oracle(hm, oracle):
         assert Pg.tobytes() == Po.tobytes() and Qg.tobytes() == Qo.tobytes(), k
         zero += g == 0
     assert 0 < zero < n
+
+
+def test_f32_rss_lower_bound_is_conservative(hm, oracle, oracle_env_rob):
+    """The single-precision steering bound must never exceed the exact RSS distance (it may be
+    smaller): checked on real node pairs at the benchmark's pose distribution and on close /
+    near-parallel / huge-offset configurations."""
+    import ctypes as C
+
+    env, rob = oracle_env_rob
+    a1, a2 = env.arrays(), rob.arrays()
+    rng = np.random.default_rng(23)
+    n = 300000
+    rel = _rel_pose(random_poses(n, seed=31))
+    rel[: n // 3, 9:] *= rng.uniform(0, 0.3, size=(n // 3, 1))           # close configurations
+    q = n // 3
+    ang = np.round(rng.uniform(0, 2 * np.pi, size=(q, 3)) / (np.pi / 2)) * (np.pi / 2) + rng.normal(0, 1e-6, size=(q, 3))
+    from fcl_b200.poses import euler_to_matrix
+    rel[q:2 * q, :9] = euler_to_matrix(ang[:, 0], ang[:, 1], ang[:, 2]).reshape(q, 9)  # near axis-aligned
+    rel[-2000:, 9:] *= 50.0                                              # far away (large magnitudes)
+    i1 = rng.integers(0, env.num_bvs, n).astype(np.int32)
+    i2 = rng.integers(0, rob.num_bvs, n).astype(np.int32)
+    exact = np.empty(n)
+    L = hm.lib()
+    L.hm_rss_pairs(n, hm.dptr(rel), hm.iptr(i1), hm.iptr(i2), hm.dptr(a1["axis"]), hm.dptr(a1["rss_To"]),
+                   hm.dptr(a1["rss_l"]), hm.dptr(a1["rss_r"]), hm.dptr(a2["axis"]), hm.dptr(a2["rss_To"]),
+                   hm.dptr(a2["rss_l"]), hm.dptr(a2["rss_r"]), hm.dptr(exact))
+    lb = np.empty(n, np.float32)
+    L.hm_rss_lb32_pairs(n, hm.dptr(rel), hm.iptr(i1), hm.iptr(i2), hm.dptr(a1["axis"]), hm.dptr(a1["rss_To"]),
+                        hm.dptr(a1["rss_l"]), hm.dptr(a1["rss_r"]), hm.dptr(a2["axis"]), hm.dptr(a2["rss_To"]),
+                        hm.dptr(a2["rss_l"]), hm.dptr(a2["rss_r"]), lb.ctypes.data_as(C.POINTER(C.c_float)))
+    lb = lb.astype(np.float64)
+    assert (lb <= exact).all(), float((lb - exact).max())
+    # and it is a useful bound: on separated pairs it recovers most of the exact distance
+    sep = exact > 50
+    assert sep.sum() > 10000
+    assert np.median(lb[sep] / exact[sep]) > 0.9
