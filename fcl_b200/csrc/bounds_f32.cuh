@@ -132,4 +132,65 @@ FD float rss_lower_bound_f32(const float* R0, const float* T0, float t0_l1, cons
   return fmaxf(lb, 0.0f);
 }
 
+
+// 64-byte single-precision OBB record: axis[9] row-major, centre c[3], half extents e[3]
+// (rounded up), magnitude scale s = |c|_1 + |e|_1 (rounded up).
+struct ObbRec32 {
+  float a[9];
+  float c[3];
+  float e[3];
+  float s;
+};
+
+// true only when the two boxes are CERTAINLY disjoint: some axis of the 15-axis SAT separates
+// them by more than the worst-case single-precision rounding error (256 u M, unnormalised
+// axes; see the error budget at the top of this file).  "false" means "maybe overlapping":
+// the traversal then descends, which can only add work, never change a result.
+FD bool obb_certainly_disjoint_f32(const float* R0, const float* T0, float t0_l1, const ObbRec32& n1, const ObbRec32& n2) {
+  float B[9], D[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      B[3 * r + c] = fmaf(R0[3 * r + 2], n2.a[6 + c], fmaf(R0[3 * r + 1], n2.a[3 + c], R0[3 * r] * n2.a[c]));
+    const float cb = fmaf(R0[3 * r + 2], n2.c[2], fmaf(R0[3 * r + 1], n2.c[1], fmaf(R0[3 * r], n2.c[0], T0[r])));
+    D[r] = cb - n1.c[r];
+  }
+  float C[9], DA[3], DB[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      C[3 * i + j] = fabsf(fmaf(n1.a[6 + i], B[6 + j], fmaf(n1.a[3 + i], B[3 + j], n1.a[i] * B[j])));
+    DA[i] = fmaf(n1.a[6 + i], D[2], fmaf(n1.a[3 + i], D[1], n1.a[i] * D[0]));
+    DB[i] = fmaf(B[6 + i], D[2], fmaf(B[3 + i], D[1], B[i] * D[0]));
+  }
+  // signed products for the cross axes need the signed C: recompute sign-carrying terms from A1, B
+  float best = -3.0e38f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float ga = fabsf(DA[i]) - n1.e[i] - fmaf(n2.e[2], C[3 * i + 2], fmaf(n2.e[1], C[3 * i + 1], n2.e[0] * C[3 * i]));
+    const float gb = fabsf(DB[i]) - n2.e[i] - fmaf(n1.e[2], C[6 + i], fmaf(n1.e[1], C[3 + i], n1.e[0] * C[i]));
+    best = fmaxf(best, fmaxf(ga, gb));
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      // D . (a_i x b_j) = (D x a_i) . b_j, evaluated directly (no signed C needed)
+      const float ux = fmaf(D[1], n1.a[6 + i], -(D[2] * n1.a[3 + i]));
+      const float uy = fmaf(D[2], n1.a[i], -(D[0] * n1.a[6 + i]));
+      const float uz = fmaf(D[0], n1.a[3 + i], -(D[1] * n1.a[i]));
+      const float num = fabsf(fmaf(uz, B[6 + j], fmaf(uy, B[3 + j], ux * B[j])));
+      const float ra = fmaf(n1.e[i2], C[3 * i1 + j], n1.e[i1] * C[3 * i2 + j]);
+      const float rb = fmaf(n2.e[j2], C[3 * i + j1], n2.e[j1] * C[3 * i + j2]);
+      best = fmaxf(best, num - ra - rb);
+    }
+  }
+  const float M = n1.s + n2.s + t0_l1;
+  return best > 1.52587890625e-05f * M;  // 256 * 2^-24 * M
+}
+
 }  // namespace fclgpu

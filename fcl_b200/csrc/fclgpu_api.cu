@@ -49,9 +49,11 @@ int fail(int code, const char* fmt, ...) {
 // options
 std::mutex g_opt_mu;
 std::map<std::string, long long> g_opts = {
-    // 1 (default): collide = thread per query with deferred leaf rounds, distance = warp per query sorted front
+    // 2 (default): like 1, but the BV tests that steer the traversal are conservative single-precision tests
+    //    (bounds_f32.cuh); every result still comes from the exact FP64 triangle routines
+    // 1: collide = thread per query with deferred leaf rounds, distance = warp per query sorted front, FP64 BV tests
     // 0: thread per query, the reference's visiting order exactly (work counters match the reference's)
-    {"traversal", 1},
+    {"traversal", 2},
     {"contact_stride", 1024},  // per-query contact scratch slots when num_max_contacts is larger
     {"scratch_bytes", 2ll << 30},
     {"blocks_per_sm", 0},      // 0 = occupancy query
@@ -131,6 +133,8 @@ struct fclgpu_model {
   DeviceModel d;
   double *obb, *rss, *tri;
   RssRec32* rss32;
+  ObbRec32* obb32;
+  double2* topo;
   int32_t* fc;
   int depth;
 };
@@ -223,12 +227,29 @@ extern "C" int fclgpu_model_create_obbrss(int device, int32_t n_nodes, const int
       return fail(FCLGPU_ERR_MODEL_OUT_OF_MEMORY, "rss32 upload failed");
     }
   }
+  {
+    std::vector<ObbRec32> o32(n_nodes);
+    std::vector<double2> topo(n_nodes);
+    for (int i = 0; i < n_nodes; ++i) {
+      pack_obb32(axis9 + 9 * (size_t)i, obb_To3 + 3 * (size_t)i, obb_extent3 + 3 * (size_t)i, o32[i]);
+      long long bits = (long long)(unsigned)first_child[i];  // low word = first_child
+      std::memcpy(&topo[i].x, &bits, 8);
+      topo[i].y = obb[(size_t)i * kNodeDoubles + 15];
+    }
+    if (cudaMalloc((void**)&m->obb32, sizeof(ObbRec32) * n_nodes) != cudaSuccess ||
+        cudaMemcpy(m->obb32, o32.data(), sizeof(ObbRec32) * n_nodes, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMalloc((void**)&m->topo, sizeof(double2) * n_nodes) != cudaSuccess ||
+        cudaMemcpy(m->topo, topo.data(), sizeof(double2) * n_nodes, cudaMemcpyHostToDevice) != cudaSuccess) {
+      fclgpu_model_destroy(m);
+      return fail(FCLGPU_ERR_MODEL_OUT_OF_MEMORY, "obb32/topo upload failed");
+    }
+  }
   if (cudaMalloc((void**)&m->fc, sizeof(int32_t) * n_nodes) != cudaSuccess ||
       cudaMemcpy(m->fc, first_child, sizeof(int32_t) * n_nodes, cudaMemcpyHostToDevice) != cudaSuccess) {
     fclgpu_model_destroy(m);
     return fail(FCLGPU_ERR_MODEL_OUT_OF_MEMORY, "first_child upload failed");
   }
-  m->d = DeviceModel{m->obb, m->rss, m->fc, m->tri, m->rss32, n_nodes, n_tris};
+  m->d = DeviceModel{m->obb, m->rss, m->fc, m->tri, m->rss32, m->obb32, m->topo, n_nodes, n_tris};
   *out = m;
   return FCLGPU_OK;
 }
@@ -252,6 +273,8 @@ extern "C" int fclgpu_model_destroy(fclgpu_model* m) {
   cudaFree(m->tri);
   cudaFree(m->fc);
   cudaFree(m->rss32);
+  cudaFree(m->obb32);
+  cudaFree(m->topo);
   delete m;
   return FCLGPU_OK;
 }
@@ -454,10 +477,14 @@ extern "C" int fclgpu_collide_batch(const fclgpu_model* m1, const fclgpu_model* 
     P.n_leaf = n_leaf ? n_leaf + s : nullptr;
     P.work_counter = next_counter(w, st);
     P.status = w->status;
-    if (opt("traversal") >= 1) {
-      const int trig = (int)opt("leaf_trigger");
-      rc = stats ? launch_persistent(collide_deferred_kernel<true>, P, w, 128, st, 0, trig)
-                 : launch_persistent(collide_deferred_kernel<false>, P, w, 128, st, 0, trig);
+    const long long trav = opt("traversal");
+    const int trig = (int)opt("leaf_trigger");
+    if (trav >= 2) {
+      rc = stats ? launch_persistent(collide_deferred_kernel<true, true>, P, w, 128, st, 0, trig)
+                 : launch_persistent(collide_deferred_kernel<false, true>, P, w, 128, st, 0, trig);
+    } else if (trav == 1) {
+      rc = stats ? launch_persistent(collide_deferred_kernel<true, false>, P, w, 128, st, 0, trig)
+                 : launch_persistent(collide_deferred_kernel<false, false>, P, w, 128, st, 0, trig);
     } else {
       rc = stats ? launch_persistent(collide_thread_kernel<true>, P, w, 128, st)
                  : launch_persistent(collide_thread_kernel<false>, P, w, 128, st);

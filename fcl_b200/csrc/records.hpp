@@ -29,6 +29,17 @@ inline void pack_rss32(const double* axis9, const double* To, const double* l, d
   o.s = round_up_f32(s + l[0] + l[1] + r);
 }
 
+inline void pack_obb32(const double* axis9, const double* To, const double* ext, ObbRec32& o) {
+  for (int k = 0; k < 9; ++k) o.a[k] = (float)axis9[k];
+  double s = 0;
+  for (int k = 0; k < 3; ++k) {
+    o.c[k] = (float)To[k];
+    o.e[k] = round_up_f32(ext[k]);
+    s += std::fabs(To[k]) + ext[k];
+  }
+  o.s = round_up_f32(s);
+}
+
 inline void pack_pose32(const double* R9, const double* T3, float* R0, float* T0, float& t_l1) {
   for (int k = 0; k < 9; ++k) R0[k] = (float)R9[k];
   double s = 0;

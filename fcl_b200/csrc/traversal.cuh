@@ -31,6 +31,8 @@ struct DeviceModel {
   const int32_t* first_child;
   const double* tri;
   const RssRec32* rss32;  // single-precision steering records (bounds_f32.cuh), 64 B per node
+  const ObbRec32* obb32;
+  const double2* topo;    // per node {first_child (int32 in the low word of .x), size}: one LDG.128
   int32_t n_nodes, n_tris;
 };
 
@@ -68,6 +70,23 @@ __device__ __forceinline__ RssRec32 load_rss32(const RssRec32* __restrict__ base
   n.a[8] = v2.x; n.c[0] = v2.y; n.c[1] = v2.z; n.c[2] = v2.w;
   n.h0 = v3.x; n.h1 = v3.y; n.r = v3.z; n.s = v3.w;
   return n;
+}
+
+__device__ __forceinline__ ObbRec32 load_obb32(const ObbRec32* __restrict__ base, int idx) {
+  const float4* p = reinterpret_cast<const float4*>(base + idx);
+  const float4 v0 = __ldg(p + 0), v1 = __ldg(p + 1), v2 = __ldg(p + 2), v3 = __ldg(p + 3);
+  ObbRec32 n;
+  n.a[0] = v0.x; n.a[1] = v0.y; n.a[2] = v0.z; n.a[3] = v0.w;
+  n.a[4] = v1.x; n.a[5] = v1.y; n.a[6] = v1.z; n.a[7] = v1.w;
+  n.a[8] = v2.x; n.c[0] = v2.y; n.c[1] = v2.z; n.c[2] = v2.w;
+  n.e[0] = v3.x; n.e[1] = v3.y; n.e[2] = v3.z; n.s = v3.w;
+  return n;
+}
+
+__device__ __forceinline__ void load_topo(const double2* __restrict__ base, int idx, int& first_child, double& size) {
+  const double2 t = __ldg(base + idx);
+  first_child = __double2loint(t.x);
+  size = t.y;
 }
 
 __device__ __forceinline__ void load_tri(const double* __restrict__ base, int t, V3 out[3]) {
@@ -710,8 +729,11 @@ constexpr int kLeafFifo = 8;  // deferred pairs per lane (power of two)
 #ifndef FCLGPU_COLLIDE_MINBLOCKS
 #define FCLGPU_COLLIDE_MINBLOCKS 3
 #endif
-template <bool kStats>
-__global__ void __launch_bounds__(128, FCLGPU_COLLIDE_MINBLOCKS) collide_deferred_kernel(CollideParams P, int leaf_trigger) {
+#ifndef FCLGPU_COLLIDE32_MINBLOCKS
+#define FCLGPU_COLLIDE32_MINBLOCKS 3
+#endif
+template <bool kStats, bool kSat32>
+__global__ void __launch_bounds__(128, kSat32 ? FCLGPU_COLLIDE32_MINBLOCKS : FCLGPU_COLLIDE_MINBLOCKS) collide_deferred_kernel(CollideParams P, int leaf_trigger) {
   __shared__ uint2 fifo[4][kLeafFifo][32];  // [warp][slot][lane]
   uint2 stk[kStackCap];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -720,6 +742,7 @@ __global__ void __launch_bounds__(128, FCLGPU_COLLIDE_MINBLOCKS) collide_deferre
   PoseRT tf1;
   M3 R;
   V3 T;
+  float Rf[9], Tf[3], t_l1 = 0.0f;
   long long count = 0;
   uint32_t bv_tests = 0, leaf_tests = 0;
   bool exhausted = false;
@@ -743,6 +766,12 @@ __global__ void __launch_bounds__(128, FCLGPU_COLLIDE_MINBLOCKS) collide_deferre
         const PoseRT tf2 = load_pose(P.tf2, q);
         R = mulTM(tf1.R, tf2.R);
         T = mulTv(tf1.R, tf2.t - tf1.t);
+        if (kSat32) {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) Rf[k] = (float)R.m[k];
+          Tf[0] = (float)T.x; Tf[1] = (float)T.y; Tf[2] = (float)T.z;
+          t_l1 = __double2float_ru((fabs(T.x) + fabs(T.y)) + fabs(T.z));
+        }
         count = 0;
         bv_tests = leaf_tests = 0;
         stk[0] = make_uint2(0u, 0u);
@@ -821,12 +850,26 @@ __global__ void __launch_bounds__(128, FCLGPU_COLLIDE_MINBLOCKS) collide_deferre
     if (sp > 0 && qcount < kLeafFifo) {
       const uint2 e = stk[--sp];
       const int b1 = (int)e.x, b2 = (int)e.y;
-      const NodeRec n1 = load_node(P.m1.obb, b1);
-      const NodeRec n2 = load_node(P.m2.obb, b2);
-      const int fc1 = __ldg(P.m1.first_child + b1);
-      const int fc2 = __ldg(P.m2.first_child + b2);
+      int fc1, fc2;
+      double size1, size2;
+      bool disjoint;
+      if (kSat32) {
+        const ObbRec32 n1 = load_obb32(P.m1.obb32, b1);
+        const ObbRec32 n2 = load_obb32(P.m2.obb32, b2);
+        load_topo(P.m1.topo, b1, fc1, size1);
+        load_topo(P.m2.topo, b2, fc2, size2);
+        disjoint = obb_certainly_disjoint_f32(Rf, Tf, t_l1, n1, n2);
+      } else {
+        const NodeRec n1 = load_node(P.m1.obb, b1);
+        const NodeRec n2 = load_node(P.m2.obb, b2);
+        fc1 = __ldg(P.m1.first_child + b1);
+        fc2 = __ldg(P.m2.first_child + b2);
+        size1 = n1.size;
+        size2 = n2.size;
+        disjoint = obb_pair_disjoint(R, T, n1.axis, n1.To, mk(n1.e0, n1.e1, n1.e2), n2.axis, n2.To, mk(n2.e0, n2.e1, n2.e2));
+      }
       if (kStats) bv_tests++;
-      if (!obb_pair_disjoint(R, T, n1.axis, n1.To, mk(n1.e0, n1.e1, n1.e2), n2.axis, n2.To, mk(n2.e0, n2.e1, n2.e2))) {
+      if (!disjoint) {
         const bool l1 = fc1 < 0, l2 = fc2 < 0;
         if (l1 && l2) {
           fifo[wid][(qhead + qcount) & (kLeafFifo - 1)][lane] = make_uint2((unsigned)(-(fc1 + 1)), (unsigned)(-(fc2 + 1)));
@@ -837,7 +880,7 @@ __global__ void __launch_bounds__(128, FCLGPU_COLLIDE_MINBLOCKS) collide_deferre
           qcount = 0;
         } else {
           uint2 left, right;
-          if (l2 || (!l1 && (n1.size > n2.size))) {
+          if (l2 || (!l1 && (size1 > size2))) {
             left = make_uint2((unsigned)fc1, (unsigned)b2);
             right = make_uint2((unsigned)fc1 + 1u, (unsigned)b2);
           } else {

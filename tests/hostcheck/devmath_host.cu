@@ -73,4 +73,17 @@ void hm_rss_lb32_pairs(long long n, const double* pose12, const int* idx1, const
     out[k] = rss_lower_bound_f32(R0, T0, t1, a, b);
   }
 }
+void hm_obb_disjoint32_pairs(long long n, const double* pose12, const int* idx1, const int* idx2,
+                             const double* axis1, const double* To1, const double* ext1,
+                             const double* axis2, const double* To2, const double* ext2, int* out) {
+  for (long long k = 0; k < n; ++k) {
+    int i = idx1[k], j = idx2[k];
+    ObbRec32 a, b;
+    pack_obb32(axis1 + 9 * i, To1 + 3 * i, ext1 + 3 * i, a);
+    pack_obb32(axis2 + 9 * j, To2 + 3 * j, ext2 + 3 * j, b);
+    float R0[9], T0[3], t1;
+    pack_pose32(pose12 + 12 * k, pose12 + 12 * k + 9, R0, T0, t1);
+    out[k] = obb_certainly_disjoint_f32(R0, T0, t1, a, b) ? 1 : 0;
+  }
+}
 }

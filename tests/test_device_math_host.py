@@ -176,3 +176,35 @@ def test_f32_rss_lower_bound_is_conservative(hm, oracle, oracle_env_rob):
     sep = exact > 50
     assert sep.sum() > 10000
     assert np.median(lb[sep] / exact[sep]) > 0.9
+
+
+def test_f32_obb_sat_is_conservative(hm, oracle_env_rob):
+    """"certainly disjoint" in single precision must imply disjoint for the exact (FP64) SAT, and
+    it should recognise almost every disjoint pair (otherwise the traversal would do extra work)."""
+    env, rob = oracle_env_rob
+    a1, a2 = env.arrays(), rob.arrays()
+    rng = np.random.default_rng(29)
+    n = 400000
+    rel = _rel_pose(random_poses(n, seed=37))
+    rel[: n // 2, 9:] *= rng.uniform(0, 0.4, size=(n // 2, 1))
+    i1 = rng.integers(0, env.num_bvs, n).astype(np.int32)
+    i2 = rng.integers(0, rob.num_bvs, n).astype(np.int32)
+    # a third of the pairs: put box 2 next to box 1 (touching / barely separated / overlapping)
+    m = n // 3
+    R0 = rel[:m, :9].reshape(m, 3, 3)
+    c1, c2 = a1["obb_To"][i1[:m]], a2["obb_To"][i2[:m]]
+    reach = np.linalg.norm(a1["obb_ext"][i1[:m]], axis=1) + np.linalg.norm(a2["obb_ext"][i2[:m]], axis=1)
+    dirs = rng.normal(size=(m, 3))
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    rel[:m, 9:] = c1 - np.einsum("nij,nj->ni", R0, c2) + dirs * (reach * rng.uniform(0.0, 1.1, size=m))[:, None]
+    L = hm.lib()
+    exact = np.empty(n, np.int32)
+    L.hm_obb_pairs(n, hm.dptr(rel), hm.iptr(i1), hm.iptr(i2), hm.dptr(a1["axis"]), hm.dptr(a1["obb_To"]),
+                   hm.dptr(a1["obb_ext"]), hm.dptr(a2["axis"]), hm.dptr(a2["obb_To"]), hm.dptr(a2["obb_ext"]), hm.iptr(exact))
+    got = np.empty(n, np.int32)
+    L.hm_obb_disjoint32_pairs(n, hm.dptr(rel), hm.iptr(i1), hm.iptr(i2), hm.dptr(a1["axis"]), hm.dptr(a1["obb_To"]),
+                              hm.dptr(a1["obb_ext"]), hm.dptr(a2["axis"]), hm.dptr(a2["obb_To"]), hm.dptr(a2["obb_ext"]), hm.iptr(got))
+    assert not np.any((got == 1) & (exact == 0))          # never "disjoint" when the exact test says overlap
+    assert exact.sum() > n // 10 and (exact == 0).sum() > n // 20
+    missed = ((got == 0) & (exact == 1)).sum()
+    assert missed < 2e-3 * exact.sum(), missed            # sharp: < 0.2 % of disjoint pairs left undecided

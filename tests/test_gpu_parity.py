@@ -26,7 +26,7 @@ def models(env_rob_npz, oracle):
 def traversal(request):
     _capi.set_option("traversal", request.param)
     yield request.param
-    _capi.set_option("traversal", 1)  # library default
+    _capi.set_option("traversal", 2)  # library default
 
 
 def _contacts_equal(got, ref):
