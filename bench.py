@@ -147,7 +147,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="distance", choices=sorted(WORKLOADS))
@@ -300,11 +300,11 @@ def main():
 
         def step_e2e():
             if wl == "distance":
-                r = F.distance_batch(env, hp, rob, None, dreq, device=local)
+                r = F.distance_batch(env, hp, rob, None, dreq, device=local, pinned=True)
                 return r.min_distance
             if wl == "collide":
-                return F.collide_batch(env, hp, rob, None, creq, want_contacts=False, device=local).num_contacts
-            return F.collide_batch(env, hp, rob, None, creq, contact_capacity=64 * n, device=local).num_contacts
+                return F.collide_batch(env, hp, rob, None, creq, want_contacts=False, device=local, pinned=True).num_contacts
+            return F.collide_batch(env, hp, rob, None, creq, contact_capacity=40 * n, device=local, pinned=True).num_contacts
 
         for _ in range(2):
             step_e2e()

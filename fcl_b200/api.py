@@ -346,6 +346,27 @@ class DistanceResult:
 # ------------------------------------------------------------------------------------------------
 # batched entry points (the product)
 # ------------------------------------------------------------------------------------------------
+_PINNED_POOL = {}
+
+
+def _out(shape, dtype, pinned, tag=""):
+    """Output buffer: plain numpy, or page-locked (pinned) host memory so that the device->host copy is
+    asynchronous and overlaps the next chunk's kernel.  Pinned buffers come from a small pool keyed by
+    (tag, size) and are REUSED by the next call with the same shapes (page-locking gigabytes per call
+    would cost more than the copy), so a pinned result is valid until that next call.
+    Returns (array, keepalive)."""
+    if not pinned:
+        return np.zeros(shape, dtype), None
+    torch = _torch()
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    key = (tag, nbytes)
+    t = _PINNED_POOL.get(key)
+    if t is None:
+        t = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
+        _PINNED_POOL[key] = t
+    return t.numpy()[:nbytes].view(dtype).reshape(shape), t
+
+
 class BatchCollisionResult:
     """num_contacts[n]; contacts (structured array / tensor view) with offsets[n+1]; optional counters."""
 
@@ -367,7 +388,7 @@ class BatchDistanceResult:
 
 
 def collide_batch(o1, tf1, o2, tf2, request, contact_capacity=None, want_contacts=True, stats=False, device=None,
-                  grow_on_overflow=False):
+                  grow_on_overflow=False, pinned=False):
     """Host arrays in, host arrays out (copies inside): n independent fcl::collide() calls.
 
     tf1 / tf2: (n,12) float64 pose records, a Transform3, or None (identity)."""
@@ -380,12 +401,15 @@ def collide_batch(o1, tf1, o2, tf2, request, contact_capacity=None, want_contact
         raise ValueError("tf1 and tf2 must have the same length")
     m1, m2 = o1.device_model(device), o2.device_model(device)
     req = request._c()
-    counts = np.zeros(n, np.int32)
+    keep = []
+    counts, k = _out(n, np.int32, pinned, "counts")
+    keep.append(k)
     if want_contacts:
         if contact_capacity is None:
             contact_capacity = int(min(max(request.num_max_contacts, 0), 64)) * n
         contact_capacity = max(int(contact_capacity), 1)
-        contacts = np.zeros(contact_capacity, CONTACT_DTYPE)
+        contacts, k = _out(contact_capacity, CONTACT_DTYPE, pinned, "contacts")
+        keep.append(k)
         offsets = np.zeros(n + 1, np.int64)
     else:
         contact_capacity, contacts, offsets = 0, None, None
@@ -404,10 +428,12 @@ def collide_batch(o1, tf1, o2, tf2, request, contact_capacity=None, want_contact
     check(rc)
     if want_contacts:
         contacts = contacts[: offsets[n]]
-    return BatchCollisionResult(counts, contacts, offsets, n_bv, n_leaf)
+    res = BatchCollisionResult(counts, contacts, offsets, n_bv, n_leaf)
+    res._keepalive = keep
+    return res
 
 
-def distance_batch(o1, tf1, o2, tf2, request, stats=False, device=None):
+def distance_batch(o1, tf1, o2, tf2, request, stats=False, device=None, pinned=False):
     tf1, n1 = _poses(tf1)
     tf2, n2 = _poses(tf2)
     n = n1 if n1 is not None else n2
@@ -415,16 +441,15 @@ def distance_batch(o1, tf1, o2, tf2, request, stats=False, device=None):
         raise ValueError("at least one of tf1/tf2 must be given")
     m1, m2 = o1.device_model(device), o2.device_model(device)
     req = request._c()
-    dist = np.zeros(n)
-    p1 = np.zeros((n, 3))
-    p2 = np.zeros((n, 3))
-    b1 = np.zeros(n, np.int32)
-    b2 = np.zeros(n, np.int32)
+    (dist, k0), (p1, k1), (p2, k2) = _out(n, np.float64, pinned, "dist"), _out((n, 3), np.float64, pinned, "p1"), _out((n, 3), np.float64, pinned, "p2")
+    (b1, k3), (b2, k4) = _out(n, np.int32, pinned, "b1"), _out(n, np.int32, pinned, "b2")
     n_bv = np.zeros(n, np.uint32) if stats else None
     n_leaf = np.zeros(n, np.uint32) if stats else None
     check(_capi.lib().fclgpu_distance_batch_host(m1, m2, n, addr(tf1), addr(tf2), C.byref(req), addr(dist), addr(p1),
                                                  addr(p2), addr(b1), addr(b2), addr(n_bv), addr(n_leaf)))
-    return BatchDistanceResult(dist, p1, p2, b1, b2, n_bv, n_leaf)
+    res = BatchDistanceResult(dist, p1, p2, b1, b2, n_bv, n_leaf)
+    res._keepalive = [k0, k1, k2, k3, k4]
+    return res
 
 
 def collide_batch_device(o1, tf1, o2, tf2, request, num_contacts, contacts=None, contact_offsets=None, n_bv=None,

@@ -80,9 +80,10 @@ struct Workspace {
   void* scan_tmp = nullptr;
   size_t scan_bytes = 0;
   long long* scan_base = nullptr;  // running contact offset across chunks
-  // host-API staging (device side)
+  // host-API staging (device side) and the two streams of the chunked copy/compute pipeline
   void* dev_io = nullptr;
   size_t dev_io_bytes = 0;
+  cudaStream_t pipe[2] = {nullptr, nullptr};
   std::mutex mu;
 };
 
@@ -108,6 +109,8 @@ int get_ws(int device, Workspace** out) {
   CUDA_TRY(cudaMalloc(&w->status, sizeof(int)));
   CUDA_TRY(cudaMemset(w->status, 0, sizeof(int)));
   CUDA_TRY(cudaMalloc(&w->scan_base, sizeof(long long)));
+  CUDA_TRY(cudaStreamCreateWithFlags(&w->pipe[0], cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&w->pipe[1], cudaStreamNonBlocking));
   g_ws[device] = w;
   *out = w;
   return 0;
@@ -596,6 +599,15 @@ struct DevBuf {  // carve typed sub-buffers out of one device allocation (256-by
 size_t padded(size_t bytes) { return (bytes + 255) & ~size_t(255); }
 }  // namespace
 
+namespace {
+constexpr int64_t kHostChunk = 1 << 17;  // queries per pipeline stage (12.6 MB of poses)
+
+int finish_pipeline(Workspace* w, int device) {
+  CUDA_TRY(cudaStreamSynchronize(w->pipe[0]));
+  return fclgpu_sync_status(device, w->pipe[1]);
+}
+}  // namespace
+
 extern "C" int fclgpu_collide_batch_host(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1,
                                          const double* tf2, const fclgpu_collision_request* request,
                                          int32_t* num_contacts, fclgpu_contact* contacts, int64_t contact_capacity,
@@ -608,6 +620,34 @@ extern "C" int fclgpu_collide_batch_host(const fclgpu_model* m1, const fclgpu_mo
   if (rc) return rc;
   const bool want = contacts != nullptr || contact_offsets != nullptr;
   if (contacts == nullptr) contact_capacity = 0;
+  if (!want && n > 0) {  // counts / verdicts only: chunked two-stream pipeline (see the distance wrapper)
+    const size_t C = (size_t)std::min<int64_t>(n, kHostChunk);
+    const size_t per_stage = (tf1 ? padded(96 * C) : 0) + (tf2 ? padded(96 * C) : 0) + 3 * padded(4 * C) + 256;
+    {
+      std::lock_guard<std::mutex> lock(w->mu);
+      rc = ensure(&w->dev_io, &w->dev_io_bytes, 2 * per_stage);
+      if (rc) return rc;
+    }
+    int stage = 0;
+    for (int64_t s = 0; s < n; s += (int64_t)C, stage ^= 1) {
+      const size_t cn = (size_t)std::min<int64_t>((int64_t)C, n - s);
+      cudaStream_t st = w->pipe[stage];
+      DevBuf B{(char*)w->dev_io + stage * per_stage};
+      double* d_tf1 = tf1 ? B.take<double>(12 * C) : nullptr;
+      double* d_tf2 = tf2 ? B.take<double>(12 * C) : nullptr;
+      int32_t* d_cnt = B.take<int32_t>(C);
+      uint32_t* d_bv = n_bv ? B.take<uint32_t>(C) : nullptr;
+      uint32_t* d_leaf = n_leaf ? B.take<uint32_t>(C) : nullptr;
+      if (tf1) CUDA_TRY(cudaMemcpyAsync(d_tf1, tf1 + 12 * s, 96 * cn, cudaMemcpyHostToDevice, st));
+      if (tf2) CUDA_TRY(cudaMemcpyAsync(d_tf2, tf2 + 12 * s, 96 * cn, cudaMemcpyHostToDevice, st));
+      rc = fclgpu_collide_batch(m1, m2, (int64_t)cn, d_tf1, d_tf2, request, d_cnt, nullptr, 0, nullptr, d_bv, d_leaf, st);
+      if (rc) return rc;
+      CUDA_TRY(cudaMemcpyAsync(num_contacts + s, d_cnt, 4 * cn, cudaMemcpyDeviceToHost, st));
+      if (n_bv) CUDA_TRY(cudaMemcpyAsync(n_bv + s, d_bv, 4 * cn, cudaMemcpyDeviceToHost, st));
+      if (n_leaf) CUDA_TRY(cudaMemcpyAsync(n_leaf + s, d_leaf, 4 * cn, cudaMemcpyDeviceToHost, st));
+    }
+    return finish_pipeline(w, m1->device);
+  }
   size_t bytes = (tf1 ? padded(96 * (size_t)n) : 0) + (tf2 ? padded(96 * (size_t)n) : 0) + padded(4 * (size_t)n) +
                  (want ? padded(8 * (size_t)(n + 1)) + padded(64 * (size_t)contact_capacity) : 0) +
                  (n_bv ? padded(4 * (size_t)n) : 0) + (n_leaf ? padded(4 * (size_t)n) : 0) + 256;
@@ -655,37 +695,47 @@ extern "C" int fclgpu_distance_batch_host(const fclgpu_model* m1, const fclgpu_m
   Workspace* w;
   int rc = get_ws(m1->device, &w);
   if (rc) return rc;
-  const size_t N = (size_t)n;
-  size_t bytes = (tf1 ? padded(96 * N) : 0) + (tf2 ? padded(96 * N) : 0) + padded(8 * N) + 2 * padded(24 * N) +
-                 4 * padded(4 * N) + 256;
+  if (n == 0) return FCLGPU_OK;
+  // Chunked two-stream pipeline: while chunk c computes, chunk c+1's poses go up and chunk
+  // c-1's results come down (the copies are asynchronous when the caller's buffers are pinned).
+  const size_t C = (size_t)std::min<int64_t>(n, kHostChunk);
+  const size_t per_stage = (tf1 ? padded(96 * C) : 0) + (tf2 ? padded(96 * C) : 0) + padded(8 * C) + 2 * padded(24 * C) +
+                           4 * padded(4 * C) + 256;
   {
     std::lock_guard<std::mutex> lock(w->mu);
-    rc = ensure(&w->dev_io, &w->dev_io_bytes, bytes);
+    rc = ensure(&w->dev_io, &w->dev_io_bytes, 2 * per_stage);
     if (rc) return rc;
   }
-  DevBuf B{(char*)w->dev_io};
-  double* d_tf1 = tf1 ? B.take<double>(12 * N) : nullptr;
-  double* d_tf2 = tf2 ? B.take<double>(12 * N) : nullptr;
-  double* d_dist = B.take<double>(N);
-  double* d_p1 = nearest_p1 ? B.take<double>(3 * N) : nullptr;
-  double* d_p2 = nearest_p2 ? B.take<double>(3 * N) : nullptr;
-  int32_t* d_b1 = b1 ? B.take<int32_t>(N) : nullptr;
-  int32_t* d_b2 = b2 ? B.take<int32_t>(N) : nullptr;
-  uint32_t* d_bv = n_bv ? B.take<uint32_t>(N) : nullptr;
-  uint32_t* d_leaf = n_leaf ? B.take<uint32_t>(N) : nullptr;
-  cudaStream_t st = 0;
-  if (tf1) CUDA_TRY(cudaMemcpyAsync(d_tf1, tf1, 96 * N, cudaMemcpyHostToDevice, st));
-  if (tf2) CUDA_TRY(cudaMemcpyAsync(d_tf2, tf2, 96 * N, cudaMemcpyHostToDevice, st));
-  rc = fclgpu_distance_batch(m1, m2, n, d_tf1, d_tf2, request, d_dist, d_p1, d_p2, d_b1, d_b2, d_bv, d_leaf, st);
-  if (rc) return rc;
-  if (min_distance) CUDA_TRY(cudaMemcpyAsync(min_distance, d_dist, 8 * N, cudaMemcpyDeviceToHost, st));
-  if (nearest_p1 && request->enable_nearest_points) CUDA_TRY(cudaMemcpyAsync(nearest_p1, d_p1, 24 * N, cudaMemcpyDeviceToHost, st));
-  if (nearest_p2 && request->enable_nearest_points) CUDA_TRY(cudaMemcpyAsync(nearest_p2, d_p2, 24 * N, cudaMemcpyDeviceToHost, st));
-  if (b1) CUDA_TRY(cudaMemcpyAsync(b1, d_b1, 4 * N, cudaMemcpyDeviceToHost, st));
-  if (b2) CUDA_TRY(cudaMemcpyAsync(b2, d_b2, 4 * N, cudaMemcpyDeviceToHost, st));
-  if (n_bv) CUDA_TRY(cudaMemcpyAsync(n_bv, d_bv, 4 * N, cudaMemcpyDeviceToHost, st));
-  if (n_leaf) CUDA_TRY(cudaMemcpyAsync(n_leaf, d_leaf, 4 * N, cudaMemcpyDeviceToHost, st));
-  return fclgpu_sync_status(m1->device, st);
+  const bool np = request->enable_nearest_points != 0;
+  int stage = 0;
+  for (int64_t s = 0; s < n; s += (int64_t)C, stage ^= 1) {
+    const size_t cn = (size_t)std::min<int64_t>((int64_t)C, n - s);
+    cudaStream_t st = w->pipe[stage];
+    DevBuf B{(char*)w->dev_io + stage * per_stage};
+    double* d_tf1 = tf1 ? B.take<double>(12 * C) : nullptr;
+    double* d_tf2 = tf2 ? B.take<double>(12 * C) : nullptr;
+    double* d_dist = B.take<double>(C);
+    double* d_p1 = (nearest_p1 && np) ? B.take<double>(3 * C) : nullptr;
+    double* d_p2 = (nearest_p2 && np) ? B.take<double>(3 * C) : nullptr;
+    int32_t* d_b1 = b1 ? B.take<int32_t>(C) : nullptr;
+    int32_t* d_b2 = b2 ? B.take<int32_t>(C) : nullptr;
+    uint32_t* d_bv = n_bv ? B.take<uint32_t>(C) : nullptr;
+    uint32_t* d_leaf = n_leaf ? B.take<uint32_t>(C) : nullptr;
+    if (tf1) CUDA_TRY(cudaMemcpyAsync(d_tf1, tf1 + 12 * s, 96 * cn, cudaMemcpyHostToDevice, st));
+    if (tf2) CUDA_TRY(cudaMemcpyAsync(d_tf2, tf2 + 12 * s, 96 * cn, cudaMemcpyHostToDevice, st));
+    rc = fclgpu_distance_batch(m1, m2, (int64_t)cn, d_tf1, d_tf2, request, d_dist, d_p1, d_p2, d_b1, d_b2, d_bv, d_leaf, st);
+    if (rc) return rc;
+    if (min_distance) CUDA_TRY(cudaMemcpyAsync(min_distance + s, d_dist, 8 * cn, cudaMemcpyDeviceToHost, st));
+    if (d_p1) CUDA_TRY(cudaMemcpyAsync(nearest_p1 + 3 * s, d_p1, 24 * cn, cudaMemcpyDeviceToHost, st));
+    if (d_p2) CUDA_TRY(cudaMemcpyAsync(nearest_p2 + 3 * s, d_p2, 24 * cn, cudaMemcpyDeviceToHost, st));
+    if (b1) CUDA_TRY(cudaMemcpyAsync(b1 + s, d_b1, 4 * cn, cudaMemcpyDeviceToHost, st));
+    if (b2) CUDA_TRY(cudaMemcpyAsync(b2 + s, d_b2, 4 * cn, cudaMemcpyDeviceToHost, st));
+    if (n_bv) CUDA_TRY(cudaMemcpyAsync(n_bv + s, d_bv, 4 * cn, cudaMemcpyDeviceToHost, st));
+    if (n_leaf) CUDA_TRY(cudaMemcpyAsync(n_leaf + s, d_leaf, 4 * cn, cudaMemcpyDeviceToHost, st));
+    // a stage's device buffers are reused two chunks later: that chunk is enqueued on the same
+    // stream, so stream order already protects them
+  }
+  return finish_pipeline(w, m1->device);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -493,7 +493,7 @@ __device__ __forceinline__ unsigned warp_sort_keys(unsigned key, int lane) {
 }
 
 #ifndef FCLGPU_DIST_MINBLOCKS
-#define FCLGPU_DIST_MINBLOCKS 4
+#define FCLGPU_DIST_MINBLOCKS 5
 #endif
 template <bool kStats, bool kBound32>
 __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distance_warp_kernel(DistanceParams P) {
@@ -730,7 +730,7 @@ constexpr int kLeafFifo = 8;  // deferred pairs per lane (power of two)
 #define FCLGPU_COLLIDE_MINBLOCKS 3
 #endif
 #ifndef FCLGPU_COLLIDE32_MINBLOCKS
-#define FCLGPU_COLLIDE32_MINBLOCKS 3
+#define FCLGPU_COLLIDE32_MINBLOCKS 2
 #endif
 template <bool kStats, bool kSat32>
 __global__ void __launch_bounds__(128, kSat32 ? FCLGPU_COLLIDE32_MINBLOCKS : FCLGPU_COLLIDE_MINBLOCKS) collide_deferred_kernel(CollideParams P, int leaf_trigger) {
