@@ -86,4 +86,16 @@ void hm_obb_disjoint32_pairs(long long n, const double* pose12, const int* idx1,
     out[k] = obb_certainly_disjoint_f32(R0, T0, t1, a, b) ? 1 : 0;
   }
 }
+// triangle-level FP32 lower bound; S9 / T9 in a common frame (FP64); translation by -S0 and rounding done here
+float hm_tri_lb32(const double* S9, const double* T9) {
+  float s1[3], s2[3], t0[3], t1[3], t2[3];
+  for (int c = 0; c < 3; ++c) {
+    s1[c] = (float)(S9[3 + c] - S9[c]);
+    s2[c] = (float)(S9[6 + c] - S9[c]);
+    t0[c] = (float)(T9[c] - S9[c]);
+    t1[c] = (float)(T9[3 + c] - S9[c]);
+    t2[c] = (float)(T9[6 + c] - S9[c]);
+  }
+  return tri_lower_bound_f32(s1, s2, t0, t1, t2);
+}
 }

@@ -208,3 +208,35 @@ def test_f32_obb_sat_is_conservative(hm, oracle_env_rob):
     assert exact.sum() > n // 10 and (exact == 0).sum() > n // 20
     missed = ((got == 0) & (exact == 1)).sum()
     assert missed < 2e-3 * exact.sum(), missed            # sharp: < 0.2 % of disjoint pairs left undecided
+
+
+def test_f32_triangle_lower_bound_is_conservative(hm, oracle, env_rob_npz):
+    """lb32(tri, tri) <= exact triDistance, on synthetic pairs at several scales and on real
+    env/rob triangle pairs under benchmark poses; and it is tight enough to be useful."""
+    L = hm.lib()
+    rng = np.random.default_rng(41)
+    ratios = []
+    for scale, offset in ((1.0, 0.0), (1000.0, 3000.0), (0.01, 100.0)):
+        n = 20000
+        S, T = _tri_pairs(rng, n, 2.5)
+        S, T = S * scale + offset, T * scale + offset
+        for k in range(n):
+            lb = float(L.hm_tri_lb32(hm.dptr(S[k]), hm.dptr(T[k])))
+            d, _, _ = oracle.tri_distance(S[k], T[k])
+            assert lb <= d, (scale, k, lb, d)
+            if d > 0.5 * scale:
+                ratios.append(lb / d)
+    (ev, et), (rv, rt) = env_rob_npz
+    P = random_poses(4000, seed=43)
+    ti = rng.integers(0, len(et), len(P))
+    tj = rng.integers(0, len(rt), len(P))
+    for k in range(len(P)):
+        R1, t1 = P[k, :9].reshape(3, 3), P[k, 9:]
+        S = ev[et[ti[k]]].reshape(9)
+        Tw = (R1.T @ (rv[rt[tj[k]]] - t1).T).T.reshape(9)  # rob triangle in env's frame
+        lb = float(L.hm_tri_lb32(hm.dptr(S), hm.dptr(np.ascontiguousarray(Tw))))
+        d, _, _ = oracle.tri_distance(S, Tw)
+        assert lb <= d, (k, lb, d)
+        if d > 10:
+            ratios.append(lb / d)
+    assert np.median(ratios) > 0.95
