@@ -251,4 +251,65 @@ FD float tri_lower_bound_f32(const float* s1, const float* s2, const float* t0, 
   return fmaxf(lb, 0.0f);
 }
 
+
+// Single-precision classification of a triangle pair for the collide leaf test:
+//   +1  certainly separated   (some axis of the reference's 17-axis SAT separates the projections
+//                              by more than the rounding margin => intersect_Triangle is false)
+//   -1  certainly intersecting (on all 17 axes the projections overlap by more than the margin
+//                              => intersect_Triangle is true)
+//    0  undecided: run the exact FP64 test.
+// Inputs: local coordinates (both triangles translated by -P1 in FP64 by the caller, so p1 = 0,
+// and rounded once).  Error budget with Lm = largest |coordinate| (u = 2^-24): edge vectors
+// <= 3 u Lm, first-level axes (n1, m1, e_i x f_j) <= 28 u Lm^2, their projections <= 50 u Lm^3;
+// second-level axes (e_i x n1, f_j x m1) <= 140 u Lm^3, projections <= 260 u Lm^4.  Margins used:
+// 1024 u Lm^3 and 8192 u Lm^4.
+FD int tri_classify_f32(const float* p2, const float* p3, const float* q1, const float* q2, const float* q3) {
+  auto amax3 = [](const float* v) { return fmaxf(fabsf(v[0]), fmaxf(fabsf(v[1]), fabsf(v[2]))); };
+  const float Lm = fmaxf(fmaxf(amax3(p2), amax3(p3)), fmaxf(amax3(q1), fmaxf(amax3(q2), amax3(q3))));
+  const float L3 = Lm * Lm * Lm;
+  const float m1 = 6.103515625e-05f * L3;          // 1024 * 2^-24 * Lm^3
+  const float m2 = 4.8828125e-04f * L3 * Lm;       // 8192 * 2^-24 * Lm^4
+  bool sep = false, all_overlap = true;
+  auto axis = [&](float ax, float ay, float az, float margin) {
+    const float P2 = fmaf(az, p2[2], fmaf(ay, p2[1], ax * p2[0]));
+    const float P3 = fmaf(az, p3[2], fmaf(ay, p3[1], ax * p3[0]));
+    const float Q1 = fmaf(az, q1[2], fmaf(ay, q1[1], ax * q1[0]));
+    const float Q2 = fmaf(az, q2[2], fmaf(ay, q2[1], ax * q2[0]));
+    const float Q3 = fmaf(az, q3[2], fmaf(ay, q3[1], ax * q3[0]));
+    const float mnP = fminf(0.0f, fminf(P2, P3)), mxP = fmaxf(0.0f, fmaxf(P2, P3));
+    const float mnQ = fminf(Q1, fminf(Q2, Q3)), mxQ = fmaxf(Q1, fmaxf(Q2, Q3));
+    const float gap = fmaxf(mnP - mxQ, mnQ - mxP);  // > 0: separated on this axis
+    sep = sep || (gap > margin);
+    all_overlap = all_overlap && (gap < -margin);
+  };
+  const float e1[3] = {p2[0], p2[1], p2[2]};
+  const float e2[3] = {p3[0] - p2[0], p3[1] - p2[1], p3[2] - p2[2]};
+  const float e3[3] = {-p3[0], -p3[1], -p3[2]};
+  const float f1[3] = {q2[0] - q1[0], q2[1] - q1[1], q2[2] - q1[2]};
+  const float f2[3] = {q3[0] - q2[0], q3[1] - q2[1], q3[2] - q2[2]};
+  const float f3[3] = {q1[0] - q3[0], q1[1] - q3[1], q1[2] - q3[2]};
+  const float* E[3] = {e1, e2, e3};
+  const float* Fv[3] = {f1, f2, f3};
+  float n1[3], mm[3];
+  n1[0] = fmaf(e1[1], e2[2], -(e1[2] * e2[1])); n1[1] = fmaf(e1[2], e2[0], -(e1[0] * e2[2])); n1[2] = fmaf(e1[0], e2[1], -(e1[1] * e2[0]));
+  mm[0] = fmaf(f1[1], f2[2], -(f1[2] * f2[1])); mm[1] = fmaf(f1[2], f2[0], -(f1[0] * f2[2])); mm[2] = fmaf(f1[0], f2[1], -(f1[1] * f2[0]));
+  axis(n1[0], n1[1], n1[2], m1);
+  axis(mm[0], mm[1], mm[2], m1);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      axis(fmaf(E[i][1], Fv[j][2], -(E[i][2] * Fv[j][1])), fmaf(E[i][2], Fv[j][0], -(E[i][0] * Fv[j][2])),
+           fmaf(E[i][0], Fv[j][1], -(E[i][1] * Fv[j][0])), m1);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    axis(fmaf(E[i][1], n1[2], -(E[i][2] * n1[1])), fmaf(E[i][2], n1[0], -(E[i][0] * n1[2])),
+         fmaf(E[i][0], n1[1], -(E[i][1] * n1[0])), m2);
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+    axis(fmaf(Fv[j][1], mm[2], -(Fv[j][2] * mm[1])), fmaf(Fv[j][2], mm[0], -(Fv[j][0] * mm[2])),
+         fmaf(Fv[j][0], mm[1], -(Fv[j][1] * mm[0])), m2);
+  return sep ? 1 : (all_overlap ? -1 : 0);
+}
+
 }  // namespace fclgpu

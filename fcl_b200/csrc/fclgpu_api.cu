@@ -482,12 +482,15 @@ extern "C" int fclgpu_collide_batch(const fclgpu_model* m1, const fclgpu_model* 
     P.status = w->status;
     const long long trav = opt("traversal");
     const int trig = (int)opt("leaf_trigger");
-    if (trav >= 2) {
-      rc = stats ? launch_persistent(collide_deferred_kernel<true, true>, P, w, 128, st, 0, trig)
-                 : launch_persistent(collide_deferred_kernel<false, true>, P, w, 128, st, 0, trig);
+    if (trav >= 2 && !P.enable_contact) {
+      rc = stats ? launch_persistent(collide_deferred_kernel<true, true, true>, P, w, 128, st, 0, trig)
+                 : launch_persistent(collide_deferred_kernel<false, true, true>, P, w, 128, st, 0, trig);
+    } else if (trav >= 2) {
+      rc = stats ? launch_persistent(collide_deferred_kernel<true, true, false>, P, w, 128, st, 0, trig)
+                 : launch_persistent(collide_deferred_kernel<false, true, false>, P, w, 128, st, 0, trig);
     } else if (trav == 1) {
-      rc = stats ? launch_persistent(collide_deferred_kernel<true, false>, P, w, 128, st, 0, trig)
-                 : launch_persistent(collide_deferred_kernel<false, false>, P, w, 128, st, 0, trig);
+      rc = stats ? launch_persistent(collide_deferred_kernel<true, false, false>, P, w, 128, st, 0, trig)
+                 : launch_persistent(collide_deferred_kernel<false, false, false>, P, w, 128, st, 0, trig);
     } else {
       rc = stats ? launch_persistent(collide_thread_kernel<true>, P, w, 128, st)
                  : launch_persistent(collide_thread_kernel<false>, P, w, 128, st);

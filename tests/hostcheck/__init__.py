@@ -41,6 +41,8 @@ def lib():
         L.hm_tri_distance.restype = C.c_double
         L.hm_tri_distance.argtypes = [dp, dp, dp, dp]
         L.hm_obb_disjoint32_pairs.argtypes = [C.c_longlong, dp, ip, ip, dp, dp, dp, dp, dp, dp, ip]
+        L.hm_tri_classify32.restype = C.c_int
+        L.hm_tri_classify32.argtypes = [dp, dp, dp]
         L.hm_tri_lb32.restype = C.c_float
         L.hm_tri_lb32.argtypes = [dp, dp]
         L.hm_rss_lb32_pairs.argtypes = [C.c_longlong, dp, ip, ip, dp, dp, dp, dp, dp, dp, dp, dp, C.POINTER(C.c_float)]

@@ -98,4 +98,16 @@ float hm_tri_lb32(const double* S9, const double* T9) {
   }
   return tri_lower_bound_f32(s1, s2, t0, t1, t2);
 }
+// FP32 triangle-pair classification exactly as the collide kernel does it: Q' = R Q + T and the
+// translation by -P1 in FP64, one rounding to float, then tri_classify_f32
+int hm_tri_classify32(const double* P9, const double* Q9, const double* pose12) {
+  M3 R = m3(pose12); V3 T = v3(pose12 + 9);
+  V3 P[3] = {v3(P9), v3(P9 + 3), v3(P9 + 6)};
+  V3 Q[3] = {mulv(R, v3(Q9)) + T, mulv(R, v3(Q9 + 3)) + T, mulv(R, v3(Q9 + 6)) + T};
+  const V3 a = P[1] - P[0], b = P[2] - P[0], c = Q[0] - P[0], d = Q[1] - P[0], e = Q[2] - P[0];
+  float p2[3] = {(float)a.x, (float)a.y, (float)a.z}, p3[3] = {(float)b.x, (float)b.y, (float)b.z};
+  float q1[3] = {(float)c.x, (float)c.y, (float)c.z}, q2[3] = {(float)d.x, (float)d.y, (float)d.z};
+  float q3[3] = {(float)e.x, (float)e.y, (float)e.z};
+  return tri_classify_f32(p2, p3, q1, q2, q3);
+}
 }

@@ -240,3 +240,38 @@ def test_f32_triangle_lower_bound_is_conservative(hm, oracle, env_rob_npz):
         if d > 10:
             ratios.append(lb / d)
     assert np.median(ratios) > 0.95
+
+
+def test_f32_triangle_classification_is_sound(hm, oracle, env_rob_npz):
+    """+1 (certainly separated) => the exact test says no intersection; -1 (certainly intersecting)
+    => the exact test says intersection; 0 (undecided) must be rare on generic input."""
+    L = hm.lib()
+    rng = np.random.default_rng(47)
+    stats = {1: 0, -1: 0, 0: 0}
+    for scale, offset, spread in ((1.0, 0.0, 0.8), (500.0, 4000.0, 0.8), (0.01, 50.0, 1.5)):
+        n = 15000
+        P, Q = _tri_pairs(rng, n, spread)
+        P, Q = P * scale + offset, Q * scale + offset
+        Q[:1000, :3] = P[:1000, :3]            # shared vertex (touching) -> must never be classified wrongly
+        Q[1000:1500] = P[1000:1500]            # identical triangles (coplanar, parallel edges)
+        pose = np.concatenate([np.eye(3).reshape(9), np.zeros(3)])
+        for k in range(n):
+            c = L.hm_tri_classify32(hm.dptr(P[k]), hm.dptr(Q[k]), hm.dptr(pose))
+            hit = oracle.tri_intersect(P[k], Q[k])
+            assert not (c == 1 and hit), (scale, k)
+            assert not (c == -1 and not hit), (scale, k)
+            if k >= 1500:  # generic pairs only (the injected touching / coplanar ones are legitimately undecided)
+                stats[c] += 1
+    # real mesh triangles under benchmark poses (model coordinates ~1e3, poses ~1e3)
+    (ev, et), (rv, rt) = env_rob_npz
+    poses = random_poses(6000, seed=53)
+    rel = _rel_pose(poses)
+    ti, tj = rng.integers(0, len(et), len(poses)), rng.integers(0, len(rt), len(poses))
+    for k in range(len(poses)):
+        Pk = np.ascontiguousarray(ev[et[ti[k]]].reshape(9))
+        Qk = np.ascontiguousarray(rv[rt[tj[k]]].reshape(9))
+        c = L.hm_tri_classify32(hm.dptr(Pk), hm.dptr(Qk), hm.dptr(rel[k]))
+        hit = oracle.tri_intersect(Pk, Qk, rel[k, :9], rel[k, 9:])
+        assert not (c == 1 and hit) and not (c == -1 and not hit), k
+    assert stats[1] > 10000 and stats[-1] > 3000
+    assert stats[0] < 0.002 * sum(stats.values()), stats   # undecided only for touching / degenerate pairs
