@@ -153,7 +153,7 @@ def main():
     ap.add_argument("--workload", default="distance", choices=sorted(WORKLOADS))
     ap.add_argument("--poses", type=int, default=1_000_000, help="poses per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=20000)
-    ap.add_argument("--traversal", type=int, default=2, help="kernel variant (fclgpu option 'traversal', see DESIGN.md)")
+    ap.add_argument("--traversal", type=int, default=3, help="kernel variant (fclgpu option 'traversal', see DESIGN.md)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

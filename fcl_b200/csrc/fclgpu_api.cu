@@ -49,15 +49,18 @@ int fail(int code, const char* fmt, ...) {
 // options
 std::mutex g_opt_mu;
 std::map<std::string, long long> g_opts = {
-    // 2 (default): like 1, but the BV tests that steer the traversal are conservative single-precision tests
+    // 3 (default): like 2, and collide with contact generation pools the warp's deferred triangle pairs
+    //    over all 32 lanes (collide_pooled_kernel)
+    // 2: like 1, but the BV tests that steer the traversal are conservative single-precision tests
     //    (bounds_f32.cuh); every result still comes from the exact FP64 triangle routines
     // 1: collide = thread per query with deferred leaf rounds, distance = warp per query sorted front, FP64 BV tests
     // 0: thread per query, the reference's visiting order exactly (work counters match the reference's)
-    {"traversal", 2},
+    {"traversal", 3},
     {"contact_stride", 1024},  // per-query contact scratch slots when num_max_contacts is larger
     {"scratch_bytes", 2ll << 30},
     {"blocks_per_sm", 0},      // 0 = occupancy query
     {"stats", 1},
+    {"pool_trigger", 32},      // collide variant P: queued pairs in the warp that trigger a pooled leaf round
     {"leaf_trigger", 20},      // collide variant D: lanes with queued triangle pairs that trigger a leaf round
 };
 long long opt(const char* k) {
@@ -485,6 +488,10 @@ extern "C" int fclgpu_collide_batch(const fclgpu_model* m1, const fclgpu_model* 
     if (trav >= 2 && !P.enable_contact) {
       rc = stats ? launch_persistent(collide_deferred_kernel<true, true, true>, P, w, 128, st, 0, trig)
                  : launch_persistent(collide_deferred_kernel<false, true, true>, P, w, 128, st, 0, trig);
+    } else if (trav >= 3) {  // contact generation with pooled leaf rounds
+      const int ptrig = (int)opt("pool_trigger");
+      rc = stats ? launch_persistent(collide_pooled_kernel<true>, P, w, 128, st, sizeof(PoolWarp) * 4, ptrig)
+                 : launch_persistent(collide_pooled_kernel<false>, P, w, 128, st, sizeof(PoolWarp) * 4, ptrig);
     } else if (trav >= 2) {
       rc = stats ? launch_persistent(collide_deferred_kernel<true, true, false>, P, w, 128, st, 0, trig)
                  : launch_persistent(collide_deferred_kernel<false, true, false>, P, w, 128, st, 0, trig);

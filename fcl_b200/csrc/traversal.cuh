@@ -987,3 +987,234 @@ collide_deferred_kernel(CollideParams P, int leaf_trigger) {
 }
 
 }  // namespace fclgpu
+
+namespace fclgpu {
+
+// ---------------------------------------------------------------------------------------
+// Variant P for collide with contact generation (thread per query, POOLED leaf rounds):
+// like variant D every lane walks its own query depth first and defers the triangle pairs it
+// meets to a per-lane FIFO, but a leaf round treats the FIFOs of the whole warp as one pool:
+// the first 32 queued pairs (owner-major, FIFO order inside an owner) are handed one per lane,
+// so a lane stuck in a dense contact region gets its backlog tested by the idle lanes.  Each
+// helper recomputes the owner's relative pose, runs the exact FP64 triangle SAT and contact
+// generation, and stages the result in shared memory; afterwards every owner consumes its own
+// results in FIFO (= DFS) order and applies the num_max_contacts budget exactly like the
+// reference's leaf test, so the contact list and its truncation are unchanged.
+// ---------------------------------------------------------------------------------------
+constexpr int kPoolFifo = 16;  // deferred pairs per lane (power of two)
+
+struct __align__(16) PoolStage {  // result of one triangle-pair test, 96 bytes
+  double pos[2][3];
+  double normal[3];
+  double depth;
+  int32_t id1, id2;
+  int32_t nc;   // -1: no intersection, else number of contact points (0..2)
+  int32_t pad;
+};
+
+struct __align__(16) PoolWarp {
+  uint2 fifo[kPoolFifo][32];
+  PoolStage stage[32];
+  long long pose[32];
+  int incl[32];
+  int excl[32];
+  int head[32];
+};
+
+template <bool kStats>
+__global__ void __launch_bounds__(128, 2) collide_pooled_kernel(CollideParams P, int leaf_trigger) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PoolWarp& S = reinterpret_cast<PoolWarp*>(smem_raw)[threadIdx.x >> 5];
+  uint2 stk[kStackCap];
+  const int lane = threadIdx.x & 31;
+  int sp = 0, qhead = 0, qcount = 0;
+  long long q = -1;
+  M3 R;
+  V3 T;
+  float Rf[9], Tf[3], t_l1 = 0.0f;
+  long long count = 0;
+  uint32_t bv_tests = 0, leaf_tests = 0;
+  bool exhausted = false;
+
+  while (true) {
+    const bool need = (sp == 0) && (qcount == 0) && !exhausted;
+    if (need && q >= 0) {
+      P.num_contacts[q] = (int32_t)count;
+      if (kStats) {
+        if (P.n_bv) P.n_bv[q] = bv_tests;
+        if (P.n_leaf) P.n_leaf[q] = leaf_tests;
+      }
+      q = -1;
+    }
+    const long long nq = fetch_work(need, P.work_counter);
+    if (need) {
+      if (nq < P.n) {
+        q = nq;
+        const PoseRT tf1 = load_pose(P.tf1, q);
+        const PoseRT tf2 = load_pose(P.tf2, q);
+        R = mulTM(tf1.R, tf2.R);
+        T = mulTv(tf1.R, tf2.t - tf1.t);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Rf[k] = (float)R.m[k];
+        Tf[0] = (float)T.x; Tf[1] = (float)T.y; Tf[2] = (float)T.z;
+        t_l1 = __double2float_ru((fabs(T.x) + fabs(T.y)) + fabs(T.z));
+        count = 0;
+        bv_tests = leaf_tests = 0;
+        stk[0] = make_uint2(0u, 0u);
+        sp = 1;
+      } else {
+        exhausted = true;
+      }
+    }
+    const unsigned bv_mask = __ballot_sync(0xffffffffu, sp > 0 && qcount < kPoolFifo);
+    // pool size
+    int incl = qcount;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (bv_mask == 0u && total == 0) break;
+
+    const bool leaf_round = (total > 0) && (bv_mask == 0u || total >= leaf_trigger ||
+                                            __any_sync(0xffffffffu, qcount == kPoolFifo));
+    if (leaf_round) {
+      S.incl[lane] = incl;
+      S.excl[lane] = incl - qcount;
+      S.head[lane] = qhead;
+      S.pose[lane] = q;
+      __syncwarp();
+      const int nproc = total < 32 ? total : 32;
+      if (lane < nproc) {
+        // owner of pooled pair j = lane: number of lanes whose inclusive count is <= j
+        int owner = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1)
+          if (S.incl[owner + step - 1] <= lane) owner += step;
+        const int slot = (S.head[owner] + (lane - S.excl[owner])) & (kPoolFifo - 1);
+        const uint2 ids = S.fifo[slot][owner];
+        const long long qo = S.pose[owner];
+        const PoseRT tf1 = load_pose(P.tf1, qo);
+        const PoseRT tf2 = load_pose(P.tf2, qo);
+        const M3 Ro = mulTM(tf1.R, tf2.R);
+        const V3 To = mulTv(tf1.R, tf2.t - tf1.t);
+        V3 Pt[3], Qt[3];
+        load_tri(P.m1.tri, (int)ids.x, Pt);
+        load_tri(P.m2.tri, (int)ids.y, Qt);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) Qt[k] = mulv(Ro, Qt[k]) + To;
+        PoolStage& out = S.stage[lane];
+        out.id1 = (int)ids.x;
+        out.id2 = (int)ids.y;
+        out.nc = -1;
+        if (tri_intersect(Pt[0], Pt[1], Pt[2], Qt[0], Qt[1], Qt[2])) {
+          out.nc = 0;
+          if (P.enable_contact) {
+            V3 cp[2], nrm;
+            unsigned nc;
+            double depth;
+            tri_contact_info(Pt, Qt, cp, nc, depth, nrm);
+            const V3 nw = mulv(tf1.R, nrm);  // tf1.linear() * n
+            out.normal[0] = nw.x; out.normal[1] = nw.y; out.normal[2] = nw.z;
+            out.depth = depth;
+            out.nc = (int)nc;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const V3 pw = mulv(tf1.R, cp[k]) + tf1.t;  // tf1 * p
+              out.pos[k][0] = pw.x; out.pos[k][1] = pw.y; out.pos[k][2] = pw.z;
+            }
+          }
+        }
+      }
+      __syncwarp();
+      // owners consume their results in FIFO order
+      int mine = nproc - (incl - qcount);
+      mine = mine < 0 ? 0 : (mine > qcount ? qcount : mine);
+      const int first = incl - qcount;
+      if (kStats) leaf_tests += mine;
+      qhead = (qhead + mine) & (kPoolFifo - 1);
+      qcount -= mine;
+      for (int k = 0; k < mine; ++k) {
+        const PoolStage& r = S.stage[first + k];
+        if (r.nc < 0) continue;
+        if (!P.enable_contact) {
+          if (count < P.max_contacts) {
+            if (P.scratch) {
+              if (count < P.stride) {
+                fclgpu_contact* c = P.scratch + q * P.stride + count;
+                c->b1 = r.id1;
+                c->b2 = r.id2;
+              } else {
+                atomicMin(P.status, (int)FCLGPU_ERR_CONTACT_OVERFLOW);
+              }
+            }
+            count++;
+          }
+        } else {
+          long long nc = r.nc;
+          if (P.max_contacts < count + nc) nc = (P.max_contacts > count) ? (P.max_contacts - count) : 0;
+          for (long long c2 = 0; c2 < nc; ++c2) {
+            if (P.scratch) {
+              if (count < P.stride) {
+                fclgpu_contact* c = P.scratch + q * P.stride + count;
+                c->b1 = r.id1;
+                c->b2 = r.id2;
+                c->normal[0] = r.normal[0]; c->normal[1] = r.normal[1]; c->normal[2] = r.normal[2];
+                c->pos[0] = r.pos[c2][0]; c->pos[1] = r.pos[c2][1]; c->pos[2] = r.pos[c2][2];
+                c->penetration_depth = r.depth;
+              } else {
+                atomicMin(P.status, (int)FCLGPU_ERR_CONTACT_OVERFLOW);
+              }
+            }
+            count++;
+          }
+        }
+        if (count > 0 && P.max_contacts <= count) {  // canStop(): drop everything still pending
+          sp = 0;
+          qcount = 0;
+          break;
+        }
+      }
+      __syncwarp();
+      continue;
+    }
+
+    // ---- BV round (conservative FP32 box test, see bounds_f32.cuh) ----
+    if (sp > 0 && qcount < kPoolFifo) {
+      const uint2 e = stk[--sp];
+      const int b1 = (int)e.x, b2 = (int)e.y;
+      int fc1, fc2;
+      double size1, size2;
+      const ObbRec32 n1 = load_obb32(P.m1.obb32, b1);
+      const ObbRec32 n2 = load_obb32(P.m2.obb32, b2);
+      load_topo(P.m1.topo, b1, fc1, size1);
+      load_topo(P.m2.topo, b2, fc2, size2);
+      if (kStats) bv_tests++;
+      if (!obb_certainly_disjoint_f32(Rf, Tf, t_l1, n1, n2)) {
+        const bool l1 = fc1 < 0, l2 = fc2 < 0;
+        if (l1 && l2) {
+          S.fifo[(qhead + qcount) & (kPoolFifo - 1)][lane] = make_uint2((unsigned)(-(fc1 + 1)), (unsigned)(-(fc2 + 1)));
+          qcount++;
+        } else if (sp + 2 > kStackCap) {
+          atomicMin(P.status, (int)FCLGPU_ERR_STACK_OVERFLOW);
+          sp = 0;
+          qcount = 0;
+        } else {
+          uint2 left, right;
+          if (l2 || (!l1 && (size1 > size2))) {
+            left = make_uint2((unsigned)fc1, (unsigned)b2);
+            right = make_uint2((unsigned)fc1 + 1u, (unsigned)b2);
+          } else {
+            left = make_uint2((unsigned)b1, (unsigned)fc2);
+            right = make_uint2((unsigned)b1, (unsigned)fc2 + 1u);
+          }
+          stk[sp++] = right;
+          stk[sp++] = left;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace fclgpu

@@ -22,11 +22,11 @@ def models(env_rob_npz, oracle):
     return (F.BVHModel.from_arrays(ev, et), F.BVHModel.from_arrays(rv, rt)), (oracle.Model(ev, et), oracle.Model(rv, rt))
 
 
-@pytest.fixture(params=[0, 1, 2], ids=["thread", "front64", "front32"])
+@pytest.fixture(params=[0, 1, 2, 3], ids=["thread", "front64", "front32", "pooled"])
 def traversal(request):
     _capi.set_option("traversal", request.param)
     yield request.param
-    _capi.set_option("traversal", 2)  # library default
+    _capi.set_option("traversal", 3)  # library default
 
 
 def _contacts_equal(got, ref):
