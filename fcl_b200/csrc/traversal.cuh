@@ -36,6 +36,9 @@ struct DeviceModel {
   int32_t n_nodes, n_tris;
 };
 
+#ifndef FCLGPU_PREFETCH
+#define FCLGPU_PREFETCH 0
+#endif
 constexpr int kNodeDoubles = 16;
 constexpr int kTriDoubles = 10;
 constexpr int kStackCap = 128;  // per-query DFS stack entries; host checks depth1+depth2+2 <= cap
@@ -81,6 +84,16 @@ __device__ __forceinline__ ObbRec32 load_obb32(const ObbRec32* __restrict__ base
   n.a[8] = v2.x; n.c[0] = v2.y; n.c[1] = v2.z; n.c[2] = v2.w;
   n.e[0] = v3.x; n.e[1] = v3.y; n.e[2] = v3.z; n.s = v3.w;
   return n;
+}
+
+// L1 prefetch of the records the next BV round will need (the next entry is known as soon as the
+// current one is decided; the lines arrive while the warp does its round bookkeeping)
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_bv32(const DeviceModel& m1, const DeviceModel& m2, uint2 e) {
+  prefetch_l1(m1.obb32 + e.x);
+  prefetch_l1(m2.obb32 + e.y);
+  prefetch_l1(m1.topo + e.x);
+  prefetch_l1(m2.topo + e.y);
 }
 
 __device__ __forceinline__ void load_topo(const double2* __restrict__ base, int idx, int& first_child, double& size) {
@@ -982,6 +995,7 @@ collide_deferred_kernel(CollideParams P, int leaf_trigger) {
           stk[sp++] = left;
         }
       }
+      if (FCLGPU_PREFETCH && kSat32 && sp > 0) prefetch_bv32(P.m1, P.m2, stk[sp - 1]);
     }
   }
 }
@@ -1021,8 +1035,14 @@ struct __align__(16) PoolWarp {
   int head[32];
 };
 
+#ifndef FCLGPU_POOLED_MINBLOCKS
+#define FCLGPU_POOLED_MINBLOCKS 4
+#endif
+#ifndef FCLGPU_POOLED_OUTOFLINE
+#define FCLGPU_POOLED_OUTOFLINE 1
+#endif
 template <bool kStats>
-__global__ void __launch_bounds__(128, 2) collide_pooled_kernel(CollideParams P, int leaf_trigger) {
+__global__ void __launch_bounds__(128, FCLGPU_POOLED_MINBLOCKS) collide_pooled_kernel(CollideParams P, int leaf_trigger) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PoolWarp& S = reinterpret_cast<PoolWarp*>(smem_raw)[threadIdx.x >> 5];
   uint2 stk[kStackCap];
@@ -1067,19 +1087,18 @@ __global__ void __launch_bounds__(128, 2) collide_pooled_kernel(CollideParams P,
       }
     }
     const unsigned bv_mask = __ballot_sync(0xffffffffu, sp > 0 && qcount < kPoolFifo);
-    // pool size
-    int incl = qcount;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int y = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += y;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int total = __reduce_add_sync(0xffffffffu, qcount);  // pool size
     if (bv_mask == 0u && total == 0) break;
 
     const bool leaf_round = (total > 0) && (bv_mask == 0u || total >= leaf_trigger ||
                                             __any_sync(0xffffffffu, qcount == kPoolFifo));
     if (leaf_round) {
+      int incl = qcount;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
       S.incl[lane] = incl;
       S.excl[lane] = incl - qcount;
       S.head[lane] = qhead;
@@ -1108,13 +1127,14 @@ __global__ void __launch_bounds__(128, 2) collide_pooled_kernel(CollideParams P,
         out.id1 = (int)ids.x;
         out.id2 = (int)ids.y;
         out.nc = -1;
-        if (tri_intersect(Pt[0], Pt[1], Pt[2], Qt[0], Qt[1], Qt[2])) {
+        if (FCLGPU_POOLED_OUTOFLINE ? tri_intersect_outofline(Pt, Qt) : tri_intersect(Pt[0], Pt[1], Pt[2], Qt[0], Qt[1], Qt[2])) {
           out.nc = 0;
           if (P.enable_contact) {
             V3 cp[2], nrm;
             unsigned nc;
             double depth;
-            tri_contact_info(Pt, Qt, cp, nc, depth, nrm);
+            if (FCLGPU_POOLED_OUTOFLINE) tri_contact_info_outofline(Pt, Qt, cp, &nc, &depth, &nrm);
+            else tri_contact_info(Pt, Qt, cp, nc, depth, nrm);
             const V3 nw = mulv(tf1.R, nrm);  // tf1.linear() * n
             out.normal[0] = nw.x; out.normal[1] = nw.y; out.normal[2] = nw.z;
             out.depth = depth;
@@ -1213,6 +1233,7 @@ __global__ void __launch_bounds__(128, 2) collide_pooled_kernel(CollideParams P,
           stk[sp++] = left;
         }
       }
+      if (FCLGPU_PREFETCH && sp > 0) prefetch_bv32(P.m1, P.m2, stk[sp - 1]);
     }
   }
 }
