@@ -460,6 +460,16 @@ namespace fclgpu {
 // Measured against the sequential recursion on env/rob this order needs 0.7x the BV tests and
 // 0.5x the leaf tests (nearest-first expansion tightens the bound sooner).
 // ---------------------------------------------------------------------------------------
+
+#ifndef FCLGPU_DIST_OUTOFLINE
+#define FCLGPU_DIST_OUTOFLINE 0
+#endif
+// exact triDistance out of line: the hot BV loop of the sorted-front kernel then needs far fewer
+// registers than the FP64 leaf routine
+__device__ __noinline__ double tri_distance_outofline(const V3* Sv, const V3* Tv, V3* Pn, V3* Qn) {
+  return tri_distance(Sv, Tv, *Pn, *Qn);
+}
+
 constexpr int kDistPop = 16;         // entries expanded per BV round (2 lanes each)
 constexpr int kDistStackCap = 512;   // entries per warp
 constexpr int kLeafCap = 64;
@@ -623,7 +633,7 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
           load_tri(P.m2.tri, (int)ids.y, Tv);
 #pragma unroll
           for (int c = 0; c < 3; ++c) Tv[c] = mulv(R, Tv[c]) + T;
-          d = tri_distance(Sv, Tv, Pn, Qn);
+          d = (FCLGPU_DIST_OUTOFLINE && kBound32) ? tri_distance_outofline(Sv, Tv, &Pn, &Qn) : tri_distance(Sv, Tv, Pn, Qn);
         }
         // warp arg-min (distances are >= 0, so the bit pattern orders like the value); ties -> lowest lane
         unsigned long long key = (unsigned long long)__double_as_longlong(d);
