@@ -60,6 +60,9 @@ std::map<std::string, long long> g_opts = {
     {"scratch_bytes", 2ll << 30},
     {"blocks_per_sm", 0},      // 0 = occupancy query
     {"stats", 1},
+    // binary-mode collide at traversal >= 3: 1 = pooled kernel (measured fastest: 3.8 ms per 1M poses),
+    // 2 = pooled kernel with the FP32 triangle classification (4.2 ms), 0 = deferred kernel with classification (4.9 ms)
+    {"binary_pooled", 1},
     {"pool_trigger", 32},      // collide variant P: queued pairs in the warp that trigger a pooled leaf round
     {"leaf_trigger", 20},      // collide variant D: lanes with queued triangle pairs that trigger a leaf round
 };
@@ -485,13 +488,18 @@ extern "C" int fclgpu_collide_batch(const fclgpu_model* m1, const fclgpu_model* 
     P.status = w->status;
     const long long trav = opt("traversal");
     const int trig = (int)opt("leaf_trigger");
-    if (trav >= 2 && !P.enable_contact) {
+    if (trav >= 2 && !P.enable_contact && (trav == 2 || !opt("binary_pooled"))) {
       rc = stats ? launch_persistent(collide_deferred_kernel<true, true, true>, P, w, 128, st, 0, trig)
                  : launch_persistent(collide_deferred_kernel<false, true, true>, P, w, 128, st, 0, trig);
-    } else if (trav >= 3) {  // contact generation with pooled leaf rounds
+    } else if (trav >= 3) {  // pooled leaf rounds
       const int ptrig = (int)opt("pool_trigger");
-      rc = stats ? launch_persistent(collide_pooled_kernel<true>, P, w, 128, st, sizeof(PoolWarp) * 4, ptrig)
-                 : launch_persistent(collide_pooled_kernel<false>, P, w, 128, st, sizeof(PoolWarp) * 4, ptrig);
+      const size_t psm = sizeof(PoolWarp) * 4;
+      if (!P.enable_contact && opt("binary_pooled") >= 2)
+        rc = stats ? launch_persistent(collide_pooled_kernel<true, true>, P, w, 128, st, psm, ptrig)
+                   : launch_persistent(collide_pooled_kernel<false, true>, P, w, 128, st, psm, ptrig);
+      else
+        rc = stats ? launch_persistent(collide_pooled_kernel<true, false>, P, w, 128, st, psm, ptrig)
+                   : launch_persistent(collide_pooled_kernel<false, false>, P, w, 128, st, psm, ptrig);
     } else if (trav >= 2) {
       rc = stats ? launch_persistent(collide_deferred_kernel<true, true, false>, P, w, 128, st, 0, trig)
                  : launch_persistent(collide_deferred_kernel<false, true, false>, P, w, 128, st, 0, trig);

@@ -1051,7 +1051,7 @@ struct __align__(16) PoolWarp {
 #ifndef FCLGPU_POOLED_OUTOFLINE
 #define FCLGPU_POOLED_OUTOFLINE 1
 #endif
-template <bool kStats>
+template <bool kStats, bool kClassify32>
 __global__ void __launch_bounds__(128, FCLGPU_POOLED_MINBLOCKS) collide_pooled_kernel(CollideParams P, int leaf_trigger) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PoolWarp& S = reinterpret_cast<PoolWarp*>(smem_raw)[threadIdx.x >> 5];
@@ -1137,7 +1137,19 @@ __global__ void __launch_bounds__(128, FCLGPU_POOLED_MINBLOCKS) collide_pooled_k
         out.id1 = (int)ids.x;
         out.id2 = (int)ids.y;
         out.nc = -1;
-        if (FCLGPU_POOLED_OUTOFLINE ? tri_intersect_outofline(Pt, Qt) : tri_intersect(Pt[0], Pt[1], Pt[2], Qt[0], Qt[1], Qt[2])) {
+        bool hit;
+        if (kClassify32) {  // binary mode: single-precision classification, exact SAT only when undecided
+          const V3 a = Pt[1] - Pt[0], b = Pt[2] - Pt[0], c = Qt[0] - Pt[0], d = Qt[1] - Pt[0], e = Qt[2] - Pt[0];
+          const float p2[3] = {(float)a.x, (float)a.y, (float)a.z}, p3[3] = {(float)b.x, (float)b.y, (float)b.z};
+          const float q1[3] = {(float)c.x, (float)c.y, (float)c.z}, q2[3] = {(float)d.x, (float)d.y, (float)d.z};
+          const float q3[3] = {(float)e.x, (float)e.y, (float)e.z};
+          const int cls = tri_classify_f32(p2, p3, q1, q2, q3);
+          hit = cls < 0;
+          if (cls == 0) hit = tri_intersect_outofline(Pt, Qt);
+        } else {
+          hit = FCLGPU_POOLED_OUTOFLINE ? tri_intersect_outofline(Pt, Qt) : tri_intersect(Pt[0], Pt[1], Pt[2], Qt[0], Qt[1], Qt[2]);
+        }
+        if (hit) {
           out.nc = 0;
           if (P.enable_contact) {
             V3 cp[2], nrm;
