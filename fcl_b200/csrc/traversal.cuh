@@ -1055,7 +1055,10 @@ template <bool kStats, bool kClassify32>
 __global__ void __launch_bounds__(128, FCLGPU_POOLED_MINBLOCKS) collide_pooled_kernel(CollideParams P, int leaf_trigger) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PoolWarp& S = reinterpret_cast<PoolWarp*>(smem_raw)[threadIdx.x >> 5];
+  // DFS stack: the top entry lives in a register (an expanded node's left child is consumed by the very
+  // next BV round), the rest in local memory; sp counts both
   uint2 stk[kStackCap];
+  uint2 top = make_uint2(0u, 0u);
   const int lane = threadIdx.x & 31;
   int sp = 0, qhead = 0, qcount = 0;
   long long q = -1;
@@ -1090,7 +1093,7 @@ __global__ void __launch_bounds__(128, FCLGPU_POOLED_MINBLOCKS) collide_pooled_k
         t_l1 = __double2float_ru((fabs(T.x) + fabs(T.y)) + fabs(T.z));
         count = 0;
         bv_tests = leaf_tests = 0;
-        stk[0] = make_uint2(0u, 0u);
+        top = make_uint2(0u, 0u);
         sp = 1;
       } else {
         exhausted = true;
@@ -1224,7 +1227,9 @@ __global__ void __launch_bounds__(128, FCLGPU_POOLED_MINBLOCKS) collide_pooled_k
 
     // ---- BV round (conservative FP32 box test, see bounds_f32.cuh) ----
     if (sp > 0 && qcount < kPoolFifo) {
-      const uint2 e = stk[--sp];
+      const uint2 e = top;
+      --sp;
+      bool have_top = false;
       const int b1 = (int)e.x, b2 = (int)e.y;
       int fc1, fc2;
       double size1, size2;
@@ -1251,11 +1256,13 @@ __global__ void __launch_bounds__(128, FCLGPU_POOLED_MINBLOCKS) collide_pooled_k
             left = make_uint2((unsigned)b1, (unsigned)fc2);
             right = make_uint2((unsigned)b1, (unsigned)fc2 + 1u);
           }
-          stk[sp++] = right;
-          stk[sp++] = left;
+          stk[sp++] = right;  // slot sp-1 (the old top's slot) .. the register holds the new top
+          top = left;
+          ++sp;
+          have_top = true;
         }
       }
-      if (FCLGPU_PREFETCH && sp > 0) prefetch_bv32(P.m1, P.m2, stk[sp - 1]);
+      if (!have_top && sp > 0) top = stk[sp - 1];  // entry below becomes the top
     }
   }
 }
