@@ -252,6 +252,44 @@ def _current_device():
     return 0
 
 
+class CollisionObject:
+    """fcl::CollisionObject<double> for BVHModel geometries (narrowphase/collision_object.h): a geometry
+    plus a transform; collide(o1, o2, request, result) / distance(o1, o2, request, result) forward the
+    geometry and getTransform() exactly like collision-inl.h:81-91,154-175."""
+
+    def __init__(self, cgeom, tf=None):
+        self.cgeom = cgeom
+        self.t = Transform3() if tf is None else tf
+        self.user_data = None
+
+    def collisionGeometry(self):
+        return self.cgeom
+
+    def getTransform(self):
+        return self.t
+
+    def setTransform(self, R_or_tf, T=None):
+        self.t = R_or_tf if isinstance(R_or_tf, Transform3) else Transform3(R_or_tf, T)
+
+    def getRotation(self):
+        return self.t.R
+
+    def getTranslation(self):
+        return self.t.t
+
+    def setRotation(self, R):
+        self.t = Transform3(R, self.t.t)
+
+    def setTranslation(self, T):
+        self.t = Transform3(self.t.R, T)
+
+    def getObjectType(self):
+        return self.cgeom.getObjectType()
+
+    def getNodeType(self):
+        return self.cgeom.getNodeType()
+
+
 class CollisionRequest:
     def __init__(self, num_max_contacts=1, enable_contact=False, num_max_cost_sources=1, enable_cost=False,
                  use_approximate_cost=True, gjk_solver_type="GST_LIBCCD", gjk_tolerance=1e-6):
@@ -489,9 +527,14 @@ def sync_status(device=None, stream=None):
 # ------------------------------------------------------------------------------------------------
 # single-query entry points with the reference's signatures
 # ------------------------------------------------------------------------------------------------
-def collide(o1, tf1, o2, tf2, request, result):
-    """fcl::collide(o1, tf1, o2, tf2, request, result) for two BVHModel<OBBRSS> (collision-inl.h:95-207).
+def collide(o1, tf1, o2=None, tf2=None, request=None, result=None):
+    """fcl::collide(o1, tf1, o2, tf2, request, result) for two BVHModel<OBBRSS> (collision-inl.h:95-207),
+    or the CollisionObject overload collide(obj1, obj2, request, result) (collision-inl.h:154-175).
     Appends to `result` (results accumulate across calls unless cleared) and returns numContacts()."""
+    if isinstance(o1, CollisionObject):  # collide(obj1, obj2, request, result)
+        obj1, obj2, request, result = o1, tf1, o2, tf2
+        return collide(obj1.collisionGeometry(), obj1.getTransform(), obj2.collisionGeometry(), obj2.getTransform(),
+                       request, result)
     if request.num_max_contacts == 0:
         sys.stderr.write(f"Warning: should stop early as num_max_contact is {request.num_max_contacts} !\n")
         return 0
@@ -515,8 +558,13 @@ def collide(o1, tf1, o2, tf2, request, result):
     return result.numContacts()
 
 
-def distance(o1, tf1, o2, tf2, request, result):
-    """fcl::distance(o1, tf1, o2, tf2, request, result) (distance-inl.h:92-246); returns min_distance."""
+def distance(o1, tf1, o2=None, tf2=None, request=None, result=None):
+    """fcl::distance(o1, tf1, o2, tf2, request, result) (distance-inl.h:92-246), or the CollisionObject
+    overload distance(obj1, obj2, request, result) (distance-inl.h:196-218); returns min_distance."""
+    if isinstance(o1, CollisionObject):
+        obj1, obj2, request, result = o1, tf1, o2, tf2
+        return distance(obj1.collisionGeometry(), obj1.getTransform(), obj2.collisionGeometry(), obj2.getTransform(),
+                        request, result)
     if not (isinstance(o1, BVHModel) and isinstance(o2, BVHModel)):
         sys.stderr.write("Warning: distance function between these node types is not supported\n")
         return DBL_MAX

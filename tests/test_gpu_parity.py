@@ -255,3 +255,47 @@ def test_full_size_properties_1m(models, oracle):
     assert np.array_equal(cnt.cpu().numpy()[idx], ref["counts"])
     rd = oracle.distance_batch(oenv, orob, P[idx], None, True, 2, nthreads=8)
     assert np.array_equal(dist.cpu().numpy()[idx], rd["min_distance"])
+
+
+def test_mesh_mesh_consistency_across_split_methods(env_rob_npz, oracle):
+    """FCL_COLLISION.mesh_mesh / FCL_DISTANCE.mesh_distance on the GPU path
+    (test/test_fcl_collision.cpp:792-886, test/test_fcl_distance.cpp:177-298): with
+    num_max_contacts = INT_MAX and enable_contact the sorted contact (b1, b2) sets are identical for
+    MEAN / MEDIAN / BV_CENTER trees and for "pose carried by the node" vs "pose baked into the
+    vertices"; distances agree (the reference tolerates 1e-3, here they are equal)."""
+    (ev, et), (rv, rt) = env_rob_npz
+    P = random_poses(10, seed=17)  # the reference uses 10 poses
+    per_split, dists = [], []
+    for split in (F.SPLIT_METHOD_MEAN, F.SPLIT_METHOD_MEDIAN, F.SPLIT_METHOD_BV_CENTER):
+        env, rob = F.BVHModel.from_arrays(ev, et, split), F.BVHModel.from_arrays(rv, rt, split)
+        r = F.collide_batch(env, P, rob, None, F.CollisionRequest(INT_MAX, True), contact_capacity=4000, grow_on_overflow=True)
+        per_split.append([sorted(set(zip(r.contacts_of(i)["b1"].tolist(), r.contacts_of(i)["b2"].tolist()))) for i in range(len(P))])
+        dists.append(F.distance_batch(env, P, rob, None, F.DistanceRequest(True)).min_distance)
+    assert per_split[0] == per_split[1] == per_split[2]
+    assert np.array_equal(dists[0], dists[1]) and np.array_equal(dists[0], dists[2])
+    assert any(len(s) > 0 for s in per_split[0])
+    # collide_Test2 style: transform env's vertices on the host, identity pose
+    for i in range(len(P)):
+        R, t = P[i, :9].reshape(3, 3), P[i, 9:]
+        env_t = F.BVHModel.from_arrays(ev @ R.T + t, et)
+        r = F.collide_batch(env_t, identity_poses(1), F.BVHModel.from_arrays(rv, rt), None, F.CollisionRequest(INT_MAX, True),
+                            contact_capacity=4000, grow_on_overflow=True)
+        got = sorted(set(zip(r.contacts["b1"].tolist(), r.contacts["b2"].tolist())))
+        # baking the pose rounds the vertices, so razor-edge pairs may flip: require near-identity
+        a, b = set(got), set(per_split[0][i])
+        assert len(a ^ b) <= max(2, len(b) // 100)
+
+
+def test_collision_object_overloads(models, oracle):
+    (env, rob), (oenv, orob) = models
+    P = random_poses(5, seed=18)
+    for i in range(len(P)):
+        o1 = F.CollisionObject(env, F.Transform3.from_pose12(P[i]))
+        o2 = F.CollisionObject(rob)
+        res = F.CollisionResult()
+        n = F.collide(o1, o2, F.CollisionRequest(1000, True), res)
+        ref = oracle.collide_batch(oenv, orob, P[i:i + 1], None, 1000, True)
+        assert n == ref["counts"][0]
+        dres = F.DistanceResult()
+        d = F.distance(o1, o2, F.DistanceRequest(True), dres)
+        assert d == oracle.distance_batch(oenv, orob, P[i:i + 1], None, True)["min_distance"][0]
