@@ -47,6 +47,8 @@ class FclGpuError(RuntimeError):
 # every symbol include/fclgpu.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "fclgpu_bvh_build_obbrss", "fclgpu_bvh_destroy", "fclgpu_bvh_num_nodes", "fclgpu_bvh_num_tris", "fclgpu_bvh_get",
+    "fclgpu_bvh_refit_topdown", "fclgpu_bvh_num_vertices", "fclgpu_bvh_get_partition", "fclgpu_model_set_partition",
+    "fclgpu_model_refit_topdown", "fclgpu_model_download",
     "fclgpu_model_create_obbrss", "fclgpu_model_from_bvh", "fclgpu_model_destroy", "fclgpu_model_num_nodes",
     "fclgpu_model_num_tris", "fclgpu_model_device", "fclgpu_collide_batch", "fclgpu_collide_batch_host",
     "fclgpu_distance_batch", "fclgpu_distance_batch_host", "fclgpu_abi_version", "fclgpu_device_count",
@@ -74,6 +76,12 @@ def lib():
     L.fclgpu_bvh_num_nodes.argtypes = [vp]
     L.fclgpu_bvh_num_tris.argtypes = [vp]
     L.fclgpu_bvh_get.argtypes = [vp] * 9
+    L.fclgpu_bvh_refit_topdown.argtypes = [vp, vp, C.c_int32]
+    L.fclgpu_bvh_num_vertices.argtypes = [vp]
+    L.fclgpu_bvh_get_partition.argtypes = [vp] * 5
+    L.fclgpu_model_set_partition.argtypes = [vp, C.c_int32, vp, vp, vp, vp]
+    L.fclgpu_model_refit_topdown.argtypes = [vp, vp, C.c_int32, C.c_int32, vp]
+    L.fclgpu_model_download.argtypes = [vp] * 8
     L.fclgpu_model_create_obbrss.argtypes = [C.c_int, C.c_int32, vp, vp, vp, vp, vp, vp, vp, C.c_int32, vp,
                                              C.POINTER(C.c_void_p)]
     L.fclgpu_model_from_bvh.argtypes = [C.c_int, vp, C.POINTER(C.c_void_p)]

@@ -33,6 +33,7 @@ BVH_ERR_UNKNOWN = -8
 
 # BVHBuildState (BVH_internal.h:48-57)
 BVH_BUILD_STATE_EMPTY, BVH_BUILD_STATE_BEGUN, BVH_BUILD_STATE_PROCESSED = 0, 1, 2
+BVH_BUILD_STATE_UPDATE_BEGUN, BVH_BUILD_STATE_UPDATED, BVH_BUILD_STATE_REPLACE_BEGUN = 3, 4, 5
 
 SPLIT_METHOD_MEAN, SPLIT_METHOD_MEDIAN, SPLIT_METHOD_BV_CENTER = 0, 1, 2
 
@@ -188,6 +189,100 @@ class BVHModel:
         self._bvh = h
         self.build_state = BVH_BUILD_STATE_PROCESSED
         return BVH_OK
+
+    # -- replace protocol (BVH_model-inl.h:521-620) --
+    def beginReplaceModel(self):
+        if self.build_state != BVH_BUILD_STATE_PROCESSED:
+            sys.stderr.write("BVH Error! Call beginReplaceModel() on a BVHModel that has no previous frame.\n")
+            return BVH_ERR_BUILD_EMPTY_PREVIOUS_FRAME
+        self._replace = []
+        self.num_vertex_updated = 0
+        self.build_state = BVH_BUILD_STATE_REPLACE_BEGUN
+        return BVH_OK
+
+    def replaceSubModel(self, ps):
+        if self.build_state != BVH_BUILD_STATE_REPLACE_BEGUN:
+            sys.stderr.write("BVH Warning! Call replaceSubModel() in a wrong order. replaceSubModel() was ignored. Must do "
+                             "a beginReplaceModel() for initialization.\n")
+            return BVH_ERR_BUILD_OUT_OF_SEQUENCE
+        ps = np.asarray(ps, dtype=np.float64).reshape(-1, 3)
+        self._replace.append(ps)
+        self.num_vertex_updated += len(ps)
+        return BVH_OK
+
+    def replaceVertex(self, p):
+        if self.build_state != BVH_BUILD_STATE_REPLACE_BEGUN:
+            sys.stderr.write("BVH Warning! Call replaceVertex() in a wrong order. replaceVertex() was ignored. Must do a "
+                             "beginReplaceModel() for initialization.\n")
+            return BVH_ERR_BUILD_OUT_OF_SEQUENCE
+        return self.replaceSubModel(np.asarray(p, dtype=np.float64).reshape(1, 3))
+
+    def replaceTriangle(self, p1, p2, p3):
+        if self.build_state != BVH_BUILD_STATE_REPLACE_BEGUN:
+            sys.stderr.write("BVH Warning! Call replaceTriangle() in a wrong order. replaceTriangle() was ignored. Must do a "
+                             "beginReplaceModel() for initialization.\n")
+            return BVH_ERR_BUILD_OUT_OF_SEQUENCE
+        return self.replaceSubModel(np.array([p1, p2, p3], dtype=np.float64))
+
+    def endReplaceModel(self, refit=True, bottomup=True):
+        """refit=True, bottomup=False: top-down refit (refitTree_topdown) on the host copy AND, by a kernel,
+        on every uploaded device copy (bit-identical BVs).  refit=False: rebuild the tree (buildTree) and
+        re-upload.  The bottom-up refit (fit3 + BV merging, BVH_model-inl.h:961-1037) is not on this path."""
+        if self.build_state != BVH_BUILD_STATE_REPLACE_BEGUN:
+            sys.stderr.write("BVH Warning! Call endReplaceModel() in a wrong order. endReplaceModel() was ignored. \n")
+            return BVH_ERR_BUILD_OUT_OF_SEQUENCE
+        if self.num_vertex_updated != self.num_vertices:
+            sys.stderr.write("BVH Error! The replaced model should have the same number of vertices as the old model.\n")
+            return BVH_ERR_INCORRECT_DATA
+        new_v = np.ascontiguousarray(np.concatenate(self._replace), dtype=np.float64)
+        if refit and bottomup:
+            sys.stderr.write("BVH Error! bottom-up refit is not supported on the OBBRSS mesh-mesh GPU path; use "
+                             "endReplaceModel(True, False) or endReplaceModel(False).\n")
+            return BVH_ERR_UNSUPPORTED_FUNCTION
+        self.vertices = new_v
+        L = _capi.lib()
+        if refit:
+            rc = L.fclgpu_bvh_refit_topdown(self._bvh, addr(new_v), self.num_vertices)
+            if rc != 0:
+                return rc
+            for dev, h in self._dev.items():
+                check(L.fclgpu_model_refit_topdown(h, addr(new_v), self.num_vertices, 0, None))
+                check(L.fclgpu_sync_status(int(dev), None))
+        else:
+            self._release()
+            h = C.c_void_p()
+            rc = L.fclgpu_bvh_build_obbrss(addr(self.vertices), self.num_vertices, addr(self.tri_indices), self.num_tris,
+                                           self.split_method, C.byref(h))
+            if rc != 0:
+                return rc
+            self._bvh = h
+        self.build_state = BVH_BUILD_STATE_PROCESSED
+        return BVH_OK
+
+    def refit_device(self, vertices, device=None, stream=None):
+        """Device-resident update: `vertices` is a CUDA float64 tensor (num_vertices, 3); only the device copy
+        on that GPU is refitted (asynchronous on `stream`); the host copy is left untouched."""
+        torch = _torch()
+        dev = vertices.device.index if device is None else device
+        st = (stream or torch.cuda.current_stream(dev)).cuda_stream
+        check(_capi.lib().fclgpu_model_refit_topdown(self.device_model(dev), addr(vertices), self.num_vertices, 1, st))
+
+    def download_device_arrays(self, device=None):
+        """FP64 node records as they currently are in HBM (for tests / inspection)."""
+        h = self.device_model(device)
+        n, nt = self.getNumBVs(), self.num_tris
+        out = dict(axis=np.empty((n, 9)), obb_To=np.empty((n, 3)), obb_ext=np.empty((n, 3)), rss_To=np.empty((n, 3)),
+                   rss_l=np.empty((n, 2)), rss_r=np.empty(n), tri_verts=np.empty((nt, 9)))
+        check(_capi.lib().fclgpu_model_download(h, addr(out["axis"]), addr(out["obb_To"]), addr(out["obb_ext"]),
+                                                addr(out["rss_To"]), addr(out["rss_l"]), addr(out["rss_r"]),
+                                                addr(out["tri_verts"])))
+        return out
+
+    def partition(self):
+        n, nt = self.getNumBVs(), self.num_tris
+        fp, npr, pi = np.empty(n, np.int32), np.empty(n, np.int32), np.empty(nt, np.int32)
+        check(_capi.lib().fclgpu_bvh_get_partition(self._bvh, addr(fp), addr(npr), addr(pi), None))
+        return fp, npr, pi
 
     @classmethod
     def from_arrays(cls, verts, tris, split_method=SPLIT_METHOD_MEAN):

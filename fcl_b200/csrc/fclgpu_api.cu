@@ -16,6 +16,7 @@
 #include "bvh_build.hpp"
 #include "records.hpp"
 #include "traversal.cuh"
+#include "refit.cuh"
 
 using namespace fclgpu;
 
@@ -63,6 +64,7 @@ std::map<std::string, long long> g_opts = {
     // binary-mode collide at traversal >= 3: 1 = pooled kernel (measured fastest: 3.8 ms per 1M poses),
     // 2 = pooled kernel with the FP32 triangle classification (4.2 ms), 0 = deferred kernel with classification (4.9 ms)
     {"binary_pooled", 1},
+    {"refit_warp", 1},         // on-device refit: 1 = warp-cooperative fit for large nodes, 0 = one thread per node
     {"pool_trigger", 32},      // collide variant P: queued pairs in the warp that trigger a pooled leaf round
     {"leaf_trigger", 20},      // collide variant D: lanes with queued triangle pairs that trigger a leaf round
 };
@@ -144,6 +146,12 @@ struct fclgpu_model {
   RssRec32* rss32;
   ObbRec32* obb32;
   double2* topo;
+  // refit topology (optional)
+  int32_t num_vertices = 0;
+  int32_t *tri_index = nullptr, *node_first = nullptr, *node_count = nullptr, *by_size = nullptr;
+  int32_t n_big = 0;  // nodes with more than kRefitWarpThreshold triangles (front of by_size)
+  uint32_t* prim_order = nullptr;
+  double* vert_stage = nullptr;
   int32_t* fc;
   int depth;
 };
@@ -263,6 +271,47 @@ extern "C" int fclgpu_model_create_obbrss(int device, int32_t n_nodes, const int
   return FCLGPU_OK;
 }
 
+extern "C" int fclgpu_model_set_partition(fclgpu_model* m, int32_t num_vertices, const int32_t* tri_indices3,
+                                          const int32_t* first_primitive, const int32_t* num_primitives,
+                                          const int32_t* primitive_indices) {
+  if (!m || !tri_indices3 || !first_primitive || !num_primitives || !primitive_indices || num_vertices <= 0)
+    return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL partition array");
+  const int nn = m->d.n_nodes, nt = m->d.n_tris;
+  long long covered = 0;
+  for (int i = 0; i < nn; ++i) {
+    if (first_primitive[i] < 0 || num_primitives[i] <= 0 || first_primitive[i] + num_primitives[i] > nt)
+      return fail(FCLGPU_ERR_INCORRECT_DATA, "node %d: primitive range out of bounds", i);
+    if (num_primitives[i] == 1) covered++;
+  }
+  if (covered != nt) return fail(FCLGPU_ERR_INCORRECT_DATA, "partition does not have one leaf per triangle");
+  for (long long i = 0; i < 3ll * nt; ++i)
+    if (tri_indices3[i] < 0 || tri_indices3[i] >= num_vertices) return fail(FCLGPU_ERR_INCORRECT_DATA, "triangle index out of range");
+  std::vector<int32_t> by_size(nn);
+  for (int i = 0; i < nn; ++i) by_size[i] = i;
+  std::stable_sort(by_size.begin(), by_size.end(), [&](int a, int b) { return num_primitives[a] > num_primitives[b]; });
+  int n_big = 0;
+  while (n_big < nn && num_primitives[by_size[n_big]] > 24) ++n_big;  // larger nodes get a whole warp
+  m->n_big = n_big;
+  CUDA_TRY(cudaSetDevice(m->device));
+  auto up = [&](int32_t** dst, const void* src, size_t count) -> int {
+    if (*dst) CUDA_TRY(cudaFree(*dst));
+    *dst = nullptr;
+    CUDA_TRY(cudaMalloc((void**)dst, count * sizeof(int32_t)));
+    CUDA_TRY(cudaMemcpy(*dst, src, count * sizeof(int32_t), cudaMemcpyHostToDevice));
+    return 0;
+  };
+  int rc;
+  if ((rc = up(&m->tri_index, tri_indices3, 3 * (size_t)nt)) || (rc = up(&m->node_first, first_primitive, nn)) ||
+      (rc = up(&m->node_count, num_primitives, nn)) || (rc = up(&m->by_size, by_size.data(), nn)) ||
+      (rc = up((int32_t**)&m->prim_order, primitive_indices, nt)))
+    return rc;
+  if (m->vert_stage) CUDA_TRY(cudaFree(m->vert_stage));
+  m->vert_stage = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&m->vert_stage, 3 * (size_t)num_vertices * sizeof(double)));
+  m->num_vertices = num_vertices;
+  return FCLGPU_OK;
+}
+
 extern "C" int fclgpu_model_from_bvh(int device, const fclgpu_bvh* bvh, fclgpu_model** out) {
   if (!bvh) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "bvh is NULL");
   const int nn = fclgpu_bvh_num_nodes(bvh), nt = fclgpu_bvh_num_tris(bvh);
@@ -270,8 +319,74 @@ extern "C" int fclgpu_model_from_bvh(int device, const fclgpu_bvh* bvh, fclgpu_m
   std::vector<double> axis(9 * (size_t)nn), oT(3 * (size_t)nn), oe(3 * (size_t)nn), rT(3 * (size_t)nn), rl(2 * (size_t)nn),
       rr(nn), tv(9 * (size_t)nt);
   fclgpu_bvh_get(bvh, fc.data(), axis.data(), oT.data(), oe.data(), rT.data(), rl.data(), rr.data(), tv.data());
-  return fclgpu_model_create_obbrss(device, nn, fc.data(), axis.data(), oT.data(), oe.data(), rT.data(), rl.data(),
-                                    rr.data(), nt, tv.data(), out);
+  int rc = fclgpu_model_create_obbrss(device, nn, fc.data(), axis.data(), oT.data(), oe.data(), rT.data(), rl.data(),
+                                      rr.data(), nt, tv.data(), out);
+  if (rc) return rc;
+  std::vector<int32_t> nf(nn), nc(nn), po(nt), ti(3 * (size_t)nt);
+  fclgpu_bvh_get_partition(bvh, nf.data(), nc.data(), po.data(), ti.data());
+  rc = fclgpu_model_set_partition(*out, fclgpu_bvh_num_vertices(bvh), ti.data(), nf.data(), nc.data(), po.data());
+  if (rc) {
+    fclgpu_model_destroy(*out);
+    *out = nullptr;
+  }
+  return rc;
+}
+
+extern "C" int fclgpu_model_refit_topdown(fclgpu_model* m, const double* vertices, int32_t num_vertices,
+                                          int32_t vertices_on_device, void* stream) {
+  if (!m || !vertices) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL model/vertices");
+  if (!m->prim_order) return fail(FCLGPU_ERR_UNSUPPORTED_FUNCTION, "model has no refit topology (fclgpu_model_set_partition)");
+  if (num_vertices != m->num_vertices)  // BVH_model-inl.h:602-606
+    return fail(FCLGPU_ERR_INCORRECT_DATA, "the replaced model must have the same number of vertices (%d != %d)", num_vertices, m->num_vertices);
+  CUDA_TRY(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const double* dv = vertices;
+  if (!vertices_on_device) {
+    CUDA_TRY(cudaMemcpyAsync(m->vert_stage, vertices, 3 * (size_t)num_vertices * sizeof(double), cudaMemcpyHostToDevice, st));
+    dv = m->vert_stage;
+  }
+  RefitParams P{m->obb, m->rss, m->tri, m->rss32, m->obb32, m->topo, m->tri_index, m->node_first, m->node_count,
+                m->prim_order, m->by_size, m->d.n_nodes, m->d.n_tris};
+  gather_tris_kernel<<<(P.n_tris + 255) / 256, 256, 0, st>>>(P, dv);
+  if (opt("refit_warp") && m->n_big > 0) {
+    refit_big_nodes_kernel<<<(m->n_big * 32 + 127) / 128, 128, 0, st>>>(P, m->n_big);
+    if (P.n_nodes > m->n_big) refit_small_nodes_kernel<<<(P.n_nodes - m->n_big + 63) / 64, 64, 0, st>>>(P, m->n_big);
+    g_launches += 3;
+  } else {
+    refit_nodes_kernel<<<(P.n_nodes + 63) / 64, 64, 0, st>>>(P);
+    g_launches += 2;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return FCLGPU_OK;
+}
+
+extern "C" int fclgpu_model_download(const fclgpu_model* m, double* axis9, double* obb_To3, double* obb_extent3,
+                                     double* rss_To3, double* rss_l2, double* rss_r, double* tri_verts9) {
+  if (!m) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL model");
+  CUDA_TRY(cudaSetDevice(m->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  const int nn = m->d.n_nodes, nt = m->d.n_tris;
+  std::vector<double> obb((size_t)nn * kNodeDoubles), rss((size_t)nn * kNodeDoubles), tri((size_t)nt * kTriDoubles);
+  CUDA_TRY(cudaMemcpy(obb.data(), m->obb, obb.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(rss.data(), m->rss, rss.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(tri.data(), m->tri, tri.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < nn; ++i) {
+    const double* o = &obb[(size_t)i * kNodeDoubles];
+    const double* r = &rss[(size_t)i * kNodeDoubles];
+    for (int k = 0; k < 9; ++k)
+      if (axis9) axis9[9 * (size_t)i + k] = o[k];
+    for (int k = 0; k < 3; ++k) {
+      if (obb_To3) obb_To3[3 * (size_t)i + k] = o[9 + k];
+      if (obb_extent3) obb_extent3[3 * (size_t)i + k] = o[12 + k];
+      if (rss_To3) rss_To3[3 * (size_t)i + k] = r[9 + k];
+    }
+    if (rss_l2) { rss_l2[2 * (size_t)i] = r[12]; rss_l2[2 * (size_t)i + 1] = r[13]; }
+    if (rss_r) rss_r[i] = r[14];
+  }
+  if (tri_verts9)
+    for (int t = 0; t < nt; ++t)
+      for (int k = 0; k < 9; ++k) tri_verts9[9 * (size_t)t + k] = tri[(size_t)t * kTriDoubles + k];
+  return FCLGPU_OK;
 }
 
 extern "C" int fclgpu_model_destroy(fclgpu_model* m) {
@@ -284,6 +399,12 @@ extern "C" int fclgpu_model_destroy(fclgpu_model* m) {
   cudaFree(m->rss32);
   cudaFree(m->obb32);
   cudaFree(m->topo);
+  cudaFree(m->tri_index);
+  cudaFree(m->node_first);
+  cudaFree(m->node_count);
+  cudaFree(m->by_size);
+  cudaFree(m->prim_order);
+  cudaFree(m->vert_stage);
   delete m;
   return FCLGPU_OK;
 }

@@ -1,0 +1,371 @@
+// refit.cuh — on-device top-down refit of an OBBRSS BVH.
+//
+// Reference semantics: BVHModel::endReplaceModel(refit = true, bottomup = false) ->
+// refitTree_topdown (include/fcl/geometry/bvh/BVH_model-inl.h:594-620, 1064-1076): the tree
+// keeps its shape; every node's OBBRSS is fitted again over the node's primitive range in
+// primitive_indices order (FitImpl<OBBRSS>, detail/BV_fitter-inl.h:449-477).
+//
+// Kernels: gather_tris (vertices -> de-indexed 80-byte triangle records), refit_nodes (one
+// thread per node runs fit_obbrss sequentially, so every sum has the reference's order and
+// the BVs are bit-identical to a CPU refit; nodes are processed largest first), and the same
+// thread repacks the node's FP64 records, its single-precision steering records and `size`.
+// The work of a node is proportional to its triangle count, so the launch time is set by the
+// root (n triangles, sequential); that is the price of bit-exact sums and is still several
+// times faster than the host refit and needs no PCIe round trip.
+#pragma once
+#include "bvh_fit.cuh"
+#include "records.hpp"
+#include "traversal.cuh"
+
+namespace fclgpu {
+
+struct RefitParams {
+  double* obb;
+  double* rss;
+  double* tri;  // 10 doubles per triangle
+  RssRec32* rss32;
+  ObbRec32* obb32;
+  double2* topo;
+  const int32_t* tri_index;   // 3 per triangle
+  const int32_t* node_first;  // per node
+  const int32_t* node_count;
+  const uint32_t* prim_order;
+  const int32_t* by_size;     // node ids sorted by decreasing primitive count
+  int32_t n_nodes, n_tris;
+};
+
+__global__ void gather_tris_kernel(RefitParams P, const double* __restrict__ vertices) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P.n_tris) return;
+  double* o = P.tri + (size_t)t * kTriDoubles;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double* v = vertices + 3 * (size_t)P.tri_index[3 * (size_t)t + k];
+    o[3 * k] = v[0];
+    o[3 * k + 1] = v[1];
+    o[3 * k + 2] = v[2];
+  }
+  o[9] = 0.0;
+}
+
+__global__ void __launch_bounds__(64) refit_nodes_kernel(RefitParams P) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= P.n_nodes) return;
+  const int node = P.by_size[k];
+  NodeFit f;
+  fit_obbrss(P.tri, kTriDoubles, P.prim_order + P.node_first[node], P.node_count[node], f);
+  double* o = P.obb + (size_t)node * kNodeDoubles;
+  double* r = P.rss + (size_t)node * kNodeDoubles;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) o[i] = r[i] = f.axis[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    o[9 + i] = f.obb_To[i];
+    o[12 + i] = f.obb_ext[i];
+    r[9 + i] = f.rss_To[i];
+  }
+  r[12] = f.rss_l[0];
+  r[13] = f.rss_l[1];
+  r[14] = f.rss_r;
+  const double size = (f.obb_ext[0] * f.obb_ext[0] + f.obb_ext[1] * f.obb_ext[1]) + f.obb_ext[2] * f.obb_ext[2];
+  o[15] = r[15] = size;
+  RssRec32 r32;
+  pack_rss32(f.axis, f.rss_To, f.rss_l, f.rss_r, r32);
+  P.rss32[node] = r32;
+  ObbRec32 o32;
+  pack_obb32(f.axis, f.obb_To, f.obb_ext, o32);
+  P.obb32[node] = o32;
+  double2 t = P.topo[node];
+  t.y = size;
+  P.topo[node] = t;
+}
+
+}  // namespace fclgpu
+
+namespace fclgpu {
+
+// ---------------------------------------------------------------------------------------
+// Warp-cooperative fit for large nodes.  Bit-identical to fit_obbrss:
+//   * covariance: the 32 lanes compute the per-triangle terms of a chunk in parallel, then
+//     nine lanes (one per accumulator) add the 32 terms IN ORDER, so each running sum sees
+//     exactly the sequence of additions of the sequential loop;
+//   * extents, z range, extreme points (first index wins ties), rectangle growth: min / max /
+//     arg-min reductions, which are exact and order independent (the reference's "skip points
+//     inside the current bound" tests only skip candidates that cannot change the result);
+//   * corner growth: the rectangle only grows, so only points outside the INITIAL rectangle in
+//     both coordinates can ever trigger; they are found in parallel and replayed in order.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = (w < v) ? w : v;
+  }
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = (w > v) ? w : v;
+  }
+  return v;
+}
+// (value, index) with the smallest value; ties -> smallest index.  sign = -1 turns it into arg-max.
+__device__ __forceinline__ void warp_argmin(double& v, int& idx) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double w = __shfl_xor_sync(0xffffffffu, v, o);
+    const int wi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (w < v || (w == v && wi < idx)) {
+      v = w;
+      idx = wi;
+    }
+  }
+}
+
+__device__ inline void fit_obbrss_warp(const double* __restrict__ tv, int tri_stride, const uint32_t* __restrict__ idx,
+                                       int n, double (*terms)[9], NodeFit& f) {
+  const int lane = threadIdx.x & 31;
+  // --- covariance ---
+  double acc = 0.0;  // lane k < 9 owns accumulator k: S1[0..2], S2 xx yy zz xy xz yz
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    if (i < n) {
+      const double* p1 = tv + (size_t)idx[i] * tri_stride;
+      const double* p2 = p1 + 3;
+      const double* p3 = p1 + 6;
+      double t[9];
+      for (int k = 0; k < 3; ++k) t[k] = ((p1[k] + p2[k]) + p3[k]);
+      t[3] = (p1[0] * p1[0] + p2[0] * p2[0] + p3[0] * p3[0]);
+      t[4] = (p1[1] * p1[1] + p2[1] * p2[1] + p3[1] * p3[1]);
+      t[5] = (p1[2] * p1[2] + p2[2] * p2[2] + p3[2] * p3[2]);
+      t[6] = (p1[0] * p1[1] + p2[0] * p2[1] + p3[0] * p3[1]);
+      t[7] = (p1[0] * p1[2] + p2[0] * p2[2] + p3[0] * p3[2]);
+      t[8] = (p1[1] * p1[2] + p2[1] * p2[2] + p3[1] * p3[2]);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) terms[lane][k] = t[k];
+    }
+    __syncwarp();
+    if (lane < 9) {
+      const int cnt = (n - base) < 32 ? (n - base) : 32;
+      for (int r = 0; r < cnt; ++r) acc += terms[r][lane];
+    }
+    __syncwarp();
+  }
+  double S1[3], S2[6];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) S1[k] = __shfl_sync(0xffffffffu, acc, k);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) S2[k] = __shfl_sync(0xffffffffu, acc, 3 + k);
+  const int np = 3 * n;
+  double M[3][3];
+  M[0][0] = S2[0] - S1[0] * S1[0] / np;
+  M[1][1] = S2[1] - S1[1] * S1[1] / np;
+  M[2][2] = S2[2] - S1[2] * S1[2] / np;
+  M[0][1] = M[1][0] = S2[3] - S1[0] * S1[1] / np;
+  M[1][2] = M[2][1] = S2[5] - S1[1] * S1[2] / np;
+  M[0][2] = M[2][0] = S2[4] - S1[0] * S1[2] / np;
+  double ev[3], V[3][3];
+  jacobi3(M, ev, V);
+  int lo, mid, hi;
+  if (ev[0] > ev[1]) { hi = 0; lo = 1; } else { lo = 0; hi = 1; }
+  if (ev[2] < ev[lo]) { mid = lo; lo = 2; }
+  else if (ev[2] > ev[hi]) { mid = hi; hi = 2; }
+  else mid = 2;
+  double* A = f.axis;
+  for (int r = 0; r < 3; ++r) {
+    A[3 * r + 0] = V[r][hi];
+    A[3 * r + 1] = V[r][mid];
+  }
+  A[2] = A[3] * A[7] - A[6] * A[4];
+  A[5] = A[6] * A[1] - A[0] * A[7];
+  A[8] = A[0] * A[4] - A[3] * A[1];
+  const double a00 = A[0], a10 = A[3], a20 = A[6], a01 = A[1], a11 = A[4], a21 = A[7], a02 = A[2], a12 = A[5], a22 = A[8];
+  const int m = 3 * n;
+#define W_PT(j) (tv + (size_t)idx[(j) / 3] * tri_stride + 3 * ((j) % 3))
+#define W_PX(p) ((a00 * (p)[0] + a10 * (p)[1]) + a20 * (p)[2])
+#define W_PY(p) ((a01 * (p)[0] + a11 * (p)[1]) + a21 * (p)[2])
+#define W_PZ(p) ((a02 * (p)[0] + a12 * (p)[1]) + a22 * (p)[2])
+  // --- extents (min / max of the projections) and extreme points along x and y (first index wins) ---
+  double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+  double vminx = DBL_MAX, vmaxx = DBL_MAX, vminy = DBL_MAX, vmaxy = DBL_MAX;  // arg-max tracked on the negated value
+  int iminx = 0x7fffffff, imaxx = 0x7fffffff, iminy = 0x7fffffff, imaxy = 0x7fffffff;
+  for (int j = lane; j < m; j += 32) {
+    const double* p = W_PT(j);
+    const double c0 = W_PX(p), c1 = W_PY(p), c2 = W_PZ(p);
+    if (c0 > mx[0]) mx[0] = c0;
+    if (c0 < mn[0]) mn[0] = c0;
+    if (c1 > mx[1]) mx[1] = c1;
+    if (c1 < mn[1]) mn[1] = c1;
+    if (c2 > mx[2]) mx[2] = c2;
+    if (c2 < mn[2]) mn[2] = c2;
+    if (c0 < vminx) { vminx = c0; iminx = j; }
+    if (-c0 < vmaxx) { vmaxx = -c0; imaxx = j; }
+    if (c1 < vminy) { vminy = c1; iminy = j; }
+    if (-c1 < vmaxy) { vmaxy = -c1; imaxy = j; }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    mn[k] = warp_min(mn[k]);
+    mx[k] = warp_max(mx[k]);
+  }
+  warp_argmin(vminx, iminx);
+  warp_argmin(vmaxx, imaxx);
+  warp_argmin(vminy, iminy);
+  warp_argmin(vmaxy, imaxy);
+  const double o[3] = {(mx[0] + mn[0]) / 2, (mx[1] + mn[1]) / 2, (mx[2] + mn[2]) / 2};
+  for (int r = 0; r < 3; ++r) {
+    f.obb_To[r] = (A[3 * r] * o[0] + A[3 * r + 1] * o[1]) + A[3 * r + 2] * o[2];
+    f.obb_ext[r] = (mx[r] - mn[r]) / 2;
+  }
+  const double minz = mn[2], maxz = mx[2];
+  const double r = 0.5 * (maxz - minz), radsqr = r * r, cz = 0.5 * (maxz + minz);
+  // initial rectangle from the extreme points
+  double minx, maxx, miny, maxy;
+  {
+    const double* p = W_PT(iminx);
+    double dz = W_PZ(p) - cz;
+    minx = W_PX(p) + sqrt(fmax(radsqr - dz * dz, 0.0));
+    p = W_PT(imaxx);
+    dz = W_PZ(p) - cz;
+    maxx = W_PX(p) - sqrt(fmax(radsqr - dz * dz, 0.0));
+    p = W_PT(iminy);
+    dz = W_PZ(p) - cz;
+    miny = W_PY(p) + sqrt(fmax(radsqr - dz * dz, 0.0));
+    p = W_PT(imaxy);
+    dz = W_PZ(p) - cz;
+    maxy = W_PY(p) - sqrt(fmax(radsqr - dz * dz, 0.0));
+  }
+  // growth: lo = min(lo, val + reach) over points with val < lo ; hi = max(hi, val - reach) over val > hi
+  {
+    double lx = minx, hx = maxx, ly = miny, hy = maxy;
+    for (int j = lane; j < m; j += 32) {
+      const double* p = W_PT(j);
+      const double px = W_PX(p), py = W_PY(p);
+      if (px < minx || px > maxx || py < miny || py > maxy) {
+        const double dz = W_PZ(p) - cz;
+        const double reach = sqrt(fmax(radsqr - dz * dz, 0.0));
+        if (px < minx) { const double x = px + reach; if (x < lx) lx = x; }
+        if (px > maxx) { const double x = px - reach; if (x > hx) hx = x; }
+        if (py < miny) { const double y = py + reach; if (y < ly) ly = y; }
+        if (py > maxy) { const double y = py - reach; if (y > hy) hy = y; }
+      }
+    }
+    // NOTE: the reference grows minx first and then tests maxx against the ORIGINAL maxx etc.; each of the
+    // four bounds depends only on its own initial value, so they can be reduced together.
+    minx = warp_min(lx);
+    maxx = warp_max(hx);
+    miny = warp_min(ly);
+    maxy = warp_max(hy);
+  }
+  // corner growth, replayed in point order over the candidates
+  const double a = sqrt(0.5);
+  const double minx0 = minx, maxx0 = maxx, miny0 = miny, maxy0 = maxy;
+  for (int base = 0; base < m; base += 32) {
+    const int j = base + lane;
+    double px = 0, py = 0, pz = 0;
+    bool cand = false;
+    if (j < m) {
+      const double* p = W_PT(j);
+      px = W_PX(p); py = W_PY(p); pz = W_PZ(p);
+      cand = (px > maxx0 || px < minx0) && (py > maxy0 || py < miny0);
+    }
+    unsigned mask = __ballot_sync(0xffffffffu, cand);
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const double qx = __shfl_sync(0xffffffffu, px, src), qy = __shfl_sync(0xffffffffu, py, src), qz = __shfl_sync(0xffffffffu, pz, src);
+      double dx, dy, u, t;
+      if (qx > maxx) {
+        if (qy > maxy) {
+          dx = qx - maxx; dy = qy - maxy;
+          u = dx * a + dy * a;
+          t = (a * u - dx) * (a * u - dx) + (a * u - dy) * (a * u - dy) + (cz - qz) * (cz - qz);
+          u = u - sqrt(fmax(radsqr - t, 0.0));
+          if (u > 0) { maxx += u * a; maxy += u * a; }
+        } else if (qy < miny) {
+          dx = qx - maxx; dy = qy - miny;
+          u = dx * a - dy * a;
+          t = (a * u - dx) * (a * u - dx) + (-a * u - dy) * (-a * u - dy) + (cz - qz) * (cz - qz);
+          u = u - sqrt(fmax(radsqr - t, 0.0));
+          if (u > 0) { maxx += u * a; miny -= u * a; }
+        }
+      } else if (qx < minx) {
+        if (qy > maxy) {
+          dx = qx - minx; dy = qy - maxy;
+          u = dy * a - dx * a;
+          t = (-a * u - dx) * (-a * u - dx) + (a * u - dy) * (a * u - dy) + (cz - qz) * (cz - qz);
+          u = u - sqrt(fmax(radsqr - t, 0.0));
+          if (u > 0) { minx -= u * a; maxy += u * a; }
+        } else if (qy < miny) {
+          dx = qx - minx; dy = qy - miny;
+          u = -dx * a - dy * a;
+          t = (-a * u - dx) * (-a * u - dx) + (-a * u - dy) * (-a * u - dy) + (cz - qz) * (cz - qz);
+          u = u - sqrt(fmax(radsqr - t, 0.0));
+          if (u > 0) { minx -= u * a; miny -= u * a; }
+        }
+      }
+    }
+  }
+  for (int k = 0; k < 3; ++k) f.rss_To[k] = (A[3 * k] * minx + A[3 * k + 1] * miny) + A[3 * k + 2] * cz;
+  f.rss_l[0] = maxx - minx;
+  if (f.rss_l[0] < 0) f.rss_l[0] = 0;
+  f.rss_l[1] = maxy - miny;
+  if (f.rss_l[1] < 0) f.rss_l[1] = 0;
+  f.rss_r = r;
+#undef W_PT
+#undef W_PX
+#undef W_PY
+#undef W_PZ
+}
+
+__device__ __forceinline__ void store_node_records(const RefitParams& P, int node, const NodeFit& f) {
+  double* o = P.obb + (size_t)node * kNodeDoubles;
+  double* r = P.rss + (size_t)node * kNodeDoubles;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) o[i] = r[i] = f.axis[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    o[9 + i] = f.obb_To[i];
+    o[12 + i] = f.obb_ext[i];
+    r[9 + i] = f.rss_To[i];
+  }
+  r[12] = f.rss_l[0];
+  r[13] = f.rss_l[1];
+  r[14] = f.rss_r;
+  const double size = (f.obb_ext[0] * f.obb_ext[0] + f.obb_ext[1] * f.obb_ext[1]) + f.obb_ext[2] * f.obb_ext[2];
+  o[15] = r[15] = size;
+  RssRec32 r32;
+  pack_rss32(f.axis, f.rss_To, f.rss_l, f.rss_r, r32);
+  P.rss32[node] = r32;
+  ObbRec32 o32;
+  pack_obb32(f.axis, f.obb_To, f.obb_ext, o32);
+  P.obb32[node] = o32;
+  double2 t = P.topo[node];
+  t.y = size;
+  P.topo[node] = t;
+}
+
+// one warp per node for the n_big largest nodes (by_size[0 .. n_big))
+__global__ void __launch_bounds__(128) refit_big_nodes_kernel(RefitParams P, int n_big) {
+  __shared__ double terms[4][32][9];
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= n_big) return;
+  const int node = P.by_size[warp];
+  NodeFit f;
+  fit_obbrss_warp(P.tri, kTriDoubles, P.prim_order + P.node_first[node], P.node_count[node], terms[threadIdx.x >> 5], f);
+  if ((threadIdx.x & 31) == 0) store_node_records(P, node, f);
+}
+
+// one thread per node for the rest (by_size[n_big .. n_nodes))
+__global__ void __launch_bounds__(64) refit_small_nodes_kernel(RefitParams P, int n_big) {
+  const int k = n_big + blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= P.n_nodes) return;
+  const int node = P.by_size[k];
+  NodeFit f;
+  fit_obbrss(P.tri, kTriDoubles, P.prim_order + P.node_first[node], P.node_count[node], f);
+  store_node_records(P, node, f);
+}
+
+}  // namespace fclgpu

@@ -108,6 +108,16 @@ int fclgpu_bvh_get(const fclgpu_bvh* bvh, int32_t* first_child, double* axis9, d
                    double* obb_extent3, double* rss_To3, double* rss_l2, double* rss_r,
                    double* tri_verts9);
 
+/* Top-down refit on the host: BVHModel::beginReplaceModel / replaceSubModel / endReplaceModel(
+ * refit = true, bottomup = false) (BVH_model-inl.h:521-620, refitTree_topdown :1064-1076): new vertex
+ * positions (same count), same tree, every BV refitted over its stored primitive range. */
+int fclgpu_bvh_refit_topdown(fclgpu_bvh* bvh, const double* vertices, int32_t num_vertices);
+int32_t fclgpu_bvh_num_vertices(const fclgpu_bvh* bvh);
+/* BVNodeBase::first_primitive / num_primitives per node, BVHModel::primitive_indices, tri_indices
+ * (any pointer may be NULL). */
+int fclgpu_bvh_get_partition(const fclgpu_bvh* bvh, int32_t* first_primitive, int32_t* num_primitives,
+                             int32_t* primitive_indices, int32_t* tri_indices3);
+
 /* ---------------------------------------------------------------------------------------
  * Upload: flattens BVNode<OBBRSS<double>>[] (include/fcl/geometry/bvh/BV_node.h:50-72,
  * BVH_model.h:160-203) + triangles into device records ("HBM layout").
@@ -123,6 +133,19 @@ int fclgpu_model_create_obbrss(int device, int32_t n_nodes, const int32_t* first
                                int32_t n_tris, const double* tri_verts9, fclgpu_model** out);
 int fclgpu_model_from_bvh(int device, const fclgpu_bvh* bvh, fclgpu_model** out);
 int fclgpu_model_destroy(fclgpu_model* m);
+/* Refit topology for a model created from raw node arrays (fclgpu_model_from_bvh sets it itself). */
+int fclgpu_model_set_partition(fclgpu_model* m, int32_t num_vertices, const int32_t* tri_indices3,
+                               const int32_t* first_primitive, const int32_t* num_primitives,
+                               const int32_t* primitive_indices);
+/* On-device top-down refit: same semantics as fclgpu_bvh_refit_topdown, but the
+ * node records in HBM are recomputed by a kernel (one thread per node, sums in the reference's
+ * order => bit-identical BVs).  `vertices` (num_vertices x 3) is a device pointer when
+ * vertices_on_device != 0, else a host pointer.  Asynchronous on `stream`. */
+int fclgpu_model_refit_topdown(fclgpu_model* m, const double* vertices, int32_t num_vertices,
+                               int32_t vertices_on_device, void* stream);
+/* Copies the FP64 node records back to the host (testing / inspection; any pointer may be NULL). */
+int fclgpu_model_download(const fclgpu_model* m, double* axis9, double* obb_To3, double* obb_extent3,
+                          double* rss_To3, double* rss_l2, double* rss_r, double* tri_verts9);
 int32_t fclgpu_model_num_nodes(const fclgpu_model* m);
 int32_t fclgpu_model_num_tris(const fclgpu_model* m);
 int fclgpu_model_device(const fclgpu_model* m);

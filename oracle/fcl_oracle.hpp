@@ -64,6 +64,8 @@ struct Model {
   std::vector<Vec3> verts;
   std::vector<Tri> tris;
   std::vector<Node> nodes;
+  std::vector<unsigned> prim;  // BVHModel::primitive_indices after the build (node i owns prim[first_primitive .. +num_primitives))
+  SplitMethod split = SPLIT_MEAN;
 };
 
 // rigid pose: p_world = R * p + t
@@ -92,6 +94,10 @@ struct DistanceOut {
 bool load_obj(const std::string& path, std::vector<Vec3>& pts, std::vector<Tri>& tris);
 void build_model(Model& m, const std::vector<Vec3>& pts, const std::vector<Tri>& tris,
                  SplitMethod split = SPLIT_MEAN);
+
+// endReplaceModel(refit=true, bottomup=false): new vertex positions, same topology; every node is
+// refitted over its stored primitive range (BVH_model-inl.h:594-620, refitTree_topdown :1064-1076)
+void refit_topdown(Model& m, const std::vector<Vec3>& new_verts);
 
 // ---- BV / leaf kernels -------------------------------------------------------
 bool obb_disjoint(const Mat3& B, const Vec3& T, const Vec3& a, const Vec3& b);

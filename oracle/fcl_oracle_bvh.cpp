@@ -378,6 +378,18 @@ void build_model(Model& m, const std::vector<Vec3>& pts, const std::vector<Tri>&
   b.prim.resize(nt);
   for (int i = 0; i < nt; ++i) b.prim[i] = i;
   b.recurse(0, 0, nt);
+  m.prim = b.prim;
+  m.split = split;
+}
+
+// refitTree_topdown — BVH_model-inl.h:1064-1076 (prev_vertices == nullptr after beginReplaceModel, :530-534)
+void refit_topdown(Model& m, const std::vector<Vec3>& new_verts) {
+  m.verts = new_verts;
+  Builder b{m, m.split, m.prim, (int)m.nodes.size()};
+  for (size_t i = 0; i < m.nodes.size(); ++i) {
+    Node& nd = m.nodes[i];
+    b.fit(b.prim.data() + nd.first_primitive, nd.num_primitives, nd);
+  }
 }
 
 // -----------------------------------------------------------------------------

@@ -87,6 +87,25 @@ void* orc_model_from_arrays(const double* verts, int nv, const int32_t* tris, in
 
 void orc_model_free(void* h) { delete (Model*)h; }
 
+// endReplaceModel(refit=true, bottomup=false) with nv new vertex positions
+int orc_model_refit_topdown(void* h, const double* verts, int nv) {
+  Model* m = (Model*)h;
+  if ((size_t)nv != m->verts.size()) return -7;  // BVH_ERR_INCORRECT_DATA (BVH_model-inl.h:602-606)
+  std::vector<Vec3> pts(nv);
+  for (int i = 0; i < nv; ++i) pts[i] = Vec3{{verts[3 * i], verts[3 * i + 1], verts[3 * i + 2]}};
+  refit_topdown(*m, pts);
+  return 0;
+}
+
+void orc_model_partition(void* h, int32_t* first_primitive, int32_t* num_primitives, int32_t* primitive_indices) {
+  Model* m = (Model*)h;
+  for (size_t i = 0; i < m->nodes.size(); ++i) {
+    first_primitive[i] = m->nodes[i].first_primitive;
+    num_primitives[i] = m->nodes[i].num_primitives;
+  }
+  for (size_t i = 0; i < m->prim.size(); ++i) primitive_indices[i] = (int32_t)m->prim[i];
+}
+
 void orc_model_counts(void* h, int* nv, int* nt, int* nn) {
   Model* m = (Model*)h;
   *nv = (int)m->verts.size();

@@ -46,6 +46,9 @@ def lib():
         L.orc_model_from_arrays.restype = vp
         L.orc_model_from_arrays.argtypes = [dp, C.c_int, ip, C.c_int, C.c_int]
         L.orc_model_free.argtypes = [vp]
+        L.orc_model_refit_topdown.restype = C.c_int
+        L.orc_model_refit_topdown.argtypes = [vp, dp, C.c_int]
+        L.orc_model_partition.argtypes = [vp, ip, ip, ip]
         L.orc_model_counts.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.orc_model_get.argtypes = [vp, dp, ip, ip, dp, dp, dp, dp, dp, dp]
         L.orc_collide_batch.restype = vp
@@ -126,6 +129,19 @@ class Model:
                 self.h = None
         except Exception:
             pass
+
+    def refit_topdown(self, new_verts):
+        """endReplaceModel(refit=True, bottomup=False): same topology, every BV refitted."""
+        v = np.ascontiguousarray(new_verts, dtype=np.float64).reshape(-1, 3)
+        rc = lib().orc_model_refit_topdown(self.h, _dp(v), len(v))
+        if rc == 0:
+            self.verts = v
+        return rc
+
+    def partition(self):
+        fp, npr, pi = np.empty(self.num_bvs, np.int32), np.empty(self.num_bvs, np.int32), np.empty(self.num_tris, np.int32)
+        lib().orc_model_partition(self.h, _ip(fp), _ip(npr), _ip(pi))
+        return fp, npr, pi
 
     def arrays(self):
         """Flattened node tree: dict of numpy arrays (axis row-major 9 per node)."""

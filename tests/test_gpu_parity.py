@@ -299,3 +299,65 @@ def test_collision_object_overloads(models, oracle):
         dres = F.DistanceResult()
         d = F.distance(o1, o2, F.DistanceRequest(True), dres)
         assert d == oracle.distance_batch(oenv, orob, P[i:i + 1], None, True)["min_distance"][0]
+
+
+def test_device_refit_topdown_is_bit_exact(oracle, env_rob_npz):
+    """on-device top-down refit.  After moving the vertices the BV records in HBM
+    (recomputed by refit_nodes_kernel) equal the oracle's refitted BVs bit for bit, and queries on the
+    refitted model match the oracle's."""
+    (ev, et), (rv, rt) = env_rob_npz
+    rng = np.random.default_rng(3)
+    env, rob = F.BVHModel.from_arrays(ev, et), F.BVHModel.from_arrays(rv, rt)
+    oenv, orob = oracle.Model(ev, et), oracle.Model(rv, rt)
+    env.device_model()
+    rob.device_model()  # upload before the refit so that the device copies are refitted by the kernel
+    ev2 = ev * (1.0 + 0.02 * np.sin(ev[:, [1, 2, 0]] / 500.0))  # smooth deformation
+    rv2 = rv + rng.normal(0, 10.0, size=rv.shape)
+    for m, o, v2 in ((env, oenv, ev2), (rob, orob, rv2)):
+        assert m.beginReplaceModel() == F.BVH_OK and m.replaceSubModel(v2) == F.BVH_OK
+        assert m.endReplaceModel(True, False) == F.BVH_OK
+        assert o.refit_topdown(v2) == 0
+        dev, ref = m.download_device_arrays(), o.arrays()
+        for k in ("axis", "obb_To", "obb_ext", "rss_To", "rss_l", "rss_r"):
+            assert dev[k].tobytes() == ref[k].tobytes(), k
+        host = m.node_arrays()
+        assert dev["tri_verts"].tobytes() == host["tri_verts"].tobytes()
+    P = random_poses(5000, seed=19)
+    got = F.collide_batch(env, P, rob, None, F.CollisionRequest(50, True), contact_capacity=50 * len(P))
+    refc = oracle.collide_batch(oenv, orob, P, None, 50, True, nthreads=8)
+    assert np.array_equal(got.num_contacts, refc["counts"]) and got.contacts.tobytes() == refc["contacts"].tobytes()
+    gd = F.distance_batch(env, P, rob, None, F.DistanceRequest(True))
+    rd = oracle.distance_batch(oenv, orob, P, None, True, 2, nthreads=8)
+    assert np.array_equal(gd.min_distance, rd["min_distance"])
+    # device-resident vertices (no host round trip)
+    import torch
+
+    rv3 = rv2 + 5.0
+    rob.refit_device(torch.from_numpy(rv3).cuda())
+    F.sync_status()
+    assert orob.refit_topdown(rv3) == 0
+    dev, ref = rob.download_device_arrays(), orob.arrays()
+    for k in ("axis", "obb_To", "obb_ext", "rss_To", "rss_l", "rss_r"):
+        assert dev[k].tobytes() == ref[k].tobytes(), k
+
+
+def test_device_refit_thread_and_warp_variants_agree(oracle):
+    """Both refit kernels (one thread per node / warp-cooperative for large nodes) give the oracle's BVs,
+    also on a mesh large enough for deep trees and many large nodes."""
+    import torch
+    from tests.meshes import heightfield
+
+    v, t = heightfield(60, size=10.0, seed=3, amp=0.6)  # 7200 triangles
+    m, o = F.BVHModel.from_arrays(v, t), oracle.Model(v, t)
+    m.device_model()
+    rng = np.random.default_rng(8)
+    for variant in (1, 0):
+        _capi.set_option("refit_warp", variant)
+        v2 = v + rng.normal(0, 0.05, size=v.shape)
+        m.refit_device(torch.from_numpy(v2).cuda())
+        F.sync_status()
+        assert o.refit_topdown(v2) == 0
+        dev, ref = m.download_device_arrays(), o.arrays()
+        for k in ("axis", "obb_To", "obb_ext", "rss_To", "rss_l", "rss_r"):
+            assert dev[k].tobytes() == ref[k].tobytes(), (variant, k)
+    _capi.set_option("refit_warp", 1)

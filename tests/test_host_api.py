@@ -123,3 +123,36 @@ def test_transform_conversion():
     M[:3, 3] = rng.normal(size=3)
     tf = F.Transform3.from_matrix4_colmajor(M.T.reshape(16))  # column-major storage
     assert np.array_equal(tf.R, M[:3, :3]) and np.array_equal(tf.t, M[:3, 3])
+
+
+def test_replace_model_topdown_refit_matches_oracle(oracle, env_rob_npz, capfd):
+    """beginReplaceModel / replaceSubModel / endReplaceModel(refit=True, bottomup=False)
+    (BVH_model-inl.h:521-620, refitTree_topdown :1064-1076): host refit is bit-identical to the oracle's."""
+    (ev, et), (rv, rt) = env_rob_npz
+    rng = np.random.default_rng(2)
+    for v, t in ((rv, rt), random_soup(400, 9), uv_sphere(5.0, 12, 12)):
+        v = np.asarray(v, dtype=np.float64)
+        m, o = F.BVHModel.from_arrays(v, t), oracle.Model(v, t)
+        assert [a.tobytes() for a in m.partition()] == [a.tobytes() for a in o.partition()]
+        v2 = v + rng.normal(0, 0.05 * np.abs(v).max(), size=v.shape)
+        assert m.beginReplaceModel() == F.BVH_OK
+        assert m.replaceSubModel(v2[: len(v2) // 2]) == F.BVH_OK
+        assert m.endReplaceModel(True, False) == F.BVH_ERR_INCORRECT_DATA  # vertex count mismatch (:602-606)
+        assert m.replaceSubModel(v2[len(v2) // 2:]) == F.BVH_OK
+        assert m.endReplaceModel(True, True) == F.BVH_ERR_UNSUPPORTED_FUNCTION  # bottom-up refit: not on this path
+        assert m.endReplaceModel(True, False) == F.BVH_OK
+        assert o.refit_topdown(v2) == 0
+        got, ref = m.node_arrays(), o.arrays()
+        for k in ref:
+            assert got[k].tobytes() == ref[k].tobytes(), k
+        # refit=False rebuilds the tree: equal to a fresh build on the new vertices
+        assert m.beginReplaceModel() == F.BVH_OK and m.replaceSubModel(v2) == F.BVH_OK
+        assert m.endReplaceModel(False) == F.BVH_OK
+        fresh = oracle.Model(v2, t).arrays()
+        got = m.node_arrays()
+        for k in fresh:
+            assert got[k].tobytes() == fresh[k].tobytes(), k
+    fresh = F.BVHModel()
+    assert fresh.beginReplaceModel() == F.BVH_ERR_BUILD_EMPTY_PREVIOUS_FRAME
+    assert fresh.replaceVertex([0, 0, 0]) == F.BVH_ERR_BUILD_OUT_OF_SEQUENCE
+    assert "no previous frame" in capfd.readouterr().err
