@@ -102,9 +102,12 @@ class BVHModel:
     Build protocol and return codes as the reference: beginModel() -> addSubModel()/
     addTriangle()* -> endModel() (BVH_model-inl.h:207-253, 256-446, 450-517).  endModel()
     builds the OBBRSS tree on the host; the flattened tree is uploaded to a GPU on first use.
+    With build_on_device=True endModel() only records the mesh and the tree is built by kernels on
+    the GPU that first uses the model (same tree, bit for bit; mean / BV-centre split rules).
     """
 
-    def __init__(self, split_method=SPLIT_METHOD_MEAN):
+    def __init__(self, split_method=SPLIT_METHOD_MEAN, build_on_device=False):
+        self.build_on_device = bool(build_on_device)
         self.split_method = split_method
         self.build_state = BVH_BUILD_STATE_EMPTY
         self._verts = []
@@ -181,6 +184,13 @@ class BVHModel:
             return BVH_ERR_UNSUPPORTED_FUNCTION
         self.vertices = np.ascontiguousarray(np.concatenate(self._verts), dtype=np.float64)
         self.tri_indices = np.ascontiguousarray(np.concatenate(self._tris), dtype=np.int32)
+        if self.build_on_device:
+            if self.split_method not in (SPLIT_METHOD_MEAN, SPLIT_METHOD_BV_CENTER):
+                return BVH_ERR_UNSUPPORTED_FUNCTION
+            if self.tri_indices.min() < 0 or self.tri_indices.max() >= self.num_vertices:
+                return BVH_ERR_INCORRECT_DATA
+            self.build_state = BVH_BUILD_STATE_PROCESSED
+            return BVH_OK
         h = C.c_void_p()
         rc = _capi.lib().fclgpu_bvh_build_obbrss(addr(self.vertices), self.num_vertices, addr(self.tri_indices),
                                                  self.num_tris, self.split_method, C.byref(h))
@@ -242,20 +252,22 @@ class BVHModel:
         self.vertices = new_v
         L = _capi.lib()
         if refit:
-            rc = L.fclgpu_bvh_refit_topdown(self._bvh, addr(new_v), self.num_vertices)
-            if rc != 0:
-                return rc
+            if self._bvh is not None:
+                rc = L.fclgpu_bvh_refit_topdown(self._bvh, addr(new_v), self.num_vertices)
+                if rc != 0:
+                    return rc
             for dev, h in self._dev.items():
                 check(L.fclgpu_model_refit_topdown(h, addr(new_v), self.num_vertices, 0, None))
                 check(L.fclgpu_sync_status(int(dev), None))
         else:
             self._release()
-            h = C.c_void_p()
-            rc = L.fclgpu_bvh_build_obbrss(addr(self.vertices), self.num_vertices, addr(self.tri_indices), self.num_tris,
-                                           self.split_method, C.byref(h))
-            if rc != 0:
-                return rc
-            self._bvh = h
+            if not self.build_on_device:
+                h = C.c_void_p()
+                rc = L.fclgpu_bvh_build_obbrss(addr(self.vertices), self.num_vertices, addr(self.tri_indices),
+                                               self.num_tris, self.split_method, C.byref(h))
+                if rc != 0:
+                    return rc
+                self._bvh = h
         self.build_state = BVH_BUILD_STATE_PROCESSED
         return BVH_OK
 
@@ -281,12 +293,15 @@ class BVHModel:
     def partition(self):
         n, nt = self.getNumBVs(), self.num_tris
         fp, npr, pi = np.empty(n, np.int32), np.empty(n, np.int32), np.empty(nt, np.int32)
-        check(_capi.lib().fclgpu_bvh_get_partition(self._bvh, addr(fp), addr(npr), addr(pi), None))
+        if self._bvh is None:
+            check(_capi.lib().fclgpu_model_get_topology(self.device_model(), None, addr(fp), addr(npr), addr(pi)))
+        else:
+            check(_capi.lib().fclgpu_bvh_get_partition(self._bvh, addr(fp), addr(npr), addr(pi), None))
         return fp, npr, pi
 
     @classmethod
-    def from_arrays(cls, verts, tris, split_method=SPLIT_METHOD_MEAN):
-        m = cls(split_method)
+    def from_arrays(cls, verts, tris, split_method=SPLIT_METHOD_MEAN, build_on_device=False):
+        m = cls(split_method, build_on_device)
         m.beginModel()
         m.addSubModel(verts, tris)
         rc = m.endModel()
@@ -295,11 +310,18 @@ class BVHModel:
         return m
 
     def getNumBVs(self):
-        return 0 if self._bvh is None else int(_capi.lib().fclgpu_bvh_num_nodes(self._bvh))
+        if self._bvh is None:
+            return 2 * self.num_tris - 1 if (self.build_on_device and self.build_state == BVH_BUILD_STATE_PROCESSED) else 0
+        return int(_capi.lib().fclgpu_bvh_num_nodes(self._bvh))
 
     def node_arrays(self):
         """The flattened node tree as numpy arrays (what the upload step sends to HBM)."""
         n, nt = self.getNumBVs(), self.num_tris
+        if self._bvh is None:  # built on the device: read the records back
+            out = self.download_device_arrays()
+            out["first_child"] = np.empty(n, np.int32)
+            check(_capi.lib().fclgpu_model_get_topology(self.device_model(), addr(out["first_child"]), None, None, None))
+            return out
         out = dict(first_child=np.empty(n, np.int32), axis=np.empty((n, 9)), obb_To=np.empty((n, 3)),
                    obb_ext=np.empty((n, 3)), rss_To=np.empty((n, 3)), rss_l=np.empty((n, 2)), rss_r=np.empty(n),
                    tri_verts=np.empty((nt, 9)))
@@ -317,7 +339,12 @@ class BVHModel:
         h = self._dev.get(device)
         if h is None:
             h = C.c_void_p()
-            check(_capi.lib().fclgpu_model_from_bvh(int(device), self._bvh, C.byref(h)))
+            if self._bvh is None:
+                check(_capi.lib().fclgpu_model_build_obbrss(int(device), addr(self.vertices), self.num_vertices,
+                                                            addr(self.tri_indices), self.num_tris, self.split_method,
+                                                            C.byref(h)))
+            else:
+                check(_capi.lib().fclgpu_model_from_bvh(int(device), self._bvh, C.byref(h)))
             self._dev[device] = h
         return h
 

@@ -27,6 +27,8 @@ namespace fclgpu {
 struct NodeFit {
   double axis[9];  // row-major, columns = box axes
   double obb_To[3], obb_ext[3], rss_To[3], rss_l[2], rss_r;
+  double vsum[3];  // sum over the node's triangles of ((p1 + p2) + p3), in primitive order: the covariance's S1
+                   // and, term for term, the centroid sum of the mean split rule (BV_splitter-inl.h:578-589)
 };
 
 // symmetric 3x3 eigen-decomposition, cyclic Jacobi; v[r][k]: k-th eigenvector in column k
@@ -108,6 +110,9 @@ __host__ __device__ inline void fit_obbrss(const double* tv, int tri_stride, con
     S2[5] += (p1[1] * p1[2] + p2[1] * p2[2] + p3[1] * p3[2]);
   }
   const int np = 3 * n;
+  f.vsum[0] = S1[0];
+  f.vsum[1] = S1[1];
+  f.vsum[2] = S1[2];
   double M[3][3];
   M[0][0] = S2[0] - S1[0] * S1[0] / np;
   M[1][1] = S2[1] - S1[1] * S1[1] / np;

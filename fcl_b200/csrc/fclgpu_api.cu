@@ -47,6 +47,12 @@ int fail(int code, const char* fmt, ...) {
                   "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
 
+inline int cuda_status(cudaError_t e) {
+  return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver
+             ? FCLGPU_ERR_NO_DEVICE
+             : (e == cudaErrorMemoryAllocation ? FCLGPU_ERR_MODEL_OUT_OF_MEMORY : FCLGPU_ERR_CUDA);
+}
+
 // options
 std::mutex g_opt_mu;
 std::map<std::string, long long> g_opts = {
@@ -357,6 +363,137 @@ extern "C" int fclgpu_model_refit_topdown(fclgpu_model* m, const double* vertice
     g_launches += 2;
   }
   CUDA_TRY(cudaGetLastError());
+  return FCLGPU_OK;
+}
+
+// On-device build: BVHModel::endModel() (BVH_model-inl.h:450-517) for the mean / BV-centre split rules,
+// level by level (refit.cuh).  Produces the same tree, node numbering, primitive order and volumes as
+// fclgpu_bvh_build_obbrss + fclgpu_model_from_bvh.
+extern "C" int fclgpu_model_build_obbrss(int device, const double* vertices, int32_t num_vertices,
+                                         const int32_t* triangles, int32_t num_tris, int32_t split_method,
+                                         fclgpu_model** out) {
+  if (!out) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  if (num_tris <= 0 || num_vertices <= 0) return fail(FCLGPU_ERR_BUILD_EMPTY_MODEL, "empty model");
+  if (!vertices || !triangles) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL vertices/triangles");
+  if (split_method != FCLGPU_SPLIT_METHOD_MEAN && split_method != FCLGPU_SPLIT_METHOD_BV_CENTER)
+    return fail(FCLGPU_ERR_UNSUPPORTED_FUNCTION, "the on-device build supports the mean and BV-centre split rules");
+  for (int64_t i = 0; i < 3 * (int64_t)num_tris; ++i)
+    if (triangles[i] < 0 || triangles[i] >= num_vertices) return fail(FCLGPU_ERR_INCORRECT_DATA, "triangle index out of range");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(FCLGPU_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "device %d out of range", device);
+  CUDA_TRY(cudaSetDevice(device));
+  const int nt = num_tris, nn = 2 * nt - 1;
+
+  fclgpu_model* m = new fclgpu_model{};
+  m->device = device;
+  m->num_vertices = num_vertices;
+  uint8_t* flag = nullptr;
+  uint32_t* queue = nullptr;
+  BuildNode* lists = nullptr;
+  int32_t* next_count = nullptr;
+  auto cleanup = [&](int rc) {
+    cudaFree(flag);
+    cudaFree(queue);
+    cudaFree(lists);
+    cudaFree(next_count);
+    if (rc) fclgpu_model_destroy(m);
+    return rc;
+  };
+#define BUILD_TRY(expr)                                                                    \
+  do {                                                                                     \
+    cudaError_t e_ = (expr);                                                               \
+    if (e_ != cudaSuccess) return cleanup(fail(cuda_status(e_), "%s: %s", #expr, cudaGetErrorString(e_))); \
+  } while (0)
+  BUILD_TRY(cudaMalloc((void**)&m->obb, (size_t)nn * kNodeDoubles * sizeof(double)));
+  BUILD_TRY(cudaMalloc((void**)&m->rss, (size_t)nn * kNodeDoubles * sizeof(double)));
+  BUILD_TRY(cudaMalloc((void**)&m->tri, (size_t)nt * kTriDoubles * sizeof(double)));
+  BUILD_TRY(cudaMemset(m->tri, 0, (size_t)nt * kTriDoubles * sizeof(double)));
+  BUILD_TRY(cudaMalloc((void**)&m->rss32, sizeof(RssRec32) * nn));
+  BUILD_TRY(cudaMalloc((void**)&m->obb32, sizeof(ObbRec32) * nn));
+  BUILD_TRY(cudaMalloc((void**)&m->topo, sizeof(double2) * nn));
+  BUILD_TRY(cudaMemset(m->topo, 0, sizeof(double2) * nn));
+  BUILD_TRY(cudaMalloc((void**)&m->fc, sizeof(int32_t) * nn));
+  BUILD_TRY(cudaMalloc((void**)&m->tri_index, sizeof(int32_t) * 3 * (size_t)nt));
+  BUILD_TRY(cudaMalloc((void**)&m->node_first, sizeof(int32_t) * nn));
+  BUILD_TRY(cudaMalloc((void**)&m->node_count, sizeof(int32_t) * nn));
+  BUILD_TRY(cudaMalloc((void**)&m->by_size, sizeof(int32_t) * nn));
+  BUILD_TRY(cudaMalloc((void**)&m->prim_order, sizeof(uint32_t) * nt));
+  BUILD_TRY(cudaMalloc((void**)&m->vert_stage, 3 * (size_t)num_vertices * sizeof(double)));
+  BUILD_TRY(cudaMalloc((void**)&flag, nt));
+  BUILD_TRY(cudaMalloc((void**)&queue, sizeof(uint32_t) * 2 * (size_t)nt));
+  BUILD_TRY(cudaMalloc((void**)&lists, sizeof(BuildNode) * 2 * (size_t)nt));
+  BUILD_TRY(cudaMalloc((void**)&next_count, sizeof(int32_t)));
+  BUILD_TRY(cudaMemcpy(m->vert_stage, vertices, 3 * (size_t)num_vertices * sizeof(double), cudaMemcpyHostToDevice));
+  BUILD_TRY(cudaMemcpy(m->tri_index, triangles, sizeof(int32_t) * 3 * (size_t)nt, cudaMemcpyHostToDevice));
+
+  BuildParams B{};
+  B.R = RefitParams{m->obb, m->rss, m->tri, m->rss32, m->obb32, m->topo, m->tri_index, m->node_first, m->node_count,
+                    m->prim_order, m->by_size, nn, nt};
+  B.first_child = m->fc;
+  B.node_first = m->node_first;
+  B.node_count = m->node_count;
+  B.prim_order = m->prim_order;
+  B.flag = flag;
+  B.queue = queue;
+  B.next_count = next_count;
+  B.split = split_method;
+  gather_tris_kernel<<<(nt + 255) / 256, 256>>>(B.R, m->vert_stage);
+  iota_kernel<<<(nt + 255) / 256, 256>>>(m->prim_order, nt);
+  g_launches += 2;
+  const BuildNode root{0, 0, nt, 1};
+  BUILD_TRY(cudaMemcpy(lists, &root, sizeof root, cudaMemcpyHostToDevice));
+  int n_level = 1, cur = 0, depth = 0;
+  while (true) {
+    BUILD_TRY(cudaMemset(next_count, 0, sizeof(int32_t)));
+    B.level = lists + (size_t)cur * nt;
+    B.next = lists + (size_t)(cur ^ 1) * nt;
+    B.n_level = n_level;
+    if ((long long)n_level * 12 >= nt)  // average node of the level has <= 12 triangles: lanes take whole nodes
+      build_level_kernel<true><<<(n_level + 127) / 128, 128>>>(B);
+    else
+      build_level_kernel<false><<<(int)(((size_t)n_level * 32 + 127) / 128), 128>>>(B);
+    g_launches++;
+    int32_t n_next = 0;
+    BUILD_TRY(cudaMemcpy(&n_next, next_count, sizeof n_next, cudaMemcpyDeviceToHost));
+    if (n_next == 0) break;
+    if (n_next > nt) return cleanup(fail(FCLGPU_ERR_UNKNOWN, "level overflow in the on-device build"));
+    n_level = n_next;
+    cur ^= 1;
+    ++depth;
+  }
+  BUILD_TRY(cudaGetLastError());
+  // node sizes -> refit schedule
+  std::vector<int32_t> cnt(nn), by_size(nn);
+  BUILD_TRY(cudaMemcpy(cnt.data(), m->node_count, sizeof(int32_t) * nn, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < nn; ++i) by_size[i] = i;
+  std::stable_sort(by_size.begin(), by_size.end(), [&](int a, int b) { return cnt[a] > cnt[b]; });
+  int n_big = 0;
+  while (n_big < nn && cnt[by_size[n_big]] > 24) ++n_big;
+  m->n_big = n_big;
+  BUILD_TRY(cudaMemcpy(m->by_size, by_size.data(), sizeof(int32_t) * nn, cudaMemcpyHostToDevice));
+  m->depth = depth;
+  m->d = DeviceModel{m->obb, m->rss, m->fc, m->tri, m->rss32, m->obb32, m->topo, nn, nt};
+#undef BUILD_TRY
+  *out = m;
+  return cleanup(FCLGPU_OK);
+}
+
+// topology of a device model (first_child per node, and the build partition when present)
+extern "C" int fclgpu_model_get_topology(const fclgpu_model* m, int32_t* first_child, int32_t* first_primitive,
+                                         int32_t* num_primitives, int32_t* primitive_indices) {
+  if (!m) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL model");
+  CUDA_TRY(cudaSetDevice(m->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  const int nn = m->d.n_nodes, nt = m->d.n_tris;
+  if (first_child) CUDA_TRY(cudaMemcpy(first_child, m->fc, sizeof(int32_t) * nn, cudaMemcpyDeviceToHost));
+  if ((first_primitive || num_primitives || primitive_indices) && !m->prim_order)
+    return fail(FCLGPU_ERR_UNSUPPORTED_FUNCTION, "model has no partition");
+  if (first_primitive) CUDA_TRY(cudaMemcpy(first_primitive, m->node_first, sizeof(int32_t) * nn, cudaMemcpyDeviceToHost));
+  if (num_primitives) CUDA_TRY(cudaMemcpy(num_primitives, m->node_count, sizeof(int32_t) * nn, cudaMemcpyDeviceToHost));
+  if (primitive_indices) CUDA_TRY(cudaMemcpy(primitive_indices, m->prim_order, sizeof(int32_t) * nt, cudaMemcpyDeviceToHost));
   return FCLGPU_OK;
 }
 

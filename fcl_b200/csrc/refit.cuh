@@ -159,6 +159,9 @@ __device__ inline void fit_obbrss_warp(const double* __restrict__ tv, int tri_st
 #pragma unroll
   for (int k = 0; k < 6; ++k) S2[k] = __shfl_sync(0xffffffffu, acc, 3 + k);
   const int np = 3 * n;
+  f.vsum[0] = S1[0];
+  f.vsum[1] = S1[1];
+  f.vsum[2] = S1[2];
   double M[3][3];
   M[0][0] = S2[0] - S1[0] * S1[0] / np;
   M[1][1] = S2[1] - S1[1] * S1[1] / np;
@@ -366,6 +369,201 @@ __global__ void __launch_bounds__(64) refit_small_nodes_kernel(RefitParams P, in
   NodeFit f;
   fit_obbrss(P.tri, kTriDoubles, P.prim_order + P.node_first[node], P.node_count[node], f);
   store_node_records(P, node, f);
+}
+
+}  // namespace fclgpu
+
+namespace fclgpu {
+
+// ---------------------------------------------------------------------------------------
+// On-device top-down BUILD (BVHModel::buildTree / recursiveBuildTree, BVH_model-inl.h:833-938)
+// for the mean and BV-centre split rules, level by level.  Per node of the current level:
+//   1. fit (same routines as the refit);
+//   2. split threshold: mean rule = (vsum . axis0) / (3 n) with vsum from the fit (the rule sums
+//      the same terms in the same order, BV_splitter-inl.h:578-589); BV-centre rule = obb.To[0];
+//   3. side flag of every primitive (parallel): !(axis0 . centroid > threshold);
+//   4. the reference's in-place swap partition (:888-926), reproduced exactly: elements going left
+//      keep their order; the elements staying right behave as a queue that is rotated by one each
+//      time a left element arrives.  One lane replays that queue on a scratch array;
+//   5. children: ids follow the reference's pre-order pair allocation -- a node whose pair is
+//      (c, c+1) gives its left child the pair c+2 and its right child the pair c + 2*n_left.
+// ---------------------------------------------------------------------------------------
+struct BuildNode {
+  int32_t id, first, count, pair;  // pair = first_child id to assign if the node is internal
+};
+
+struct BuildParams {
+  RefitParams R;          // record arrays to fill (obb, rss, tri, rss32, obb32, topo, prim_order ...)
+  int32_t* first_child;   // per node
+  int32_t* node_first;    // per node (writable aliases of R.node_first / R.node_count)
+  int32_t* node_count;
+  uint32_t* prim_order;   // writable alias of R.prim_order
+  uint8_t* flag;          // per primitive slot: 1 = goes left
+  uint32_t* queue;        // 2 slots per primitive slot
+  const BuildNode* level; // nodes of this level
+  BuildNode* next;        // nodes of the next level
+  int32_t* next_count;
+  int32_t n_level;
+  int32_t split;          // FCLGPU_SPLIT_METHOD_MEAN or _BV_CENTER
+};
+
+__device__ inline void build_finish_node(const BuildParams& B, const BuildNode nd, const NodeFit& f, int lane, bool warp_mode) {
+  const RefitParams& P = B.R;
+  uint32_t* idx = B.prim_order + nd.first;
+  const int n = nd.count;
+  if (!warp_mode || lane == 0) {
+    store_node_records(P, nd.id, f);
+    B.node_first[nd.id] = nd.first;
+    B.node_count[nd.id] = n;
+  }
+  if (n == 1) {
+    if (!warp_mode || lane == 0) {
+      const int fc = -((int)idx[0] + 1);
+      B.first_child[nd.id] = fc;
+      double2 t = P.topo[nd.id];
+      long long bits = (long long)(unsigned)fc;
+      t.x = __longlong_as_double(bits);
+      P.topo[nd.id] = t;
+    }
+    return;
+  }
+  const double sv0 = f.axis[0], sv1 = f.axis[3], sv2 = f.axis[6];
+  const double thr = (B.split == FCLGPU_SPLIT_METHOD_BV_CENTER)
+                         ? f.obb_To[0]
+                         : (f.vsum[0] * sv0 + f.vsum[1] * sv1 + f.vsum[2] * sv2) / (3 * n);
+  // side flags
+  for (int i = warp_mode ? lane : 0; i < n; i += warp_mode ? 32 : 1) {
+    const double* p1 = P.tri + (size_t)idx[i] * kTriDoubles;
+    const double* p2 = p1 + 3;
+    const double* p3 = p1 + 6;
+    const double cx = ((p1[0] + p2[0]) + p3[0]) / 3.0, cy = ((p1[1] + p2[1]) + p3[1]) / 3.0, cz = ((p1[2] + p2[2]) + p3[2]) / 3.0;
+    B.flag[nd.first + i] = (((sv0 * cx + sv1 * cy) + sv2 * cz) > thr) ? 0 : 1;
+  }
+  int c1 = 0;
+  if (warp_mode) {
+    // Parallel form of the replay.  Let i0 be the first right element; number the operations from there
+    // (time 1 = i0).  Every operation enqueues exactly one item (a push, or the re-queue of the served head)
+    // and, the queue being FIFO, the j-th rotation serves the item enqueued at time j.  With J rotations in
+    // total the final queue holds the items enqueued at times J+1..T, in that order; an item enqueued by a
+    // rotation is the item of an earlier time, so each output follows a chain of strictly decreasing times
+    // until it reaches a push.  Chains of different outputs are disjoint (total work <= T).
+    __syncwarp();
+    uint32_t* old = B.queue + 2 * (size_t)nd.first;  // copy of the incoming order
+    uint32_t* lrank = old + n;                        // inclusive count of left flags
+    const uint8_t* fl = B.flag + nd.first;
+    int run = 0, i0 = n;
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + lane;
+      const bool in = i < n;
+      const bool left = in && fl[i];
+      if (in) old[i] = idx[i];
+      const unsigned m = __ballot_sync(0xffffffffu, left);
+      if (in) lrank[i] = run + __popc(m & (0xffffffffu >> (31 - lane)));
+      if (i0 == n) {
+        const unsigned rm = __ballot_sync(0xffffffffu, in && !left);
+        if (rm) i0 = base + __ffs(rm) - 1;
+      }
+      run += __popc(m);
+    }
+    c1 = run;
+    __syncwarp();
+    if (c1 != 0 && c1 != n) {
+      const int J = c1 - i0, T = n - i0;
+      for (int i = lane; i < n; i += 32)
+        if (fl[i]) idx[lrank[i] - 1] = old[i];
+      for (int k = J + 1 + lane; k <= T; k += 32) {
+        int i = i0 + k - 1;
+        while (fl[i]) i = i0 + ((int)lrank[i] - i0) - 1;  // rotation number j -> item of time j
+        idx[c1 + (k - J - 1)] = old[i];
+      }
+    } else {
+      c1 = n / 2;  // degenerate split: the reference's loop leaves the order untouched
+    }
+    __syncwarp();
+  } else {
+    // replay the swap partition: left elements in order, right elements through the rotating queue
+    uint32_t* Q = B.queue + 2 * (size_t)nd.first;
+    int head = 0, tail = 0;
+    for (int i = 0; i < n; ++i) {
+      const uint32_t x = idx[i];
+      if (B.flag[nd.first + i]) {
+        if (tail > head) Q[tail++] = Q[head++];  // the oldest right element jumps behind the block
+        idx[c1++] = x;                           // c1 <= i: slot already consumed
+      } else {
+        Q[tail++] = x;
+      }
+    }
+    if (c1 != 0 && c1 != n)
+      for (int k = 0; k < n - c1; ++k) idx[c1 + k] = Q[head + k];
+    else {
+      // degenerate split: the reference's loop leaves the order untouched (self swaps / no swaps)
+      if (c1 == 0)
+        for (int k = 0; k < n; ++k) idx[k] = Q[head + k];
+      c1 = n / 2;
+    }
+  }
+  if (!warp_mode || lane == 0) {
+    B.first_child[nd.id] = nd.pair;
+    double2 t = P.topo[nd.id];
+    long long bits = (long long)(unsigned)nd.pair;
+    t.x = __longlong_as_double(bits);
+    P.topo[nd.id] = t;
+    const int slot = atomicAdd(B.next_count, 2);
+    B.next[slot] = BuildNode{nd.pair, nd.first, c1, nd.pair + 2};
+    B.next[slot + 1] = BuildNode{nd.pair + 1, nd.first + c1, n - c1, nd.pair + 2 * c1};
+  }
+}
+
+// kGrouped = false: one warp per node of the level (upper levels: few, large nodes).
+// kGrouped = true: a warp takes 32 consecutive nodes; nodes of <= 24 triangles are done one per lane,
+// the larger ones among the 32 afterwards by the whole warp, one at a time (lower levels: many small nodes).
+template <bool kGrouped>
+__global__ void __launch_bounds__(128) build_level_kernel(BuildParams B) {
+  __shared__ double terms[4][32][9];
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  NodeFit f;
+  if (!kGrouped) {
+    if (warp >= B.n_level) return;
+    const BuildNode nd = B.level[warp];
+    if (nd.count > 24) {
+      fit_obbrss_warp(B.R.tri, kTriDoubles, B.prim_order + nd.first, nd.count, terms[threadIdx.x >> 5], f);
+      build_finish_node(B, nd, f, lane, true);
+    } else if (lane == 0) {
+      fit_obbrss(B.R.tri, kTriDoubles, B.prim_order + nd.first, nd.count, f);
+      build_finish_node(B, nd, f, 0, false);
+    }
+  } else {
+    if (warp * 32 >= B.n_level) return;
+    const int k = warp * 32 + lane;
+    const bool valid = k < B.n_level;
+    BuildNode nd{0, 0, 0, 0};
+    if (valid) nd = B.level[k];
+    const bool small = valid && nd.count <= 24;
+    if (small) {
+      fit_obbrss(B.R.tri, kTriDoubles, B.prim_order + nd.first, nd.count, f);
+      build_finish_node(B, nd, f, 0, false);
+    }
+    __syncwarp();
+    unsigned big = __ballot_sync(0xffffffffu, valid && !small);
+    while (big) {
+      const int src = __ffs(big) - 1;
+      big &= big - 1;
+      BuildNode b;
+      b.id = __shfl_sync(0xffffffffu, nd.id, src);
+      b.first = __shfl_sync(0xffffffffu, nd.first, src);
+      b.count = __shfl_sync(0xffffffffu, nd.count, src);
+      b.pair = __shfl_sync(0xffffffffu, nd.pair, src);
+      fit_obbrss_warp(B.R.tri, kTriDoubles, B.prim_order + b.first, b.count, terms[threadIdx.x >> 5], f);
+      build_finish_node(B, b, f, lane, true);
+      __syncwarp();
+    }
+  }
+}
+
+__global__ void iota_kernel(uint32_t* p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (uint32_t)i;
 }
 
 }  // namespace fclgpu

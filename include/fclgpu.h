@@ -132,6 +132,19 @@ int fclgpu_model_create_obbrss(int device, int32_t n_nodes, const int32_t* first
                                const double* rss_To3, const double* rss_l2, const double* rss_r,
                                int32_t n_tris, const double* tri_verts9, fclgpu_model** out);
 int fclgpu_model_from_bvh(int device, const fclgpu_bvh* bvh, fclgpu_model** out);
+/* On-device build: BVHModel::endModel() for BVH_MODEL_TRIANGLES + OBBRSS
+ * (BVH_model-inl.h:450-517, 833-938) executed level by level on the GPU from the host arrays
+ * `vertices` (num_vertices x 3) and `triangles` (num_tris x 3).  Same tree, node numbering,
+ * primitive order and volumes as fclgpu_bvh_build_obbrss + fclgpu_model_from_bvh, bit for bit.
+ * split_method: FCLGPU_SPLIT_METHOD_MEAN or FCLGPU_SPLIT_METHOD_BV_CENTER (the median rule sorts per node;
+ * use the host builder for it -> FCLGPU_ERR_UNSUPPORTED_FUNCTION here). Synchronous. */
+int fclgpu_model_build_obbrss(int device, const double* vertices, int32_t num_vertices,
+                              const int32_t* triangles, int32_t num_tris, int32_t split_method,
+                              fclgpu_model** out);
+/* Topology of a device model: first_child per node and, when the model carries it, the build
+ * partition (BVNodeBase::first_primitive / num_primitives, BVHModel::primitive_indices). Any pointer may be NULL. */
+int fclgpu_model_get_topology(const fclgpu_model* m, int32_t* first_child, int32_t* first_primitive,
+                              int32_t* num_primitives, int32_t* primitive_indices);
 int fclgpu_model_destroy(fclgpu_model* m);
 /* Refit topology for a model created from raw node arrays (fclgpu_model_from_bvh sets it itself). */
 int fclgpu_model_set_partition(fclgpu_model* m, int32_t num_vertices, const int32_t* tri_indices3,

@@ -361,3 +361,60 @@ def test_device_refit_thread_and_warp_variants_agree(oracle):
         for k in ("axis", "obb_To", "obb_ext", "rss_To", "rss_l", "rss_r"):
             assert dev[k].tobytes() == ref[k].tobytes(), (variant, k)
     _capi.set_option("refit_warp", 1)
+
+
+@pytest.mark.parametrize("split", [F.SPLIT_METHOD_MEAN, F.SPLIT_METHOD_BV_CENTER])
+def test_device_build_equals_host_build(oracle, env_rob_npz, split):
+    """SURVEY 8f rank 1: BVHModel::endModel() on the device (level-by-level fit / split / swap-partition replay).
+    Tree, node numbering, primitive order and every BV equal the host builder's and the oracle's bit for bit;
+    queries and a later refit behave like on an uploaded model."""
+    from tests.meshes import heightfield, random_soup, uv_sphere
+
+    meshes = [env_rob_npz[0], env_rob_npz[1], heightfield(60, size=10.0, seed=3, amp=0.6), uv_sphere(1.0, 24, 24),
+              random_soup(3000, seed=5)]
+    one_tri = (np.array([[0.0, 0, 0], [1, 0, 0], [0, 1, 0]]), np.array([[0, 1, 2]], np.int32))
+    coplanar = heightfield(12, size=4.0, seed=1, amp=0.0)  # flat grid: degenerate covariance, many split ties
+    for v, t in meshes + [one_tri, coplanar]:
+        host = F.BVHModel.from_arrays(v, t, split)
+        dev = F.BVHModel.from_arrays(v, t, split, build_on_device=True)
+        assert dev.getNumBVs() == host.getNumBVs()
+        a, b = host.node_arrays(), dev.node_arrays()
+        assert np.array_equal(a["first_child"], b["first_child"])
+        for k in ("axis", "obb_To", "obb_ext", "rss_To", "rss_l", "rss_r", "tri_verts"):
+            assert a[k].tobytes() == b[k].tobytes(), k
+        for x, y in zip(host.partition(), dev.partition()):
+            assert np.array_equal(x, y)
+    (ev, et), (rv, rt) = env_rob_npz[0], env_rob_npz[1]
+    env = F.BVHModel.from_arrays(ev, et, split, build_on_device=True)
+    rob = F.BVHModel.from_arrays(rv, rt, split, build_on_device=True)
+    oenv, orob = oracle.Model(ev, et, split), oracle.Model(rv, rt, split)
+    P = random_poses(4000, seed=23)
+    got = F.collide_batch(env, P, rob, None, F.CollisionRequest(50, True), contact_capacity=50 * len(P))
+    refc = oracle.collide_batch(oenv, orob, P, None, 50, True, nthreads=8)
+    assert np.array_equal(got.num_contacts, refc["counts"]) and got.contacts.tobytes() == refc["contacts"].tobytes()
+    gd = F.distance_batch(env, P, rob, None, F.DistanceRequest(True))
+    rd = oracle.distance_batch(oenv, orob, P, None, True, 2, nthreads=8)
+    assert np.array_equal(gd.min_distance, rd["min_distance"])
+    # refit of a device-built model
+    rv2 = rv * 1.01
+    assert rob.beginReplaceModel() == F.BVH_OK and rob.replaceSubModel(rv2) == F.BVH_OK
+    assert rob.endReplaceModel(True, False) == F.BVH_OK
+    assert orob.refit_topdown(rv2) == 0
+    d, r = rob.download_device_arrays(), orob.arrays()
+    for k in ("axis", "obb_To", "obb_ext", "rss_To", "rss_l", "rss_r"):
+        assert d[k].tobytes() == r[k].tobytes(), k
+
+
+def test_device_build_rejects_what_the_reference_rejects():
+    import ctypes as C
+    from fcl_b200 import _capi
+
+    L = _capi.lib()
+
+    h = C.c_void_p()
+    v = np.zeros((3, 3))
+    t = np.array([[0, 1, 5]], np.int32)
+    assert L.fclgpu_model_build_obbrss(0, v.ctypes.data, 3, t.ctypes.data, 1, 0, C.byref(h)) == F.BVH_ERR_INCORRECT_DATA
+    assert L.fclgpu_model_build_obbrss(0, v.ctypes.data, 3, t.ctypes.data, 0, 0, C.byref(h)) == F.BVH_ERR_BUILD_EMPTY_MODEL
+    t[0, 2] = 2
+    assert L.fclgpu_model_build_obbrss(0, v.ctypes.data, 3, t.ctypes.data, 1, 1, C.byref(h)) == F.BVH_ERR_UNSUPPORTED_FUNCTION

@@ -22,3 +22,16 @@ for name, (v, t) in (("env.obj 2180 tris", (e["verts"], e["tris"])), ("heightfie
     F._capi.lib().fclgpu_bvh_refit_topdown(m._bvh, F._capi.addr(np.ascontiguousarray(v * 1.01)), m.num_vertices)
     th = time.perf_counter() - t0
     print("%-24s device refit %.2f ms   host refit %.2f ms" % (name, e0.elapsed_time(e1) / 3, th * 1e3))
+    # build: host builder + upload vs on-device build (wall clock, both synchronous)
+    t0 = time.perf_counter()
+    mh = F.BVHModel.from_arrays(v, t)
+    mh.device_model()
+    torch.cuda.synchronize()
+    tb_host = time.perf_counter() - t0
+    F.BVHModel.from_arrays(v, t, build_on_device=True).device_model()  # warm the kernels
+    t0 = time.perf_counter()
+    md = F.BVHModel.from_arrays(v, t, build_on_device=True)
+    md.device_model()
+    torch.cuda.synchronize()
+    tb_dev = time.perf_counter() - t0
+    print("%-24s device build %.2f ms   host build + upload %.2f ms" % (name, tb_dev * 1e3, tb_host * 1e3))
