@@ -70,7 +70,8 @@ std::map<std::string, long long> g_opts = {
     // binary-mode collide at traversal >= 3: 1 = pooled kernel (measured fastest: 3.8 ms per 1M poses),
     // 2 = pooled kernel with the FP32 triangle classification (4.2 ms), 0 = deferred kernel with classification (4.9 ms)
     {"binary_pooled", 1},
-    {"refit_warp", 1},         // on-device refit: 1 = warp-cooperative fit for large nodes, 0 = one thread per node
+    {"refit_warp", 2},         // on-device refit / build: 2 = block-cooperative fit for nodes > 2048 triangles and
+                               // warp-cooperative for nodes > 24, 1 = warp-cooperative only, 0 = one thread per node
     {"pool_trigger", 32},      // collide variant P: queued pairs in the warp that trigger a pooled leaf round
     {"leaf_trigger", 20},      // collide variant D: lanes with queued triangle pairs that trigger a leaf round
 };
@@ -155,7 +156,8 @@ struct fclgpu_model {
   // refit topology (optional)
   int32_t num_vertices = 0;
   int32_t *tri_index = nullptr, *node_first = nullptr, *node_count = nullptr, *by_size = nullptr;
-  int32_t n_big = 0;  // nodes with more than kRefitWarpThreshold triangles (front of by_size)
+  int32_t n_big = 0;   // nodes with more than 24 triangles (front of by_size): a warp each
+  int32_t n_huge = 0;  // of those, nodes with more than 2048 triangles: a block each
   uint32_t* prim_order = nullptr;
   double* vert_stage = nullptr;
   int32_t* fc;
@@ -277,6 +279,24 @@ extern "C" int fclgpu_model_create_obbrss(int device, int32_t n_nodes, const int
   return FCLGPU_OK;
 }
 
+namespace {
+// Refit schedule: node ids with the huge nodes (> 2048 triangles, a block each) first, then the big ones
+// (> 24, a warp each), then the rest (a thread each); huge and big nodes largest first.  O(n) apart from the
+// sort of the few large nodes.
+void refit_schedule(const int32_t* count, int nn, std::vector<int32_t>& by_size, int& n_huge, int& n_big) {
+  by_size.clear();
+  by_size.reserve(nn);
+  for (int i = 0; i < nn; ++i)
+    if (count[i] > 24) by_size.push_back(i);
+  std::stable_sort(by_size.begin(), by_size.end(), [&](int a, int b) { return count[a] > count[b]; });
+  n_big = (int)by_size.size();
+  n_huge = 0;
+  while (n_huge < n_big && count[by_size[n_huge]] > 2048) ++n_huge;
+  for (int i = 0; i < nn; ++i)
+    if (count[i] <= 24) by_size.push_back(i);
+}
+}  // namespace
+
 extern "C" int fclgpu_model_set_partition(fclgpu_model* m, int32_t num_vertices, const int32_t* tri_indices3,
                                           const int32_t* first_primitive, const int32_t* num_primitives,
                                           const int32_t* primitive_indices) {
@@ -292,12 +312,8 @@ extern "C" int fclgpu_model_set_partition(fclgpu_model* m, int32_t num_vertices,
   if (covered != nt) return fail(FCLGPU_ERR_INCORRECT_DATA, "partition does not have one leaf per triangle");
   for (long long i = 0; i < 3ll * nt; ++i)
     if (tri_indices3[i] < 0 || tri_indices3[i] >= num_vertices) return fail(FCLGPU_ERR_INCORRECT_DATA, "triangle index out of range");
-  std::vector<int32_t> by_size(nn);
-  for (int i = 0; i < nn; ++i) by_size[i] = i;
-  std::stable_sort(by_size.begin(), by_size.end(), [&](int a, int b) { return num_primitives[a] > num_primitives[b]; });
-  int n_big = 0;
-  while (n_big < nn && num_primitives[by_size[n_big]] > 24) ++n_big;  // larger nodes get a whole warp
-  m->n_big = n_big;
+  std::vector<int32_t> by_size;
+  refit_schedule(num_primitives, nn, by_size, m->n_huge, m->n_big);
   CUDA_TRY(cudaSetDevice(m->device));
   auto up = [&](int32_t** dst, const void* src, size_t count) -> int {
     if (*dst) CUDA_TRY(cudaFree(*dst));
@@ -355,9 +371,12 @@ extern "C" int fclgpu_model_refit_topdown(fclgpu_model* m, const double* vertice
                 m->prim_order, m->by_size, m->d.n_nodes, m->d.n_tris};
   gather_tris_kernel<<<(P.n_tris + 255) / 256, 256, 0, st>>>(P, dv);
   if (opt("refit_warp") && m->n_big > 0) {
-    refit_big_nodes_kernel<<<(m->n_big * 32 + 127) / 128, 128, 0, st>>>(P, m->n_big);
+    const int n_huge = opt("refit_warp") >= 2 ? m->n_huge : 0;
+    if (n_huge > 0) refit_huge_nodes_kernel<<<n_huge, kFitBlock, 0, st>>>(P);
+    if (m->n_big > n_huge)
+      refit_big_nodes_kernel<<<((m->n_big - n_huge) * 32 + 127) / 128, 128, 0, st>>>(P, n_huge, m->n_big);
     if (P.n_nodes > m->n_big) refit_small_nodes_kernel<<<(P.n_nodes - m->n_big + 63) / 64, 64, 0, st>>>(P, m->n_big);
-    g_launches += 3;
+    g_launches += 2 + (n_huge > 0) + (m->n_big > n_huge);
   } else {
     refit_nodes_kernel<<<(P.n_nodes + 63) / 64, 64, 0, st>>>(P);
     g_launches += 2;
@@ -451,7 +470,9 @@ extern "C" int fclgpu_model_build_obbrss(int device, const double* vertices, int
     B.level = lists + (size_t)cur * nt;
     B.next = lists + (size_t)(cur ^ 1) * nt;
     B.n_level = n_level;
-    if ((long long)n_level * 12 >= nt)  // average node of the level has <= 12 triangles: lanes take whole nodes
+    if ((long long)n_level * 2048 < nt && opt("refit_warp") >= 2)  // a handful of huge nodes: a block each
+      build_level_block_kernel<<<n_level, kFitBlock>>>(B);
+    else if ((long long)n_level * 12 >= nt)  // average node of the level has <= 12 triangles: lanes take whole nodes
       build_level_kernel<true><<<(n_level + 127) / 128, 128>>>(B);
     else
       build_level_kernel<false><<<(int)(((size_t)n_level * 32 + 127) / 128), 128>>>(B);
@@ -466,13 +487,9 @@ extern "C" int fclgpu_model_build_obbrss(int device, const double* vertices, int
   }
   BUILD_TRY(cudaGetLastError());
   // node sizes -> refit schedule
-  std::vector<int32_t> cnt(nn), by_size(nn);
+  std::vector<int32_t> cnt(nn), by_size;
   BUILD_TRY(cudaMemcpy(cnt.data(), m->node_count, sizeof(int32_t) * nn, cudaMemcpyDeviceToHost));
-  for (int i = 0; i < nn; ++i) by_size[i] = i;
-  std::stable_sort(by_size.begin(), by_size.end(), [&](int a, int b) { return cnt[a] > cnt[b]; });
-  int n_big = 0;
-  while (n_big < nn && cnt[by_size[n_big]] > 24) ++n_big;
-  m->n_big = n_big;
+  refit_schedule(cnt.data(), nn, by_size, m->n_huge, m->n_big);
   BUILD_TRY(cudaMemcpy(m->by_size, by_size.data(), sizeof(int32_t) * nn, cudaMemcpyHostToDevice));
   m->depth = depth;
   m->d = DeviceModel{m->obb, m->rss, m->fc, m->tri, m->rss32, m->obb32, m->topo, nn, nt};

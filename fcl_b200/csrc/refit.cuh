@@ -124,6 +124,43 @@ __device__ __forceinline__ void warp_argmin(double& v, int& idx) {
   }
 }
 
+// One step of the corner growth of getRadiusAndOriginAndRectangleSize (math/geometry-inl.h:893-968) for a
+// point (qx, qy, qz) in the box frame: a point beyond a corner of the rectangle pushes that corner outwards.
+__device__ __forceinline__ void rss_corner_grow(double qx, double qy, double qz, double cz, double radsqr, double& minx,
+                                                double& maxx, double& miny, double& maxy) {
+  const double a = sqrt(0.5);
+  double dx, dy, u, t;
+  if (qx > maxx) {
+    if (qy > maxy) {
+      dx = qx - maxx; dy = qy - maxy;
+      u = dx * a + dy * a;
+      t = (a * u - dx) * (a * u - dx) + (a * u - dy) * (a * u - dy) + (cz - qz) * (cz - qz);
+      u = u - sqrt(fmax(radsqr - t, 0.0));
+      if (u > 0) { maxx += u * a; maxy += u * a; }
+    } else if (qy < miny) {
+      dx = qx - maxx; dy = qy - miny;
+      u = dx * a - dy * a;
+      t = (a * u - dx) * (a * u - dx) + (-a * u - dy) * (-a * u - dy) + (cz - qz) * (cz - qz);
+      u = u - sqrt(fmax(radsqr - t, 0.0));
+      if (u > 0) { maxx += u * a; miny -= u * a; }
+    }
+  } else if (qx < minx) {
+    if (qy > maxy) {
+      dx = qx - minx; dy = qy - maxy;
+      u = dy * a - dx * a;
+      t = (-a * u - dx) * (-a * u - dx) + (a * u - dy) * (a * u - dy) + (cz - qz) * (cz - qz);
+      u = u - sqrt(fmax(radsqr - t, 0.0));
+      if (u > 0) { minx -= u * a; maxy += u * a; }
+    } else if (qy < miny) {
+      dx = qx - minx; dy = qy - miny;
+      u = -dx * a - dy * a;
+      t = (-a * u - dx) * (-a * u - dx) + (-a * u - dy) * (-a * u - dy) + (cz - qz) * (cz - qz);
+      u = u - sqrt(fmax(radsqr - t, 0.0));
+      if (u > 0) { minx -= u * a; miny -= u * a; }
+    }
+  }
+}
+
 __device__ inline void fit_obbrss_warp(const double* __restrict__ tv, int tri_stride, const uint32_t* __restrict__ idx,
                                        int n, double (*terms)[9], NodeFit& f) {
   const int lane = threadIdx.x & 31;
@@ -263,7 +300,6 @@ __device__ inline void fit_obbrss_warp(const double* __restrict__ tv, int tri_st
     maxy = warp_max(hy);
   }
   // corner growth, replayed in point order over the candidates
-  const double a = sqrt(0.5);
   const double minx0 = minx, maxx0 = maxx, miny0 = miny, maxy0 = maxy;
   for (int base = 0; base < m; base += 32) {
     const int j = base + lane;
@@ -279,36 +315,7 @@ __device__ inline void fit_obbrss_warp(const double* __restrict__ tv, int tri_st
       const int src = __ffs(mask) - 1;
       mask &= mask - 1;
       const double qx = __shfl_sync(0xffffffffu, px, src), qy = __shfl_sync(0xffffffffu, py, src), qz = __shfl_sync(0xffffffffu, pz, src);
-      double dx, dy, u, t;
-      if (qx > maxx) {
-        if (qy > maxy) {
-          dx = qx - maxx; dy = qy - maxy;
-          u = dx * a + dy * a;
-          t = (a * u - dx) * (a * u - dx) + (a * u - dy) * (a * u - dy) + (cz - qz) * (cz - qz);
-          u = u - sqrt(fmax(radsqr - t, 0.0));
-          if (u > 0) { maxx += u * a; maxy += u * a; }
-        } else if (qy < miny) {
-          dx = qx - maxx; dy = qy - miny;
-          u = dx * a - dy * a;
-          t = (a * u - dx) * (a * u - dx) + (-a * u - dy) * (-a * u - dy) + (cz - qz) * (cz - qz);
-          u = u - sqrt(fmax(radsqr - t, 0.0));
-          if (u > 0) { maxx += u * a; miny -= u * a; }
-        }
-      } else if (qx < minx) {
-        if (qy > maxy) {
-          dx = qx - minx; dy = qy - maxy;
-          u = dy * a - dx * a;
-          t = (-a * u - dx) * (-a * u - dx) + (a * u - dy) * (a * u - dy) + (cz - qz) * (cz - qz);
-          u = u - sqrt(fmax(radsqr - t, 0.0));
-          if (u > 0) { minx -= u * a; maxy += u * a; }
-        } else if (qy < miny) {
-          dx = qx - minx; dy = qy - miny;
-          u = -dx * a - dy * a;
-          t = (-a * u - dx) * (-a * u - dx) + (-a * u - dy) * (-a * u - dy) + (cz - qz) * (cz - qz);
-          u = u - sqrt(fmax(radsqr - t, 0.0));
-          if (u > 0) { minx -= u * a; miny -= u * a; }
-        }
-      }
+      rss_corner_grow(qx, qy, qz, cz, radsqr, minx, maxx, miny, maxy);
     }
   }
   for (int k = 0; k < 3; ++k) f.rss_To[k] = (A[3 * k] * minx + A[3 * k + 1] * miny) + A[3 * k + 2] * cz;
@@ -317,6 +324,266 @@ __device__ inline void fit_obbrss_warp(const double* __restrict__ tv, int tri_st
   f.rss_l[1] = maxy - miny;
   if (f.rss_l[1] < 0) f.rss_l[1] = 0;
   f.rss_r = r;
+#undef W_PT
+#undef W_PX
+#undef W_PY
+#undef W_PZ
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Block-cooperative fit for the few huge nodes near the root (a warp would spend tens of
+// milliseconds on a 200k-triangle root).  Same construction as the warp version: parallel
+// terms + in-order accumulation for the covariance, exact min / max / arg-min reductions, and
+// the corner growth replayed in point order over the (few) candidate points.
+// ---------------------------------------------------------------------------------------
+constexpr int kFitBlock = 256;
+constexpr int kCornerCap = 1024;
+struct BlockFitSmem {
+  double terms[kFitBlock][9];
+  double red[kFitBlock / 32][14];
+  double bc[16];
+  int redi[kFitBlock / 32][4];
+  int cand[kCornerCap], sorted[kCornerCap];
+  int wcnt[kFitBlock / 32];
+  int ncand;
+};
+
+__device__ inline void fit_obbrss_block(const double* __restrict__ tv, int tri_stride, const uint32_t* __restrict__ idx,
+                                        int n, BlockFitSmem& sm, NodeFit& f) {
+  constexpr int NW = kFitBlock / 32;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) sm.ncand = 0;
+  // --- covariance ---
+  double acc = 0.0;  // thread k < 9 owns accumulator k
+  for (int base = 0; base < n; base += kFitBlock) {
+    const int i = base + tid;
+    if (i < n) {
+      const double* p1 = tv + (size_t)idx[i] * tri_stride;
+      const double* p2 = p1 + 3;
+      const double* p3 = p1 + 6;
+      double* t = sm.terms[tid];
+      for (int k = 0; k < 3; ++k) t[k] = ((p1[k] + p2[k]) + p3[k]);
+      t[3] = (p1[0] * p1[0] + p2[0] * p2[0] + p3[0] * p3[0]);
+      t[4] = (p1[1] * p1[1] + p2[1] * p2[1] + p3[1] * p3[1]);
+      t[5] = (p1[2] * p1[2] + p2[2] * p2[2] + p3[2] * p3[2]);
+      t[6] = (p1[0] * p1[1] + p2[0] * p2[1] + p3[0] * p3[1]);
+      t[7] = (p1[0] * p1[2] + p2[0] * p2[2] + p3[0] * p3[2]);
+      t[8] = (p1[1] * p1[2] + p2[1] * p2[2] + p3[1] * p3[2]);
+    }
+    __syncthreads();
+    if (tid < 9) {
+      const int cnt = (n - base) < kFitBlock ? (n - base) : kFitBlock;
+#pragma unroll 8
+      for (int r = 0; r < cnt; ++r) acc += sm.terms[r][tid];
+    }
+    __syncthreads();
+  }
+  if (tid < 9) sm.bc[tid] = acc;
+  __syncthreads();
+  double S1[3], S2[6];
+  for (int k = 0; k < 3; ++k) S1[k] = sm.bc[k];
+  for (int k = 0; k < 6; ++k) S2[k] = sm.bc[3 + k];
+  const int np = 3 * n;
+  f.vsum[0] = S1[0];
+  f.vsum[1] = S1[1];
+  f.vsum[2] = S1[2];
+  double M[3][3];
+  M[0][0] = S2[0] - S1[0] * S1[0] / np;
+  M[1][1] = S2[1] - S1[1] * S1[1] / np;
+  M[2][2] = S2[2] - S1[2] * S1[2] / np;
+  M[0][1] = M[1][0] = S2[3] - S1[0] * S1[1] / np;
+  M[1][2] = M[2][1] = S2[5] - S1[1] * S1[2] / np;
+  M[0][2] = M[2][0] = S2[4] - S1[0] * S1[2] / np;
+  double ev[3], V[3][3];
+  jacobi3(M, ev, V);
+  int lo, mid, hi;
+  if (ev[0] > ev[1]) { hi = 0; lo = 1; } else { lo = 0; hi = 1; }
+  if (ev[2] < ev[lo]) { mid = lo; lo = 2; }
+  else if (ev[2] > ev[hi]) { mid = hi; hi = 2; }
+  else mid = 2;
+  double* A = f.axis;
+  for (int r = 0; r < 3; ++r) {
+    A[3 * r + 0] = V[r][hi];
+    A[3 * r + 1] = V[r][mid];
+  }
+  A[2] = A[3] * A[7] - A[6] * A[4];
+  A[5] = A[6] * A[1] - A[0] * A[7];
+  A[8] = A[0] * A[4] - A[3] * A[1];
+  const double a00 = A[0], a10 = A[3], a20 = A[6], a01 = A[1], a11 = A[4], a21 = A[7], a02 = A[2], a12 = A[5], a22 = A[8];
+  const int m = 3 * n;
+#define W_PT(j) (tv + (size_t)idx[(j) / 3] * tri_stride + 3 * ((j) % 3))
+#define W_PX(p) ((a00 * (p)[0] + a10 * (p)[1]) + a20 * (p)[2])
+#define W_PY(p) ((a01 * (p)[0] + a11 * (p)[1]) + a21 * (p)[2])
+#define W_PZ(p) ((a02 * (p)[0] + a12 * (p)[1]) + a22 * (p)[2])
+  // --- extents and extreme points ---
+  double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+  double vminx = DBL_MAX, vmaxx = DBL_MAX, vminy = DBL_MAX, vmaxy = DBL_MAX;
+  int iminx = 0x7fffffff, imaxx = 0x7fffffff, iminy = 0x7fffffff, imaxy = 0x7fffffff;
+  for (int j = tid; j < m; j += kFitBlock) {
+    const double* p = W_PT(j);
+    const double c0 = W_PX(p), c1 = W_PY(p), c2 = W_PZ(p);
+    if (c0 > mx[0]) mx[0] = c0;
+    if (c0 < mn[0]) mn[0] = c0;
+    if (c1 > mx[1]) mx[1] = c1;
+    if (c1 < mn[1]) mn[1] = c1;
+    if (c2 > mx[2]) mx[2] = c2;
+    if (c2 < mn[2]) mn[2] = c2;
+    if (c0 < vminx) { vminx = c0; iminx = j; }
+    if (-c0 < vmaxx) { vmaxx = -c0; imaxx = j; }
+    if (c1 < vminy) { vminy = c1; iminy = j; }
+    if (-c1 < vmaxy) { vmaxy = -c1; imaxy = j; }
+  }
+  for (int k = 0; k < 3; ++k) {
+    mn[k] = warp_min(mn[k]);
+    mx[k] = warp_max(mx[k]);
+  }
+  warp_argmin(vminx, iminx);
+  warp_argmin(vmaxx, imaxx);
+  warp_argmin(vminy, iminy);
+  warp_argmin(vmaxy, imaxy);
+  if (lane == 0) {
+    for (int k = 0; k < 3; ++k) {
+      sm.red[wid][k] = mn[k];
+      sm.red[wid][3 + k] = mx[k];
+    }
+    sm.red[wid][6] = vminx; sm.red[wid][7] = vmaxx; sm.red[wid][8] = vminy; sm.red[wid][9] = vmaxy;
+    sm.redi[wid][0] = iminx; sm.redi[wid][1] = imaxx; sm.redi[wid][2] = iminy; sm.redi[wid][3] = imaxy;
+  }
+  __syncthreads();
+  for (int k = 0; k < 3; ++k) {
+    mn[k] = sm.red[0][k];
+    mx[k] = sm.red[0][3 + k];
+  }
+  double av[4];
+  int ai[4];
+  for (int q = 0; q < 4; ++q) {
+    av[q] = sm.red[0][6 + q];
+    ai[q] = sm.redi[0][q];
+  }
+  for (int w = 1; w < NW; ++w) {
+    for (int k = 0; k < 3; ++k) {
+      const double a = sm.red[w][k], b = sm.red[w][3 + k];
+      if (a < mn[k]) mn[k] = a;
+      if (b > mx[k]) mx[k] = b;
+    }
+    for (int q = 0; q < 4; ++q) {
+      const double v = sm.red[w][6 + q];
+      const int vi = sm.redi[w][q];
+      if (v < av[q] || (v == av[q] && vi < ai[q])) {
+        av[q] = v;
+        ai[q] = vi;
+      }
+    }
+  }
+  iminx = ai[0]; imaxx = ai[1]; iminy = ai[2]; imaxy = ai[3];
+  const double o[3] = {(mx[0] + mn[0]) / 2, (mx[1] + mn[1]) / 2, (mx[2] + mn[2]) / 2};
+  for (int r = 0; r < 3; ++r) {
+    f.obb_To[r] = (A[3 * r] * o[0] + A[3 * r + 1] * o[1]) + A[3 * r + 2] * o[2];
+    f.obb_ext[r] = (mx[r] - mn[r]) / 2;
+  }
+  const double minz = mn[2], maxz = mx[2];
+  const double r = 0.5 * (maxz - minz), radsqr = r * r, cz = 0.5 * (maxz + minz);
+  double minx, maxx, miny, maxy;
+  {
+    const double* p = W_PT(iminx);
+    double dz = W_PZ(p) - cz;
+    minx = W_PX(p) + sqrt(fmax(radsqr - dz * dz, 0.0));
+    p = W_PT(imaxx);
+    dz = W_PZ(p) - cz;
+    maxx = W_PX(p) - sqrt(fmax(radsqr - dz * dz, 0.0));
+    p = W_PT(iminy);
+    dz = W_PZ(p) - cz;
+    miny = W_PY(p) + sqrt(fmax(radsqr - dz * dz, 0.0));
+    p = W_PT(imaxy);
+    dz = W_PZ(p) - cz;
+    maxy = W_PY(p) - sqrt(fmax(radsqr - dz * dz, 0.0));
+  }
+  {
+    double lx = minx, hx = maxx, ly = miny, hy = maxy;
+    for (int j = tid; j < m; j += kFitBlock) {
+      const double* p = W_PT(j);
+      const double px = W_PX(p), py = W_PY(p);
+      if (px < minx || px > maxx || py < miny || py > maxy) {
+        const double dz = W_PZ(p) - cz;
+        const double reach = sqrt(fmax(radsqr - dz * dz, 0.0));
+        if (px < minx) { const double x = px + reach; if (x < lx) lx = x; }
+        if (px > maxx) { const double x = px - reach; if (x > hx) hx = x; }
+        if (py < miny) { const double y = py + reach; if (y < ly) ly = y; }
+        if (py > maxy) { const double y = py - reach; if (y > hy) hy = y; }
+      }
+    }
+    lx = warp_min(lx); hx = warp_max(hx); ly = warp_min(ly); hy = warp_max(hy);
+    if (lane == 0) {
+      sm.red[wid][10] = lx; sm.red[wid][11] = hx; sm.red[wid][12] = ly; sm.red[wid][13] = hy;
+    }
+    __syncthreads();
+    minx = sm.red[0][10]; maxx = sm.red[0][11]; miny = sm.red[0][12]; maxy = sm.red[0][13];
+    for (int w = 1; w < NW; ++w) {
+      if (sm.red[w][10] < minx) minx = sm.red[w][10];
+      if (sm.red[w][11] > maxx) maxx = sm.red[w][11];
+      if (sm.red[w][12] < miny) miny = sm.red[w][12];
+      if (sm.red[w][13] > maxy) maxy = sm.red[w][13];
+    }
+  }
+  // --- corner growth: candidates in parallel, replay in point order ---
+  const double minx0 = minx, maxx0 = maxx, miny0 = miny, maxy0 = maxy;
+  for (int j = tid; j < m; j += kFitBlock) {
+    const double* p = W_PT(j);
+    const double px = W_PX(p), py = W_PY(p);
+    if ((px > maxx0 || px < minx0) && (py > maxy0 || py < miny0)) {
+      const int slot = atomicAdd(&sm.ncand, 1);
+      if (slot < kCornerCap) sm.cand[slot] = j;
+    }
+  }
+  __syncthreads();
+  const int nc = sm.ncand;
+  if (nc > 0) {
+    if (nc <= kCornerCap) {
+      for (int c = tid; c < nc; c += kFitBlock) {  // rank sort (indices are distinct)
+        const int mine = sm.cand[c];
+        int rank = 0;
+        for (int q = 0; q < nc; ++q) rank += sm.cand[q] < mine;
+        sm.sorted[rank] = mine;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        for (int c = 0; c < nc; ++c) {
+          const double* p = W_PT(sm.sorted[c]);
+          rss_corner_grow(W_PX(p), W_PY(p), W_PZ(p), cz, radsqr, minx, maxx, miny, maxy);
+        }
+        sm.bc[0] = minx; sm.bc[1] = maxx; sm.bc[2] = miny; sm.bc[3] = maxy;
+      }
+    } else if (wid == 0) {  // too many candidates for the list: warp 0 walks all points in order
+      for (int base = 0; base < m; base += 32) {
+        const int j = base + lane;
+        double px = 0, py = 0, pz = 0;
+        bool cand = false;
+        if (j < m) {
+          const double* p = W_PT(j);
+          px = W_PX(p); py = W_PY(p); pz = W_PZ(p);
+          cand = (px > maxx0 || px < minx0) && (py > maxy0 || py < miny0);
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, cand);
+        while (mask) {
+          const int src = __ffs(mask) - 1;
+          mask &= mask - 1;
+          rss_corner_grow(__shfl_sync(0xffffffffu, px, src), __shfl_sync(0xffffffffu, py, src),
+                          __shfl_sync(0xffffffffu, pz, src), cz, radsqr, minx, maxx, miny, maxy);
+        }
+      }
+      if (lane == 0) { sm.bc[0] = minx; sm.bc[1] = maxx; sm.bc[2] = miny; sm.bc[3] = maxy; }
+    }
+    __syncthreads();
+    minx = sm.bc[0]; maxx = sm.bc[1]; miny = sm.bc[2]; maxy = sm.bc[3];
+  }
+  for (int k = 0; k < 3; ++k) f.rss_To[k] = (A[3 * k] * minx + A[3 * k + 1] * miny) + A[3 * k + 2] * cz;
+  f.rss_l[0] = maxx - minx;
+  if (f.rss_l[0] < 0) f.rss_l[0] = 0;
+  f.rss_l[1] = maxy - miny;
+  if (f.rss_l[1] < 0) f.rss_l[1] = 0;
+  f.rss_r = r;
+  __syncthreads();  // the shared scratch may be reused by the caller
 #undef W_PT
 #undef W_PX
 #undef W_PY
@@ -350,15 +617,24 @@ __device__ __forceinline__ void store_node_records(const RefitParams& P, int nod
   P.topo[node] = t;
 }
 
-// one warp per node for the n_big largest nodes (by_size[0 .. n_big))
-__global__ void __launch_bounds__(128) refit_big_nodes_kernel(RefitParams P, int n_big) {
+// one warp per node for the next largest nodes (by_size[n_huge .. n_big))
+__global__ void __launch_bounds__(128) refit_big_nodes_kernel(RefitParams P, int n_huge, int n_big) {
   __shared__ double terms[4][32][9];
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int warp = n_huge + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (warp >= n_big) return;
   const int node = P.by_size[warp];
   NodeFit f;
   fit_obbrss_warp(P.tri, kTriDoubles, P.prim_order + P.node_first[node], P.node_count[node], terms[threadIdx.x >> 5], f);
   if ((threadIdx.x & 31) == 0) store_node_records(P, node, f);
+}
+
+// one block per node for the n_huge largest nodes (by_size[0 .. n_huge))
+__global__ void __launch_bounds__(kFitBlock) refit_huge_nodes_kernel(RefitParams P) {
+  __shared__ BlockFitSmem sm;
+  const int node = P.by_size[blockIdx.x];
+  NodeFit f;
+  fit_obbrss_block(P.tri, kTriDoubles, P.prim_order + P.node_first[node], P.node_count[node], sm, f);
+  if (threadIdx.x == 0) store_node_records(P, node, f);
 }
 
 // one thread per node for the rest (by_size[n_big .. n_nodes))
@@ -511,6 +787,103 @@ __device__ inline void build_finish_node(const BuildParams& B, const BuildNode n
     const int slot = atomicAdd(B.next_count, 2);
     B.next[slot] = BuildNode{nd.pair, nd.first, c1, nd.pair + 2};
     B.next[slot + 1] = BuildNode{nd.pair + 1, nd.first + c1, n - c1, nd.pair + 2 * c1};
+  }
+}
+
+// Block-cooperative version of build_finish_node for huge nodes (same results; see the warp branch above
+// for the closed form of the swap-partition replay).
+__device__ inline void build_finish_node_block(const BuildParams& B, const BuildNode nd, const NodeFit& f, BlockFitSmem& sm) {
+  constexpr int NW = kFitBlock / 32;
+  const RefitParams& P = B.R;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  uint32_t* idx = B.prim_order + nd.first;
+  const int n = nd.count;  // > 24
+  if (tid == 0) {
+    store_node_records(P, nd.id, f);
+    B.node_first[nd.id] = nd.first;
+    B.node_count[nd.id] = n;
+  }
+  const double sv0 = f.axis[0], sv1 = f.axis[3], sv2 = f.axis[6];
+  const double thr = (B.split == FCLGPU_SPLIT_METHOD_BV_CENTER)
+                         ? f.obb_To[0]
+                         : (f.vsum[0] * sv0 + f.vsum[1] * sv1 + f.vsum[2] * sv2) / (3 * n);
+  uint32_t* old = B.queue + 2 * (size_t)nd.first;
+  uint32_t* lrank = old + n;
+  uint8_t* fl = B.flag + nd.first;
+  int run = 0, my_i0 = n;
+  for (int base = 0; base < n; base += kFitBlock) {
+    const int i = base + tid;
+    const bool in = i < n;
+    bool left = false;
+    if (in) {
+      const uint32_t pi = idx[i];
+      const double* p1 = P.tri + (size_t)pi * kTriDoubles;
+      const double* p2 = p1 + 3;
+      const double* p3 = p1 + 6;
+      const double cx = ((p1[0] + p2[0]) + p3[0]) / 3.0, cy = ((p1[1] + p2[1]) + p3[1]) / 3.0, cz = ((p1[2] + p2[2]) + p3[2]) / 3.0;
+      left = !(((sv0 * cx + sv1 * cy) + sv2 * cz) > thr);
+      fl[i] = left ? 1 : 0;
+      old[i] = pi;
+      if (!left && my_i0 == n) my_i0 = i;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, left);
+    if (lane == 0) sm.wcnt[wid] = __popc(m);
+    __syncthreads();
+    int pre = 0, tot = 0;
+    for (int w = 0; w < NW; ++w) {
+      const int c = sm.wcnt[w];
+      pre += (w < wid) ? c : 0;
+      tot += c;
+    }
+    if (in) lrank[i] = run + pre + __popc(m & (0xffffffffu >> (31 - lane)));
+    run += tot;
+    __syncthreads();
+  }
+  // first right element
+  for (int o = 16; o > 0; o >>= 1) {
+    const int w = __shfl_xor_sync(0xffffffffu, my_i0, o);
+    my_i0 = w < my_i0 ? w : my_i0;
+  }
+  if (lane == 0) sm.wcnt[wid] = my_i0;
+  __syncthreads();  // also makes old / lrank / fl visible to the whole block
+  int i0 = n;
+  for (int w = 0; w < NW; ++w) i0 = sm.wcnt[w] < i0 ? sm.wcnt[w] : i0;
+  int c1 = run;
+  if (c1 != 0 && c1 != n) {
+    const int J = c1 - i0, T = n - i0;
+    for (int i = tid; i < n; i += kFitBlock)
+      if (fl[i]) idx[lrank[i] - 1] = old[i];
+    for (int k = J + 1 + tid; k <= T; k += kFitBlock) {
+      int i = i0 + k - 1;
+      while (fl[i]) i = (int)lrank[i] - 1;  // = i0 + (lrank - i0) - 1: rotation number j -> item of time j
+      idx[c1 + (k - J - 1)] = old[i];
+    }
+  } else {
+    c1 = n / 2;
+  }
+  if (tid == 0) {
+    B.first_child[nd.id] = nd.pair;
+    double2 t = P.topo[nd.id];
+    long long bits = (long long)(unsigned)nd.pair;
+    t.x = __longlong_as_double(bits);
+    P.topo[nd.id] = t;
+    const int slot = atomicAdd(B.next_count, 2);
+    B.next[slot] = BuildNode{nd.pair, nd.first, c1, nd.pair + 2};
+    B.next[slot + 1] = BuildNode{nd.pair + 1, nd.first + c1, n - c1, nd.pair + 2 * c1};
+  }
+}
+
+// one block per node of the level (top levels: a handful of huge nodes)
+__global__ void __launch_bounds__(kFitBlock) build_level_block_kernel(BuildParams B) {
+  __shared__ BlockFitSmem sm;
+  const BuildNode nd = B.level[blockIdx.x];
+  NodeFit f;
+  if (nd.count > 24) {
+    fit_obbrss_block(B.R.tri, kTriDoubles, B.prim_order + nd.first, nd.count, sm, f);
+    build_finish_node_block(B, nd, f, sm);
+  } else if (threadIdx.x == 0) {
+    fit_obbrss(B.R.tri, kTriDoubles, B.prim_order + nd.first, nd.count, f);
+    build_finish_node(B, nd, f, 0, false);
   }
 }
 

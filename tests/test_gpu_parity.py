@@ -342,8 +342,8 @@ def test_device_refit_topdown_is_bit_exact(oracle, env_rob_npz):
 
 
 def test_device_refit_thread_and_warp_variants_agree(oracle):
-    """Both refit kernels (one thread per node / warp-cooperative for large nodes) give the oracle's BVs,
-    also on a mesh large enough for deep trees and many large nodes."""
+    """All refit schedules (one thread per node / warp-cooperative for large nodes / block-cooperative for the
+    huge ones) give the oracle's BVs, also on a mesh large enough for deep trees and many large nodes."""
     import torch
     from tests.meshes import heightfield
 
@@ -351,7 +351,7 @@ def test_device_refit_thread_and_warp_variants_agree(oracle):
     m, o = F.BVHModel.from_arrays(v, t), oracle.Model(v, t)
     m.device_model()
     rng = np.random.default_rng(8)
-    for variant in (1, 0):
+    for variant in (2, 1, 0):
         _capi.set_option("refit_warp", variant)
         v2 = v + rng.normal(0, 0.05, size=v.shape)
         m.refit_device(torch.from_numpy(v2).cuda())
@@ -360,7 +360,7 @@ def test_device_refit_thread_and_warp_variants_agree(oracle):
         dev, ref = m.download_device_arrays(), o.arrays()
         for k in ("axis", "obb_To", "obb_ext", "rss_To", "rss_l", "rss_r"):
             assert dev[k].tobytes() == ref[k].tobytes(), (variant, k)
-    _capi.set_option("refit_warp", 1)
+    _capi.set_option("refit_warp", 2)
 
 
 @pytest.mark.parametrize("split", [F.SPLIT_METHOD_MEAN, F.SPLIT_METHOD_BV_CENTER])
@@ -371,7 +371,7 @@ def test_device_build_equals_host_build(oracle, env_rob_npz, split):
     from tests.meshes import heightfield, random_soup, uv_sphere
 
     meshes = [env_rob_npz[0], env_rob_npz[1], heightfield(60, size=10.0, seed=3, amp=0.6), uv_sphere(1.0, 24, 24),
-              random_soup(3000, seed=5)]
+              random_soup(3000, seed=5), random_soup(20000, seed=6, scale=3.0, tri_size=0.05)]
     one_tri = (np.array([[0.0, 0, 0], [1, 0, 0], [0, 1, 0]]), np.array([[0, 1, 2]], np.int32))
     coplanar = heightfield(12, size=4.0, seed=1, amp=0.0)  # flat grid: degenerate covariance, many split ties
     for v, t in meshes + [one_tri, coplanar]:
