@@ -63,6 +63,7 @@ std::map<std::string, long long> g_opts = {
     // 1: collide = thread per query with deferred leaf rounds, distance = warp per query sorted front, FP64 BV tests
     // 0: thread per query, the reference's visiting order exactly (work counters match the reference's)
     {"traversal", 3},
+    {"host_chunk", 1 << 17},   // queries per stage of the host API's two-stream copy/compute pipeline
     {"contact_stride", 1024},  // per-query contact scratch slots when num_max_contacts is larger
     {"scratch_bytes", 2ll << 30},
     {"blocks_per_sm", 0},      // 0 = occupancy query
@@ -893,7 +894,8 @@ size_t padded(size_t bytes) { return (bytes + 255) & ~size_t(255); }
 }  // namespace
 
 namespace {
-constexpr int64_t kHostChunk = 1 << 17;  // queries per pipeline stage (12.6 MB of poses)
+// queries per pipeline stage of the host API: option "host_chunk" (default 1 << 17 = 12.6 MB of poses)
+static int64_t host_chunk() { return std::max<long long>(1024, opt("host_chunk")); }
 
 int finish_pipeline(Workspace* w, int device) {
   CUDA_TRY(cudaStreamSynchronize(w->pipe[0]));
@@ -914,7 +916,7 @@ extern "C" int fclgpu_collide_batch_host(const fclgpu_model* m1, const fclgpu_mo
   const bool want = contacts != nullptr || contact_offsets != nullptr;
   if (contacts == nullptr) contact_capacity = 0;
   if (!want && n > 0) {  // counts / verdicts only: chunked two-stream pipeline (see the distance wrapper)
-    const size_t C = (size_t)std::min<int64_t>(n, kHostChunk);
+    const size_t C = (size_t)std::min<int64_t>(n, host_chunk());
     const size_t per_stage = (tf1 ? padded(96 * C) : 0) + (tf2 ? padded(96 * C) : 0) + 3 * padded(4 * C) + 256;
     {
       std::lock_guard<std::mutex> lock(w->mu);
@@ -991,7 +993,7 @@ extern "C" int fclgpu_distance_batch_host(const fclgpu_model* m1, const fclgpu_m
   if (n == 0) return FCLGPU_OK;
   // Chunked two-stream pipeline: while chunk c computes, chunk c+1's poses go up and chunk
   // c-1's results come down (the copies are asynchronous when the caller's buffers are pinned).
-  const size_t C = (size_t)std::min<int64_t>(n, kHostChunk);
+  const size_t C = (size_t)std::min<int64_t>(n, host_chunk());
   const size_t per_stage = (tf1 ? padded(96 * C) : 0) + (tf2 ? padded(96 * C) : 0) + padded(8 * C) + 2 * padded(24 * C) +
                            4 * padded(4 * C) + 256;
   {

@@ -555,6 +555,8 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
     }
 
     double min_d = 1.7976931348623157e308;
+    // bounds are floats: (double)b < min_d  <=>  b < min_f with min_f = min_d rounded up (the smallest float >= min_d)
+    float min_f = __int_as_float(0x7f800000);
     int sp = 1, nleaf = 1, nraw = 0;
     uint32_t bv_tests = 0, leaf_tests = 0;
     if (lane == 0) {
@@ -624,7 +626,7 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
         bool mine = lane < k;
         if (mine) {
           ids = S.leaf_pair[nleaf + lane];
-          mine = (double)S.leaf_bound[nleaf + lane] < min_d;
+          mine = S.leaf_bound[nleaf + lane] < min_f;
         }
         if (kStats) leaf_tests += __popc(__ballot_sync(0xffffffffu, mine));
         if (mine) {
@@ -650,6 +652,7 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
         const double dmin = __longlong_as_double((long long)key);
         if (dmin < min_d) {  // strictly smaller, like DistanceResult::update
           min_d = dmin;
+          min_f = __double2float_ru(dmin);
           if (lane == who) {
             S.best[0] = Pn.x; S.best[1] = Pn.y; S.best[2] = Pn.z;
             S.best[3] = Qn.x; S.best[4] = Qn.y; S.best[5] = Qn.z;
@@ -673,7 +676,7 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
       if (alive) {
         pr = S.pair[sp - 1 - lane];
         bd = S.bound[sp - 1 - lane];
-        alive = (double)bd < min_d;  // canStop(c): bound >= min_distance -> skip
+        alive = bd < min_f;  // canStop(c): bound >= min_distance -> skip
       }
       int fc1 = 0, fc2 = 0;
       if (alive) {
@@ -747,7 +750,7 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
           const double la[2] = {n1.e0, n1.e1}, lb[2] = {n2.e0, n2.e1};
           d = __double2float_rd(rss_pair_distance(R, T, n1.axis, n1.To, la, n1.e2, n2.axis, n2.To, lb, n2.e2));
         }
-        if ((double)d < min_d) key = (__float_as_uint(d) & ~31u) | (unsigned)lane;
+        if (d < min_f) key = (__float_as_uint(d) & ~31u) | (unsigned)lane;
       }
       if (kStats) bv_tests += 2 * n_exp;
       const int nkeep = __popc(__ballot_sync(0xffffffffu, key != 0xffffffffu));

@@ -5,7 +5,7 @@ libs="$1"; wls="$2"; shift 2
 for lib in $libs; do
   for w in $wls; do
     if [ "$lib" = default ]; then unset FCLGPU_LIB_PATH; else export FCLGPU_LIB_PATH=$PWD/fcl_b200/lib/variants/libfclgpu_$lib.so; fi
-    timeout 300 python bench.py --steps 3 --warmup 3 --workload $w --traversal 1 --no-cpu-baseline --no-e2e "$@" > gpurun_out/ab_${lib}_$w.json 2> gpurun_out/ab_${lib}_$w.err
+    timeout 300 python bench.py --steps 3 --warmup 3 --workload $w --traversal ${TRAV:-3} --no-cpu-baseline --no-e2e "$@" > gpurun_out/ab_${lib}_$w.json 2> gpurun_out/ab_${lib}_$w.err
     python - <<PY
 import json
 try:
