@@ -343,8 +343,17 @@ def main():
         ncon = None
     alg_bytes = float(algorithmic_bytes(wl, h_nbv, h_nleaf, ncon).sum())
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    try:  # measured DRAM bytes of the dominant kernel (one ncu --set full capture, committed under profiles/)
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f).get(wl)
+        if t and t["poses"] == n and t["traversal"] == args.traversal:
+            traffic = t["dram_bytes_per_launch"] * t["launches_per_step"]
+            traffic_src = "profiles/r01_traffic.json (%s, %d launch(es) per step)" % (t["kernel"], t["launches_per_step"])
+    except Exception:  # pragma: no cover
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)" if which == "measured" else "fallback",
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)" if which == "measured" else "fallback",
                 "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "mean_n_bv": float(h_nbv.mean()), "mean_n_leaf": float(h_nleaf.mean()),
                 "note": "working set (~1 MB of BVH records) is L2/L1 resident; the binding resource is the FP64 pipe, see fp64"}

@@ -22,6 +22,7 @@ ERR_NO_DEVICE = -21
 ERR_CUDA = -22
 ERR_CONTACT_OVERFLOW = -23
 ERR_STACK_OVERFLOW = -24
+ERR_INPUT_STALLED = -25
 
 CONTACT_DTYPE = np.dtype(
     [("b1", "<i4"), ("b2", "<i4"), ("normal", "<f8", (3,)), ("pos", "<f8", (3,)), ("penetration_depth", "<f8")]

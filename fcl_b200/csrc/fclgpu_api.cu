@@ -100,8 +100,15 @@ struct Workspace {
   void* dev_io = nullptr;
   size_t dev_io_bytes = 0;
   cudaStream_t pipe[2] = {nullptr, nullptr};
-  std::mutex mu;
+  unsigned* ready = nullptr;      // device: per-chunk "input has landed" flags of the streamed host path
+  unsigned* host_one = nullptr;   // pinned host word (= 1) the copy stream writes into ready[c]
+  long long* host_totals = nullptr;  // pinned: running contact totals read back per sub-batch
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  std::mutex mu;       // held while enqueuing (work counters, scratch growth)
+  std::mutex host_mu;  // held for a whole *_batch_host call: the staging buffers and pipeline streams are shared
 };
+constexpr int kReadySlots = 1 << 16;
+constexpr int kTotalSlots = 1 << 12;
 
 std::mutex g_ws_mu;
 std::map<int, Workspace*> g_ws;
@@ -125,6 +132,13 @@ int get_ws(int device, Workspace** out) {
   CUDA_TRY(cudaMalloc(&w->status, sizeof(int)));
   CUDA_TRY(cudaMemset(w->status, 0, sizeof(int)));
   CUDA_TRY(cudaMalloc(&w->scan_base, sizeof(long long)));
+  CUDA_TRY(cudaMalloc(&w->ready, sizeof(unsigned) * kReadySlots));
+  CUDA_TRY(cudaMemset(w->ready, 0, sizeof(unsigned) * kReadySlots));
+  CUDA_TRY(cudaHostAlloc((void**)&w->host_one, sizeof(unsigned), cudaHostAllocDefault));
+  *w->host_one = 1u;
+  CUDA_TRY(cudaHostAlloc((void**)&w->host_totals, sizeof(long long) * kTotalSlots, cudaHostAllocDefault));
+  CUDA_TRY(cudaEventCreateWithFlags(&w->ev[0], cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&w->ev[1], cudaEventDisableTiming));
   CUDA_TRY(cudaStreamCreateWithFlags(&w->pipe[0], cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&w->pipe[1], cudaStreamNonBlocking));
   g_ws[device] = w;
@@ -702,10 +716,33 @@ unsigned long long* next_counter(Workspace* w, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------
 // collide
 // ------------------------------------------------------------------------------------------
+namespace {
+// Hidden knobs of the host wrappers around collide_enqueue.
+struct CollideExtra {
+  const unsigned* ready = nullptr;  // streamed input: per-chunk "poses have landed" flags (see wait_ready)
+  int ready_shift = 0;
+  long long ready_q0 = 0;           // index of this call's first query in the flagged batch
+  bool continue_scan = false;       // keep the running contact offset of the previous call (sub-batches of one result)
+};
+int collide_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1, const double* tf2,
+                    const fclgpu_collision_request* request, int32_t* num_contacts, fclgpu_contact* contacts,
+                    int64_t contact_capacity, int64_t* contact_offsets, uint32_t* n_bv, uint32_t* n_leaf, void* stream,
+                    const CollideExtra& X);
+}  // namespace
+
 extern "C" int fclgpu_collide_batch(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1,
                                     const double* tf2, const fclgpu_collision_request* request,
                                     int32_t* num_contacts, fclgpu_contact* contacts, int64_t contact_capacity,
                                     int64_t* contact_offsets, uint32_t* n_bv, uint32_t* n_leaf, void* stream) {
+  return collide_enqueue(m1, m2, n, tf1, tf2, request, num_contacts, contacts, contact_capacity, contact_offsets, n_bv,
+                         n_leaf, stream, CollideExtra{});
+}
+
+namespace {
+int collide_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1, const double* tf2,
+                    const fclgpu_collision_request* request, int32_t* num_contacts, fclgpu_contact* contacts,
+                    int64_t contact_capacity, int64_t* contact_offsets, uint32_t* n_bv, uint32_t* n_leaf, void* stream,
+                    const CollideExtra& X) {
   if (!m1 || !m2 || !request || n < 0) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL model/request or n<0");
   if (m1->device != m2->device) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "models live on different devices");
   if (request->enable_cost) return fail(FCLGPU_ERR_UNSUPPORTED_FUNCTION, "cost sources are not supported on this path");
@@ -742,7 +779,7 @@ extern "C" int fclgpu_collide_batch(const fclgpu_model* m1, const fclgpu_model* 
     const long long nblk = (chunk + kScanBlock - 1) / kScanBlock;
     rc = ensure(&w->scan_tmp, &w->scan_bytes, (size_t)(chunk + nblk) * sizeof(long long));
     if (rc) return rc;
-    CUDA_TRY(cudaMemsetAsync(w->scan_base, 0, sizeof(long long), st));
+    if (!X.continue_scan) CUDA_TRY(cudaMemsetAsync(w->scan_base, 0, sizeof(long long), st));
   }
 
   for (long long s = 0; s < n; s += chunk) {
@@ -762,6 +799,9 @@ extern "C" int fclgpu_collide_batch(const fclgpu_model* m1, const fclgpu_model* 
     P.n_leaf = n_leaf ? n_leaf + s : nullptr;
     P.work_counter = next_counter(w, st);
     P.status = w->status;
+    P.ready = X.ready;
+    P.ready_shift = X.ready_shift;
+    P.ready_q0 = X.ready_q0 + s;
     const long long trav = opt("traversal");
     const int trig = (int)opt("leaf_trigger");
     if (trav >= 2 && !P.enable_contact && (trav == 2 || !opt("binary_pooled"))) {
@@ -808,6 +848,7 @@ extern "C" int fclgpu_collide_batch(const fclgpu_model* m1, const fclgpu_model* 
   CUDA_TRY(cudaGetLastError());
   return FCLGPU_OK;
 }
+}  // namespace
 
 // ------------------------------------------------------------------------------------------
 // distance
@@ -874,6 +915,7 @@ extern "C" int fclgpu_sync_status(int device, void* stream) {
     CUDA_TRY(cudaMemset(w->status, 0, sizeof(int)));
     return fail(s, s == FCLGPU_ERR_CONTACT_OVERFLOW ? "contact capacity exceeded (counts are exact; raise contact "
                                                       "capacity or the contact_stride option)"
+                   : s == FCLGPU_ERR_INPUT_STALLED  ? "a pose chunk did not reach the device in time (host API input stream)"
                                                     : "traversal stack overflow");
   }
   return FCLGPU_OK;
@@ -913,34 +955,127 @@ extern "C" int fclgpu_collide_batch_host(const fclgpu_model* m1, const fclgpu_mo
   Workspace* w;
   int rc = get_ws(m1->device, &w);
   if (rc) return rc;
+  std::lock_guard<std::mutex> host_lock(w->host_mu);
   const bool want = contacts != nullptr || contact_offsets != nullptr;
   if (contacts == nullptr) contact_capacity = 0;
-  if (!want && n > 0) {  // counts / verdicts only: chunked two-stream pipeline (see the distance wrapper)
-    const size_t C = (size_t)std::min<int64_t>(n, host_chunk());
-    const size_t per_stage = (tf1 ? padded(96 * C) : 0) + (tf2 ? padded(96 * C) : 0) + 3 * padded(4 * C) + 256;
+  if (!want && n > 0) {
+    // Counts / verdicts only.  ONE persistent launch over the whole batch on the compute stream while the copy
+    // stream brings the poses up chunk by chunk; behind every chunk it writes ready[c] (a 4-byte DMA from a pinned
+    // word -- not a memset, which could need an SM the spinning kernel holds), and lanes that fetch a query of a
+    // chunk still in flight wait on that flag.  No per-chunk launch tails, copies fully overlapped.
+    int shift = 10;
+    while ((1ll << (shift + 1)) <= host_chunk()) ++shift;
+    while (((n + (1ll << shift) - 1) >> shift) > kReadySlots) ++shift;
+    const int64_t C = 1ll << shift;
+    const int nchunks = (int)((n + C - 1) / C);
+    const size_t bytes = (tf1 ? padded(96 * (size_t)n) : 0) + (tf2 ? padded(96 * (size_t)n) : 0) + 3 * padded(4 * (size_t)n) + 256;
     {
       std::lock_guard<std::mutex> lock(w->mu);
-      rc = ensure(&w->dev_io, &w->dev_io_bytes, 2 * per_stage);
+      rc = ensure(&w->dev_io, &w->dev_io_bytes, bytes);
       if (rc) return rc;
     }
-    int stage = 0;
-    for (int64_t s = 0; s < n; s += (int64_t)C, stage ^= 1) {
-      const size_t cn = (size_t)std::min<int64_t>((int64_t)C, n - s);
-      cudaStream_t st = w->pipe[stage];
-      DevBuf B{(char*)w->dev_io + stage * per_stage};
-      double* d_tf1 = tf1 ? B.take<double>(12 * C) : nullptr;
-      double* d_tf2 = tf2 ? B.take<double>(12 * C) : nullptr;
-      int32_t* d_cnt = B.take<int32_t>(C);
-      uint32_t* d_bv = n_bv ? B.take<uint32_t>(C) : nullptr;
-      uint32_t* d_leaf = n_leaf ? B.take<uint32_t>(C) : nullptr;
-      if (tf1) CUDA_TRY(cudaMemcpyAsync(d_tf1, tf1 + 12 * s, 96 * cn, cudaMemcpyHostToDevice, st));
-      if (tf2) CUDA_TRY(cudaMemcpyAsync(d_tf2, tf2 + 12 * s, 96 * cn, cudaMemcpyHostToDevice, st));
-      rc = fclgpu_collide_batch(m1, m2, (int64_t)cn, d_tf1, d_tf2, request, d_cnt, nullptr, 0, nullptr, d_bv, d_leaf, st);
-      if (rc) return rc;
-      CUDA_TRY(cudaMemcpyAsync(num_contacts + s, d_cnt, 4 * cn, cudaMemcpyDeviceToHost, st));
-      if (n_bv) CUDA_TRY(cudaMemcpyAsync(n_bv + s, d_bv, 4 * cn, cudaMemcpyDeviceToHost, st));
-      if (n_leaf) CUDA_TRY(cudaMemcpyAsync(n_leaf + s, d_leaf, 4 * cn, cudaMemcpyDeviceToHost, st));
+    DevBuf B{(char*)w->dev_io};
+    double* d_tf1 = tf1 ? B.take<double>(12 * (size_t)n) : nullptr;
+    double* d_tf2 = tf2 ? B.take<double>(12 * (size_t)n) : nullptr;
+    int32_t* d_cnt = B.take<int32_t>((size_t)n);
+    uint32_t* d_bv = n_bv ? B.take<uint32_t>((size_t)n) : nullptr;
+    uint32_t* d_leaf = n_leaf ? B.take<uint32_t>((size_t)n) : nullptr;
+    cudaStream_t copy = w->pipe[0], compute = w->pipe[1];
+    CUDA_TRY(cudaMemsetAsync(w->ready, 0, sizeof(unsigned) * nchunks, copy));
+    CUDA_TRY(cudaEventRecord(w->ev[0], copy));
+    CUDA_TRY(cudaStreamWaitEvent(compute, w->ev[0], 0));  // the kernel must not see flags of an earlier call
+    for (int c = 0; c < nchunks; ++c) {
+      const int64_t s = (int64_t)c * C;
+      const size_t cn = (size_t)std::min<int64_t>(C, n - s);
+      if (tf1) CUDA_TRY(cudaMemcpyAsync(d_tf1 + 12 * s, tf1 + 12 * s, 96 * cn, cudaMemcpyHostToDevice, copy));
+      if (tf2) CUDA_TRY(cudaMemcpyAsync(d_tf2 + 12 * s, tf2 + 12 * s, 96 * cn, cudaMemcpyHostToDevice, copy));
+      CUDA_TRY(cudaMemcpyAsync(w->ready + c, w->host_one, sizeof(unsigned), cudaMemcpyHostToDevice, copy));
     }
+    CollideExtra X;
+    X.ready = w->ready;
+    X.ready_shift = shift;
+    rc = collide_enqueue(m1, m2, n, d_tf1, d_tf2, request, d_cnt, nullptr, 0, nullptr, d_bv, d_leaf, compute, X);
+    if (rc) {
+      cudaStreamSynchronize(copy);  // never leave a kernel waiting for copies that are not coming
+      return rc;
+    }
+    CUDA_TRY(cudaMemcpyAsync(num_contacts, d_cnt, 4 * (size_t)n, cudaMemcpyDeviceToHost, compute));
+    if (n_bv) CUDA_TRY(cudaMemcpyAsync(n_bv, d_bv, 4 * (size_t)n, cudaMemcpyDeviceToHost, compute));
+    if (n_leaf) CUDA_TRY(cudaMemcpyAsync(n_leaf, d_leaf, 4 * (size_t)n, cudaMemcpyDeviceToHost, compute));
+    return finish_pipeline(w, m1->device);
+  }
+  if (want && n > 0 && request->num_max_contacts > 0) {
+    // Contacts wanted.  The result can be gigabytes (64 B per contact), so the copy back is the long pole: the
+    // batch runs as sub-batches that append to one contact array (continue_scan), and while sub-batch k computes
+    // the copy stream brings sub-batch k-1's contact range down.  The host learns each range from the running
+    // total, read back behind the sub-batch.  Poses go up on the copy stream ahead of everything, flagged per
+    // chunk like in the counts-only path.
+    int shift = 10;
+    while ((1ll << (shift + 1)) <= host_chunk()) ++shift;
+    while (((n + (1ll << shift) - 1) >> shift) > kTotalSlots) ++shift;
+    const int64_t C = 1ll << shift;
+    const int nsub = (int)((n + C - 1) / C);
+    const size_t bytes = (tf1 ? padded(96 * (size_t)n) : 0) + (tf2 ? padded(96 * (size_t)n) : 0) + padded(4 * (size_t)n) +
+                         padded(8 * (size_t)(n + 1)) + padded(64 * (size_t)contact_capacity) +
+                         (n_bv ? padded(4 * (size_t)n) : 0) + (n_leaf ? padded(4 * (size_t)n) : 0) + 256;
+    {
+      std::lock_guard<std::mutex> lock(w->mu);
+      rc = ensure(&w->dev_io, &w->dev_io_bytes, bytes);
+      if (rc) return rc;
+    }
+    DevBuf B{(char*)w->dev_io};
+    double* d_tf1 = tf1 ? B.take<double>(12 * (size_t)n) : nullptr;
+    double* d_tf2 = tf2 ? B.take<double>(12 * (size_t)n) : nullptr;
+    int32_t* d_cnt = B.take<int32_t>((size_t)n);
+    int64_t* d_off = B.take<int64_t>((size_t)n + 1);
+    fclgpu_contact* d_con = contact_capacity > 0 ? B.take<fclgpu_contact>((size_t)contact_capacity) : nullptr;
+    uint32_t* d_bv = n_bv ? B.take<uint32_t>((size_t)n) : nullptr;
+    uint32_t* d_leaf = n_leaf ? B.take<uint32_t>((size_t)n) : nullptr;
+    cudaStream_t copy = w->pipe[0], compute = w->pipe[1];
+    CUDA_TRY(cudaMemsetAsync(w->ready, 0, sizeof(unsigned) * nsub, copy));
+    CUDA_TRY(cudaEventRecord(w->ev[0], copy));
+    CUDA_TRY(cudaStreamWaitEvent(compute, w->ev[0], 0));
+    for (int c = 0; c < nsub; ++c) {
+      const int64_t s = (int64_t)c * C;
+      const size_t cn = (size_t)std::min<int64_t>(C, n - s);
+      if (tf1) CUDA_TRY(cudaMemcpyAsync(d_tf1 + 12 * s, tf1 + 12 * s, 96 * cn, cudaMemcpyHostToDevice, copy));
+      if (tf2) CUDA_TRY(cudaMemcpyAsync(d_tf2 + 12 * s, tf2 + 12 * s, 96 * cn, cudaMemcpyHostToDevice, copy));
+      CUDA_TRY(cudaMemcpyAsync(w->ready + c, w->host_one, sizeof(unsigned), cudaMemcpyHostToDevice, copy));
+    }
+    int64_t done = 0;  // contacts already on their way to the host
+    auto drain = [&](int k) -> int {  // copy sub-batch k's contact range once its running total is known
+      CUDA_TRY(cudaEventSynchronize(w->ev[k & 1]));
+      const int64_t upto = std::min<int64_t>(w->host_totals[k], contact_capacity);
+      if (contacts && upto > done)
+        CUDA_TRY(cudaMemcpyAsync(contacts + done, d_con + done, 64 * (size_t)(upto - done), cudaMemcpyDeviceToHost, copy));
+      done = std::max(done, upto);
+      return 0;
+    };
+    for (int k = 0; k < nsub; ++k) {
+      const int64_t s = (int64_t)k * C;
+      const int64_t cn = std::min<int64_t>(C, n - s);
+      CollideExtra X;
+      X.ready = w->ready;
+      X.ready_shift = shift;
+      X.ready_q0 = s;
+      X.continue_scan = k > 0;
+      rc = collide_enqueue(m1, m2, cn, d_tf1 ? d_tf1 + 12 * s : nullptr, d_tf2 ? d_tf2 + 12 * s : nullptr, request,
+                           d_cnt + s, d_con, contact_capacity, d_off + s, d_bv ? d_bv + s : nullptr,
+                           d_leaf ? d_leaf + s : nullptr, compute, X);
+      if (rc) {
+        cudaStreamSynchronize(copy);
+        cudaStreamSynchronize(compute);
+        return rc;
+      }
+      CUDA_TRY(cudaMemcpyAsync(w->host_totals + k, w->scan_base, sizeof(long long), cudaMemcpyDeviceToHost, compute));
+      CUDA_TRY(cudaEventRecord(w->ev[k & 1], compute));
+      if (k >= 1 && (rc = drain(k - 1))) return rc;
+    }
+    CUDA_TRY(cudaMemcpyAsync(num_contacts, d_cnt, 4 * (size_t)n, cudaMemcpyDeviceToHost, compute));
+    if (contact_offsets) CUDA_TRY(cudaMemcpyAsync(contact_offsets, d_off, 8 * (size_t)(n + 1), cudaMemcpyDeviceToHost, compute));
+    if (n_bv) CUDA_TRY(cudaMemcpyAsync(n_bv, d_bv, 4 * (size_t)n, cudaMemcpyDeviceToHost, compute));
+    if (n_leaf) CUDA_TRY(cudaMemcpyAsync(n_leaf, d_leaf, 4 * (size_t)n, cudaMemcpyDeviceToHost, compute));
+    if ((rc = drain(nsub - 1))) return rc;
     return finish_pipeline(w, m1->device);
   }
   size_t bytes = (tf1 ? padded(96 * (size_t)n) : 0) + (tf2 ? padded(96 * (size_t)n) : 0) + padded(4 * (size_t)n) +
@@ -990,6 +1125,7 @@ extern "C" int fclgpu_distance_batch_host(const fclgpu_model* m1, const fclgpu_m
   Workspace* w;
   int rc = get_ws(m1->device, &w);
   if (rc) return rc;
+  std::lock_guard<std::mutex> host_lock(w->host_mu);
   if (n == 0) return FCLGPU_OK;
   // Chunked two-stream pipeline: while chunk c computes, chunk c+1's poses go up and chunk
   // c-1's results come down (the copies are asynchronous when the caller's buffers are pinned).

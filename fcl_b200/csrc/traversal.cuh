@@ -157,7 +157,33 @@ struct CollideParams {
   uint32_t* n_leaf;           // optional
   unsigned long long* work_counter;
   int* status;                // sticky device status (0 ok)
+  // streamed input (host API): poses of queries [c << ready_shift, (c + 1) << ready_shift) may be read once
+  // ready[c] != 0; the copy stream sets the flag right behind chunk c's copy.  nullptr = everything is resident.
+  const unsigned* ready;
+  int ready_shift;
+  long long ready_q0;  // index of query 0 of this launch in the flagged batch
 };
+
+// Spin until the chunk that holds query q has landed.  Acquire load: the pose loads that follow cannot be
+// hoisted above it.  Chunks are multiples of four poses (3 cache lines), so no line is shared between chunks.
+// The wait is bounded (kReadyTimeoutNs): if the copies never arrive the kernel reports it instead of hanging.
+constexpr unsigned long long kReadyTimeoutNs = 4000000000ull;
+__device__ __forceinline__ bool wait_ready(const unsigned* ready, int shift, long long q) {
+  if (ready == nullptr || q < 0) return true;
+  const unsigned* f = ready + (q >> shift);
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+  if (v) return true;
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (true) {
+    __nanosleep(256);
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    if (v) return true;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > kReadyTimeoutNs) return false;
+  }
+}
 
 // ---------------------------------------------------------------------------------------
 // Variant T (thread per query, persistent lanes): every lane runs the reference's depth-first
@@ -189,6 +215,7 @@ __global__ void __launch_bounds__(128) collide_thread_kernel(CollideParams P) {
       q = -1;
     }
     const long long nq = fetch_work(need, P.work_counter);
+    if (nq >= 0 && nq < P.n && !wait_ready(P.ready, P.ready_shift, nq + P.ready_q0)) atomicMin(P.status, (int)FCLGPU_ERR_INPUT_STALLED);
     if (need) {
       if (nq < P.n) {
         q = nq;
@@ -861,6 +888,7 @@ collide_deferred_kernel(CollideParams P, int leaf_trigger) {
       q = -1;
     }
     const long long nq = fetch_work(need, P.work_counter);
+    if (nq >= 0 && nq < P.n && !wait_ready(P.ready, P.ready_shift, nq + P.ready_q0)) atomicMin(P.status, (int)FCLGPU_ERR_INPUT_STALLED);
     if (need) {
       if (nq < P.n) {
         q = nq;
@@ -1083,6 +1111,7 @@ __global__ void __launch_bounds__(128, FCLGPU_POOLED_MINBLOCKS) collide_pooled_k
       q = -1;
     }
     const long long nq = fetch_work(need, P.work_counter);
+    if (nq >= 0 && nq < P.n && !wait_ready(P.ready, P.ready_shift, nq + P.ready_q0)) atomicMin(P.status, (int)FCLGPU_ERR_INPUT_STALLED);
     if (need) {
       if (nq < P.n) {
         q = nq;

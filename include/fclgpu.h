@@ -51,7 +51,8 @@ typedef enum fclgpu_status {
   FCLGPU_ERR_NO_DEVICE = -21,
   FCLGPU_ERR_CUDA = -22,
   FCLGPU_ERR_CONTACT_OVERFLOW = -23, /* per-pose or pool capacity too small; counts are still exact */
-  FCLGPU_ERR_STACK_OVERFLOW = -24    /* traversal stack exhausted (tree deeper than supported) */
+  FCLGPU_ERR_STACK_OVERFLOW = -24,   /* traversal stack exhausted (tree deeper than supported) */
+  FCLGPU_ERR_INPUT_STALLED = -25     /* host API: a pose chunk did not reach the device within the kernel's wait budget */
 } fclgpu_status;
 
 /* Split rules of the reference's BVSplitter (include/fcl/geometry/bvh/detail/BV_splitter.h). */

@@ -418,3 +418,37 @@ def test_device_build_rejects_what_the_reference_rejects():
     assert L.fclgpu_model_build_obbrss(0, v.ctypes.data, 3, t.ctypes.data, 0, 0, C.byref(h)) == F.BVH_ERR_BUILD_EMPTY_MODEL
     t[0, 2] = 2
     assert L.fclgpu_model_build_obbrss(0, v.ctypes.data, 3, t.ctypes.data, 1, 1, C.byref(h)) == F.BVH_ERR_UNSUPPORTED_FUNCTION
+
+
+@pytest.mark.parametrize("host_chunk", [4096, 1 << 17])
+def test_host_api_pinned_pipelines_match_oracle(oracle, env_rob_npz, host_chunk):
+    """The host API with page-locked buffers (truly asynchronous copies): streamed-input single launch for
+    verdicts, sub-batch pipeline with overlapped contact download, chunked distance pipeline.  Small chunks
+    force many chunks / sub-batches per call."""
+    import torch
+
+    (ev, et), (rv, rt) = env_rob_npz
+    env, rob = F.BVHModel.from_arrays(ev, et), F.BVHModel.from_arrays(rv, rt)
+    oenv, orob = oracle.Model(ev, et), oracle.Model(rv, rt)
+    n = 30000
+    P = torch.from_numpy(random_poses(n, seed=29)).pin_memory().numpy()
+    _capi.set_option("host_chunk", host_chunk)
+    try:
+        for rep in range(2):  # second call reuses flags / staging of the first
+            got = F.collide_batch(env, P, rob, None, F.CollisionRequest(), want_contacts=False, pinned=True)
+            ref = oracle.collide_batch(oenv, orob, P, None, 1, False, nthreads=8)
+            assert np.array_equal(got.num_contacts, ref["counts"])
+            gc = F.collide_batch(env, P, rob, None, F.CollisionRequest(20, True), contact_capacity=20 * n, pinned=True)
+            rc = oracle.collide_batch(oenv, orob, P, None, 20, True, nthreads=8)
+            assert np.array_equal(gc.num_contacts, rc["counts"])
+            assert np.array_equal(gc.offsets, rc["offsets"])
+            assert gc.contacts.tobytes() == rc["contacts"].tobytes()
+            gd = F.distance_batch(env, P, rob, None, F.DistanceRequest(True), pinned=True)
+            rd = oracle.distance_batch(oenv, orob, P, None, True, 2, nthreads=8)
+            assert np.array_equal(gd.min_distance, rd["min_distance"])
+        # capacity overflow keeps the counts exact and reports the status
+        with pytest.raises(F.FclGpuError) as ei:
+            F.collide_batch(env, P, rob, None, F.CollisionRequest(20, True), contact_capacity=1000, pinned=True)
+        assert ei.value.code == _capi.ERR_CONTACT_OVERFLOW
+    finally:
+        _capi.set_option("host_chunk", 1 << 17)

@@ -23,10 +23,12 @@ for _ in range(5):
     out.copy_(torch.empty(n, dtype=torch.int32, device="cuda"), non_blocking=True)
 torch.cuda.synchronize(); print("pinned D2H 4 MB: %.2f ms" % ((time.perf_counter() - t0) / 5 * 1e3))
 P = Ph.numpy()
-for chunk in (1 << 15, 1 << 16, 1 << 17, 1 << 18, 1 << 19, 1 << 20):
+for chunk in (1 << 14, 1 << 15, 1 << 16, 1 << 17, 1 << 18, 1 << 19):
     _capi.set_option("host_chunk", chunk)
-    for wl in ("collide", "distance"):
-        f = (lambda: F.collide_batch(env, P, rob, None, F.CollisionRequest(), want_contacts=False, pinned=True)) if wl == "collide" else (lambda: F.distance_batch(env, P, rob, None, F.DistanceRequest(True), pinned=True))
+    for wl in ("collide", "contacts", "distance"):
+        f = {"collide": lambda: F.collide_batch(env, P, rob, None, F.CollisionRequest(), want_contacts=False, pinned=True),
+             "contacts": lambda: F.collide_batch(env, P, rob, None, F.CollisionRequest(100, True), contact_capacity=40 * n, pinned=True),
+             "distance": lambda: F.distance_batch(env, P, rob, None, F.DistanceRequest(True), pinned=True)}[wl]
         f(); f()
         t0 = time.perf_counter()
         for _ in range(3):
