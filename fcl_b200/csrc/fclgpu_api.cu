@@ -63,6 +63,7 @@ std::map<std::string, long long> g_opts = {
     // 1: collide = thread per query with deferred leaf rounds, distance = warp per query sorted front, FP64 BV tests
     // 0: thread per query, the reference's visiting order exactly (work counters match the reference's)
     {"traversal", 3},
+    {"dist_spill_entries", 4096},  // per-warp global overflow entries of the distance front (allocated for big models)
     {"host_chunk", 1 << 17},   // queries per stage of the host API's two-stream copy/compute pipeline
     {"contact_stride", 1024},  // per-query contact scratch slots when num_max_contacts is larger
     {"scratch_bytes", 2ll << 30},
@@ -100,6 +101,9 @@ struct Workspace {
   void* dev_io = nullptr;
   size_t dev_io_bytes = 0;
   cudaStream_t pipe[2] = {nullptr, nullptr};
+  uint2* spill_pair = nullptr;    // distance kernel: per-warp overflow area of the sorted front (deep trees)
+  float* spill_bound = nullptr;
+  int spill_cap = 0;
   unsigned* ready = nullptr;      // device: per-chunk "input has landed" flags of the streamed host path
   unsigned* host_one = nullptr;   // pinned host word (= 1) the copy stream writes into ready[c]
   long long* host_totals = nullptr;  // pinned: running contact totals read back per sub-batch
@@ -884,10 +888,37 @@ extern "C" int fclgpu_distance_batch(const fclgpu_model* m1, const fclgpu_model*
   P.n_leaf = n_leaf;
   P.work_counter = next_counter(w, st);
   P.status = w->status;
+  P.spill_pair = nullptr;
+  P.spill_bound = nullptr;
+  P.spill_cap = 0;
+  P.spill_warps = 0;
+  if ((long long)m1->d.n_nodes + m2->d.n_nodes >= (1 << 17) && opt("dist_spill_entries") >= kSpillBlock) {
+    // big models: the sorted front may outgrow its shared-memory stack; give every warp of the largest
+    // possible grid an overflow area in HBM (12 bytes per entry)
+    const int cap = (int)opt("dist_spill_entries");
+    if (w->spill_cap != cap) {
+      if (w->spill_pair) CUDA_TRY(cudaFree(w->spill_pair));
+      if (w->spill_bound) CUDA_TRY(cudaFree(w->spill_bound));
+      w->spill_pair = nullptr;
+      w->spill_bound = nullptr;
+      w->spill_cap = 0;
+      const size_t warps = (size_t)w->sm_count * 8 * kDistWarps;  // up to 8 resident blocks per SM
+      CUDA_TRY(cudaMalloc((void**)&w->spill_pair, warps * cap * sizeof(uint2)));
+      CUDA_TRY(cudaMalloc((void**)&w->spill_bound, warps * cap * sizeof(float)));
+      w->spill_cap = cap;
+    }
+    P.spill_pair = w->spill_pair;
+    P.spill_bound = w->spill_bound;
+    P.spill_cap = cap;
+    P.spill_warps = w->sm_count * 8 * kDistWarps;
+  }
   const bool stats = (n_bv || n_leaf);
   const long long trav = opt("traversal");
   const size_t front_smem = sizeof(WarpFront) * kDistWarps;
-  if (trav >= 2) {
+  if (trav >= 2 && P.spill_pair) {
+    rc = stats ? launch_persistent(distance_warp_kernel<true, true, true>, P, w, kDistWarps * 32, st, front_smem)
+               : launch_persistent(distance_warp_kernel<false, true, true>, P, w, kDistWarps * 32, st, front_smem);
+  } else if (trav >= 2) {
     rc = stats ? launch_persistent(distance_warp_kernel<true, true>, P, w, kDistWarps * 32, st, front_smem)
                : launch_persistent(distance_warp_kernel<false, true>, P, w, kDistWarps * 32, st, front_smem);
   } else if (trav == 1) {

@@ -331,6 +331,11 @@ struct DistanceParams {
   uint32_t* n_leaf;
   unsigned long long* work_counter;
   int* status;
+  // overflow area of the sorted-front kernel (deep trees): spill_cap entries per warp, or nullptr
+  uint2* spill_pair;
+  float* spill_bound;
+  int spill_cap;
+  int spill_warps;  // warps the area was sized for
 };
 
 struct DistState {
@@ -499,6 +504,7 @@ __device__ __noinline__ double tri_distance_outofline(const V3* Sv, const V3* Tv
 
 constexpr int kDistPop = 16;         // entries expanded per BV round (2 lanes each)
 constexpr int kDistStackCap = 512;   // entries per warp
+constexpr int kSpillBlock = 256;     // entries moved to / from the global overflow area at a time
 constexpr int kLeafCap = 64;
 constexpr int kLeafTrigger = 32;
 constexpr int kDistWarps = 4;        // warps per block
@@ -551,7 +557,9 @@ __device__ __forceinline__ unsigned warp_sort_keys(unsigned key, int lane) {
 #ifndef FCLGPU_DIST_MINBLOCKS
 #define FCLGPU_DIST_MINBLOCKS 5
 #endif
-template <bool kStats, bool kBound32>
+// kSpill: instantiation with the global overflow area for deep trees (kept out of the default instantiation:
+// the extra live state costs the hot loop 10 %)
+template <bool kStats, bool kBound32, bool kSpill = false>
 __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distance_warp_kernel(DistanceParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WarpFront& S = reinterpret_cast<WarpFront*>(smem_raw)[threadIdx.x >> 5];
@@ -597,7 +605,39 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
     }
     __syncwarp();
 
+    int gsp = 0;  // entries parked in the warp's global overflow area
+    const int gwarp = blockIdx.x * kDistWarps + (threadIdx.x >> 5);
+    const bool can_spill = kSpill && P.spill_pair != nullptr && gwarp < P.spill_warps;
+    uint2* const g_pair = can_spill ? P.spill_pair + (size_t)gwarp * P.spill_cap : nullptr;
+    float* const g_bound = can_spill ? P.spill_bound + (size_t)gwarp * P.spill_cap : nullptr;
+
     while (true) {
+      if (kSpill && sp == 0 && gsp > 0) {
+        // refill: bring the most recently parked block back (oldest first, so the stack order is kept),
+        // dropping what the minimum found meanwhile has made irrelevant
+        const int take = gsp < kSpillBlock ? gsp : kSpillBlock;
+        gsp -= take;
+        for (int base = 0; base < take; base += 32) {
+          const int i = base + lane;
+          uint2 pr = make_uint2(0u, 0u);
+          float bd = 0.0f;
+          bool live = false;
+          if (i < take) {
+            pr = g_pair[gsp + i];
+            bd = g_bound[gsp + i];
+            live = bd < min_f;
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, live);
+          if (live) {
+            const int pos = sp + __popc(m & lt_mask);
+            S.pair[pos] = pr;
+            S.bound[pos] = bd;
+          }
+          sp += __popc(m);
+        }
+        __syncwarp();
+        continue;
+      }
       // the screening round may add up to min(nraw, 32) pairs to the exact queue: only run it when they fit
       // (otherwise the exact queue is at least half full and the exact round below drains it first)
       const bool can_screen = kBound32 && kScreenLeaves && nraw > 0 && (nleaf + (nraw < 32 ? nraw : 32) <= kLeafCap);
@@ -732,12 +772,39 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
       const unsigned im = __ballot_sync(0xffffffffu, internal);
       const int n_int = __popc(im), rank = __popc(im & lt_mask);
       sp -= k;
+      if (kSpill && kDistStackCap - sp - n_int < kDistPop && g_pair != nullptr && sp >= kSpillBlock && gsp + kSpillBlock <= P.spill_cap) {
+        // The front no longer fits (deep trees): park the bottom of the stack -- the farthest, oldest candidates --
+        // in the warp's global overflow area and slide the rest down.
+        for (int base = 0; base < kSpillBlock; base += 32) {
+          g_pair[gsp + base + lane] = S.pair[base + lane];
+          g_bound[gsp + base + lane] = S.bound[base + lane];
+        }
+        gsp += kSpillBlock;
+        __syncwarp();
+        for (int base = kSpillBlock; base < sp; base += 32) {
+          const int i = base + lane;
+          uint2 pr2 = make_uint2(0u, 0u);
+          float bd2 = 0.0f;
+          if (i < sp) {
+            pr2 = S.pair[i];
+            bd2 = S.bound[i];
+          }
+          __syncwarp();
+          if (i < sp) {
+            S.pair[i - kSpillBlock] = pr2;
+            S.bound[i - kSpillBlock] = bd2;
+          }
+        }
+        sp -= kSpillBlock;
+        __syncwarp();
+      }
       int n_exp = n_int < kDistPop ? n_int : kDistPop;
       const int room = kDistStackCap - sp - n_int;  // after re-pushing the leftovers, 2*n_exp children minus n_exp must fit
       if (n_exp > room) n_exp = room;
       if (n_int > 0 && n_exp <= 0) {
         if (lane == 0) atomicMin(P.status, (int)FCLGPU_ERR_STACK_OVERFLOW);
         sp = 0;
+        gsp = 0;
         nleaf = 0;
         nraw = 0;
         break;

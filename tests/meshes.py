@@ -5,29 +5,23 @@ import numpy as np
 def uv_sphere(radius, seg=16, ring=16, center=(0.0, 0.0, 0.0)):
     """Tessellated sphere in the spirit of generateBVHModel(Sphere, seg, ring)
     (include/fcl/geometry/geometric_shape_to_BVH_model-inl.h): ring latitudes x seg longitudes."""
-    verts = []
-    for i in range(1, ring):
-        theta = np.pi * i / ring
-        for j in range(seg):
-            phi = 2 * np.pi * j / seg
-            verts.append([radius * np.sin(theta) * np.cos(phi), radius * np.sin(theta) * np.sin(phi), radius * np.cos(theta)])
-    top = len(verts)
-    verts.append([0, 0, radius])
-    bot = len(verts)
-    verts.append([0, 0, -radius])
-    tris = []
-    for j in range(seg):
-        tris.append([top, j, (j + 1) % seg])
-        base = (ring - 2) * seg
-        tris.append([bot, base + (j + 1) % seg, base + j])
-    for i in range(ring - 2):
-        for j in range(seg):
-            a = i * seg + j
-            b = i * seg + (j + 1) % seg
-            c = (i + 1) * seg + j
-            d = (i + 1) * seg + (j + 1) % seg
-            tris.append([a, c, b])
-            tris.append([b, c, d])
+    i = np.arange(1, ring, dtype=np.float64)[:, None]
+    j = np.arange(seg, dtype=np.float64)[None, :]
+    theta, phi = np.pi * i / ring, 2 * np.pi * j / seg
+    body = np.stack([radius * np.sin(theta) * np.cos(phi), radius * np.sin(theta) * np.sin(phi),
+                     np.broadcast_to(radius * np.cos(theta), (ring - 1, seg))], axis=-1).reshape(-1, 3)
+    top = len(body)
+    bot = top + 1
+    verts = np.concatenate([body, [[0, 0, radius]], [[0, 0, -radius]]])
+    jj = np.arange(seg)
+    jn = (jj + 1) % seg
+    base = (ring - 2) * seg
+    caps = np.stack([np.stack([np.full(seg, top), jj, jn], axis=1), np.stack([np.full(seg, bot), base + jn, base + jj], axis=1)],
+                    axis=1).reshape(-1, 3)
+    ii = np.arange(ring - 2)[:, None] * seg
+    a, bq, c, d = ii + jj[None, :], ii + jn[None, :], ii + seg + jj[None, :], ii + seg + jn[None, :]
+    quads = np.stack([np.stack([a, c, bq], axis=-1), np.stack([bq, c, d], axis=-1)], axis=2).reshape(-1, 3)
+    tris = np.concatenate([caps, quads])
     v = np.asarray(verts, dtype=np.float64) + np.asarray(center, dtype=np.float64)
     return v, np.asarray(tris, dtype=np.int32)
 

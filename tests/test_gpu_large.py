@@ -69,3 +69,40 @@ def test_cfg5_two_large_meshes(oracle):
                          grow_on_overflow=True)
     rc = oracle.collide_batch(OA, OB, identity_poses(200), P[sub], INT_MAX, True, nthreads=8)
     assert np.array_equal(gc.num_contacts, rc["counts"]) and gc.contacts.tobytes() == rc["contacts"].tobytes()
+
+
+def test_cfg5_full_size_one_million_triangles(oracle):
+    """BASELINE cfg5 at its real size: two ~1M-triangle meshes (2M-node BVHs, 0.5 GB of node records each),
+    built ON the device; every node record equals the oracle's builder output byte for byte, then collide +
+    distance agree with the oracle on a pose sample."""
+    va, ta = noisy_sphere(1.0, 710, 705, seed=21)  # 999,680 triangles
+    vb, tb = noisy_sphere(1.0, 710, 705, seed=22)
+    A = F.BVHModel.from_arrays(va, ta, build_on_device=True)
+    B = F.BVHModel.from_arrays(vb, tb, build_on_device=True)
+    OA, OB = oracle.Model(va, ta), oracle.Model(vb, tb)
+    assert A.num_tris > 990000 and A.getNumBVs() == OA.num_bvs
+    dev, ref = A.node_arrays(), OA.arrays()
+    assert np.array_equal(dev["first_child"], ref["first_child"])
+    for k in ("axis", "obb_To", "obb_ext", "rss_To", "rss_l", "rss_r"):
+        assert dev[k].tobytes() == ref[k].tobytes(), k
+    del dev, ref
+    rng = np.random.default_rng(6)
+    n = 600
+    ang = rng.uniform(0, 2 * np.pi, size=(n, 3))
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    P = np.empty((n, 12))
+    P[:, :9] = euler_to_matrix(ang[:, 0], ang[:, 1], ang[:, 2]).reshape(n, 9)
+    P[:, 9:] = d * rng.uniform(1.6, 2.6, size=(n, 1))
+    got = F.collide_batch(A, identity_poses(n), B, P, F.CollisionRequest(), want_contacts=False)
+    ref = oracle.collide_batch(OA, OB, identity_poses(n), P, 1, False, nthreads=8)
+    assert np.array_equal(got.num_contacts, ref["counts"])
+    assert 0.1 * n < got.num_contacts.sum() < 0.9 * n
+    gd = F.distance_batch(A, identity_poses(n), B, P, F.DistanceRequest(True))
+    rd = oracle.distance_batch(OA, OB, identity_poses(n), P, True, 2, nthreads=8)
+    assert np.array_equal(gd.min_distance, rd["min_distance"])
+    sub = slice(0, 60)
+    gc = F.collide_batch(A, identity_poses(60), B, P[sub], F.CollisionRequest(INT_MAX, True), contact_capacity=60 * 4000,
+                         grow_on_overflow=True)
+    rc = oracle.collide_batch(OA, OB, identity_poses(60), P[sub], INT_MAX, True, nthreads=8)
+    assert np.array_equal(gc.num_contacts, rc["counts"]) and gc.contacts.tobytes() == rc["contacts"].tobytes()
