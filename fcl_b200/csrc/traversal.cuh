@@ -1150,14 +1150,22 @@ struct __align__(16) PoolWarp {
 #ifndef FCLGPU_POOLED_OUTOFLINE
 #define FCLGPU_POOLED_OUTOFLINE 1
 #endif
-template <bool kStats, bool kClassify32>
+// kTwo: a BV round expands an entry whose boxes are already known to overlap and tests BOTH children at once
+// (their records are fetched together: one memory latency per two box tests instead of one per test, and the two
+// child records of the split node are neighbours).  Stack entries then carry {b1 | split-first flag, b2 | single
+// flag, first_child1, first_child2}, so the expansion needs no load before it can address the children.
+// The visiting order, hence every result, is unchanged; the right child's test is merely done early (wasted
+// only when the query stops before reaching it).
+template <bool kStats, bool kClassify32, bool kTwo = false>
 __global__ void __launch_bounds__(128, FCLGPU_POOLED_MINBLOCKS) collide_pooled_kernel(CollideParams P, int leaf_trigger) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PoolWarp& S = reinterpret_cast<PoolWarp*>(smem_raw)[threadIdx.x >> 5];
   // DFS stack: the top entry lives in a register (an expanded node's left child is consumed by the very
   // next BV round), the rest in local memory; sp counts both
-  uint2 stk[kStackCap];
+  uint2 stk[kTwo ? 1 : kStackCap];
   uint2 top = make_uint2(0u, 0u);
+  uint4 stk4[kTwo ? kStackCap : 1];
+  uint4 top4 = make_uint4(0u, 0u, 0u, 0u);
   const int lane = threadIdx.x & 31;
   int sp = 0, qhead = 0, qcount = 0;
   long long q = -1;
@@ -1194,6 +1202,8 @@ __global__ void __launch_bounds__(128, FCLGPU_POOLED_MINBLOCKS) collide_pooled_k
         count = 0;
         bv_tests = leaf_tests = 0;
         top = make_uint2(0u, 0u);
+        // kTwo: a virtual parent whose only child is the root pair (split-first flag, single flag, child index 0)
+        top4 = make_uint4(0x80000000u, 0x80000000u, 0u, 0u);
         sp = 1;
       } else {
         exhausted = true;
@@ -1322,6 +1332,78 @@ __global__ void __launch_bounds__(128, FCLGPU_POOLED_MINBLOCKS) collide_pooled_k
         }
       }
       __syncwarp();
+      continue;
+    }
+
+    // ---- BV round, two children per round ----
+    if (kTwo) {
+      if (sp > 0 && qcount < kPoolFifo) {
+        const uint4 e = top4;
+        --sp;
+        bool have_top = false;
+        const bool split1 = (e.x >> 31) != 0u, single = (e.y >> 31) != 0u;
+        const int b1 = (int)(e.x & 0x7fffffffu), b2 = (int)(e.y & 0x7fffffffu);
+        const int fc1 = (int)e.z, fc2 = (int)e.w;
+        if (fc1 < 0 && fc2 < 0) {  // an overlapping leaf pair: the next triangle test in DFS order
+          S.fifo[(qhead + qcount) & (kPoolFifo - 1)][lane] = make_uint2((unsigned)(-(fc1 + 1)), (unsigned)(-(fc2 + 1)));
+          qcount++;
+        } else if (sp + 2 > kStackCap) {
+          atomicMin(P.status, (int)FCLGPU_ERR_STACK_OVERFLOW);
+          sp = 0;
+          qcount = 0;
+        } else {
+          // child A = left, child B = right; the split node's children are records ci and ci + 1
+          const int ci = split1 ? fc1 : fc2, oi = split1 ? b2 : b1;
+          const int cj = single ? ci : ci + 1;
+          const ObbRec32 A1 = load_obb32(P.m1.obb32, split1 ? ci : oi);
+          const ObbRec32 A2 = load_obb32(P.m2.obb32, split1 ? oi : ci);
+          const ObbRec32 C = load_obb32(split1 ? P.m1.obb32 : P.m2.obb32, cj);
+          int fa, fb, fo;
+          double sa, sb, so;
+          load_topo(split1 ? P.m1.topo : P.m2.topo, ci, fa, sa);
+          load_topo(split1 ? P.m1.topo : P.m2.topo, cj, fb, sb);
+          load_topo(split1 ? P.m2.topo : P.m1.topo, oi, fo, so);
+          ObbRec32 B1, B2;
+#pragma unroll
+          for (int k = 0; k < 9; ++k) {
+            B1.a[k] = split1 ? C.a[k] : A1.a[k];
+            B2.a[k] = split1 ? A2.a[k] : C.a[k];
+          }
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            B1.c[k] = split1 ? C.c[k] : A1.c[k];
+            B2.c[k] = split1 ? A2.c[k] : C.c[k];
+            B1.e[k] = split1 ? C.e[k] : A1.e[k];
+            B2.e[k] = split1 ? A2.e[k] : C.e[k];
+          }
+          B1.s = split1 ? C.s : A1.s;
+          B2.s = split1 ? A2.s : C.s;
+          const bool hitA = !obb_certainly_disjoint_f32(Rf, Tf, t_l1, A1, A2);
+          const bool hitB = !single && !obb_certainly_disjoint_f32(Rf, Tf, t_l1, B1, B2);
+          if (kStats) bv_tests += single ? 1u : 2u;
+          const bool lo = fo < 0;
+          if (hitB) {
+            const bool lb = fb < 0;
+            const uint4 eb = split1 ? make_uint4((unsigned)cj | ((lo || (!lb && sb > so)) ? 0x80000000u : 0u), (unsigned)oi, (unsigned)fb, (unsigned)fo)
+                                    : make_uint4((unsigned)oi | ((lb || (!lo && so > sb)) ? 0x80000000u : 0u), (unsigned)cj, (unsigned)fo, (unsigned)fb);
+            if (hitA) {
+              stk4[sp++] = eb;  // the slot the popped entry had; child A goes into the register
+            } else {
+              top4 = eb;
+              ++sp;
+              have_top = true;
+            }
+          }
+          if (hitA) {
+            const bool la = fa < 0;
+            top4 = split1 ? make_uint4((unsigned)ci | ((lo || (!la && sa > so)) ? 0x80000000u : 0u), (unsigned)oi, (unsigned)fa, (unsigned)fo)
+                          : make_uint4((unsigned)oi | ((la || (!lo && so > sa)) ? 0x80000000u : 0u), (unsigned)ci, (unsigned)fo, (unsigned)fa);
+            ++sp;
+            have_top = true;
+          }
+        }
+        if (!have_top && sp > 0) top4 = stk4[sp - 1];
+      }
       continue;
     }
 

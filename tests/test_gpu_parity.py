@@ -22,7 +22,7 @@ def models(env_rob_npz, oracle):
     return (F.BVHModel.from_arrays(ev, et), F.BVHModel.from_arrays(rv, rt)), (oracle.Model(ev, et), oracle.Model(rv, rt))
 
 
-@pytest.fixture(params=[0, 1, 2, 3], ids=["thread", "front64", "front32", "pooled"])
+@pytest.fixture(params=[0, 1, 2, 3, 4], ids=["thread", "front64", "front32", "pooled", "pooled2"])
 def traversal(request):
     _capi.set_option("traversal", request.param)
     yield request.param
