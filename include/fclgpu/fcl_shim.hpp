@@ -21,6 +21,7 @@
 #ifdef FCLGPU_HAVE_FCL
 #include <fcl/fcl.h>
 
+#include <algorithm>
 #include <memory>
 #include <stdexcept>
 #include <string>

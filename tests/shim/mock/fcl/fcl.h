@@ -1,0 +1,158 @@
+// MOCK of the slice of FCL's public API that include/fclgpu/fcl_shim.hpp touches -- test scaffolding only.
+// FCL and Eigen are not installed on the build image, so the shim is compile- and run-checked against
+// these stand-ins, which reproduce names, members and call signatures of the reference headers
+// (include/fcl/...): geometry/bvh/BVH_model.h:160-203 (vertices, tri_indices, num_tris, getBV, getNumBVs),
+// geometry/bvh/BV_node_base.h + BV_node.h:50-72 (first_child, bv), math/bv/OBB.h, RSS.h, OBBRSS.h (axis, To,
+// extent, l, r), math/triangle.h (operator[]), narrowphase/contact.h:48-91, collision_request.h:52-106,
+// collision_result.h (addContact / numContacts / getContact), distance_request.h:52-113,
+// distance_result.h (update overloads: only a smaller distance replaces the stored one).
+// Nothing here computes anything; it is NOT a substitute for FCL.
+#pragma once
+#include <cstddef>
+#include <limits>
+#include <vector>
+
+namespace fcl {
+
+template <typename S>
+struct Vector3 {
+  S v[3];
+  Vector3() : v{0, 0, 0} {}
+  Vector3(S x, S y, S z) : v{x, y, z} {}
+  S& operator[](int i) { return v[i]; }
+  const S& operator[](int i) const { return v[i]; }
+};
+
+template <typename S>
+struct Matrix3 {
+  S m[9];  // row-major storage; only operator()(row, col) is part of the mocked surface
+  S& operator()(int r, int c) { return m[3 * r + c]; }
+  const S& operator()(int r, int c) const { return m[3 * r + c]; }
+};
+
+// Eigen::Transform<S, 3, Isometry>: 4x4 column-major, reachable through matrix().data()
+template <typename S>
+struct Transform3 {
+  S m16[16];
+  struct MatrixView {
+    const S* p;
+    const S* data() const { return p; }
+  };
+  MatrixView matrix() const { return MatrixView{m16}; }
+  static Transform3 Identity() {
+    Transform3 t;
+    for (int i = 0; i < 16; ++i) t.m16[i] = (i % 5 == 0) ? S(1) : S(0);
+    return t;
+  }
+  void setLinear(const S* row_major9) {
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) m16[4 * c + r] = row_major9[3 * r + c];
+  }
+  void setTranslation(S x, S y, S z) { m16[12] = x; m16[13] = y; m16[14] = z; }
+};
+
+template <typename S>
+struct OBB {
+  Matrix3<S> axis;
+  Vector3<S> To, extent;
+};
+template <typename S>
+struct RSS {
+  Matrix3<S> axis;
+  Vector3<S> To;
+  S l[2];
+  S r;
+};
+template <typename S>
+struct OBBRSS {
+  OBB<S> obb;
+  RSS<S> rss;
+};
+
+struct BVNodeBase {
+  int first_child = 0, first_primitive = 0, num_primitives = 0;
+};
+template <typename BV>
+struct BVNode : BVNodeBase {
+  BV bv;
+};
+
+struct Triangle {
+  std::size_t vids[3];
+  std::size_t operator[](int i) const { return vids[i]; }
+};
+
+template <typename S>
+struct CollisionGeometry {
+  virtual ~CollisionGeometry() {}
+};
+
+template <typename BV>
+struct BVHModel : CollisionGeometry<double> {
+  Vector3<double>* vertices = nullptr;
+  Triangle* tri_indices = nullptr;
+  int num_tris = 0, num_vertices = 0;
+  int getNumBVs() const { return (int)bvs_.size(); }
+  const BVNode<BV>& getBV(int i) const { return bvs_[i]; }
+  // storage of the mock
+  std::vector<BVNode<BV>> bvs_;
+  std::vector<Vector3<double>> verts_;
+  std::vector<Triangle> tris_;
+};
+
+template <typename S>
+struct Contact {
+  const CollisionGeometry<S>* o1 = nullptr;
+  const CollisionGeometry<S>* o2 = nullptr;
+  int b1 = -1, b2 = -1;
+  Vector3<S> normal, pos;
+  S penetration_depth = 0;
+  Contact() {}
+  Contact(const CollisionGeometry<S>* a, const CollisionGeometry<S>* b, int i, int j) : o1(a), o2(b), b1(i), b2(j) {}
+  Contact(const CollisionGeometry<S>* a, const CollisionGeometry<S>* b, int i, int j, const Vector3<S>& p,
+          const Vector3<S>& n, S depth)
+      : o1(a), o2(b), b1(i), b2(j), normal(n), pos(p), penetration_depth(depth) {}
+};
+
+template <typename S>
+struct CollisionRequest {
+  std::size_t num_max_contacts = 1;
+  bool enable_contact = false;
+  std::size_t num_max_cost_sources = 1;
+  bool enable_cost = false;
+  CollisionRequest(std::size_t n = 1, bool contact = false) : num_max_contacts(n), enable_contact(contact) {}
+};
+
+template <typename S>
+struct CollisionResult {
+  void addContact(const Contact<S>& c) { contacts_.push_back(c); }
+  std::size_t numContacts() const { return contacts_.size(); }
+  const Contact<S>& getContact(std::size_t i) const { return contacts_[i]; }
+  bool isCollision() const { return !contacts_.empty(); }
+  std::vector<Contact<S>> contacts_;
+};
+
+template <typename S>
+struct DistanceRequest {
+  bool enable_nearest_points, enable_signed_distance = false;
+  S rel_err = 0, abs_err = 0;
+  explicit DistanceRequest(bool nearest = false) : enable_nearest_points(nearest) {}
+};
+
+template <typename S>
+struct DistanceResult {
+  S min_distance = std::numeric_limits<S>::max();
+  Vector3<S> nearest_points[2];
+  const CollisionGeometry<S>* o1 = nullptr;
+  const CollisionGeometry<S>* o2 = nullptr;
+  int b1 = -1, b2 = -1;
+  void update(S d, const CollisionGeometry<S>* a, const CollisionGeometry<S>* b, int i, int j) {
+    if (min_distance > d) { min_distance = d; o1 = a; o2 = b; b1 = i; b2 = j; }
+  }
+  void update(S d, const CollisionGeometry<S>* a, const CollisionGeometry<S>* b, int i, int j, const Vector3<S>& p1,
+              const Vector3<S>& p2) {
+    if (min_distance > d) { min_distance = d; o1 = a; o2 = b; b1 = i; b2 = j; nearest_points[0] = p1; nearest_points[1] = p2; }
+  }
+};
+
+}  // namespace fcl

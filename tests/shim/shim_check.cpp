@@ -1,0 +1,146 @@
+// Compile- and run-check of include/fclgpu/fcl_shim.hpp against the mock FCL API surface (tests/shim/mock).
+//   g++ -std=c++17 -Itests/shim/mock -Iinclude tests/shim/shim_check.cpp -Lfcl_b200/lib -lfclgpu -o shim_check
+// Builds two procedural meshes with the library's own host builder, exposes them through the mock
+// fcl::BVHModel<OBBRSS<double>>, runs the shim's batched collide / distance and compares every result with
+// direct C-ABI calls on the same inputs.  argv[1] = "compile-only" skips the GPU part.
+#include <fclgpu/fcl_shim.hpp>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#ifndef FCLGPU_HAVE_FCL
+#error "the mock <fcl/fcl.h> / <Eigen/Core> must be on the include path"
+#endif
+
+using Model = fcl::BVHModel<fcl::OBBRSS<double>>;
+
+static void sphere(double radius, int seg, int ring, std::vector<double>& v, std::vector<int32_t>& t) {
+  const double pi = 3.14159265358979323846;
+  for (int i = 1; i < ring; ++i)
+    for (int j = 0; j < seg; ++j) {
+      const double th = pi * i / ring, ph = 2 * pi * j / seg;
+      v.insert(v.end(), {radius * std::sin(th) * std::cos(ph), radius * std::sin(th) * std::sin(ph) * 0.7, radius * std::cos(th)});
+    }
+  const int top = (int)v.size() / 3;
+  v.insert(v.end(), {0, 0, radius});
+  const int bot = top + 1;
+  v.insert(v.end(), {0, 0, -radius});
+  for (int j = 0; j < seg; ++j) {
+    const int base = (ring - 2) * seg;
+    t.insert(t.end(), {top, j, (j + 1) % seg});
+    t.insert(t.end(), {bot, base + (j + 1) % seg, base + j});
+  }
+  for (int i = 0; i < ring - 2; ++i)
+    for (int j = 0; j < seg; ++j) {
+      const int a = i * seg + j, b = i * seg + (j + 1) % seg, c = (i + 1) * seg + j, d = (i + 1) * seg + (j + 1) % seg;
+      t.insert(t.end(), {a, c, b});
+      t.insert(t.end(), {b, c, d});
+    }
+}
+
+// fill the mock model from the library's host builder (stands in for BVHModel::endModel())
+static fclgpu_bvh* fill(Model& m, const std::vector<double>& v, const std::vector<int32_t>& t) {
+  fclgpu_bvh* b = nullptr;
+  fclgpu::check(fclgpu_bvh_build_obbrss(v.data(), (int32_t)v.size() / 3, t.data(), (int32_t)t.size() / 3, FCLGPU_SPLIT_METHOD_MEAN, &b));
+  const int n = fclgpu_bvh_num_nodes(b), nt = fclgpu_bvh_num_tris(b);
+  std::vector<int32_t> fc(n);
+  std::vector<double> ax(9 * n), oT(3 * n), oe(3 * n), rT(3 * n), rl(2 * n), rr(n);
+  fclgpu::check(fclgpu_bvh_get(b, fc.data(), ax.data(), oT.data(), oe.data(), rT.data(), rl.data(), rr.data(), nullptr));
+  m.bvs_.resize(n);
+  for (int i = 0; i < n; ++i) {
+    auto& node = m.bvs_[i];
+    node.first_child = fc[i];
+    for (int k = 0; k < 9; ++k) node.bv.obb.axis.m[k] = node.bv.rss.axis.m[k] = ax[9 * i + k];
+    for (int k = 0; k < 3; ++k) {
+      node.bv.obb.To[k] = oT[3 * i + k];
+      node.bv.obb.extent[k] = oe[3 * i + k];
+      node.bv.rss.To[k] = rT[3 * i + k];
+    }
+    node.bv.rss.l[0] = rl[2 * i];
+    node.bv.rss.l[1] = rl[2 * i + 1];
+    node.bv.rss.r = rr[i];
+  }
+  for (size_t i = 0; i < v.size() / 3; ++i) m.verts_.emplace_back(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+  for (int i = 0; i < nt; ++i) m.tris_.push_back(fcl::Triangle{{(size_t)t[3 * i], (size_t)t[3 * i + 1], (size_t)t[3 * i + 2]}});
+  m.vertices = m.verts_.data();
+  m.tri_indices = m.tris_.data();
+  m.num_tris = nt;
+  m.num_vertices = (int)m.verts_.size();
+  return b;
+}
+
+int main(int argc, char** argv) {
+  if (argc > 1 && std::string(argv[1]) == "compile-only") {
+    std::printf("shim compiled against the mock FCL surface\n");
+    return 0;
+  }
+  std::vector<double> v1, v2;
+  std::vector<int32_t> t1, t2;
+  sphere(1.0, 24, 20, v1, t1);
+  sphere(0.6, 16, 12, v2, t2);
+  Model m1, m2;
+  fclgpu_bvh* b1 = fill(m1, v1, t1);
+  fclgpu_bvh* b2 = fill(m2, v2, t2);
+  fclgpu::DeviceModel d1(m1), d2(m2);
+
+  const int n = 2000;
+  std::vector<fcl::Transform3<double>> tf1(n, fcl::Transform3<double>::Identity()), tf2(n, fcl::Transform3<double>::Identity());
+  std::vector<double> p2(12 * (size_t)n);
+  unsigned long long s = 12345;
+  auto rnd = [&]() { s = s * 6364136223846793005ull + 1442695040888963407ull; return (double)(s >> 11) / 9007199254740992.0; };
+  for (int i = 0; i < n; ++i) {
+    const double a = 6.283185307179586 * rnd(), b = 6.283185307179586 * rnd();
+    const double ca = std::cos(a), sa = std::sin(a), cb = std::cos(b), sb = std::sin(b);
+    const double R[9] = {ca * cb, -sa, ca * sb, sa * cb, ca, sa * sb, -sb, 0, cb};
+    tf2[i].setLinear(R);
+    tf2[i].setTranslation(3.2 * (rnd() - 0.5), 3.2 * (rnd() - 0.5), 3.2 * (rnd() - 0.5));
+    fclgpu_pose_from_colmajor4x4(tf2[i].m16, &p2[12 * (size_t)i]);
+  }
+
+  // direct C-ABI results on a model uploaded from the builder's own arrays
+  fclgpu_model *g1 = nullptr, *g2 = nullptr;
+  fclgpu::check(fclgpu_model_from_bvh(0, b1, &g1));
+  fclgpu::check(fclgpu_model_from_bvh(0, b2, &g2));
+  fclgpu_collision_request creq{20, 1, 0};
+  std::vector<int32_t> cnt(n);
+  std::vector<int64_t> off(n + 1);
+  std::vector<fclgpu_contact> pool(20 * (size_t)n);
+  fclgpu::check(fclgpu_collide_batch_host(g1, g2, n, nullptr, p2.data(), &creq, cnt.data(), pool.data(), (int64_t)pool.size(), off.data(), nullptr, nullptr));
+  fclgpu_distance_request dreq{1, 0, 0.0, 0.0};
+  std::vector<double> dist(n), q1(3 * (size_t)n), q2(3 * (size_t)n);
+  std::vector<int32_t> i1(n), i2(n);
+  fclgpu::check(fclgpu_distance_batch_host(g1, g2, n, nullptr, p2.data(), &dreq, dist.data(), q1.data(), q2.data(), i1.data(), i2.data(), nullptr, nullptr));
+
+  // the same through the shim
+  std::vector<fcl::CollisionResult<double>> cres;
+  fclgpu::collide(d1, tf1, d2, tf2, fcl::CollisionRequest<double>(20, true), cres);
+  std::vector<fcl::DistanceResult<double>> dres;
+  fclgpu::distance(d1, tf1, d2, tf2, fcl::DistanceRequest<double>(true), dres);
+
+  long long colliding = 0, contacts = 0;
+  for (int i = 0; i < n; ++i) {
+    if ((int)cres[i].numContacts() != cnt[i]) { std::printf("FAIL count %d: %zu vs %d\n", i, cres[i].numContacts(), cnt[i]); return 1; }
+    colliding += cnt[i] > 0;
+    for (int k = 0; k < cnt[i]; ++k) {
+      const fclgpu_contact& c = pool[off[i] + k];
+      const auto& r = cres[i].getContact(k);
+      ++contacts;
+      if (r.b1 != c.b1 || r.b2 != c.b2 || r.o1 != &m1 || r.o2 != &m2 || std::memcmp(r.pos.v, c.pos, 24) || std::memcmp(r.normal.v, c.normal, 24) ||
+          r.penetration_depth != c.penetration_depth) { std::printf("FAIL contact %d/%d\n", i, k); return 1; }
+    }
+    if (dres[i].min_distance != dist[i] || dres[i].b1 != i1[i] || dres[i].b2 != i2[i] ||
+        std::memcmp(dres[i].nearest_points[0].v, &q1[3 * (size_t)i], 24) || std::memcmp(dres[i].nearest_points[1].v, &q2[3 * (size_t)i], 24)) {
+      std::printf("FAIL distance %d\n", i);
+      return 1;
+    }
+  }
+  if (colliding < n / 20 || colliding > n - n / 20) { std::printf("FAIL: degenerate pose sample (%lld colliding)\n", colliding); return 1; }
+  std::printf("shim OK: %d queries, %lld colliding, %lld contacts compared, distances identical\n", n, colliding, contacts);
+  fclgpu_model_destroy(g1);
+  fclgpu_model_destroy(g2);
+  fclgpu_bvh_destroy(b1);
+  fclgpu_bvh_destroy(b2);
+  return 0;
+}
