@@ -141,10 +141,34 @@ def run_reference(args, rank, world):
                          "sample": f"first {sample} poses of the seed-1 batch per step, {threads} host threads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_RESULT_FD = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner there when NCCL_DEBUG is
+    set on the box) write to file descriptor 1 directly, so point fd 1 at stderr for the whole run and keep the
+    real stdout for the result line."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -405,7 +429,7 @@ def main():
                    "multi_gpu": "BVHs replicated, poses partitioned, results all-gathered with NCCL" if world > 1 else "single GPU"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches_timed, "roofline": roofline, "fp64": fp64, "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
