@@ -374,7 +374,11 @@ def test_device_build_equals_host_build(oracle, env_rob_npz, split):
               random_soup(3000, seed=5), random_soup(20000, seed=6, scale=3.0, tri_size=0.05)]
     one_tri = (np.array([[0.0, 0, 0], [1, 0, 0], [0, 1, 0]]), np.array([[0, 1, 2]], np.int32))
     coplanar = heightfield(12, size=4.0, seed=1, amp=0.0)  # flat grid: degenerate covariance, many split ties
-    for v, t in meshes + [one_tri, coplanar]:
+    same = (np.array([[0.0, 0, 0], [1, 0, 0], [0, 1, 0]]), np.tile(np.array([[0, 1, 2]], np.int32), (64, 1)))  # every split ties
+    line = np.arange(40, dtype=np.float64)[:, None] * np.array([[1.0, 2.0, 3.0]])  # collinear vertices: zero-area triangles
+    degenerate = (line, np.stack([np.arange(38), np.arange(38) + 1, np.arange(38) + 2], axis=1).astype(np.int32))
+    two = (np.array([[0.0, 0, 0], [1, 0, 0], [0, 1, 0], [5, 5, 5], [6, 5, 5], [5, 6, 5]]), np.array([[0, 1, 2], [3, 4, 5]], np.int32))
+    for v, t in meshes + [one_tri, coplanar, same, degenerate, two]:
         host = F.BVHModel.from_arrays(v, t, split)
         dev = F.BVHModel.from_arrays(v, t, split, build_on_device=True)
         assert dev.getNumBVs() == host.getNumBVs()

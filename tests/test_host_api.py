@@ -52,6 +52,12 @@ def test_build_protocol_and_return_codes(capfd):
 @pytest.mark.parametrize("split", [0, 1, 2])
 def test_product_bvh_builder_matches_oracle_bitwise(oracle, env_rob_npz, split):
     meshes = list(env_rob_npz) + [uv_sphere(20, 16, 16), box_mesh(1, 2, 3), random_soup(300, 3), ([[0, 0, 0], [1, 0, 0], [0, 1, 0]], [[0, 1, 2]])]
+    # degenerate inputs: 64 copies of one triangle (every split ties), collinear vertices (zero-area triangles,
+    # rank-deficient covariance), two far-apart triangles
+    line = np.arange(40, dtype=np.float64)[:, None] * np.array([[1.0, 2.0, 3.0]])
+    meshes += [(np.array([[0.0, 0, 0], [1, 0, 0], [0, 1, 0]]), np.tile(np.array([[0, 1, 2]], np.int32), (64, 1))),
+               (line, np.stack([np.arange(38), np.arange(38) + 1, np.arange(38) + 2], axis=1).astype(np.int32)),
+               (np.array([[0.0, 0, 0], [1, 0, 0], [0, 1, 0], [5, 5, 5], [6, 5, 5], [5, 6, 5]]), np.array([[0, 1, 2], [3, 4, 5]], np.int32))]
     for v, t in meshes:
         got = F.BVHModel.from_arrays(v, t, split).node_arrays()
         ref = oracle.Model(v, t, split).arrays()
