@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--traversal", type=int, default=3, help="kernel variant (fclgpu option 'traversal', see DESIGN.md)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="name=value library option (A/B runs; recorded in config)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -207,6 +208,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     _capi.set_option("traversal", args.traversal)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        _capi.set_option(k, int(v))
 
     (ev, et), (rv, rt) = load_meshes()
     env, rob = F.BVHModel.from_arrays(ev, et), F.BVHModel.from_arrays(rv, rt)
@@ -425,7 +429,7 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOADS[wl], "poses_per_gpu": n, "global_poses": world * n, "pose_seed": 1,
                    "models": "env.obj (2180 tris, 4359 nodes) posed vs rob.obj (216 tris, 431 nodes) at identity",
-                   "l2_flush_between_steps": True, "traversal": _capi.get_option("traversal"),
+                   "l2_flush_between_steps": True, "traversal": _capi.get_option("traversal"), **({"options": args.opt} if args.opt else {}),
                    "multi_gpu": "BVHs replicated, poses partitioned, results all-gathered with NCCL" if world > 1 else "single GPU"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches_timed, "roofline": roofline, "fp64": fp64, "cpu_baseline": cpu,
     }

@@ -64,6 +64,7 @@ std::map<std::string, long long> g_opts = {
     // 0: thread per query, the reference's visiting order exactly (work counters match the reference's)
     {"traversal", 3},
     {"dist_spill_entries", 4096},  // per-warp global overflow entries of the distance front (allocated for big models)
+    {"collide_front", 1},      // counts-only collide: warp-per-query front kernel (0 never, 1 big BVHs, 2 always)
     {"host_chunk", 1 << 17},   // queries per stage of the host API's two-stream copy/compute pipeline
     {"contact_stride", 1024},  // per-query contact scratch slots when num_max_contacts is larger
     {"scratch_bytes", 2ll << 30},
@@ -808,7 +809,14 @@ int collide_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, c
     P.ready_q0 = X.ready_q0 + s;
     const long long trav = opt("traversal");
     const int trig = (int)opt("leaf_trigger");
-    if (trav >= 2 && !P.enable_contact && (trav == 2 || !opt("binary_pooled"))) {
+    const long long front = opt("collide_front");  // 0 never, 1 (default) for BVHs beyond the caches, 2 always
+    if (!want_contacts && !P.enable_contact && trav >= 1 &&
+        (front >= 2 || (front == 1 && (long long)m1->d.n_nodes + m2->d.n_nodes >= (1 << 17)))) {
+      // counts only: the result does not depend on the visiting order -> warp-per-query front kernel
+      const size_t fsm = sizeof(CollideFront) * 4;
+      rc = stats ? launch_persistent(collide_front_kernel<true>, P, w, 128, st, fsm)
+                 : launch_persistent(collide_front_kernel<false>, P, w, 128, st, fsm);
+    } else if (trav >= 2 && !P.enable_contact && (trav == 2 || !opt("binary_pooled"))) {
       rc = stats ? launch_persistent(collide_deferred_kernel<true, true, true>, P, w, 128, st, 0, trig)
                  : launch_persistent(collide_deferred_kernel<false, true, true>, P, w, 128, st, 0, trig);
     } else if (trav >= 3) {  // pooled leaf rounds

@@ -1450,3 +1450,157 @@ __global__ void __launch_bounds__(128, FCLGPU_POOLED_MINBLOCKS) collide_pooled_k
 }
 
 }  // namespace fclgpu
+
+namespace fclgpu {
+
+// ---------------------------------------------------------------------------------------
+// Variant F for collide, COUNTS ONLY (no contact list, enable_contact = false): one warp per query.
+// num_contacts = min(number of intersecting triangle pairs, num_max_contacts) does not depend on the
+// order in which the pairs are found, so the warp may expand its BVTT front breadth-wise like the
+// distance kernel: a shared-memory stack of node pairs, up to 16 entries expanded per round by two
+// lanes each (conservative FP32 box test of the two children), surviving children pushed by ballot
+// compaction, leaf pairs queued and tested 32 at a time with the exact FP64 triangle SAT.  All
+// 32 lanes have independent record loads in flight, which is what the lane-per-query kernels lack
+// once the BVH no longer fits the caches (cfg5: 1M-triangle meshes).  Near the stack limit the
+// warp falls back to one expansion per round (plain DFS, depth-bounded), so it never overflows.
+// ---------------------------------------------------------------------------------------
+constexpr int kFrontStackCap = 768;
+constexpr int kFrontLeafCap = 64;
+
+struct __align__(16) CollideFront {
+  uint2 pair[kFrontStackCap];
+  uint2 leaf[kFrontLeafCap];
+  uint2 expand[32];
+};
+
+template <bool kStats>
+__global__ void __launch_bounds__(128, 4) collide_front_kernel(CollideParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CollideFront& S = reinterpret_cast<CollideFront*>(smem_raw)[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  while (true) {
+    long long q = 0;
+    if (lane == 0) q = (long long)atomicAdd(P.work_counter, 1ull);
+    q = __shfl_sync(0xffffffffu, q, 0);
+    if (q >= P.n) break;
+    if (!wait_ready(P.ready, P.ready_shift, q + P.ready_q0) && lane == 0) atomicMin(P.status, (int)FCLGPU_ERR_INPUT_STALLED);
+
+    M3 R;
+    V3 T;
+    {
+      const PoseRT tf1 = load_pose(P.tf1, q);
+      const PoseRT tf2 = load_pose(P.tf2, q);
+      R = mulTM(tf1.R, tf2.R);
+      T = mulTv(tf1.R, tf2.t - tf1.t);
+    }
+    float Rf[9], Tf[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Rf[k] = (float)R.m[k];
+    Tf[0] = (float)T.x; Tf[1] = (float)T.y; Tf[2] = (float)T.z;
+    const float t_l1 = __double2float_ru((fabs(T.x) + fabs(T.y)) + fabs(T.z));
+
+    long long count = 0;
+    int sp = 0, nleaf = 0;
+    uint32_t bv_tests = 1, leaf_tests = 0;
+    {  // root pair
+      const ObbRec32 n1 = load_obb32(P.m1.obb32, 0), n2 = load_obb32(P.m2.obb32, 0);
+      if (!obb_certainly_disjoint_f32(Rf, Tf, t_l1, n1, n2)) {
+        if (lane == 0) S.pair[0] = make_uint2(0u, 0u);
+        sp = 1;
+      }
+    }
+    __syncwarp();
+
+    while (true) {
+      const bool do_leaf = (nleaf >= 32) || (sp == 0 && nleaf > 0);
+      if (do_leaf) {
+        const int k = nleaf < 32 ? nleaf : 32;
+        nleaf -= k;
+        bool hit = false;
+        if (lane < k) {
+          const uint2 ids = S.leaf[nleaf + lane];
+          V3 Pt[3], Qt[3];
+          load_tri(P.m1.tri, (int)ids.x, Pt);
+          load_tri(P.m2.tri, (int)ids.y, Qt);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) Qt[c] = mulv(R, Qt[c]) + T;
+          hit = tri_intersect_outofline(Pt, Qt);
+        }
+        if (kStats) leaf_tests += k;
+        count += __popc(__ballot_sync(0xffffffffu, hit));
+        __syncwarp();
+        if (count >= P.max_contacts) {  // canStop()
+          count = P.max_contacts;
+          break;
+        }
+        continue;
+      }
+      if (sp == 0) break;
+
+      // ---- BV round: entries on the stack are known to overlap ----
+      const bool tight = sp > kFrontStackCap - 160;  // close to the limit: one entry per round (depth-first)
+      const int k = tight ? 1 : (sp < 32 ? sp : 32);
+      uint2 pr = make_uint2(0u, 0u);
+      int fc1 = 0, fc2 = 0;
+      double size1 = 0.0, size2 = 0.0;
+      const bool have = lane < k;
+      if (have) {
+        pr = S.pair[sp - 1 - lane];
+        load_topo(P.m1.topo, (int)pr.x, fc1, size1);
+        load_topo(P.m2.topo, (int)pr.y, fc2, size2);
+      }
+      const bool l1 = fc1 < 0, l2 = fc2 < 0;
+      const bool leafpair = have && l1 && l2;
+      const unsigned lm = __ballot_sync(0xffffffffu, leafpair);
+      if (leafpair) S.leaf[nleaf + __popc(lm & lt_mask)] = make_uint2((unsigned)(-(fc1 + 1)), (unsigned)(-(fc2 + 1)));
+      nleaf += __popc(lm);
+      const bool internal = have && !leafpair;
+      const unsigned im = __ballot_sync(0xffffffffu, internal);
+      const int n_int = __popc(im), rank = __popc(im & lt_mask);
+      sp -= k;
+      const int n_exp = n_int < 16 ? n_int : 16;
+      __syncwarp();  // every lane has read its popped entry before slots are overwritten
+      if (internal) {
+        if (rank < n_exp) {
+          if (l2 || (!l1 && (size1 > size2))) {  // firstOverSecond
+            S.expand[2 * rank] = make_uint2((unsigned)fc1, pr.y);
+            S.expand[2 * rank + 1] = make_uint2((unsigned)fc1 + 1u, pr.y);
+          } else {
+            S.expand[2 * rank] = make_uint2(pr.x, (unsigned)fc2);
+            S.expand[2 * rank + 1] = make_uint2(pr.x, (unsigned)fc2 + 1u);
+          }
+        } else {  // not expanded this round: back on the stack
+          S.pair[sp + (n_int - 1 - rank)] = pr;
+        }
+      }
+      sp += n_int - n_exp;
+      __syncwarp();
+      bool keep = false;
+      uint2 xy = make_uint2(0u, 0u);
+      if (lane < 2 * n_exp) {
+        xy = S.expand[lane];
+        const ObbRec32 n1 = load_obb32(P.m1.obb32, (int)xy.x);
+        const ObbRec32 n2 = load_obb32(P.m2.obb32, (int)xy.y);
+        keep = !obb_certainly_disjoint_f32(Rf, Tf, t_l1, n1, n2);
+      }
+      if (kStats) bv_tests += 2 * n_exp;
+      const unsigned km = __ballot_sync(0xffffffffu, keep);
+      if (keep) S.pair[sp + __popc(km & lt_mask)] = xy;
+      sp += __popc(km);
+      __syncwarp();
+    }
+
+    if (lane == 0) {
+      P.num_contacts[q] = (int32_t)count;
+      if (kStats) {
+        if (P.n_bv) P.n_bv[q] = bv_tests;
+        if (P.n_leaf) P.n_leaf[q] = leaf_tests;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace fclgpu

@@ -456,3 +456,20 @@ def test_host_api_pinned_pipelines_match_oracle(oracle, env_rob_npz, host_chunk)
         assert ei.value.code == _capi.ERR_CONTACT_OVERFLOW
     finally:
         _capi.set_option("host_chunk", 1 << 17)
+
+
+def test_counts_only_front_kernel_matches_oracle(models, oracle):
+    """Counts-only collide through the warp-per-query front kernel (chosen automatically for BVHs beyond the
+    caches, forced here): num_contacts = min(#intersecting pairs, num_max_contacts) for every budget."""
+    (env, rob), (oenv, orob) = models
+    P = random_poses(20000, seed=31)
+    _capi.set_option("collide_front", 2)
+    try:
+        for max_contacts in (1, 7, 100000):
+            got = F.collide_batch(env, P, rob, None, F.CollisionRequest(max_contacts, False), want_contacts=False, stats=True)
+            ref = oracle.collide_batch(oenv, orob, P, None, max_contacts, False, nthreads=8)
+            assert np.array_equal(got.num_contacts, ref["counts"]), max_contacts
+        assert got.num_contacts.max() > 100  # the exhaustive budget really counted every pair
+        assert (got.n_bv > 0).all()
+    finally:
+        _capi.set_option("collide_front", 1)
