@@ -56,6 +56,7 @@ inline int cuda_status(cudaError_t e) {
 // options
 std::mutex g_opt_mu;
 std::map<std::string, long long> g_opts = {
+    // 4: like 3 with the pooled collide kernel testing both children per BV round (chosen automatically for big BVHs)
     // 3 (default): like 2, and collide with contact generation pools the warp's deferred triangle pairs
     //    over all 32 lanes (collide_pooled_kernel)
     // 2: like 1, but the BV tests that steer the traversal are conservative single-precision tests
