@@ -252,6 +252,65 @@ FD float tri_lower_bound_f32(const float* s1, const float* s2, const float* t0, 
 }
 
 
+// Selectable subset of the 19 directions of tri_lower_bound_f32 (same validity argument and slack; every
+// direction only adds cost and tightness): kDirs bit 0 = the two face normals, bit 1 = centroid direction,
+// bit 2 = the nine edge x edge products, bit 3 = the six in-plane edge normals.
+template <int kDirs>
+FD float tri_lower_bound_dirs_f32(const float* s1, const float* s2, const float* t0, const float* t1, const float* t2) {
+  float best = 0.0f;
+  auto consider = [&](float lx, float ly, float lz) {
+    const float len2 = fmaf(lz, lz, fmaf(ly, ly, lx * lx));
+    const float a1 = fmaf(lz, s1[2], fmaf(ly, s1[1], lx * s1[0]));
+    const float a2 = fmaf(lz, s2[2], fmaf(ly, s2[1], lx * s2[0]));
+    const float b0 = fmaf(lz, t0[2], fmaf(ly, t0[1], lx * t0[0]));
+    const float b1 = fmaf(lz, t1[2], fmaf(ly, t1[1], lx * t1[0]));
+    const float b2 = fmaf(lz, t2[2], fmaf(ly, t2[1], lx * t2[0]));
+    const float mnS = fminf(0.0f, fminf(a1, a2)), mxS = fmaxf(0.0f, fmaxf(a1, a2));
+    const float mnT = fminf(b0, fminf(b1, b2)), mxT = fmaxf(b0, fmaxf(b1, b2));
+    const float g = fmaxf(mnT - mxS, mnS - mxT);
+    const bool ok = (len2 > 1e-30f) && (len2 < 1e30f);
+    const float v = g * f32_rsqrt(ok ? len2 : 1.0f);
+    best = fmaxf(best, ok ? v : 0.0f);
+  };
+  const float e0[3] = {s1[0], s1[1], s1[2]};
+  const float e1[3] = {s2[0] - s1[0], s2[1] - s1[1], s2[2] - s1[2]};
+  const float e2[3] = {-s2[0], -s2[1], -s2[2]};
+  const float f0[3] = {t1[0] - t0[0], t1[1] - t0[1], t1[2] - t0[2]};
+  const float f1[3] = {t2[0] - t1[0], t2[1] - t1[1], t2[2] - t1[2]};
+  const float f2[3] = {t0[0] - t2[0], t0[1] - t2[1], t0[2] - t2[2]};
+  const float* E[3] = {e0, e1, e2};
+  const float* Fv[3] = {f0, f1, f2};
+  float n1[3], n2[3];
+  n1[0] = fmaf(e0[1], e1[2], -(e0[2] * e1[1])); n1[1] = fmaf(e0[2], e1[0], -(e0[0] * e1[2])); n1[2] = fmaf(e0[0], e1[1], -(e0[1] * e1[0]));
+  n2[0] = fmaf(f0[1], f1[2], -(f0[2] * f1[1])); n2[1] = fmaf(f0[2], f1[0], -(f0[0] * f1[2])); n2[2] = fmaf(f0[0], f1[1], -(f0[1] * f1[0]));
+  if (kDirs & 1) {
+    consider(n1[0], n1[1], n1[2]);
+    consider(n2[0], n2[1], n2[2]);
+  }
+  if (kDirs & 2)
+    consider((t0[0] + t1[0] + t2[0]) - (s1[0] + s2[0]), (t0[1] + t1[1] + t2[1]) - (s1[1] + s2[1]),
+             (t0[2] + t1[2] + t2[2]) - (s1[2] + s2[2]));
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (kDirs & 4) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        consider(fmaf(E[i][1], Fv[j][2], -(E[i][2] * Fv[j][1])), fmaf(E[i][2], Fv[j][0], -(E[i][0] * Fv[j][2])),
+                 fmaf(E[i][0], Fv[j][1], -(E[i][1] * Fv[j][0])));
+    }
+    if (kDirs & 8) {
+      consider(fmaf(E[i][1], n1[2], -(E[i][2] * n1[1])), fmaf(E[i][2], n1[0], -(E[i][0] * n1[2])),
+               fmaf(E[i][0], n1[1], -(E[i][1] * n1[0])));
+      consider(fmaf(Fv[i][1], n2[2], -(Fv[i][2] * n2[1])), fmaf(Fv[i][2], n2[0], -(Fv[i][0] * n2[2])),
+               fmaf(Fv[i][0], n2[1], -(Fv[i][1] * n2[0])));
+    }
+  }
+  auto l1 = [](const float* p) { return fabsf(p[0]) + fabsf(p[1]) + fabsf(p[2]); };
+  const float Lsum = fmaxf(fmaxf(l1(s1), l1(s2)), fmaxf(l1(t0), fmaxf(l1(t1), l1(t2))));
+  const float lb = fmaf(best, 0.999999f, -(1.9073486328125e-06f * Lsum));  // 32 * 2^-24 * Lsum
+  return fmaxf(lb, 0.0f);
+}
+
 // Single-precision classification of a triangle pair for the collide leaf test:
 //   +1  certainly separated   (some axis of the reference's 17-axis SAT separates the projections
 //                              by more than the rounding margin => intersect_Triangle is false)

@@ -508,10 +508,16 @@ constexpr int kSpillBlock = 256;     // entries moved to / from the global overf
 constexpr int kLeafCap = 64;
 constexpr int kLeafTrigger = 32;
 constexpr int kDistWarps = 4;        // warps per block
-// Triangle-level FP32 screening of leaf pairs before the exact triDistance (tri_lower_bound_f32).
-// Measured on B200: exact tests per query drop 134 -> 59, but the extra code raises instruction-
-// fetch stalls (ncu: no_instructions 27 %) and the kernel ends up 7 % slower, so it is off.
-constexpr bool kScreenLeaves = false;
+// Triangle-level FP32 screening of leaf pairs before the exact triDistance: a conservative lower bound on the
+// triangle distance from the support-function gap along a few directions (tri_lower_bound_dirs_f32); only pairs
+// whose bound still beats the minimum go on to the exact queue.  Measured on B200 (1M poses, env/rob), direction
+// set -> kernel ms / exact tests per query: none 41.4 / 147; face normals 41.6 / 133; normals + centroid 39.2 / 105;
+// + nine edge x edge 41.4 / 70; in-plane edge normals only 37.4 / 78; normals + in-plane 37.3 / 71 (default);
+// all 19 directions 46.5 / 59 (instruction fetch).
+#ifndef FCLGPU_SCREEN_LEAVES
+#define FCLGPU_SCREEN_LEAVES 9
+#endif
+constexpr bool kScreenLeaves = FCLGPU_SCREEN_LEAVES != 0;  // direction set of the screening bound (bit mask, see tri_lower_bound_dirs_f32)
 
 struct __align__(16) WarpFront {
   float bound[kDistStackCap];   // lower bounds are stored in single precision, rounded down
@@ -565,6 +571,9 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
   WarpFront& S = reinterpret_cast<WarpFront*>(smem_raw)[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
+  // the screening round pays off when triangle tests dominate; on BVHs beyond the caches (the kSpill instantiation)
+  // box tests dominate and the later minimum update costs more than the saved tests (cfg5: 48 -> 56 ms)
+  constexpr bool kScreen = kScreenLeaves && !kSpill;
 
   while (true) {
     long long q = 0;
@@ -640,7 +649,7 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
       }
       // the screening round may add up to min(nraw, 32) pairs to the exact queue: only run it when they fit
       // (otherwise the exact queue is at least half full and the exact round below drains it first)
-      const bool can_screen = kBound32 && kScreenLeaves && nraw > 0 && (nleaf + (nraw < 32 ? nraw : 32) <= kLeafCap);
+      const bool can_screen = kBound32 && kScreen && nraw > 0 && (nleaf + (nraw < 32 ? nraw : 32) <= kLeafCap);
       if (can_screen && (nraw >= 32 || sp == 0)) {
         // ---- screening round: triangle-level lower bound (FP32, branch-free) on up to 32 raw leaf pairs;
         // only pairs that can still beat the minimum go on to the exact queue
@@ -652,7 +661,7 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
         if (mine) {
           ids = S.raw_pair[nraw + lane];
           b = S.raw_bound[nraw + lane];
-          mine = (double)b < min_d;
+          mine = b < min_f;
         }
         bool keep = false;
         if (mine) {
@@ -669,9 +678,9 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
             t1[0] = (float)u1.x; t1[1] = (float)u1.y; t1[2] = (float)u1.z;
             t2[0] = (float)u2.x; t2[1] = (float)u2.y; t2[2] = (float)u2.z;
           }
-          const float lb = tri_lower_bound_f32(s1, s2, t0, t1, t2);
+          const float lb = tri_lower_bound_dirs_f32<(FCLGPU_SCREEN_LEAVES ? FCLGPU_SCREEN_LEAVES : 15)>(s1, s2, t0, t1, t2);
           b = fmaxf(b, lb);
-          keep = (double)b < min_d;
+          keep = b < min_f;
         }
         const unsigned km = __ballot_sync(0xffffffffu, keep);
         if (keep) {
@@ -756,7 +765,7 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
       const unsigned lm = __ballot_sync(0xffffffffu, leafpair);
       if (leafpair) {
         const uint2 tri_ids = make_uint2((unsigned)(-(fc1 + 1)), (unsigned)(-(fc2 + 1)));
-        if (kBound32 && kScreenLeaves) {
+        if (kBound32 && kScreen) {
           const int pos = nraw + __popc(lm & lt_mask);
           S.raw_pair[pos] = tri_ids;
           S.raw_bound[pos] = bd;
@@ -766,7 +775,7 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
           S.leaf_bound[pos] = bd;
         }
       }
-      if (kBound32 && kScreenLeaves) nraw += __popc(lm);
+      if (kBound32 && kScreen) nraw += __popc(lm);
       else nleaf += __popc(lm);
       const bool internal = alive && !leafpair;
       const unsigned im = __ballot_sync(0xffffffffu, internal);

@@ -98,6 +98,23 @@ float hm_tri_lb32(const double* S9, const double* T9) {
   }
   return tri_lower_bound_f32(s1, s2, t0, t1, t2);
 }
+// the same with a direction subset (the distance kernel's screening round uses subset 9, see traversal.cuh)
+float hm_tri_lb32_dirs(const double* S9, const double* T9, int dirs) {
+  float s1[3], s2[3], t0[3], t1[3], t2[3];
+  for (int c = 0; c < 3; ++c) {
+    s1[c] = (float)(S9[3 + c] - S9[c]);
+    s2[c] = (float)(S9[6 + c] - S9[c]);
+    t0[c] = (float)(T9[c] - S9[c]);
+    t1[c] = (float)(T9[3 + c] - S9[c]);
+    t2[c] = (float)(T9[6 + c] - S9[c]);
+  }
+  switch (dirs) {
+    case 9: return tri_lower_bound_dirs_f32<9>(s1, s2, t0, t1, t2);
+    case 11: return tri_lower_bound_dirs_f32<11>(s1, s2, t0, t1, t2);
+    case 3: return tri_lower_bound_dirs_f32<3>(s1, s2, t0, t1, t2);
+    default: return tri_lower_bound_dirs_f32<15>(s1, s2, t0, t1, t2);
+  }
+}
 // FP32 triangle-pair classification exactly as the collide kernel does it: Q' = R Q + T and the
 // translation by -P1 in FP64, one rounding to float, then tri_classify_f32
 int hm_tri_classify32(const double* P9, const double* Q9, const double* pose12) {

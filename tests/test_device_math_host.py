@@ -242,6 +242,44 @@ def test_f32_triangle_lower_bound_is_conservative(hm, oracle, env_rob_npz):
     assert np.median(ratios) > 0.95
 
 
+def test_f32_triangle_screening_subset_is_a_valid_lower_bound(hm, oracle, env_rob_npz):
+    """The direction subset the distance kernel's screening round uses (FCLGPU_SCREEN_LEAVES = 9: face normals +
+    in-plane edge normals) never exceeds the exact triangle distance -- also for touching / overlapping pairs and
+    at large coordinate offsets -- and the full set reproduces tri_lower_bound_f32."""
+    import ctypes as C
+
+    L = hm.lib()
+    L.hm_tri_lb32_dirs.restype = C.c_float
+    L.hm_tri_lb32_dirs.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    rng = np.random.default_rng(53)
+    ratios = []
+    for scale, offset, spread in ((1.0, 0.0, 2.5), (1000.0, 3000.0, 2.5), (0.01, 100.0, 2.5), (1.0, 0.0, 0.3)):
+        n = 12000
+        S, T = _tri_pairs(rng, n, spread)
+        S, T = S * scale + offset, T * scale + offset
+        T[:500, :3] = S[:500, :3]  # shared vertex: distance 0
+        for k in range(n):
+            d, _, _ = oracle.tri_distance(S[k], T[k])
+            for dirs in (9, 3, 11):
+                lb = float(L.hm_tri_lb32_dirs(hm.dptr(S[k]), hm.dptr(T[k]), dirs))
+                assert lb <= d, (scale, k, dirs, lb, d)
+            if k < 2000:
+                assert float(L.hm_tri_lb32_dirs(hm.dptr(S[k]), hm.dptr(T[k]), 15)) == float(L.hm_tri_lb32(hm.dptr(S[k]), hm.dptr(T[k])))
+            if d > 0.5 * scale:
+                ratios.append(float(L.hm_tri_lb32_dirs(hm.dptr(S[k]), hm.dptr(T[k]), 9)) / d)
+    (ev, et), (rv, rt) = env_rob_npz
+    P = random_poses(3000, seed=59)
+    ti = rng.integers(0, len(et), len(P))
+    tj = rng.integers(0, len(rt), len(P))
+    for k in range(len(P)):
+        R1, t1 = P[k, :9].reshape(3, 3), P[k, 9:]
+        S = ev[et[ti[k]]].reshape(9)
+        Tw = np.ascontiguousarray((R1.T @ (rv[rt[tj[k]]] - t1).T).T.reshape(9))
+        d, _, _ = oracle.tri_distance(S, Tw)
+        assert float(L.hm_tri_lb32_dirs(hm.dptr(S), hm.dptr(Tw), 9)) <= d, k
+    assert np.median(ratios) > 0.5
+
+
 def test_f32_triangle_classification_is_sound(hm, oracle, env_rob_npz):
     """+1 (certainly separated) => the exact test says no intersection; -1 (certainly intersecting)
     => the exact test says intersection; 0 (undecided) must be rare on generic input."""
