@@ -502,7 +502,10 @@ __device__ __noinline__ double tri_distance_outofline(const V3* Sv, const V3* Tv
   return tri_distance(Sv, Tv, *Pn, *Qn);
 }
 
-constexpr int kDistPop = 16;         // entries expanded per BV round (2 lanes each)
+#ifndef FCLGPU_DIST_POP
+#define FCLGPU_DIST_POP 16
+#endif
+constexpr int kDistPop = FCLGPU_DIST_POP;  // entries expanded per BV round (2 lanes each)
 constexpr int kDistStackCap = 512;   // entries per warp
 constexpr int kSpillBlock = 256;     // entries moved to / from the global overflow area at a time
 constexpr int kLeafCap = 64;
