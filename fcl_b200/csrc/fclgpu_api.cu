@@ -1008,8 +1008,10 @@ extern "C" int fclgpu_collide_batch_host(const fclgpu_model* m1, const fclgpu_mo
     // stream brings the poses up chunk by chunk; behind every chunk it writes ready[c] (a 4-byte DMA from a pinned
     // word -- not a memset, which could need an SM the spinning kernel holds), and lanes that fetch a query of a
     // chunk still in flight wait on that flag.  No per-chunk launch tails, copies fully overlapped.
+    // chunks of host_chunk / 8 queries: no launch depends on the chunk size here, finer chunks only let the kernel
+    // start earlier (1M verdicts: 4.55 ms with 131072-query chunks, 4.40 ms with 16384)
     int shift = 10;
-    while ((1ll << (shift + 1)) <= host_chunk()) ++shift;
+    while ((1ll << (shift + 1)) <= host_chunk() / 8) ++shift;
     while (((n + (1ll << shift) - 1) >> shift) > kReadySlots) ++shift;
     const int64_t C = 1ll << shift;
     const int nchunks = (int)((n + C - 1) / C);
