@@ -473,3 +473,42 @@ def test_counts_only_front_kernel_matches_oracle(models, oracle):
         assert (got.n_bv > 0).all()
     finally:
         _capi.set_option("collide_front", 1)
+
+
+def test_tiny_and_coincident_models_all_variants(oracle):
+    """Edge cases of the traversals: models of 1..9 triangles (single-node trees, leaf-vs-internal pairs), identical
+    poses (coincident meshes: every tie-break and touching rule is exercised), far-apart poses (root boxes disjoint).
+    Every kernel variant must reproduce the oracle's contacts bit for bit and its distances exactly."""
+    rng = np.random.default_rng(61)
+    cases = []
+    for nt1, nt2 in ((1, 1), (1, 7), (2, 2), (5, 1), (9, 3), (4, 8)):
+        v1, t1 = random_soup(nt1, seed=int(rng.integers(1 << 30)), scale=1.0, tri_size=0.8)
+        v2, t2 = random_soup(nt2, seed=int(rng.integers(1 << 30)), scale=1.0, tri_size=0.8)
+        cases.append((v1, t1, v2, t2))
+    v, t = box_mesh(1.0, 0.5, 0.25)
+    cases.append((v, t, v, t))  # the same box twice
+    P = random_poses(600, seed=67, extents=(-1.5, -1.5, -1.5, 1.5, 1.5, 1.5))
+    P[:50] = identity_poses(50)          # coincident
+    P[50:100, 9:] += 100.0               # far apart
+    try:
+        for v1, t1, v2, t2 in cases:
+            m1, m2 = F.BVHModel.from_arrays(v1, t1), F.BVHModel.from_arrays(v2, t2)
+            o1, o2 = oracle.Model(v1, t1), oracle.Model(v2, t2)
+            rc = oracle.collide_batch(o1, o2, P, None, 1000, True, nthreads=4)
+            rb = oracle.collide_batch(o1, o2, P, None, 1, False, nthreads=4)
+            rd = oracle.distance_batch(o1, o2, P, None, True, 2, nthreads=4)
+            for trav in (0, 1, 2, 3, 4):
+                _capi.set_option("traversal", trav)
+                for front in (1, 2):
+                    _capi.set_option("collide_front", front)
+                    gb = F.collide_batch(m1, P, m2, None, F.CollisionRequest(), want_contacts=False)
+                    assert np.array_equal(gb.num_contacts, rb["counts"]), (trav, front, len(t1), len(t2))
+                _capi.set_option("collide_front", 1)
+                gc = F.collide_batch(m1, P, m2, None, F.CollisionRequest(1000, True), contact_capacity=1000 * 20, grow_on_overflow=True)
+                assert np.array_equal(gc.num_contacts, rc["counts"]), (trav, len(t1), len(t2))
+                assert gc.contacts.tobytes() == rc["contacts"].tobytes(), (trav, len(t1), len(t2))
+                gd = F.distance_batch(m1, P, m2, None, F.DistanceRequest(True))
+                assert np.array_equal(gd.min_distance, rd["min_distance"]), (trav, len(t1), len(t2))
+    finally:
+        _capi.set_option("traversal", 3)
+        _capi.set_option("collide_front", 1)
