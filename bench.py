@@ -167,6 +167,24 @@ def emit(line):
         os.write(_RESULT_FD, data)
 
 
+def ensure_built(local_rank):
+    """The CUDA library normally travels with the tree (built by __graft_entry__.build()); on a bare checkout build it
+    once (local rank 0) instead of failing -- there is still no CPU fallback, only a compile step."""
+    lib = os.path.join(ROOT, "fcl_b200", "lib", "libfclgpu.so")
+    if os.path.exists(lib):
+        return
+    if local_rank == 0:
+        tmp_out = "../lib/libfclgpu.so.building"
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "fcl_b200", "csrc"), "-s", "OUT=" + tmp_out], stdout=sys.stderr)
+        os.replace(os.path.join(ROOT, "fcl_b200", "lib", "libfclgpu.so.building"), lib)
+    else:
+        for _ in range(1800):
+            if os.path.exists(lib):
+                return
+            time.sleep(1.0)
+        raise SystemExit("libfclgpu.so was not built")
+
+
 def main():
     quiet_stdout()
     ap = argparse.ArgumentParser()
@@ -196,6 +214,7 @@ def main():
     import torch
     import torch.distributed as dist
 
+    ensure_built(local)
     import fcl_b200 as F
     from fcl_b200 import _capi
     from fcl_b200.sharding import all_gather_records
