@@ -12,6 +12,12 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the product library normally travels with the tree; on a bare checkout compile it (nvcc cross-compiles
+    # sm_100a without a GPU) -- the package itself never falls back to anything else
+    if not os.path.exists(os.path.join(ROOT, "fcl_b200", "lib", "libfclgpu.so")):
+        import subprocess
+
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "fcl_b200", "csrc"), "-s"])
 
 
 @pytest.fixture(scope="session")
