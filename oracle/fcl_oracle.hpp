@@ -119,6 +119,19 @@ double distance(const Model& m1, const Pose& tf1, const Model& m2, const Pose& t
                 bool enable_nearest_points, DistanceOut& out, int qsize = 2,
                 CollideStats* stats = nullptr);
 
+// ---- mesh <-> sphere (closed-form leaf test, no GJK on this pair) ----------------
+// sphereTriangleIntersect, narrowphase/detail/primitive_shape_algorithm/sphere_triangle-inl.h:147-244.
+// center / P1..P3 in one frame.  Outputs as the reference writes them (normal is negated by the caller).
+bool sphere_tri_intersect(const Vec3& center, double radius, const Vec3& P1, const Vec3& P2, const Vec3& P3,
+                          Vec3* contact_point, double* penetration_depth, Vec3* normal);
+// computeBV<OBBRSS>(Sphere, tf): OBB part, fitted over the 12 bound vertices (sphere-inl.h:95-120, BV_fitter fitn)
+void sphere_obb(double radius, const Pose& tf, Node& bv);
+// fcl::collide(BVHModel<OBBRSS>, tf1, Sphere(radius), tf2): contacts {b1 = triangle, b2 = -1 (Contact::NONE)}
+size_t collide_mesh_sphere(const Model& m1, const Pose& tf1, double radius, const Pose& tf2, size_t num_max_contacts,
+                           bool enable_contact, std::vector<Contact>& out, CollideStats* stats = nullptr);
+// every triangle tested in primitive order (for the invariants): ids of the intersecting triangles
+void brute_mesh_sphere(const Model& m1, const Pose& tf1, double radius, const Pose& tf2, std::vector<int>& tris);
+
 // brute force over all triangle pairs (for the invariants)
 void brute_collide_pairs(const Model& m1, const Pose& tf1, const Model& m2, const Pose& tf2,
                          std::vector<std::pair<int, int>>& pairs);

@@ -365,6 +365,65 @@ struct Builder {
   }
 };
 
+
+// ---------------------------------------------------------------------------------------
+// computeBV<OBBRSS<S>>(Sphere, tf) -- geometry/shape/utility-inl.h generic ComputeBVImpl:
+// fit(getBoundVertices(tf)) with n = 12 > 3 -> fitn (BV_fitter-inl.h): getCovariance (point branch,
+// math/geometry-inl.h:1383-1409), eigen_old, axisFromEigen, getExtentAndCenter_pointcloud (:229-292).
+// Only the OBB part is needed by the collide traversal.
+// ---------------------------------------------------------------------------------------
+void sphere_obb_impl(double radius, const Pose& tf, Node& bv) {
+  const double m = (1 + std::sqrt(5.0)) / 2.0;
+  const double edge = radius * 6 / (std::sqrt(27.0) + std::sqrt(15.0));
+  const double a = edge, b = m * edge;
+  const double L[12][3] = {{0, a, b}, {0, -a, b}, {0, a, -b}, {0, -a, -b}, {a, b, 0}, {-a, b, 0},
+                           {a, -b, 0}, {-a, -b, 0}, {b, 0, a}, {b, 0, -a}, {-b, 0, a}, {-b, 0, -a}};
+  Vec3 ps[12];
+  for (int i = 0; i < 12; ++i) ps[i] = add(mul(tf.R, Vec3{{L[i][0], L[i][1], L[i][2]}}), tf.t);
+  double S1[3] = {0, 0, 0}, S2[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int i = 0; i < 12; ++i) {
+    const Vec3& p = ps[i];
+    for (int k = 0; k < 3; ++k) S1[k] += p[k];
+    S2[0][0] += (p[0] * p[0]);
+    S2[1][1] += (p[1] * p[1]);
+    S2[2][2] += (p[2] * p[2]);
+    S2[0][1] += (p[0] * p[1]);
+    S2[0][2] += (p[0] * p[2]);
+    S2[1][2] += (p[1] * p[2]);
+  }
+  const int n_points = 12;
+  double M[3][3];
+  M[0][0] = S2[0][0] - S1[0] * S1[0] / n_points;
+  M[1][1] = S2[1][1] - S1[1] * S1[1] / n_points;
+  M[2][2] = S2[2][2] - S1[2] * S1[2] / n_points;
+  M[0][1] = S2[0][1] - S1[0] * S1[1] / n_points;
+  M[1][2] = S2[1][2] - S1[1] * S1[2] / n_points;
+  M[0][2] = S2[0][2] - S1[0] * S1[2] / n_points;
+  M[1][0] = M[0][1];
+  M[2][0] = M[0][2];
+  M[2][1] = M[1][2];
+  double sv[3], E[3][3];
+  Builder::jacobi(M, sv, E);
+  Builder::axis_from_eigen(E, sv, bv.axis);
+  const double real_max = std::numeric_limits<double>::max();
+  double mn[3] = {real_max, real_max, real_max}, mx[3] = {-real_max, -real_max, -real_max};
+  for (int i = 0; i < 12; ++i)
+    for (int k = 0; k < 3; ++k) {
+      const double proj = dot(col(bv.axis, k), ps[i]);
+      if (proj > mx[k]) mx[k] = proj;
+      if (proj < mn[k]) mn[k] = proj;
+    }
+  const Vec3 o{{(mx[0] + mn[0]) / 2, (mx[1] + mn[1]) / 2, (mx[2] + mn[2]) / 2}};
+  bv.obb_To = mul(bv.axis, o);
+  bv.obb_ext = Vec3{{(mx[0] - mn[0]) * 0.5, (mx[1] - mn[1]) * 0.5, (mx[2] - mn[2]) * 0.5}};
+  bv.first_child = -1;
+  bv.first_primitive = 0;
+  bv.num_primitives = 0;
+  bv.rss_To = bv.obb_To;
+  bv.rss_l[0] = bv.rss_l[1] = 0;
+  bv.rss_r = 0;
+}
+
 }  // namespace
 
 // beginModel/addSubModel/endModel/buildTree — BVH_model-inl.h:207-253,383-517,833-864
@@ -695,6 +754,109 @@ double brute_distance(const Model& m1, const Pose& tf1, const Model& m2, const P
   out.p1 = add(mul(tf1.R, ctx.p1), tf1.t);
   out.p2 = add(mul(tf1.R, ctx.p2), tf1.t);
   return out.min_distance;
+}
+
+// ---------------------------------------------------------------------------------------
+// Mesh <-> sphere collide: BVHShapeCollider<OBBRSS, Sphere>::collide -> orientedBVHShapeCollide
+// (detail/collision_func_matrix-inl.h:378-430) -> initialize / setupMeshShapeCollisionOrientedNode
+// (computeBV(model2, tf2, model2_bv)) -> collisionRecurse with a leaf second node.
+// ---------------------------------------------------------------------------------------
+void sphere_obb(double radius, const Pose& tf, Node& bv) { sphere_obb_impl(radius, tf, bv); }
+
+namespace {
+struct MeshSphereCtx {
+  const Model& m1;
+  Pose tf1, tf2;
+  double radius;
+  Node shape_bv;
+  size_t max_contacts;
+  bool enable_contact;
+  std::vector<Contact>& out;
+  long long n_bv = 0, n_leaf = 0;
+
+  bool can_stop() const { return !out.empty() && max_contacts <= out.size(); }
+
+  // MeshShapeCollisionTraversalNodeOBBRSS::BVTesting (mesh_shape_collision_traversal_node-inl.h:398-404):
+  // !overlap(tf1.linear(), tf1.translation(), model2_bv, model1->getBV(b1).bv)
+  bool bv_disjoint(int b1) {
+    n_bv++;
+    return !obb_overlap(tf1.R, tf1.t, shape_bv, m1.nodes[b1]);
+  }
+
+  // meshShapeCollisionOrientedNodeLeafTesting (:193-262) with the sphere specialisation of the transformed
+  // shapeTriangleIntersect (gjk_solver_libccd-inl.h:479-497): triangle moved to the world by tf1
+  void leaf(int b1) {
+    n_leaf++;
+    const int id = -(m1.nodes[b1].first_child + 1);
+    const Tri& t = m1.tris[id];
+    const Vec3 p1 = add(mul(tf1.R, m1.verts[t.v[0]]), tf1.t);
+    const Vec3 p2 = add(mul(tf1.R, m1.verts[t.v[1]]), tf1.t);
+    const Vec3 p3 = add(mul(tf1.R, m1.verts[t.v[2]]), tf1.t);
+    if (!enable_contact) {
+      if (sphere_tri_intersect(tf2.t, radius, p1, p2, p3, nullptr, nullptr, nullptr)) {
+        if (max_contacts > out.size()) {
+          Contact c{};
+          c.b1 = id;
+          c.b2 = -1;
+          out.push_back(c);
+        }
+      }
+    } else {
+      Vec3 cp, nrm;
+      double pen;
+      if (sphere_tri_intersect(tf2.t, radius, p1, p2, p3, &cp, &pen, &nrm)) {
+        if (max_contacts > out.size()) {
+          Contact c;
+          c.b1 = id;
+          c.b2 = -1;
+          c.pos = cp;
+          c.normal = Vec3{{-nrm[0], -nrm[1], -nrm[2]}};
+          c.depth = pen;
+          out.push_back(c);
+        }
+      }
+    }
+  }
+
+  // collisionRecurse (traversal_recurse-inl.h:84-130): the second node is always a leaf, firstOverSecond = true
+  void recurse(int b1) {
+    const Node& n1 = m1.nodes[b1];
+    if (n1.first_child < 0) {
+      if (bv_disjoint(b1)) return;
+      leaf(b1);
+      return;
+    }
+    if (bv_disjoint(b1)) return;
+    recurse(n1.first_child);
+    if (can_stop()) return;
+    recurse(n1.first_child + 1);
+  }
+};
+}  // namespace
+
+size_t collide_mesh_sphere(const Model& m1, const Pose& tf1, double radius, const Pose& tf2, size_t num_max_contacts,
+                           bool enable_contact, std::vector<Contact>& out, CollideStats* stats) {
+  if (num_max_contacts == 0) return 0;
+  if (!out.empty() && num_max_contacts <= out.size()) return out.size();
+  if (m1.nodes.empty()) return out.size();
+  MeshSphereCtx ctx{m1, tf1, tf2, radius, Node{}, num_max_contacts, enable_contact, out};
+  sphere_obb(radius, tf2, ctx.shape_bv);
+  ctx.recurse(0);
+  if (stats) {
+    stats->n_bv += ctx.n_bv;
+    stats->n_leaf += ctx.n_leaf;
+  }
+  return out.size();
+}
+
+void brute_mesh_sphere(const Model& m1, const Pose& tf1, double radius, const Pose& tf2, std::vector<int>& tris) {
+  for (int i = 0; i < (int)m1.tris.size(); ++i) {
+    const Tri& t = m1.tris[i];
+    const Vec3 p1 = add(mul(tf1.R, m1.verts[t.v[0]]), tf1.t);
+    const Vec3 p2 = add(mul(tf1.R, m1.verts[t.v[1]]), tf1.t);
+    const Vec3 p3 = add(mul(tf1.R, m1.verts[t.v[2]]), tf1.t);
+    if (sphere_tri_intersect(tf2.t, radius, p1, p2, p3, nullptr, nullptr, nullptr)) tris.push_back(i);
+  }
 }
 
 }  // namespace oracle

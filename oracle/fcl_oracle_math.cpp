@@ -720,4 +720,100 @@ double tri_distance(const Vec3 T1[3], const Vec3 T2[3], Vec3& P, Vec3& Q) {
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------
+// sphereTriangleIntersect and its helpers segmentSqrDistance / projectInTriangle --
+// narrowphase/detail/primitive_shape_algorithm/sphere_triangle-inl.h:85-244
+// ---------------------------------------------------------------------------------------
+namespace {
+double segment_sqr_distance(const Vec3& from, const Vec3& to, const Vec3& p, Vec3& nearest) {  // :85-111
+  Vec3 diff = sub(p, from);
+  const Vec3 v = sub(to, from);
+  double t = dot(v, diff);
+  if (t > 0) {
+    const double dotVV = dot(v, v);
+    if (t < dotVV) {
+      t /= dotVV;
+      diff = sub(diff, scale(v, t));
+    } else {
+      t = 1;
+      diff = sub(diff, v);
+    }
+  } else {
+    t = 0;
+  }
+  nearest = add(from, scale(v, t));
+  return dot(diff, diff);
+}
+
+bool project_in_triangle(const Vec3& p1, const Vec3& p2, const Vec3& p3, const Vec3& normal, const Vec3& p) {  // :115-139
+  const Vec3 edge1 = sub(p2, p1), edge2 = sub(p3, p2), edge3 = sub(p1, p3);
+  const Vec3 p1_to_p = sub(p, p1), p2_to_p = sub(p, p2), p3_to_p = sub(p, p3);
+  const double r1 = dot(cross(edge1, normal), p1_to_p);
+  const double r2 = dot(cross(edge2, normal), p2_to_p);
+  const double r3 = dot(cross(edge3, normal), p3_to_p);
+  return (r1 > 0 && r2 > 0 && r3 > 0) || (r1 <= 0 && r2 <= 0 && r3 <= 0);
+}
+}  // namespace
+
+bool sphere_tri_intersect(const Vec3& center, double radius, const Vec3& P1, const Vec3& P2, const Vec3& P3,
+                          Vec3* contact_point_out, double* penetration_depth, Vec3* normal_out) {  // :143-244
+  Vec3 normal = cross(sub(P2, P1), sub(P3, P1));
+  {  // Eigen normalize(): v /= sqrt(v.squaredNorm()), a true division per component
+    const double nn = norm(normal);
+    normal = Vec3{{normal[0] / nn, normal[1] / nn, normal[2] / nn}};
+  }
+  const double radius_with_threshold = radius + std::numeric_limits<double>::epsilon();
+  const Vec3 p1_to_center = sub(center, P1);
+  double distance_from_plane = dot(p1_to_center, normal);
+  if (distance_from_plane < 0) {
+    distance_from_plane *= -1;
+    normal = scale(normal, -1.0);
+  }
+  const bool is_inside_contact_plane = distance_from_plane < radius_with_threshold;
+  bool has_contact = false;
+  Vec3 contact_point{{0, 0, 0}};
+  if (is_inside_contact_plane) {
+    if (project_in_triangle(P1, P2, P3, normal, center)) {
+      has_contact = true;
+      contact_point = sub(center, scale(normal, distance_from_plane));
+    } else {
+      const double contact_capsule_radius_sqr = radius_with_threshold * radius_with_threshold;
+      Vec3 nearest_on_edge;
+      double distance_sqr = segment_sqr_distance(P1, P2, center, nearest_on_edge);
+      if (distance_sqr < contact_capsule_radius_sqr) {
+        has_contact = true;
+        contact_point = nearest_on_edge;
+      }
+      distance_sqr = segment_sqr_distance(P2, P3, center, nearest_on_edge);
+      if (distance_sqr < contact_capsule_radius_sqr) {
+        has_contact = true;
+        contact_point = nearest_on_edge;
+      }
+      distance_sqr = segment_sqr_distance(P3, P1, center, nearest_on_edge);
+      if (distance_sqr < contact_capsule_radius_sqr) {
+        has_contact = true;
+        contact_point = nearest_on_edge;
+      }
+    }
+  }
+  if (has_contact) {
+    const Vec3 contact_to_center = sub(contact_point, center);
+    const double distance_sqr = sqnorm(contact_to_center);
+    if (distance_sqr < radius_with_threshold * radius_with_threshold) {
+      if (distance_sqr > 0) {
+        const double distance = std::sqrt(distance_sqr);
+        if (normal_out) *normal_out = Vec3{{contact_to_center[0] / distance, contact_to_center[1] / distance, contact_to_center[2] / distance}};  // normalized()
+        if (contact_point_out) *contact_point_out = contact_point;
+        if (penetration_depth) *penetration_depth = -(radius - distance);
+      } else {
+        if (normal_out) *normal_out = scale(normal, -1.0);
+        if (contact_point_out) *contact_point_out = contact_point;
+        if (penetration_depth) *penetration_depth = -radius;
+      }
+      return true;
+    }
+  }
+  return false;
+}
+
 }  // namespace oracle

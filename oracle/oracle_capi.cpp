@@ -163,6 +163,50 @@ void* orc_collide_batch(void* h1, void* h2, long long n, const double* tf1, cons
   return b;
 }
 
+// mesh <-> sphere collide batch: tf1 poses of the mesh, tf2 poses of the sphere (only the translation matters
+// for the leaf test; the rotation enters the sphere's fitted OBB)
+void* orc_collide_mesh_sphere_batch(void* h1, double radius, long long n, const double* tf1, const double* tf2,
+                                    long long num_max_contacts, int enable_contact, int nthreads) {
+  Model* m1 = (Model*)h1;
+  CollideBatch* b = new CollideBatch;
+  b->counts.assign(n, 0);
+  b->per_pose.resize(n);
+  b->n_bv.assign(n, 0);
+  b->n_leaf.assign(n, 0);
+  auto t0 = std::chrono::steady_clock::now();
+  parallel_for(n, nthreads, [&](long long i) {
+    Pose a = pose_from(tf1 ? tf1 + 12 * i : nullptr);
+    Pose c = pose_from(tf2 ? tf2 + 12 * i : nullptr);
+    CollideStats st;
+    collide_mesh_sphere(*m1, a, radius, c, (size_t)num_max_contacts, enable_contact != 0, b->per_pose[i], &st);
+    b->counts[i] = (int32_t)b->per_pose[i].size();
+    b->n_bv[i] = st.n_bv;
+    b->n_leaf[i] = st.n_leaf;
+  });
+  b->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return b;
+}
+
+// ids of all triangles the sphere intersects (brute force, primitive order); returns the count
+long long orc_brute_mesh_sphere(void* h1, double radius, const double* tf1, const double* tf2, int32_t* out, long long cap) {
+  std::vector<int> tris;
+  brute_mesh_sphere(*(Model*)h1, pose_from(tf1), radius, pose_from(tf2), tris);
+  for (size_t i = 0; i < tris.size() && (long long)i < cap; ++i) out[i] = tris[i];
+  return (long long)tris.size();
+}
+
+// unit kernel: sphere (center, radius) vs triangle (9 doubles) in one frame; out7 = contact point, depth, normal
+int orc_sphere_tri_intersect(const double* center, double radius, const double* tri9, double* out7) {
+  Vec3 cp{{0, 0, 0}}, nrm{{0, 0, 0}};
+  double pen = 0;
+  const bool hit = sphere_tri_intersect(Vec3{{center[0], center[1], center[2]}}, radius, Vec3{{tri9[0], tri9[1], tri9[2]}}, Vec3{{tri9[3], tri9[4], tri9[5]}}, Vec3{{tri9[6], tri9[7], tri9[8]}}, &cp, &pen, &nrm);
+  if (out7 && hit) {
+    for (int k = 0; k < 3; ++k) { out7[k] = cp[k]; out7[4 + k] = nrm[k]; }
+    out7[3] = pen;
+  }
+  return hit ? 1 : 0;
+}
+
 double orc_collide_seconds(void* hb) { return ((CollideBatch*)hb)->seconds; }
 
 long long orc_collide_total(void* hb) {

@@ -184,6 +184,53 @@ def collide_batch(m1, m2, tf1, tf2=None, num_max_contacts=1, enable_contact=Fals
     return dict(counts=counts, contacts=contacts, offsets=offsets, n_bv=n_bv, n_leaf=n_leaf, seconds=secs)
 
 
+def collide_mesh_sphere_batch(m1, radius, tf1, tf2, num_max_contacts=1, enable_contact=False, nthreads=1):
+    """fcl::collide(BVHModel<OBBRSS>, tf1[i], Sphere(radius), tf2[i]); contacts carry b2 = -1 (Contact::NONE)."""
+    tf1 = _poses(tf1)
+    tf2 = _poses(tf2)
+    n = len(tf1) if tf1 is not None else len(tf2)
+    L = lib()
+    L.orc_collide_mesh_sphere_batch.restype = C.c_void_p
+    L.orc_collide_mesh_sphere_batch.argtypes = [C.c_void_p, C.c_double, C.c_longlong, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                                C.c_longlong, C.c_int, C.c_int]
+    hb = L.orc_collide_mesh_sphere_batch(m1.h, float(radius), n, _dp(tf1), _dp(tf2), int(num_max_contacts), int(enable_contact), nthreads)
+    try:
+        total = L.orc_collide_total(hb)
+        counts = np.empty(n, np.int32)
+        contacts = np.zeros(total, CONTACT_DTYPE)
+        n_bv = np.empty(n, np.int64)
+        n_leaf = np.empty(n, np.int64)
+        L.orc_collide_copy(hb, _ip(counts), contacts.ctypes.data_as(C.c_void_p), _lp(n_bv), _lp(n_leaf))
+    finally:
+        L.orc_collide_free(hb)
+    offsets = np.zeros(n + 1, np.int64)
+    np.cumsum(counts, out=offsets[1:])
+    return dict(counts=counts, contacts=contacts, offsets=offsets, n_bv=n_bv, n_leaf=n_leaf)
+
+
+def brute_mesh_sphere(m1, radius, tf1, tf2):
+    """Ids of every triangle of m1 (posed by tf1) the sphere (centre tf2's translation) intersects."""
+    L = lib()
+    L.orc_brute_mesh_sphere.restype = C.c_longlong
+    L.orc_brute_mesh_sphere.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_longlong]
+    a = np.ascontiguousarray(tf1, dtype=np.float64).reshape(12)
+    b = np.ascontiguousarray(tf2, dtype=np.float64).reshape(12)
+    out = np.empty(m1.num_tris, np.int32)
+    k = L.orc_brute_mesh_sphere(m1.h, float(radius), _dp(a), _dp(b), _ip(out), len(out))
+    return out[:k]
+
+
+def sphere_tri_intersect(center, radius, tri9):
+    """(hit, contact_point[3], depth, normal[3]) of sphereTriangleIntersect in one frame."""
+    L = lib()
+    L.orc_sphere_tri_intersect.argtypes = [C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    c = np.ascontiguousarray(center, dtype=np.float64).reshape(3)
+    t = np.ascontiguousarray(tri9, dtype=np.float64).reshape(9)
+    out = np.zeros(7)
+    hit = L.orc_sphere_tri_intersect(_dp(c), float(radius), _dp(t), _dp(out))
+    return bool(hit), out[:3].copy(), float(out[3]), out[4:].copy()
+
+
 def distance_batch(m1, m2, tf1, tf2=None, enable_nearest_points=True, qsize=2, nthreads=1):
     tf1 = _poses(tf1)
     tf2 = _poses(tf2)

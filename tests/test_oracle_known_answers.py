@@ -165,3 +165,59 @@ def test_contact_geometry_box_box(oracle):
     c = r["contacts"]
     assert np.allclose(np.linalg.norm(c["normal"], axis=1), 1.0, atol=1e-12)
     assert (np.abs(c["pos"]) <= 2.5 + 1e-9).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# mesh <-> sphere (closed-form sphereTriangleIntersect; no GJK on this pair)
+# ---------------------------------------------------------------------------------------------
+def test_sphere_triangle_known_answers(oracle):
+    """test/test_fcl_geometric_shapes.cpp:1248-1287 (shapeIntersection_spheretriangle): sphere r = 10 at the
+    origin hits both triangles; for the second one the normal is (1, 0, 0); the same after a rigid motion of
+    both (normal rotated accordingly)."""
+    from fcl_b200.poses import random_poses
+
+    t_a = np.array([[20.0, 0, 0], [-20, 0, 0], [0, 20, 0]])
+    t_b = np.array([[30.0, 0, 0], [9.9, -20, 0], [9.9, 20, 0]])
+    hit, _, _, _ = oracle.sphere_tri_intersect([0, 0, 0], 10.0, t_a)
+    assert hit
+    hit, cp, depth, n = oracle.sphere_tri_intersect([0, 0, 0], 10.0, t_b)
+    assert hit and np.allclose(n, [1, 0, 0], atol=1e-9) and np.allclose(cp, [9.9, 0, 0]) and abs(depth + 0.1) < 1e-12
+    for pose in random_poses(20, seed=71):
+        R, t = pose[:9].reshape(3, 3), pose[9:]
+        hit, _, _, _ = oracle.sphere_tri_intersect(t, 10.0, t_a @ R.T + t)
+        assert hit
+        hit, _, _, n = oracle.sphere_tri_intersect(t, 10.0, t_b @ R.T + t)
+        assert hit and np.allclose(n, R @ np.array([1.0, 0, 0]), atol=1e-9)
+    # just outside (gap beyond the epsilon threshold) / touching an edge from outside the face
+    assert not oracle.sphere_tri_intersect([0, 0, 10.0 + 1e-9], 10.0, t_a)[0]
+    assert oracle.sphere_tri_intersect([0, -5.0, 0], 10.0, t_a)[0]       # projects outside, edge within reach
+    assert not oracle.sphere_tri_intersect([0, -10.5, 0], 10.0, t_a)[0]
+
+
+def test_mesh_sphere_traversal_equals_brute_force(oracle, oracle_env_rob):
+    """The OBBRSS traversal with the sphere's fitted OBB reports exactly the triangles the brute-force loop finds
+    (in DFS order), budgets truncate that list, and every contact has b2 = -1 (Contact::NONE)."""
+    from fcl_b200.poses import identity_poses, random_poses
+
+    env, _ = oracle_env_rob
+    n = 300
+    S = random_poses(n, seed=73)       # sphere poses inside env's extents
+    M = identity_poses(n)
+    M[: n // 2] = random_poses(n // 2, seed=79)  # half of the queries also move the mesh
+    S[: n // 2, 9:] = np.einsum("nij,nj->ni", M[: n // 2, :9].reshape(-1, 3, 3), S[: n // 2, 9:]) + M[: n // 2, 9:]
+    radius = 400.0
+    full = oracle.collide_mesh_sphere_batch(env, radius, M, S, 1 << 30, True, nthreads=4)
+    few = oracle.collide_mesh_sphere_batch(env, radius, M, S, 3, False, nthreads=4)
+    hits = 0
+    for i in range(n):
+        ids = full["contacts"]["b1"][full["offsets"][i]:full["offsets"][i + 1]]
+        brute = oracle.brute_mesh_sphere(env, radius, M[i], S[i])
+        assert sorted(ids.tolist()) == brute.tolist(), i
+        assert (full["contacts"]["b2"][full["offsets"][i]:full["offsets"][i + 1]] == -1).all()
+        k = few["contacts"]["b1"][few["offsets"][i]:few["offsets"][i + 1]]
+        assert k.tolist() == ids[:3].tolist()
+        hits += len(brute) > 0
+    assert 0.15 * n < hits < 0.95 * n
+    c = full["contacts"]
+    assert (c["depth"] <= 0).all() and (c["depth"] >= -radius).all()
+    assert np.allclose(np.linalg.norm(c["normal"], axis=1), 1.0, atol=1e-12)
