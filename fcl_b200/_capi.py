@@ -50,6 +50,7 @@ SYMBOLS = [
     "fclgpu_bvh_build_obbrss", "fclgpu_bvh_destroy", "fclgpu_bvh_num_nodes", "fclgpu_bvh_num_tris", "fclgpu_bvh_get",
     "fclgpu_bvh_refit_topdown", "fclgpu_bvh_num_vertices", "fclgpu_bvh_get_partition", "fclgpu_model_set_partition",
     "fclgpu_model_refit_topdown", "fclgpu_model_download", "fclgpu_model_build_obbrss", "fclgpu_model_get_topology",
+    "fclgpu_collide_mesh_sphere_batch", "fclgpu_collide_mesh_sphere_batch_host",
     "fclgpu_model_create_obbrss", "fclgpu_model_from_bvh", "fclgpu_model_destroy", "fclgpu_model_num_nodes",
     "fclgpu_model_num_tris", "fclgpu_model_device", "fclgpu_collide_batch", "fclgpu_collide_batch_host",
     "fclgpu_distance_batch", "fclgpu_distance_batch_host", "fclgpu_abi_version", "fclgpu_device_count",
@@ -96,6 +97,10 @@ def lib():
                                        vp, up, up, vp]
     L.fclgpu_collide_batch_host.argtypes = [vp, vp, C.c_int64, dp, dp, C.POINTER(CollisionRequestC), ip, vp,
                                             C.c_int64, vp, up, up]
+    L.fclgpu_collide_mesh_sphere_batch.argtypes = [vp, C.c_double, C.c_int64, dp, dp, C.POINTER(CollisionRequestC), ip, vp,
+                                                   C.c_int64, vp, up, up, vp]
+    L.fclgpu_collide_mesh_sphere_batch_host.argtypes = [vp, C.c_double, C.c_int64, dp, dp, C.POINTER(CollisionRequestC), ip,
+                                                        vp, C.c_int64, vp, up, up]
     L.fclgpu_distance_batch.argtypes = [vp, vp, C.c_int64, dp, dp, C.POINTER(DistanceRequestC), dp, dp, dp, ip, ip,
                                         up, up, vp]
     L.fclgpu_distance_batch_host.argtypes = [vp, vp, C.c_int64, dp, dp, C.POINTER(DistanceRequestC), dp, dp, dp, ip,

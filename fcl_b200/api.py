@@ -374,6 +374,23 @@ def _current_device():
     return 0
 
 
+class Sphere:
+    """fcl::Sphere<double> (geometry/shape/sphere.h): centred at the origin of its own frame.  On this path it is
+    the second geometry of a mesh <-> sphere collide."""
+
+    def __init__(self, radius):
+        self.radius = float(radius)
+        self.cost_density = 1.0
+        self.threshold_occupied = 1.0
+        self.threshold_free = 0.0
+
+    def getObjectType(self):
+        return "OT_GEOM"
+
+    def getNodeType(self):
+        return "GEOM_SPHERE"
+
+
 class CollisionObject:
     """fcl::CollisionObject<double> for BVHModel geometries (narrowphase/collision_object.h): a geometry
     plus a transform; collide(o1, o2, request, result) / distance(o1, o2, request, result) forward the
@@ -593,6 +610,45 @@ def collide_batch(o1, tf1, o2, tf2, request, contact_capacity=None, want_contact
     return res
 
 
+def collide_mesh_sphere_batch(o1, tf1, sphere, tf2, request, contact_capacity=None, want_contacts=True, stats=False,
+                              device=None, grow_on_overflow=False):
+    """n independent fcl::collide(mesh, tf1[i], Sphere, tf2[i]) calls (host arrays in and out).  Contacts: one per
+    intersecting triangle, b2 = -1 (Contact::NONE), in the reference's traversal order."""
+    tf1, n1 = _poses(tf1)
+    tf2, n2 = _poses(tf2)
+    n = n1 if n1 is not None else n2
+    if n is None:
+        raise ValueError("at least one of tf1/tf2 must be given")
+    if n1 is not None and n2 is not None and n1 != n2:
+        raise ValueError("tf1 and tf2 must have the same length")
+    m1 = o1.device_model(device)
+    req = request._c()
+    counts = np.zeros(n, np.int32)
+    if want_contacts:
+        if contact_capacity is None:
+            contact_capacity = int(min(max(request.num_max_contacts, 0), 64)) * n
+        contact_capacity = max(int(contact_capacity), 1)
+        contacts = np.zeros(contact_capacity, CONTACT_DTYPE)
+        offsets = np.zeros(n + 1, np.int64)
+    else:
+        contact_capacity, contacts, offsets = 0, None, None
+    n_bv = np.zeros(n, np.uint32) if stats else None
+    n_leaf = np.zeros(n, np.uint32) if stats else None
+    rc = _capi.lib().fclgpu_collide_mesh_sphere_batch_host(m1, float(sphere.radius), n, addr(tf1), addr(tf2), C.byref(req),
+                                                           addr(counts), addr(contacts), contact_capacity, addr(offsets),
+                                                           addr(n_bv), addr(n_leaf))
+    if rc == _capi.ERR_CONTACT_OVERFLOW and grow_on_overflow:
+        need_stride = int(counts.max())
+        if need_stride > _capi.get_option("contact_stride"):
+            _capi.set_option("contact_stride", 1 << int(need_stride - 1).bit_length())
+        return collide_mesh_sphere_batch(o1, tf1, sphere, tf2, request, contact_capacity=int(counts.sum(dtype=np.int64)),
+                                         want_contacts=True, stats=stats, device=device, grow_on_overflow=False)
+    check(rc)
+    if want_contacts:
+        contacts = contacts[: offsets[n]]
+    return BatchCollisionResult(counts, contacts, offsets, n_bv, n_leaf)
+
+
 def distance_batch(o1, tf1, o2, tf2, request, stats=False, device=None, pinned=False):
     tf1, n1 = _poses(tf1)
     tf2, n2 = _poses(tf2)
@@ -660,17 +716,21 @@ def collide(o1, tf1, o2=None, tf2=None, request=None, result=None):
     if request.num_max_contacts == 0:
         sys.stderr.write(f"Warning: should stop early as num_max_contact is {request.num_max_contacts} !\n")
         return 0
-    if not (isinstance(o1, BVHModel) and isinstance(o2, BVHModel)):
+    mesh_sphere = isinstance(o1, BVHModel) and isinstance(o2, Sphere)
+    if not (isinstance(o1, BVHModel) and isinstance(o2, BVHModel)) and not mesh_sphere:
         sys.stderr.write("Warning: collision function between these node types is not supported\n")
         return 0
-    if request.isSatisfied(result):  # orientedMeshCollide, collision_func_matrix-inl.h:580
+    if request.isSatisfied(result):  # orientedMeshCollide / orientedBVHShapeCollide, collision_func_matrix-inl.h:580,389
         return result.numContacts()
     if request.enable_cost:
         raise FclGpuError(BVH_ERR_UNSUPPORTED_FUNCTION, "cost sources are not supported on this path")
     # a non-empty result consumes part of the contact budget
     budget = request.num_max_contacts - result.numContacts()
     sub = CollisionRequest(budget, request.enable_contact)
-    r = collide_batch(o1, tf1, o2, tf2, sub, contact_capacity=min(budget, 256), grow_on_overflow=True)
+    if mesh_sphere:
+        r = collide_mesh_sphere_batch(o1, tf1, o2, tf2, sub, contact_capacity=min(budget, 256), grow_on_overflow=True)
+    else:
+        r = collide_batch(o1, tf1, o2, tf2, sub, contact_capacity=min(budget, 256), grow_on_overflow=True)
     for c in r.contacts_of(0):
         if request.enable_contact:
             result.addContact(Contact(o1, o2, int(c["b1"]), int(c["b2"]), c["pos"].copy(), c["normal"].copy(),

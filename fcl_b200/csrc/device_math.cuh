@@ -612,6 +612,85 @@ FD double tri_distance(const V3 T1[3], const V3 T2[3], V3& P, V3& Q) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Sphere vs triangle (mesh <-> sphere collide): sphereTriangleIntersect,
+// narrowphase/detail/primitive_shape_algorithm/sphere_triangle-inl.h:85-244.  c = sphere centre, P[3] = triangle,
+// same frame.  On a hit: cp = contact point, depth = -(radius - distance) (<= 0), nrm = unit vector from the
+// centre to the contact point (the caller negates it, mesh_shape_collision_traversal_node-inl.h:243).
+// Structure differs from the oracle's restatement (one edge routine, last in-reach edge wins by a loop),
+// arithmetic order is the same.
+// ---------------------------------------------------------------------------------------
+FD double point_segment_sq(const V3& a, const V3& b, const V3& p, V3& nearest) {
+  V3 diff = p - a;
+  const V3 v = b - a;
+  double t = dot(v, diff);
+  if (t > 0) {
+    const double vv = dot(v, v);
+    if (t < vv) {
+      t /= vv;
+      diff = diff - v * t;
+    } else {
+      t = 1;
+      diff = diff - v;
+    }
+  } else {
+    t = 0;
+  }
+  nearest = a + v * t;
+  return dot(diff, diff);
+}
+
+FD bool sphere_tri_intersect(const V3& c, double radius, const V3 P[3], V3& cp, double& depth, V3& nrm) {
+  V3 n = cross(P[1] - P[0], P[2] - P[0]);
+  {
+    const double len = sqrt(dot(n, n));
+    n = mk(n.x / len, n.y / len, n.z / len);
+  }
+  const double reach = radius + 2.220446049250313e-16;  // radius + epsilon
+  double h = dot(c - P[0], n);
+  if (h < 0) {
+    h *= -1;
+    n = n * (-1.0);
+  }
+  if (!(h < reach)) return false;
+  bool touched = false;
+  V3 q = mk(0, 0, 0);
+  {
+    const double r1 = dot(cross(P[1] - P[0], n), c - P[0]);
+    const double r2 = dot(cross(P[2] - P[1], n), c - P[1]);
+    const double r3 = dot(cross(P[0] - P[2], n), c - P[2]);
+    if ((r1 > 0 && r2 > 0 && r3 > 0) || (r1 <= 0 && r2 <= 0 && r3 <= 0)) {
+      touched = true;
+      q = c - n * h;
+    } else {
+      const double reach2 = reach * reach;
+#pragma unroll 1
+      for (int e = 0; e < 3; ++e) {  // edges P1P2, P2P3, P3P1: the last one within reach supplies the point
+        V3 near_e;
+        const double d2 = point_segment_sq(sel3(P, e), sel3(P, (e + 1) % 3), c, near_e);
+        if (d2 < reach2) {
+          touched = true;
+          q = near_e;
+        }
+      }
+    }
+  }
+  if (!touched) return false;
+  const V3 w = q - c;
+  const double d2 = dot(w, w);
+  if (!(d2 < reach * reach)) return false;
+  cp = q;
+  if (d2 > 0) {
+    const double d = sqrt(d2);
+    nrm = mk(w.x / d, w.y / d, w.z / d);
+    depth = -(radius - d);
+  } else {
+    nrm = n * (-1.0);
+    depth = -radius;
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------
 // BV-pair tests in the relative pose (R0, T0) of model2 in model1's frame.
 //   overlap(R0,T0,OBB,OBB)   include/fcl/math/bv/OBB-inl.h:384-395
 //   distance(R0,T0,RSS,RSS)  include/fcl/math/bv/RSS-inl.h:1957-1974

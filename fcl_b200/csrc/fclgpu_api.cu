@@ -729,6 +729,7 @@ struct CollideExtra {
   int ready_shift = 0;
   long long ready_q0 = 0;           // index of this call's first query in the flagged batch
   bool continue_scan = false;       // keep the running contact offset of the previous call (sub-batches of one result)
+  double sphere_radius = -1.0;      // >= 0: model 2 is a sphere of this radius (mesh <-> sphere collide)
 };
 int collide_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1, const double* tf2,
                     const fclgpu_collision_request* request, int32_t* num_contacts, fclgpu_contact* contacts,
@@ -753,7 +754,7 @@ int collide_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, c
   if (m1->device != m2->device) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "models live on different devices");
   if (request->enable_cost) return fail(FCLGPU_ERR_UNSUPPORTED_FUNCTION, "cost sources are not supported on this path");
   if (!num_contacts) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "num_contacts is NULL");
-  if (m1->depth + m2->depth + 2 > kStackCap)
+  if (m1->depth + (X.sphere_radius >= 0 ? 0 : m2->depth) + 2 > kStackCap)
     return fail(FCLGPU_ERR_STACK_OVERFLOW, "tree depths %d+%d exceed the traversal stack", m1->depth, m2->depth);
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_TRY(cudaSetDevice(m1->device));
@@ -811,7 +812,10 @@ int collide_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, c
     const long long trav = opt("traversal");
     const int trig = (int)opt("leaf_trigger");
     const long long front = opt("collide_front");  // 0 never, 1 (default) for BVHs beyond the caches, 2 always
-    if (!want_contacts && !P.enable_contact && trav >= 1 &&
+    if (X.sphere_radius >= 0) {
+      rc = stats ? launch_persistent(collide_mesh_sphere_kernel<true>, P, w, 128, st, 0, X.sphere_radius)
+                 : launch_persistent(collide_mesh_sphere_kernel<false>, P, w, 128, st, 0, X.sphere_radius);
+    } else if (!want_contacts && !P.enable_contact && trav >= 1 &&
         (front >= 2 || (front == 1 && (long long)m1->d.n_nodes + m2->d.n_nodes >= (1 << 17)))) {
       // counts only: the result does not depend on the visiting order -> warp-per-query front kernel
       const size_t fsm = sizeof(CollideFront) * 4;
@@ -867,6 +871,20 @@ int collide_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, c
   return FCLGPU_OK;
 }
 }  // namespace
+
+// ------------------------------------------------------------------------------------------
+// mesh <-> sphere collide
+// ------------------------------------------------------------------------------------------
+extern "C" int fclgpu_collide_mesh_sphere_batch(const fclgpu_model* m1, double radius, int64_t n, const double* tf1,
+                                                const double* tf2, const fclgpu_collision_request* request,
+                                                int32_t* num_contacts, fclgpu_contact* contacts, int64_t contact_capacity,
+                                                int64_t* contact_offsets, uint32_t* n_bv, uint32_t* n_leaf, void* stream) {
+  if (!(radius >= 0)) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "sphere radius must be >= 0");
+  CollideExtra X;
+  X.sphere_radius = radius;
+  return collide_enqueue(m1, m1, n, tf1, tf2, request, num_contacts, contacts, contact_capacity, contact_offsets, n_bv,
+                         n_leaf, stream, X);
+}
 
 // ------------------------------------------------------------------------------------------
 // distance
@@ -1215,6 +1233,58 @@ extern "C" int fclgpu_distance_batch_host(const fclgpu_model* m1, const fclgpu_m
   }
   return finish_pipeline(w, m1->device);
 }
+
+extern "C" int fclgpu_collide_mesh_sphere_batch_host(const fclgpu_model* m1, double radius, int64_t n, const double* tf1,
+                                                     const double* tf2, const fclgpu_collision_request* request,
+                                                     int32_t* num_contacts, fclgpu_contact* contacts,
+                                                     int64_t contact_capacity, int64_t* contact_offsets, uint32_t* n_bv,
+                                                     uint32_t* n_leaf) {
+  if (!m1 || !request || n < 0 || !num_contacts) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL model/request/num_contacts or n<0");
+  CUDA_TRY(cudaSetDevice(m1->device));
+  Workspace* w;
+  int rc = get_ws(m1->device, &w);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> host_lock(w->host_mu);
+  const bool want = contacts != nullptr || contact_offsets != nullptr;
+  if (contacts == nullptr) contact_capacity = 0;
+  const size_t bytes = (tf1 ? padded(96 * (size_t)n) : 0) + (tf2 ? padded(96 * (size_t)n) : 0) + padded(4 * (size_t)n) +
+                       (want ? padded(8 * (size_t)(n + 1)) + padded(64 * (size_t)contact_capacity) : 0) +
+                       (n_bv ? padded(4 * (size_t)n) : 0) + (n_leaf ? padded(4 * (size_t)n) : 0) + 256;
+  {
+    std::lock_guard<std::mutex> lock(w->mu);
+    rc = ensure(&w->dev_io, &w->dev_io_bytes, bytes);
+    if (rc) return rc;
+  }
+  DevBuf B{(char*)w->dev_io};
+  double* d_tf1 = tf1 ? B.take<double>(12 * (size_t)n) : nullptr;
+  double* d_tf2 = tf2 ? B.take<double>(12 * (size_t)n) : nullptr;
+  int32_t* d_cnt = B.take<int32_t>((size_t)n);
+  int64_t* d_off = want ? B.take<int64_t>((size_t)n + 1) : nullptr;
+  fclgpu_contact* d_con = (want && contact_capacity > 0) ? B.take<fclgpu_contact>((size_t)contact_capacity) : nullptr;
+  uint32_t* d_bv = n_bv ? B.take<uint32_t>((size_t)n) : nullptr;
+  uint32_t* d_leaf = n_leaf ? B.take<uint32_t>((size_t)n) : nullptr;
+  cudaStream_t st = w->pipe[1];
+  if (tf1) CUDA_TRY(cudaMemcpyAsync(d_tf1, tf1, 96 * (size_t)n, cudaMemcpyHostToDevice, st));
+  if (tf2) CUDA_TRY(cudaMemcpyAsync(d_tf2, tf2, 96 * (size_t)n, cudaMemcpyHostToDevice, st));
+  rc = fclgpu_collide_mesh_sphere_batch(m1, radius, n, d_tf1, d_tf2, request, d_cnt, d_con, contact_capacity, d_off, d_bv,
+                                        d_leaf, st);
+  if (rc) return rc;
+  if (n > 0) CUDA_TRY(cudaMemcpyAsync(num_contacts, d_cnt, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  if (n_bv && n > 0) CUDA_TRY(cudaMemcpyAsync(n_bv, d_bv, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  if (n_leaf && n > 0) CUDA_TRY(cudaMemcpyAsync(n_leaf, d_leaf, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  if (want && n > 0 && request->num_max_contacts > 0) {
+    if (contact_offsets) CUDA_TRY(cudaMemcpyAsync(contact_offsets, d_off, 8 * (size_t)(n + 1), cudaMemcpyDeviceToHost, st));
+    int64_t total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, d_off + n, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (contacts && total > 0)
+      CUDA_TRY(cudaMemcpyAsync(contacts, d_con, 64 * (size_t)std::min<int64_t>(total, contact_capacity), cudaMemcpyDeviceToHost, st));
+  } else if (contact_offsets) {
+    std::memset(contact_offsets, 0, 8 * (size_t)(n + 1));
+  }
+  return fclgpu_sync_status(m1->device, st);
+}
+
 
 // ------------------------------------------------------------------------------------------
 // utilities

@@ -1616,3 +1616,102 @@ __global__ void __launch_bounds__(128, 4) collide_front_kernel(CollideParams P) 
 }
 
 }  // namespace fclgpu
+
+namespace fclgpu {
+
+// ---------------------------------------------------------------------------------------
+// Mesh <-> sphere collide: fcl::collide(BVHModel<OBBRSS>, tf1, Sphere, tf2)
+// = BVHShapeCollider<OBBRSS, Sphere> -> orientedBVHShapeCollide (collision_func_matrix-inl.h:378-430)
+// -> collisionRecurse over the mesh tree with the sphere as a single leaf.  One lane per query,
+// depth first in the reference's order (left child first), so contacts -- one per intersecting
+// triangle, {b1 = triangle, b2 = -1 (Contact::NONE), pos, -normal, depth} -- come in the reference's
+// order and the num_max_contacts prefix is exact.
+// BV test: the reference tests the node's OBB against an OBB fitted around the sphere's 12 bound
+// vertices; any conservative test visits a superset of the nodes that can hold a contact and therefore
+// yields the same contacts.  Here: exact point-to-box distance of the sphere centre (in the mesh
+// frame) against the node's OBB, with a margin far above the rounding error -- tighter and 8x cheaper
+// than the box-box SAT.  Leaf: sphere_tri_intersect on the triangle moved to the world by tf1, like
+// the reference's transformed shapeTriangleIntersect (gjk_solver_libccd-inl.h:479-497).
+// ---------------------------------------------------------------------------------------
+template <bool kStats>
+__global__ void __launch_bounds__(128) collide_mesh_sphere_kernel(CollideParams P, double radius) {
+  int stk[kStackCap];
+  const int lane = threadIdx.x & 31;
+  (void)lane;
+  bool exhausted = false;
+  while (true) {
+    const long long q = fetch_work(!exhausted, P.work_counter);
+    if (__all_sync(0xffffffffu, exhausted || q >= P.n)) break;
+    if (exhausted) continue;
+    if (q >= P.n) {
+      exhausted = true;
+      continue;
+    }
+    const PoseRT tf1 = load_pose(P.tf1, q);
+    const PoseRT tf2 = load_pose(P.tf2, q);
+    const V3 c = tf2.t;                             // sphere centre, world
+    const V3 cm = mulTv(tf1.R, c - tf1.t);          // ... in the mesh frame
+    const double cm_l1 = (fabs(cm.x) + fabs(cm.y)) + fabs(cm.z);
+    long long count = 0;
+    uint32_t bv_tests = 0, leaf_tests = 0;
+    int sp = 0;
+    stk[sp++] = 0;
+    while (sp > 0) {
+      const int b = stk[--sp];
+      const NodeRec nd = load_node(P.m1.obb, b);
+      const int fc = __ldg(P.m1.first_child + b);
+      if (kStats) bv_tests++;
+      {
+        const V3 l = mulTv(nd.axis, cm - nd.To);
+        const double ex = fmax(fabs(l.x) - nd.e0, 0.0), ey = fmax(fabs(l.y) - nd.e1, 0.0), ez = fmax(fabs(l.z) - nd.e2, 0.0);
+        const double scale = (((fabs(nd.To.x) + fabs(nd.To.y)) + fabs(nd.To.z)) + ((nd.e0 + nd.e1) + nd.e2)) + cm_l1;
+        const double reach = radius * 1.000001 + 1e-6 * scale;
+        if ((ex * ex + ey * ey) + ez * ez > reach * reach) continue;  // certainly out of reach
+      }
+      if (fc >= 0) {
+        if (sp + 2 > kStackCap) {
+          atomicMin(P.status, (int)FCLGPU_ERR_STACK_OVERFLOW);
+          break;
+        }
+        stk[sp++] = fc + 1;
+        stk[sp++] = fc;  // left child first
+        continue;
+      }
+      const int id = -(fc + 1);
+      V3 T[3];
+      load_tri(P.m1.tri, id, T);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) T[k] = mulv(tf1.R, T[k]) + tf1.t;
+      if (kStats) leaf_tests++;
+      V3 cp, nrm;
+      double depth;
+      if (sphere_tri_intersect(c, radius, T, cp, depth, nrm)) {
+        if (count < P.max_contacts) {
+          if (P.scratch) {
+            if (count < P.stride) {
+              fclgpu_contact* o = P.scratch + q * P.stride + count;
+              o->b1 = id;
+              o->b2 = -1;
+              if (P.enable_contact) {
+                o->normal[0] = -nrm.x; o->normal[1] = -nrm.y; o->normal[2] = -nrm.z;
+                o->pos[0] = cp.x; o->pos[1] = cp.y; o->pos[2] = cp.z;
+                o->penetration_depth = depth;
+              }
+            } else {
+              atomicMin(P.status, (int)FCLGPU_ERR_CONTACT_OVERFLOW);
+            }
+          }
+          count++;
+        }
+        if (count > 0 && P.max_contacts <= count) sp = 0;  // canStop()
+      }
+    }
+    P.num_contacts[q] = (int32_t)count;
+    if (kStats) {
+      if (P.n_bv) P.n_bv[q] = bv_tests;
+      if (P.n_leaf) P.n_leaf[q] = leaf_tests;
+    }
+  }
+}
+
+}  // namespace fclgpu

@@ -190,6 +190,25 @@ int fclgpu_collide_batch_host(const fclgpu_model* m1, const fclgpu_model* m2, in
                               int64_t* contact_offsets, uint32_t* n_bv, uint32_t* n_leaf);
 
 /* ---------------------------------------------------------------------------------------
+ * Batched mesh <-> sphere collide: query i evaluates
+ * fcl::collide(m1, tf1[i], Sphere(radius), tf2[i], request, result_i) =
+ * BVHShapeCollider<OBBRSS<S>, Sphere<S>> -> orientedBVHShapeCollide
+ * (narrowphase/detail/collision_func_matrix-inl.h:378-430, mesh_shape_collision_traversal_node-inl.h:193-262)
+ * with the closed-form sphereTriangleIntersect leaf test (sphere_triangle-inl.h:143-244; no GJK on this pair).
+ * One contact per intersecting triangle, in the reference's traversal order: b1 = triangle id, b2 = -1
+ * (Contact::NONE), pos = contact point, normal = -(centre -> contact) direction, penetration_depth <= 0 as the
+ * reference reports it.  Same buffers, capacities and error conventions as fclgpu_collide_batch.
+ * ------------------------------------------------------------------------------------- */
+int fclgpu_collide_mesh_sphere_batch(const fclgpu_model* m1, double radius, int64_t n, const double* tf1,
+                                     const double* tf2, const fclgpu_collision_request* request,
+                                     int32_t* num_contacts, fclgpu_contact* contacts, int64_t contact_capacity,
+                                     int64_t* contact_offsets, uint32_t* n_bv, uint32_t* n_leaf, void* stream);
+int fclgpu_collide_mesh_sphere_batch_host(const fclgpu_model* m1, double radius, int64_t n, const double* tf1,
+                                          const double* tf2, const fclgpu_collision_request* request,
+                                          int32_t* num_contacts, fclgpu_contact* contacts, int64_t contact_capacity,
+                                          int64_t* contact_offsets, uint32_t* n_bv, uint32_t* n_leaf);
+
+/* ---------------------------------------------------------------------------------------
  * Batched distance: query i evaluates fcl::distance(m1, tf1[i], m2, tf2[i], request, result_i)
  * (distance-inl.h:92-246 -> orientedMeshDistance, distance_func_matrix-inl.h:386-403;
  * recursive traversal, qsize = 2, traversal/collision_node.h:67).

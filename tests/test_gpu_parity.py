@@ -512,3 +512,56 @@ def test_tiny_and_coincident_models_all_variants(oracle):
     finally:
         _capi.set_option("traversal", 3)
         _capi.set_option("collide_front", 1)
+
+
+def test_mesh_sphere_collide_matches_oracle(oracle, env_rob_npz):
+    """SURVEY 8f rank 2: fcl::collide(BVHModel<OBBRSS>, tf1, Sphere, tf2) on the GPU.  Contacts (triangle id,
+    b2 = -1, contact point, normal, depth), their order and the num_max_contacts truncation equal the oracle's bit
+    for bit, for fixed and moving meshes and through the single-query entry point."""
+    (ev, et), _ = env_rob_npz
+    env, oenv = F.BVHModel.from_arrays(ev, et), oracle.Model(ev, et)
+    n = 20000
+    S = random_poses(n, seed=83)
+    M = identity_poses(n)
+    M[: n // 2] = random_poses(n // 2, seed=89)
+    S[: n // 2, 9:] = np.einsum("nij,nj->ni", M[: n // 2, :9].reshape(-1, 3, 3), S[: n // 2, 9:]) + M[: n // 2, 9:]
+    sphere = F.Sphere(350.0)
+    for max_contacts, enable_contact in ((1, False), (5, True), (1 << 20, True)):
+        got = F.collide_mesh_sphere_batch(env, M, sphere, S, F.CollisionRequest(max_contacts, enable_contact),
+                                          contact_capacity=64 * n, grow_on_overflow=True, stats=True)
+        ref = oracle.collide_mesh_sphere_batch(oenv, sphere.radius, M, S, max_contacts, enable_contact, nthreads=8)
+        assert np.array_equal(got.num_contacts, ref["counts"]), (max_contacts, enable_contact)
+        assert np.array_equal(got.offsets, ref["offsets"])
+        assert np.array_equal(got.contacts["b1"], ref["contacts"]["b1"]) and (got.contacts["b2"] == -1).all()
+        if enable_contact:
+            assert got.contacts.tobytes() == ref["contacts"].tobytes()
+        assert (got.n_bv > 0).all()
+    assert 0.1 * n < (got.num_contacts > 0).sum() < 0.95 * n
+    # counts only
+    cnt = F.collide_mesh_sphere_batch(env, M, sphere, S, F.CollisionRequest(7, False), want_contacts=False)
+    ref7 = oracle.collide_mesh_sphere_batch(oenv, sphere.radius, M, S, 7, False, nthreads=8)
+    assert np.array_equal(cnt.num_contacts, ref7["counts"])
+    # single-query entry point, result accumulation like the reference
+    i = int(np.argmax(got.num_contacts))
+    res = F.CollisionResult()
+    k = F.collide(env, F.Transform3.from_pose12(M[i]), sphere, F.Transform3.from_pose12(S[i]), F.CollisionRequest(1000, True), res)
+    assert k == got.num_contacts[i] == res.numContacts()
+    c0 = res.getContact(0)
+    assert c0.b2 == -1 and c0.b1 == got.contacts_of(i)[0]["b1"] and c0.penetration_depth <= 0
+
+
+def test_mesh_sphere_on_a_large_mesh(oracle):
+    from tests.meshes import heightfield
+
+    v, t = heightfield(200, size=10.0, seed=7, amp=0.5)  # 79,202 triangles
+    m, o = F.BVHModel.from_arrays(v, t, build_on_device=True), oracle.Model(v, t)
+    n = 5000
+    rng = np.random.default_rng(97)
+    S = identity_poses(n)
+    S[:, 9:11] = rng.uniform(-5, 5, size=(n, 2))
+    S[:, 11] = rng.uniform(-0.5, 1.0, size=n)
+    got = F.collide_mesh_sphere_batch(m, None, F.Sphere(0.3), S, F.CollisionRequest(1 << 20, True), contact_capacity=400 * n,
+                                      grow_on_overflow=True)
+    ref = oracle.collide_mesh_sphere_batch(o, 0.3, None, S, 1 << 20, True, nthreads=8)
+    assert np.array_equal(got.num_contacts, ref["counts"]) and got.contacts.tobytes() == ref["contacts"].tobytes()
+    assert got.num_contacts.max() > 20
