@@ -1,0 +1,32 @@
+"""Kernel timing of the mesh <-> sphere collide (GPU box only)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import fcl_b200 as F
+from fcl_b200 import _capi
+import ctypes as C
+g = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+e = np.load(os.path.join(g, "env.npz"))
+env = F.BVHModel.from_arrays(e["verts"], e["tris"])
+n = 1_000_000
+S = torch.from_numpy(F.random_poses(n, seed=3)).cuda()
+cnt = torch.empty(n, dtype=torch.int32, device="cuda")
+L = _capi.lib()
+for radius in (100.0, 350.0, 800.0):
+    for req, label in ((F.CollisionRequest(), "verdict"), (F.CollisionRequest(100, True), "contacts<=100")):
+        rq = req._c()
+        con = torch.empty(64 * 40 * n, dtype=torch.uint8, device="cuda") if req.enable_contact else None
+        off = torch.empty(n + 1, dtype=torch.int64, device="cuda") if req.enable_contact else None
+        def run():
+            rc = L.fclgpu_collide_mesh_sphere_batch(env.device_model(0), radius, n, None, S.data_ptr(), C.byref(rq), cnt.data_ptr(),
+                                                    con.data_ptr() if con is not None else None, 40 * n if con is not None else 0,
+                                                    off.data_ptr() if off is not None else None, None, None, torch.cuda.current_stream().cuda_stream)
+            assert rc == 0, rc
+        run(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3): run()
+        e1.record(); e1.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        F.sync_status()
+        print("sphere r=%-5g %-14s %.2f ms per 1M queries  %.3g q/s  (colliding %.0f %%, contacts/query %.1f)" % (radius, label, ms, n / ms * 1e3, 100.0 * (cnt > 0).float().mean().item(), cnt.float().mean().item()))

@@ -26,6 +26,8 @@ _capi.set_option("collide_front", 2)
 f = F.collide_batch(env, P, rob, None, F.CollisionRequest(100000, False), want_contacts=False)
 print("front", int(f.num_contacts.sum()))
 _capi.set_option("collide_front", 1)
+ms = F.collide_mesh_sphere_batch(env, None, F.Sphere(350.0), P, F.CollisionRequest(50, True), contact_capacity=50 * n, stats=True)
+print("mesh-sphere", int(ms.num_contacts.sum()))
 # on-device build and refit (block-, warp- and thread-cooperative paths), distance overflow area
 v, t = heightfield(40, size=10.0, seed=3, amp=0.6)
 for variant in (2, 1, 0):
