@@ -716,6 +716,10 @@ def collide(o1, tf1, o2=None, tf2=None, request=None, result=None):
     if request.num_max_contacts == 0:
         sys.stderr.write(f"Warning: should stop early as num_max_contact is {request.num_max_contacts} !\n")
         return 0
+    if isinstance(o1, Sphere) and isinstance(o2, BVHModel):
+        # (OT_GEOM, OT_BVH): the reference calls the [BVH][GEOM] cell with the arguments swapped and does not flip
+        # the contacts (collision-inl.h:124-134), so o1 of every contact is the mesh
+        o1, tf1, o2, tf2 = o2, tf2, o1, tf1
     mesh_sphere = isinstance(o1, BVHModel) and isinstance(o2, Sphere)
     if not (isinstance(o1, BVHModel) and isinstance(o2, BVHModel)) and not mesh_sphere:
         sys.stderr.write("Warning: collision function between these node types is not supported\n")

@@ -548,6 +548,11 @@ def test_mesh_sphere_collide_matches_oracle(oracle, env_rob_npz):
     assert k == got.num_contacts[i] == res.numContacts()
     c0 = res.getContact(0)
     assert c0.b2 == -1 and c0.b1 == got.contacts_of(i)[0]["b1"] and c0.penetration_depth <= 0
+    # (sphere, mesh) argument order: the reference swaps the arguments and leaves the contacts as they are
+    res2 = F.CollisionResult()
+    k2 = F.collide(sphere, F.Transform3.from_pose12(S[i]), env, F.Transform3.from_pose12(M[i]), F.CollisionRequest(1000, True), res2)
+    assert k2 == k and res2.getContact(0).b1 == c0.b1 and res2.getContact(0).o1 is env
+    assert np.array_equal(res2.getContact(k - 1).pos, res.getContact(k - 1).pos)
 
 
 def test_mesh_sphere_on_a_large_mesh(oracle):
