@@ -119,6 +119,50 @@ inline void collide(const DeviceModel& o1, const std::vector<fcl::Transform3<dou
     }
 }
 
+// n independent fcl::collide(mesh, tf1[i], sphere, tf2[i], request, results[i]) calls
+// (collision_matrix[BV_OBBRSS][GEOM_SPHERE]; contacts carry b2 = Contact::NONE)
+inline void collide(const DeviceModel& o1, const std::vector<fcl::Transform3<double>>& tf1, const fcl::Sphere<double>& sphere,
+                    const std::vector<fcl::Transform3<double>>& tf2, const fcl::CollisionRequest<double>& request,
+                    std::vector<fcl::CollisionResult<double>>& results) {
+  const int64_t n = (int64_t)tf1.size();
+  results.assign(n, fcl::CollisionResult<double>());
+  if (request.num_max_contacts == 0 || n == 0) return;
+  std::vector<double> p1(12 * n), p2(12 * n);
+  for (int64_t i = 0; i < n; ++i) {
+    to_pose(tf1[i], &p1[12 * i]);
+    to_pose(tf2[i], &p2[12 * i]);
+  }
+  fclgpu_collision_request req{(int64_t)std::min<std::size_t>(request.num_max_contacts, (std::size_t)1 << 62),
+                               request.enable_contact ? 1 : 0, request.enable_cost ? 1 : 0};
+  std::vector<int32_t> counts(n);
+  std::vector<int64_t> off(n + 1);
+  int64_t cap = std::max<int64_t>(64 * n, 1024);
+  std::vector<fclgpu_contact> pool(cap);
+  int rc = fclgpu_collide_mesh_sphere_batch_host(o1.handle(), sphere.radius, n, p1.data(), p2.data(), &req, counts.data(),
+                                                 pool.data(), cap, off.data(), nullptr, nullptr);
+  if (rc == FCLGPU_ERR_CONTACT_OVERFLOW) {  // counts are exact: size the pool and rerun
+    cap = 0;
+    int32_t mx = 1;
+    for (int32_t c : counts) { cap += c; mx = std::max(mx, c); }
+    if (mx > fclgpu_get_option("contact_stride")) fclgpu_set_option("contact_stride", mx);
+    pool.resize(cap);
+    rc = fclgpu_collide_mesh_sphere_batch_host(o1.handle(), sphere.radius, n, p1.data(), p2.data(), &req, counts.data(),
+                                               pool.data(), cap, off.data(), nullptr, nullptr);
+  }
+  check(rc);
+  for (int64_t i = 0; i < n; ++i)
+    for (int64_t k = off[i]; k < off[i + 1]; ++k) {
+      const fclgpu_contact& c = pool[k];
+      if (request.enable_contact)
+        results[i].addContact(fcl::Contact<double>(o1.host(), &sphere, c.b1, fcl::Contact<double>::NONE,
+                                                   fcl::Vector3<double>(c.pos[0], c.pos[1], c.pos[2]),
+                                                   fcl::Vector3<double>(c.normal[0], c.normal[1], c.normal[2]),
+                                                   c.penetration_depth));
+      else
+        results[i].addContact(fcl::Contact<double>(o1.host(), &sphere, c.b1, fcl::Contact<double>::NONE));
+    }
+}
+
 inline void distance(const DeviceModel& o1, const std::vector<fcl::Transform3<double>>& tf1, const DeviceModel& o2,
                      const std::vector<fcl::Transform3<double>>& tf2, const fcl::DistanceRequest<double>& request,
                      std::vector<fcl::DistanceResult<double>>& results) {

@@ -100,8 +100,16 @@ struct BVHModel : CollisionGeometry<double> {
   std::vector<Triangle> tris_;
 };
 
+// geometry/shape/sphere.h: public member `radius`
+template <typename S>
+struct Sphere : CollisionGeometry<S> {
+  S radius;
+  explicit Sphere(S r) : radius(r) {}
+};
+
 template <typename S>
 struct Contact {
+  static const int NONE = -1;  // contact.h: id of "no primitive" (shape side)
   const CollisionGeometry<S>* o1 = nullptr;
   const CollisionGeometry<S>* o2 = nullptr;
   int b1 = -1, b2 = -1;

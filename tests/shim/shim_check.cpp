@@ -136,6 +136,31 @@ int main(int argc, char** argv) {
       return 1;
     }
   }
+  // mesh <-> sphere through the shim vs the C ABI
+  {
+    fcl::Sphere<double> sph(0.5);
+    std::vector<fcl::CollisionResult<double>> sres;
+    fclgpu::collide(d1, tf1, sph, tf2, fcl::CollisionRequest<double>(20, true), sres);
+    std::vector<int32_t> scnt(n);
+    std::vector<int64_t> soff(n + 1);
+    std::vector<fclgpu_contact> spool(20 * (size_t)n);
+    fclgpu::check(fclgpu_collide_mesh_sphere_batch_host(g1, 0.5, n, nullptr, p2.data(), &creq, scnt.data(), spool.data(), (int64_t)spool.size(), soff.data(), nullptr, nullptr));
+    long long shits = 0;
+    for (int i = 0; i < n; ++i) {
+      if ((int)sres[i].numContacts() != scnt[i]) { std::printf("FAIL sphere count %d\n", i); return 1; }
+      shits += scnt[i] > 0;
+      for (int k = 0; k < scnt[i]; ++k) {
+        const fclgpu_contact& c = spool[soff[i] + k];
+        const auto& r = sres[i].getContact(k);
+        if (r.b1 != c.b1 || r.b2 != fcl::Contact<double>::NONE || r.o2 != &sph || std::memcmp(r.pos.v, c.pos, 24) || r.penetration_depth != c.penetration_depth) {
+          std::printf("FAIL sphere contact %d/%d\n", i, k);
+          return 1;
+        }
+      }
+    }
+    if (shits == 0) { std::printf("FAIL: no sphere hits\n"); return 1; }
+    std::printf("shim sphere OK: %lld colliding\n", shits);
+  }
   if (colliding < n / 20 || colliding > n - n / 20) { std::printf("FAIL: degenerate pose sample (%lld colliding)\n", colliding); return 1; }
   std::printf("shim OK: %d queries, %lld colliding, %lld contacts compared, distances identical\n", n, colliding, contacts);
   fclgpu_model_destroy(g1);
