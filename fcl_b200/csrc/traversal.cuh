@@ -748,7 +748,11 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
       // every lane pops one entry; dead entries (bound no longer beats the minimum) vanish, leaf
       // pairs move to the leaf queue, the first kDistPop internal entries (nearest first) are
       // expanded by two lanes each and the remaining internal entries go back on the stack.
-      const int k = sp < 32 ? sp : 32;
+      // Close to the stack limit (a front that nothing prunes, e.g. coincident meshes before the first zero distance
+      // is found) the instantiation without an overflow area pops and expands ONE entry per round: plain
+      // nearest-first depth first, whose growth is bounded by the tree depths (checked on the host).
+      const bool tight = !kSpill && sp > kDistStackCap - 160;
+      const int k = tight ? 1 : (sp < 32 ? sp : 32);
       uint2 pr = make_uint2(0u, 0u);
       float bd = 0.0f;
       bool alive = lane < k;
