@@ -751,7 +751,10 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
       // Close to the stack limit (a front that nothing prunes, e.g. coincident meshes before the first zero distance
       // is found) the instantiation without an overflow area pops and expands ONE entry per round: plain
       // nearest-first depth first, whose growth is bounded by the tree depths (checked on the host).
-      const bool tight = !kSpill && sp > kDistStackCap - 160;
+#ifndef FCLGPU_DIST_TIGHT
+#define FCLGPU_DIST_TIGHT 1
+#endif
+      const bool tight = FCLGPU_DIST_TIGHT && !kSpill && sp > kDistStackCap - 160;
       const int k = tight ? 1 : (sp < 32 ? sp : 32);
       uint2 pr = make_uint2(0u, 0u);
       float bd = 0.0f;

@@ -570,3 +570,28 @@ def test_mesh_sphere_on_a_large_mesh(oracle):
     ref = oracle.collide_mesh_sphere_batch(o, 0.3, None, S, 1 << 20, True, nthreads=8)
     assert np.array_equal(got.num_contacts, ref["counts"]) and got.contacts.tobytes() == ref["contacts"].tobytes()
     assert got.num_contacts.max() > 20
+
+
+def test_distance_front_survives_unprunable_fronts(oracle):
+    """Regression (found by tools/stress_parity.py): a 2,048-triangle heightfield against a 384-triangle sphere, both
+    built with the BV-centre split, under poses for which the sorted front of the FP64-bound variant outgrew its
+    512-entry shared-memory stack and reported FCLGPU_ERR_STACK_OVERFLOW.  Near the limit the warp now degrades to
+    nearest-first depth first.  tests/golden/front_overflow.npz holds the meshes and 32 poses (8 of them overflowed)."""
+    import os
+
+    from tests.conftest import GOLDEN
+
+    d = np.load(os.path.join(GOLDEN, "front_overflow.npz"))
+    split = int(d["split"])
+    m1, m2 = F.BVHModel.from_arrays(d["v1"], d["t1"], split), F.BVHModel.from_arrays(d["v2"], d["t2"], split)
+    o1, o2 = oracle.Model(d["v1"], d["t1"], split), oracle.Model(d["v2"], d["t2"], split)
+    P1, P2 = np.ascontiguousarray(d["P1"]), np.ascontiguousarray(d["P2"])
+    assert int(d["n_bad"]) == 8
+    rd = oracle.distance_batch(o1, o2, P1, P2, True, 2, nthreads=4)
+    for trav in (0, 1, 2, 3):
+        _capi.set_option("traversal", trav)
+        try:
+            gd = F.distance_batch(m1, P1, m2, P2, F.DistanceRequest(True))
+        finally:
+            _capi.set_option("traversal", 3)
+        assert np.all(np.abs(gd.min_distance - rd["min_distance"]) <= 1e-14 * np.abs(rd["min_distance"])), trav

@@ -68,7 +68,12 @@ while time.time() < t_end:
     refc = ref["counts"] if not ec else O.collide_batch(o1, o2, P1, P2, mx, False, nthreads=8)["counts"]
     ok = ok and np.array_equal(cnt.num_contacts, refc)
     rd = O.distance_batch(o1, o2, P1, P2, True, 2, nthreads=8)
-    gd = F.distance_batch(m1, P1, m2, P2, F.DistanceRequest(True))
+    try:
+        gd = F.distance_batch(m1, P1, m2, P2, F.DistanceRequest(True))
+    except F.FclGpuError as ex:
+        print("DISTANCE ERROR", ex, tag)
+        np.savez("gpurun_out/stress_fail.npz", v1=v1, t1=t1, v2=v2, t2=t2, P1=P1, P2=P2 if P2 is not None else np.zeros(0), split=split)
+        sys.exit(3)
     # Minimum distance: bit-identical with traversal 0 (the reference's visiting order).  The front traversals may
     # meet mathematically tied candidates (adjacent triangles sharing the closest vertex / edge) in another order;
     # their computed distances can differ in the last bit and the reference's tight bounds prune whichever comes
