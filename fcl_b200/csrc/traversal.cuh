@@ -749,12 +749,13 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
       // pairs move to the leaf queue, the first kDistPop internal entries (nearest first) are
       // expanded by two lanes each and the remaining internal entries go back on the stack.
       // Close to the stack limit (a front that nothing prunes, e.g. coincident meshes before the first zero distance
-      // is found) the instantiation without an overflow area pops and expands ONE entry per round: plain
+      // is found) a warp without (room in) an overflow area pops and expands ONE entry per round: plain
       // nearest-first depth first, whose growth is bounded by the tree depths (checked on the host).
 #ifndef FCLGPU_DIST_TIGHT
 #define FCLGPU_DIST_TIGHT 1
 #endif
-      const bool tight = FCLGPU_DIST_TIGHT && !kSpill && sp > kDistStackCap - 160;
+      const bool tight = FCLGPU_DIST_TIGHT && sp > kDistStackCap - 160 &&
+                         (!kSpill || g_pair == nullptr || gsp + kSpillBlock > P.spill_cap);  // ... or the overflow area is full
       const int k = tight ? 1 : (sp < 32 ? sp : 32);
       uint2 pr = make_uint2(0u, 0u);
       float bd = 0.0f;
