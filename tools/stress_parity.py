@@ -20,12 +20,12 @@ def make_mesh():
     kind = rng.integers(0, 5)
     s = int(rng.integers(1 << 30))
     if kind == 0:
-        return random_soup(int(rng.integers(1, 400)), seed=s, scale=float(rng.uniform(0.5, 3)), tri_size=float(rng.uniform(0.05, 1.0)))
+        return random_soup(int(rng.integers(1, 4000 if rng.integers(0, 8) == 0 else 400)), seed=s, scale=float(rng.uniform(0.5, 3)), tri_size=float(rng.uniform(0.05, 1.0)))
     if kind == 1:
         return noisy_sphere(float(rng.uniform(0.3, 2)), int(rng.integers(4, 30)), int(rng.integers(3, 30)), seed=s, noise=float(rng.uniform(0, 0.2)),
                             scale=tuple(rng.uniform(0.3, 3, size=3)))
     if kind == 2:
-        return heightfield(int(rng.integers(2, 40)), size=float(rng.uniform(1, 6)), seed=s, amp=float(rng.uniform(0, 1)))
+        return heightfield(int(rng.integers(2, 100 if rng.integers(0, 8) == 0 else 40)), size=float(rng.uniform(1, 6)), seed=s, amp=float(rng.uniform(0, 1)))
     if kind == 3:
         return box_mesh(*rng.uniform(0.1, 2, size=3))
     return uv_sphere(float(rng.uniform(0.2, 2)), int(rng.integers(3, 20)), int(rng.integers(2, 20)))
@@ -38,7 +38,7 @@ while time.time() < t_end:
     m1 = F.BVHModel.from_arrays(v1, t1, split, build_on_device=on_dev)
     m2 = F.BVHModel.from_arrays(v2, t2, split)
     o1, o2 = O.Model(v1, t1, split), O.Model(v2, t2, split)
-    n = int(rng.integers(50, 3000))
+    n = int(rng.integers(50, 20000 if rng.integers(0, 6) == 0 else 3000))
     ext = float(rng.uniform(0.5, 6))
     P1 = random_poses(n, seed=int(rng.integers(1 << 30)), extents=(-ext, -ext, -ext, ext, ext, ext))
     P2 = random_poses(n, seed=int(rng.integers(1 << 30)), extents=(-ext, -ext, -ext, ext, ext, ext)) if rng.integers(0, 2) else None
@@ -51,7 +51,12 @@ while time.time() < t_end:
     trav = int(rng.choice([0, 1, 2, 3, 3, 3, 4]))
     _capi.set_option("traversal", trav)
     _capi.set_option("collide_front", int(rng.choice([1, 2])))
-    tag = dict(nt1=len(t1), nt2=len(t2), split=split, on_dev=on_dev, n=n, ext=ext, mx=mx, ec=ec, trav=trav)
+    scratch = int(rng.choice([2 << 30, 8 << 20]))   # small scratch: contact-mode batches run in several chunks
+    chunk = int(rng.choice([1 << 17, 2048]))          # small host chunks: many pipeline stages / sub-batches
+    pinned = bool(rng.integers(0, 2))
+    _capi.set_option("scratch_bytes", scratch)
+    _capi.set_option("host_chunk", chunk)
+    tag = dict(nt1=len(t1), nt2=len(t2), split=split, on_dev=on_dev, n=n, ext=ext, mx=mx, ec=ec, trav=trav, scratch=scratch, chunk=chunk, pinned=pinned)
     if on_dev:  # the device-built tree must be the oracle's tree
         a, b = m1.node_arrays(), o1.arrays()
         if not (np.array_equal(a["first_child"], b["first_child"]) and all(a[k].tobytes() == b[k].tobytes() for k in ("axis", "obb_To", "obb_ext", "rss_To", "rss_l", "rss_r"))):
@@ -60,16 +65,17 @@ while time.time() < t_end:
             np.savez("gpurun_out/stress_fail_mesh.npz", v=v1, t=t1, split=split)
             sys.exit(2)
     ref = O.collide_batch(o1, o2, P1, P2, mx, ec, nthreads=8)
-    got = F.collide_batch(m1, P1, m2, P2, F.CollisionRequest(mx, ec), contact_capacity=max(64 * n, 1024), grow_on_overflow=True)
-    ok = np.array_equal(got.num_contacts, ref["counts"]) and np.array_equal(got.contacts["b1"], ref["contacts"]["b1"]) and np.array_equal(got.contacts["b2"], ref["contacts"]["b2"])
+    got = F.collide_batch(m1, P1, m2, P2, F.CollisionRequest(mx, ec), contact_capacity=max(64 * n, 1024), grow_on_overflow=True, pinned=pinned)
+    got_counts, got_contacts = got.num_contacts.copy(), got.contacts.copy()  # pinned results live until the next call
+    ok = np.array_equal(got_counts, ref["counts"]) and np.array_equal(got_contacts["b1"], ref["contacts"]["b1"]) and np.array_equal(got_contacts["b2"], ref["contacts"]["b2"])
     if ec:
-        ok = ok and got.contacts.tobytes() == ref["contacts"].tobytes()
-    cnt = F.collide_batch(m1, P1, m2, P2, F.CollisionRequest(mx, False), want_contacts=False)
+        ok = ok and got_contacts.tobytes() == ref["contacts"].tobytes()
+    cnt = F.collide_batch(m1, P1, m2, P2, F.CollisionRequest(mx, False), want_contacts=False, pinned=pinned)
     refc = ref["counts"] if not ec else O.collide_batch(o1, o2, P1, P2, mx, False, nthreads=8)["counts"]
     ok = ok and np.array_equal(cnt.num_contacts, refc)
     rd = O.distance_batch(o1, o2, P1, P2, True, 2, nthreads=8)
     try:
-        gd = F.distance_batch(m1, P1, m2, P2, F.DistanceRequest(True))
+        gd = F.distance_batch(m1, P1, m2, P2, F.DistanceRequest(True), pinned=pinned)
     except F.FclGpuError as ex:
         print("DISTANCE ERROR", ex, tag)
         np.savez("gpurun_out/stress_fail.npz", v1=v1, t1=t1, v2=v2, t2=t2, P1=P1, P2=P2 if P2 is not None else np.zeros(0), split=split)
@@ -102,4 +108,6 @@ while time.time() < t_end:
         sys.exit(1)
 _capi.set_option("traversal", 3)
 _capi.set_option("collide_front", 1)
+_capi.set_option("scratch_bytes", 2 << 30)
+_capi.set_option("host_chunk", 1 << 17)
 print("stress parity OK: %d random configurations, %d query comparisons; front-traversal distances differing from the oracle in the last bits: %d of %d" % (rounds, checks, ulp_diffs, dist_checks))
