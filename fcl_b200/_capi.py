@@ -51,6 +51,7 @@ SYMBOLS = [
     "fclgpu_bvh_refit_topdown", "fclgpu_bvh_num_vertices", "fclgpu_bvh_get_partition", "fclgpu_model_set_partition",
     "fclgpu_model_refit_topdown", "fclgpu_model_download", "fclgpu_model_build_obbrss", "fclgpu_model_get_topology",
     "fclgpu_collide_mesh_sphere_batch", "fclgpu_collide_mesh_sphere_batch_host",
+    "fclgpu_distance_mesh_sphere_batch", "fclgpu_distance_mesh_sphere_batch_host",
     "fclgpu_model_create_obbrss", "fclgpu_model_from_bvh", "fclgpu_model_destroy", "fclgpu_model_num_nodes",
     "fclgpu_model_num_tris", "fclgpu_model_device", "fclgpu_collide_batch", "fclgpu_collide_batch_host",
     "fclgpu_distance_batch", "fclgpu_distance_batch_host", "fclgpu_abi_version", "fclgpu_device_count",
@@ -105,6 +106,10 @@ def lib():
                                         up, up, vp]
     L.fclgpu_distance_batch_host.argtypes = [vp, vp, C.c_int64, dp, dp, C.POINTER(DistanceRequestC), dp, dp, dp, ip,
                                              ip, up, up]
+    L.fclgpu_distance_mesh_sphere_batch.argtypes = [vp, C.c_double, C.c_int64, dp, dp, C.POINTER(DistanceRequestC), dp, dp,
+                                                    dp, ip, ip, up, up, vp]
+    L.fclgpu_distance_mesh_sphere_batch_host.argtypes = [vp, C.c_double, C.c_int64, dp, dp, C.POINTER(DistanceRequestC), dp,
+                                                         dp, dp, ip, ip, up, up]
     L.fclgpu_last_error.restype = C.c_char_p
     L.fclgpu_pose_from_colmajor4x4.argtypes = [vp, vp]
     L.fclgpu_pose_from_colmajor4x4.restype = None

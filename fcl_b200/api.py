@@ -376,7 +376,7 @@ def _current_device():
 
 class Sphere:
     """fcl::Sphere<double> (geometry/shape/sphere.h): centred at the origin of its own frame.  On this path it is
-    the second geometry of a mesh <-> sphere collide."""
+    the second geometry of a mesh <-> sphere collide / distance."""
 
     def __init__(self, radius):
         self.radius = float(radius)
@@ -668,6 +668,31 @@ def distance_batch(o1, tf1, o2, tf2, request, stats=False, device=None, pinned=F
     return res
 
 
+def distance_mesh_sphere_batch(o1, tf1, sphere, tf2, request, stats=False, device=None, pinned=False):
+    """n independent fcl::distance(mesh, tf1[i], Sphere, tf2[i]) calls (host arrays in and out).  nearest_p1 is in the
+    mesh frame and nearest_p2 in the sphere frame (the reference's postprocess is empty for this node), b1 = closest
+    triangle, b2 = -1 (DistanceResult::NONE).  Centre within the radius of a triangle: min_distance = -1, NaN points."""
+    tf1, n1 = _poses(tf1)
+    tf2, n2 = _poses(tf2)
+    n = n1 if n1 is not None else n2
+    if n is None:
+        raise ValueError("at least one of tf1/tf2 must be given")
+    if n1 is not None and n2 is not None and n1 != n2:
+        raise ValueError("tf1 and tf2 must have the same length")
+    m1 = o1.device_model(device)
+    req = request._c()
+    (dist, k0), (p1, k1), (p2, k2) = _out(n, np.float64, pinned, "dist"), _out((n, 3), np.float64, pinned, "p1"), _out((n, 3), np.float64, pinned, "p2")
+    (b1, k3), (b2, k4) = _out(n, np.int32, pinned, "b1"), _out(n, np.int32, pinned, "b2")
+    n_bv = np.zeros(n, np.uint32) if stats else None
+    n_leaf = np.zeros(n, np.uint32) if stats else None
+    check(_capi.lib().fclgpu_distance_mesh_sphere_batch_host(m1, float(sphere.radius), n, addr(tf1), addr(tf2), C.byref(req),
+                                                             addr(dist), addr(p1), addr(p2), addr(b1), addr(b2),
+                                                             addr(n_bv), addr(n_leaf)))
+    res = BatchDistanceResult(dist, p1, p2, b1, b2, n_bv, n_leaf)
+    res._keepalive = [k0, k1, k2, k3, k4]
+    return res
+
+
 def collide_batch_device(o1, tf1, o2, tf2, request, num_contacts, contacts=None, contact_offsets=None, n_bv=None,
                          n_leaf=None, stream=None):
     """Device-resident variant: every argument is a CUDA torch tensor (or None); asynchronous on
@@ -751,13 +776,25 @@ def distance(o1, tf1, o2=None, tf2=None, request=None, result=None):
         obj1, obj2, request, result = o1, tf1, o2, tf2
         return distance(obj1.collisionGeometry(), obj1.getTransform(), obj2.collisionGeometry(), obj2.getTransform(),
                         request, result)
-    if not (isinstance(o1, BVHModel) and isinstance(o2, BVHModel)):
+    if isinstance(o1, Sphere) and isinstance(o2, BVHModel):
+        # (OT_GEOM, OT_BVH): the reference calls the [BVH][GEOM] cell with the arguments swapped and does not flip
+        # the result (distance-inl.h:117-127), so o1 / nearest_points[0] of the result belong to the mesh
+        o1, tf1, o2, tf2 = o2, tf2, o1, tf1
+    mesh_sphere = isinstance(o1, BVHModel) and isinstance(o2, Sphere)
+    if not (isinstance(o1, BVHModel) and isinstance(o2, BVHModel)) and not mesh_sphere:
         sys.stderr.write("Warning: distance function between these node types is not supported\n")
         return DBL_MAX
-    if request.isSatisfied(result):  # orientedMeshDistance, distance_func_matrix-inl.h:395
+    if request.isSatisfied(result):  # orientedMeshDistance / orientedBVHShapeDistance, distance_func_matrix-inl.h:395,268
         return result.min_distance
-    r = distance_batch(o1, tf1, o2, tf2, request)
-    if request.enable_nearest_points:
+    if mesh_sphere:
+        ident = np.array([[1.0, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0]])
+        # the mesh-shape leaf always hands its nearest points to DistanceResult::update
+        # (mesh_shape_distance_traversal_node-inl.h:186-199), whatever the request says
+        r = distance_mesh_sphere_batch(o1, ident if tf1 is None else tf1, o2, ident if tf2 is None else tf2,
+                                       DistanceRequest(True))
+    else:
+        r = distance_batch(o1, tf1, o2, tf2, request)
+    if request.enable_nearest_points or mesh_sphere:
         result.update(float(r.min_distance[0]), o1, o2, int(r.b1[0]), int(r.b2[0]), r.nearest_p1[0], r.nearest_p2[0])
     else:
         result.update(float(r.min_distance[0]), o1, o2, int(r.b1[0]), int(r.b2[0]))

@@ -691,6 +691,82 @@ FD bool sphere_tri_intersect(const V3& c, double radius, const V3 P[3], V3& cp, 
 }
 
 // ---------------------------------------------------------------------------------------
+// Sphere vs triangle distance (mesh <-> sphere distance): the nearest-point overload of
+// sphereTriangleDistance (sphere_triangle-inl.h:469-496) on top of Project::projectTriangle / projectLine
+// (math/detail/project-inl.h:54-123).  o = sphere centre, P[3] = triangle, same frame.
+// Returns false when the centre is within the radius of the triangle (or the triangle has zero area);
+// otherwise d = distance, on_tri = projection of the centre, on_sphere = o - dir * radius.
+// Structure differs from the oracle's restatement (edge loop carries the two barycentric weights of the best
+// edge and its index instead of a parameterisation array), arithmetic order is the same.
+// ---------------------------------------------------------------------------------------
+FD bool sphere_tri_distance(const V3& o, double radius, const V3 P[3], double& d, V3& on_sphere, V3& on_tri) {
+  const V3 e0 = P[0] - P[1], e1 = P[1] - P[2], e2 = P[2] - P[0];
+  const V3 E[3] = {e0, e1, e2};
+  const V3 n = cross(e0, e1);
+  const double l = dot(n, n);
+  if (!(l > 0)) return false;
+  double best = -1, wa = 0, wb = 0;
+  int best_i = -1;
+#pragma unroll 1
+  for (int i = 0; i < 3; ++i) {
+    const V3 a = sel3(P, i);
+    if (dot(a - o, cross(sel3(E, i), n)) > 0) {  // outside edge i: candidate = closest point of that edge
+      const V3 b = sel3(P, (i + 1) % 3);
+      const V3 dv = b - a;
+      const double ll = dot(dv, dv);
+      double s = -1, t1 = 0;
+      if (ll > 0) {
+        const double t = dot(o - a, dv);
+        if (t >= ll) {
+          t1 = 1;
+          const V3 w = o - b;
+          s = dot(w, w);
+        } else if (t <= 0) {
+          t1 = 0;
+          const V3 w = o - a;
+          s = dot(w, w);
+        } else {
+          t1 = t / ll;
+          const V3 w = (a + dv * t1) - o;
+          s = dot(w, w);
+        }
+      }
+      if (best < 0 || s < best) {
+        best = s;
+        best_i = i;
+        wa = (ll > 0) ? 1 - t1 : 0.0;
+        wb = t1;
+      }
+    }
+  }
+  double w0, w1, w2;
+  if (best < 0) {  // the projection falls inside the triangle
+    const double h = dot(P[0] - o, n);
+    const double s = sqrt(l);
+    const V3 pp = n * (h / l);
+    best = dot(pp, pp);
+    const V3 c1 = cross(e1, (P[1] - o) - pp), c2 = cross(e2, (P[2] - o) - pp);
+    w0 = sqrt(dot(c1, c1)) / s;
+    w1 = sqrt(dot(c2, c2)) / s;
+    w2 = 1 - w0 - w1;
+  } else {
+    w0 = (best_i == 0) ? wa : ((best_i == 2) ? wb : 0.0);
+    w1 = (best_i == 1) ? wa : ((best_i == 0) ? wb : 0.0);
+    w2 = (best_i == 2) ? wa : ((best_i == 1) ? wb : 0.0);
+  }
+  if (!(best > radius * radius)) return false;
+  d = sqrt(best) - radius;
+  on_tri = (P[0] * w0 + P[1] * w1) + P[2] * w2;
+  V3 dir = o - on_tri;
+  {
+    const double len = sqrt(dot(dir, dir));
+    dir = mk(dir.x / len, dir.y / len, dir.z / len);
+  }
+  on_sphere = o - dir * radius;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------
 // BV-pair tests in the relative pose (R0, T0) of model2 in model1's frame.
 //   overlap(R0,T0,OBB,OBB)   include/fcl/math/bv/OBB-inl.h:384-395
 //   distance(R0,T0,RSS,RSS)  include/fcl/math/bv/RSS-inl.h:1957-1974

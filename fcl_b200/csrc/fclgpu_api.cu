@@ -889,13 +889,15 @@ extern "C" int fclgpu_collide_mesh_sphere_batch(const fclgpu_model* m1, double r
 // ------------------------------------------------------------------------------------------
 // distance
 // ------------------------------------------------------------------------------------------
-extern "C" int fclgpu_distance_batch(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1,
-                                     const double* tf2, const fclgpu_distance_request* request,
-                                     double* min_distance, double* nearest_p1, double* nearest_p2, int32_t* b1,
-                                     int32_t* b2, uint32_t* n_bv, uint32_t* n_leaf, void* stream) {
+namespace {
+// sphere_radius >= 0: model 2 is a sphere of that radius (mesh <-> sphere distance; m2 == m1 is passed and ignored)
+int distance_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1, const double* tf2,
+                     const fclgpu_distance_request* request, double* min_distance, double* nearest_p1,
+                     double* nearest_p2, int32_t* b1, int32_t* b2, uint32_t* n_bv, uint32_t* n_leaf, void* stream,
+                     double sphere_radius) {
   if (!m1 || !m2 || !request || n < 0) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL model/request or n<0");
   if (m1->device != m2->device) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "models live on different devices");
-  if (m1->depth + m2->depth + 2 > kStackCap)
+  if (m1->depth + (sphere_radius >= 0 ? 0 : m2->depth) + 2 > kStackCap)
     return fail(FCLGPU_ERR_STACK_OVERFLOW, "tree depths %d+%d exceed the traversal stack", m1->depth, m2->depth);
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_TRY(cudaSetDevice(m1->device));
@@ -945,6 +947,10 @@ extern "C" int fclgpu_distance_batch(const fclgpu_model* m1, const fclgpu_model*
     P.spill_warps = w->sm_count * 8 * kDistWarps;
   }
   const bool stats = (n_bv || n_leaf);
+  if (sphere_radius >= 0) {
+    return stats ? launch_persistent(distance_mesh_sphere_kernel<true>, P, w, 128, st, 0, sphere_radius)
+                 : launch_persistent(distance_mesh_sphere_kernel<false>, P, w, 128, st, 0, sphere_radius);
+  }
   const long long trav = opt("traversal");
   const size_t front_smem = sizeof(WarpFront) * kDistWarps;
   if (trav >= 2 && P.spill_pair) {
@@ -961,6 +967,25 @@ extern "C" int fclgpu_distance_batch(const fclgpu_model* m1, const fclgpu_model*
                : launch_persistent(distance_thread_kernel<false>, P, w, 128, st);
   }
   return rc;
+}
+}  // namespace
+
+extern "C" int fclgpu_distance_batch(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1,
+                                     const double* tf2, const fclgpu_distance_request* request,
+                                     double* min_distance, double* nearest_p1, double* nearest_p2, int32_t* b1,
+                                     int32_t* b2, uint32_t* n_bv, uint32_t* n_leaf, void* stream) {
+  return distance_enqueue(m1, m2, n, tf1, tf2, request, min_distance, nearest_p1, nearest_p2, b1, b2, n_bv, n_leaf, stream,
+                          -1.0);
+}
+
+// mesh <-> sphere distance
+extern "C" int fclgpu_distance_mesh_sphere_batch(const fclgpu_model* m1, double radius, int64_t n, const double* tf1,
+                                                 const double* tf2, const fclgpu_distance_request* request,
+                                                 double* min_distance, double* nearest_p1, double* nearest_p2,
+                                                 int32_t* b1, int32_t* b2, uint32_t* n_bv, uint32_t* n_leaf, void* stream) {
+  if (!(radius >= 0)) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "sphere radius must be >= 0");
+  return distance_enqueue(m1, m1, n, tf1, tf2, request, min_distance, nearest_p1, nearest_p2, b1, b2, n_bv, n_leaf, stream,
+                          radius);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1180,11 +1205,10 @@ extern "C" int fclgpu_collide_batch_host(const fclgpu_model* m1, const fclgpu_mo
   return fclgpu_sync_status(m1->device, st);
 }
 
-extern "C" int fclgpu_distance_batch_host(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n,
-                                          const double* tf1, const double* tf2,
-                                          const fclgpu_distance_request* request, double* min_distance,
-                                          double* nearest_p1, double* nearest_p2, int32_t* b1, int32_t* b2,
-                                          uint32_t* n_bv, uint32_t* n_leaf) {
+namespace {
+int distance_host(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1, const double* tf2,
+                  const fclgpu_distance_request* request, double* min_distance, double* nearest_p1, double* nearest_p2,
+                  int32_t* b1, int32_t* b2, uint32_t* n_bv, uint32_t* n_leaf, double sphere_radius) {
   if (!m1 || !m2 || !request || n < 0) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL model/request or n<0");
   CUDA_TRY(cudaSetDevice(m1->device));
   Workspace* w;
@@ -1219,7 +1243,8 @@ extern "C" int fclgpu_distance_batch_host(const fclgpu_model* m1, const fclgpu_m
     uint32_t* d_leaf = n_leaf ? B.take<uint32_t>(C) : nullptr;
     if (tf1) CUDA_TRY(cudaMemcpyAsync(d_tf1, tf1 + 12 * s, 96 * cn, cudaMemcpyHostToDevice, st));
     if (tf2) CUDA_TRY(cudaMemcpyAsync(d_tf2, tf2 + 12 * s, 96 * cn, cudaMemcpyHostToDevice, st));
-    rc = fclgpu_distance_batch(m1, m2, (int64_t)cn, d_tf1, d_tf2, request, d_dist, d_p1, d_p2, d_b1, d_b2, d_bv, d_leaf, st);
+    rc = distance_enqueue(m1, m2, (int64_t)cn, d_tf1, d_tf2, request, d_dist, d_p1, d_p2, d_b1, d_b2, d_bv, d_leaf, st,
+                          sphere_radius);
     if (rc) return rc;
     if (min_distance) CUDA_TRY(cudaMemcpyAsync(min_distance + s, d_dist, 8 * cn, cudaMemcpyDeviceToHost, st));
     if (d_p1) CUDA_TRY(cudaMemcpyAsync(nearest_p1 + 3 * s, d_p1, 24 * cn, cudaMemcpyDeviceToHost, st));
@@ -1232,6 +1257,23 @@ extern "C" int fclgpu_distance_batch_host(const fclgpu_model* m1, const fclgpu_m
     // stream, so stream order already protects them
   }
   return finish_pipeline(w, m1->device);
+}
+}  // namespace
+
+extern "C" int fclgpu_distance_batch_host(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n,
+                                          const double* tf1, const double* tf2,
+                                          const fclgpu_distance_request* request, double* min_distance,
+                                          double* nearest_p1, double* nearest_p2, int32_t* b1, int32_t* b2,
+                                          uint32_t* n_bv, uint32_t* n_leaf) {
+  return distance_host(m1, m2, n, tf1, tf2, request, min_distance, nearest_p1, nearest_p2, b1, b2, n_bv, n_leaf, -1.0);
+}
+
+extern "C" int fclgpu_distance_mesh_sphere_batch_host(const fclgpu_model* m1, double radius, int64_t n, const double* tf1,
+                                                      const double* tf2, const fclgpu_distance_request* request,
+                                                      double* min_distance, double* nearest_p1, double* nearest_p2,
+                                                      int32_t* b1, int32_t* b2, uint32_t* n_bv, uint32_t* n_leaf) {
+  if (!(radius >= 0)) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "sphere radius must be >= 0");
+  return distance_host(m1, m1, n, tf1, tf2, request, min_distance, nearest_p1, nearest_p2, b1, b2, n_bv, n_leaf, radius);
 }
 
 extern "C" int fclgpu_collide_mesh_sphere_batch_host(const fclgpu_model* m1, double radius, int64_t n, const double* tf1,

@@ -13,6 +13,7 @@
 #include "../../include/fclgpu.h"
 #include "bounds_f32.cuh"
 #include "device_math.cuh"
+#include "mesh_sphere.cuh"
 
 namespace fclgpu {
 
@@ -1718,6 +1719,67 @@ __global__ void __launch_bounds__(128) collide_mesh_sphere_kernel(CollideParams 
     if (kStats) {
       if (P.n_bv) P.n_bv[q] = bv_tests;
       if (P.n_leaf) P.n_leaf[q] = leaf_tests;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Mesh <-> sphere distance: fcl::distance(BVHModel<OBBRSS>, tf1, Sphere, tf2).  One lane per
+// query; the per-query traversal, its bound and the leaf are in mesh_sphere.cuh (shared with the host check).
+// The point on the triangle goes back to the mesh frame with tf1^-1, the point on the sphere to the sphere
+// frame with tf2^-1 -- the reference leaves both local (sphere_triangle-inl.h:485, 499-508; empty postprocess).
+// ---------------------------------------------------------------------------------------
+struct DeviceMeshAccessor {
+  const DeviceModel& m;
+  __device__ __forceinline__ int first_child(int b) const { return __ldg(m.first_child + b); }
+  __device__ __forceinline__ void box(int b, M3& axis, V3& To, double& e0, double& e1, double& e2) const {
+    const NodeRec nd = load_node(m.obb, b);
+    axis = nd.axis;
+    To = nd.To;
+    e0 = nd.e0;
+    e1 = nd.e1;
+    e2 = nd.e2;
+  }
+  __device__ __forceinline__ void tri(int id, V3 T[3]) const { load_tri(m.tri, id, T); }
+};
+
+template <bool kStats>
+__global__ void __launch_bounds__(128) distance_mesh_sphere_kernel(DistanceParams P, double radius) {
+  int stk[kStackCap];
+  float stk_lb[kStackCap];
+  bool exhausted = false;
+  const DeviceMeshAccessor acc{P.m1};
+  while (true) {
+    const long long q = fetch_work(!exhausted, P.work_counter);
+    if (__all_sync(0xffffffffu, exhausted || q >= P.n)) break;
+    if (exhausted) continue;
+    if (q >= P.n) {
+      exhausted = true;
+      continue;
+    }
+    const PoseRT tf1 = load_pose(P.tf1, q);
+    const PoseRT tf2 = load_pose(P.tf2, q);
+    MeshSphereDistance s;
+    mesh_sphere_distance_query(acc, tf1.R, tf1.t, tf2.t, radius, stk, stk_lb, kStackCap, s);
+    if (s.overflow) atomicMin(P.status, (int)FCLGPU_ERR_STACK_OVERFLOW);
+    if (P.min_distance) P.min_distance[q] = s.min_d;
+    if (P.b1) P.b1[q] = s.best;
+    if (P.b2) P.b2[q] = -1;  // DistanceResult::NONE
+    if (P.enable_nearest_points) {
+      V3 a, b;
+      if (s.min_d < 0.0) {
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        a = b = mk(nan, nan, nan);
+      } else {
+        a = inverse_apply(tf1.R, tf1.t, s.on_tri);
+        b = inverse_apply(tf2.R, tf2.t, s.on_sph);
+      }
+      if (P.p1) { P.p1[3 * q] = a.x; P.p1[3 * q + 1] = a.y; P.p1[3 * q + 2] = a.z; }
+      if (P.p2) { P.p2[3 * q] = b.x; P.p2[3 * q + 1] = b.y; P.p2[3 * q + 2] = b.z; }
+    }
+    if (kStats) {
+      if (P.n_bv) P.n_bv[q] = s.bv_tests;
+      if (P.n_leaf) P.n_leaf[q] = s.leaf_tests;
     }
   }
 }

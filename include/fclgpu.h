@@ -228,6 +228,31 @@ int fclgpu_distance_batch_host(const fclgpu_model* m1, const fclgpu_model* m2, i
                                uint32_t* n_bv, uint32_t* n_leaf);
 
 /* ---------------------------------------------------------------------------------------
+ * Batched mesh <-> sphere distance: query i evaluates
+ * fcl::distance(m1, tf1[i], Sphere(radius), tf2[i], request, result_i) =
+ * BVHShapeDistancer<OBBRSS<S>, Sphere<S>> -> orientedBVHShapeDistance
+ * (narrowphase/detail/distance_func_matrix-inl.h:259-277, 322-341;
+ * traversal/distance/mesh_shape_distance_traversal_node-inl.h:163-236, 351-413) with the closed-form
+ * sphereTriangleDistance leaf (primitive_shape_algorithm/sphere_triangle-inl.h:469-508 on
+ * Project::projectTriangle, math/detail/project-inl.h:54-123; no GJK on this pair).
+ *   min_distance[i] = min over the triangles of (distance(centre, triangle) - radius);
+ *   nearest_p1 = closest point on the mesh in the MESH frame, nearest_p2 = closest point on the sphere in the
+ *   SPHERE frame (the reference's postprocess is empty for this node: both stay local), written only when
+ *   enable_nearest_points; b1 = closest triangle, b2 = -1 (DistanceResult::NONE).  Any output may be NULL.
+ *   Centre within the radius of a triangle: the reference's solver returns false without writing the distance
+ *   and its leaf reads it uninitialised; here that case is DEFINED as min_distance = -1 (the value the
+ *   distance-only overload writes, sphere_triangle-inl.h:462), NaN points, b1 = a triangle within the radius.
+ * ------------------------------------------------------------------------------------- */
+int fclgpu_distance_mesh_sphere_batch(const fclgpu_model* m1, double radius, int64_t n, const double* tf1,
+                                      const double* tf2, const fclgpu_distance_request* request,
+                                      double* min_distance, double* nearest_p1, double* nearest_p2, int32_t* b1,
+                                      int32_t* b2, uint32_t* n_bv, uint32_t* n_leaf, void* stream);
+int fclgpu_distance_mesh_sphere_batch_host(const fclgpu_model* m1, double radius, int64_t n, const double* tf1,
+                                           const double* tf2, const fclgpu_distance_request* request,
+                                           double* min_distance, double* nearest_p1, double* nearest_p2, int32_t* b1,
+                                           int32_t* b2, uint32_t* n_bv, uint32_t* n_leaf);
+
+/* ---------------------------------------------------------------------------------------
  * Utilities
  * ------------------------------------------------------------------------------------- */
 int fclgpu_abi_version(void);

@@ -124,13 +124,24 @@ double distance(const Model& m1, const Pose& tf1, const Model& m2, const Pose& t
 // center / P1..P3 in one frame.  Outputs as the reference writes them (normal is negated by the caller).
 bool sphere_tri_intersect(const Vec3& center, double radius, const Vec3& P1, const Vec3& P2, const Vec3& P3,
                           Vec3* contact_point, double* penetration_depth, Vec3* normal);
-// computeBV<OBBRSS>(Sphere, tf): OBB part, fitted over the 12 bound vertices (sphere-inl.h:95-120, BV_fitter fitn)
+// computeBV<OBBRSS>(Sphere, tf): OBB and RSS fitted over the 12 bound vertices (sphere-inl.h:95-120, fitn)
 void sphere_obb(double radius, const Pose& tf, Node& bv);
 // fcl::collide(BVHModel<OBBRSS>, tf1, Sphere(radius), tf2): contacts {b1 = triangle, b2 = -1 (Contact::NONE)}
 size_t collide_mesh_sphere(const Model& m1, const Pose& tf1, double radius, const Pose& tf2, size_t num_max_contacts,
                            bool enable_contact, std::vector<Contact>& out, CollideStats* stats = nullptr);
 // every triangle tested in primitive order (for the invariants): ids of the intersecting triangles
 void brute_mesh_sphere(const Model& m1, const Pose& tf1, double radius, const Pose& tf2, std::vector<int>& tris);
+
+// sphereTriangleDistance with nearest points (sphere_triangle-inl.h:469-496) on top of Project::projectTriangle
+// (math/detail/project-inl.h:54-123): centre o and triangle in one frame; false = centre within the radius of the
+// triangle (the reference then leaves every output unwritten).
+bool sphere_tri_distance(const Vec3& o, double radius, const Vec3& P1, const Vec3& P2, const Vec3& P3, double* dist,
+                         Vec3* on_sphere_world, Vec3* on_triangle);
+// fcl::distance(BVHModel<OBBRSS>, tf1, Sphere(radius), tf2): out.p1 in the MESH frame, out.p2 in the SPHERE frame (the
+// reference's postprocess is empty for this node), b2 = -1; centre within the radius: min_distance = -1, NaN points
+double distance_mesh_sphere(const Model& m1, const Pose& tf1, double radius, const Pose& tf2, DistanceOut& out,
+                            CollideStats* stats = nullptr);
+double brute_distance_mesh_sphere(const Model& m1, const Pose& tf1, double radius, const Pose& tf2, DistanceOut& out);
 
 // brute force over all triangle pairs (for the invariants)
 void brute_collide_pairs(const Model& m1, const Pose& tf1, const Model& m2, const Pose& tf2,

@@ -419,9 +419,17 @@ void sphere_obb_impl(double radius, const Pose& tf, Node& bv) {
   bv.first_child = -1;
   bv.first_primitive = 0;
   bv.num_primitives = 0;
-  bv.rss_To = bv.obb_To;
-  bv.rss_l[0] = bv.rss_l[1] = 0;
-  bv.rss_r = 0;
+  // RSS part (RSS_fit_functions::fitn, math/bv/utility-inl.h:244-259): same covariance / eigen / axes, then
+  // getRadiusAndOriginAndRectangleSize over the 12 points (point branch, math/geometry-inl.h:725-760: P[i] =
+  // projections of ps[i]).  The triangle routine fed with 4 "triangles" (0,1,2) .. (9,10,11) builds the same P.
+  {
+    Model tmp;
+    tmp.verts.assign(ps, ps + 12);
+    for (int i = 0; i < 4; ++i) tmp.tris.push_back(Tri{{3 * i, 3 * i + 1, 3 * i + 2}});
+    const unsigned idx[4] = {0, 1, 2, 3};
+    Builder b{tmp, SPLIT_MEAN, {}, 0};
+    b.rss_fit(idx, 4, bv.axis, bv.rss_To, bv.rss_l, bv.rss_r);
+  }
 }
 
 }  // namespace
@@ -857,6 +865,116 @@ void brute_mesh_sphere(const Model& m1, const Pose& tf1, double radius, const Po
     const Vec3 p3 = add(mul(tf1.R, m1.verts[t.v[2]]), tf1.t);
     if (sphere_tri_intersect(tf2.t, radius, p1, p2, p3, nullptr, nullptr, nullptr)) tris.push_back(i);
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// Mesh <-> sphere distance: BVHShapeDistancer<OBBRSS, Sphere>::distance -> orientedBVHShapeDistance
+// (detail/distance_func_matrix-inl.h:259-277, 322-341) -> setupMeshShapeDistanceOrientedNode
+// (mesh_shape_distance_traversal_node-inl.h:386-413: computeBV(model2, tf2, model2_bv)) -> detail::distance:
+// preprocess (triangle 0), distanceRecurse with a leaf second node, empty postprocess (:351-364).
+// Nearest points stay in the LOCAL frames: the solver maps the point on the sphere with tf2^-1 and the point on
+// the triangle with tf1^-1 (sphere_triangle-inl.h:485, 499-508).
+// Centre within the radius of a triangle: the reference's leaf passes an uninitialised distance to
+// DistanceResult::update (the solver returned false without writing it).  The restatement DEFINES that case
+// as distance -1 (what the distance-only overload writes, sphere_triangle-inl.h:462) and NaN points.
+// ---------------------------------------------------------------------------------------
+namespace {
+struct MeshSphereDistCtx {
+  const Model& m1;
+  Pose tf1, tf2;
+  double radius;
+  Node shape_bv;
+  double min_distance = std::numeric_limits<double>::max();
+  Vec3 p1{{0, 0, 0}}, p2{{0, 0, 0}};
+  int rb1 = -1;
+  long long n_bv = 0, n_leaf = 0;
+
+  static Vec3 inverse_apply(const Pose& tf, const Vec3& p) {  // tf.inverse(Isometry) * p
+    Vec3 it = mulTv(tf.R, tf.t);
+    it = Vec3{{-it[0], -it[1], -it[2]}};
+    return add(mulTv(tf.R, p), it);
+  }
+
+  // meshShapeDistanceOrientedNodeLeafTesting / distancePreprocessOrientedNode (:163-236)
+  void tri(int id) {
+    const Tri& t = m1.tris[id];
+    const Vec3 P1 = add(mul(tf1.R, m1.verts[t.v[0]]), tf1.t);
+    const Vec3 P2 = add(mul(tf1.R, m1.verts[t.v[1]]), tf1.t);
+    const Vec3 P3 = add(mul(tf1.R, m1.verts[t.v[2]]), tf1.t);
+    double d;
+    Vec3 on_sphere, on_tri;
+    if (sphere_tri_distance(tf2.t, radius, P1, P2, P3, &d, &on_sphere, &on_tri)) {
+      if (min_distance > d) {  // DistanceResult::update, distance_result-inl.h:66-103
+        min_distance = d;
+        rb1 = id;
+        p1 = inverse_apply(tf1, on_tri);
+        p2 = inverse_apply(tf2, on_sphere);
+      }
+    } else if (min_distance > -1) {
+      const double nan = std::numeric_limits<double>::quiet_NaN();
+      min_distance = -1;
+      rb1 = id;
+      p1 = p2 = Vec3{{nan, nan, nan}};
+    }
+  }
+
+  bool can_stop(double c) const { return c >= min_distance; }  // :100-106 with rel_err = abs_err = 0
+
+  // MeshShapeDistanceTraversalNodeOBBRSS::BVTesting (:366-375)
+  double bv(int b1) {
+    n_bv++;
+    return rss_distance(tf1.R, tf1.t, shape_bv, m1.nodes[b1]);
+  }
+
+  // distanceRecurse (traversal_recurse-inl.h:259-316); the second node is always a leaf, firstOverSecond = true
+  void recurse(int b1) {
+    const Node& n1 = m1.nodes[b1];
+    if (n1.first_child < 0) {
+      n_leaf++;
+      tri(-(n1.first_child + 1));
+      return;
+    }
+    const int a1 = n1.first_child, c1 = n1.first_child + 1;
+    const double d1 = bv(a1);
+    const double d2 = bv(c1);
+    if (d2 < d1) {
+      if (!can_stop(d2)) recurse(c1);
+      if (!can_stop(d1)) recurse(a1);
+    } else {
+      if (!can_stop(d1)) recurse(a1);
+      if (!can_stop(d2)) recurse(c1);
+    }
+  }
+};
+}  // namespace
+
+double distance_mesh_sphere(const Model& m1, const Pose& tf1, double radius, const Pose& tf2, DistanceOut& out,
+                            CollideStats* stats) {
+  MeshSphereDistCtx ctx{m1, tf1, tf2, radius, Node{}};
+  sphere_obb(radius, tf2, ctx.shape_bv);
+  ctx.tri(0);  // preprocess
+  ctx.recurse(0);
+  out.min_distance = ctx.min_distance;
+  out.b1 = ctx.rb1;
+  out.b2 = -1;  // DistanceResult::NONE
+  out.p1 = ctx.p1;
+  out.p2 = ctx.p2;
+  if (stats) {
+    stats->n_bv += ctx.n_bv;
+    stats->n_leaf += ctx.n_leaf;
+  }
+  return out.min_distance;
+}
+
+double brute_distance_mesh_sphere(const Model& m1, const Pose& tf1, double radius, const Pose& tf2, DistanceOut& out) {
+  MeshSphereDistCtx ctx{m1, tf1, tf2, radius, Node{}};
+  for (int i = 0; i < (int)m1.tris.size(); ++i) ctx.tri(i);
+  out.min_distance = ctx.min_distance;
+  out.b1 = ctx.rb1;
+  out.b2 = -1;
+  out.p1 = ctx.p1;
+  out.p2 = ctx.p2;
+  return out.min_distance;
 }
 
 }  // namespace oracle

@@ -816,4 +816,100 @@ bool sphere_tri_intersect(const Vec3& center, double radius, const Vec3& P1, con
   return false;
 }
 
+// ---------------------------------------------------------------------------------------
+// Project<S>::projectLine / projectTriangle -- include/fcl/math/detail/project-inl.h:54-123,
+// and the nearest-point overload of sphereTriangleDistance (sphere_triangle-inl.h:469-508), which is
+// what the mesh <-> sphere distance leaf always reaches (it passes both nearest-point pointers,
+// mesh_shape_distance_traversal_node-inl.h:186-190).
+// ---------------------------------------------------------------------------------------
+namespace {
+struct ProjectResult {  // project.h:53-66, ctor project-inl.h:311-315
+  double parameterization[4] = {0.0, 0.0, 0.0, 0.0};
+  double sqr_distance = -1;
+  unsigned encode = 0;
+};
+
+ProjectResult project_line(const Vec3& a, const Vec3& b, const Vec3& p) {  // :54-73
+  ProjectResult res;
+  const Vec3 d = sub(b, a);
+  const double l = sqnorm(d);
+  if (l > 0) {
+    const double t = dot(sub(p, a), d);
+    res.parameterization[1] = (t >= l) ? 1 : ((t <= 0) ? 0 : (t / l));
+    res.parameterization[0] = 1 - res.parameterization[1];
+    if (t >= l) {
+      res.sqr_distance = sqnorm(sub(p, b));
+      res.encode = 2;
+    } else if (t <= 0) {
+      res.sqr_distance = sqnorm(sub(p, a));
+      res.encode = 1;
+    } else {
+      res.sqr_distance = sqnorm(sub(add(a, scale(d, res.parameterization[1])), p));
+      res.encode = 3;
+    }
+  }
+  return res;
+}
+
+ProjectResult project_triangle(const Vec3& a, const Vec3& b, const Vec3& c, const Vec3& p) {  // :77-123
+  ProjectResult res;
+  static const int nexti[3] = {1, 2, 0};
+  const Vec3* vt[] = {&a, &b, &c};
+  const Vec3 dl[] = {sub(a, b), sub(b, c), sub(c, a)};
+  const Vec3 n = cross(dl[0], dl[1]);
+  const double l = sqnorm(n);
+  if (l > 0) {
+    double mindist = -1;
+    for (int i = 0; i < 3; ++i) {
+      if (dot(sub(*vt[i], p), cross(dl[i], n)) > 0) {  // outside this edge: the optimum can only be on the edge
+        const int j = nexti[i];
+        const ProjectResult res_line = project_line(*vt[i], *vt[j], p);
+        if (mindist < 0 || res_line.sqr_distance < mindist) {
+          mindist = res_line.sqr_distance;
+          res.encode = ((res_line.encode & 1) ? 1u << i : 0u) + ((res_line.encode & 2) ? 1u << j : 0u);
+          res.parameterization[i] = res_line.parameterization[0];
+          res.parameterization[j] = res_line.parameterization[1];
+          res.parameterization[nexti[j]] = 0;
+        }
+      }
+    }
+    if (mindist < 0) {  // the projection falls inside the triangle
+      const double d = dot(sub(a, p), n);
+      const double s = std::sqrt(l);
+      const Vec3 p_to_project = scale(n, d / l);
+      mindist = sqnorm(p_to_project);
+      res.encode = 7;
+      res.parameterization[0] = norm(cross(dl[1], sub(sub(b, p), p_to_project))) / s;
+      res.parameterization[1] = norm(cross(dl[2], sub(sub(c, p), p_to_project))) / s;
+      res.parameterization[2] = 1 - res.parameterization[0] - res.parameterization[1];
+    }
+    res.sqr_distance = mindist;
+  }
+  return res;
+}
+}  // namespace
+
+// sphereTriangleDistance(sp, tf, P1, P2, P3, dist, p1, p2), :469-496: centre o = tf.translation(), triangle in
+// the same (world) frame.  Returns false -- and, in the reference, leaves *dist and the points UNWRITTEN --
+// when the centre is within the radius of the triangle (or the triangle has zero area: sqr_distance = -1).
+// on_sphere_world = o - dir * radius (before the reference maps it into the sphere's frame), on_triangle = project_p.
+bool sphere_tri_distance(const Vec3& o, double radius, const Vec3& P1, const Vec3& P2, const Vec3& P3, double* dist,
+                         Vec3* on_sphere_world, Vec3* on_triangle) {
+  const ProjectResult result = project_triangle(P1, P2, P3, o);
+  if (result.sqr_distance > radius * radius) {
+    if (dist) *dist = std::sqrt(result.sqr_distance) - radius;
+    const Vec3 project_p = add(add(scale(P1, result.parameterization[0]), scale(P2, result.parameterization[1])),
+                               scale(P3, result.parameterization[2]));
+    Vec3 dir = sub(o, project_p);
+    {  // Eigen normalize()
+      const double nn = norm(dir);
+      dir = Vec3{{dir[0] / nn, dir[1] / nn, dir[2] / nn}};
+    }
+    if (on_sphere_world) *on_sphere_world = sub(o, scale(dir, radius));
+    if (on_triangle) *on_triangle = project_p;
+    return true;
+  }
+  return false;
+}
+
 }  // namespace oracle

@@ -207,6 +207,59 @@ int orc_sphere_tri_intersect(const double* center, double radius, const double* 
   return hit ? 1 : 0;
 }
 
+// mesh <-> sphere distance batch (brute != 0: every triangle in primitive order instead of the traversal);
+// p1 in the mesh frame, p2 in the sphere frame, b1 = triangle; returns wall seconds
+double orc_distance_mesh_sphere_batch(void* h1, double radius, long long n, const double* tf1, const double* tf2,
+                                      int brute, int nthreads, double* dist, double* p1, double* p2, int32_t* b1,
+                                      long long* n_bv, long long* n_leaf) {
+  Model* m1 = (Model*)h1;
+  auto t0 = std::chrono::steady_clock::now();
+  parallel_for(n, nthreads, [&](long long i) {
+    Pose a = pose_from(tf1 ? tf1 + 12 * i : nullptr);
+    Pose c = pose_from(tf2 ? tf2 + 12 * i : nullptr);
+    CollideStats st;
+    DistanceOut o;
+    if (brute) brute_distance_mesh_sphere(*m1, a, radius, c, o);
+    else distance_mesh_sphere(*m1, a, radius, c, o, &st);
+    if (dist) dist[i] = o.min_distance;
+    for (int k = 0; k < 3; ++k) {
+      if (p1) p1[3 * i + k] = o.p1[k];
+      if (p2) p2[3 * i + k] = o.p2[k];
+    }
+    if (b1) b1[i] = o.b1;
+    if (n_bv) n_bv[i] = st.n_bv;
+    if (n_leaf) n_leaf[i] = st.n_leaf;
+  });
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// unit kernel: sphereTriangleDistance with nearest points, centre and triangle in one frame;
+// out7 = distance, point on the sphere (same frame), point on the triangle; returns 0 when the centre is within the radius
+int orc_sphere_tri_distance(const double* center, double radius, const double* tri9, double* out7) {
+  double d = 0;
+  Vec3 ps{{0, 0, 0}}, pt{{0, 0, 0}};
+  const bool ok = sphere_tri_distance(Vec3{{center[0], center[1], center[2]}}, radius, Vec3{{tri9[0], tri9[1], tri9[2]}},
+                                      Vec3{{tri9[3], tri9[4], tri9[5]}}, Vec3{{tri9[6], tri9[7], tri9[8]}}, &d, &ps, &pt);
+  if (out7 && ok) {
+    out7[0] = d;
+    for (int k = 0; k < 3; ++k) { out7[1 + k] = ps[k]; out7[4 + k] = pt[k]; }
+  }
+  return ok ? 1 : 0;
+}
+
+// computeBV<OBBRSS>(Sphere(radius), tf): axis9 row-major, obb_To3, obb_ext3, rss_To3, rss_l2, rss_r
+void orc_sphere_bv(double radius, const double* tf, double* axis9, double* obb_To, double* obb_ext, double* rss_To,
+                   double* rss_l, double* rss_r) {
+  Node bv;
+  sphere_obb(radius, pose_from(tf), bv);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) axis9[3 * r + c] = bv.axis.m[r][c];
+  for (int k = 0; k < 3; ++k) { obb_To[k] = bv.obb_To[k]; obb_ext[k] = bv.obb_ext[k]; rss_To[k] = bv.rss_To[k]; }
+  rss_l[0] = bv.rss_l[0];
+  rss_l[1] = bv.rss_l[1];
+  *rss_r = bv.rss_r;
+}
+
 double orc_collide_seconds(void* hb) { return ((CollideBatch*)hb)->seconds; }
 
 long long orc_collide_total(void* hb) {

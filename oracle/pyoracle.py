@@ -259,6 +259,52 @@ def brute_collide(m1, m2, tf1, tf2=None):
         cap = int(k)
 
 
+def distance_mesh_sphere_batch(m1, radius, tf1, tf2, brute=False, nthreads=1):
+    """fcl::distance(BVHModel<OBBRSS>, tf1[i], Sphere(radius), tf2[i]): p1 in the mesh frame, p2 in the sphere frame
+    (the reference leaves them local), b1 = closest triangle; centre within the radius of a triangle: -1 and NaN
+    points (the reference leaves that case undefined).  brute=True tests every triangle in primitive order."""
+    L = lib()
+    dp, lp, ip = C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_int32)
+    L.orc_distance_mesh_sphere_batch.restype = C.c_double
+    L.orc_distance_mesh_sphere_batch.argtypes = [C.c_void_p, C.c_double, C.c_longlong, dp, dp, C.c_int, C.c_int, dp, dp, dp,
+                                                 ip, lp, lp]
+    tf1 = _poses(tf1)
+    tf2 = _poses(tf2)
+    n = len(tf1) if tf1 is not None else len(tf2)
+    dist = np.empty(n)
+    p1 = np.empty((n, 3))
+    p2 = np.empty((n, 3))
+    b1 = np.empty(n, np.int32)
+    n_bv = np.zeros(n, np.int64)
+    n_leaf = np.zeros(n, np.int64)
+    secs = L.orc_distance_mesh_sphere_batch(m1.h, float(radius), n, _dp(tf1), _dp(tf2), int(brute), nthreads, _dp(dist),
+                                            _dp(p1), _dp(p2), _ip(b1), _lp(n_bv), _lp(n_leaf))
+    return dict(min_distance=dist, p1=p1, p2=p2, b1=b1, n_bv=n_bv, n_leaf=n_leaf, seconds=secs)
+
+
+def sphere_tri_distance(center, radius, tri9):
+    """(separated, distance, point_on_sphere[3], point_on_triangle[3]) of sphereTriangleDistance in one frame."""
+    L = lib()
+    L.orc_sphere_tri_distance.argtypes = [C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    c = np.ascontiguousarray(center, dtype=np.float64).reshape(3)
+    t = np.ascontiguousarray(tri9, dtype=np.float64).reshape(9)
+    out = np.zeros(7)
+    ok = L.orc_sphere_tri_distance(_dp(c), float(radius), _dp(t), _dp(out))
+    return bool(ok), float(out[0]), out[1:4].copy(), out[4:].copy()
+
+
+def sphere_bv(radius, tf):
+    """computeBV<OBBRSS>(Sphere(radius), tf) -> dict(axis, obb_To, obb_ext, rss_To, rss_l, rss_r)."""
+    L = lib()
+    dp = C.POINTER(C.c_double)
+    L.orc_sphere_bv.restype = None
+    L.orc_sphere_bv.argtypes = [C.c_double, dp, dp, dp, dp, dp, dp, dp]
+    tf = np.ascontiguousarray(tf, dtype=np.float64).reshape(12)
+    axis, oT, oe, rT, rl, rr = np.zeros(9), np.zeros(3), np.zeros(3), np.zeros(3), np.zeros(2), np.zeros(1)
+    L.orc_sphere_bv(float(radius), _dp(tf), _dp(axis), _dp(oT), _dp(oe), _dp(rT), _dp(rl), _dp(rr))
+    return dict(axis=axis.reshape(3, 3), obb_To=oT, obb_ext=oe, rss_To=rT, rss_l=rl, rss_r=float(rr[0]))
+
+
 def brute_distance(m1, m2, tf1, tf2=None):
     tf1 = None if tf1 is None else np.ascontiguousarray(tf1, dtype=np.float64).reshape(12)
     tf2 = None if tf2 is None else np.ascontiguousarray(tf2, dtype=np.float64).reshape(12)

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "devmath_host.cu")
 _CSRC = os.path.join(_HERE, "..", "..", "fcl_b200", "csrc")
 _HDR = os.path.join(_CSRC, "device_math.cuh")
-_HDRS = [os.path.join(_CSRC, f) for f in ("device_math.cuh", "bounds_f32.cuh", "records.hpp")]
+_HDRS = [os.path.join(_CSRC, f) for f in ("device_math.cuh", "mesh_sphere.cuh", "bounds_f32.cuh", "records.hpp")]
 _OUT = os.path.join(_HERE, "_build", "libdevmath_host.so")
 
 
@@ -40,6 +40,13 @@ def lib():
         L.hm_tri_intersect.argtypes = [dp, dp, dp, C.c_int, C.POINTER(C.c_uint32), dp, dp, dp]
         L.hm_tri_distance.restype = C.c_double
         L.hm_tri_distance.argtypes = [dp, dp, dp, dp]
+        L.hm_sphere_tri_intersect.restype = C.c_int
+        L.hm_sphere_tri_intersect.argtypes = [dp, C.c_double, dp, dp]
+        L.hm_sphere_tri_distance.restype = C.c_int
+        L.hm_sphere_tri_distance.argtypes = [dp, C.c_double, dp, dp]
+        L.hm_mesh_sphere_distance.restype = C.c_int
+        L.hm_mesh_sphere_distance.argtypes = [C.c_longlong, dp, dp, C.c_double, ip, dp, dp, dp, dp, dp, dp, dp, ip,
+                                              C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.hm_obb_disjoint32_pairs.argtypes = [C.c_longlong, dp, ip, ip, dp, dp, dp, dp, dp, dp, ip]
         L.hm_tri_classify32.restype = C.c_int
         L.hm_tri_classify32.argtypes = [dp, dp, dp]

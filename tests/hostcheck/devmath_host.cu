@@ -2,6 +2,7 @@
 // suite can compare it bit-for-bit with the oracle without a GPU.  Not part of the product.
 #include "../../fcl_b200/csrc/device_math.cuh"
 #include "../../fcl_b200/csrc/bounds_f32.cuh"
+#include "../../fcl_b200/csrc/mesh_sphere.cuh"
 #include "../../fcl_b200/csrc/records.hpp"
 using namespace fclgpu;
 
@@ -58,6 +59,75 @@ double hm_tri_distance(const double* S9, const double* T9, double* P3, double* Q
   double d = tri_distance(S, T, P, Q);
   P3[0] = P.x; P3[1] = P.y; P3[2] = P.z; Q3[0] = Q.x; Q3[1] = Q.y; Q3[2] = Q.z;
   return d;
+}
+// sphere (centre c3, radius) vs triangle T9, one frame; out7 = contact point, depth, normal (as the routine writes them)
+int hm_sphere_tri_intersect(const double* c3, double radius, const double* T9, double* out7) {
+  V3 T[3] = {v3(T9), v3(T9 + 3), v3(T9 + 6)};
+  V3 cp = mk(0, 0, 0), nrm = mk(0, 0, 0);
+  double depth = 0;
+  const bool hit = sphere_tri_intersect(v3(c3), radius, T, cp, depth, nrm);
+  if (hit) {
+    out7[0] = cp.x; out7[1] = cp.y; out7[2] = cp.z; out7[3] = depth; out7[4] = nrm.x; out7[5] = nrm.y; out7[6] = nrm.z;
+  }
+  return hit ? 1 : 0;
+}
+// out7 = distance, point on the sphere, point on the triangle; 0 = centre within the radius
+int hm_sphere_tri_distance(const double* c3, double radius, const double* T9, double* out7) {
+  V3 T[3] = {v3(T9), v3(T9 + 3), v3(T9 + 6)};
+  V3 ps = mk(0, 0, 0), pt = mk(0, 0, 0);
+  double d = 0;
+  const bool ok = sphere_tri_distance(v3(c3), radius, T, d, ps, pt);
+  if (ok) {
+    out7[0] = d; out7[1] = ps.x; out7[2] = ps.y; out7[3] = ps.z; out7[4] = pt.x; out7[5] = pt.y; out7[6] = pt.z;
+  }
+  return ok ? 1 : 0;
+}
+// The product's mesh <-> sphere distance traversal (mesh_sphere.cuh, the code the kernel inlines) over host arrays:
+// first_child[n_nodes], axis 9 / obb_To 3 / obb_ext 3 per node, tri9 = de-indexed triangles.  Outputs as the
+// kernel writes them (p1 mesh frame, p2 sphere frame, NaN points and -1 when the centre is within the radius).
+struct HostMeshAccessor {
+  const int* fc;
+  const double *axis, *To, *ext, *tri9;
+  int first_child(int b) const { return fc[b]; }
+  void box(int b, M3& A, V3& T, double& e0, double& e1, double& e2) const {
+    A = m3(axis + 9 * b);
+    T = v3(To + 3 * b);
+    e0 = ext[3 * b];
+    e1 = ext[3 * b + 1];
+    e2 = ext[3 * b + 2];
+  }
+  void tri(int id, V3 T[3]) const {
+    for (int k = 0; k < 3; ++k) T[k] = v3(tri9 + 9 * id + 3 * k);
+  }
+};
+int hm_mesh_sphere_distance(long long n, const double* tf1, const double* tf2, double radius, const int* first_child,
+                            const double* axis, const double* obb_To, const double* obb_ext, const double* tri9,
+                            double* dist, double* p1, double* p2, int* b1, unsigned* n_bv, unsigned* n_leaf) {
+  const HostMeshAccessor acc{first_child, axis, obb_To, obb_ext, tri9};
+  int stk[128];
+  float lb[128];
+  int overflow = 0;
+  for (long long q = 0; q < n; ++q) {
+    const M3 R1 = m3(tf1 + 12 * q), R2 = m3(tf2 + 12 * q);
+    const V3 t1 = v3(tf1 + 12 * q + 9), t2 = v3(tf2 + 12 * q + 9);
+    MeshSphereDistance s;
+    mesh_sphere_distance_query(acc, R1, t1, t2, radius, stk, lb, 128, s);
+    overflow |= s.overflow;
+    dist[q] = s.min_d;
+    b1[q] = s.best;
+    n_bv[q] = s.bv_tests;
+    n_leaf[q] = s.leaf_tests;
+    V3 a, b;
+    if (s.min_d < 0.0) {
+      a = b = mk(NAN, NAN, NAN);
+    } else {
+      a = inverse_apply(R1, t1, s.on_tri);
+      b = inverse_apply(R2, t2, s.on_sph);
+    }
+    p1[3 * q] = a.x; p1[3 * q + 1] = a.y; p1[3 * q + 2] = a.z;
+    p2[3 * q] = b.x; p2[3 * q + 1] = b.y; p2[3 * q + 2] = b.z;
+  }
+  return overflow;
 }
 // conservative FP32 RSS lower bound on n node pairs (records packed exactly like the upload step does)
 void hm_rss_lb32_pairs(long long n, const double* pose12, const int* idx1, const int* idx2,

@@ -142,6 +142,107 @@ def test_tri_distance_matches_oracle(hm, oracle):
     assert 0 < zero < n
 
 
+def _sphere_cases(rng, n):
+    """Triangles of size ~1 and sphere centres placed over faces, edges, vertices, far away and on the plane."""
+    T = rng.normal(0, 1, size=(n, 9))
+    w = rng.dirichlet([1, 1, 1], size=n)
+    w[: n // 4] = rng.dirichlet([0.05, 0.05, 0.05], size=n // 4)  # close to vertices / edges
+    on = np.einsum("nk,nkj->nj", w, T.reshape(n, 3, 3))
+    nrm = np.cross(T[:, 3:6] - T[:, :3], T[:, 6:] - T[:, :3])
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    h = rng.normal(0, 1.0, size=(n, 1))
+    h[n // 2: n // 2 + n // 8] = 0.0  # centre in the triangle's plane
+    c = on + nrm * h + rng.normal(0, 0.7, size=(n, 3)) * (rng.random((n, 1)) < 0.6)
+    radius = rng.choice([0.0, 0.05, 0.5, 1.5], size=n)
+    T[n - 200:, 3:6] = T[n - 200:, :3]  # zero-area triangles
+    return T, c, radius
+
+
+def test_sphere_triangle_routines_match_oracle(hm, oracle):
+    rng = np.random.default_rng(21)
+    L = hm.lib()
+    n = 40000
+    T, c, radius = _sphere_cases(rng, n)
+    hits = seps = 0
+    for k in range(n):
+        out = np.zeros(7)
+        g = L.hm_sphere_tri_intersect(hm.dptr(c[k]), float(radius[k]), hm.dptr(T[k]), hm.dptr(out))
+        hit, cp, depth, nrm = oracle.sphere_tri_intersect(c[k], radius[k], T[k])
+        assert bool(g) == hit, k
+        if hit:
+            assert out.tobytes() == np.concatenate([cp, [depth], nrm]).tobytes(), k
+        hits += hit
+        out = np.zeros(7)
+        g = L.hm_sphere_tri_distance(hm.dptr(c[k]), float(radius[k]), hm.dptr(T[k]), hm.dptr(out))
+        ok, d, ps, pt = oracle.sphere_tri_distance(c[k], radius[k], T[k])
+        assert bool(g) == ok, k
+        if ok:
+            assert out.tobytes() == np.concatenate([[d], ps, pt]).tobytes(), k
+            if k < n - 200:  # the closed form really is the point-triangle distance (checked against sampling-free geometry)
+                assert abs(np.linalg.norm(pt - c[k]) - radius[k] - d) < 1e-9 * max(1.0, d)
+        seps += ok
+    assert 0.05 * n < hits < 0.95 * n and 0.05 * n < seps < 0.95 * n
+
+
+def _host_mesh_sphere(hm, model, verts, tris, radius, M, S):
+    a = model.arrays()
+    tri9 = np.ascontiguousarray(np.asarray(verts, np.float64)[np.asarray(tris)].reshape(-1, 9))
+    n = len(S)
+    dist, p1, p2 = np.empty(n), np.empty((n, 3)), np.empty((n, 3))
+    b1, n_bv, n_leaf = np.empty(n, np.int32), np.empty(n, np.uint32), np.empty(n, np.uint32)
+    M, S = np.ascontiguousarray(M), np.ascontiguousarray(S)
+    ov = hm.lib().hm_mesh_sphere_distance(n, hm.dptr(M), hm.dptr(S), float(radius), hm.iptr(a["first_child"]), hm.dptr(a["axis"]),
+                                          hm.dptr(a["obb_To"]), hm.dptr(a["obb_ext"]), hm.dptr(tri9), hm.dptr(dist), hm.dptr(p1),
+                                          hm.dptr(p2), hm.iptr(b1), n_bv.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                          n_leaf.ctypes.data_as(C.POINTER(C.c_uint32)))
+    assert ov == 0
+    return dict(min_distance=dist, p1=p1, p2=p2, b1=b1, n_bv=n_bv, n_leaf=n_leaf)
+
+
+def test_mesh_sphere_distance_traversal_matches_oracle(hm, oracle, env_rob_npz):
+    """The traversal the kernel inlines (csrc/mesh_sphere.cuh), run on the host over the oracle's node arrays:
+    minimum distance bit-exact against the oracle's brute-force pass over all triangles (the point-to-box bound
+    never excludes the closest triangle), equal to the reference-order traversal up to ties between adjacent
+    triangles, nearest points bit-exact whenever the same triangle is reported."""
+    from fcl_b200.poses import identity_poses
+    from tests.meshes import heightfield
+
+    (ev, et), _ = env_rob_npz
+    hv, ht = heightfield(40, size=10.0, seed=5, amp=0.5)
+    rng = np.random.default_rng(5)
+    cases = []
+    n = 6000
+    S = random_poses(n, seed=31)
+    M = identity_poses(n)
+    M[: n // 2] = random_poses(n // 2, seed=37)
+    S[: n // 2, 9:] = np.einsum("nij,nj->ni", M[: n // 2, :9].reshape(-1, 3, 3), S[: n // 2, 9:]) + M[: n // 2, 9:]
+    cases.append((ev, et, (0.0, 10.0, 150.0, 600.0), M, S))
+    Sh = identity_poses(3000)
+    Sh[:, 9:11] = rng.uniform(-6, 6, size=(3000, 2))
+    Sh[:, 11] = rng.uniform(-1.0, 3.0, size=3000)
+    cases.append((hv, ht, (0.05, 0.3), identity_poses(3000), Sh))
+    for v, t, radii, M, S in cases:
+        o = oracle.Model(v, t)
+        for radius in radii:
+            got = _host_mesh_sphere(hm, o, v, t, radius, M, S)
+            brute = oracle.distance_mesh_sphere_batch(o, radius, M, S, brute=True, nthreads=8)
+            trav = oracle.distance_mesh_sphere_batch(o, radius, M, S, nthreads=8)
+            assert np.array_equal(got["min_distance"], brute["min_distance"]), radius
+            pos = brute["min_distance"] > 0
+            assert np.array_equal(brute["min_distance"] < 0, trav["min_distance"] < 0)
+            rel = np.abs(brute["min_distance"][pos] - trav["min_distance"][pos]) / trav["min_distance"][pos]
+            assert rel.max() <= 1e-12
+            same = pos & (got["b1"] == brute["b1"])
+            assert same.sum() > 0.3 * pos.sum()  # exact ties at shared vertices / edges may name the neighbouring triangle
+            assert got["p1"][same].tobytes() == brute["p1"][same].tobytes()
+            assert got["p2"][same].tobytes() == brute["p2"][same].tobytes()
+            assert np.allclose(got["p1"][pos], brute["p1"][pos], rtol=1e-6, atol=1e-6 * (1 + np.abs(brute["p1"][pos]).max()))
+            assert np.isnan(got["p1"][~pos]).all() and np.isnan(got["p2"][~pos]).all()
+            # tighter bound than the reference's RSS-to-RSS test: no more leaf tests than its traversal
+            assert got["n_leaf"].mean() <= trav["n_leaf"].mean() + 1
+            assert 0 < pos.sum() and (radius < 100 or (~pos).sum() > 0)
+
+
 def test_f32_rss_lower_bound_is_conservative(hm, oracle, oracle_env_rob):
     """The single-precision steering bound must never exceed the exact RSS distance (it may be
     smaller): checked on real node pairs at the benchmark's pose distribution and on close /

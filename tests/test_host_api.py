@@ -107,6 +107,11 @@ def test_no_cpu_fallback_without_device():
     assert ei.value.code == _capi.ERR_NO_DEVICE
     with pytest.raises(F.FclGpuError):
         F.distance_batch(m, random_poses(4), m, None, F.DistanceRequest())
+    with pytest.raises(F.FclGpuError) as ei:
+        F.distance_mesh_sphere_batch(m, random_poses(4), F.Sphere(1.0), random_poses(4, seed=2), F.DistanceRequest(True))
+    assert ei.value.code == _capi.ERR_NO_DEVICE
+    with pytest.raises(F.FclGpuError):
+        F.collide_mesh_sphere_batch(m, random_poses(4), F.Sphere(1.0), random_poses(4, seed=2), F.CollisionRequest())
 
 
 def test_pose_generator_is_reproducible_and_shardable():

@@ -221,3 +221,54 @@ def test_mesh_sphere_traversal_equals_brute_force(oracle, oracle_env_rob):
     c = full["contacts"]
     assert (c["depth"] <= 0).all() and (c["depth"] >= -radius).all()
     assert np.allclose(np.linalg.norm(c["normal"], axis=1), 1.0, atol=1e-12)
+
+
+def test_mesh_sphere_distance_reference_known_answers(oracle):
+    """test/test_fcl_shape_mesh_consistency.cpp:57-140, the `distance(&s1_rss, pose1, &s2, pose2)` legs: an r=20
+    tessellated sphere (16x16) against an r=20 Sphere, centres 50 apart -> within 5 % of the analytic 10; 40.1 apart
+    -> within 200 % of 0.1; both also under ten common random rigid motions (extents 0..10).  Then the oracle's own
+    invariants: traversal == brute force over all triangles, |tf1 p1 - tf2 p2| == distance, p2 on the sphere."""
+    v, t = uv_sphere(20, 16, 16)
+    m = oracle.Model(v, t)
+    T = random_poses(10, seed=7, extents=(0, 0, 0, 10, 10, 10))
+    for gap, tol in ((50.0, 0.05), (40.1, 2.0)):
+        true = gap - 40.0
+        tf1 = np.concatenate([identity_poses(1), T])
+        tf2 = tf1.copy()
+        R = tf1[:, :9].reshape(-1, 3, 3)
+        tf2[:, 9:] = np.einsum("nij,j->ni", R, np.array([gap, 0.0, 0.0])) + tf1[:, 9:]
+        r = oracle.distance_mesh_sphere_batch(m, 20.0, tf1, tf2)
+        assert np.all(np.abs(r["min_distance"] - true) / true < tol)
+        assert np.allclose(r["min_distance"], r["min_distance"][0], rtol=1e-9)
+        b = oracle.distance_mesh_sphere_batch(m, 20.0, tf1, tf2, brute=True)
+        assert np.array_equal(r["min_distance"], b["min_distance"])
+        w1 = np.einsum("nij,nj->ni", R, r["p1"]) + tf1[:, 9:]
+        w2 = np.einsum("nij,nj->ni", tf2[:, :9].reshape(-1, 3, 3), r["p2"]) + tf2[:, 9:]
+        assert np.allclose(np.linalg.norm(w1 - w2, axis=1), r["min_distance"], atol=1e-9)
+        assert np.allclose(np.linalg.norm(r["p2"], axis=1), 20.0, atol=1e-9)
+    # centre within the radius of a triangle: the reference leaves the result unwritten; defined here as -1 / NaN
+    tf2 = identity_poses(1)
+    tf2[0, 9] = 30.0
+    r = oracle.distance_mesh_sphere_batch(m, 20.0, identity_poses(1), tf2)
+    assert r["min_distance"][0] == -1.0 and np.isnan(r["p1"]).all()
+
+
+def test_sphere_fitted_obbrss_encloses_its_bound_vertices(oracle):
+    """computeBV<OBBRSS>(Sphere, tf) = fit over the 12 bound vertices (geometry/shape/sphere-inl.h:95-120,
+    math/bv/utility-inl.h:516-521): every bound vertex lies inside the OBB and within r of the RSS rectangle."""
+    m = (1 + np.sqrt(5.0)) / 2.0
+    for radius, seed in ((1.0, 1), (20.0, 2), (350.0, 3)):
+        tf = random_poses(1, seed=seed)[0]
+        bv = oracle.sphere_bv(radius, tf)
+        edge = radius * 6 / (np.sqrt(27.0) + np.sqrt(15.0))
+        a, b = edge, m * edge
+        L = np.array([[0, a, b], [0, -a, b], [0, a, -b], [0, -a, -b], [a, b, 0], [-a, b, 0], [a, -b, 0], [-a, -b, 0],
+                      [b, 0, a], [b, 0, -a], [-b, 0, a], [-b, 0, -a]])
+        P = L @ tf[:9].reshape(3, 3).T + tf[9:]
+        loc = (P - bv["obb_To"]) @ bv["axis"]
+        assert np.all(np.abs(loc) <= bv["obb_ext"] * (1 + 1e-12) + 1e-9)
+        q = (P - bv["rss_To"]) @ bv["axis"]
+        dx = np.maximum(np.maximum(-q[:, 0], q[:, 0] - bv["rss_l"][0]), 0)
+        dy = np.maximum(np.maximum(-q[:, 1], q[:, 1] - bv["rss_l"][1]), 0)
+        assert np.all(np.sqrt(dx * dx + dy * dy + q[:, 2] ** 2) <= bv["rss_r"] * (1 + 1e-9) + 1e-9)
+        assert np.all(np.linalg.norm(P - tf[9:], axis=1) >= radius * (1 - 1e-12))  # the icosahedron encloses the sphere
