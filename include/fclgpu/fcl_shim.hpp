@@ -188,5 +188,29 @@ inline void distance(const DeviceModel& o1, const std::vector<fcl::Transform3<do
   }
 }
 
+// n independent fcl::distance(mesh, tf1[i], sphere, tf2[i], request, results[i]) calls
+// (distance_matrix[BV_OBBRSS][GEOM_SPHERE]).  Like the reference's mesh-shape leaf, the nearest points are always
+// handed to DistanceResult::update and stay in the local frames of the mesh and of the sphere; b2 = NONE.
+inline void distance(const DeviceModel& o1, const std::vector<fcl::Transform3<double>>& tf1, const fcl::Sphere<double>& sphere,
+                     const std::vector<fcl::Transform3<double>>& tf2, const fcl::DistanceRequest<double>& request,
+                     std::vector<fcl::DistanceResult<double>>& results) {
+  const int64_t n = (int64_t)tf1.size();
+  results.assign(n, fcl::DistanceResult<double>());
+  if (n == 0) return;
+  std::vector<double> p1(12 * n), p2(12 * n), d(n), a(3 * n), b(3 * n);
+  std::vector<int32_t> b1(n);
+  for (int64_t i = 0; i < n; ++i) {
+    to_pose(tf1[i], &p1[12 * i]);
+    to_pose(tf2[i], &p2[12 * i]);
+  }
+  fclgpu_distance_request req{1, request.enable_signed_distance ? 1 : 0, request.rel_err, request.abs_err};
+  check(fclgpu_distance_mesh_sphere_batch_host(o1.handle(), sphere.radius, n, p1.data(), p2.data(), &req, d.data(), a.data(),
+                                               b.data(), b1.data(), nullptr, nullptr, nullptr));
+  for (int64_t i = 0; i < n; ++i)
+    results[i].update(d[i], o1.host(), &sphere, b1[i], fcl::DistanceResult<double>::NONE,
+                      fcl::Vector3<double>(a[3 * i], a[3 * i + 1], a[3 * i + 2]),
+                      fcl::Vector3<double>(b[3 * i], b[3 * i + 1], b[3 * i + 2]));
+}
+
 }  // namespace fclgpu
 #endif  // FCLGPU_HAVE_FCL

@@ -153,6 +153,7 @@ struct DistanceResult {
   Vector3<S> nearest_points[2];
   const CollisionGeometry<S>* o1 = nullptr;
   const CollisionGeometry<S>* o2 = nullptr;
+  static const int NONE = -1;  // distance_result.h:78
   int b1 = -1, b2 = -1;
   void update(S d, const CollisionGeometry<S>* a, const CollisionGeometry<S>* b, int i, int j) {
     if (min_distance > d) { min_distance = d; o1 = a; o2 = b; b1 = i; b2 = j; }

@@ -160,6 +160,25 @@ int main(int argc, char** argv) {
     }
     if (shits == 0) { std::printf("FAIL: no sphere hits\n"); return 1; }
     std::printf("shim sphere OK: %lld colliding\n", shits);
+    // mesh <-> sphere distance through the shim vs the C ABI
+    std::vector<fcl::DistanceResult<double>> sd;
+    fclgpu::distance(d1, tf1, sph, tf2, fcl::DistanceRequest<double>(false), sd);
+    std::vector<double> sdist(n), sa(3 * (size_t)n), sb(3 * (size_t)n);
+    std::vector<int32_t> sb1(n);
+    fclgpu_distance_request sreq{1, 0, 0.0, 0.0};
+    fclgpu::check(fclgpu_distance_mesh_sphere_batch_host(g1, 0.5, n, nullptr, p2.data(), &sreq, sdist.data(), sa.data(), sb.data(), sb1.data(), nullptr, nullptr, nullptr));
+    long long separated = 0;
+    for (int i = 0; i < n; ++i) {
+      if (sd[i].min_distance != sdist[i] || sd[i].b1 != sb1[i] || sd[i].b2 != fcl::DistanceResult<double>::NONE || sd[i].o2 != &sph ||
+          std::memcmp(sd[i].nearest_points[0].v, &sa[3 * (size_t)i], 24) || std::memcmp(sd[i].nearest_points[1].v, &sb[3 * (size_t)i], 24)) {
+        std::printf("FAIL sphere distance %d\n", i);
+        return 1;
+      }
+      separated += sdist[i] > 0;
+      if ((sdist[i] > 0) != (scnt[i] == 0)) { std::printf("FAIL sphere distance vs collide verdict %d\n", i); return 1; }
+    }
+    if (separated == 0) { std::printf("FAIL: no separated sphere\n"); return 1; }
+    std::printf("shim sphere distance OK: %lld separated\n", separated);
   }
   if (colliding < n / 20 || colliding > n - n / 20) { std::printf("FAIL: degenerate pose sample (%lld colliding)\n", colliding); return 1; }
   std::printf("shim OK: %d queries, %lld colliding, %lld contacts compared, distances identical\n", n, colliding, contacts);

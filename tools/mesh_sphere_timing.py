@@ -30,3 +30,28 @@ for radius in (100.0, 350.0, 800.0):
         ms = e0.elapsed_time(e1) / 3
         F.sync_status()
         print("sphere r=%-5g %-14s %.2f ms per 1M queries  %.3g q/s  (colliding %.0f %%, contacts/query %.1f)" % (radius, label, ms, n / ms * 1e3, 100.0 * (cnt > 0).float().mean().item(), cnt.float().mean().item()))
+
+# ---- mesh <-> sphere distance (same poses): kernel time, separated fraction, work per query ----
+dist = torch.empty(n, dtype=torch.float64, device="cuda")
+p1 = torch.empty(3 * n, dtype=torch.float64, device="cuda")
+p2 = torch.empty(3 * n, dtype=torch.float64, device="cuda")
+b1 = torch.empty(n, dtype=torch.int32, device="cuda")
+nbv = torch.empty(n, dtype=torch.int32, device="cuda")
+nlf = torch.empty(n, dtype=torch.int32, device="cuda")
+dq = F.DistanceRequest(True)._c()
+for radius in (10.0, 100.0, 350.0):
+    def run_d(stats=False):
+        rc = L.fclgpu_distance_mesh_sphere_batch(env.device_model(0), radius, n, None, S.data_ptr(), C.byref(dq), dist.data_ptr(),
+                                                 p1.data_ptr(), p2.data_ptr(), b1.data_ptr(), None,
+                                                 nbv.data_ptr() if stats else None, nlf.data_ptr() if stats else None,
+                                                 torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, rc
+    run_d(True); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3): run_d()
+    e1.record(); e1.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    F.sync_status()
+    print("sphere r=%-5g distance+points %.2f ms per 1M queries  %.3g q/s  (separated %.0f %%, box tests/query %.1f, triangle tests/query %.1f)" % (
+        radius, ms, n / ms * 1e3, 100.0 * (dist > 0).float().mean().item(), nbv.float().mean().item(), nlf.float().mean().item()))
