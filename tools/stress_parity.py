@@ -100,8 +100,19 @@ while time.time() < t_end:
     rs = O.collide_mesh_sphere_batch(o1, r, P1, S, mx, True, nthreads=8)
     gs = F.collide_mesh_sphere_batch(m1, P1, F.Sphere(r), S, F.CollisionRequest(mx, True), contact_capacity=max(64 * n, 1024), grow_on_overflow=True)
     ok = ok and np.array_equal(gs.num_contacts, rs["counts"]) and gs.contacts.tobytes() == rs["contacts"].tobytes()
+    # mesh <-> sphere distance: bit-exact against the oracle's pass over all triangles, within tie rounding of its traversal
+    bs = O.distance_mesh_sphere_batch(o1, r, P1, S, brute=len(t1) * n <= 40_000_000, nthreads=8)
+    ds = F.distance_mesh_sphere_batch(m1, P1, F.Sphere(r), S, F.DistanceRequest(True), pinned=pinned)
+    if len(t1) * n <= 40_000_000:
+        ok = ok and np.array_equal(ds.min_distance, bs["min_distance"])
+    else:
+        ok = ok and np.array_equal(ds.min_distance < 0, bs["min_distance"] < 0) and bool(
+            np.all(np.abs(ds.min_distance - bs["min_distance"]) <= 1e-12 * np.abs(bs["min_distance"])))
+    sep = bs["min_distance"] > 0
+    if sep.any():
+        ok = ok and bool((np.abs(ds.nearest_p1[sep] - bs["p1"][sep]) <= 1e-6 * (np.abs(bs["p1"][sep]).max() + 1.0)).all())
     rounds += 1
-    checks += 4 * n
+    checks += 5 * n
     if not ok:
         print("MISMATCH", tag)
         np.savez("gpurun_out/stress_fail.npz", v1=v1, t1=t1, v2=v2, t2=t2, P1=P1, P2=P2 if P2 is not None else np.zeros(0), S=S, r=r)
