@@ -27,18 +27,20 @@ FD float float_below(double x) {
 
 // Lower bound on (distance from the sphere to anything inside the node's OBB): exact distance from the centre
 // cm (mesh frame) to the box, minus the radius, minus a margin far above the rounding error of the box fit,
-// of cm and of the leaf arithmetic (which runs in the world frame): 1e-9 relative + 1e-9 of the coordinates'
+// of cm and of the leaf arithmetic (which runs in the world frame): 2e-7 relative + 1e-9 of the coordinates'
 // magnitude, against rounding errors of ~1e-15 of that magnitude.
 // The reference bounds a node by the RSS distance between the node's RSS and an RSS fitted around the sphere's
 // 12 bound vertices; a bound only decides which triangles get tested, so any valid lower bound yields the
 // minimum over all triangles no valid bound excludes.
+// The square root runs in single precision (correctly rounded on both host and device, so the two agree bit for
+// bit): g = sqrtf(rd(gap^2)) <= sqrt(gap^2) (1 + 2^-24), and g * 0.9999998 <= gap.
 FD double sphere_box_lower_bound(const M3& axis, const V3& To, double e0, double e1, double e2, const V3& cm,
                                  double cm_l1, double radius) {
   const V3 l = mulTv(axis, cm - To);
   const double ex = fmax(fabs(l.x) - e0, 0.0), ey = fmax(fabs(l.y) - e1, 0.0), ez = fmax(fabs(l.z) - e2, 0.0);
   const double scale = (((fabs(To.x) + fabs(To.y)) + fabs(To.z)) + ((e0 + e1) + e2)) + cm_l1;
-  const double gap = sqrt((ex * ex + ey * ey) + ez * ez);
-  return (gap * 0.999999999 - radius) - 1e-9 * scale;
+  const float g = sqrtf(float_below((ex * ex + ey * ey) + ez * ez));
+  return ((double)g * 0.9999998 - radius) - 1e-9 * scale;
 }
 
 struct MeshSphereDistance {
@@ -53,6 +55,7 @@ struct MeshSphereDistance {
 // Leaf: sphere_tri_distance on the triangle moved to the world by tf1 = (R1, t1), like the reference's
 // transformed shapeTriangleDistance (sphere_triangle-inl.h:499-508).  Centre within the radius of the triangle
 // (the reference's solver returns false and its leaf reads an uninitialised distance): DEFINED as -1.
+#pragma nv_exec_check_disable
 template <class Acc>
 FD void mesh_sphere_leaf(const Acc& acc, int id, const M3& R1, const V3& t1, const V3& c, double radius,
                          MeshSphereDistance& s) {

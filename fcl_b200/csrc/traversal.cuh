@@ -1784,4 +1784,126 @@ __global__ void __launch_bounds__(128) distance_mesh_sphere_kernel(DistanceParam
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// The same query with the leaf tests taken out of the box loop (default).  In the kernel above a warp pays for the
+// triangle routine in almost every iteration -- some lane is at a leaf 80 % of the time while the other ~30 lanes
+// wait (ncu: profiles/r01_ncu_sphere_distance.txt).  Here a lane that reaches a leaf (or has just fetched a
+// query: the preprocess seed, triangle 0) parks the triangle id and waits; the warp runs a LEAF ROUND -- every
+// parked lane runs sphere_tri_distance at once -- when `leaf_trigger` lanes are parked or nobody can do box work.
+// Bound, leaf and result arithmetic are the shared routines of mesh_sphere.cuh; only the interleaving differs, and
+// the minimum over the triangles does not depend on it.
+// ---------------------------------------------------------------------------------------
+template <bool kStats>
+__global__ void __launch_bounds__(128) distance_mesh_sphere_rounds_kernel(DistanceParams P, double radius, int leaf_trigger) {
+  int stk[kStackCap];
+  float stk_lb[kStackCap];
+  const DeviceMeshAccessor acc{P.m1};
+  int sp = 0, pend = -1;
+  long long q = -1;
+  bool exhausted = false;
+  PoseRT tf1, tf2;
+  V3 cm = mk(0, 0, 0);
+  double cm_l1 = 0;
+  MeshSphereDistance s;
+  s.min_d = 0;
+  s.best = -1;
+  s.on_tri = s.on_sph = mk(0, 0, 0);
+  s.bv_tests = s.leaf_tests = 0;
+  s.overflow = false;
+  while (true) {
+    const bool idle = (sp == 0) && (pend < 0);
+    if (idle && q >= 0) {
+      if (P.min_distance) P.min_distance[q] = s.min_d;
+      if (P.b1) P.b1[q] = s.best;
+      if (P.b2) P.b2[q] = -1;  // DistanceResult::NONE
+      if (P.enable_nearest_points) {
+        V3 a, b;
+        if (s.min_d < 0.0) {
+          const double nan = __longlong_as_double(0x7ff8000000000000LL);
+          a = b = mk(nan, nan, nan);
+        } else {
+          a = inverse_apply(tf1.R, tf1.t, s.on_tri);
+          b = inverse_apply(tf2.R, tf2.t, s.on_sph);
+        }
+        if (P.p1) { P.p1[3 * q] = a.x; P.p1[3 * q + 1] = a.y; P.p1[3 * q + 2] = a.z; }
+        if (P.p2) { P.p2[3 * q] = b.x; P.p2[3 * q + 1] = b.y; P.p2[3 * q + 2] = b.z; }
+      }
+      if (kStats) {
+        if (P.n_bv) P.n_bv[q] = s.bv_tests;
+        if (P.n_leaf) P.n_leaf[q] = s.leaf_tests;
+      }
+      q = -1;
+    }
+    const bool need = idle && !exhausted;
+    const long long nq = fetch_work(need, P.work_counter);
+    if (need) {
+      if (nq < P.n) {
+        q = nq;
+        tf1 = load_pose(P.tf1, q);
+        tf2 = load_pose(P.tf2, q);
+        cm = mulTv(tf1.R, tf2.t - tf1.t);
+        cm_l1 = (fabs(cm.x) + fabs(cm.y)) + fabs(cm.z);
+        s.min_d = 1.7976931348623157e308;
+        s.best = -1;
+        s.bv_tests = s.leaf_tests = 0;
+        stk[0] = 0;  // the root, never bound-tested
+        stk_lb[0] = -3.0e38f;
+        sp = 1;
+        pend = 0;  // preprocess: seed with triangle 0
+      } else {
+        exhausted = true;
+      }
+    }
+    if (__all_sync(0xffffffffu, exhausted && sp == 0 && pend < 0)) break;
+
+    // box step
+    if (pend < 0 && sp > 0) {
+      --sp;
+      const int b = stk[sp];
+      if (!((double)stk_lb[sp] >= s.min_d)) {  // canStop(c)
+        const int fc = acc.first_child(b);
+        if (fc < 0) {
+          pend = -(fc + 1);
+          if (kStats) s.leaf_tests++;
+        } else if (sp + 2 > kStackCap) {
+          atomicMin(P.status, (int)FCLGPU_ERR_STACK_OVERFLOW);
+          sp = 0;
+        } else {
+          M3 ax;
+          V3 To;
+          double e0, e1, e2;
+          acc.box(fc, ax, To, e0, e1, e2);
+          const double d1 = sphere_box_lower_bound(ax, To, e0, e1, e2, cm, cm_l1, radius);
+          acc.box(fc + 1, ax, To, e0, e1, e2);
+          const double d2 = sphere_box_lower_bound(ax, To, e0, e1, e2, cm, cm_l1, radius);
+          if (kStats) s.bv_tests += 2;
+          const bool second_first = d2 < d1;  // nearer child on top
+          const int far_b = second_first ? fc : fc + 1, near_b = second_first ? fc + 1 : fc;
+          const double far_d = second_first ? d1 : d2, near_d = second_first ? d2 : d1;
+          if (far_d < s.min_d) {
+            stk[sp] = far_b;
+            stk_lb[sp] = float_below(far_d);
+            sp++;
+          }
+          if (near_d < s.min_d) {
+            stk[sp] = near_b;
+            stk_lb[sp] = float_below(near_d);
+            sp++;
+          }
+        }
+      }
+    }
+
+    // leaf round?
+    const unsigned parked = __ballot_sync(0xffffffffu, pend >= 0);
+    const unsigned movable = __ballot_sync(0xffffffffu, pend < 0 && (sp > 0 || !exhausted));
+    if (parked != 0 && (__popc(parked) >= leaf_trigger || movable == 0)) {
+      if (pend >= 0) {
+        mesh_sphere_leaf(acc, pend, tf1.R, tf1.t, tf2.t, radius, s);
+        pend = -1;
+      }
+    }
+  }
+}
+
 }  // namespace fclgpu

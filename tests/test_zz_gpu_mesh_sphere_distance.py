@@ -17,6 +17,16 @@ from fcl_b200.poses import identity_poses, random_poses
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[12, 0, 32, 1], ids=lambda v: "leaf_trigger=%d" % v, autouse=True)
+def leaf_trigger(request):
+    """Kernel variants: leaf rounds triggered by 12 (default) / 32 / 1 parked lanes, 0 = leaf tests inline."""
+    from fcl_b200 import _capi
+
+    _capi.set_option("sphere_leaf_trigger", request.param)
+    yield request.param
+    _capi.set_option("sphere_leaf_trigger", 12)
+
+
 def _check(got, brute, trav, radius):
     assert np.array_equal(got.min_distance, brute["min_distance"])  # bit-exact, -1 cases included
     pos = brute["min_distance"] > 0

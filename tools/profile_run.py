@@ -39,9 +39,16 @@ off = torch.empty(n + 1, dtype=torch.int64, device="cuda")
 for _ in range(a.launches):
     if a.workload == "distance":
         F.distance_batch_device(env, dP, rob, None, F.DistanceRequest(True), dist, p1, p2, b1, b2)
+    elif a.workload == "sphere_distance":  # sphere centres = the pose translations, radius 100
+        import ctypes as C
+        rq = F.DistanceRequest(True)._c()
+        rc = _capi.lib().fclgpu_distance_mesh_sphere_batch(env.device_model(0), 100.0, n, None, dP.data_ptr(), C.byref(rq), dist.data_ptr(),
+                                                           p1.data_ptr(), p2.data_ptr(), b1.data_ptr(), b2.data_ptr(), None, None,
+                                                           torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, rc
     elif a.workload == "collide":
         F.collide_batch_device(env, dP, rob, None, F.CollisionRequest(), cnt)
     else:
         F.collide_batch_device(env, dP, rob, None, F.CollisionRequest(100, True), cnt, con, off)
 F.sync_status()
-print("done", a.workload, n, float(dist.sum()) if a.workload == "distance" else int(cnt.sum()))
+print("done", a.workload, n, float(dist.sum()) if a.workload in ("distance", "sphere_distance") else int(cnt.sum()))
