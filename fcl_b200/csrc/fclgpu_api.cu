@@ -78,6 +78,7 @@ std::map<std::string, long long> g_opts = {
                                // warp-cooperative for nodes > 24, 1 = warp-cooperative only, 0 = one thread per node
     {"pool_trigger", 32},      // collide variant P: queued pairs in the warp that trigger a pooled leaf round
     {"leaf_trigger", 20},      // collide variant D: lanes with queued triangle pairs that trigger a leaf round
+    {"sphere_bound32", 1},        // mesh <-> sphere distance: box bound from the 64-byte FP32 records (0 = FP64 records)
     {"sphere_leaf_trigger", 12},  // mesh <-> sphere distance: parked lanes that trigger a leaf round (0 = leaf tests inline)
 };
 long long opt(const char* k) {
@@ -950,9 +951,10 @@ int distance_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, 
   const bool stats = (n_bv || n_leaf);
   if (sphere_radius >= 0) {
     const int trig = (int)opt("sphere_leaf_trigger");
+    const int b32 = (int)opt("sphere_bound32");
     if (trig > 0)
-      return stats ? launch_persistent(distance_mesh_sphere_rounds_kernel<true>, P, w, 128, st, 0, sphere_radius, trig)
-                   : launch_persistent(distance_mesh_sphere_rounds_kernel<false>, P, w, 128, st, 0, sphere_radius, trig);
+      return stats ? launch_persistent(distance_mesh_sphere_rounds_kernel<true>, P, w, 128, st, 0, sphere_radius, trig, b32)
+                   : launch_persistent(distance_mesh_sphere_rounds_kernel<false>, P, w, 128, st, 0, sphere_radius, trig, b32);
     return stats ? launch_persistent(distance_mesh_sphere_kernel<true>, P, w, 128, st, 0, sphere_radius)
                  : launch_persistent(distance_mesh_sphere_kernel<false>, P, w, 128, st, 0, sphere_radius);
   }

@@ -10,6 +10,7 @@
 #pragma once
 #include <cstdint>
 
+#include "bounds_f32.cuh"
 #include "device_math.cuh"
 
 namespace fclgpu {
@@ -41,6 +42,44 @@ FD double sphere_box_lower_bound(const M3& axis, const V3& To, double e0, double
   const double scale = (((fabs(To.x) + fabs(To.y)) + fabs(To.z)) + ((e0 + e1) + e2)) + cm_l1;
   const float g = sqrtf(float_below((ex * ex + ey * ey) + ez * ez));
   return ((double)g * 0.9999998 - radius) - 1e-9 * scale;
+}
+
+// The same bound from the 64-byte single-precision OBB record (half the bytes per box test; the kernel is bound by
+// the L1 data pipe, profiles/r01_ncu_sphere_distance.txt).  u = 2^-24, M = |c|_1 + |e|_1 + |cm|_1 (rounded up):
+// inputs rounded once (<= uM each), centre difference <= 3uM, box-frame coordinates <= 25uM, per-axis excess <= 27uM
+// (extents are stored rounded up), gap <= 47uM + 6uM for the squares and the square root.  Slack used: 128uM.
+struct SphereCentre32 {
+  float c[3];      // centre in the mesh frame
+  float l1;        // |c|_1 rounded up
+  float radius;    // rounded up
+};
+FD float float_above(double x) {
+#ifdef __CUDA_ARCH__
+  return __double2float_ru(x);
+#else
+  float f = (float)x;
+  if ((double)f < x) f = nextafterf(f, 3.0e38f);
+  return f;
+#endif
+}
+FD SphereCentre32 make_centre32(const V3& cm, double cm_l1, double radius) {
+  SphereCentre32 q;
+  q.c[0] = (float)cm.x;
+  q.c[1] = (float)cm.y;
+  q.c[2] = (float)cm.z;
+  q.l1 = float_above(cm_l1);
+  q.radius = float_above(radius);
+  return q;
+}
+FD float sphere_box_lower_bound_f32(const ObbRec32& n, const SphereCentre32& q) {
+  const float dx = q.c[0] - n.c[0], dy = q.c[1] - n.c[1], dz = q.c[2] - n.c[2];
+  const float lx = (n.a[0] * dx + n.a[3] * dy) + n.a[6] * dz;
+  const float ly = (n.a[1] * dx + n.a[4] * dy) + n.a[7] * dz;
+  const float lz = (n.a[2] * dx + n.a[5] * dy) + n.a[8] * dz;
+  const float ex = fmaxf(fabsf(lx) - n.e[0], 0.0f), ey = fmaxf(fabsf(ly) - n.e[1], 0.0f), ez = fmaxf(fabsf(lz) - n.e[2], 0.0f);
+  const float g = sqrtf((ex * ex + ey * ey) + ez * ez);
+  const float M = n.s + q.l1;
+  return (g * 0.9999995f - q.radius) - 7.62939453125e-6f * M * 1.000001f;
 }
 
 struct MeshSphereDistance {
@@ -84,9 +123,10 @@ FD void mesh_sphere_leaf(const Acc& acc, int id, const M3& R1, const V3& t1, con
 #pragma nv_exec_check_disable
 template <class Acc>
 FD void mesh_sphere_distance_query(const Acc& acc, const M3& R1, const V3& t1, const V3& c, double radius, int* stk,
-                                   float* stk_lb, int cap, MeshSphereDistance& s) {
+                                   float* stk_lb, int cap, MeshSphereDistance& s, bool bound32 = false) {
   const V3 cm = mulTv(R1, c - t1);  // centre in the mesh frame (bounds only)
   const double cm_l1 = (fabs(cm.x) + fabs(cm.y)) + fabs(cm.z);
+  const SphereCentre32 q32 = make_centre32(cm, cm_l1, radius);
   s.min_d = 1.7976931348623157e308;
   s.best = -1;
   s.on_tri = s.on_sph = mk(0, 0, 0);
@@ -108,13 +148,22 @@ FD void mesh_sphere_distance_query(const Acc& acc, const M3& R1, const V3& t1, c
       mesh_sphere_leaf(acc, -(fc + 1), R1, t1, c, radius, s);
       continue;
     }
-    M3 ax;
-    V3 To;
-    double e0, e1, e2;
-    acc.box(fc, ax, To, e0, e1, e2);
-    const double d1 = sphere_box_lower_bound(ax, To, e0, e1, e2, cm, cm_l1, radius);
-    acc.box(fc + 1, ax, To, e0, e1, e2);
-    const double d2 = sphere_box_lower_bound(ax, To, e0, e1, e2, cm, cm_l1, radius);
+    double d1, d2;
+    if (bound32) {
+      ObbRec32 n;
+      acc.box32(fc, n);
+      d1 = (double)sphere_box_lower_bound_f32(n, q32);
+      acc.box32(fc + 1, n);
+      d2 = (double)sphere_box_lower_bound_f32(n, q32);
+    } else {
+      M3 ax;
+      V3 To;
+      double e0, e1, e2;
+      acc.box(fc, ax, To, e0, e1, e2);
+      d1 = sphere_box_lower_bound(ax, To, e0, e1, e2, cm, cm_l1, radius);
+      acc.box(fc + 1, ax, To, e0, e1, e2);
+      d2 = sphere_box_lower_bound(ax, To, e0, e1, e2, cm, cm_l1, radius);
+    }
     s.bv_tests += 2;
     if (sp + 2 > cap) {
       s.overflow = true;

@@ -1740,6 +1740,7 @@ struct DeviceMeshAccessor {
     e1 = nd.e1;
     e2 = nd.e2;
   }
+  __device__ __forceinline__ void box32(int b, ObbRec32& n) const { n = load_obb32(m.obb32, b); }
   __device__ __forceinline__ void tri(int id, V3 T[3]) const { load_tri(m.tri, id, T); }
 };
 
@@ -1794,7 +1795,8 @@ __global__ void __launch_bounds__(128) distance_mesh_sphere_kernel(DistanceParam
 // the minimum over the triangles does not depend on it.
 // ---------------------------------------------------------------------------------------
 template <bool kStats>
-__global__ void __launch_bounds__(128) distance_mesh_sphere_rounds_kernel(DistanceParams P, double radius, int leaf_trigger) {
+__global__ void __launch_bounds__(128) distance_mesh_sphere_rounds_kernel(DistanceParams P, double radius, int leaf_trigger,
+                                                                          int bound32) {
   int stk[kStackCap];
   float stk_lb[kStackCap];
   const DeviceMeshAccessor acc{P.m1};
@@ -1804,6 +1806,7 @@ __global__ void __launch_bounds__(128) distance_mesh_sphere_rounds_kernel(Distan
   PoseRT tf1, tf2;
   V3 cm = mk(0, 0, 0);
   double cm_l1 = 0;
+  SphereCentre32 q32 = make_centre32(cm, 0.0, radius);
   MeshSphereDistance s;
   s.min_d = 0;
   s.best = -1;
@@ -1843,6 +1846,7 @@ __global__ void __launch_bounds__(128) distance_mesh_sphere_rounds_kernel(Distan
         tf2 = load_pose(P.tf2, q);
         cm = mulTv(tf1.R, tf2.t - tf1.t);
         cm_l1 = (fabs(cm.x) + fabs(cm.y)) + fabs(cm.z);
+        q32 = make_centre32(cm, cm_l1, radius);
         s.min_d = 1.7976931348623157e308;
         s.best = -1;
         s.bv_tests = s.leaf_tests = 0;
@@ -1869,13 +1873,22 @@ __global__ void __launch_bounds__(128) distance_mesh_sphere_rounds_kernel(Distan
           atomicMin(P.status, (int)FCLGPU_ERR_STACK_OVERFLOW);
           sp = 0;
         } else {
-          M3 ax;
-          V3 To;
-          double e0, e1, e2;
-          acc.box(fc, ax, To, e0, e1, e2);
-          const double d1 = sphere_box_lower_bound(ax, To, e0, e1, e2, cm, cm_l1, radius);
-          acc.box(fc + 1, ax, To, e0, e1, e2);
-          const double d2 = sphere_box_lower_bound(ax, To, e0, e1, e2, cm, cm_l1, radius);
+          double d1, d2;
+          if (bound32) {
+            ObbRec32 n;
+            acc.box32(fc, n);
+            d1 = (double)sphere_box_lower_bound_f32(n, q32);
+            acc.box32(fc + 1, n);
+            d2 = (double)sphere_box_lower_bound_f32(n, q32);
+          } else {
+            M3 ax;
+            V3 To;
+            double e0, e1, e2;
+            acc.box(fc, ax, To, e0, e1, e2);
+            d1 = sphere_box_lower_bound(ax, To, e0, e1, e2, cm, cm_l1, radius);
+            acc.box(fc + 1, ax, To, e0, e1, e2);
+            d2 = sphere_box_lower_bound(ax, To, e0, e1, e2, cm, cm_l1, radius);
+          }
           if (kStats) s.bv_tests += 2;
           const bool second_first = d2 < d1;  // nearer child on top
           const int far_b = second_first ? fc : fc + 1, near_b = second_first ? fc + 1 : fc;

@@ -46,7 +46,7 @@ def lib():
         L.hm_sphere_tri_distance.argtypes = [dp, C.c_double, dp, dp]
         L.hm_mesh_sphere_distance.restype = C.c_int
         L.hm_mesh_sphere_distance.argtypes = [C.c_longlong, dp, dp, C.c_double, ip, dp, dp, dp, dp, dp, dp, dp, ip,
-                                              C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+                                              C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int]
         L.hm_obb_disjoint32_pairs.argtypes = [C.c_longlong, dp, ip, ip, dp, dp, dp, dp, dp, dp, ip]
         L.hm_tri_classify32.restype = C.c_int
         L.hm_tri_classify32.argtypes = [dp, dp, dp]

@@ -96,13 +96,14 @@ struct HostMeshAccessor {
     e1 = ext[3 * b + 1];
     e2 = ext[3 * b + 2];
   }
+  void box32(int b, ObbRec32& n) const { pack_obb32(axis + 9 * b, To + 3 * b, ext + 3 * b, n); }  // as the upload step packs it
   void tri(int id, V3 T[3]) const {
     for (int k = 0; k < 3; ++k) T[k] = v3(tri9 + 9 * id + 3 * k);
   }
 };
 int hm_mesh_sphere_distance(long long n, const double* tf1, const double* tf2, double radius, const int* first_child,
                             const double* axis, const double* obb_To, const double* obb_ext, const double* tri9,
-                            double* dist, double* p1, double* p2, int* b1, unsigned* n_bv, unsigned* n_leaf) {
+                            double* dist, double* p1, double* p2, int* b1, unsigned* n_bv, unsigned* n_leaf, int bound32) {
   const HostMeshAccessor acc{first_child, axis, obb_To, obb_ext, tri9};
   int stk[128];
   float lb[128];
@@ -111,7 +112,7 @@ int hm_mesh_sphere_distance(long long n, const double* tf1, const double* tf2, d
     const M3 R1 = m3(tf1 + 12 * q), R2 = m3(tf2 + 12 * q);
     const V3 t1 = v3(tf1 + 12 * q + 9), t2 = v3(tf2 + 12 * q + 9);
     MeshSphereDistance s;
-    mesh_sphere_distance_query(acc, R1, t1, t2, radius, stk, lb, 128, s);
+    mesh_sphere_distance_query(acc, R1, t1, t2, radius, stk, lb, 128, s, bound32 != 0);
     overflow |= s.overflow;
     dist[q] = s.min_d;
     b1[q] = s.best;

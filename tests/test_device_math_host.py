@@ -184,7 +184,7 @@ def test_sphere_triangle_routines_match_oracle(hm, oracle):
     assert 0.05 * n < hits < 0.95 * n and 0.05 * n < seps < 0.95 * n
 
 
-def _host_mesh_sphere(hm, model, verts, tris, radius, M, S):
+def _host_mesh_sphere(hm, model, verts, tris, radius, M, S, bound32=False):
     a = model.arrays()
     tri9 = np.ascontiguousarray(np.asarray(verts, np.float64)[np.asarray(tris)].reshape(-1, 9))
     n = len(S)
@@ -194,7 +194,7 @@ def _host_mesh_sphere(hm, model, verts, tris, radius, M, S):
     ov = hm.lib().hm_mesh_sphere_distance(n, hm.dptr(M), hm.dptr(S), float(radius), hm.iptr(a["first_child"]), hm.dptr(a["axis"]),
                                           hm.dptr(a["obb_To"]), hm.dptr(a["obb_ext"]), hm.dptr(tri9), hm.dptr(dist), hm.dptr(p1),
                                           hm.dptr(p2), hm.iptr(b1), n_bv.ctypes.data_as(C.POINTER(C.c_uint32)),
-                                          n_leaf.ctypes.data_as(C.POINTER(C.c_uint32)))
+                                          n_leaf.ctypes.data_as(C.POINTER(C.c_uint32)), int(bound32))
     assert ov == 0
     return dict(min_distance=dist, p1=p1, p2=p2, b1=b1, n_bv=n_bv, n_leaf=n_leaf)
 
@@ -223,8 +223,8 @@ def test_mesh_sphere_distance_traversal_matches_oracle(hm, oracle, env_rob_npz):
     cases.append((hv, ht, (0.05, 0.3), identity_poses(3000), Sh))
     for v, t, radii, M, S in cases:
         o = oracle.Model(v, t)
-        for radius in radii:
-            got = _host_mesh_sphere(hm, o, v, t, radius, M, S)
+        for radius, bound32 in [(r, b) for r in radii for b in (False, True)]:
+            got = _host_mesh_sphere(hm, o, v, t, radius, M, S, bound32)
             brute = oracle.distance_mesh_sphere_batch(o, radius, M, S, brute=True, nthreads=8)
             trav = oracle.distance_mesh_sphere_batch(o, radius, M, S, nthreads=8)
             assert np.array_equal(got["min_distance"], brute["min_distance"]), radius

@@ -35,7 +35,8 @@ while time.time() < t_end:
     M = random_poses(n, seed=int(rng.integers(1 << 30)), extents=(-ext, -ext, -ext, ext, ext, ext)) if rng.integers(0, 2) else identity_poses(n)
     S = random_poses(n, seed=int(rng.integers(1 << 30)), extents=(-ext, -ext, -ext, ext, ext, ext))
     r = float(rng.choice([0.0, rng.uniform(0.01, 2.0)])) * unit
-    got = _host_mesh_sphere(hm, o, v, t, r, M, S)
+    b32 = bool(rng.integers(0, 2))  # box bound from the FP64 records or from the packed FP32 records
+    got = _host_mesh_sphere(hm, o, v, t, r, M, S, b32)
     brute = O.distance_mesh_sphere_batch(o, r, M, S, brute=True, nthreads=8)
     trav = O.distance_mesh_sphere_batch(o, r, M, S, nthreads=8)
     pos = brute["min_distance"] > 0
@@ -48,6 +49,6 @@ while time.time() < t_end:
     rounds += 1
     checks += n
     if not ok:
-        print("MISMATCH", dict(kind=int(kind), nt=len(t), unit=unit, split=split, n=n, ext=ext, r=r))
+        print("MISMATCH", dict(kind=int(kind), nt=len(t), unit=unit, split=split, n=n, ext=ext, r=r, b32=b32))
         sys.exit(1)
 print("mesh-sphere distance host stress OK: %d random configurations, %d queries; reference-order traversal differing from the all-triangles minimum in the last bits: %d" % (rounds, checks, ties))
