@@ -79,7 +79,7 @@ std::map<std::string, long long> g_opts = {
     {"pool_trigger", 32},      // collide variant P: queued pairs in the warp that trigger a pooled leaf round
     {"leaf_trigger", 20},      // collide variant D: lanes with queued triangle pairs that trigger a leaf round
     {"sphere_bound32", 1},        // mesh <-> sphere distance: box bound from the 64-byte FP32 records (0 = FP64 records)
-    {"sphere_leaf_trigger", 12},  // mesh <-> sphere distance: parked lanes that trigger a leaf round (0 = leaf tests inline)
+    {"sphere_leaf_trigger", 16},  // mesh <-> sphere distance: parked lanes that trigger a leaf round (0 = leaf tests inline)
 };
 long long opt(const char* k) {
   std::lock_guard<std::mutex> g(g_opt_mu);

@@ -17,16 +17,16 @@ from fcl_b200.poses import identity_poses, random_poses
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[(12, 1), (12, 0), (0, 0), (32, 1), (1, 1)], ids=lambda v: "leaf_trigger=%d,bound32=%d" % v, autouse=True)
+@pytest.fixture(params=[(16, 1), (16, 0), (0, 0), (32, 1), (1, 1)], ids=lambda v: "leaf_trigger=%d,bound32=%d" % v, autouse=True)
 def kernel_variant(request):
-    """Kernel variants: leaf rounds triggered by 12 (default) / 32 / 1 parked lanes, 0 = leaf tests inline; box bound
+    """Kernel variants: leaf rounds triggered by 16 (default) / 32 / 1 parked lanes, 0 = leaf tests inline; box bound
     from the packed FP32 records (default) or from the FP64 records."""
     from fcl_b200 import _capi
 
     _capi.set_option("sphere_leaf_trigger", request.param[0])
     _capi.set_option("sphere_bound32", request.param[1])
     yield request.param
-    _capi.set_option("sphere_leaf_trigger", 12)
+    _capi.set_option("sphere_leaf_trigger", 16)
     _capi.set_option("sphere_bound32", 1)
 
 

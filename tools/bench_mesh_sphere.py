@@ -84,7 +84,7 @@ line = {
     "steps": a.steps, "warmup": a.warmup, "ms_per_step": k_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
     "dtype": "f64", "data": "synthetic",
     "config": {"workload": "env.obj (2180 tris) at identity vs Sphere(r=%g) at %d random centres (seed-1 pose translations), distance() with nearest points" % (a.radius, n),
-               "l2_flush_between_steps": True, "sphere_leaf_trigger": _capi.get_option("sphere_leaf_trigger")},
+               "l2_flush_between_steps": True, "sphere_leaf_trigger": _capi.get_option("sphere_leaf_trigger"), "sphere_bound32": _capi.get_option("sphere_bound32")},
     "clocks": clocks,
     "e2e": {"value": n * a.steps / dt, "unit": "queries/s", "h2d_bytes_per_step": 96 * n, "d2h_bytes_per_step": n * (8 + 24 + 24 + 4 + 4)},
     "gpu_launches": launches,

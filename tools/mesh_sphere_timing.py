@@ -39,7 +39,7 @@ b1 = torch.empty(n, dtype=torch.int32, device="cuda")
 nbv = torch.empty(n, dtype=torch.int32, device="cuda")
 nlf = torch.empty(n, dtype=torch.int32, device="cuda")
 dq = F.DistanceRequest(True)._c()
-for trig, b32, radius in [(t, b, r) for (t, b) in ((12, 1), (12, 0), (16, 1), (8, 1), (0, 0)) for r in (10.0, 100.0, 350.0)]:
+for trig, b32, radius in [(t, b, r) for (t, b) in ((16, 1), (16, 0), (0, 0)) for r in (10.0, 100.0, 350.0)]:
     _capi.set_option("sphere_leaf_trigger", trig)
     _capi.set_option("sphere_bound32", b32)
     def run_d(stats=False):
@@ -57,5 +57,5 @@ for trig, b32, radius in [(t, b, r) for (t, b) in ((12, 1), (12, 0), (16, 1), (8
     F.sync_status()
     print("sphere r=%-5g leaf_trigger=%-2d bound32=%d distance+points %.2f ms per 1M queries  %.3g q/s  (separated %.0f %%, box tests/query %.1f, triangle tests/query %.1f)" % (
         radius, trig, b32, ms, n / ms * 1e3, 100.0 * (dist > 0).float().mean().item(), nbv.float().mean().item(), nlf.float().mean().item()))
-_capi.set_option("sphere_leaf_trigger", 12)
+_capi.set_option("sphere_leaf_trigger", 16)
 _capi.set_option("sphere_bound32", 1)

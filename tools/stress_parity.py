@@ -101,7 +101,7 @@ while time.time() < t_end:
     gs = F.collide_mesh_sphere_batch(m1, P1, F.Sphere(r), S, F.CollisionRequest(mx, True), contact_capacity=max(64 * n, 1024), grow_on_overflow=True)
     ok = ok and np.array_equal(gs.num_contacts, rs["counts"]) and gs.contacts.tobytes() == rs["contacts"].tobytes()
     # mesh <-> sphere distance: bit-exact against the oracle's pass over all triangles, within tie rounding of its traversal
-    _capi.set_option("sphere_leaf_trigger", int(rng.choice([0, 1, 12, 12, 32])))
+    _capi.set_option("sphere_leaf_trigger", int(rng.choice([0, 1, 16, 16, 32])))
     _capi.set_option("sphere_bound32", int(rng.integers(0, 2)))
     bs = O.distance_mesh_sphere_batch(o1, r, P1, S, brute=len(t1) * n <= 40_000_000, nthreads=8)
     ds = F.distance_mesh_sphere_batch(m1, P1, F.Sphere(r), S, F.DistanceRequest(True), pinned=pinned)
@@ -123,6 +123,6 @@ _capi.set_option("traversal", 3)
 _capi.set_option("collide_front", 1)
 _capi.set_option("scratch_bytes", 2 << 30)
 _capi.set_option("host_chunk", 1 << 17)
-_capi.set_option("sphere_leaf_trigger", 12)
+_capi.set_option("sphere_leaf_trigger", 16)
 _capi.set_option("sphere_bound32", 1)
 print("stress parity OK: %d random configurations, %d query comparisons; front-traversal distances differing from the oracle in the last bits: %d of %d" % (rounds, checks, ulp_diffs, dist_checks))
