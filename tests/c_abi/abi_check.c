@@ -40,8 +40,27 @@ int main(void) {
     int32_t n = -1;
     rc = fclgpu_collide_batch_host(m, m, 1, tf, NULL, &req, &n, NULL, 0, NULL, NULL, NULL);
     if (rc != FCLGPU_OK || n != 1) { printf("collide failed rc=%d n=%d\n", rc, n); return 1; }
+    /* mesh <-> sphere: a unit-radius sphere 3 away from the box centre along x is 1 away from the face x = 1 */
+    fclgpu_distance_request dreq = {1, 0, 0.0, 0.0};
+    double stf[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 3.0, 0.25, -0.5}, d = 0, p1[3], p2[3];
+    int32_t b1 = -5, b2 = -5;
+    rc = fclgpu_distance_mesh_sphere_batch_host(m, 1.0, 1, NULL, stf, &dreq, &d, p1, p2, &b1, &b2, NULL, NULL);
+    if (rc != FCLGPU_OK || d != 1.0 || b2 != -1 || b1 != 8 || p1[0] != 1.0 || p1[2] != -0.5 || p2[0] != -1.0) {
+      printf("sphere distance failed rc=%d d=%.17g b1=%d b2=%d p1x=%g p2x=%g\n", rc, d, b1, b2, p1[0], p2[0]);
+      return 1;
+    }
     fclgpu_model_destroy(m);
     printf("device run ok\n");
+  }
+  /* argument checks need no device */
+  {
+    fclgpu_distance_request dreq = {1, 0, 0.0, 0.0};
+    double d;
+    if (fclgpu_distance_mesh_sphere_batch_host(NULL, 1.0, 1, NULL, NULL, &dreq, &d, NULL, NULL, NULL, NULL, NULL, NULL) != FCLGPU_ERR_INVALID_ARGUMENT ||
+        fclgpu_distance_mesh_sphere_batch(NULL, -1.0, 1, NULL, NULL, &dreq, &d, NULL, NULL, NULL, NULL, NULL, NULL, NULL) != FCLGPU_ERR_INVALID_ARGUMENT) {
+      printf("sphere distance argument checks\n");
+      return 1;
+    }
   }
   fclgpu_bvh_destroy(bvh);
   printf("abi_check ok\n");
