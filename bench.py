@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — batched OBBRSS mesh-mesh queries/second on B200 (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--workload distance|collide|contacts]
+    python bench.py --gpus N --steps K --warmup W [--workload distance|collide|contacts|sphere_distance]
     python bench.py --impl reference ...     # the CPU oracle (the only CPU FCL buildable here)
 
 A step = one pass of the hot path over one batch of synthetic poses (env.obj vs rob.obj).
@@ -28,7 +28,10 @@ WORKLOADS = {
     "distance": "cfg2: env.obj vs rob.obj distance() with nearest points, 1M random poses per GPU, double",
     "collide": "cfg1-style: env.obj vs rob.obj collide() binary verdict (CollisionRequest()), 1M random poses per GPU",
     "contacts": "cfg3: env.obj vs rob.obj collide() enable_contact, num_max_contacts=100, 1M random poses per GPU",
+    # SURVEY 8f rank 2 (the row next to the path), single GPU: see run_sphere_distance()
+    "sphere_distance": "env.obj at identity vs Sphere(r=100) at the seed-1 pose translations, distance() with nearest points, 1M queries",
 }
+SPHERE_RADIUS = 100.0
 
 
 def load_meshes():
@@ -120,7 +123,12 @@ def run_reference(args, rank, world):
     sample = args.cpu_sample
     P = random_poses(sample, seed=1)
 
+    ident = np.zeros((sample, 12))
+    ident[:, 0] = ident[:, 4] = ident[:, 8] = 1.0
+
     def step():
+        if args.workload == "sphere_distance":
+            return O.distance_mesh_sphere_batch(env, SPHERE_RADIUS, ident, P, nthreads=threads)["seconds"]
         if args.workload == "distance":
             return O.distance_batch(env, rob, P, None, True, 2, nthreads=threads)["seconds"]
         if args.workload == "collide":
@@ -185,6 +193,111 @@ def ensure_built(local_rank):
         raise SystemExit("libfclgpu.so was not built")
 
 
+def run_sphere_distance(args, local):
+    """--workload sphere_distance (single GPU): the row next to the path, SURVEY 8f rank 2.  value = kernel throughput with
+    the inputs resident in HBM; e2e = through fclgpu_distance_mesh_sphere_batch_host with pinned host buffers; roofline from
+    the REFERENCE traversal's counters (the oracle's n_bv / n_leaf on the CPU sample, SURVEY 8d accounting: 2 poses + 120 B
+    per node test + 72 B per triangle test + 64 B out); cpu_baseline = the oracle on the host cores."""
+    import ctypes as C
+
+    import torch
+
+    import fcl_b200 as F
+    from fcl_b200 import _capi
+
+    (ev, et), _ = load_meshes()
+    env = F.BVHModel.from_arrays(ev, et)
+    n = args.poses
+    S = F.random_poses(n, seed=1)
+    hS = torch.from_numpy(S).pin_memory()
+    dS = hS.cuda()
+    dist_d = torch.empty(n, dtype=torch.float64, device="cuda")
+    p1 = torch.empty(n, 3, dtype=torch.float64, device="cuda")
+    p2 = torch.empty(n, 3, dtype=torch.float64, device="cuda")
+    b1 = torch.empty(n, dtype=torch.int32, device="cuda")
+    rq = F.DistanceRequest(True)._c()
+    L = _capi.lib()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def kernel():
+        rc = L.fclgpu_distance_mesh_sphere_batch(env.device_model(local), SPHERE_RADIUS, n, None, dS.data_ptr(), C.byref(rq),
+                                                 dist_d.data_ptr(), p1.data_ptr(), p2.data_ptr(), b1.data_ptr(), None, None, None,
+                                                 torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, rc
+
+    for _ in range(args.warmup):
+        kernel()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = _capi.launch_count()
+    ms = 0.0
+    for _ in range(args.steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        kernel()
+        e1.record()
+        e1.synchronize()
+        ms += e0.elapsed_time(e1)
+    launches = _capi.launch_count() - launches0
+    clocks = sampler.stop()
+    F.sync_status(local)
+    k_ms = ms / args.steps
+    sphere = F.Sphere(SPHERE_RADIUS)
+    hs = hS.numpy()
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            F.distance_mesh_sphere_batch(env, None, sphere, hs, F.DistanceRequest(True), pinned=True)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            F.distance_mesh_sphere_batch(env, None, sphere, hs, F.DistanceRequest(True), pinned=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {"value": n * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": 96 * n, "d2h_bytes_per_step": n * (8 + 24 + 24 + 4 + 4)}
+    from oracle import pyoracle as O  # checker and CPU baseline only
+
+    O.build()
+    s = min(args.cpu_sample, n)
+    oenv = O.Model(ev, et)
+    threads = O.hardware_threads()
+    ident = F.identity_poses(s)
+    ref = O.distance_mesh_sphere_batch(oenv, SPHERE_RADIUS, ident, S[:s], nthreads=threads)
+    brute = O.distance_mesh_sphere_batch(oenv, SPHERE_RADIUS, ident, S[:s], brute=True, nthreads=threads)
+    got = dist_d.cpu().numpy()[:s]
+    per_query = 2 * 96 + ref["n_bv"].astype(np.float64) * 120 + ref["n_leaf"].astype(np.float64) * 72 + 64
+    alg = float(per_query.mean()) * n
+    peak, which = measured_peaks()
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f).get("sphere_distance")
+        if t and t["poses"] == n:
+            traffic = t["dram_bytes_per_launch"] * t["launches_per_step"]
+            traffic_src = "profiles/r01_traffic.json (%s, %d launch(es) per step)" % (t["kernel"], t["launches_per_step"])
+    except Exception:  # pragma: no cover
+        pass
+    achieved = alg / (k_ms * 1e-3) / 1e9
+    emit({
+        "metric": METRIC, "value": n / (k_ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": k_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS["sphere_distance"], "poses_per_gpu": n, "pose_seed": 1, "l2_flush_between_steps": True,
+                   "sphere_leaf_trigger": _capi.get_option("sphere_leaf_trigger"), "sphere_bound32": _capi.get_option("sphere_bound32"),
+                   "multi_gpu": "single GPU"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "traffic_source": traffic_src, "peak_source": which, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg,
+                     "mean_n_bv": float(ref["n_bv"].mean()), "mean_n_leaf": float(ref["n_leaf"].mean()),
+                     "note": "counters of the reference's traversal from the oracle on the CPU sample, scaled to the batch; records are "
+                             "L1/L2 resident, the binding resource is the L1 data pipe (profiles/r01_ncu_sphere_distance.txt)"},
+        "cpu_baseline": {"value": s / ref["seconds"], "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"first {s} queries of the batch, {threads} host threads, one pass",
+                         "matches_gpu": bool(np.array_equal(got, brute["min_distance"])),
+                         "matches_gpu_traversal_1e-12": bool(np.all(np.abs(got - ref["min_distance"]) <= 1e-12 * np.abs(ref["min_distance"])))},
+    })
+
+
 def main():
     quiet_stdout()
     ap = argparse.ArgumentParser()
@@ -230,6 +343,12 @@ def main():
     for kv in args.opt:
         k, v = kv.split("=")
         _capi.set_option(k, int(v))
+
+    if args.workload == "sphere_distance":
+        if world > 1:
+            raise SystemExit("--workload sphere_distance is a single-GPU line (run it without torchrun)")
+        run_sphere_distance(args, local)
+        return
 
     (ev, et), (rv, rt) = load_meshes()
     env, rob = F.BVHModel.from_arrays(ev, et), F.BVHModel.from_arrays(rv, rt)

@@ -1,7 +1,7 @@
 """Randomised differential run of the mesh <-> sphere distance traversal (csrc/mesh_sphere.cuh, host build of the very
-code the kernel inlines) against the oracle, no GPU needed:  python tools/stress_mesh_sphere_host.py [seconds] [seed]"""
+code the kernel inlines) against the oracle, no GPU needed:  python tests/stress/stress_mesh_sphere_host.py [seconds] [seed]"""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from fcl_b200.poses import random_poses, identity_poses
 from oracle import pyoracle as O

@@ -1,7 +1,7 @@
 """Randomised differential test GPU vs oracle over many mesh pairs / pose distributions / requests (GPU box only).
-    python tools/stress_parity.py [seconds] [seed]     -- exits non-zero on the first mismatch"""
+    python tests/stress/stress_parity.py [seconds] [seed]     -- exits non-zero on the first mismatch"""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import fcl_b200 as F
 from fcl_b200 import _capi

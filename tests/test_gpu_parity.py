@@ -573,7 +573,7 @@ def test_mesh_sphere_on_a_large_mesh(oracle):
 
 
 def test_distance_front_survives_unprunable_fronts(oracle):
-    """Regression (found by tools/stress_parity.py): a 2,048-triangle heightfield against a 384-triangle sphere, both
+    """Regression (found by tests/stress/stress_parity.py): a 2,048-triangle heightfield against a 384-triangle sphere, both
     built with the BV-centre split, under poses for which the sorted front of the FP64-bound variant outgrew its
     512-entry shared-memory stack and reported FCLGPU_ERR_STACK_OVERFLOW.  Near the limit the warp now degrades to
     nearest-first depth first.  tests/golden/front_overflow.npz holds the meshes and 32 poses (8 of them overflowed)."""
