@@ -78,6 +78,7 @@ std::map<std::string, long long> g_opts = {
                                // warp-cooperative for nodes > 24, 1 = warp-cooperative only, 0 = one thread per node
     {"pool_trigger", 32},      // collide variant P: queued pairs in the warp that trigger a pooled leaf round
     {"leaf_trigger", 20},      // collide variant D: lanes with queued triangle pairs that trigger a leaf round
+    {"sphere_blocks", 4},         // mesh <-> sphere distance: resident blocks per SM the kernel is compiled for (3, 4, 5)
     {"sphere_bound32", 1},        // mesh <-> sphere distance: box bound from the 64-byte FP32 records (0 = FP64 records)
     {"sphere_leaf_trigger", 16},  // mesh <-> sphere distance: parked lanes that trigger a leaf round (0 = leaf tests inline)
 };
@@ -952,9 +953,13 @@ int distance_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, 
   if (sphere_radius >= 0) {
     const int trig = (int)opt("sphere_leaf_trigger");
     const int b32 = (int)opt("sphere_bound32");
-    if (trig > 0)
-      return stats ? launch_persistent(distance_mesh_sphere_rounds_kernel<true>, P, w, 128, st, 0, sphere_radius, trig, b32)
-                   : launch_persistent(distance_mesh_sphere_rounds_kernel<false>, P, w, 128, st, 0, sphere_radius, trig, b32);
+    if (trig > 0) {
+      const long long occ = opt("sphere_blocks");  // register budget of the kernel: 3, 4 or 5 resident blocks per SM
+      if (stats) return launch_persistent(distance_mesh_sphere_rounds_kernel<true, 3>, P, w, 128, st, 0, sphere_radius, trig, b32);
+      if (occ >= 5) return launch_persistent(distance_mesh_sphere_rounds_kernel<false, 5>, P, w, 128, st, 0, sphere_radius, trig, b32);
+      if (occ == 4) return launch_persistent(distance_mesh_sphere_rounds_kernel<false, 4>, P, w, 128, st, 0, sphere_radius, trig, b32);
+      return launch_persistent(distance_mesh_sphere_rounds_kernel<false, 3>, P, w, 128, st, 0, sphere_radius, trig, b32);
+    }
     return stats ? launch_persistent(distance_mesh_sphere_kernel<true>, P, w, 128, st, 0, sphere_radius)
                  : launch_persistent(distance_mesh_sphere_kernel<false>, P, w, 128, st, 0, sphere_radius);
   }

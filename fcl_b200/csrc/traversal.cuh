@@ -1794,9 +1794,9 @@ __global__ void __launch_bounds__(128) distance_mesh_sphere_kernel(DistanceParam
 // Bound, leaf and result arithmetic are the shared routines of mesh_sphere.cuh; only the interleaving differs, and
 // the minimum over the triangles does not depend on it.
 // ---------------------------------------------------------------------------------------
-template <bool kStats>
-__global__ void __launch_bounds__(128) distance_mesh_sphere_rounds_kernel(DistanceParams P, double radius, int leaf_trigger,
-                                                                          int bound32) {
+template <bool kStats, int kMinBlocks>
+__global__ void __launch_bounds__(128, kMinBlocks) distance_mesh_sphere_rounds_kernel(DistanceParams P, double radius,
+                                                                                      int leaf_trigger, int bound32) {
   int stk[kStackCap];
   float stk_lb[kStackCap];
   const DeviceMeshAccessor acc{P.m1};

@@ -17,17 +17,20 @@ from fcl_b200.poses import identity_poses, random_poses
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[(16, 1), (16, 0), (0, 0), (32, 1), (1, 1)], ids=lambda v: "leaf_trigger=%d,bound32=%d" % v, autouse=True)
+@pytest.fixture(params=[(16, 1, 3), (16, 0, 3), (0, 0, 3), (32, 1, 4), (1, 1, 5)],
+                ids=lambda v: "leaf_trigger=%d,bound32=%d,blocks=%d" % v, autouse=True)
 def kernel_variant(request):
     """Kernel variants: leaf rounds triggered by 16 (default) / 32 / 1 parked lanes, 0 = leaf tests inline; box bound
-    from the packed FP32 records (default) or from the FP64 records."""
+    from the packed FP32 records (default) or from the FP64 records; register budget for 3 / 4 / 5 blocks per SM."""
     from fcl_b200 import _capi
 
+    saved = {k: _capi.get_option(k) for k in ("sphere_leaf_trigger", "sphere_bound32", "sphere_blocks")}
     _capi.set_option("sphere_leaf_trigger", request.param[0])
     _capi.set_option("sphere_bound32", request.param[1])
+    _capi.set_option("sphere_blocks", request.param[2])
     yield request.param
-    _capi.set_option("sphere_leaf_trigger", 16)
-    _capi.set_option("sphere_bound32", 1)
+    for k, v in saved.items():
+        _capi.set_option(k, v)
 
 
 def _check(got, brute, trav, radius):
