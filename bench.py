@@ -284,6 +284,7 @@ def run_sphere_distance(args, local):
         "ms_per_step": k_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOADS["sphere_distance"], "poses_per_gpu": n, "pose_seed": 1, "l2_flush_between_steps": True,
                    "sphere_leaf_trigger": _capi.get_option("sphere_leaf_trigger"), "sphere_bound32": _capi.get_option("sphere_bound32"),
+                   "sphere_blocks": _capi.get_option("sphere_blocks"),
                    "multi_gpu": "single GPU"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
