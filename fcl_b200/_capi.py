@@ -52,6 +52,7 @@ SYMBOLS = [
     "fclgpu_model_refit_topdown", "fclgpu_model_download", "fclgpu_model_build_obbrss", "fclgpu_model_get_topology",
     "fclgpu_collide_mesh_sphere_batch", "fclgpu_collide_mesh_sphere_batch_host",
     "fclgpu_distance_mesh_sphere_batch", "fclgpu_distance_mesh_sphere_batch_host",
+    "fclgpu_distance_cutoff_batch", "fclgpu_distance_cutoff_batch_host",
     "fclgpu_model_create_obbrss", "fclgpu_model_from_bvh", "fclgpu_model_destroy", "fclgpu_model_num_nodes",
     "fclgpu_model_num_tris", "fclgpu_model_device", "fclgpu_collide_batch", "fclgpu_collide_batch_host",
     "fclgpu_distance_batch", "fclgpu_distance_batch_host", "fclgpu_abi_version", "fclgpu_device_count",
@@ -110,6 +111,10 @@ def lib():
                                                     dp, ip, ip, up, up, vp]
     L.fclgpu_distance_mesh_sphere_batch_host.argtypes = [vp, C.c_double, C.c_int64, dp, dp, C.POINTER(DistanceRequestC), dp,
                                                          dp, dp, ip, ip, up, up]
+    L.fclgpu_distance_cutoff_batch.argtypes = [vp, vp, C.c_int64, dp, dp, C.POINTER(DistanceRequestC), C.c_double, dp, dp, dp,
+                                               ip, ip, up, up, vp]
+    L.fclgpu_distance_cutoff_batch_host.argtypes = [vp, vp, C.c_int64, dp, dp, C.POINTER(DistanceRequestC), C.c_double, dp, dp,
+                                                    dp, ip, ip, up, up]
     L.fclgpu_last_error.restype = C.c_char_p
     L.fclgpu_pose_from_colmajor4x4.argtypes = [vp, vp]
     L.fclgpu_pose_from_colmajor4x4.restype = None

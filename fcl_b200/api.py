@@ -649,7 +649,9 @@ def collide_mesh_sphere_batch(o1, tf1, sphere, tf2, request, contact_capacity=No
     return BatchCollisionResult(counts, contacts, offsets, n_bv, n_leaf)
 
 
-def distance_batch(o1, tf1, o2, tf2, request, stats=False, device=None, pinned=False):
+def distance_batch(o1, tf1, o2, tf2, request, stats=False, device=None, pinned=False, cutoff=None):
+    """n independent fcl::distance() calls (host arrays in and out).  cutoff (extension, see include/fclgpu.h): the
+    traversal starts from min_distance = cutoff, so results >= cutoff come back as cutoff with b1 = b2 = -1."""
     tf1, n1 = _poses(tf1)
     tf2, n2 = _poses(tf2)
     n = n1 if n1 is not None else n2
@@ -661,11 +663,25 @@ def distance_batch(o1, tf1, o2, tf2, request, stats=False, device=None, pinned=F
     (b1, k3), (b2, k4) = _out(n, np.int32, pinned, "b1"), _out(n, np.int32, pinned, "b2")
     n_bv = np.zeros(n, np.uint32) if stats else None
     n_leaf = np.zeros(n, np.uint32) if stats else None
-    check(_capi.lib().fclgpu_distance_batch_host(m1, m2, n, addr(tf1), addr(tf2), C.byref(req), addr(dist), addr(p1),
-                                                 addr(p2), addr(b1), addr(b2), addr(n_bv), addr(n_leaf)))
+    if cutoff is None:
+        check(_capi.lib().fclgpu_distance_batch_host(m1, m2, n, addr(tf1), addr(tf2), C.byref(req), addr(dist), addr(p1),
+                                                     addr(p2), addr(b1), addr(b2), addr(n_bv), addr(n_leaf)))
+    else:
+        check(_capi.lib().fclgpu_distance_cutoff_batch_host(m1, m2, n, addr(tf1), addr(tf2), C.byref(req), float(cutoff),
+                                                            addr(dist), addr(p1), addr(p2), addr(b1), addr(b2), addr(n_bv),
+                                                            addr(n_leaf)))
     res = BatchDistanceResult(dist, p1, p2, b1, b2, n_bv, n_leaf)
     res._keepalive = [k0, k1, k2, k3, k4]
     return res
+
+
+def within_tolerance_batch(o1, tf1, o2, tf2, tolerance, stats=False, device=None):
+    """Tolerance verification (extension; BASELINE cfg5): bool[n], query i is True iff fcl::distance(o1, tf1[i], o2,
+    tf2[i]) <= tolerance.  Runs the distance traversal from min_distance = nextafter(tolerance, +inf), so node pairs
+    farther apart than the tolerance are pruned from the first round on.  Returns (within, BatchDistanceResult)."""
+    r = distance_batch(o1, tf1, o2, tf2, DistanceRequest(False), stats=stats, device=device,
+                       cutoff=float(np.nextafter(float(tolerance), np.inf)))
+    return r.min_distance <= float(tolerance), r
 
 
 def distance_mesh_sphere_batch(o1, tf1, sphere, tf2, request, stats=False, device=None, pinned=False):

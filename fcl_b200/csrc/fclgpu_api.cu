@@ -897,7 +897,7 @@ namespace {
 int distance_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1, const double* tf2,
                      const fclgpu_distance_request* request, double* min_distance, double* nearest_p1,
                      double* nearest_p2, int32_t* b1, int32_t* b2, uint32_t* n_bv, uint32_t* n_leaf, void* stream,
-                     double sphere_radius) {
+                     double sphere_radius, double cutoff = 1.7976931348623157e308) {
   if (!m1 || !m2 || !request || n < 0) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL model/request or n<0");
   if (m1->device != m2->device) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "models live on different devices");
   if (m1->depth + (sphere_radius >= 0 ? 0 : m2->depth) + 2 > kStackCap)
@@ -929,6 +929,7 @@ int distance_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, 
   P.spill_bound = nullptr;
   P.spill_cap = 0;
   P.spill_warps = 0;
+  P.cutoff = cutoff;
   if ((long long)m1->d.n_nodes + m2->d.n_nodes >= (1 << 17) && opt("dist_spill_entries") >= kSpillBlock) {
     // big models: the sorted front may outgrow its shared-memory stack; give every warp of the largest
     // possible grid an overflow area in HBM (12 bytes per entry)
@@ -988,6 +989,16 @@ extern "C" int fclgpu_distance_batch(const fclgpu_model* m1, const fclgpu_model*
                                      int32_t* b2, uint32_t* n_bv, uint32_t* n_leaf, void* stream) {
   return distance_enqueue(m1, m2, n, tf1, tf2, request, min_distance, nearest_p1, nearest_p2, b1, b2, n_bv, n_leaf, stream,
                           -1.0);
+}
+
+// tolerance verification (extension, BASELINE cfg5): fcl::distance started from min_distance = cutoff
+extern "C" int fclgpu_distance_cutoff_batch(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1,
+                                            const double* tf2, const fclgpu_distance_request* request, double cutoff,
+                                            double* min_distance, double* nearest_p1, double* nearest_p2, int32_t* b1,
+                                            int32_t* b2, uint32_t* n_bv, uint32_t* n_leaf, void* stream) {
+  if (!(cutoff > 0)) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "cutoff must be > 0");
+  return distance_enqueue(m1, m2, n, tf1, tf2, request, min_distance, nearest_p1, nearest_p2, b1, b2, n_bv, n_leaf, stream,
+                          -1.0, cutoff);
 }
 
 // mesh <-> sphere distance
@@ -1220,7 +1231,8 @@ extern "C" int fclgpu_collide_batch_host(const fclgpu_model* m1, const fclgpu_mo
 namespace {
 int distance_host(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1, const double* tf2,
                   const fclgpu_distance_request* request, double* min_distance, double* nearest_p1, double* nearest_p2,
-                  int32_t* b1, int32_t* b2, uint32_t* n_bv, uint32_t* n_leaf, double sphere_radius) {
+                  int32_t* b1, int32_t* b2, uint32_t* n_bv, uint32_t* n_leaf, double sphere_radius,
+                  double cutoff = 1.7976931348623157e308) {
   if (!m1 || !m2 || !request || n < 0) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL model/request or n<0");
   CUDA_TRY(cudaSetDevice(m1->device));
   Workspace* w;
@@ -1256,7 +1268,7 @@ int distance_host(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, con
     if (tf1) CUDA_TRY(cudaMemcpyAsync(d_tf1, tf1 + 12 * s, 96 * cn, cudaMemcpyHostToDevice, st));
     if (tf2) CUDA_TRY(cudaMemcpyAsync(d_tf2, tf2 + 12 * s, 96 * cn, cudaMemcpyHostToDevice, st));
     rc = distance_enqueue(m1, m2, (int64_t)cn, d_tf1, d_tf2, request, d_dist, d_p1, d_p2, d_b1, d_b2, d_bv, d_leaf, st,
-                          sphere_radius);
+                          sphere_radius, cutoff);
     if (rc) return rc;
     if (min_distance) CUDA_TRY(cudaMemcpyAsync(min_distance + s, d_dist, 8 * cn, cudaMemcpyDeviceToHost, st));
     if (d_p1) CUDA_TRY(cudaMemcpyAsync(nearest_p1 + 3 * s, d_p1, 24 * cn, cudaMemcpyDeviceToHost, st));
@@ -1278,6 +1290,15 @@ extern "C" int fclgpu_distance_batch_host(const fclgpu_model* m1, const fclgpu_m
                                           double* nearest_p1, double* nearest_p2, int32_t* b1, int32_t* b2,
                                           uint32_t* n_bv, uint32_t* n_leaf) {
   return distance_host(m1, m2, n, tf1, tf2, request, min_distance, nearest_p1, nearest_p2, b1, b2, n_bv, n_leaf, -1.0);
+}
+
+extern "C" int fclgpu_distance_cutoff_batch_host(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n,
+                                                 const double* tf1, const double* tf2,
+                                                 const fclgpu_distance_request* request, double cutoff,
+                                                 double* min_distance, double* nearest_p1, double* nearest_p2, int32_t* b1,
+                                                 int32_t* b2, uint32_t* n_bv, uint32_t* n_leaf) {
+  if (!(cutoff > 0)) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "cutoff must be > 0");
+  return distance_host(m1, m2, n, tf1, tf2, request, min_distance, nearest_p1, nearest_p2, b1, b2, n_bv, n_leaf, -1.0, cutoff);
 }
 
 extern "C" int fclgpu_distance_mesh_sphere_batch_host(const fclgpu_model* m1, double radius, int64_t n, const double* tf1,

@@ -337,6 +337,9 @@ struct DistanceParams {
   float* spill_bound;
   int spill_cap;
   int spill_warps;  // warps the area was sized for
+  // value the minimum starts from (DistanceResult's initial min_distance): DBL_MAX for fcl::distance; a finite cutoff
+  // for the tolerance-verification extension -- everything whose bound is >= cutoff is pruned from the first round on
+  double cutoff;
 };
 
 struct DistState {
@@ -404,7 +407,7 @@ __global__ void __launch_bounds__(128) distance_thread_kernel(DistanceParams P) 
         R = mulTM(tf1.R, tf2.R);
         const V3 it = mulTv(tf1.R, tf1.t);
         T = mulTv(tf1.R, tf2.t) + mk(-it.x, -it.y, -it.z);
-        s.min_d = 1.7976931348623157e308;
+        s.min_d = P.cutoff;
         s.b1 = s.b2 = -1;
         s.p1 = s.p2 = mk(0, 0, 0);
         bv_tests = leaf_tests = 0;
@@ -602,9 +605,10 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
       t_l1 = __double2float_ru((fabs(T.x) + fabs(T.y)) + fabs(T.z));
     }
 
-    double min_d = 1.7976931348623157e308;
-    // bounds are floats: (double)b < min_d  <=>  b < min_f with min_f = min_d rounded up (the smallest float >= min_d)
-    float min_f = __int_as_float(0x7f800000);
+    double min_d = P.cutoff;  // DBL_MAX for fcl::distance
+    // bounds are floats: (double)b < min_d  <=>  b < min_f with min_f = min_d rounded up (the smallest float >= min_d;
+    // +inf for DBL_MAX)
+    float min_f = __double2float_ru(min_d);
     int sp = 1, nleaf = 1, nraw = 0;
     uint32_t bv_tests = 0, leaf_tests = 0;
     if (lane == 0) {

@@ -228,6 +228,25 @@ int fclgpu_distance_batch_host(const fclgpu_model* m1, const fclgpu_model* m2, i
                                uint32_t* n_bv, uint32_t* n_leaf);
 
 /* ---------------------------------------------------------------------------------------
+ * Tolerance verification (EXTENSION; BASELINE cfg5).  The reference advertises "tolerance verification" for
+ * meshes (README.md:13-14) but has no API for it; a caller gets it from fcl::distance by comparing the result with
+ * the tolerance.  Here the traversal of fclgpu_distance_batch starts from min_distance = cutoff instead of the
+ * DistanceResult default DBL_MAX (distance_result-inl.h:52-60), so every node pair whose bound is >= cutoff is pruned
+ * from the first round on:
+ *   min_distance[i] = the same value fclgpu_distance_batch returns when that is < cutoff (ids and nearest points too),
+ *   otherwise cutoff, with b1 = b2 = -1 and unspecified nearest points.
+ * "within tolerance tol"  <=>  min_distance[i] <= tol  with cutoff = nextafter(tol, +inf).  cutoff must be > 0.
+ * ------------------------------------------------------------------------------------- */
+int fclgpu_distance_cutoff_batch(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1,
+                                 const double* tf2, const fclgpu_distance_request* request, double cutoff,
+                                 double* min_distance, double* nearest_p1, double* nearest_p2, int32_t* b1, int32_t* b2,
+                                 uint32_t* n_bv, uint32_t* n_leaf, void* stream);
+int fclgpu_distance_cutoff_batch_host(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1,
+                                      const double* tf2, const fclgpu_distance_request* request, double cutoff,
+                                      double* min_distance, double* nearest_p1, double* nearest_p2, int32_t* b1, int32_t* b2,
+                                      uint32_t* n_bv, uint32_t* n_leaf);
+
+/* ---------------------------------------------------------------------------------------
  * Batched mesh <-> sphere distance: query i evaluates
  * fcl::distance(m1, tf1[i], Sphere(radius), tf2[i], request, result_i) =
  * BVHShapeDistancer<OBBRSS<S>, Sphere<S>> -> orientedBVHShapeDistance
