@@ -2,7 +2,7 @@
 //   g++ -std=c++17 -Itests/shim/mock -Iinclude tests/shim/shim_check.cpp -Lfcl_b200/lib -lfclgpu -o shim_check
 // Builds two procedural meshes with the library's own host builder, exposes them through the mock
 // fcl::BVHModel<OBBRSS<double>>, runs the shim's batched collide / distance and compares every result with
-// direct C-ABI calls on the same inputs.  argv[1] = "compile-only" skips the GPU part.
+// direct C-ABI calls on the same inputs.  argv[1] = "compile-only" skips the GPU part, "tolerance" adds the extension check.
 #include <fclgpu/fcl_shim.hpp>
 
 #include <cmath>
@@ -179,6 +179,18 @@ int main(int argc, char** argv) {
     }
     if (separated == 0) { std::printf("FAIL: no separated sphere\n"); return 1; }
     std::printf("shim sphere distance OK: %lld separated\n", separated);
+    // tolerance verification through the shim vs the plain distances above (argv[1] = "tolerance": run by the last GPU test file)
+    if (argc > 1 && std::string(argv[1]) == "tolerance") {
+    std::vector<char> within;
+    fclgpu::within_tolerance(d1, tf1, d2, tf2, 0.25, within);
+    long long n_within = 0;
+    for (int i = 0; i < n; ++i) {
+      if ((within[i] != 0) != (dist[i] <= 0.25)) { std::printf("FAIL within tolerance %d\n", i); return 1; }
+      n_within += within[i] != 0;
+    }
+    if (n_within == 0 || n_within == n) { std::printf("FAIL: degenerate tolerance sample\n"); return 1; }
+    std::printf("shim tolerance OK: %lld within 0.25\n", n_within);
+    }
   }
   if (colliding < n / 20 || colliding > n - n / 20) { std::printf("FAIL: degenerate pose sample (%lld colliding)\n", colliding); return 1; }
   std::printf("shim OK: %d queries, %lld colliding, %lld contacts compared, distances identical\n", n, colliding, contacts);

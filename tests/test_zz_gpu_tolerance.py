@@ -54,3 +54,14 @@ def test_cutoff_argument_is_checked(env_rob_npz):
     with pytest.raises(F.FclGpuError) as ei:
         F.distance_batch(env, random_poses(4), env, None, F.DistanceRequest(), cutoff=0.0)
     assert ei.value.code == _capi.ERR_INVALID_ARGUMENT
+
+
+def test_shim_within_tolerance_equals_plain_distances(tmp_path):
+    """include/fclgpu/fcl_shim.hpp: fclgpu::within_tolerance against fclgpu::distance <= tolerance (tests/shim/shim_check.cpp)."""
+    import subprocess
+
+    from tests.test_fcl_shim import _build
+
+    out = subprocess.run([_build(tmp_path), "tolerance"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "shim tolerance OK" in out.stdout
