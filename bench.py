@@ -1,12 +1,22 @@
 #!/usr/bin/env python
 """bench.py — batched OBBRSS mesh-mesh queries/second on B200 (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--workload distance|collide|contacts|sphere_distance]
+    python bench.py --gpus N --steps K --warmup W [--workload all|distance|collide|cfg1|contacts|sphere_distance|cfg4|cfg5]
     python bench.py --impl reference ...     # the CPU oracle (the only CPU FCL buildable here)
 
-A step = one pass of the hot path over one batch of synthetic poses (env.obj vs rob.obj).
-Default workload = BASELINE configs[1]: distance() with nearest points, 1M poses per GPU.
-Prints ONE JSON line (rank 0).
+A step = one pass of the hot path over one batch of synthetic poses.  The headline (top-level keys of the ONE JSON
+line rank 0 prints) is BASELINE configs[1]: env.obj vs rob.obj distance() with nearest points, 1M poses per GPU.
+With the default --workload all the same line carries, under "workloads", the other env/rob configurations measured
+the same way: cfg1 (collide, binary verdict, at its real size of 10k poses and at 1M), cfg3 (contacts, max 100).
+cfg4 (7-link arm vs 200k-triangle scene) and cfg5 (two 1M-triangle meshes: collide, distance, tolerance
+verification) are separate invocations (--workload cfg4 | cfg5, --scaling weak|strong).
+
+Roofline: per workload, the bound is the SLOWER of
+  fp64 : executed mul+add+cmp of the reference's sequential traversal (instrumented oracle, oracle/fcl_oracle_counted.cpp)
+         over the measured unfused FP64 issue rate (fclgpu_microbench kind 0), and
+  l2   : algorithmic record bytes (96 + n_bv*2*(120|128) + n_leaf*2*72 + out) over the measured L2 read bandwidth
+         (fclgpu_microbench kind 2) -- or `hbm` (MEASURED_PEAKS.json hbm_gbs) when the BVHs exceed the L2;
+frac = that bound's time / the traversal kernel's measured time (CUDA events around the launch).
 """
 import argparse
 import json
@@ -24,14 +34,17 @@ sys.path.insert(0, ROOT)
 METRIC = "mesh-mesh collide/distance queries/sec at 1/2/4/8 B200 vs host-core FCL"
 UNIT = "queries/s"
 WORKLOADS = {
-    # name: (BASELINE config it corresponds to, description)
     "distance": "cfg2: env.obj vs rob.obj distance() with nearest points, 1M random poses per GPU, double",
-    "collide": "cfg1-style: env.obj vs rob.obj collide() binary verdict (CollisionRequest()), 1M random poses per GPU",
+    "collide": "cfg1 at 1M: env.obj vs rob.obj collide() binary verdict (CollisionRequest()), 1M random poses per GPU",
+    "cfg1": "cfg1 at its real size: env.obj vs rob.obj collide() binary verdict, 10k random poses per GPU",
     "contacts": "cfg3: env.obj vs rob.obj collide() enable_contact, num_max_contacts=100, 1M random poses per GPU",
-    # SURVEY 8f rank 2 (the row next to the path), single GPU: see run_sphere_distance()
     "sphere_distance": "env.obj at identity vs Sphere(r=100) at the seed-1 pose translations, distance() with nearest points, 1M queries",
+    "cfg4": "cfg4: 7-link arm (7 x 4,900-triangle links) vs 199,712-triangle scene, collide() verdict per link, robot configurations sharded across GPUs",
+    "cfg5": "cfg5: two 999,680-triangle meshes, collide() verdict + distance() + tolerance verification, poses sharded across GPUs",
 }
+ENV_ROB = ("distance", "collide", "cfg1", "contacts")
 SPHERE_RADIUS = 100.0
+L2_BYTES = 126 << 20
 
 
 def load_meshes():
@@ -45,10 +58,10 @@ def measured_peaks():
     if os.path.exists(p):
         try:
             d = json.load(open(p))
-            return float(d["hbm_gbs"]), "measured"
+            return float(d["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
         except Exception:
             pass
-    return 6650.0, "fallback"
+    return 6650.0, "fallback of /opt/skills/guides/B200_PROFILING.md"
 
 
 class ClockSampler:
@@ -97,59 +110,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def algorithmic_bytes(workload, n_bv, n_leaf, n_contacts=None):
-    """bytes per query from the reference traversal's counters.  Node records are
-    128 B here (120 B of fields + the precomputed size), triangles 72 B."""
-    n_bv = n_bv.astype(np.float64)
-    n_leaf = n_leaf.astype(np.float64)
-    if workload == "distance":
+def algorithmic_bytes(kind, n_bv, n_leaf, n_contacts=None):
+    """bytes per query from the REFERENCE traversal's counters (120 B of OBB fields / 128 B of RSS
+    fields per node, 72 B per triangle, 96 B pose in, result out)."""
+    n_bv = np.asarray(n_bv, np.float64)
+    n_leaf = np.asarray(n_leaf, np.float64)
+    if kind == "distance":
         return 96 + n_bv * 2 * 128 + n_leaf * 2 * 72 + 64
-    out = 1.0 if workload == "collide" else 4.0 + 64.0 * n_contacts.astype(np.float64)
+    out = 1.0 if n_contacts is None else 4.0 + 64.0 * np.asarray(n_contacts, np.float64)
     return 96 + n_bv * 2 * 120 + n_leaf * 2 * 72 + out
-
-
-def run_reference(args, rank, world):
-    """--impl reference: the CPU oracle (restatement of the reference; real FCL needs Eigen/libccd,
-    absent from this image) on all host threads, bounded sample per step."""
-    if rank != 0:
-        return
-    from fcl_b200.poses import random_poses
-    from oracle import pyoracle as O
-
-    O.build()
-    (ev, et), (rv, rt) = load_meshes()
-    env, rob = O.Model(ev, et), O.Model(rv, rt)
-    threads = O.hardware_threads()
-    sample = args.cpu_sample
-    P = random_poses(sample, seed=1)
-
-    ident = np.zeros((sample, 12))
-    ident[:, 0] = ident[:, 4] = ident[:, 8] = 1.0
-
-    def step():
-        if args.workload == "sphere_distance":
-            return O.distance_mesh_sphere_batch(env, SPHERE_RADIUS, ident, P, nthreads=threads)["seconds"]
-        if args.workload == "distance":
-            return O.distance_batch(env, rob, P, None, True, 2, nthreads=threads)["seconds"]
-        if args.workload == "collide":
-            return O.collide_batch(env, rob, P, None, 1, False, nthreads=threads)["seconds"]
-        return O.collide_batch(env, rob, P, None, 100, True, nthreads=threads)["seconds"]
-
-    for _ in range(args.warmup):
-        step()
-    secs = [step() for _ in range(args.steps)]
-    total = float(sum(secs))
-    value = sample * args.steps / total
-    line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload], "sample_poses_per_step": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"first {sample} poses of the seed-1 batch per step, {threads} host threads"},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    emit(line)
 
 
 _RESULT_FD = None
@@ -193,18 +162,421 @@ def ensure_built(local_rank):
         raise SystemExit("libfclgpu.so was not built")
 
 
-def run_sphere_distance(args, local):
-    """--workload sphere_distance (single GPU): the row next to the path, SURVEY 8f rank 2.  value = kernel throughput with
-    the inputs resident in HBM; e2e = through fclgpu_distance_mesh_sphere_batch_host with pinned host buffers; roofline from
-    the REFERENCE traversal's counters (the oracle's n_bv / n_leaf on the CPU sample, SURVEY 8d accounting: 2 poses + 120 B
-    per node test + 72 B per triangle test + 64 B out); cpu_baseline = the oracle on the host cores."""
-    import ctypes as C
+# ------------------------------------------------------------------------------------------------
+# CPU side: the oracle as baseline and as the source of the reference traversal's executed work
+# ------------------------------------------------------------------------------------------------
+def oracle_pair_run(kind, O, m1, m2, tf1, tf2, threads, **kw):
+    if kind == "distance":
+        return O.distance_batch(m1, m2, tf1, tf2, True, 2, nthreads=threads)
+    return O.collide_batch(m1, m2, tf1, tf2, kw.get("num_max_contacts", 1), kw.get("enable_contact", False), nthreads=threads)
 
-    import torch
+
+def request_of(wl):
+    if wl == "contacts":
+        return {"num_max_contacts": 100, "enable_contact": True}
+    return {"num_max_contacts": 1, "enable_contact": False}
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU oracle (restatement of the reference; real FCL needs Eigen/libccd, absent from this
+    image) on all host threads, bounded sample per step, for the headline workload and -- under "workloads" -- the
+    other env/rob configurations of the default line."""
+    if rank != 0:
+        return
+    from fcl_b200.poses import identity_poses, random_poses
+    from oracle import pyoracle as O
+
+    O.build()
+    (ev, et), (rv, rt) = load_meshes()
+    env, rob = O.Model(ev, et), O.Model(rv, rt)
+    threads = O.hardware_threads()
+    sample = args.cpu_sample
+    P = random_poses(sample, seed=1)
+
+    def one(wl, steps, warmup):
+        s = min(sample, 10000) if wl == "cfg1" else sample
+
+        def step():
+            if wl == "sphere_distance":
+                return O.distance_mesh_sphere_batch(env, SPHERE_RADIUS, identity_poses(s), P[:s], nthreads=threads)["seconds"]
+            kind = "distance" if wl == "distance" else "collide"
+            return oracle_pair_run(kind, O, env, rob, P[:s], None, threads, **request_of(wl))["seconds"]
+
+        for _ in range(warmup):
+            step()
+        total = float(sum(step() for _ in range(steps)))
+        return s * steps / total, 1e3 * total / steps, s
+
+    head = "distance" if args.workload == "all" else args.workload
+    if head in ("cfg4", "cfg5"):
+        emit(reference_big(args, head, O, threads))
+        return
+    value, ms, s = one(head, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[head], "sample_poses_per_step": s},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"first {s} poses of the seed-1 batch per step, {threads} host threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    if args.workload == "all":
+        subs = {}
+        for wl in ENV_ROB:
+            v, m, ss = (value, ms, s) if wl == head else one(wl, max(2, min(args.steps, 5)), 1)
+            subs[wl] = {"workload": WORKLOADS[wl], "value": v, "unit": UNIT, "ms_per_step": m, "sample_poses_per_step": ss,
+                        "cores": threads, "kind": "port"}
+        line["workloads"] = subs
+    emit(line)
+
+
+def reference_big(args, head, O, threads):
+    """--impl reference for cfg4 / cfg5: the oracle on a bounded pose sample of the same meshes."""
+    from fcl_b200 import workloads as W
+    from fcl_b200.poses import identity_poses
+
+    s = min(args.cpu_sample, 2000)
+    subs = {}
+    t0 = time.perf_counter()
+    if head == "cfg4":
+        (sv, st), links = W.cfg4_meshes()
+        scene = O.Model(sv, st)
+        olinks = [O.Model(v, t) for v, t in links]
+        LP = W.arm_configurations(s, seed=4)
+        secs = 0.0
+        for _ in range(max(1, min(args.steps, 3))):
+            secs = sum(O.collide_batch(scene, olinks[j], None, np.ascontiguousarray(LP[:, j]), 1, False, nthreads=threads)["seconds"]
+                       for j in range(7))
+        value = 7 * s / secs
+        subs["collide"] = {"value": value, "unit": UNIT, "configurations_per_s": s / secs}
+    else:
+        (va, ta), (vb, tb) = W.cfg5_meshes()
+        A, B = O.Model(va, ta), O.Model(vb, tb)
+        P = W.shell_poses(s, 1.5, 3.0, seed=6)
+        rc = O.collide_batch(A, B, identity_poses(s), P, 1, False, nthreads=threads)
+        rd = O.distance_batch(A, B, identity_poses(s), P, True, 2, nthreads=threads)
+        value = s / rc["seconds"]
+        subs["collide"] = {"value": value, "unit": UNIT}
+        subs["distance"] = {"value": s / rd["seconds"], "unit": UNIT}
+        subs["tolerance"] = {"value": s / rd["seconds"], "unit": UNIT,
+                             "note": "the reference has no tolerance query: a caller compares fcl::distance with the tolerance"}
+    return {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * (7 if head == "cfg4" else 1) * s / value, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOADS[head], "sample_poses_per_step": s, "setup_s": time.perf_counter() - t0},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{s} poses / configurations per step, {threads} host threads (BVH build excluded)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "workloads": subs}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------------
+class Ctx:
+    """Process-wide state of one bench run (one rank = one GPU)."""
+
+    def __init__(self, args, rank, world, local):
+        import torch
+        import torch.distributed as dist
+
+        self.args, self.rank, self.world, self.local = args, rank, world, local
+        self.torch, self.dist = torch, dist
+        self.dev = torch.device("cuda", local)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
+        self.comm_stream = torch.cuda.Stream(self.dev) if world > 1 else None
+        self._pending = None
+        self.peaks = None
+
+    # ---- step loop on the device clock, L2 flushed before every step, max over ranks.  One GPU: the sum of the per-step
+    # event intervals (flush outside the intervals).  Several GPUs: steps overlap (step k's results leave over NVLink
+    # while step k+1 computes), so ONE interval brackets all K steps, flushes and the final drain included. ----
+    def timed(self, fn, steps, warmup, drain=None):
+        torch, dist = self.torch, self.dist
+        for k in range(warmup):
+            fn(k)
+        if drain:
+            drain()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if self.world == 1:
+            ms = 0.0
+            for k in range(steps):
+                self.flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn(k)
+                e1.record()
+                e1.synchronize()
+                ms += e0.elapsed_time(e1)
+            torch.cuda.synchronize()
+            return ms
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(steps):
+            self.flush.fill_(1)
+            fn(k)
+        if drain:
+            drain()
+        e1.record()
+        e1.synchronize()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        dist.barrier()
+        t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- the traversal kernel alone: CUDA events around each launch (flush outside the events) ----
+    def timed_kernel(self, fn, steps):
+        torch = self.torch
+        fn(0)
+        torch.cuda.synchronize()
+        ms = 0.0
+        for k in range(steps):
+            self.flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(k)
+            e1.record()
+            e1.synchronize()
+            ms += e0.elapsed_time(e1)
+        return ms / steps
+
+    # ---- results of step k leave over NVLink while step k+1 computes (one packed record buffer per step) ----
+    def gather_async(self, local_buf, out_buf):
+        torch, dist = self.torch, self.dist
+        if self.world == 1:
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ev)
+            dist.all_gather_into_tensor(out_buf, local_buf)
+
+    def drain(self):
+        if self.world > 1:
+            self.torch.cuda.current_stream().wait_stream(self.comm_stream)
+
+    def microbench(self):
+        if self.peaks is None:
+            from fcl_b200 import _capi
+
+            hbm, src = measured_peaks()
+            self.peaks = {"fp64_unfused_ops_per_s": _capi.microbench(0, self.local), "dfma_per_s": _capi.microbench(1, self.local),
+                          "l2_read_gbs": _capi.microbench(2, self.local), "hbm_gbs": hbm, "hbm_source": src}
+        return self.peaks
+
+
+def roofline_of(ctx, kind, n, k_ms, nbv_sum, nleaf_sum, bytes_sum, flops_sum, flops_note, model_bytes, traffic=None, extra=None):
+    """bound = the slower of the FP64 pipe and the memory level that holds the BVH records."""
+    pk = ctx.microbench()
+    mem_level = "l2" if model_bytes <= L2_BYTES else "hbm"
+    mem_peak = pk["l2_read_gbs"] if mem_level == "l2" else pk["hbm_gbs"]
+    t_fp64 = flops_sum / pk["fp64_unfused_ops_per_s"]
+    t_mem = bytes_sum / (mem_peak * 1e9)
+    sec = k_ms * 1e-3
+    if t_fp64 >= t_mem:
+        r = {"bound": "fp64", "achieved": flops_sum / sec / 1e12, "peak": pk["fp64_unfused_ops_per_s"] / 1e12, "unit": "TFLOP/s",
+             "peak_source": "fclgpu_microbench(0): separately rounded DMUL+DADD issue rate measured on this GPU in this run"}
+    else:
+        r = {"bound": mem_level, "achieved": bytes_sum / sec / 1e9, "peak": mem_peak, "unit": "GB/s",
+             "peak_source": ("fclgpu_microbench(2): L2-resident read bandwidth measured on this GPU in this run" if mem_level == "l2"
+                             else pk["hbm_source"])}
+    r["frac"] = r["achieved"] / r["peak"]
+    r["traffic"] = traffic
+    r.update({
+        "kernel_ms": k_ms,
+        "fp64": {"executed_ops_per_launch": flops_sum, "bound_ms": 1e3 * t_fp64, "frac": t_fp64 / sec, "ops_source": flops_note},
+        mem_level: {"algorithmic_bytes_per_launch": bytes_sum, "bound_ms": 1e3 * t_mem, "frac": t_mem / sec, "peak_gbs": mem_peak},
+        "mean_n_bv": nbv_sum / n, "mean_n_leaf": nleaf_sum / n, "bvh_record_bytes": model_bytes,
+        "definition": "frac = max(executed FP64 mul+add+cmp / unfused FP64 rate, algorithmic bytes / bandwidth of the level "
+                      "holding the BVH) / kernel time; work counted on the REFERENCE's sequential traversal (SURVEY 8d)",
+    })
+    if extra:
+        r.update(extra)
+    return r
+
+
+def traffic_of(wl, n, traversal):
+    """Measured DRAM bytes of the dominant kernel from the committed ncu --set full capture (profiles/*traffic.json)."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                t = json.load(f).get(wl)
+            if t and t["poses"] == n and t.get("traversal", traversal) == traversal:
+                return t["dram_bytes_per_launch"] * t["launches_per_step"], "profiles/%s (%s, %d launch(es) per step)" % (
+                    name, t["kernel"], t["launches_per_step"])
+        except Exception:
+            pass
+    return None, None
+
+
+def run_env_rob(ctx, wl, n, steps, warmup, models, meshes, with_cpu):
+    """One env.obj-vs-rob.obj workload: device-resident throughput (value), the traversal kernel alone (roofline),
+    end to end through the host-buffer API (e2e), the CPU oracle beside it (cpu_baseline)."""
+    import fcl_b200 as F
+    from fcl_b200 import _capi
+
+    torch, dist = ctx.torch, ctx.dist
+    args, world, rank, local, dev = ctx.args, ctx.world, ctx.rank, ctx.local, ctx.dev
+    env, rob = models
+    (ev, et), (rv, rt) = meshes
+    kind = "distance" if wl == "distance" else "collide"
+    P = F.random_poses(n, seed=1, start=rank * n)  # rank r owns poses [r*n, (r+1)*n) of the global batch
+    hP = torch.from_numpy(P).pin_memory()
+    dP = hP.to(dev)
+    rq = request_of(wl)
+    creq = F.CollisionRequest(rq["num_max_contacts"], rq["enable_contact"])
+    dreq = F.DistanceRequest(True)
+
+    # resident outputs: ONE packed record buffer per step parity (64 B per query for distance, 4 B for collide), so that a
+    # step's results leave with a single all-gather while the next step computes into the other buffer
+    rec = 64 if kind == "distance" else 4
+    bufs, gath = [], []
+    for _ in range(2 if world > 1 else 1):
+        b = torch.empty(n * rec, dtype=torch.uint8, device=dev)
+        bufs.append(b)
+        gath.append(torch.empty(world * n * rec, dtype=torch.uint8, device=dev) if world > 1 else None)
+
+    def views(b):
+        if kind == "distance":
+            return (b[:8 * n].view(torch.float64), b[8 * n:32 * n].view(torch.float64).view(n, 3),
+                    b[32 * n:56 * n].view(torch.float64).view(n, 3), b[56 * n:60 * n].view(torch.int32), b[60 * n:].view(torch.int32))
+        return (b.view(torch.int32),)
+
+    if wl == "contacts":
+        cap = 64 * n
+        o_con = torch.empty(cap * 64, dtype=torch.uint8, device=dev)
+        o_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+
+    def compute(k, nbv=None, nleaf=None):
+        v = views(bufs[k % len(bufs)])
+        if kind == "distance":
+            F.distance_batch_device(env, dP, rob, None, dreq, v[0], v[1], v[2], v[3], v[4], nbv, nleaf)
+        elif wl == "contacts":
+            F.collide_batch_device(env, dP, rob, None, creq, v[0], o_con, o_off, nbv, nleaf)
+        else:
+            F.collide_batch_device(env, dP, rob, None, creq, v[0], None, None, nbv, nleaf)
+
+    def step(k):
+        compute(k)
+        if world > 1:  # per-GPU results gathered with NCCL all-gather over NVLink (contact blocks stay on their GPU)
+            ctx.gather_async(bufs[k % 2], gath[k % 2])
+
+    # ---- untimed stats pass: the REFERENCE traversal's counters for the roofline accounting ----
+    nbv = torch.zeros(n, dtype=torch.int32, device=dev)
+    nleaf = torch.zeros(n, dtype=torch.int32, device=dev)
+    trav = _capi.get_option("traversal")
+    _capi.set_option("traversal", 0)  # the thread-per-query traversal visits exactly the reference's BVTT nodes
+    if kind == "distance":
+        F.distance_batch_device(env, dP, rob, None, dreq, views(bufs[0])[0], None, None, None, None, nbv, nleaf)
+    else:
+        F.collide_batch_device(env, dP, rob, None, creq, views(bufs[0])[0], None, None, nbv, nleaf)
+    F.sync_status(local)
+    _capi.set_option("traversal", trav)
+    h_nbv, h_nleaf = nbv.cpu().numpy().astype(np.int64), nleaf.cpu().numpy().astype(np.int64)
+
+    # ---- device-resident throughput ----
+    launches0 = _capi.launch_count()
+    total_ms = ctx.timed(step, steps, warmup, ctx.drain)
+    launches = (_capi.launch_count() - launches0) * steps // (steps + warmup)
+    F.sync_status(local)
+    value = world * n * steps / (total_ms * 1e-3)
+
+    # ---- dominant kernel alone (rank 0) ----
+    k_ms = ctx.timed_kernel(compute, steps) if rank == 0 else None
+    F.sync_status(local)
+    result0 = views(bufs[0])[0].clone()
+    ncon = result0.cpu().numpy().astype(np.int64) if wl == "contacts" else None
+
+    # ---- end to end through the host-pointer API (pinned host buffers, copies inside the timed region) ----
+    e2e = None
+    if not args.no_e2e:
+        hp = hP.numpy()
+
+        def step_e2e():
+            if kind == "distance":
+                return F.distance_batch(env, hp, rob, None, dreq, device=local, pinned=True).min_distance
+            if wl == "contacts":
+                return F.collide_batch(env, hp, rob, None, creq, contact_capacity=40 * n, device=local, pinned=True).num_contacts
+            return F.collide_batch(env, hp, rob, None, creq, want_contacts=False, device=local, pinned=True).num_contacts
+
+        for _ in range(2):
+            step_e2e()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step_e2e()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        if kind == "distance":
+            d2h = n * (8 + 24 + 24 + 4 + 4)
+        elif wl == "contacts":
+            d2h = n * 4 + (n + 1) * 8 + int(ncon.sum()) * 64 if ncon is not None else None
+        else:
+            d2h = n * 4
+        e2e = {"value": world * n * steps / dt, "unit": UNIT, "h2d_bytes_per_step": n * 96, "d2h_bytes_per_step": d2h,
+               "note": "per-rank host buffers; at N > 1 every rank runs its shard through the host API concurrently"}
+    if rank != 0:
+        return None
+
+    # ---- CPU baseline + executed work of the reference traversal (oracle, bounded sample) ----
+    s = min(args.cpu_sample, n)
+    cpu, flops_sum, flops_note = None, None, None
+    if with_cpu:
+        from oracle import pyoracle as O
+
+        O.build()
+        oenv, orob = O.Model(ev, et), O.Model(rv, rt)
+        threads = O.hardware_threads()
+        r = oracle_pair_run(kind, O, oenv, orob, P[:s], None, threads, **rq)
+        got = result0.cpu().numpy()[:s]
+        ok = bool(np.array_equal(r["min_distance"] if kind == "distance" else r["counts"], got))
+        counters_ok = bool(np.array_equal(r["n_bv"], h_nbv[:s]) and np.array_equal(r["n_leaf"], h_nleaf[:s]))
+        cpu = {"value": s / r["seconds"], "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"first {s} poses of rank 0's batch, {threads} host threads, one pass",
+               "matches_gpu": ok, "counters_match_gpu": counters_ok}
+        c = O.counted_query(kind, O.CountedModel(ev, et), O.CountedModel(rv, rt), P[:s], None, nthreads=threads, **rq)
+        ops = c["ops"].sum(axis=0).astype(np.float64)
+        sample_flops = float(ops[:3].sum())
+        # scale the sample's executed operations to the batch by the reference traversal's own work counters
+        scale = 0.5 * float(h_nbv.sum() / max(1, c["n_bv"].sum()) + h_nleaf.sum() / max(1, c["n_leaf"].sum()))
+        flops_sum = sample_flops * scale
+        flops_note = ("instrumented oracle (oracle/fcl_oracle_counted.cpp) on the first %d poses: executed mul %.4g add %.4g cmp %.4g "
+                      "(div %.3g, sqrt %.3g not counted) per query, scaled x%.2f to the batch by the reference traversal's n_bv / n_leaf"
+                      % (s, ops[0] / s, ops[1] / s, ops[2] / s, ops[3] / s, ops[4] / s, scale))
+    else:  # nominal fallback when the oracle leg is switched off: SURVEY 8(d) upper bounds halved (measured ratio)
+        F_BV, F_LEAF = (430.0, 1100.0) if kind == "distance" else (300.0, 860.0)
+        flops_sum = 0.5 * float((h_nbv * F_BV + h_nleaf * F_LEAF).sum())
+        flops_note = "no oracle leg (--no-cpu-baseline): 0.5 x SURVEY 8(d) upper bounds"
+
+    bytes_sum = float(algorithmic_bytes(kind, h_nbv, h_nleaf, ncon).sum())
+    model_bytes = (env.getNumBVs() + rob.getNumBVs()) * 128 + (env.num_tris + rob.num_tris) * 72
+    traffic, traffic_src = traffic_of(wl, n, trav)
+    roof = roofline_of(ctx, kind, n, k_ms, float(h_nbv.sum()), float(h_nleaf.sum()), bytes_sum, flops_sum, flops_note, model_bytes,
+                       traffic, {"traffic_source": traffic_src})
+    return {"workload": WORKLOADS[wl], "poses_per_gpu": n, "value": value, "unit": UNIT, "ms_per_step": total_ms / steps,
+            "steps": steps, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+            **({"mean_contacts_per_query": float(ncon.mean())} if ncon is not None else {})}
+
+
+def run_sphere_distance(ctx):
+    """--workload sphere_distance (single GPU): the row next to the path, SURVEY 8f rank 2."""
+    import ctypes as C
 
     import fcl_b200 as F
     from fcl_b200 import _capi
 
+    torch, args, local = ctx.torch, ctx.args, ctx.local
     (ev, et), _ = load_meshes()
     env = F.BVHModel.from_arrays(ev, et)
     n = args.poses
@@ -217,33 +589,21 @@ def run_sphere_distance(args, local):
     b1 = torch.empty(n, dtype=torch.int32, device="cuda")
     rq = F.DistanceRequest(True)._c()
     L = _capi.lib()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
-    def kernel():
+    def kernel(k=0):
         rc = L.fclgpu_distance_mesh_sphere_batch(env.device_model(local), SPHERE_RADIUS, n, None, dS.data_ptr(), C.byref(rq),
                                                  dist_d.data_ptr(), p1.data_ptr(), p2.data_ptr(), b1.data_ptr(), None, None, None,
                                                  torch.cuda.current_stream().cuda_stream)
         assert rc == 0, rc
 
-    for _ in range(args.warmup):
-        kernel()
-    torch.cuda.synchronize()
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = _capi.launch_count()
-    ms = 0.0
-    for _ in range(args.steps):
-        flush.fill_(1)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        kernel()
-        e1.record()
-        e1.synchronize()
-        ms += e0.elapsed_time(e1)
-    launches = _capi.launch_count() - launches0
+    total_ms = ctx.timed(kernel, args.steps, args.warmup)
+    launches = (_capi.launch_count() - launches0) * args.steps // (args.steps + args.warmup)
     clocks = sampler.stop()
+    k_ms = ctx.timed_kernel(kernel, args.steps)
     F.sync_status(local)
-    k_ms = ms / args.steps
     sphere = F.Sphere(SPHERE_RADIUS)
     hs = hS.numpy()
     e2e = None
@@ -268,30 +628,23 @@ def run_sphere_distance(args, local):
     got = dist_d.cpu().numpy()[:s]
     per_query = 2 * 96 + ref["n_bv"].astype(np.float64) * 120 + ref["n_leaf"].astype(np.float64) * 72 + 64
     alg = float(per_query.mean()) * n
-    peak, which = measured_peaks()
-    traffic, traffic_src = None, None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            t = json.load(f).get("sphere_distance")
-        if t and t["poses"] == n:
-            traffic = t["dram_bytes_per_launch"] * t["launches_per_step"]
-            traffic_src = "profiles/r01_traffic.json (%s, %d launch(es) per step)" % (t["kernel"], t["launches_per_step"])
-    except Exception:  # pragma: no cover
-        pass
+    pk = ctx.microbench()
     achieved = alg / (k_ms * 1e-3) / 1e9
+    traffic, traffic_src = traffic_of("sphere_distance", n, None)
     emit({
-        "metric": METRIC, "value": n / (k_ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": k_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "metric": METRIC, "value": n * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOADS["sphere_distance"], "poses_per_gpu": n, "pose_seed": 1, "l2_flush_between_steps": True,
                    "sphere_leaf_trigger": _capi.get_option("sphere_leaf_trigger"), "sphere_bound32": _capi.get_option("sphere_bound32"),
-                   "sphere_blocks": _capi.get_option("sphere_blocks"),
-                   "multi_gpu": "single GPU"},
+                   "sphere_blocks": _capi.get_option("sphere_blocks"), "multi_gpu": "single GPU"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "traffic_source": traffic_src, "peak_source": which, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg,
+        "roofline": {"bound": "l2", "achieved": achieved, "peak": pk["l2_read_gbs"], "unit": "GB/s", "frac": achieved / pk["l2_read_gbs"],
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": "fclgpu_microbench(2): L2-resident read bandwidth measured on this GPU in this run",
+                     "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg,
                      "mean_n_bv": float(ref["n_bv"].mean()), "mean_n_leaf": float(ref["n_leaf"].mean()),
-                     "note": "counters of the reference's traversal from the oracle on the CPU sample, scaled to the batch; records are "
-                             "L1/L2 resident, the binding resource is the L1 data pipe (profiles/r01_ncu_sphere_distance.txt)"},
+                     "note": "counters of the reference's traversal from the oracle on the CPU sample, scaled to the batch; records "
+                             "are L1/L2 resident (1 MB of BVH)"},
         "cpu_baseline": {"value": s / ref["seconds"], "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"first {s} queries of the batch, {threads} host threads, one pass",
                          "matches_gpu": bool(np.array_equal(got, brute["min_distance"])),
@@ -306,8 +659,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="distance", choices=sorted(WORKLOADS))
-    ap.add_argument("--poses", type=int, default=1_000_000, help="poses per GPU per step")
+    ap.add_argument("--workload", default="all", choices=["all"] + sorted(WORKLOADS))
+    ap.add_argument("--poses", type=int, default=1_000_000, help="poses per GPU per step (cfg4: robot configurations)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="cfg4 / cfg5: weak = --poses per GPU, strong = --poses in total, split across the GPUs")
     ap.add_argument("--cpu-sample", type=int, default=20000)
     ap.add_argument("--traversal", type=int, default=3, help="kernel variant (fclgpu option 'traversal', see DESIGN.md)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -322,7 +677,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank)
         return
 
     import torch
@@ -331,7 +686,6 @@ def main():
     ensure_built(local)
     import fcl_b200 as F
     from fcl_b200 import _capi
-    from fcl_b200.sharding import all_gather_records
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
@@ -344,235 +698,57 @@ def main():
     for kv in args.opt:
         k, v = kv.split("=")
         _capi.set_option(k, int(v))
+    ctx = Ctx(args, rank, world, local)
 
     if args.workload == "sphere_distance":
         if world > 1:
             raise SystemExit("--workload sphere_distance is a single-GPU line (run it without torchrun)")
-        run_sphere_distance(args, local)
+        run_sphere_distance(ctx)
         return
+    if args.workload in ("cfg4", "cfg5"):
+        import bench_big
 
-    (ev, et), (rv, rt) = load_meshes()
-    env, rob = F.BVHModel.from_arrays(ev, et), F.BVHModel.from_arrays(rv, rt)
-    env.device_model(local)
-    rob.device_model(local)  # BVHs replicated on every GPU
-
-    n = args.poses
-    P = F.random_poses(n, seed=1, start=rank * n)  # rank r owns poses [r*n, (r+1)*n) of the global batch
-    hP = torch.from_numpy(P).pin_memory()
-    dP = hP.to(dev)
-    wl = args.workload
-    creq = F.CollisionRequest() if wl == "collide" else F.CollisionRequest(100, True)
-    dreq = F.DistanceRequest(True)
-
-    # resident outputs
-    if wl == "distance":
-        o_dist = torch.empty(n, dtype=torch.float64, device=dev)
-        o_p1 = torch.empty(n, 3, dtype=torch.float64, device=dev)
-        o_p2 = torch.empty(n, 3, dtype=torch.float64, device=dev)
-        o_b1 = torch.empty(n, dtype=torch.int32, device=dev)
-        o_b2 = torch.empty(n, dtype=torch.int32, device=dev)
-    else:
-        o_cnt = torch.empty(n, dtype=torch.int32, device=dev)
-        if wl == "contacts":
-            cap = 64 * n
-            o_con = torch.empty(cap * 64, dtype=torch.uint8, device=dev)
-            o_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
-
-    def step_resident():
-        if wl == "distance":
-            F.distance_batch_device(env, dP, rob, None, dreq, o_dist, o_p1, o_p2, o_b1, o_b2)
-            if world > 1:  # per-GPU results gathered with NCCL allgather over NVLink
-                all_gather_records(o_dist, world * n)
-                all_gather_records(torch.cat([o_p1, o_p2], dim=1), world * n)
-        elif wl == "collide":
-            F.collide_batch_device(env, dP, rob, None, creq, o_cnt)
-            if world > 1:
-                all_gather_records(o_cnt, world * n)
-        else:
-            F.collide_batch_device(env, dP, rob, None, creq, o_cnt, o_con, o_off)
-            if world > 1:
-                all_gather_records(o_cnt, world * n)
-
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    def timed(fn, steps, warmup, do_flush=True):
-        for _ in range(warmup):
-            fn()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        ms = 0.0
-        for _ in range(steps):
-            if do_flush:
-                flush.fill_(1)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn()
-            e1.record()
-            e1.synchronize()
-            ms += e0.elapsed_time(e1)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- untimed stats pass: per-query work counters for the roofline accounting ----
-    nbv = torch.zeros(n, dtype=torch.int32, device=dev)
-    nleaf = torch.zeros(n, dtype=torch.int32, device=dev)
-    _capi.set_option("traversal", 0)  # the thread-per-query traversal visits exactly the reference's BVTT nodes
-    if wl == "distance":
-        F.distance_batch_device(env, dP, rob, None, dreq, o_dist, None, None, None, None, nbv, nleaf)
-    else:
-        F.collide_batch_device(env, dP, rob, None, creq, o_cnt, None, None, nbv, nleaf)
-    F.sync_status(local)
-    _capi.set_option("traversal", args.traversal)
-    h_nbv, h_nleaf = nbv.cpu().numpy().astype(np.int64), nleaf.cpu().numpy().astype(np.int64)
-
-    # ---- device-resident throughput (value) ----
-    sampler = ClockSampler(local)
-    launches0 = _capi.launch_count()
-    sampler.start()
-    total_ms = timed(step_resident, args.steps, args.warmup)
-    clocks = sampler.stop()
-    launches = _capi.launch_count() - launches0
-    launches_timed = launches * args.steps // (args.steps + args.warmup)
-    F.sync_status(local)
-    value = world * n * args.steps / (total_ms * 1e-3)
-
-    # ---- dominant-kernel roofline: traversal kernel timed alone on this rank ----
-    def kernel_only():
-        if wl == "distance":
-            F.distance_batch_device(env, dP, rob, None, dreq, o_dist, o_p1, o_p2, o_b1, o_b2)
-        elif wl == "collide":
-            F.collide_batch_device(env, dP, rob, None, creq, o_cnt)
-        else:
-            F.collide_batch_device(env, dP, rob, None, creq, o_cnt, o_con, o_off)
-
-    world_save, k_ms = world, None
-    if rank == 0:
-        world = 1
-        k_ms = timed(kernel_only, args.steps, 1) / args.steps
-        world = world_save
-    if world > 1:
-        dist.barrier()
-
-    # ---- end to end through the host-pointer API (pinned host buffers, copies inside) ----
-    e2e = None
-    if not args.no_e2e:
-        hp = hP.numpy()
-
-        def step_e2e():
-            if wl == "distance":
-                r = F.distance_batch(env, hp, rob, None, dreq, device=local, pinned=True)
-                return r.min_distance
-            if wl == "collide":
-                return F.collide_batch(env, hp, rob, None, creq, want_contacts=False, device=local, pinned=True).num_contacts
-            return F.collide_batch(env, hp, rob, None, creq, contact_capacity=40 * n, device=local, pinned=True).num_contacts
-
-        for _ in range(2):
-            step_e2e()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_e2e()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        if wl == "distance":
-            d2h = n * (8 + 24 + 24 + 4 + 4)
-        elif wl == "collide":
-            d2h = n * 4
-        else:
-            d2h = n * 4 + (n + 1) * 8 + int(h_nleaf.sum() * 0)  # + contacts, counted below
-        e2e = {"value": world * n * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": n * 96, "d2h_bytes_per_step": d2h}
-
-    if rank != 0:
+        line = bench_big.run(ctx, args.workload)
+        if rank == 0:
+            emit(line)
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline numbers ----
-    peak, which = measured_peaks()
-    if wl == "contacts":
-        ncon = o_cnt.cpu().numpy().astype(np.int64)
-        if e2e:
-            e2e["d2h_bytes_per_step"] += int(ncon.sum()) * 64
-    else:
-        ncon = None
-    alg_bytes = float(algorithmic_bytes(wl, h_nbv, h_nleaf, ncon).sum())
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    traffic, traffic_src = None, None
-    try:  # measured DRAM bytes of the dominant kernel (one ncu --set full capture, committed under profiles/)
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            t = json.load(f).get(wl)
-        if t and t["poses"] == n and t["traversal"] == args.traversal:
-            traffic = t["dram_bytes_per_launch"] * t["launches_per_step"]
-            traffic_src = "profiles/r01_traffic.json (%s, %d launch(es) per step)" % (t["kernel"], t["launches_per_step"])
-    except Exception:  # pragma: no cover
-        pass
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": traffic_src, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)" if which == "measured" else "fallback",
-                "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                "mean_n_bv": float(h_nbv.mean()), "mean_n_leaf": float(h_nleaf.mean()),
-                "note": "working set (~1 MB of BVH records) is L2/L1 resident; the binding resource is the FP64 pipe, see fp64"}
-    # FP64 pipe: measured unfused DMUL+DADD issue rate vs nominal per-test operation counts
-    fp64 = None
-    try:
-        unfused = _capi.microbench(0, local)
-        fused = _capi.microbench(1, local)
-        l2 = _capi.microbench(2, local)
-        F_BV = 430.0 if wl == "distance" else 300.0   # upper-bound mul+add per BV test
-        F_LEAF = 1100.0 if wl == "distance" else 860.0
-        flops = float((h_nbv * F_BV + h_nleaf * F_LEAF).sum())
-        fp64 = {"unfused_ops_per_s_peak": unfused, "dfma_per_s_peak": fused, "l2_read_gbs": l2,
-                "algorithmic_ops_upper_bound_per_launch": flops, "achieved_ops_per_s": flops / (k_ms * 1e-3),
-                "frac_of_unfused_peak_upper_bound": flops / (k_ms * 1e-3) / unfused}
-    except Exception as ex:  # pragma: no cover
-        fp64 = {"error": str(ex)}
-
-    # ---- CPU baseline: the oracle on this box's host cores, bounded sample ----
-    cpu = None
-    if not args.no_cpu_baseline:
-        from oracle import pyoracle as O
-
-        O.build()
-        oenv, orob = O.Model(ev, et), O.Model(rv, rt)
-        threads = O.hardware_threads()
-        s = min(args.cpu_sample, n)
-        if wl == "distance":
-            r = O.distance_batch(oenv, orob, P[:s], None, True, 2, nthreads=threads)
-            ok = bool(np.array_equal(r["min_distance"], o_dist.cpu().numpy()[:s]))
-        elif wl == "collide":
-            r = O.collide_batch(oenv, orob, P[:s], None, 1, False, nthreads=threads)
-            ok = bool(np.array_equal(r["counts"], o_cnt.cpu().numpy()[:s]))
-        else:
-            r = O.collide_batch(oenv, orob, P[:s], None, 100, True, nthreads=threads)
-            ok = bool(np.array_equal(r["counts"], o_cnt.cpu().numpy()[:s]))
-        counters_ok = bool(np.array_equal(r["n_bv"], h_nbv[:s]) and np.array_equal(r["n_leaf"], h_nleaf[:s]))
-        cpu = {"value": s / r["seconds"], "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"first {s} poses of rank 0's batch, {threads} host threads, one pass",
-               "matches_gpu": ok, "counters_match_gpu": counters_ok}
-
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[wl], "poses_per_gpu": n, "global_poses": world * n, "pose_seed": 1,
-                   "models": "env.obj (2180 tris, 4359 nodes) posed vs rob.obj (216 tris, 431 nodes) at identity",
-                   "l2_flush_between_steps": True, "traversal": _capi.get_option("traversal"), **({"options": args.opt} if args.opt else {}),
-                   "multi_gpu": "BVHs replicated, poses partitioned, results all-gathered with NCCL" if world > 1 else "single GPU"},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": launches_timed, "roofline": roofline, "fp64": fp64, "cpu_baseline": cpu,
-    }
-    emit(line)
+    meshes = load_meshes()
+    (ev, et), (rv, rt) = meshes
+    env, rob = F.BVHModel.from_arrays(ev, et), F.BVHModel.from_arrays(rv, rt)
+    env.device_model(local)
+    rob.device_model(local)  # BVHs replicated on every GPU
+    head = "distance" if args.workload == "all" else args.workload
+    names = list(ENV_ROB) if args.workload == "all" else [head]
+    with_cpu = not args.no_cpu_baseline
+    results = {}
+    sampler = ClockSampler(local)
+    sampler.start()
+    for wl in names:
+        n = 10_000 if wl == "cfg1" else args.poses
+        steps = args.steps if wl == head else max(3, min(args.steps, 10))
+        results[wl] = run_env_rob(ctx, wl, n, steps, args.warmup, (env, rob), meshes, with_cpu)
+    clocks = sampler.stop()
+    if rank == 0:
+        h = results[head]
+        line = {
+            "metric": METRIC, "value": h["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": h["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOADS[head], "poses_per_gpu": h["poses_per_gpu"], "global_poses": world * h["poses_per_gpu"],
+                       "pose_seed": 1, "models": "env.obj (2180 tris, 4359 nodes) posed vs rob.obj (216 tris, 431 nodes) at identity",
+                       "l2_flush_between_steps": True, "l2_flush_inside_timed_region": world > 1,
+                       "traversal": _capi.get_option("traversal"), **({"options": args.opt} if args.opt else {}),
+                       "multi_gpu": ("BVHs replicated, poses partitioned, one packed 64 B/query result record all-gathered with NCCL "
+                                     "per step, overlapped with the next step's traversal") if world > 1 else "single GPU"},
+            "clocks": clocks, "e2e": h["e2e"], "gpu_launches": h["gpu_launches"], "roofline": h["roofline"],
+            "cpu_baseline": h["cpu_baseline"], "peaks": ctx.microbench(),
+        }
+        if args.workload == "all":
+            line["workloads"] = results
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -31,7 +31,8 @@ assert CONTACT_DTYPE.itemsize == 64
 
 
 class CollisionRequestC(C.Structure):
-    _fields_ = [("num_max_contacts", C.c_int64), ("enable_contact", C.c_int32), ("enable_cost", C.c_int32)]
+    _fields_ = [("num_max_contacts", C.c_int64), ("enable_contact", C.c_int32), ("enable_cost", C.c_int32),
+                ("stage_capacity", C.c_int64)]
 
 
 class DistanceRequestC(C.Structure):

@@ -443,9 +443,9 @@ class CollisionRequest:
     def isSatisfied(self, result):
         return (not self.enable_cost) and result.isCollision() and self.num_max_contacts <= result.numContacts()
 
-    def _c(self):
+    def _c(self, stage_capacity=0):
         return _capi.CollisionRequestC(int(min(self.num_max_contacts, 2**62)), int(bool(self.enable_contact)),
-                                       int(bool(self.enable_cost)))
+                                       int(bool(self.enable_cost)), int(stage_capacity))
 
 
 class Contact:
@@ -545,17 +545,48 @@ def _out(shape, dtype, pinned, tag=""):
 
 
 class BatchCollisionResult:
-    """num_contacts[n]; contacts (structured array / tensor view) with offsets[n+1]; optional counters."""
+    """num_contacts[n] plus the contact list of every query.
 
-    def __init__(self, num_contacts, contacts, offsets, n_bv=None, n_leaf=None):
+    The library appends each query's contacts as one contiguous block to a dense pool; `starts[i]` is the first slot of
+    query i's block (`starts[n]` = total), blocks come in the order the queries retire on the GPU unless the library
+    option `contact_order` is 1 (include/fclgpu.h).  `contacts_of(i)` reads a block in place.  `contacts` / `offsets`
+    present the same list in QUERY order (offsets = exclusive prefix sum of num_contacts, n+1 entries) -- a host-side
+    gather done on first use, for callers (and the parity tests) that want one flat, deterministic array."""
+
+    def __init__(self, num_contacts, pool, starts, n_bv=None, n_leaf=None):
         self.num_contacts = num_contacts
-        self.contacts = contacts
-        self.offsets = offsets
+        self.pool = pool
+        self.starts = starts
         self.n_bv = n_bv
         self.n_leaf = n_leaf
+        self._ordered = None
 
     def contacts_of(self, i):
-        return self.contacts[self.offsets[i]:self.offsets[i + 1]]
+        return self.pool[self.starts[i]:self.starts[i] + self.num_contacts[i]]
+
+    def _order(self):
+        if self._ordered is None and self.pool is not None:
+            n = len(self.num_contacts)
+            cnt = self.num_contacts.astype(np.int64)
+            off = np.zeros(n + 1, np.int64)
+            np.cumsum(cnt, out=off[1:])
+            st = np.asarray(self.starts[:n], np.int64)
+            if off[n] != self.starts[n]:  # truncated by a capacity overflow: keep the library's layout
+                self._ordered = (self.pool, self.starts)
+            elif np.array_equal(st[cnt > 0], off[:n][cnt > 0]):
+                self._ordered = (self.pool, off)
+            else:
+                idx = np.repeat(st - off[:n], cnt) + np.arange(off[n], dtype=np.int64)
+                self._ordered = (self.pool[idx], off)
+        return self._ordered
+
+    @property
+    def contacts(self):
+        return None if self.pool is None else self._order()[0]
+
+    @property
+    def offsets(self):
+        return None if self.pool is None else self._order()[1]
 
 
 class BatchDistanceResult:
@@ -565,7 +596,7 @@ class BatchDistanceResult:
 
 
 def collide_batch(o1, tf1, o2, tf2, request, contact_capacity=None, want_contacts=True, stats=False, device=None,
-                  grow_on_overflow=False, pinned=False):
+                  grow_on_overflow=False, pinned=False, stage_capacity=0):
     """Host arrays in, host arrays out (copies inside): n independent fcl::collide() calls.
 
     tf1 / tf2: (n,12) float64 pose records, a Transform3, or None (identity)."""
@@ -577,7 +608,7 @@ def collide_batch(o1, tf1, o2, tf2, request, contact_capacity=None, want_contact
     if n1 is not None and n2 is not None and n1 != n2:
         raise ValueError("tf1 and tf2 must have the same length")
     m1, m2 = o1.device_model(device), o2.device_model(device)
-    req = request._c()
+    req = request._c(stage_capacity)
     keep = []
     counts, k = _out(n, np.int32, pinned, "counts")
     keep.append(k)
@@ -596,12 +627,10 @@ def collide_batch(o1, tf1, o2, tf2, request, contact_capacity=None, want_contact
                                                addr(contacts), contact_capacity, addr(offsets), addr(n_bv),
                                                addr(n_leaf))
     if rc == _capi.ERR_CONTACT_OVERFLOW and grow_on_overflow:
-        # counts are exact even when the pool / per-query scratch was too small: size both and rerun
-        need_stride = int(counts.max())
-        if need_stride > _capi.get_option("contact_stride"):
-            _capi.set_option("contact_stride", 1 << int(need_stride - 1).bit_length())
+        # counts are exact even when the pool / the per-query staging was too small: size both (per call) and rerun
         return collide_batch(o1, tf1, o2, tf2, request, contact_capacity=int(counts.sum(dtype=np.int64)),
-                             want_contacts=True, stats=stats, device=device, grow_on_overflow=False)
+                             want_contacts=True, stats=stats, device=device, grow_on_overflow=False,
+                             stage_capacity=max(int(counts.max()), 1))
     check(rc)
     if want_contacts:
         contacts = contacts[: offsets[n]]
@@ -611,7 +640,7 @@ def collide_batch(o1, tf1, o2, tf2, request, contact_capacity=None, want_contact
 
 
 def collide_mesh_sphere_batch(o1, tf1, sphere, tf2, request, contact_capacity=None, want_contacts=True, stats=False,
-                              device=None, grow_on_overflow=False):
+                              device=None, grow_on_overflow=False, stage_capacity=0):
     """n independent fcl::collide(mesh, tf1[i], Sphere, tf2[i]) calls (host arrays in and out).  Contacts: one per
     intersecting triangle, b2 = -1 (Contact::NONE), in the reference's traversal order."""
     tf1, n1 = _poses(tf1)
@@ -622,7 +651,7 @@ def collide_mesh_sphere_batch(o1, tf1, sphere, tf2, request, contact_capacity=No
     if n1 is not None and n2 is not None and n1 != n2:
         raise ValueError("tf1 and tf2 must have the same length")
     m1 = o1.device_model(device)
-    req = request._c()
+    req = request._c(stage_capacity)
     counts = np.zeros(n, np.int32)
     if want_contacts:
         if contact_capacity is None:
@@ -638,11 +667,9 @@ def collide_mesh_sphere_batch(o1, tf1, sphere, tf2, request, contact_capacity=No
                                                            addr(counts), addr(contacts), contact_capacity, addr(offsets),
                                                            addr(n_bv), addr(n_leaf))
     if rc == _capi.ERR_CONTACT_OVERFLOW and grow_on_overflow:
-        need_stride = int(counts.max())
-        if need_stride > _capi.get_option("contact_stride"):
-            _capi.set_option("contact_stride", 1 << int(need_stride - 1).bit_length())
         return collide_mesh_sphere_batch(o1, tf1, sphere, tf2, request, contact_capacity=int(counts.sum(dtype=np.int64)),
-                                         want_contacts=True, stats=stats, device=device, grow_on_overflow=False)
+                                         want_contacts=True, stats=stats, device=device, grow_on_overflow=False,
+                                         stage_capacity=max(int(counts.max()), 1))
     check(rc)
     if want_contacts:
         contacts = contacts[: offsets[n]]
@@ -657,6 +684,8 @@ def distance_batch(o1, tf1, o2, tf2, request, stats=False, device=None, pinned=F
     n = n1 if n1 is not None else n2
     if n is None:
         raise ValueError("at least one of tf1/tf2 must be given")
+    if n1 is not None and n2 is not None and n1 != n2:
+        raise ValueError("tf1 and tf2 must have the same length")
     m1, m2 = o1.device_model(device), o2.device_model(device)
     req = request._c()
     (dist, k0), (p1, k1), (p2, k2) = _out(n, np.float64, pinned, "dist"), _out((n, 3), np.float64, pinned, "p1"), _out((n, 3), np.float64, pinned, "p2")

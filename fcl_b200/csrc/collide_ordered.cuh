@@ -1,0 +1,281 @@
+// collide_ordered.cuh — collide() WITH a contact list: one warp per query, DFS-ORDERED front.
+//
+// Reference semantics (file:line under /root/reference/include/fcl):
+//   collisionRecurse   narrowphase/detail/traversal/traversal_recurse-inl.h:84-130 (left subtree before right, canStop
+//                      between the two)
+//   leaf test / budget narrowphase/detail/traversal/collision/mesh_collision_traversal_node-inl.h:527-620
+//   canStop            collision_request-inl.h:77-82
+// The reference's contact list is: the intersecting triangle pairs in the depth-first order of the BVTT, each
+// contributing 1 entry (binary mode) or <= 2 contact points (contact mode), cut after num_max_contacts entries.
+// That list does not depend on WHEN a box test is evaluated, only on the ORDER in which the leaf pairs are consumed.
+// So the warp keeps the query's BVTT front as a list in depth-first order (a shared-memory stack whose top is the
+// next node pair of the recursion) and works on its head breadth-wise:
+//   * BV round: the top <= 32 entries are popped; the leading run of leaf pairs -- nothing precedes them any more --
+//     moves to the leaf FIFO; the first <= 16 internal entries are replaced IN PLACE by those of their two children
+//     (firstOverSecond picks the side to split, left child first) whose boxes are not certainly disjoint -- two
+//     lanes per entry run the conservative FP32 box test of bounds_f32.cuh; everything else keeps its place.  Output
+//     positions come from two ballots (every entry yields 0, 1 or 2 entries).
+//   * leaf round (32 queued pairs, or the stack has run empty): 32 lanes run the exact FP64 intersect_Triangle (and
+//     the contact computation) at once; an ordered prefix count over the lanes gives every contact its index in the
+//     query's list, the budget cuts the list exactly where the reference's leaf test stops appending, and once it is
+//     exhausted the query ends (canStop).
+// Box tests that the sequential recursion would have skipped after its early stop are speculative work; they never
+// change a result.  Near the stack limit the warp expands one entry per round: plain depth first, whose growth is
+// bounded by the tree depths (checked on the host).
+//
+// Output: contacts are staged in a per-warp scratch (resident warps x stride x 64 B: L2-resident) and, when the query
+// retires, appended to the caller's dense pool with one atomic reservation: ONE launch per batch, no per-query
+// scratch, no scan / compaction passes.  Blocks therefore land in completion order; contact_offsets[i] names the
+// start of query i's block (see include/fclgpu.h).
+#pragma once
+#include "traversal.cuh"
+
+namespace fclgpu {
+
+constexpr int kOrdCap = 384;      // BVTT front entries per warp
+constexpr int kOrdLeafCap = 64;   // leaf FIFO (ring), power of two
+constexpr int kOrdWarps = 4;      // warps per block
+#ifndef FCLGPU_ORD_MINBLOCKS
+#define FCLGPU_ORD_MINBLOCKS 4
+#endif
+#ifndef FCLGPU_ORD_OUTOFLINE
+#define FCLGPU_ORD_OUTOFLINE 1
+#endif
+
+struct __align__(16) OrderedFront {
+  uint2 pair[kOrdCap];
+  uint2 leaf[kOrdLeafCap];
+  uint2 expand[32];
+  int base[16];
+  double tf1[12];  // pose of model 1 (contacts go to the world frame with it)
+  double rel[12];  // exact relative pose R = R1^T R2, T = R1^T (t2 - t1)
+};
+
+struct OrderedParams {
+  CollideParams C;             // models, poses, request, num_contacts, counters, status, ready flags
+  fclgpu_contact* pool;        // caller's dense contact array (or nullptr: counts + offsets only)
+  long long pool_capacity;
+  unsigned long long* cursor;  // running number of contacts appended to the pool
+  long long* starts;           // [n] start of query i's block in the pool (or nullptr)
+  int depth_sum;               // depth(model1) + depth(model2)
+};
+
+template <bool kStats>
+__global__ void __launch_bounds__(kOrdWarps * 32, FCLGPU_ORD_MINBLOCKS) collide_ordered_kernel(OrderedParams Q) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  OrderedFront& S = reinterpret_cast<OrderedFront*>(smem_raw)[threadIdx.x >> 5];
+  const CollideParams& P = Q.C;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const long long gwarp = (long long)blockIdx.x * kOrdWarps + (threadIdx.x >> 5);
+  fclgpu_contact* const stage = P.scratch ? P.scratch + gwarp * P.stride : nullptr;
+  // a normal round adds at most 16 entries; the depth-first fallback at most depth_sum + 1 in total
+  const int normal_limit = kOrdCap - (Q.depth_sum + 2) - 16;
+  const bool coherent = P.ready != nullptr;
+
+  while (true) {
+    long long q = 0;
+    if (lane == 0) q = (long long)atomicAdd(P.work_counter, 1ull);
+    q = __shfl_sync(0xffffffffu, q, 0);
+    if (q >= P.n) break;
+    if (!wait_ready(P.ready, P.ready_shift, q + P.ready_q0) && lane == 0) atomicMin(P.status, (int)FCLGPU_ERR_INPUT_STALLED);
+
+    float Rf[9], Tf[3], t_l1;
+    {
+      const PoseRT tf1 = load_pose(P.tf1, q, coherent);
+      const PoseRT tf2 = load_pose(P.tf2, q, coherent);
+      const M3 R = mulTM(tf1.R, tf2.R);             // R1^T R2                 (math/geometry-inl.h:681-682)
+      const V3 T = mulTv(tf1.R, tf2.t - tf1.t);     // R1^T (t2 - t1)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) Rf[k] = (float)R.m[k];
+      Tf[0] = (float)T.x; Tf[1] = (float)T.y; Tf[2] = (float)T.z;
+      t_l1 = __double2float_ru((fabs(T.x) + fabs(T.y)) + fabs(T.z));
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          S.tf1[k] = tf1.R.m[k];
+          S.rel[k] = R.m[k];
+        }
+        S.tf1[9] = tf1.t.x; S.tf1[10] = tf1.t.y; S.tf1[11] = tf1.t.z;
+        S.rel[9] = T.x; S.rel[10] = T.y; S.rel[11] = T.z;
+      }
+    }
+
+    long long count = 0;
+    int sp = 0, nleaf = 0, head = 0;
+    uint32_t bv_tests = 1, leaf_tests = 0;
+    {  // root pair
+      const ObbRec32 n1 = load_obb32(P.m1.obb32, 0), n2 = load_obb32(P.m2.obb32, 0);
+      if (!obb_certainly_disjoint_f32(Rf, Tf, t_l1, n1, n2)) {
+        if (lane == 0) S.pair[0] = make_uint2(0u, 0u);
+        sp = 1;
+      }
+    }
+    __syncwarp();
+
+    while (true) {
+      if (nleaf >= 32 || (sp == 0 && nleaf > 0)) {
+        // ---- leaf round: the next <= 32 triangle pairs of the depth-first order ----
+        const int k = nleaf < 32 ? nleaf : 32;
+        const bool mine = lane < k;
+        uint2 ids = make_uint2(0u, 0u);
+        if (mine) ids = S.leaf[(head + lane) & (kOrdLeafCap - 1)];
+        head = (head + k) & (kOrdLeafCap - 1);
+        nleaf -= k;
+        int ncp = 0;  // entries this pair adds to the list: 1 per hit (binary mode) or its 0..2 contact points
+        V3 cp[2], nrm;
+        double depth = 0.0;
+        cp[0] = cp[1] = nrm = mk(0, 0, 0);
+        if (mine) {
+          M3 R;
+#pragma unroll
+          for (int c = 0; c < 9; ++c) R.m[c] = S.rel[c];
+          const V3 T = mk(S.rel[9], S.rel[10], S.rel[11]);
+          V3 Pt[3], Qt[3];
+          load_tri(P.m1.tri, (int)ids.x, Pt);
+          load_tri(P.m2.tri, (int)ids.y, Qt);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) Qt[c] = mulv(R, Qt[c]) + T;
+          const bool hit = FCLGPU_ORD_OUTOFLINE ? tri_intersect_outofline(Pt, Qt)
+                                                : tri_intersect(Pt[0], Pt[1], Pt[2], Qt[0], Qt[1], Qt[2]);
+          if (hit) {
+            ncp = 1;
+            if (P.enable_contact) {
+              unsigned nc;
+              if (FCLGPU_ORD_OUTOFLINE) tri_contact_info_outofline(Pt, Qt, cp, &nc, &depth, &nrm);
+              else tri_contact_info(Pt, Qt, cp, nc, depth, nrm);
+              ncp = (int)nc;
+            }
+          }
+        }
+        if (kStats) leaf_tests += k;
+        const unsigned m1 = __ballot_sync(0xffffffffu, ncp & 1), m2 = __ballot_sync(0xffffffffu, ncp >> 1);
+        const long long before = __popc(m1 & lt_mask) + 2 * __popc(m2 & lt_mask);
+        const long long total = __popc(m1) + 2 * __popc(m2);
+        const long long room = P.max_contacts - count;  // > 0 here
+        if (ncp > 0 && stage != nullptr && before < room) {
+          // mesh_collision_traversal_node-inl.h:594-600: a pair that does not fit entirely contributes its first points
+          int nw = ncp;
+          if (before + nw > room) nw = (int)(room - before);
+          M3 R1;
+          V3 t1 = mk(0, 0, 0), nw3 = mk(0, 0, 0);
+          if (P.enable_contact) {
+#pragma unroll
+            for (int c = 0; c < 9; ++c) R1.m[c] = S.tf1[c];
+            t1 = mk(S.tf1[9], S.tf1[10], S.tf1[11]);
+            nw3 = mulv(R1, nrm);  // tf1.linear() * n
+          }
+          for (int j = 0; j < nw; ++j) {
+            const long long slot = count + before + j;
+            if (slot < P.stride) {
+              fclgpu_contact* c = stage + slot;
+              c->b1 = (int)ids.x;
+              c->b2 = (int)ids.y;
+              if (P.enable_contact) {
+                const V3 pw = mulv(R1, cp[j]) + t1;  // tf1 * p
+                c->normal[0] = nw3.x; c->normal[1] = nw3.y; c->normal[2] = nw3.z;
+                c->pos[0] = pw.x; c->pos[1] = pw.y; c->pos[2] = pw.z;
+                c->penetration_depth = depth;
+              }
+            } else {
+              atomicMin(P.status, (int)FCLGPU_ERR_CONTACT_OVERFLOW);
+            }
+          }
+        }
+        count += total < room ? total : room;
+        __syncwarp();
+        if (count > 0 && P.max_contacts <= count) break;  // canStop(): everything still pending is dropped
+        continue;
+      }
+      if (sp == 0) break;
+
+      // ---- BV round on the head of the depth-first list ----
+      const bool tight = sp > normal_limit;
+      const int k = tight ? 1 : (sp < 32 ? sp : 32);
+      uint2 pr = make_uint2(0u, 0u);
+      int fc1 = 0, fc2 = 0;
+      double size1 = 0.0, size2 = 0.0;
+      const bool have = lane < k;
+      if (have) {
+        pr = S.pair[sp - 1 - lane];
+        load_topo(P.m1.topo, (int)pr.x, fc1, size1);
+        load_topo(P.m2.topo, (int)pr.y, fc2, size2);
+      }
+      const bool l1 = fc1 < 0, l2 = fc2 < 0;
+      const bool leafpair = have && l1 && l2;
+      const bool internal = have && !leafpair;
+      const unsigned im = __ballot_sync(0xffffffffu, internal);
+      const int lead = im ? (__ffs(im) - 1) : k;  // leaf pairs ahead of every internal entry: next in DFS order
+      if (lane < lead) S.leaf[(head + nleaf + lane) & (kOrdLeafCap - 1)] = make_uint2((unsigned)(-(fc1 + 1)), (unsigned)(-(fc2 + 1)));
+      nleaf += lead;
+      const int n_int = __popc(im), rank = __popc(im & lt_mask);
+      const int n_exp = n_int < 16 ? n_int : 16;
+      const bool expanded = internal && rank < n_exp;
+      __syncwarp();  // every lane holds its popped entry before slots are overwritten
+      if (expanded) {
+        if (l2 || (!l1 && (size1 > size2))) {  // firstOverSecond
+          S.expand[2 * rank] = make_uint2((unsigned)fc1, pr.y);
+          S.expand[2 * rank + 1] = make_uint2((unsigned)fc1 + 1u, pr.y);
+        } else {
+          S.expand[2 * rank] = make_uint2(pr.x, (unsigned)fc2);
+          S.expand[2 * rank + 1] = make_uint2(pr.x, (unsigned)fc2 + 1u);
+        }
+      }
+      __syncwarp();
+      bool keep = false;
+      uint2 xy = make_uint2(0u, 0u);
+      if (lane < 2 * n_exp) {
+        xy = S.expand[lane];
+        const ObbRec32 n1 = load_obb32(P.m1.obb32, (int)xy.x);
+        const ObbRec32 n2 = load_obb32(P.m2.obb32, (int)xy.y);
+        keep = !obb_certainly_disjoint_f32(Rf, Tf, t_l1, n1, n2);
+      }
+      if (kStats) bv_tests += 2 * n_exp;
+      const unsigned km = __ballot_sync(0xffffffffu, keep);
+      int cnt = 0;  // entries this popped entry leaves on the list
+      if (have && lane >= lead) cnt = expanded ? __popc((km >> (2 * rank)) & 3u) : 1;
+      const unsigned c1 = __ballot_sync(0xffffffffu, cnt & 1), c2 = __ballot_sync(0xffffffffu, cnt >> 1);
+      const int pre = __popc(c1 & lt_mask) + 2 * __popc(c2 & lt_mask);
+      const int new_sp = sp - k + __popc(c1) + 2 * __popc(c2);
+      if (have && lane >= lead) {
+        if (expanded) S.base[rank] = pre;
+        else S.pair[new_sp - 1 - pre] = pr;  // keeps its place
+      }
+      __syncwarp();
+      if (keep) {
+        const int p = S.base[lane >> 1] + ((lane & 1) ? (int)((km >> (lane - 1)) & 1u) : 0);  // left child first
+        S.pair[new_sp - 1 - p] = xy;
+      }
+      sp = new_sp;
+      __syncwarp();
+    }
+
+    // ---- retire: reserve the query's block in the dense pool and move the staged contacts there ----
+    if (lane == 0) {
+      P.num_contacts[q] = (int32_t)count;
+      if (kStats) {
+        if (P.n_bv) P.n_bv[q] = bv_tests;
+        if (P.n_leaf) P.n_leaf[q] = leaf_tests;
+      }
+    }
+    if (stage != nullptr) {
+      long long stored = count < P.stride ? count : P.stride;
+      unsigned long long off = 0;
+      if (lane == 0 && stored > 0) off = atomicAdd(Q.cursor, (unsigned long long)stored);
+      off = shfl_u64(off, 0);
+      if (lane == 0 && Q.starts) Q.starts[q] = (long long)off;
+      if (Q.pool != nullptr && stored > 0) {
+        if ((long long)off + stored > Q.pool_capacity) {
+          if (lane == 0) atomicMin(P.status, (int)FCLGPU_ERR_CONTACT_OVERFLOW);
+          stored = Q.pool_capacity > (long long)off ? Q.pool_capacity - (long long)off : 0;
+        }
+        const int4* src = reinterpret_cast<const int4*>(stage);
+        int4* dst = reinterpret_cast<int4*>(Q.pool + off);
+        for (long long i = lane; i < stored * 4; i += 32) dst[i] = src[i];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace fclgpu

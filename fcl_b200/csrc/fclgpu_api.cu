@@ -16,6 +16,7 @@
 #include "bvh_build.hpp"
 #include "records.hpp"
 #include "traversal.cuh"
+#include "collide_ordered.cuh"
 #include "refit.cuh"
 
 using namespace fclgpu;
@@ -67,7 +68,11 @@ std::map<std::string, long long> g_opts = {
     {"dist_spill_entries", 4096},  // per-warp global overflow entries of the distance front (allocated for big models)
     {"collide_front", 1},      // counts-only collide: warp-per-query front kernel (0 never, 1 big BVHs, 2 always)
     {"host_chunk", 1 << 17},   // queries per stage of the host API's two-stream copy/compute pipeline
-    {"contact_stride", 1024},  // per-query contact scratch slots when num_max_contacts is larger
+    {"contact_stride", 1024},  // contact staging slots per query (per resident warp on the ordered-front path) when num_max_contacts is larger
+    // layout of a contact list: 0 (default) = blocks appended in completion order by the one-launch ordered-front kernel
+    // (contact_offsets[i] = start of query i's block); 1 = blocks in query order (contact_offsets = exclusive prefix sum
+    // of num_contacts): per-query scratch + scan + compaction passes around the lane-per-query kernels
+    {"contact_order", 0},
     {"scratch_bytes", 2ll << 30},
     {"blocks_per_sm", 0},      // 0 = occupancy query
     {"stats", 1},
@@ -96,12 +101,21 @@ struct Workspace {
   int sm_count = 0;
   unsigned long long* counters = nullptr;  // ring of work counters (one per launch in flight)
   int counter_slots = 0, counter_next = 0;
-  int* status = nullptr;
+  // Sticky status word and running contact total PER STREAM (slot 0 doubles as the overflow slot when more than
+  // kStreamSlots streams are in use): concurrent *_batch calls on different streams neither mix their contact offsets
+  // nor report / clear each other's errors.
+  int* status_pool = nullptr;
+  long long* cursor_pool = nullptr;
+  std::map<cudaStream_t, int> stream_slot;
+  // The contact scratch and the distance front's overflow area are one allocation per device: launches that use them
+  // on DIFFERENT streams are ordered with an event (same-stream launches are ordered anyway).
+  cudaEvent_t scratch_ev = nullptr, spill_ev = nullptr;
+  cudaStream_t scratch_stream = nullptr, spill_stream = nullptr;
+  bool scratch_used = false, spill_used = false;
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
   void* scan_tmp = nullptr;
   size_t scan_bytes = 0;
-  long long* scan_base = nullptr;  // running contact offset across chunks
   // host-API staging (device side) and the two streams of the chunked copy/compute pipeline
   void* dev_io = nullptr;
   size_t dev_io_bytes = 0;
@@ -116,6 +130,7 @@ struct Workspace {
   std::mutex mu;       // held while enqueuing (work counters, scratch growth)
   std::mutex host_mu;  // held for a whole *_batch_host call: the staging buffers and pipeline streams are shared
 };
+constexpr int kStreamSlots = 64;
 constexpr int kReadySlots = 1 << 16;
 constexpr int kTotalSlots = 1 << 12;
 
@@ -138,9 +153,12 @@ int get_ws(int device, Workspace** out) {
   w->counter_slots = 4096;
   CUDA_TRY(cudaMalloc(&w->counters, sizeof(unsigned long long) * w->counter_slots));
   CUDA_TRY(cudaMemset(w->counters, 0, sizeof(unsigned long long) * w->counter_slots));
-  CUDA_TRY(cudaMalloc(&w->status, sizeof(int)));
-  CUDA_TRY(cudaMemset(w->status, 0, sizeof(int)));
-  CUDA_TRY(cudaMalloc(&w->scan_base, sizeof(long long)));
+  CUDA_TRY(cudaMalloc(&w->status_pool, sizeof(int) * kStreamSlots));
+  CUDA_TRY(cudaMemset(w->status_pool, 0, sizeof(int) * kStreamSlots));
+  CUDA_TRY(cudaMalloc(&w->cursor_pool, sizeof(long long) * kStreamSlots));
+  CUDA_TRY(cudaMemset(w->cursor_pool, 0, sizeof(long long) * kStreamSlots));
+  CUDA_TRY(cudaEventCreateWithFlags(&w->scratch_ev, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&w->spill_ev, cudaEventDisableTiming));
   CUDA_TRY(cudaMalloc(&w->ready, sizeof(unsigned) * kReadySlots));
   CUDA_TRY(cudaMemset(w->ready, 0, sizeof(unsigned) * kReadySlots));
   CUDA_TRY(cudaHostAlloc((void**)&w->host_one, sizeof(unsigned), cudaHostAllocDefault));
@@ -153,6 +171,32 @@ int get_ws(int device, Workspace** out) {
   g_ws[device] = w;
   *out = w;
   return 0;
+}
+
+// per-stream slot (caller holds w->mu)
+struct StreamState {
+  int* status;
+  long long* cursor;
+};
+StreamState stream_state(Workspace* w, cudaStream_t st) {
+  auto it = w->stream_slot.find(st);
+  int slot;
+  if (it != w->stream_slot.end()) {
+    slot = it->second;
+  } else {
+    slot = (int)w->stream_slot.size() + 1 < kStreamSlots ? (int)w->stream_slot.size() + 1 : 0;
+    w->stream_slot[st] = slot;
+  }
+  return StreamState{w->status_pool + slot, w->cursor_pool + slot};
+}
+// order a launch that uses a per-device buffer after the previous user of that buffer on ANOTHER stream
+void order_after(cudaStream_t st, cudaEvent_t ev, bool used, cudaStream_t last) {
+  if (used && last != st) cudaStreamWaitEvent(st, ev, 0);
+}
+void mark_use(cudaStream_t st, cudaEvent_t ev, bool& used, cudaStream_t& last) {
+  cudaEventRecord(ev, st);
+  used = true;
+  last = st;
 }
 
 int ensure(void** p, size_t* have, size_t want) {
@@ -727,6 +771,9 @@ unsigned long long* next_counter(Workspace* w, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------
 namespace {
 // Hidden knobs of the host wrappers around collide_enqueue.
+long long stage_capacity(const fclgpu_collision_request* r) {
+  return r->stage_capacity > 0 ? (long long)r->stage_capacity : std::max<long long>(1, opt("contact_stride"));
+}
 struct CollideExtra {
   const unsigned* ready = nullptr;  // streamed input: per-chunk "poses have landed" flags (see wait_ready)
   int ready_shift = 0;
@@ -778,10 +825,64 @@ int collide_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, c
   }
   const bool want_contacts = contacts != nullptr || contact_offsets != nullptr;
   const bool stats = (n_bv || n_leaf);
+  const StreamState ss = stream_state(w, st);
+  const long long trav0 = opt("traversal");
+
+  if (want_contacts && trav0 >= 3 && !opt("contact_order") && X.sphere_radius < 0) {
+    // Contact list, default path: ONE launch of the warp-per-query ordered-front kernel (collide_ordered.cuh).
+    // Contacts are staged per RESIDENT WARP (L2-resident) and appended to the caller's pool when a query retires.
+    const long long stride = std::min<long long>(request->num_max_contacts, stage_capacity(request));
+    const size_t smem = sizeof(OrderedFront) * kOrdWarps;
+    auto kern = stats ? collide_ordered_kernel<true> : collide_ordered_kernel<false>;
+    int per_sm = (int)opt("blocks_per_sm");
+    if (per_sm <= 0) {
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kOrdWarps * 32, smem));
+      if (per_sm < 1) per_sm = 1;
+    }
+    const long long warps = (long long)w->sm_count * per_sm * kOrdWarps;
+    rc = ensure(&w->scratch, &w->scratch_bytes, (size_t)(warps * stride) * sizeof(fclgpu_contact));
+    if (rc) return rc;
+    if (!X.continue_scan) CUDA_TRY(cudaMemsetAsync(ss.cursor, 0, sizeof(long long), st));
+    order_after(st, w->scratch_ev, w->scratch_used, w->scratch_stream);
+    OrderedParams Q;
+    CollideParams& P = Q.C;
+    P.m1 = m1->d;
+    P.m2 = m2->d;
+    P.tf1 = tf1;
+    P.tf2 = tf2;
+    P.n = n;
+    P.max_contacts = request->num_max_contacts;
+    P.enable_contact = request->enable_contact ? 1 : 0;
+    P.num_contacts = num_contacts;
+    P.scratch = (fclgpu_contact*)w->scratch;
+    P.stride = stride;
+    P.n_bv = n_bv;
+    P.n_leaf = n_leaf;
+    P.work_counter = next_counter(w, st);
+    P.status = ss.status;
+    P.ready = X.ready;
+    P.ready_shift = X.ready_shift;
+    P.ready_q0 = X.ready_q0;
+    Q.pool = contacts;
+    Q.pool_capacity = contacts ? contact_capacity : 0;
+    Q.cursor = (unsigned long long*)ss.cursor;
+    Q.starts = (long long*)contact_offsets;
+    Q.depth_sum = m1->depth + m2->depth;
+    kern<<<(unsigned)(w->sm_count * per_sm), kOrdWarps * 32, smem, st>>>(Q);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (contact_offsets) {
+      write_total_kernel<<<1, 1, 0, st>>>(ss.cursor, (long long*)contact_offsets + n);
+      g_launches++;
+    }
+    mark_use(st, w->scratch_ev, w->scratch_used, w->scratch_stream);
+    CUDA_TRY(cudaGetLastError());
+    return FCLGPU_OK;
+  }
 
   long long stride = 0, chunk = n;
   if (want_contacts) {
-    stride = std::min<long long>(request->num_max_contacts, std::max<long long>(1, opt("contact_stride")));
+    stride = std::min<long long>(request->num_max_contacts, stage_capacity(request));
     const long long budget = std::max<long long>(opt("scratch_bytes"), stride * (long long)sizeof(fclgpu_contact));
     chunk = std::max<long long>(1, std::min<long long>(n, budget / (stride * (long long)sizeof(fclgpu_contact))));
     rc = ensure(&w->scratch, &w->scratch_bytes, (size_t)(chunk * stride) * sizeof(fclgpu_contact));
@@ -789,7 +890,8 @@ int collide_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, c
     const long long nblk = (chunk + kScanBlock - 1) / kScanBlock;
     rc = ensure(&w->scan_tmp, &w->scan_bytes, (size_t)(chunk + nblk) * sizeof(long long));
     if (rc) return rc;
-    if (!X.continue_scan) CUDA_TRY(cudaMemsetAsync(w->scan_base, 0, sizeof(long long), st));
+    if (!X.continue_scan) CUDA_TRY(cudaMemsetAsync(ss.cursor, 0, sizeof(long long), st));
+    order_after(st, w->scratch_ev, w->scratch_used, w->scratch_stream);
   }
 
   for (long long s = 0; s < n; s += chunk) {
@@ -808,11 +910,11 @@ int collide_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, c
     P.n_bv = n_bv ? n_bv + s : nullptr;
     P.n_leaf = n_leaf ? n_leaf + s : nullptr;
     P.work_counter = next_counter(w, st);
-    P.status = w->status;
+    P.status = ss.status;
     P.ready = X.ready;
     P.ready_shift = X.ready_shift;
     P.ready_q0 = X.ready_q0 + s;
-    const long long trav = opt("traversal");
+    const long long trav = trav0;
     const int trig = (int)opt("leaf_trigger");
     const long long front = opt("collide_front");  // 0 never, 1 (default) for BVHs beyond the caches, 2 always
     if (X.sphere_radius >= 0) {
@@ -857,19 +959,20 @@ int collide_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, c
       long long* bsums = local + cn;
       const int nblk = (int)((cn + kScanBlock - 1) / kScanBlock);
       scan_block_kernel<<<nblk, kScanBlock, 0, st>>>(num_contacts + s, cn, stride, local, bsums);
-      scan_sums_kernel<<<1, kScanBlock, 0, st>>>(bsums, nblk, w->scan_base, nullptr);
+      scan_sums_kernel<<<1, kScanBlock, 0, st>>>(bsums, nblk, ss.cursor, nullptr);
       const long long threads = cn * 32;
       compact_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
           num_contacts + s, cn, stride, local, bsums, (const fclgpu_contact*)w->scratch, contacts, contact_capacity,
-          contact_offsets ? (long long*)contact_offsets + s : nullptr, w->status);
+          contact_offsets ? (long long*)contact_offsets + s : nullptr, ss.status);
       g_launches += 3;
       CUDA_TRY(cudaGetLastError());
     }
   }
   if (want_contacts && contact_offsets) {
-    write_total_kernel<<<1, 1, 0, st>>>(w->scan_base, (long long*)contact_offsets + n);
+    write_total_kernel<<<1, 1, 0, st>>>(ss.cursor, (long long*)contact_offsets + n);
     g_launches++;
   }
+  if (want_contacts) mark_use(st, w->scratch_ev, w->scratch_used, w->scratch_stream);
   CUDA_TRY(cudaGetLastError());
   return FCLGPU_OK;
 }
@@ -924,7 +1027,7 @@ int distance_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, 
   P.n_bv = n_bv;
   P.n_leaf = n_leaf;
   P.work_counter = next_counter(w, st);
-  P.status = w->status;
+  P.status = stream_state(w, st).status;
   P.spill_pair = nullptr;
   P.spill_bound = nullptr;
   P.spill_cap = 0;
@@ -949,6 +1052,8 @@ int distance_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, 
     P.spill_bound = w->spill_bound;
     P.spill_cap = cap;
     P.spill_warps = w->sm_count * 8 * kDistWarps;
+    // the area is indexed by the launch-local warp id: a launch on another stream must not overlap this one
+    order_after(st, w->spill_ev, w->spill_used, w->spill_stream);
   }
   const bool stats = (n_bv || n_leaf);
   if (sphere_radius >= 0) {
@@ -979,6 +1084,7 @@ int distance_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, 
     rc = stats ? launch_persistent(distance_thread_kernel<true>, P, w, 128, st)
                : launch_persistent(distance_thread_kernel<false>, P, w, 128, st);
   }
+  if (P.spill_pair) mark_use(st, w->spill_ev, w->spill_used, w->spill_stream);
   return rc;
 }
 }  // namespace
@@ -1020,10 +1126,15 @@ extern "C" int fclgpu_sync_status(int device, void* stream) {
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(device));
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  int* word;
+  {
+    std::lock_guard<std::mutex> lock(w->mu);
+    word = stream_state(w, (cudaStream_t)stream).status;
+  }
   int s = 0;
-  CUDA_TRY(cudaMemcpy(&s, w->status, sizeof(int), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(&s, word, sizeof(int), cudaMemcpyDeviceToHost));
   if (s != 0) {
-    CUDA_TRY(cudaMemset(w->status, 0, sizeof(int)));
+    CUDA_TRY(cudaMemset(word, 0, sizeof(int)));
     return fail(s, s == FCLGPU_ERR_CONTACT_OVERFLOW ? "contact capacity exceeded (counts are exact; raise contact "
                                                       "capacity or the contact_stride option)"
                    : s == FCLGPU_ERR_INPUT_STALLED  ? "a pose chunk did not reach the device in time (host API input stream)"
@@ -1050,9 +1161,10 @@ namespace {
 // queries per pipeline stage of the host API: option "host_chunk" (default 1 << 17 = 12.6 MB of poses)
 static int64_t host_chunk() { return std::max<long long>(1024, opt("host_chunk")); }
 
-int finish_pipeline(Workspace* w, int device) {
-  CUDA_TRY(cudaStreamSynchronize(w->pipe[0]));
-  return fclgpu_sync_status(device, w->pipe[1]);
+int finish_pipeline(Workspace* w, int device) {  // both pipeline streams may have run kernels (distance alternates)
+  const int r0 = fclgpu_sync_status(device, w->pipe[0]);
+  const int r1 = fclgpu_sync_status(device, w->pipe[1]);
+  return r0 ? r0 : r1;
 }
 }  // namespace
 
@@ -1155,6 +1267,11 @@ extern "C" int fclgpu_collide_batch_host(const fclgpu_model* m1, const fclgpu_mo
       if (tf2) CUDA_TRY(cudaMemcpyAsync(d_tf2 + 12 * s, tf2 + 12 * s, 96 * cn, cudaMemcpyHostToDevice, copy));
       CUDA_TRY(cudaMemcpyAsync(w->ready + c, w->host_one, sizeof(unsigned), cudaMemcpyHostToDevice, copy));
     }
+    long long* cursor_of_compute;
+    {
+      std::lock_guard<std::mutex> lock(w->mu);
+      cursor_of_compute = stream_state(w, compute).cursor;
+    }
     int64_t done = 0;  // contacts already on their way to the host
     auto drain = [&](int k) -> int {  // copy sub-batch k's contact range once its running total is known
       CUDA_TRY(cudaEventSynchronize(w->ev[k & 1]));
@@ -1180,7 +1297,7 @@ extern "C" int fclgpu_collide_batch_host(const fclgpu_model* m1, const fclgpu_mo
         cudaStreamSynchronize(compute);
         return rc;
       }
-      CUDA_TRY(cudaMemcpyAsync(w->host_totals + k, w->scan_base, sizeof(long long), cudaMemcpyDeviceToHost, compute));
+      CUDA_TRY(cudaMemcpyAsync(w->host_totals + k, cursor_of_compute, sizeof(long long), cudaMemcpyDeviceToHost, compute));
       CUDA_TRY(cudaEventRecord(w->ev[k & 1], compute));
       if (k >= 1 && (rc = drain(k - 1))) return rc;
     }

@@ -116,7 +116,12 @@ struct PoseRT {
   V3 t;
 };
 
-__device__ __forceinline__ PoseRT load_pose(const double* __restrict__ tf, long long i) {
+// kCoherent: the streamed host path (CollideParams::ready) has the copy engine write the pose buffer WHILE the kernel
+// runs; wait_ready's acquire load orders ordinary loads only, and ld.global.nc (__ldg) assumes data that is read-only for
+// the kernel's lifetime.  Those kernels therefore read poses with ld.global.cg (coherent at L2, never from L1/texture);
+// resident inputs keep the non-coherent path.
+__device__ __forceinline__ double2 ld_pose16(const double2* p, bool coherent) { return coherent ? __ldcg(p) : __ldg(p); }
+__device__ __forceinline__ PoseRT load_pose(const double* __restrict__ tf, long long i, bool coherent = false) {
   PoseRT p;
   if (tf == nullptr) {
 #pragma unroll
@@ -124,7 +129,8 @@ __device__ __forceinline__ PoseRT load_pose(const double* __restrict__ tf, long 
     p.t = mk(0, 0, 0);
   } else {
     const double2* q = reinterpret_cast<const double2*>(tf + 12 * i);  // 96 B records, 16-B aligned
-    double2 v0 = __ldg(q + 0), v1 = __ldg(q + 1), v2 = __ldg(q + 2), v3 = __ldg(q + 3), v4 = __ldg(q + 4), v5 = __ldg(q + 5);
+    double2 v0 = ld_pose16(q + 0, coherent), v1 = ld_pose16(q + 1, coherent), v2 = ld_pose16(q + 2, coherent);
+    double2 v3 = ld_pose16(q + 3, coherent), v4 = ld_pose16(q + 4, coherent), v5 = ld_pose16(q + 5, coherent);
     p.R.m[0] = v0.x; p.R.m[1] = v0.y; p.R.m[2] = v1.x; p.R.m[3] = v1.y; p.R.m[4] = v2.x;
     p.R.m[5] = v2.y; p.R.m[6] = v3.x; p.R.m[7] = v3.y; p.R.m[8] = v4.x;
     p.t = mk(v4.y, v5.x, v5.y);
@@ -220,8 +226,8 @@ __global__ void __launch_bounds__(128) collide_thread_kernel(CollideParams P) {
     if (need) {
       if (nq < P.n) {
         q = nq;
-        tf1 = load_pose(P.tf1, q);
-        const PoseRT tf2 = load_pose(P.tf2, q);
+        tf1 = load_pose(P.tf1, q, P.ready != nullptr);
+        const PoseRT tf2 = load_pose(P.tf2, q, P.ready != nullptr);
         R = mulTM(tf1.R, tf2.R);                    // R1^T R2
         T = mulTv(tf1.R, tf2.t - tf1.t);            // R1^T (t2 - t1)
         count = 0;
@@ -985,8 +991,8 @@ collide_deferred_kernel(CollideParams P, int leaf_trigger) {
     if (need) {
       if (nq < P.n) {
         q = nq;
-        tf1 = load_pose(P.tf1, q);
-        const PoseRT tf2 = load_pose(P.tf2, q);
+        tf1 = load_pose(P.tf1, q, P.ready != nullptr);
+        const PoseRT tf2 = load_pose(P.tf2, q, P.ready != nullptr);
         R = mulTM(tf1.R, tf2.R);
         T = mulTv(tf1.R, tf2.t - tf1.t);
         if (kSat32) {
@@ -1216,8 +1222,8 @@ __global__ void __launch_bounds__(128, FCLGPU_POOLED_MINBLOCKS) collide_pooled_k
     if (need) {
       if (nq < P.n) {
         q = nq;
-        const PoseRT tf1 = load_pose(P.tf1, q);
-        const PoseRT tf2 = load_pose(P.tf2, q);
+        const PoseRT tf1 = load_pose(P.tf1, q, P.ready != nullptr);
+        const PoseRT tf2 = load_pose(P.tf2, q, P.ready != nullptr);
         R = mulTM(tf1.R, tf2.R);
         T = mulTv(tf1.R, tf2.t - tf1.t);
 #pragma unroll
@@ -1262,8 +1268,8 @@ __global__ void __launch_bounds__(128, FCLGPU_POOLED_MINBLOCKS) collide_pooled_k
         const int slot = (S.head[owner] + (lane - S.excl[owner])) & (kPoolFifo - 1);
         const uint2 ids = S.fifo[slot][owner];
         const long long qo = S.pose[owner];
-        const PoseRT tf1 = load_pose(P.tf1, qo);
-        const PoseRT tf2 = load_pose(P.tf2, qo);
+        const PoseRT tf1 = load_pose(P.tf1, qo, P.ready != nullptr);
+        const PoseRT tf2 = load_pose(P.tf2, qo, P.ready != nullptr);
         const M3 Ro = mulTM(tf1.R, tf2.R);
         const V3 To = mulTv(tf1.R, tf2.t - tf1.t);
         V3 Pt[3], Qt[3];
@@ -1515,8 +1521,8 @@ __global__ void __launch_bounds__(128, 4) collide_front_kernel(CollideParams P) 
     M3 R;
     V3 T;
     {
-      const PoseRT tf1 = load_pose(P.tf1, q);
-      const PoseRT tf2 = load_pose(P.tf2, q);
+      const PoseRT tf1 = load_pose(P.tf1, q, P.ready != nullptr);
+      const PoseRT tf2 = load_pose(P.tf2, q, P.ready != nullptr);
       R = mulTM(tf1.R, tf2.R);
       T = mulTv(tf1.R, tf2.t - tf1.t);
     }

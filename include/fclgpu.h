@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define FCLGPU_ABI_VERSION 1
+#define FCLGPU_ABI_VERSION 2 /* 2: contact_offsets[i] = start of query i's block (order of the blocks: see below) */
 
 /* Status codes.  -1..-8 mirror the reference's BVHReturnCode
  * (include/fcl/geometry/bvh/BVH_internal.h:61-72). */
@@ -78,6 +78,11 @@ typedef struct fclgpu_collision_request {
   int64_t num_max_contacts; /* default 1; 0 -> every query returns 0 contacts (collision-inl.h:111-115) */
   int32_t enable_contact;   /* default 0 */
   int32_t enable_cost;      /* must be 0 */
+  /* Not an fcl::CollisionRequest field: contact slots staged per query before they reach the pool when a contact
+   * list is requested.  0 = library default (option "contact_stride", 1024).  A query with more contacts than
+   * min(num_max_contacts, stage_capacity) reports FCLGPU_ERR_CONTACT_OVERFLOW (counts stay exact): rerun with
+   * stage_capacity = max(num_contacts).  Per call, so concurrent callers do not share a setting. */
+  int64_t stage_capacity;
 } fclgpu_collision_request;
 
 /* Honoured fields of fcl::DistanceRequest (include/fcl/narrowphase/distance_request.h:52-113).
@@ -169,9 +174,14 @@ int fclgpu_model_device(const fclgpu_model* m);
  * with a fresh result_i (collision-inl.h:95-207 -> orientedMeshCollide,
  * collision_func_matrix-inl.h:571-590).
  *   num_contacts[i]  = result_i.numContacts()
- *   contacts         : query i's contacts, in the reference's DFS order, at
- *                      contacts[contact_offsets[i] .. contact_offsets[i+1]) (compacted).
- *   contact_offsets  : n+1 entries (exclusive prefix sum of num_contacts); may be NULL
+ *   contacts         : dense pool; query i's contacts, in the reference's DFS order, occupy the contiguous block
+ *                      contacts[contact_offsets[i] .. contact_offsets[i] + num_contacts[i]).  Blocks are disjoint and
+ *                      fill [0, contact_offsets[n]) without gaps.  In the reference every query has its own
+ *                      CollisionResult, so the ORDER OF THE BLOCKS is not reference semantics: by default (option
+ *                      "contact_order" = 0) each block is appended when its query retires on the GPU -- one kernel
+ *                      launch, one DRAM write per contact; with "contact_order" = 1 blocks come in query order and
+ *                      contact_offsets is the exclusive prefix sum of num_contacts (scan + compaction passes).
+ *   contact_offsets  : n+1 entries (start of each query's block; [n] = total number of contacts); may be NULL
  *                      together with contacts when only counts/verdicts are wanted.
  *   contact_capacity : slots available in `contacts`.
  *   n_bv / n_leaf    : optional per-query counters (num_bv_tests / num_leaf_tests of the

@@ -91,7 +91,7 @@ inline void collide(const DeviceModel& o1, const std::vector<fcl::Transform3<dou
     to_pose(tf2[i], &p2[12 * i]);
   }
   fclgpu_collision_request req{(int64_t)std::min<std::size_t>(request.num_max_contacts, (std::size_t)1 << 62),
-                               request.enable_contact ? 1 : 0, request.enable_cost ? 1 : 0};
+                               request.enable_contact ? 1 : 0, request.enable_cost ? 1 : 0, 0};
   std::vector<int32_t> counts(n);
   std::vector<int64_t> off(n + 1);
   int64_t cap = std::max<int64_t>(64 * n, 1024);
@@ -102,14 +102,14 @@ inline void collide(const DeviceModel& o1, const std::vector<fcl::Transform3<dou
     cap = 0;
     int32_t mx = 1;
     for (int32_t c : counts) { cap += c; mx = std::max(mx, c); }
-    if (mx > fclgpu_get_option("contact_stride")) fclgpu_set_option("contact_stride", mx);
+    req.stage_capacity = mx;  // per call: the reference is re-entrant, so no process-wide setting is touched
     pool.resize(cap);
     rc = fclgpu_collide_batch_host(o1.handle(), o2.handle(), n, p1.data(), p2.data(), &req, counts.data(), pool.data(),
                                    cap, off.data(), nullptr, nullptr);
   }
   check(rc);
   for (int64_t i = 0; i < n; ++i)
-    for (int64_t k = off[i]; k < off[i + 1]; ++k) {
+    for (int64_t k = off[i]; k < off[i] + counts[i]; ++k) {
       const fclgpu_contact& c = pool[k];
       if (request.enable_contact)
         results[i].addContact(fcl::Contact<double>(o1.host(), o2.host(), c.b1, c.b2,
@@ -135,7 +135,7 @@ inline void collide(const DeviceModel& o1, const std::vector<fcl::Transform3<dou
     to_pose(tf2[i], &p2[12 * i]);
   }
   fclgpu_collision_request req{(int64_t)std::min<std::size_t>(request.num_max_contacts, (std::size_t)1 << 62),
-                               request.enable_contact ? 1 : 0, request.enable_cost ? 1 : 0};
+                               request.enable_contact ? 1 : 0, request.enable_cost ? 1 : 0, 0};
   std::vector<int32_t> counts(n);
   std::vector<int64_t> off(n + 1);
   int64_t cap = std::max<int64_t>(64 * n, 1024);
@@ -146,14 +146,14 @@ inline void collide(const DeviceModel& o1, const std::vector<fcl::Transform3<dou
     cap = 0;
     int32_t mx = 1;
     for (int32_t c : counts) { cap += c; mx = std::max(mx, c); }
-    if (mx > fclgpu_get_option("contact_stride")) fclgpu_set_option("contact_stride", mx);
+    req.stage_capacity = mx;  // per call: the reference is re-entrant, so no process-wide setting is touched
     pool.resize(cap);
     rc = fclgpu_collide_mesh_sphere_batch_host(o1.handle(), sphere.radius, n, p1.data(), p2.data(), &req, counts.data(),
                                                pool.data(), cap, off.data(), nullptr, nullptr);
   }
   check(rc);
   for (int64_t i = 0; i < n; ++i)
-    for (int64_t k = off[i]; k < off[i + 1]; ++k) {
+    for (int64_t k = off[i]; k < off[i] + counts[i]; ++k) {
       const fclgpu_contact& c = pool[k];
       if (request.enable_contact)
         results[i].addContact(fcl::Contact<double>(o1.host(), &sphere, c.b1, fcl::Contact<double>::NONE,

@@ -361,3 +361,70 @@ def tri_distance(S, T):
     Q = np.zeros(3)
     d = lib().orc_tri_distance(_dp(S), _dp(T), _dp(P), _dp(Q))
     return float(d), P, Q
+
+
+# ------------------------------------------------------------------------------------------------
+# executed-operation counters (fcl_oracle_counted.cpp): the oracle recompiled over a counting scalar
+# ------------------------------------------------------------------------------------------------
+_CNT_PATH = os.path.join(_HERE, "_build", "liboracle_counted.so")
+_cnt = None
+OP_NAMES = ("mul", "add", "cmp", "div", "sqrt")
+
+
+def counted_lib():
+    global _cnt
+    if _cnt is None:
+        build()
+        if not os.path.exists(_CNT_PATH):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "_build/liboracle_counted.so"])
+        L = C.CDLL(_CNT_PATH)
+        vp, dp, ip, lp = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_longlong)
+        L.orcc_model.restype = vp
+        L.orcc_model.argtypes = [dp, C.c_int, ip, C.c_int]
+        L.orcc_model_free.argtypes = [vp]
+        L.orcc_collide.argtypes = [vp, vp, dp, dp, C.c_longlong, C.c_longlong, C.c_int, C.c_int, lp, lp, lp, dp]
+        L.orcc_distance.argtypes = [vp, vp, dp, dp, C.c_longlong, C.c_int, C.c_int, lp, lp, lp, dp]
+        _cnt = L
+    return _cnt
+
+
+class CountedModel:
+    """A model of the counting build (its BVH is built with the same arithmetic, so it equals Model's)."""
+
+    def __init__(self, verts, tris):
+        v = np.ascontiguousarray(verts, np.float64)
+        t = np.ascontiguousarray(tris, np.int32)
+        self._h = counted_lib().orcc_model(_dp(v), len(v), _ip(t), len(t))
+        self._owner = None
+
+    @classmethod
+    def share(cls, model):
+        """The counting scalar is a struct holding one double, so a Model built by the plain library has the very
+        same layout: large meshes (cfg4 / cfg5) are built once and read by both builds."""
+        counted_lib()
+        m = cls.__new__(cls)
+        m._h, m._owner = model.h, model
+        return m
+
+    def __del__(self):
+        if getattr(self, "_h", None) and getattr(self, "_owner", None) is None and _cnt is not None:
+            _cnt.orcc_model_free(self._h)
+        self._h = None
+
+
+def counted_query(kind, m1, m2, tf1, tf2=None, num_max_contacts=1, enable_contact=False, enable_nearest_points=True,
+                  nthreads=1):
+    """kind = 'collide' | 'distance'.  Returns ops[n,5] (executed mul, add, cmp, div, sqrt per query of the reference's
+    sequential traversal), n_bv[n], n_leaf[n], value[n] (numContacts / min_distance)."""
+    tf1, tf2 = _poses(tf1), _poses(tf2)
+    n = len(tf1) if tf1 is not None else len(tf2)
+    ops = np.zeros((n, 5), np.int64)
+    nbv, nleaf, val = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n, np.float64)
+    L = counted_lib()
+    if kind == "collide":
+        L.orcc_collide(m1._h, m2._h, _dp(tf1), _dp(tf2), n, int(min(num_max_contacts, 2**62)), int(enable_contact),
+                       int(nthreads), _lp(ops), _lp(nbv), _lp(nleaf), _dp(val))
+    else:
+        L.orcc_distance(m1._h, m2._h, _dp(tf1), _dp(tf2), n, int(enable_nearest_points), int(nthreads), _lp(ops),
+                        _lp(nbv), _lp(nleaf), _dp(val))
+    return {"ops": ops, "n_bv": nbv, "n_leaf": nleaf, "value": val}
