@@ -66,7 +66,8 @@ std::map<std::string, long long> g_opts = {
     // 0: thread per query, the reference's visiting order exactly (work counters match the reference's)
     {"traversal", 3},
     {"dist_spill_entries", 4096},  // per-warp global overflow entries of the distance front (allocated for big models)
-    {"collide_front", 1},      // counts-only collide: warp-per-query front kernel (0 never, 1 big BVHs, 2 always)
+    {"collide_front", 1},      // counts-only collide: warp-per-query front kernel (0 never, 1 big BVHs and small batches, 2 always)
+    {"front_small_batch", 131072},  // ... batches of at most this many queries count as small
     {"host_chunk", 1 << 17},   // queries per stage of the host API's two-stream copy/compute pipeline
     {"contact_stride", 1024},  // contact staging slots per query (per resident warp on the ordered-front path) when num_max_contacts is larger
     // layout of a contact list: 0 (default) = blocks appended in completion order by the one-launch ordered-front kernel
@@ -921,8 +922,11 @@ int collide_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, c
       rc = stats ? launch_persistent(collide_mesh_sphere_kernel<true>, P, w, 128, st, 0, X.sphere_radius)
                  : launch_persistent(collide_mesh_sphere_kernel<false>, P, w, 128, st, 0, X.sphere_radius);
     } else if (!want_contacts && !P.enable_contact && trav >= 1 &&
-        (front >= 2 || (front == 1 && (long long)m1->d.n_nodes + m2->d.n_nodes >= (1 << 17)))) {
-      // counts only: the result does not depend on the visiting order -> warp-per-query front kernel
+        (front >= 2 || (front == 1 && ((long long)m1->d.n_nodes + m2->d.n_nodes >= (1 << 17) || cn <= opt("front_small_batch"))))) {
+      // counts only: the result does not depend on the visiting order -> warp-per-query front kernel.  Chosen for BVHs
+      // beyond the caches (memory-level parallelism) and for SMALL batches: a lane-per-query launch cannot end before
+      // its longest query (~0.8 ms on env/rob), a warp-per-query launch spreads every query over 32 lanes
+      // (BASELINE cfg1 at its real size, 10k poses: 0.83 ms -> 0.11 ms)
       const size_t fsm = sizeof(CollideFront) * 4;
       rc = stats ? launch_persistent(collide_front_kernel<true>, P, w, 128, st, fsm)
                  : launch_persistent(collide_front_kernel<false>, P, w, 128, st, fsm);

@@ -7,8 +7,12 @@
 //   * evaluates batches of (tf1, tf2) pairs and fills std::vector<fcl::CollisionResult<double>>
 //     / std::vector<fcl::DistanceResult<double>>,
 //   * offers single-query functions with the exact signature of the reference's dispatch-table
-//     cell (detail/collision_func_matrix.h:67-78, detail/distance_func_matrix.h:65-76) so they
-//     can be installed in collision_matrix[BV_OBBRSS][BV_OBBRSS] / distance_matrix[..][..].
+//     cell -- collide_cell<Solver> / distance_cell<Solver> (and the mesh-vs-sphere pair) are
+//     CollisionFunc / DistanceFunc (detail/collision_func_matrix.h:67-78,
+//     detail/distance_func_matrix.h:65-76) -- and install<Solver>() / uninstall<Solver>(), which
+//     put them into collision_matrix[BV_OBBRSS][BV_OBBRSS] / distance_matrix[..][..] (and the
+//     [BV_OBBRSS][GEOM_SPHERE] cells) of the look-up tables fcl::collide / fcl::distance dispatch
+//     through (collision-inl.h:72-76, distance-inl.h:65-69).
 #pragma once
 #include "../fclgpu.h"
 
@@ -22,7 +26,9 @@
 #include <fcl/fcl.h>
 
 #include <algorithm>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <cmath>
@@ -66,23 +72,57 @@ class DeviceModel {
         for (int c = 0; c < 3; ++c) tv[9 * t + 3 * k + c] = m.vertices[m.tri_indices[t][k]][c];
     check(fclgpu_model_create_obbrss(device, n, fc.data(), axis.data(), oT.data(), oe.data(), rT.data(), rl.data(),
                                      rr.data(), nt, tv.data(), &h_));
+    // Refit topology.  BVHModel::primitive_indices is private (BVH_model.h:191), but the public node fields give it
+    // back: node i owns primitive_indices[first_primitive .. first_primitive + num_primitives), a leaf owns exactly one
+    // slot and names its triangle in first_child, so every slot is written by exactly one leaf.
+    std::vector<int32_t> first(n), count(n), prim(nt, -1), tidx(3 * (std::size_t)nt);
+    bool ok = m.num_vertices > 0;
+    for (int i = 0; i < n; ++i) {
+      const auto& node = m.getBV(i);
+      first[i] = node.first_primitive;
+      count[i] = node.num_primitives;
+      if (node.first_child < 0) {
+        if (node.first_primitive < 0 || node.first_primitive >= nt) ok = false;
+        else prim[node.first_primitive] = -(node.first_child + 1);
+      }
+    }
+    for (int t = 0; t < nt; ++t) {
+      if (prim[t] < 0) ok = false;
+      for (int k = 0; k < 3; ++k) tidx[3 * (std::size_t)t + k] = (int32_t)m.tri_indices[t][k];
+    }
+    if (ok) refit_ready_ = fclgpu_model_set_partition(h_, m.num_vertices, tidx.data(), first.data(), count.data(), prim.data()) == FCLGPU_OK;
   }
   ~DeviceModel() { fclgpu_model_destroy(h_); }
   DeviceModel(const DeviceModel&) = delete;
   DeviceModel& operator=(const DeviceModel&) = delete;
   const fclgpu_model* handle() const { return h_; }
   const BVH* host() const { return host_; }
+  // endReplaceModel(refit = true, bottomup = false) on the device copy: `vertices` = the host model's updated array
+  bool refit_ready() const { return refit_ready_; }
+  void refit_topdown() {
+    std::vector<double> v(3 * (std::size_t)host_->num_vertices);
+    for (int i = 0; i < host_->num_vertices; ++i)
+      for (int c = 0; c < 3; ++c) v[3 * (std::size_t)i + c] = host_->vertices[i][c];
+    check(fclgpu_model_refit_topdown(h_, v.data(), host_->num_vertices, 0, nullptr));
+    check(fclgpu_sync_status(fclgpu_model_device(h_), nullptr));
+  }
 
  private:
   const BVH* host_;
   fclgpu_model* h_ = nullptr;
+  bool refit_ready_ = false;
 };
+
+inline void same_size(std::size_t a, std::size_t b) {
+  if (a != b) throw std::invalid_argument("fclgpu: tf1 and tf2 must have the same length");
+}
 
 // n independent fcl::collide(o1, tf1[i], o2, tf2[i], request, results[i]) calls
 inline void collide(const DeviceModel& o1, const std::vector<fcl::Transform3<double>>& tf1, const DeviceModel& o2,
                     const std::vector<fcl::Transform3<double>>& tf2, const fcl::CollisionRequest<double>& request,
                     std::vector<fcl::CollisionResult<double>>& results) {
   const int64_t n = (int64_t)tf1.size();
+  same_size(tf1.size(), tf2.size());
   results.assign(n, fcl::CollisionResult<double>());
   if (request.num_max_contacts == 0 || n == 0) return;
   std::vector<double> p1(12 * n), p2(12 * n);
@@ -127,6 +167,7 @@ inline void collide(const DeviceModel& o1, const std::vector<fcl::Transform3<dou
                     const std::vector<fcl::Transform3<double>>& tf2, const fcl::CollisionRequest<double>& request,
                     std::vector<fcl::CollisionResult<double>>& results) {
   const int64_t n = (int64_t)tf1.size();
+  same_size(tf1.size(), tf2.size());
   results.assign(n, fcl::CollisionResult<double>());
   if (request.num_max_contacts == 0 || n == 0) return;
   std::vector<double> p1(12 * n), p2(12 * n);
@@ -169,6 +210,7 @@ inline void distance(const DeviceModel& o1, const std::vector<fcl::Transform3<do
                      const std::vector<fcl::Transform3<double>>& tf2, const fcl::DistanceRequest<double>& request,
                      std::vector<fcl::DistanceResult<double>>& results) {
   const int64_t n = (int64_t)tf1.size();
+  same_size(tf1.size(), tf2.size());
   results.assign(n, fcl::DistanceResult<double>());
   if (n == 0) return;
   std::vector<double> p1(12 * n), p2(12 * n), d(n), a(3 * n), b(3 * n);
@@ -195,6 +237,7 @@ inline void distance(const DeviceModel& o1, const std::vector<fcl::Transform3<do
 inline void within_tolerance(const DeviceModel& o1, const std::vector<fcl::Transform3<double>>& tf1, const DeviceModel& o2,
                              const std::vector<fcl::Transform3<double>>& tf2, double tolerance, std::vector<char>& within) {
   const int64_t n = (int64_t)tf1.size();
+  same_size(tf1.size(), tf2.size());
   within.assign(n, 0);
   if (n == 0) return;
   std::vector<double> p1(12 * n), p2(12 * n), d(n);
@@ -216,6 +259,7 @@ inline void distance(const DeviceModel& o1, const std::vector<fcl::Transform3<do
                      const std::vector<fcl::Transform3<double>>& tf2, const fcl::DistanceRequest<double>& request,
                      std::vector<fcl::DistanceResult<double>>& results) {
   const int64_t n = (int64_t)tf1.size();
+  same_size(tf1.size(), tf2.size());
   results.assign(n, fcl::DistanceResult<double>());
   if (n == 0) return;
   std::vector<double> p1(12 * n), p2(12 * n), d(n), a(3 * n), b(3 * n);
@@ -231,6 +275,165 @@ inline void distance(const DeviceModel& o1, const std::vector<fcl::Transform3<do
     results[i].update(d[i], o1.host(), &sphere, b1[i], fcl::DistanceResult<double>::NONE,
                       fcl::Vector3<double>(a[3 * i], a[3 * i + 1], a[3 * i + 2]),
                       fcl::Vector3<double>(b[3 * i], b[3 * i + 1], b[3 * i + 2]));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Single-query drop-in: the dispatch-table cells.
+// fcl::collide / fcl::distance look the pair (getNodeType(), getNodeType()) up in a table of function pointers
+// (collision-inl.h:95-150, distance-inl.h:92-190); the functions below have the cell signature (CollisionFunc,
+// detail/collision_func_matrix.h:67-78; DistanceFunc, detail/distance_func_matrix.h:65-76) and the cell semantics of
+// orientedMeshCollide / orientedMeshDistance (collision_func_matrix-inl.h:571-590, distance_func_matrix-inl.h:386-403):
+// early return when the request is already satisfied by the result, otherwise the query's contacts are APPENDED to the
+// caller's result (whose contacts count against num_max_contacts) / the result is updated when the distance is smaller.
+// A batch of one pays a launch and two PCIe copies: the batched overloads above are the product path, these make
+// unmodified single-query callers work.  Device copies of the models come from a process-wide cache keyed by the host
+// model's address (upload on first use; evict() when a model is rebuilt or destroyed).
+// ---------------------------------------------------------------------------------------------------------------------
+class ModelCache {
+ public:
+  DeviceModel& get(const BVH* m, int device = 0) {
+    std::lock_guard<std::mutex> g(mu_);
+    auto& slot = map_[std::make_pair(m, device)];
+    if (!slot) slot.reset(new DeviceModel(*m, device));
+    return *slot;
+  }
+  void evict(const BVH* m) {
+    std::lock_guard<std::mutex> g(mu_);
+    for (auto it = map_.begin(); it != map_.end();) it = (it->first.first == m) ? map_.erase(it) : std::next(it);
+  }
+  void clear() {
+    std::lock_guard<std::mutex> g(mu_);
+    map_.clear();
+  }
+
+ private:
+  std::mutex mu_;
+  std::map<std::pair<const BVH*, int>, std::unique_ptr<DeviceModel>> map_;
+};
+inline ModelCache& model_cache() {
+  static ModelCache c;
+  return c;
+}
+
+namespace detail {
+// the budget a non-empty result leaves (mesh_collision_traversal_node-inl.h:553-556, 594-600: addContact only while
+// request.num_max_contacts > result.numContacts())
+inline fcl::CollisionRequest<double> remaining(const fcl::CollisionRequest<double>& request, const fcl::CollisionResult<double>& result) {
+  fcl::CollisionRequest<double> sub(request);
+  sub.num_max_contacts = request.num_max_contacts - result.numContacts();
+  return sub;
+}
+inline void append(const fcl::CollisionResult<double>& from, fcl::CollisionResult<double>& to) {
+  for (std::size_t i = 0; i < from.numContacts(); ++i) to.addContact(from.getContact(i));
+}
+}  // namespace detail
+
+// collision_matrix[BV_OBBRSS][BV_OBBRSS]
+template <typename Solver>
+std::size_t collide_cell(const fcl::CollisionGeometry<double>* o1, const fcl::Transform3<double>& tf1,
+                         const fcl::CollisionGeometry<double>* o2, const fcl::Transform3<double>& tf2, const Solver*,
+                         const fcl::CollisionRequest<double>& request, fcl::CollisionResult<double>& result) {
+  if (request.isSatisfied(result)) return result.numContacts();  // collision_func_matrix-inl.h:580
+  if (request.num_max_contacts <= result.numContacts()) return result.numContacts();
+  const DeviceModel& m1 = model_cache().get(static_cast<const BVH*>(o1));
+  const DeviceModel& m2 = model_cache().get(static_cast<const BVH*>(o2));
+  std::vector<fcl::CollisionResult<double>> r;
+  collide(m1, {tf1}, m2, {tf2}, detail::remaining(request, result), r);
+  detail::append(r[0], result);
+  return result.numContacts();
+}
+
+// collision_matrix[BV_OBBRSS][GEOM_SPHERE] (BVHShapeCollider<OBBRSS, Sphere>, collision_func_matrix-inl.h:378-430)
+template <typename Solver>
+std::size_t collide_sphere_cell(const fcl::CollisionGeometry<double>* o1, const fcl::Transform3<double>& tf1,
+                                const fcl::CollisionGeometry<double>* o2, const fcl::Transform3<double>& tf2, const Solver*,
+                                const fcl::CollisionRequest<double>& request, fcl::CollisionResult<double>& result) {
+  if (request.isSatisfied(result)) return result.numContacts();  // collision_func_matrix-inl.h:389
+  if (request.num_max_contacts <= result.numContacts()) return result.numContacts();
+  const DeviceModel& m1 = model_cache().get(static_cast<const BVH*>(o1));
+  std::vector<fcl::CollisionResult<double>> r;
+  collide(m1, {tf1}, *static_cast<const fcl::Sphere<double>*>(o2), {tf2}, detail::remaining(request, result), r);
+  detail::append(r[0], result);
+  return result.numContacts();
+}
+
+// distance_matrix[BV_OBBRSS][BV_OBBRSS]
+template <typename Solver>
+double distance_cell(const fcl::CollisionGeometry<double>* o1, const fcl::Transform3<double>& tf1,
+                     const fcl::CollisionGeometry<double>* o2, const fcl::Transform3<double>& tf2, const Solver*,
+                     const fcl::DistanceRequest<double>& request, fcl::DistanceResult<double>& result) {
+  if (request.isSatisfied(result)) return result.min_distance;  // distance_func_matrix-inl.h:395
+  const DeviceModel& m1 = model_cache().get(static_cast<const BVH*>(o1));
+  const DeviceModel& m2 = model_cache().get(static_cast<const BVH*>(o2));
+  std::vector<fcl::DistanceResult<double>> r;
+  distance(m1, {tf1}, m2, {tf2}, request, r);
+  if (request.enable_nearest_points)
+    result.update(r[0].min_distance, o1, o2, r[0].b1, r[0].b2, r[0].nearest_points[0], r[0].nearest_points[1]);
+  else
+    result.update(r[0].min_distance, o1, o2, r[0].b1, r[0].b2);
+  return result.min_distance;
+}
+
+// distance_matrix[BV_OBBRSS][GEOM_SPHERE] (BVHShapeDistancer<OBBRSS, Sphere>, distance_func_matrix-inl.h:259-277, 322-341)
+template <typename Solver>
+double distance_sphere_cell(const fcl::CollisionGeometry<double>* o1, const fcl::Transform3<double>& tf1,
+                            const fcl::CollisionGeometry<double>* o2, const fcl::Transform3<double>& tf2, const Solver*,
+                            const fcl::DistanceRequest<double>& request, fcl::DistanceResult<double>& result) {
+  if (request.isSatisfied(result)) return result.min_distance;  // distance_func_matrix-inl.h:268
+  const DeviceModel& m1 = model_cache().get(static_cast<const BVH*>(o1));
+  std::vector<fcl::DistanceResult<double>> r;
+  distance(m1, {tf1}, *static_cast<const fcl::Sphere<double>*>(o2), {tf2}, request, r);
+  result.update(r[0].min_distance, o1, o2, r[0].b1, fcl::DistanceResult<double>::NONE, r[0].nearest_points[0], r[0].nearest_points[1]);
+  return result.min_distance;
+}
+
+// What install() replaced, so that uninstall() can put it back.
+template <typename Solver>
+struct InstalledCells {
+  typename fcl::detail::CollisionFunctionMatrix<Solver>::CollisionFunc collide_mesh = nullptr, collide_sphere = nullptr;
+  typename fcl::detail::DistanceFunctionMatrix<Solver>::DistanceFunc distance_mesh = nullptr, distance_sphere = nullptr;
+  bool installed = false;
+  static InstalledCells& saved() {
+    static InstalledCells s;
+    return s;
+  }
+};
+
+// Overwrites the four cells of the look-up tables of `Solver` (the public, non-const array members of the function-
+// local statics behind fcl::getCollisionFunctionLookTable / getDistanceFunctionLookTable).  Call once at start-up,
+// before other threads issue queries.  In a shared-library build of FCL with hidden visibility the library keeps its
+// own copy of the tables for the extern-template collide<double>(o1, tf1, o2, tf2, request, result); the overwrite then
+// reaches the calls instantiated in the caller's translation units (the solver-taking overloads), see INTEGRATION.md.
+template <typename Solver>
+void install() {
+  auto& c = fcl::getCollisionFunctionLookTable<Solver>();
+  auto& d = fcl::getDistanceFunctionLookTable<Solver>();
+  auto& s = InstalledCells<Solver>::saved();
+  if (!s.installed) {
+    s.collide_mesh = c.collision_matrix[fcl::BV_OBBRSS][fcl::BV_OBBRSS];
+    s.collide_sphere = c.collision_matrix[fcl::BV_OBBRSS][fcl::GEOM_SPHERE];
+    s.distance_mesh = d.distance_matrix[fcl::BV_OBBRSS][fcl::BV_OBBRSS];
+    s.distance_sphere = d.distance_matrix[fcl::BV_OBBRSS][fcl::GEOM_SPHERE];
+    s.installed = true;
+  }
+  c.collision_matrix[fcl::BV_OBBRSS][fcl::BV_OBBRSS] = &collide_cell<Solver>;
+  c.collision_matrix[fcl::BV_OBBRSS][fcl::GEOM_SPHERE] = &collide_sphere_cell<Solver>;
+  d.distance_matrix[fcl::BV_OBBRSS][fcl::BV_OBBRSS] = &distance_cell<Solver>;
+  d.distance_matrix[fcl::BV_OBBRSS][fcl::GEOM_SPHERE] = &distance_sphere_cell<Solver>;
+}
+
+template <typename Solver>
+void uninstall() {
+  auto& s = InstalledCells<Solver>::saved();
+  if (!s.installed) return;
+  auto& c = fcl::getCollisionFunctionLookTable<Solver>();
+  auto& d = fcl::getDistanceFunctionLookTable<Solver>();
+  c.collision_matrix[fcl::BV_OBBRSS][fcl::BV_OBBRSS] = s.collide_mesh;
+  c.collision_matrix[fcl::BV_OBBRSS][fcl::GEOM_SPHERE] = s.collide_sphere;
+  d.distance_matrix[fcl::BV_OBBRSS][fcl::BV_OBBRSS] = s.distance_mesh;
+  d.distance_matrix[fcl::BV_OBBRSS][fcl::GEOM_SPHERE] = s.distance_sphere;
+  s.installed = false;
+  model_cache().clear();
 }
 
 }  // namespace fclgpu

@@ -6,6 +6,12 @@
 // extent, l, r), math/triangle.h (operator[]), narrowphase/contact.h:48-91, collision_request.h:52-106,
 // collision_result.h (addContact / numContacts / getContact), distance_request.h:52-113,
 // distance_result.h (update overloads: only a smaller distance replaces the stored one).
+// The dispatch side is mocked too, so that the shim's cell functions can be installed and reached the way a real
+// caller reaches them: geometry/collision_geometry.h:53-54 (NODE_TYPE, getNodeType), narrowphase/detail/
+// collision_func_matrix.h:67-78 and distance_func_matrix.h:65-76 (the tables of function pointers),
+// collision-inl.h:72-76 / distance-inl.h:65-69 (the function-local static tables), collision-inl.h:95-150 /
+// distance-inl.h:92-190 (the solver-taking fcl::collide / fcl::distance that look the cell up), request isSatisfied
+// (collision_request-inl.h:77-82, distance_request-inl.h:73-77).
 // Nothing here computes anything; it is NOT a substitute for FCL.
 #pragma once
 #include <cstddef>
@@ -82,9 +88,15 @@ struct Triangle {
   std::size_t operator[](int i) const { return vids[i]; }
 };
 
+enum NODE_TYPE {BV_UNKNOWN, BV_AABB, BV_OBB, BV_RSS, BV_kIOS, BV_OBBRSS, BV_KDOP16, BV_KDOP18, BV_KDOP24,
+                GEOM_BOX, GEOM_SPHERE, GEOM_ELLIPSOID, GEOM_CAPSULE, GEOM_CONE, GEOM_CYLINDER, GEOM_CONVEX, GEOM_PLANE, GEOM_HALFSPACE, GEOM_TRIANGLE, GEOM_OCTREE, NODE_COUNT};
+enum OBJECT_TYPE {OT_UNKNOWN, OT_BVH, OT_GEOM, OT_OCTREE, OT_COUNT};
+
 template <typename S>
 struct CollisionGeometry {
   virtual ~CollisionGeometry() {}
+  virtual NODE_TYPE getNodeType() const { return BV_UNKNOWN; }
+  virtual OBJECT_TYPE getObjectType() const { return OT_UNKNOWN; }
 };
 
 template <typename BV>
@@ -92,6 +104,8 @@ struct BVHModel : CollisionGeometry<double> {
   Vector3<double>* vertices = nullptr;
   Triangle* tri_indices = nullptr;
   int num_tris = 0, num_vertices = 0;
+  NODE_TYPE getNodeType() const override { return BV_OBBRSS; }  // the mock only instantiates BVHModel<OBBRSS<double>>
+  OBJECT_TYPE getObjectType() const override { return OT_BVH; }
   int getNumBVs() const { return (int)bvs_.size(); }
   const BVNode<BV>& getBV(int i) const { return bvs_[i]; }
   // storage of the mock
@@ -105,6 +119,8 @@ template <typename S>
 struct Sphere : CollisionGeometry<S> {
   S radius;
   explicit Sphere(S r) : radius(r) {}
+  NODE_TYPE getNodeType() const override { return GEOM_SPHERE; }
+  OBJECT_TYPE getObjectType() const override { return OT_GEOM; }
 };
 
 template <typename S>
@@ -123,12 +139,16 @@ struct Contact {
 };
 
 template <typename S>
+struct CollisionResult;
+
+template <typename S>
 struct CollisionRequest {
   std::size_t num_max_contacts = 1;
   bool enable_contact = false;
   std::size_t num_max_cost_sources = 1;
   bool enable_cost = false;
   CollisionRequest(std::size_t n = 1, bool contact = false) : num_max_contacts(n), enable_contact(contact) {}
+  bool isSatisfied(const CollisionResult<S>& result) const;  // collision_request-inl.h:77-82
 };
 
 template <typename S>
@@ -141,10 +161,19 @@ struct CollisionResult {
 };
 
 template <typename S>
+bool CollisionRequest<S>::isSatisfied(const CollisionResult<S>& result) const {
+  return (!enable_cost) && result.isCollision() && (num_max_contacts <= result.numContacts());
+}
+
+template <typename S>
+struct DistanceResult;
+
+template <typename S>
 struct DistanceRequest {
   bool enable_nearest_points, enable_signed_distance = false;
   S rel_err = 0, abs_err = 0;
   explicit DistanceRequest(bool nearest = false) : enable_nearest_points(nearest) {}
+  bool isSatisfied(const DistanceResult<S>& result) const;  // distance_request-inl.h:73-77
 };
 
 template <typename S>
@@ -163,5 +192,83 @@ struct DistanceResult {
     if (min_distance > d) { min_distance = d; o1 = a; o2 = b; b1 = i; b2 = j; nearest_points[0] = p1; nearest_points[1] = p2; }
   }
 };
+
+template <typename S>
+bool DistanceRequest<S>::isSatisfied(const DistanceResult<S>& result) const {
+  return result.min_distance <= 0;
+}
+
+namespace detail {
+template <typename S_>
+struct GJKSolver_libccd {  // narrowphase/detail/gjk_solver_libccd.h: only the scalar type matters to the tables
+  using S = S_;
+};
+
+template <typename NarrowPhaseSolver>
+struct CollisionFunctionMatrix {  // detail/collision_func_matrix.h:53-84
+  using S = typename NarrowPhaseSolver::S;
+  using CollisionFunc = std::size_t (*)(const CollisionGeometry<S>* o1, const Transform3<S>& tf1, const CollisionGeometry<S>* o2,
+                                        const Transform3<S>& tf2, const NarrowPhaseSolver* nsolver,
+                                        const CollisionRequest<S>& request, CollisionResult<S>& result);
+  CollisionFunc collision_matrix[NODE_COUNT][NODE_COUNT];
+  CollisionFunctionMatrix() {
+    for (int i = 0; i < NODE_COUNT; ++i)
+      for (int j = 0; j < NODE_COUNT; ++j) collision_matrix[i][j] = nullptr;
+  }
+};
+
+template <typename NarrowPhaseSolver>
+struct DistanceFunctionMatrix {  // detail/distance_func_matrix.h:53-82
+  using S = typename NarrowPhaseSolver::S;
+  using DistanceFunc = S (*)(const CollisionGeometry<S>* o1, const Transform3<S>& tf1, const CollisionGeometry<S>* o2,
+                             const Transform3<S>& tf2, const NarrowPhaseSolver* nsolver, const DistanceRequest<S>& request,
+                             DistanceResult<S>& result);
+  DistanceFunc distance_matrix[NODE_COUNT][NODE_COUNT];
+  DistanceFunctionMatrix() {
+    for (int i = 0; i < NODE_COUNT; ++i)
+      for (int j = 0; j < NODE_COUNT; ++j) distance_matrix[i][j] = nullptr;
+  }
+};
+}  // namespace detail
+
+template <typename GJKSolver>
+detail::CollisionFunctionMatrix<GJKSolver>& getCollisionFunctionLookTable() {  // collision-inl.h:72-76
+  static detail::CollisionFunctionMatrix<GJKSolver> table;
+  return table;
+}
+template <typename GJKSolver>
+detail::DistanceFunctionMatrix<GJKSolver>& getDistanceFunctionLookTable() {  // distance-inl.h:65-69
+  static detail::DistanceFunctionMatrix<GJKSolver> table;
+  return table;
+}
+
+// the solver-taking fcl::collide (collision-inl.h:95-150): guard on num_max_contacts, (OT_GEOM, OT_BVH) swap, table look-up
+template <typename S, typename NarrowPhaseSolver>
+std::size_t collide(const CollisionGeometry<S>* o1, const Transform3<S>& tf1, const CollisionGeometry<S>* o2, const Transform3<S>& tf2,
+                    const NarrowPhaseSolver* nsolver, const CollisionRequest<S>& request, CollisionResult<S>& result) {
+  const auto& looktable = getCollisionFunctionLookTable<NarrowPhaseSolver>();
+  if (request.num_max_contacts == 0) return 0;
+  const NODE_TYPE t1 = o1->getNodeType(), t2 = o2->getNodeType();
+  if (o1->getObjectType() == OT_GEOM && o2->getObjectType() == OT_BVH) {
+    if (!looktable.collision_matrix[t2][t1]) return 0;
+    return looktable.collision_matrix[t2][t1](o2, tf2, o1, tf1, nsolver, request, result);
+  }
+  if (!looktable.collision_matrix[t1][t2]) return 0;
+  return looktable.collision_matrix[t1][t2](o1, tf1, o2, tf2, nsolver, request, result);
+}
+
+// the solver-taking fcl::distance (distance-inl.h:92-190)
+template <typename S, typename NarrowPhaseSolver>
+S distance(const CollisionGeometry<S>* o1, const Transform3<S>& tf1, const CollisionGeometry<S>* o2, const Transform3<S>& tf2,
+           const NarrowPhaseSolver* nsolver, const DistanceRequest<S>& request, DistanceResult<S>& result) {
+  const auto& looktable = getDistanceFunctionLookTable<NarrowPhaseSolver>();
+  const NODE_TYPE t1 = o1->getNodeType(), t2 = o2->getNodeType();
+  if (o1->getObjectType() == OT_GEOM && o2->getObjectType() == OT_BVH) {
+    if (!looktable.distance_matrix[t2][t1]) return std::numeric_limits<S>::max();
+    return looktable.distance_matrix[t2][t1](o2, tf2, o1, tf1, nsolver, request, result);
+  }
+  if (!looktable.distance_matrix[t1][t2]) return std::numeric_limits<S>::max();
+  return looktable.distance_matrix[t1][t2](o1, tf1, o2, tf2, nsolver, request, result);
+}
 
 }  // namespace fcl

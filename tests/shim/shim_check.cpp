@@ -48,10 +48,14 @@ static fclgpu_bvh* fill(Model& m, const std::vector<double>& v, const std::vecto
   std::vector<int32_t> fc(n);
   std::vector<double> ax(9 * n), oT(3 * n), oe(3 * n), rT(3 * n), rl(2 * n), rr(n);
   fclgpu::check(fclgpu_bvh_get(b, fc.data(), ax.data(), oT.data(), oe.data(), rT.data(), rl.data(), rr.data(), nullptr));
+  std::vector<int32_t> nf(n), nc(n);
+  fclgpu::check(fclgpu_bvh_get_partition(b, nf.data(), nc.data(), nullptr, nullptr));
   m.bvs_.resize(n);
   for (int i = 0; i < n; ++i) {
     auto& node = m.bvs_[i];
     node.first_child = fc[i];
+    node.first_primitive = nf[i];  // public BVNodeBase fields: the shim derives the (private) primitive_indices from them
+    node.num_primitives = nc[i];
     for (int k = 0; k < 9; ++k) node.bv.obb.axis.m[k] = node.bv.rss.axis.m[k] = ax[9 * i + k];
     for (int k = 0; k < 3; ++k) {
       node.bv.obb.To[k] = oT[3 * i + k];
@@ -191,6 +195,80 @@ int main(int argc, char** argv) {
     if (n_within == 0 || n_within == n) { std::printf("FAIL: degenerate tolerance sample\n"); return 1; }
     std::printf("shim tolerance OK: %lld within 0.25\n", n_within);
     }
+  }
+  // ---- the dispatch cells: install(), then reach them through the (mock) fcl::collide / fcl::distance look-up ----
+  {
+    using Solver = fcl::detail::GJKSolver_libccd<double>;
+    Solver solver;
+    if (fcl::getCollisionFunctionLookTable<Solver>().collision_matrix[fcl::BV_OBBRSS][fcl::BV_OBBRSS] != nullptr) { std::printf("FAIL: mock table not empty\n"); return 1; }
+    fclgpu::install<Solver>();
+    // exact CollisionFunc / DistanceFunc types (collision_func_matrix.h:67-78, distance_func_matrix.h:65-76)
+    fcl::detail::CollisionFunctionMatrix<Solver>::CollisionFunc cf = &fclgpu::collide_cell<Solver>;
+    fcl::detail::DistanceFunctionMatrix<Solver>::DistanceFunc df = &fclgpu::distance_cell<Solver>;
+    (void)cf; (void)df;
+    long long cells = 0, accumulated = 0, early = 0;
+    for (int i = 0; i < n && cells < 40; ++i) {
+      if (cnt[i] < 3) continue;  // queries with several contacts exercise the budget
+      ++cells;
+      const fcl::CollisionGeometry<double>*g1p = &m1, *g2p = &m2;
+      fcl::CollisionResult<double> res;
+      const std::size_t got = fcl::collide(g1p, tf1[i], g2p, tf2[i], &solver, fcl::CollisionRequest<double>(20, true), res);
+      if ((int)got != cnt[i] || (int)res.numContacts() != cnt[i]) { std::printf("FAIL cell count %d: %zu vs %d\n", i, got, cnt[i]); return 1; }
+      for (int k = 0; k < cnt[i]; ++k) {
+        const fclgpu_contact& c = pool[off[i] + k];
+        const auto& r = res.getContact(k);
+        if (r.b1 != c.b1 || r.b2 != c.b2 || std::memcmp(r.pos.v, c.pos, 24) || r.penetration_depth != c.penetration_depth) { std::printf("FAIL cell contact %d/%d\n", i, k); return 1; }
+      }
+      // accumulation into a NON-EMPTY result: two contacts present, budget 2 + 1 -> exactly one more (the query's first)
+      fcl::CollisionResult<double> acc;
+      acc.addContact(res.getContact(0));
+      acc.addContact(res.getContact(1));
+      const std::size_t got2 = fcl::collide(g1p, tf1[i], g2p, tf2[i], &solver, fcl::CollisionRequest<double>(3, true), acc);
+      if (got2 != 3 || acc.numContacts() != 3 || acc.getContact(2).b1 != pool[off[i]].b1 || acc.getContact(2).b2 != pool[off[i]].b2 ||
+          std::memcmp(acc.getContact(2).pos.v, pool[off[i]].pos, 24)) { std::printf("FAIL cell accumulation %d\n", i); return 1; }
+      ++accumulated;
+      // isSatisfied early return (collision_func_matrix-inl.h:580): the result already holds num_max_contacts -> no GPU work
+      const long long launches = fclgpu_launch_count();
+      const std::size_t got3 = fcl::collide(g1p, tf1[i], g2p, tf2[i], &solver, fcl::CollisionRequest<double>(3, true), acc);
+      if (got3 != 3 || fclgpu_launch_count() != launches) { std::printf("FAIL cell early return %d\n", i); return 1; }
+      ++early;
+      // distance cell: same value as the batch; a result that already holds a smaller distance keeps it; <= 0 returns early
+      fcl::DistanceResult<double> dr;
+      const double dd = fcl::distance(g1p, tf1[i], g2p, tf2[i], &solver, fcl::DistanceRequest<double>(true), dr);
+      if (dd != dist[i] || dr.b1 != i1[i] || dr.b2 != i2[i]) { std::printf("FAIL distance cell %d\n", i); return 1; }
+    }
+    int far = -1;
+    for (int i = 0; i < n; ++i) if (dist[i] > 0.1) { far = i; break; }
+    if (far >= 0) {
+      const fcl::CollisionGeometry<double>*g1p = &m1, *g2p = &m2;
+      fcl::DistanceResult<double> dr;
+      dr.min_distance = dist[far] * 0.5;  // already smaller: the cell must not overwrite it (DistanceResult::update)
+      if (fcl::distance(g1p, tf1[far], g2p, tf2[far], &solver, fcl::DistanceRequest<double>(true), dr) != dist[far] * 0.5) { std::printf("FAIL distance cell update\n"); return 1; }
+      dr.min_distance = 0.0;
+      const long long launches = fclgpu_launch_count();
+      if (fcl::distance(g1p, tf1[far], g2p, tf2[far], &solver, fcl::DistanceRequest<double>(true), dr) != 0.0 || fclgpu_launch_count() != launches) { std::printf("FAIL distance cell early return\n"); return 1; }
+      // sphere cells, both argument orders ((OT_GEOM, OT_BVH) is dispatched with swapped arguments, collision-inl.h:124-133)
+      fcl::Sphere<double> sph(0.5);
+      const fcl::CollisionGeometry<double>* sp = &sph;
+      fcl::DistanceResult<double> s1, s2;
+      const double a = fcl::distance(g1p, tf1[far], sp, tf2[far], &solver, fcl::DistanceRequest<double>(true), s1);
+      const double b = fcl::distance(sp, tf2[far], g1p, tf1[far], &solver, fcl::DistanceRequest<double>(true), s2);
+      if (a != b || s1.b1 != s2.b1 || s1.b2 != fcl::DistanceResult<double>::NONE) { std::printf("FAIL sphere cells\n"); return 1; }
+    }
+    if (cells == 0) { std::printf("FAIL: no multi-contact query for the cell check\n"); return 1; }
+    std::printf("shim cells OK: %lld single queries through the look-up table, %lld accumulations, %lld early returns\n", cells, accumulated, early);
+    // refit through the shim: the partition was derived from the public node fields
+    if (!d1.refit_ready()) { std::printf("FAIL: partition not derived\n"); return 1; }
+    for (auto& v : m1.verts_) v = fcl::Vector3<double>(v[0] * 1.01, v[1] * 1.01, v[2] * 1.01);
+    d1.refit_topdown();
+    fclgpu::check(fclgpu_bvh_refit_topdown(b1, &m1.verts_[0].v[0], m1.num_vertices));
+    std::vector<double> devT(3 * (size_t)m1.getNumBVs()), hostT(3 * (size_t)m1.getNumBVs());
+    fclgpu::check(fclgpu_model_download(d1.handle(), nullptr, devT.data(), nullptr, nullptr, nullptr, nullptr, nullptr));
+    fclgpu::check(fclgpu_bvh_get(b1, nullptr, nullptr, hostT.data(), nullptr, nullptr, nullptr, nullptr, nullptr));
+    if (std::memcmp(devT.data(), hostT.data(), devT.size() * 8)) { std::printf("FAIL: shim refit differs from the host refit\n"); return 1; }
+    std::printf("shim refit OK\n");
+    fclgpu::uninstall<Solver>();
+    if (fcl::getCollisionFunctionLookTable<Solver>().collision_matrix[fcl::BV_OBBRSS][fcl::BV_OBBRSS] != nullptr) { std::printf("FAIL: uninstall\n"); return 1; }
   }
   if (colliding < n / 20 || colliding > n - n / 20) { std::printf("FAIL: degenerate pose sample (%lld colliding)\n", colliding); return 1; }
   std::printf("shim OK: %d queries, %lld colliding, %lld contacts compared, distances identical\n", n, colliding, contacts);
