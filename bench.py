@@ -285,8 +285,26 @@ class Ctx:
         self.dev = torch.device("cuda", local)
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
         self.comm_stream = torch.cuda.Stream(self.dev) if world > 1 else None
-        self._pending = None
+        self.comm = None
         self.peaks = None
+        if world > 1:
+            # data-path collective through the C ABI (fclgpu_comm_* on raw NCCL); torch.distributed only carries the
+            # 128-byte NCCL id to the other ranks and reduces the timing
+            import ctypes as C
+
+            from fcl_b200 import _capi
+
+            L = _capi.lib()
+            ident = C.create_string_buffer(128)
+            if rank == 0:
+                rc = L.fclgpu_comm_unique_id(ident)
+                assert rc == 0, L.fclgpu_comm_last_error()
+            box = [ident.raw]
+            dist.broadcast_object_list(box, src=0)
+            h = C.c_void_p()
+            rc = L.fclgpu_comm_init(local, rank, world, box[0], C.byref(h))
+            assert rc == 0, L.fclgpu_comm_last_error()
+            self.comm = h
 
     # ---- step loop on the device clock, L2 flushed before every step, max over ranks.  One GPU: the sum of the per-step
     # event intervals (flush outside the intervals).  Several GPUs: steps overlap (step k's results leave over NVLink
@@ -352,9 +370,12 @@ class Ctx:
             return
         ev = torch.cuda.Event()
         ev.record()
-        with torch.cuda.stream(self.comm_stream):
-            self.comm_stream.wait_event(ev)
-            dist.all_gather_into_tensor(out_buf, local_buf)
+        self.comm_stream.wait_event(ev)
+        from fcl_b200 import _capi
+
+        rc = _capi.lib().fclgpu_comm_allgather(self.comm, local_buf.data_ptr(), out_buf.data_ptr(), local_buf.numel() * local_buf.element_size(),
+                                               self.comm_stream.cuda_stream)
+        assert rc == 0, _capi.lib().fclgpu_comm_last_error()
 
     def drain(self):
         if self.world > 1:
@@ -741,8 +762,9 @@ def main():
                        "pose_seed": 1, "models": "env.obj (2180 tris, 4359 nodes) posed vs rob.obj (216 tris, 431 nodes) at identity",
                        "l2_flush_between_steps": True, "l2_flush_inside_timed_region": world > 1,
                        "traversal": _capi.get_option("traversal"), **({"options": args.opt} if args.opt else {}),
-                       "multi_gpu": ("BVHs replicated, poses partitioned, one packed 64 B/query result record all-gathered with NCCL "
-                                     "per step, overlapped with the next step's traversal") if world > 1 else "single GPU"},
+                       "multi_gpu": ("BVHs replicated, poses partitioned, one packed 64 B/query result record all-gathered per step with "
+                                     "fclgpu_comm_allgather (C ABI, raw NCCL) on a second stream, overlapped with the next step's traversal")
+                                    if world > 1 else "single GPU"},
             "clocks": clocks, "e2e": h["e2e"], "gpu_launches": h["gpu_launches"], "roofline": h["roofline"],
             "cpu_baseline": h["cpu_baseline"], "peaks": ctx.microbench(),
         }

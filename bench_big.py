@@ -171,7 +171,7 @@ def run(ctx, which):
     bufs = {k: [torch.empty(n * r, dtype=torch.uint8, device=dev) for _ in range(2)] for k, r in rec.items()}
     gath = {k: [torch.empty(world * n * r, dtype=torch.uint8, device=dev) if world > 1 else None for _ in range(2)] for k, r in rec.items()}
     L = _capi.lib()
-    import ctypes as C
+    within_buf = [torch.zeros(n, dtype=torch.uint8, device=dev) for _ in range(2)]
 
     def dviews(b):
         return (b[:8 * n].view(torch.float64), b[8 * n:32 * n].view(torch.float64).view(n, 3), b[32 * n:56 * n].view(torch.float64).view(n, 3),
@@ -186,10 +186,9 @@ def run(ctx, which):
                 v = dviews(b)
                 F.distance_batch_device(A, None, B, dP, dreq, v[0], v[1], v[2], v[3], v[4])
             else:
-                rq = dreq0._c()
-                rc = L.fclgpu_distance_cutoff_batch(A.device_model(local), B.device_model(local), n, None, dP.data_ptr(), C.byref(rq),
-                                                    cutoff, b.view(torch.float64).data_ptr(), None, None, None, None, None, None,
-                                                    torch.cuda.current_stream().cuda_stream)
+                rc = L.fclgpu_within_tolerance_batch(A.device_model(local), B.device_model(local), n, None, dP.data_ptr(), tol,
+                                                     within_buf[k % 2].data_ptr(), b.view(torch.float64).data_ptr(), None, None,
+                                                     torch.cuda.current_stream().cuda_stream)
                 assert rc == 0, rc
         return f
 
@@ -225,7 +224,7 @@ def run(ctx, which):
                     return F.collide_batch(A, ident, B, hp, creq, want_contacts=False, device=local, pinned=True)
                 if kind == "distance":
                     return F.distance_batch(A, ident, B, hp, dreq, device=local, pinned=True)
-                return F.distance_batch(A, ident, B, hp, dreq0, device=local, pinned=True, cutoff=cutoff)
+                return F.within_tolerance_batch(A, ident, B, hp, tol, device=local)
             one()
             torch.cuda.synchronize()
             if world > 1:
@@ -247,9 +246,9 @@ def run(ctx, which):
     dist_res = dviews(bufs["distance"][0])[0]
     tol_res = bufs["tolerance"][0].view(torch.float64)
     cnt_res = bufs["collide"][0].view(torch.int32)
-    within = tol_res <= tol
+    within = within_buf[0] != 0
     checks = {"tolerance_equals_distance_le_tol": bool(torch.equal(within, dist_res <= tol)),
-              "tolerance_equals_min_distance_cutoff": bool(torch.equal(tol_res, torch.clamp(dist_res, max=cutoff))),
+              "witness_is_upper_bound_within_tol": bool(((tol_res >= dist_res) & ((tol_res <= tol) | ~within)).all().item()),
               "colliding_frac": float((cnt_res > 0).float().mean().item()), "within_tolerance_frac": float(within.float().mean().item()),
               "colliding_implies_zero_distance": bool((dist_res[cnt_res > 0] == 0).all().item())}
     model_bytes = (A.getNumBVs() + B.getNumBVs()) * 128 + (A.num_tris + B.num_tris) * 72

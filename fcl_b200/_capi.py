@@ -54,6 +54,9 @@ SYMBOLS = [
     "fclgpu_collide_mesh_sphere_batch", "fclgpu_collide_mesh_sphere_batch_host",
     "fclgpu_distance_mesh_sphere_batch", "fclgpu_distance_mesh_sphere_batch_host",
     "fclgpu_distance_cutoff_batch", "fclgpu_distance_cutoff_batch_host",
+    "fclgpu_within_tolerance_batch", "fclgpu_within_tolerance_batch_host",
+    "fclgpu_shard_range", "fclgpu_comm_unique_id", "fclgpu_comm_init", "fclgpu_comm_rank", "fclgpu_comm_world",
+    "fclgpu_comm_allgather", "fclgpu_comm_allgather_ragged", "fclgpu_comm_destroy", "fclgpu_comm_last_error",
     "fclgpu_model_create_obbrss", "fclgpu_model_from_bvh", "fclgpu_model_destroy", "fclgpu_model_num_nodes",
     "fclgpu_model_num_tris", "fclgpu_model_device", "fclgpu_collide_batch", "fclgpu_collide_batch_host",
     "fclgpu_distance_batch", "fclgpu_distance_batch_host", "fclgpu_abi_version", "fclgpu_device_count",
@@ -116,6 +119,18 @@ def lib():
                                                ip, ip, up, up, vp]
     L.fclgpu_distance_cutoff_batch_host.argtypes = [vp, vp, C.c_int64, dp, dp, C.POINTER(DistanceRequestC), C.c_double, dp, dp,
                                                     dp, ip, ip, up, up]
+    L.fclgpu_within_tolerance_batch.argtypes = [vp, vp, C.c_int64, dp, dp, C.c_double, vp, dp, up, up, vp]
+    L.fclgpu_within_tolerance_batch_host.argtypes = [vp, vp, C.c_int64, dp, dp, C.c_double, vp, dp, up, up]
+    L.fclgpu_shard_range.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.fclgpu_shard_range.restype = None
+    L.fclgpu_comm_unique_id.argtypes = [C.c_char_p]
+    L.fclgpu_comm_init.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(vp)]
+    L.fclgpu_comm_rank.argtypes = [vp]
+    L.fclgpu_comm_world.argtypes = [vp]
+    L.fclgpu_comm_allgather.argtypes = [vp, vp, vp, C.c_size_t, vp]
+    L.fclgpu_comm_allgather_ragged.argtypes = [vp, vp, vp, C.POINTER(C.c_int64), vp]
+    L.fclgpu_comm_destroy.argtypes = [vp]
+    L.fclgpu_comm_last_error.restype = C.c_char_p
     L.fclgpu_last_error.restype = C.c_char_p
     L.fclgpu_pose_from_colmajor4x4.argtypes = [vp, vp]
     L.fclgpu_pose_from_colmajor4x4.restype = None

@@ -39,8 +39,33 @@ constexpr int kOrdWarps = 4;      // warps per block
 #define FCLGPU_ORD_MINBLOCKS 4
 #endif
 #ifndef FCLGPU_ORD_OUTOFLINE
-#define FCLGPU_ORD_OUTOFLINE 1
+#define FCLGPU_ORD_OUTOFLINE 3   // bit 0: triangle SAT out of line, bit 1: contact computation out of line
 #endif
+#ifndef FCLGPU_ORD_ROLLED
+#define FCLGPU_ORD_ROLLED 1      // rolled-loop triangle SAT (compact code)
+#endif
+
+// out-of-line leaf routines taking their operands BY VALUE (registers), so that the caller's triangles need no stack slots
+struct TriPair {
+  V3 p0, p1, p2, q0, q1, q2;
+};
+struct ContactInfo {
+  V3 c0, c1, n;
+  double depth;
+  unsigned nc;
+};
+__device__ __noinline__ bool ord_tri_intersect(const TriPair t) {
+  return FCLGPU_ORD_ROLLED ? tri_intersect_rolled(t.p0, t.p1, t.p2, t.q0, t.q1, t.q2) : tri_intersect(t.p0, t.p1, t.p2, t.q0, t.q1, t.q2);
+}
+__device__ __noinline__ ContactInfo ord_contact_info(const TriPair t) {
+  const V3 P[3] = {t.p0, t.p1, t.p2}, Q[3] = {t.q0, t.q1, t.q2};
+  V3 cp[2];
+  ContactInfo o;
+  tri_contact_info(P, Q, cp, o.nc, o.depth, o.n);
+  o.c0 = cp[0];
+  o.c1 = cp[1];
+  return o;
+}
 
 struct __align__(16) OrderedFront {
   uint2 pair[kOrdCap];
@@ -123,9 +148,8 @@ __global__ void __launch_bounds__(kOrdWarps * 32, FCLGPU_ORD_MINBLOCKS) collide_
         head = (head + k) & (kOrdLeafCap - 1);
         nleaf -= k;
         int ncp = 0;  // entries this pair adds to the list: 1 per hit (binary mode) or its 0..2 contact points
-        V3 cp[2], nrm;
+        V3 cp0 = mk(0, 0, 0), cp1 = mk(0, 0, 0), nrm = mk(0, 0, 0);
         double depth = 0.0;
-        cp[0] = cp[1] = nrm = mk(0, 0, 0);
         if (mine) {
           M3 R;
 #pragma unroll
@@ -136,15 +160,25 @@ __global__ void __launch_bounds__(kOrdWarps * 32, FCLGPU_ORD_MINBLOCKS) collide_
           load_tri(P.m2.tri, (int)ids.y, Qt);
 #pragma unroll
           for (int c = 0; c < 3; ++c) Qt[c] = mulv(R, Qt[c]) + T;
-          const bool hit = FCLGPU_ORD_OUTOFLINE ? tri_intersect_outofline(Pt, Qt)
-                                                : tri_intersect(Pt[0], Pt[1], Pt[2], Qt[0], Qt[1], Qt[2]);
+          const TriPair tp{Pt[0], Pt[1], Pt[2], Qt[0], Qt[1], Qt[2]};
+          bool hit;
+          if (FCLGPU_ORD_OUTOFLINE & 1) hit = ord_tri_intersect(tp);
+          else if (FCLGPU_ORD_ROLLED) hit = tri_intersect_rolled(Pt[0], Pt[1], Pt[2], Qt[0], Qt[1], Qt[2]);
+          else hit = tri_intersect(Pt[0], Pt[1], Pt[2], Qt[0], Qt[1], Qt[2]);
           if (hit) {
             ncp = 1;
             if (P.enable_contact) {
-              unsigned nc;
-              if (FCLGPU_ORD_OUTOFLINE) tri_contact_info_outofline(Pt, Qt, cp, &nc, &depth, &nrm);
-              else tri_contact_info(Pt, Qt, cp, nc, depth, nrm);
-              ncp = (int)nc;
+              if (FCLGPU_ORD_OUTOFLINE & 2) {
+                const ContactInfo ci = ord_contact_info(tp);
+                cp0 = ci.c0; cp1 = ci.c1; nrm = ci.n; depth = ci.depth;
+                ncp = (int)ci.nc;
+              } else {
+                V3 cp[2];
+                unsigned nc;
+                tri_contact_info(Pt, Qt, cp, nc, depth, nrm);
+                cp0 = cp[0]; cp1 = cp[1];
+                ncp = (int)nc;
+              }
             }
           }
         }
@@ -155,31 +189,35 @@ __global__ void __launch_bounds__(kOrdWarps * 32, FCLGPU_ORD_MINBLOCKS) collide_
         const long long room = P.max_contacts - count;  // > 0 here
         if (ncp > 0 && stage != nullptr && before < room) {
           // mesh_collision_traversal_node-inl.h:594-600: a pair that does not fit entirely contributes its first points
-          int nw = ncp;
-          if (before + nw > room) nw = (int)(room - before);
-          M3 R1;
-          V3 t1 = mk(0, 0, 0), nw3 = mk(0, 0, 0);
-          if (P.enable_contact) {
-#pragma unroll
-            for (int c = 0; c < 9; ++c) R1.m[c] = S.tf1[c];
-            t1 = mk(S.tf1[9], S.tf1[10], S.tf1[11]);
-            nw3 = mulv(R1, nrm);  // tf1.linear() * n
-          }
-          for (int j = 0; j < nw; ++j) {
-            const long long slot = count + before + j;
-            if (slot < P.stride) {
-              fclgpu_contact* c = stage + slot;
-              c->b1 = (int)ids.x;
-              c->b2 = (int)ids.y;
-              if (P.enable_contact) {
-                const V3 pw = mulv(R1, cp[j]) + t1;  // tf1 * p
-                c->normal[0] = nw3.x; c->normal[1] = nw3.y; c->normal[2] = nw3.z;
-                c->pos[0] = pw.x; c->pos[1] = pw.y; c->pos[2] = pw.z;
-                c->penetration_depth = depth;
-              }
-            } else {
-              atomicMin(P.status, (int)FCLGPU_ERR_CONTACT_OVERFLOW);
+          const bool two = ncp == 2 && before + 2 <= room;
+          const long long slot = count + before;
+          if (slot + (two ? 1 : 0) < P.stride) {
+            fclgpu_contact* c = stage + slot;
+            c->b1 = (int)ids.x;
+            c->b2 = (int)ids.y;
+            if (two) {
+              c[1].b1 = (int)ids.x;
+              c[1].b2 = (int)ids.y;
             }
+            if (P.enable_contact) {
+              M3 R1;
+#pragma unroll
+              for (int k2 = 0; k2 < 9; ++k2) R1.m[k2] = S.tf1[k2];
+              const V3 t1 = mk(S.tf1[9], S.tf1[10], S.tf1[11]);
+              const V3 nw3 = mulv(R1, nrm);        // tf1.linear() * n
+              const V3 pw = mulv(R1, cp0) + t1;    // tf1 * p
+              c->normal[0] = nw3.x; c->normal[1] = nw3.y; c->normal[2] = nw3.z;
+              c->pos[0] = pw.x; c->pos[1] = pw.y; c->pos[2] = pw.z;
+              c->penetration_depth = depth;
+              if (two) {
+                const V3 pv = mulv(R1, cp1) + t1;
+                c[1].normal[0] = nw3.x; c[1].normal[1] = nw3.y; c[1].normal[2] = nw3.z;
+                c[1].pos[0] = pv.x; c[1].pos[1] = pv.y; c[1].pos[2] = pv.z;
+                c[1].penetration_depth = depth;
+              }
+            }
+          } else {
+            atomicMin(P.status, (int)FCLGPU_ERR_CONTACT_OVERFLOW);
           }
         }
         count += total < room ? total : room;

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -1004,7 +1005,8 @@ namespace {
 int distance_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1, const double* tf2,
                      const fclgpu_distance_request* request, double* min_distance, double* nearest_p1,
                      double* nearest_p2, int32_t* b1, int32_t* b2, uint32_t* n_bv, uint32_t* n_leaf, void* stream,
-                     double sphere_radius, double cutoff = 1.7976931348623157e308) {
+                     double sphere_radius, double cutoff = 1.7976931348623157e308, double stop_below = -1.0,
+                     uint8_t* within = nullptr) {
   if (!m1 || !m2 || !request || n < 0) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL model/request or n<0");
   if (m1->device != m2->device) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "models live on different devices");
   if (m1->depth + (sphere_radius >= 0 ? 0 : m2->depth) + 2 > kStackCap)
@@ -1037,6 +1039,8 @@ int distance_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, 
   P.spill_cap = 0;
   P.spill_warps = 0;
   P.cutoff = cutoff;
+  P.stop_below = stop_below;
+  P.within = within;
   if ((long long)m1->d.n_nodes + m2->d.n_nodes >= (1 << 17) && opt("dist_spill_entries") >= kSpillBlock) {
     // big models: the sorted front may outgrow its shared-memory stack; give every warp of the largest
     // possible grid an overflow area in HBM (12 bytes per entry)
@@ -1109,6 +1113,17 @@ extern "C" int fclgpu_distance_cutoff_batch(const fclgpu_model* m1, const fclgpu
   if (!(cutoff > 0)) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "cutoff must be > 0");
   return distance_enqueue(m1, m2, n, tf1, tf2, request, min_distance, nearest_p1, nearest_p2, b1, b2, n_bv, n_leaf, stream,
                           -1.0, cutoff);
+}
+
+// tolerance verdicts with early exit (extension, BASELINE cfg5)
+extern "C" int fclgpu_within_tolerance_batch(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1,
+                                             const double* tf2, double tolerance, uint8_t* within, double* witness_distance,
+                                             uint32_t* n_bv, uint32_t* n_leaf, void* stream) {
+  if (!(tolerance >= 0)) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "tolerance must be >= 0");
+  if (!within) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "within is NULL");
+  const fclgpu_distance_request rq{0, 0, 0.0, 0.0};
+  return distance_enqueue(m1, m2, n, tf1, tf2, &rq, witness_distance, nullptr, nullptr, nullptr, nullptr, n_bv, n_leaf, stream,
+                          -1.0, std::nextafter(tolerance, 1.7976931348623157e308), tolerance, within);
 }
 
 // mesh <-> sphere distance
@@ -1353,7 +1368,7 @@ namespace {
 int distance_host(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1, const double* tf2,
                   const fclgpu_distance_request* request, double* min_distance, double* nearest_p1, double* nearest_p2,
                   int32_t* b1, int32_t* b2, uint32_t* n_bv, uint32_t* n_leaf, double sphere_radius,
-                  double cutoff = 1.7976931348623157e308) {
+                  double cutoff = 1.7976931348623157e308, double stop_below = -1.0, uint8_t* within = nullptr) {
   if (!m1 || !m2 || !request || n < 0) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL model/request or n<0");
   CUDA_TRY(cudaSetDevice(m1->device));
   Workspace* w;
@@ -1365,7 +1380,7 @@ int distance_host(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, con
   // c-1's results come down (the copies are asynchronous when the caller's buffers are pinned).
   const size_t C = (size_t)std::min<int64_t>(n, host_chunk());
   const size_t per_stage = (tf1 ? padded(96 * C) : 0) + (tf2 ? padded(96 * C) : 0) + padded(8 * C) + 2 * padded(24 * C) +
-                           4 * padded(4 * C) + 256;
+                           4 * padded(4 * C) + padded(C) + 256;
   {
     std::lock_guard<std::mutex> lock(w->mu);
     rc = ensure(&w->dev_io, &w->dev_io_bytes, 2 * per_stage);
@@ -1386,11 +1401,13 @@ int distance_host(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, con
     int32_t* d_b2 = b2 ? B.take<int32_t>(C) : nullptr;
     uint32_t* d_bv = n_bv ? B.take<uint32_t>(C) : nullptr;
     uint32_t* d_leaf = n_leaf ? B.take<uint32_t>(C) : nullptr;
+    uint8_t* d_within = within ? B.take<uint8_t>(C) : nullptr;
     if (tf1) CUDA_TRY(cudaMemcpyAsync(d_tf1, tf1 + 12 * s, 96 * cn, cudaMemcpyHostToDevice, st));
     if (tf2) CUDA_TRY(cudaMemcpyAsync(d_tf2, tf2 + 12 * s, 96 * cn, cudaMemcpyHostToDevice, st));
     rc = distance_enqueue(m1, m2, (int64_t)cn, d_tf1, d_tf2, request, d_dist, d_p1, d_p2, d_b1, d_b2, d_bv, d_leaf, st,
-                          sphere_radius, cutoff);
+                          sphere_radius, cutoff, stop_below, d_within);
     if (rc) return rc;
+    if (within) CUDA_TRY(cudaMemcpyAsync(within + s, d_within, cn, cudaMemcpyDeviceToHost, st));
     if (min_distance) CUDA_TRY(cudaMemcpyAsync(min_distance + s, d_dist, 8 * cn, cudaMemcpyDeviceToHost, st));
     if (d_p1) CUDA_TRY(cudaMemcpyAsync(nearest_p1 + 3 * s, d_p1, 24 * cn, cudaMemcpyDeviceToHost, st));
     if (d_p2) CUDA_TRY(cudaMemcpyAsync(nearest_p2 + 3 * s, d_p2, 24 * cn, cudaMemcpyDeviceToHost, st));
@@ -1420,6 +1437,16 @@ extern "C" int fclgpu_distance_cutoff_batch_host(const fclgpu_model* m1, const f
                                                  int32_t* b2, uint32_t* n_bv, uint32_t* n_leaf) {
   if (!(cutoff > 0)) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "cutoff must be > 0");
   return distance_host(m1, m2, n, tf1, tf2, request, min_distance, nearest_p1, nearest_p2, b1, b2, n_bv, n_leaf, -1.0, cutoff);
+}
+
+extern "C" int fclgpu_within_tolerance_batch_host(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1,
+                                                  const double* tf2, double tolerance, uint8_t* within,
+                                                  double* witness_distance, uint32_t* n_bv, uint32_t* n_leaf) {
+  if (!(tolerance >= 0)) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "tolerance must be >= 0");
+  if (!within) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "within is NULL");
+  const fclgpu_distance_request rq{0, 0, 0.0, 0.0};
+  return distance_host(m1, m2, n, tf1, tf2, &rq, witness_distance, nullptr, nullptr, nullptr, nullptr, n_bv, n_leaf, -1.0,
+                       std::nextafter(tolerance, 1.7976931348623157e308), tolerance, within);
 }
 
 extern "C" int fclgpu_distance_mesh_sphere_batch_host(const fclgpu_model* m1, double radius, int64_t n, const double* tf1,

@@ -346,6 +346,10 @@ struct DistanceParams {
   // value the minimum starts from (DistanceResult's initial min_distance): DBL_MAX for fcl::distance; a finite cutoff
   // for the tolerance-verification extension -- everything whose bound is >= cutoff is pruned from the first round on
   double cutoff;
+  // tolerance verdicts: the traversal of a query ends as soon as its minimum is <= stop_below (a triangle pair within
+  // the tolerance has been found: the verdict is decided); -1 = never (distances are >= 0).  within[q] = min <= stop_below.
+  double stop_below;
+  uint8_t* within;
 };
 
 struct DistState {
@@ -390,6 +394,7 @@ __global__ void __launch_bounds__(128) distance_thread_kernel(DistanceParams P) 
     if (need && q >= 0) {
       // postprocess: nearest points (model1 frame) -> world with tf1
       if (P.min_distance) P.min_distance[q] = s.min_d;
+      if (P.within) P.within[q] = s.min_d <= P.stop_below ? 1 : 0;
       if (P.b1) P.b1[q] = s.b1;
       if (P.b2) P.b2[q] = s.b2;
       if (P.enable_nearest_points) {
@@ -420,7 +425,7 @@ __global__ void __launch_bounds__(128) distance_thread_kernel(DistanceParams P) 
         dist_leaf(P.m1, P.m2, R, T, 0, 0, s);  // preprocess: seed with triangle 0 / triangle 0
         stk[0] = make_uint2(0u, 0u);
         stk_d[0] = -1.0;  // the root pair is never bound-tested
-        sp = 1;
+        sp = (s.min_d <= P.stop_below) ? 0 : 1;
       } else {
         exhausted = true;
       }
@@ -439,6 +444,7 @@ __global__ void __launch_bounds__(128) distance_thread_kernel(DistanceParams P) 
     if (l1 && l2) {
       if (kStats) leaf_tests++;
       dist_leaf(P.m1, P.m2, R, T, -(fc1 + 1), -(fc2 + 1), s);
+      if (s.min_d <= P.stop_below) sp = 0;  // tolerance verdict decided
       continue;
     }
     // firstOverSecond needs both sizes (OBB extents' squared norm, stored in the rss record too)
@@ -749,6 +755,12 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
             S.best_id[0] = (int)ids.x;
             S.best_id[1] = (int)ids.y;
           }
+          if (dmin <= P.stop_below) {  // tolerance verdict decided: a pair within the tolerance exists
+            sp = 0;
+            gsp = 0;
+            nleaf = 0;
+            nraw = 0;
+          }
         }
         __syncwarp();
         continue;
@@ -898,6 +910,7 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
     // postprocess: nearest points (model1 frame) -> world with tf1
     if (lane == 0) {
       if (P.min_distance) P.min_distance[q] = min_d;
+      if (P.within) P.within[q] = min_d <= P.stop_below ? 1 : 0;
       if (P.b1) P.b1[q] = S.best_id[0];
       if (P.b2) P.b2[q] = S.best_id[1];
       if (P.enable_nearest_points) {
@@ -942,6 +955,9 @@ namespace fclgpu {
 // loop be allocated far fewer registers (higher occupancy).
 __device__ __noinline__ bool tri_intersect_outofline(const V3* Pt, const V3* Qt) {
   return tri_intersect(Pt[0], Pt[1], Pt[2], Qt[0], Qt[1], Qt[2]);
+}
+__device__ __noinline__ bool tri_intersect_rolled_outofline(const V3* Pt, const V3* Qt) {
+  return tri_intersect_rolled(Pt[0], Pt[1], Pt[2], Qt[0], Qt[1], Qt[2]);
 }
 __device__ __noinline__ void tri_contact_info_outofline(const V3* Pt, const V3* Qt, V3* cp, unsigned* nc, double* depth, V3* nrm) {
   tri_contact_info(Pt, Qt, cp, *nc, *depth, *nrm);

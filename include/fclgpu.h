@@ -52,7 +52,8 @@ typedef enum fclgpu_status {
   FCLGPU_ERR_CUDA = -22,
   FCLGPU_ERR_CONTACT_OVERFLOW = -23, /* per-pose or pool capacity too small; counts are still exact */
   FCLGPU_ERR_STACK_OVERFLOW = -24,   /* traversal stack exhausted (tree deeper than supported) */
-  FCLGPU_ERR_INPUT_STALLED = -25     /* host API: a pose chunk did not reach the device within the kernel's wait budget */
+  FCLGPU_ERR_INPUT_STALLED = -25,    /* host API: a pose chunk did not reach the device within the kernel's wait budget */
+  FCLGPU_ERR_COMM = -26              /* fclgpu_comm_*: NCCL reported an error (fclgpu_comm_last_error) */
 } fclgpu_status;
 
 /* Split rules of the reference's BVSplitter (include/fcl/geometry/bvh/detail/BV_splitter.h). */
@@ -256,6 +257,18 @@ int fclgpu_distance_cutoff_batch_host(const fclgpu_model* m1, const fclgpu_model
                                       double* min_distance, double* nearest_p1, double* nearest_p2, int32_t* b1, int32_t* b2,
                                       uint32_t* n_bv, uint32_t* n_leaf);
 
+/* Tolerance VERDICTS (EXTENSION; BASELINE cfg5): within[i] = 1 iff fcl::distance(m1, tf1[i], m2, tf2[i]) <= tolerance,
+ * the comparison a caller of the reference would make.  Same traversal as fclgpu_distance_cutoff_batch with
+ * cutoff = nextafter(tolerance, +inf), and it ENDS a query at the first triangle pair found within the tolerance
+ * (the verdict is decided; the exact minimum is not needed).  witness_distance (optional): the distance of that pair
+ * -- an upper bound of the true distance, <= tolerance -- or nextafter(tolerance) when nothing is within.  tolerance >= 0. */
+int fclgpu_within_tolerance_batch(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1,
+                                  const double* tf2, double tolerance, uint8_t* within, double* witness_distance,
+                                  uint32_t* n_bv, uint32_t* n_leaf, void* stream);
+int fclgpu_within_tolerance_batch_host(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1,
+                                       const double* tf2, double tolerance, uint8_t* within, double* witness_distance,
+                                       uint32_t* n_bv, uint32_t* n_leaf);
+
 /* ---------------------------------------------------------------------------------------
  * Batched mesh <-> sphere distance: query i evaluates
  * fcl::distance(m1, tf1[i], Sphere(radius), tf2[i], request, result_i) =
@@ -280,6 +293,32 @@ int fclgpu_distance_mesh_sphere_batch_host(const fclgpu_model* m1, double radius
                                            const double* tf2, const fclgpu_distance_request* request,
                                            double* min_distance, double* nearest_p1, double* nearest_p2, int32_t* b1,
                                            int32_t* b2, uint32_t* n_bv, uint32_t* n_leaf);
+
+/* ---------------------------------------------------------------------------------------
+ * Multi-GPU: the path shards over poses with NO exchange inside the traversal -- BVHs are replicated
+ * (upload the models on every GPU), rank r owns the contiguous block fclgpu_shard_range() names, every rank runs the
+ * *_batch calls above on its block, and the per-rank result arrays are gathered with NCCL's all-gather over NVLink.
+ * One process per GPU.  NCCL is opened at run time (libnccl.so.2); without it these calls return
+ * FCLGPU_ERR_UNSUPPORTED_FUNCTION.  Bootstrap: rank 0 calls fclgpu_comm_unique_id and hands the 128 bytes to the other
+ * ranks by whatever the application uses to start its processes (MPI, a file, a socket); every rank then calls
+ * fclgpu_comm_init.  The collectives take DEVICE pointers and are asynchronous on `stream`: enqueue the gather of
+ * batch k on a second stream (ordered by an event) to overlap it with the traversal of batch k + 1.
+ * ------------------------------------------------------------------------------------- */
+#define FCLGPU_COMM_ID_BYTES 128
+typedef struct fclgpu_comm fclgpu_comm;
+/* rank `rank` of `world` owns queries [*start, *start + *count) of a batch of n (balanced to within one query) */
+void fclgpu_shard_range(int64_t n, int rank, int world, int64_t* start, int64_t* count);
+int fclgpu_comm_unique_id(char id[FCLGPU_COMM_ID_BYTES]);
+int fclgpu_comm_init(int device, int rank, int world, const char id[FCLGPU_COMM_ID_BYTES], fclgpu_comm** out);
+int fclgpu_comm_rank(const fclgpu_comm* comm);
+int fclgpu_comm_world(const fclgpu_comm* comm);
+/* fixed-size records: recv (world * bytes_per_rank bytes) receives rank r's block at r * bytes_per_rank */
+int fclgpu_comm_allgather(fclgpu_comm* comm, const void* send, void* recv, size_t bytes_per_rank, void* stream);
+/* ragged blocks (contact lists): rank r contributes bytes_of_rank[r] bytes (HOST array, identical on every rank: gather
+ * the totals first with fclgpu_comm_allgather); recv receives the blocks back to back in rank order */
+int fclgpu_comm_allgather_ragged(fclgpu_comm* comm, const void* send, void* recv, const int64_t* bytes_of_rank, void* stream);
+int fclgpu_comm_destroy(fclgpu_comm* comm);
+const char* fclgpu_comm_last_error(void); /* thread-local */
 
 /* ---------------------------------------------------------------------------------------
  * Utilities

@@ -233,23 +233,21 @@ inline void distance(const DeviceModel& o1, const std::vector<fcl::Transform3<do
 }
 
 // Tolerance verification (extension, see fclgpu_distance_cutoff_batch in fclgpu.h): within[i] = 1 iff
-// fcl::distance(o1, tf1[i], o2, tf2[i]) <= tolerance; node pairs farther apart than the tolerance are never descended.
+// fcl::distance(o1, tf1[i], o2, tf2[i]) <= tolerance; node pairs farther apart than the tolerance are never descended and a
+// query ends at the first triangle pair found within it (fclgpu_within_tolerance_batch).
 inline void within_tolerance(const DeviceModel& o1, const std::vector<fcl::Transform3<double>>& tf1, const DeviceModel& o2,
                              const std::vector<fcl::Transform3<double>>& tf2, double tolerance, std::vector<char>& within) {
   const int64_t n = (int64_t)tf1.size();
   same_size(tf1.size(), tf2.size());
   within.assign(n, 0);
   if (n == 0) return;
-  std::vector<double> p1(12 * n), p2(12 * n), d(n);
+  std::vector<double> p1(12 * n), p2(12 * n);
   for (int64_t i = 0; i < n; ++i) {
     to_pose(tf1[i], &p1[12 * i]);
     to_pose(tf2[i], &p2[12 * i]);
   }
-  fclgpu_distance_request req{0, 0, 0.0, 0.0};
-  check(fclgpu_distance_cutoff_batch_host(o1.handle(), o2.handle(), n, p1.data(), p2.data(), &req,
-                                          std::nextafter(tolerance, std::numeric_limits<double>::infinity()), d.data(), nullptr,
-                                          nullptr, nullptr, nullptr, nullptr, nullptr));
-  for (int64_t i = 0; i < n; ++i) within[i] = d[i] <= tolerance ? 1 : 0;
+  check(fclgpu_within_tolerance_batch_host(o1.handle(), o2.handle(), n, p1.data(), p2.data(), tolerance,
+                                           reinterpret_cast<uint8_t*>(within.data()), nullptr, nullptr, nullptr));
 }
 
 // n independent fcl::distance(mesh, tf1[i], sphere, tf2[i], request, results[i]) calls

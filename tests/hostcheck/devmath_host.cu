@@ -42,6 +42,7 @@ int hm_tri_intersect(const double* P9, const double* Q9, const double* pose12, i
   V3 P[3] = {v3(P9), v3(P9 + 3), v3(P9 + 6)};
   V3 Q[3] = {mulv(R, v3(Q9)) + T, mulv(R, v3(Q9 + 3)) + T, mulv(R, v3(Q9 + 6)) + T};
   bool hit = tri_intersect(P[0], P[1], P[2], Q[0], Q[1], Q[2]);
+  if (hit != tri_intersect_rolled(P[0], P[1], P[2], Q[0], Q[1], Q[2])) return -1;  // the rolled variant must agree
   if (hit && want) {
     V3 c[2]; unsigned n; double d; V3 nrm;
     tri_contact_info(P, Q, c, n, d, nrm);

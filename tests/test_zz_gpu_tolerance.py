@@ -42,8 +42,15 @@ def test_tolerance_verification_matches_oracle(oracle, env_rob_npz, trav):
             # (front traversals may name another pair of an exact tie, DESIGN 2: ids are not compared there)
             # pruning from the first round on: fewer box tests than the unbounded query
             assert got.n_bv.astype(np.int64).sum() < full.n_bv.astype(np.int64).sum()
-            within, _ = F.within_tolerance_batch(env, P, rob, None, tol)
+            within, wres = F.within_tolerance_batch(env, P, rob, None, tol, stats=True)  # early exit at the first pair within tol
             assert np.array_equal(within, rd["min_distance"] <= tol)
+            # the witness is a real triangle-pair distance: an upper bound of the true minimum, itself within the tolerance
+            assert (wres.min_distance[within] <= tol).all() and (wres.min_distance[within] >= rd["min_distance"][within]).all()
+            assert (wres.min_distance[~within] == cutoff).all()
+            within2, full_tol = F.within_tolerance_batch(env, P, rob, None, tol, stats=True, early_exit=False)
+            assert np.array_equal(within2, within)
+            assert wres.n_bv.astype(np.int64).sum() <= full_tol.n_bv.astype(np.int64).sum()
+            assert wres.n_leaf.astype(np.int64).sum() <= full_tol.n_leaf.astype(np.int64).sum()
     finally:
         _capi.set_option("traversal", 3)
 
