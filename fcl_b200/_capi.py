@@ -23,6 +23,8 @@ ERR_CUDA = -22
 ERR_CONTACT_OVERFLOW = -23
 ERR_STACK_OVERFLOW = -24
 ERR_INPUT_STALLED = -25
+ERR_COMM = -26
+SHAPE_PLANE, SHAPE_HALFSPACE = 16, 17  # fcl::GEOM_PLANE / GEOM_HALFSPACE
 
 CONTACT_DTYPE = np.dtype(
     [("b1", "<i4"), ("b2", "<i4"), ("normal", "<f8", (3,)), ("pos", "<f8", (3,)), ("penetration_depth", "<f8")]
@@ -55,6 +57,8 @@ SYMBOLS = [
     "fclgpu_distance_mesh_sphere_batch", "fclgpu_distance_mesh_sphere_batch_host",
     "fclgpu_distance_cutoff_batch", "fclgpu_distance_cutoff_batch_host",
     "fclgpu_within_tolerance_batch", "fclgpu_within_tolerance_batch_host",
+    "fclgpu_load_obj", "fclgpu_save_obj", "fclgpu_free",
+    "fclgpu_collide_mesh_plane_batch", "fclgpu_collide_mesh_plane_batch_host",
     "fclgpu_shard_range", "fclgpu_comm_unique_id", "fclgpu_comm_init", "fclgpu_comm_rank", "fclgpu_comm_world",
     "fclgpu_comm_allgather", "fclgpu_comm_allgather_ragged", "fclgpu_comm_destroy", "fclgpu_comm_last_error",
     "fclgpu_model_create_obbrss", "fclgpu_model_from_bvh", "fclgpu_model_destroy", "fclgpu_model_num_nodes",
@@ -121,6 +125,15 @@ def lib():
                                                     dp, ip, ip, up, up]
     L.fclgpu_within_tolerance_batch.argtypes = [vp, vp, C.c_int64, dp, dp, C.c_double, vp, dp, up, up, vp]
     L.fclgpu_within_tolerance_batch_host.argtypes = [vp, vp, C.c_int64, dp, dp, C.c_double, vp, dp, up, up]
+    L.fclgpu_collide_mesh_plane_batch.argtypes = [vp, C.c_int32, dp, C.c_double, C.c_int64, dp, dp, C.POINTER(CollisionRequestC), ip,
+                                                  vp, C.c_int64, vp, up, up, vp]
+    L.fclgpu_collide_mesh_plane_batch_host.argtypes = [vp, C.c_int32, dp, C.c_double, C.c_int64, dp, dp, C.POINTER(CollisionRequestC),
+                                                       ip, vp, C.c_int64, vp, up, up]
+    L.fclgpu_load_obj.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.c_int32),
+                                  C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32)]
+    L.fclgpu_save_obj.argtypes = [C.c_char_p, dp, C.c_int32, ip, C.c_int32]
+    L.fclgpu_free.argtypes = [vp]
+    L.fclgpu_free.restype = None
     L.fclgpu_shard_range.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.fclgpu_shard_range.restype = None
     L.fclgpu_comm_unique_id.argtypes = [C.c_char_p]

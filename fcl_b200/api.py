@@ -309,6 +309,12 @@ class BVHModel:
             raise FclGpuError(rc, "endModel failed")
         return m
 
+    @classmethod
+    def from_obj(cls, path, split_method=SPLIT_METHOD_MEAN, build_on_device=False):
+        """The reference's test set-up: loadOBJFile + beginModel / addSubModel / endModel (test_fcl_collision.cpp:792-815)."""
+        verts, tris = loadOBJFile(path)
+        return cls.from_arrays(verts, tris, split_method, build_on_device)
+
     def getNumBVs(self):
         if self._bvh is None:
             return 2 * self.num_tris - 1 if (self.build_on_device and self.build_state == BVH_BUILD_STATE_PROCESSED) else 0
@@ -389,6 +395,53 @@ class Sphere:
 
     def getNodeType(self):
         return "GEOM_SPHERE"
+
+
+class _PlaneShape:
+    """n . x <= d (Halfspace) / n . x = d (Plane) in the shape's own frame; the constructor normalises like the
+    reference's unitNormalTest (geometry/shape/halfspace-inl.h:144-160, plane-inl.h:144-160)."""
+
+    def __init__(self, n, d=0.0, *rest):
+        if rest:  # Halfspace(a, b, c, d)
+            n, d = (n, d, rest[0]), rest[1]
+        n = np.asarray(n, np.float64).reshape(3)
+        l = float(np.sqrt((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]))
+        if l > 0:
+            inv_l = 1.0 / l
+            self.n, self.d = n * inv_l, float(d) * inv_l
+        else:
+            self.n, self.d = np.array([1.0, 0.0, 0.0]), 0.0
+        self.cost_density = 1.0
+        self.threshold_occupied = 1.0
+        self.threshold_free = 0.0
+
+    def signedDistance(self, p):
+        p = np.asarray(p, np.float64)
+        return float((self.n[0] * p[0] + self.n[1] * p[1]) + self.n[2] * p[2]) - self.d
+
+    def getObjectType(self):
+        return "OT_GEOM"
+
+
+class Halfspace(_PlaneShape):
+    """fcl::Halfspace<double> (geometry/shape/halfspace.h): second geometry of a mesh <-> halfspace collide."""
+
+    _kind = _capi.SHAPE_HALFSPACE
+
+    def getNodeType(self):
+        return "GEOM_HALFSPACE"
+
+
+class Plane(_PlaneShape):
+    """fcl::Plane<double> (geometry/shape/plane.h): second geometry of a mesh <-> plane collide."""
+
+    _kind = _capi.SHAPE_PLANE
+
+    def getNodeType(self):
+        return "GEOM_PLANE"
+
+    def distance(self, p):
+        return abs(self.signedDistance(p))
 
 
 class CollisionObject:
@@ -544,6 +597,32 @@ def _out(shape, dtype, pinned, tag=""):
     return t.numpy()[:nbytes].view(dtype).reshape(shape), t
 
 
+def loadOBJFile(path):
+    """loadOBJFile (test/test_fcl_utility.h:194-280) through the C ABI: (vertices (nv, 3) float64, triangles (nt, 3) int32)."""
+    L = _capi.lib()
+    v, t = C.POINTER(C.c_double)(), C.POINTER(C.c_int32)()
+    nv, nt = C.c_int32(0), C.c_int32(0)
+    rc = L.fclgpu_load_obj(str(path).encode(), C.byref(v), C.byref(nv), C.byref(t), C.byref(nt))
+    if rc == _capi.ERR_INCORRECT_DATA:
+        sys.stderr.write("file not exist\n")  # the reference's message; it returns empty arrays
+        return np.zeros((0, 3)), np.zeros((0, 3), np.int32)
+    check(rc)
+    try:
+        verts = np.ctypeslib.as_array(v, shape=(nv.value, 3)).copy() if nv.value else np.zeros((0, 3))
+        tris = np.ctypeslib.as_array(t, shape=(nt.value, 3)).copy() if nt.value else np.zeros((0, 3), np.int32)
+    finally:
+        L.fclgpu_free(v)
+        L.fclgpu_free(t)
+    return verts, tris
+
+
+def saveOBJFile(path, verts, tris):
+    """saveOBJFile (test/test_fcl_utility.h:283-309); coordinates with 17 significant digits (exact round trip)."""
+    v = np.ascontiguousarray(verts, np.float64).reshape(-1, 3)
+    t = np.ascontiguousarray(tris, np.int32).reshape(-1, 3)
+    check(_capi.lib().fclgpu_save_obj(str(path).encode(), addr(v), len(v), addr(t), len(t)))
+
+
 class BatchCollisionResult:
     """num_contacts[n] plus the contact list of every query.
 
@@ -670,6 +749,44 @@ def collide_mesh_sphere_batch(o1, tf1, sphere, tf2, request, contact_capacity=No
         return collide_mesh_sphere_batch(o1, tf1, sphere, tf2, request, contact_capacity=int(counts.sum(dtype=np.int64)),
                                          want_contacts=True, stats=stats, device=device, grow_on_overflow=False,
                                          stage_capacity=max(int(counts.max()), 1))
+    check(rc)
+    if want_contacts:
+        contacts = contacts[: offsets[n]]
+    return BatchCollisionResult(counts, contacts, offsets, n_bv, n_leaf)
+
+
+def collide_mesh_plane_batch(o1, tf1, shape, tf2, request, contact_capacity=None, want_contacts=True, stats=False,
+                             device=None, grow_on_overflow=False, stage_capacity=0):
+    """n independent fcl::collide(mesh, tf1[i], Halfspace | Plane, tf2[i]) calls (host arrays in and out).  Contacts: one
+    per intersecting triangle, b2 = -1 (Contact::NONE), in the reference's traversal order."""
+    tf1, n1 = _poses(tf1)
+    tf2, n2 = _poses(tf2)
+    n = n1 if n1 is not None else n2
+    if n is None:
+        raise ValueError("at least one of tf1/tf2 must be given")
+    if n1 is not None and n2 is not None and n1 != n2:
+        raise ValueError("tf1 and tf2 must have the same length")
+    m1 = o1.device_model(device)
+    req = request._c(stage_capacity)
+    counts = np.zeros(n, np.int32)
+    if want_contacts:
+        if contact_capacity is None:
+            contact_capacity = int(min(max(request.num_max_contacts, 0), 64)) * n
+        contact_capacity = max(int(contact_capacity), 1)
+        contacts = np.zeros(contact_capacity, CONTACT_DTYPE)
+        offsets = np.zeros(n + 1, np.int64)
+    else:
+        contact_capacity, contacts, offsets = 0, None, None
+    n_bv = np.zeros(n, np.uint32) if stats else None
+    n_leaf = np.zeros(n, np.uint32) if stats else None
+    nrm = np.ascontiguousarray(shape.n, np.float64)
+    rc = _capi.lib().fclgpu_collide_mesh_plane_batch_host(m1, shape._kind, addr(nrm), float(shape.d), n, addr(tf1), addr(tf2),
+                                                          C.byref(req), addr(counts), addr(contacts), contact_capacity,
+                                                          addr(offsets), addr(n_bv), addr(n_leaf))
+    if rc == _capi.ERR_CONTACT_OVERFLOW and grow_on_overflow:
+        return collide_mesh_plane_batch(o1, tf1, shape, tf2, request, contact_capacity=int(counts.sum(dtype=np.int64)),
+                                        want_contacts=True, stats=stats, device=device, grow_on_overflow=False,
+                                        stage_capacity=max(int(counts.max()), 1))
     check(rc)
     if want_contacts:
         contacts = contacts[: offsets[n]]
@@ -803,12 +920,13 @@ def collide(o1, tf1, o2=None, tf2=None, request=None, result=None):
     if request.num_max_contacts == 0:
         sys.stderr.write(f"Warning: should stop early as num_max_contact is {request.num_max_contacts} !\n")
         return 0
-    if isinstance(o1, Sphere) and isinstance(o2, BVHModel):
+    if isinstance(o1, (Sphere, _PlaneShape)) and isinstance(o2, BVHModel):
         # (OT_GEOM, OT_BVH): the reference calls the [BVH][GEOM] cell with the arguments swapped and does not flip
         # the contacts (collision-inl.h:124-134), so o1 of every contact is the mesh
         o1, tf1, o2, tf2 = o2, tf2, o1, tf1
     mesh_sphere = isinstance(o1, BVHModel) and isinstance(o2, Sphere)
-    if not (isinstance(o1, BVHModel) and isinstance(o2, BVHModel)) and not mesh_sphere:
+    mesh_plane = isinstance(o1, BVHModel) and isinstance(o2, _PlaneShape)
+    if not (isinstance(o1, BVHModel) and isinstance(o2, BVHModel)) and not mesh_sphere and not mesh_plane:
         sys.stderr.write("Warning: collision function between these node types is not supported\n")
         return 0
     if request.isSatisfied(result):  # orientedMeshCollide / orientedBVHShapeCollide, collision_func_matrix-inl.h:580,389
@@ -818,8 +936,12 @@ def collide(o1, tf1, o2=None, tf2=None, request=None, result=None):
     # a non-empty result consumes part of the contact budget
     budget = request.num_max_contacts - result.numContacts()
     sub = CollisionRequest(budget, request.enable_contact)
+    ident = np.array([[1.0, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0]])
     if mesh_sphere:
         r = collide_mesh_sphere_batch(o1, tf1, o2, tf2, sub, contact_capacity=min(budget, 256), grow_on_overflow=True)
+    elif mesh_plane:
+        r = collide_mesh_plane_batch(o1, ident if tf1 is None else tf1, o2, ident if tf2 is None else tf2, sub,
+                                     contact_capacity=min(budget, 256), grow_on_overflow=True)
     else:
         r = collide_batch(o1, tf1, o2, tf2, sub, contact_capacity=min(budget, 256), grow_on_overflow=True)
     for c in r.contacts_of(0):

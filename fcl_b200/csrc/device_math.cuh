@@ -735,6 +735,67 @@ FD bool sphere_tri_intersect(const V3& c, double radius, const V3 P[3], V3& cp, 
 }
 
 // ---------------------------------------------------------------------------------------
+// Halfspace / Plane vs triangle (mesh <-> halfspace / plane collide): halfspaceTriangleIntersect,
+// narrowphase/detail/primitive_shape_algorithm/halfspace-inl.h:587-621, and planeTriangleIntersect, plane-inl.h:683-759.
+// The shape is given ALREADY TRANSFORMED to the frame of the vertices (n = tf.linear() * n0, d = d0 + n . tf.translation(),
+// geometry/shape/halfspace-inl.h:168-180); V[3] = the triangle's vertices in that frame.  Outputs as the reference writes
+// them (the traversal node negates the normal).  Structure differs from the oracle's restatement (the plane routine
+// keeps the lone vertex and the two others in named registers instead of index arrays), arithmetic order is the same.
+// ---------------------------------------------------------------------------------------
+FD bool halfspace_tri_intersect(const V3& n, double d, const V3 V[3], V3& cp, double& depth_out, V3& nrm) {
+  V3 v = V[0];
+  double depth = dot(n, v) - d;
+#pragma unroll
+  for (int k = 1; k < 3; ++k) {
+    const double dk = dot(n, V[k]) - d;
+    if (dk < depth) {
+      depth = dk;
+      v = V[k];
+    }
+  }
+  if (!(depth <= 0)) return false;
+  depth_out = -depth;
+  nrm = n;
+  cp = v - n * (0.5 * depth);
+  return true;
+}
+
+FD bool plane_tri_intersect(const V3& n, double d, const V3 V[3], V3& cp, double& depth_out, V3& nrm) {
+  const double d0 = dot(n, V[0]) - d, d1 = dot(n, V[1]) - d, d2 = dot(n, V[2]) - d;
+  if ((d0 >= 0 && d1 >= 0 && d2 >= 0) || (d0 <= 0 && d1 <= 0 && d2 <= 0)) return false;
+  const bool p0 = d0 > 0, p1 = d1 > 0, p2 = d2 > 0;
+  const int n_positive = (int)p0 + (int)p1 + (int)p2;
+  double d_positive = 0, d_negative = 0;
+  // running maxima in vertex order, `<=` like the reference
+  if (p0) { if (d_positive <= d0) d_positive = d0; } else { if (d_negative <= -d0) d_negative = -d0; }
+  if (p1) { if (d_positive <= d1) d_positive = d1; } else { if (d_negative <= -d1) d_negative = -d1; }
+  if (p2) { if (d_positive <= d2) d_positive = d2; } else { if (d_negative <= -d2) d_negative = -d2; }
+  depth_out = dmin(d_positive, d_negative);
+  nrm = (d_positive > d_negative) ? n : mk(-n.x, -n.y, -n.z);
+  // the lone vertex q (the only one on its side) and the two others a, b in vertex order
+  const bool lone_positive = n_positive == 1;
+  const bool q0 = p0 == lone_positive, q1 = p1 == lone_positive;  // is vertex k the lone one?
+  const V3 q = q0 ? V[0] : (q1 ? V[1] : V[2]);
+  const double qd = q0 ? d0 : (q1 ? d1 : d2);
+  const V3 a = q0 ? V[1] : V[0];
+  const double ad = q0 ? d1 : d0;
+  const V3 b = (q0 || q1) ? V[2] : V[1];
+  const double bd = (q0 || q1) ? d2 : d1;
+  V3 t1, t2;
+  if (n_positive == 2) {  // a, b positive: t = (-p * q_d + q * p_d) / (-q_d + p_d)
+    const double den1 = -qd + ad, den2 = -qd + bd;
+    t1 = mk(((-a.x) * qd + q.x * ad) / den1, ((-a.y) * qd + q.y * ad) / den1, ((-a.z) * qd + q.z * ad) / den1);
+    t2 = mk(((-b.x) * qd + q.x * bd) / den2, ((-b.y) * qd + q.y * bd) / den2, ((-b.z) * qd + q.z * bd) / den2);
+  } else {                // a, b not positive: t = (p * q_d - q * p_d) / (q_d - p_d)
+    const double den1 = qd - ad, den2 = qd - bd;
+    t1 = mk((a.x * qd - q.x * ad) / den1, (a.y * qd - q.y * ad) / den1, (a.z * qd - q.z * ad) / den1);
+    t2 = mk((b.x * qd - q.x * bd) / den2, (b.y * qd - q.y * bd) / den2, (b.z * qd - q.z * bd) / den2);
+  }
+  cp = (t1 + t2) * 0.5;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------
 // Sphere vs triangle distance (mesh <-> sphere distance): the nearest-point overload of
 // sphereTriangleDistance (sphere_triangle-inl.h:469-496) on top of Project::projectTriangle / projectLine
 // (math/detail/project-inl.h:54-123).  o = sphere centre, P[3] = triangle, same frame.

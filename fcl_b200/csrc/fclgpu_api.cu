@@ -782,6 +782,8 @@ struct CollideExtra {
   long long ready_q0 = 0;           // index of this call's first query in the flagged batch
   bool continue_scan = false;       // keep the running contact offset of the previous call (sub-batches of one result)
   double sphere_radius = -1.0;      // >= 0: model 2 is a sphere of this radius (mesh <-> sphere collide)
+  int plane_kind = -1;              // 0 / 1: model 2 is a halfspace / plane {n . x <= d / n . x = d} (normalised)
+  double plane_n[3] = {0, 0, 0}, plane_d = 0;
 };
 int collide_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1, const double* tf2,
                     const fclgpu_collision_request* request, int32_t* num_contacts, fclgpu_contact* contacts,
@@ -806,7 +808,8 @@ int collide_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, c
   if (m1->device != m2->device) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "models live on different devices");
   if (request->enable_cost) return fail(FCLGPU_ERR_UNSUPPORTED_FUNCTION, "cost sources are not supported on this path");
   if (!num_contacts) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "num_contacts is NULL");
-  if (m1->depth + (X.sphere_radius >= 0 ? 0 : m2->depth) + 2 > kStackCap)
+  const bool shape2 = X.sphere_radius >= 0 || X.plane_kind >= 0;  // model 2 is a primitive shape: one-sided traversal
+  if (m1->depth + (shape2 ? 0 : m2->depth) + 2 > kStackCap)
     return fail(FCLGPU_ERR_STACK_OVERFLOW, "tree depths %d+%d exceed the traversal stack", m1->depth, m2->depth);
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_TRY(cudaSetDevice(m1->device));
@@ -830,7 +833,7 @@ int collide_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, c
   const StreamState ss = stream_state(w, st);
   const long long trav0 = opt("traversal");
 
-  if (want_contacts && trav0 >= 3 && !opt("contact_order") && X.sphere_radius < 0) {
+  if (want_contacts && trav0 >= 3 && !opt("contact_order") && !shape2) {
     // Contact list, default path: ONE launch of the warp-per-query ordered-front kernel (collide_ordered.cuh).
     // Contacts are staged per RESIDENT WARP (L2-resident) and appended to the caller's pool when a query retires.
     const long long stride = std::min<long long>(request->num_max_contacts, stage_capacity(request));
@@ -922,6 +925,11 @@ int collide_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, c
     if (X.sphere_radius >= 0) {
       rc = stats ? launch_persistent(collide_mesh_sphere_kernel<true>, P, w, 128, st, 0, X.sphere_radius)
                  : launch_persistent(collide_mesh_sphere_kernel<false>, P, w, 128, st, 0, X.sphere_radius);
+    } else if (X.plane_kind >= 0) {
+      rc = stats ? launch_persistent(collide_mesh_plane_kernel<true>, P, w, 128, st, 0, X.plane_kind, X.plane_n[0], X.plane_n[1],
+                                     X.plane_n[2], X.plane_d)
+                 : launch_persistent(collide_mesh_plane_kernel<false>, P, w, 128, st, 0, X.plane_kind, X.plane_n[0], X.plane_n[1],
+                                     X.plane_n[2], X.plane_d);
     } else if (!want_contacts && !P.enable_contact && trav >= 1 &&
         (front >= 2 || (front == 1 && ((long long)m1->d.n_nodes + m2->d.n_nodes >= (1 << 17) || cn <= opt("front_small_batch"))))) {
       // counts only: the result does not depend on the visiting order -> warp-per-query front kernel.  Chosen for BVHs
@@ -995,6 +1003,39 @@ extern "C" int fclgpu_collide_mesh_sphere_batch(const fclgpu_model* m1, double r
   X.sphere_radius = radius;
   return collide_enqueue(m1, m1, n, tf1, tf2, request, num_contacts, contacts, contact_capacity, contact_offsets, n_bv,
                          n_leaf, stream, X);
+}
+
+// ------------------------------------------------------------------------------------------
+// mesh <-> halfspace / plane collide
+// ------------------------------------------------------------------------------------------
+namespace {
+// Halfspace(n, d) / Plane(n, d) constructors -> unitNormalTest (geometry/shape/halfspace-inl.h:144-160)
+int plane_extra(int kind, const double* normal3, double d, CollideExtra& X) {
+  if (!normal3) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "normal is NULL");
+  const double l = std::sqrt((normal3[0] * normal3[0] + normal3[1] * normal3[1]) + normal3[2] * normal3[2]);
+  X.plane_kind = kind;
+  if (l > 0) {
+    const double inv_l = 1.0 / l;
+    for (int k = 0; k < 3; ++k) X.plane_n[k] = normal3[k] * inv_l;
+    X.plane_d = d * inv_l;
+  } else {
+    X.plane_n[0] = 1; X.plane_n[1] = 0; X.plane_n[2] = 0;
+    X.plane_d = 0;
+  }
+  return FCLGPU_OK;
+}
+}  // namespace
+
+extern "C" int fclgpu_collide_mesh_plane_batch(const fclgpu_model* m1, int32_t shape, const double* normal3, double d, int64_t n,
+                                               const double* tf1, const double* tf2, const fclgpu_collision_request* request,
+                                               int32_t* num_contacts, fclgpu_contact* contacts, int64_t contact_capacity,
+                                               int64_t* contact_offsets, uint32_t* n_bv, uint32_t* n_leaf, void* stream) {
+  if (shape != FCLGPU_SHAPE_HALFSPACE && shape != FCLGPU_SHAPE_PLANE) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "shape must be FCLGPU_SHAPE_HALFSPACE or FCLGPU_SHAPE_PLANE");
+  CollideExtra X;
+  int rc = plane_extra(shape == FCLGPU_SHAPE_HALFSPACE ? 0 : 1, normal3, d, X);
+  if (rc) return rc;
+  return collide_enqueue(m1, m1, n, tf1, tf2, request, num_contacts, contacts, contact_capacity, contact_offsets, n_bv, n_leaf,
+                         stream, X);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1457,11 +1498,11 @@ extern "C" int fclgpu_distance_mesh_sphere_batch_host(const fclgpu_model* m1, do
   return distance_host(m1, m1, n, tf1, tf2, request, min_distance, nearest_p1, nearest_p2, b1, b2, n_bv, n_leaf, radius);
 }
 
-extern "C" int fclgpu_collide_mesh_sphere_batch_host(const fclgpu_model* m1, double radius, int64_t n, const double* tf1,
-                                                     const double* tf2, const fclgpu_collision_request* request,
-                                                     int32_t* num_contacts, fclgpu_contact* contacts,
-                                                     int64_t contact_capacity, int64_t* contact_offsets, uint32_t* n_bv,
-                                                     uint32_t* n_leaf) {
+namespace {
+// host-pointer wrapper shared by the mesh <-> primitive-shape collide entry points (X names the shape)
+int mesh_shape_collide_host(const fclgpu_model* m1, const CollideExtra& X, int64_t n, const double* tf1, const double* tf2,
+                            const fclgpu_collision_request* request, int32_t* num_contacts, fclgpu_contact* contacts,
+                            int64_t contact_capacity, int64_t* contact_offsets, uint32_t* n_bv, uint32_t* n_leaf) {
   if (!m1 || !request || n < 0 || !num_contacts) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL model/request/num_contacts or n<0");
   CUDA_TRY(cudaSetDevice(m1->device));
   Workspace* w;
@@ -1489,8 +1530,7 @@ extern "C" int fclgpu_collide_mesh_sphere_batch_host(const fclgpu_model* m1, dou
   cudaStream_t st = w->pipe[1];
   if (tf1) CUDA_TRY(cudaMemcpyAsync(d_tf1, tf1, 96 * (size_t)n, cudaMemcpyHostToDevice, st));
   if (tf2) CUDA_TRY(cudaMemcpyAsync(d_tf2, tf2, 96 * (size_t)n, cudaMemcpyHostToDevice, st));
-  rc = fclgpu_collide_mesh_sphere_batch(m1, radius, n, d_tf1, d_tf2, request, d_cnt, d_con, contact_capacity, d_off, d_bv,
-                                        d_leaf, st);
+  rc = collide_enqueue(m1, m1, n, d_tf1, d_tf2, request, d_cnt, d_con, contact_capacity, d_off, d_bv, d_leaf, st, X);
   if (rc) return rc;
   if (n > 0) CUDA_TRY(cudaMemcpyAsync(num_contacts, d_cnt, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
   if (n_bv && n > 0) CUDA_TRY(cudaMemcpyAsync(n_bv, d_bv, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
@@ -1506,6 +1546,29 @@ extern "C" int fclgpu_collide_mesh_sphere_batch_host(const fclgpu_model* m1, dou
     std::memset(contact_offsets, 0, 8 * (size_t)(n + 1));
   }
   return fclgpu_sync_status(m1->device, st);
+}
+}  // namespace
+
+extern "C" int fclgpu_collide_mesh_sphere_batch_host(const fclgpu_model* m1, double radius, int64_t n, const double* tf1,
+                                                     const double* tf2, const fclgpu_collision_request* request,
+                                                     int32_t* num_contacts, fclgpu_contact* contacts,
+                                                     int64_t contact_capacity, int64_t* contact_offsets, uint32_t* n_bv,
+                                                     uint32_t* n_leaf) {
+  if (!(radius >= 0)) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "sphere radius must be >= 0");
+  CollideExtra X;
+  X.sphere_radius = radius;
+  return mesh_shape_collide_host(m1, X, n, tf1, tf2, request, num_contacts, contacts, contact_capacity, contact_offsets, n_bv, n_leaf);
+}
+
+extern "C" int fclgpu_collide_mesh_plane_batch_host(const fclgpu_model* m1, int32_t shape, const double* normal3, double d, int64_t n,
+                                                    const double* tf1, const double* tf2, const fclgpu_collision_request* request,
+                                                    int32_t* num_contacts, fclgpu_contact* contacts, int64_t contact_capacity,
+                                                    int64_t* contact_offsets, uint32_t* n_bv, uint32_t* n_leaf) {
+  if (shape != FCLGPU_SHAPE_HALFSPACE && shape != FCLGPU_SHAPE_PLANE) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "shape must be FCLGPU_SHAPE_HALFSPACE or FCLGPU_SHAPE_PLANE");
+  CollideExtra X;
+  const int rc = plane_extra(shape == FCLGPU_SHAPE_HALFSPACE ? 0 : 1, normal3, d, X);
+  if (rc) return rc;
+  return mesh_shape_collide_host(m1, X, n, tf1, tf2, request, num_contacts, contacts, contact_capacity, contact_offsets, n_bv, n_leaf);
 }
 
 

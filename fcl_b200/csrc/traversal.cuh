@@ -1511,14 +1511,25 @@ namespace fclgpu {
 // once the BVH no longer fits the caches (cfg5: 1M-triangle meshes).  Near the stack limit the
 // warp falls back to one expansion per round (plain DFS, depth-bounded), so it never overflows.
 // ---------------------------------------------------------------------------------------
-constexpr int kFrontStackCap = 768;
+constexpr int kFrontStackCap = 512;
 constexpr int kFrontLeafCap = 64;
 
+// A front entry carries everything the NEXT round needs to expand it without touching memory: both node ids, both
+// first_child fields (fetched, together with the box records, when the pair was tested) and the firstOverSecond decision
+// (bit 31 of b1).  A round is then pop -> expand -> ONE dependent global-load phase (records + topo of the two children)
+// -> test -> push, instead of two phases (topo of the popped pair, then the children's records): the kernel is latency
+// bound once the BVH leaves the caches (ncu on cfg5: 55 % of the stall samples were long_scoreboard).
 struct __align__(16) CollideFront {
-  uint2 pair[kFrontStackCap];
+  uint4 pair[kFrontStackCap];  // {b1 | split-first flag, b2, first_child1, first_child2}
   uint2 leaf[kFrontLeafCap];
-  uint2 expand[32];
+  uint4 expand[32];            // {node1, node2, first_child of the node that was NOT split (carried), which side was split}
 };
+
+__device__ __forceinline__ uint4 front_entry(int b1, int b2, int fc1, double size1, int fc2, double size2) {
+  const bool l1 = fc1 < 0, l2 = fc2 < 0;
+  const bool first = l2 || (!l1 && (size1 > size2));  // firstOverSecond (bvh_collision_traversal_node-inl.h:78-90)
+  return make_uint4((unsigned)b1 | (first ? 0x80000000u : 0u), (unsigned)b2, (unsigned)fc1, (unsigned)fc2);
+}
 
 template <bool kStats>
 __global__ void __launch_bounds__(128, 4) collide_front_kernel(CollideParams P) {
@@ -1553,8 +1564,12 @@ __global__ void __launch_bounds__(128, 4) collide_front_kernel(CollideParams P) 
     uint32_t bv_tests = 1, leaf_tests = 0;
     {  // root pair
       const ObbRec32 n1 = load_obb32(P.m1.obb32, 0), n2 = load_obb32(P.m2.obb32, 0);
+      int fc1, fc2;
+      double size1, size2;
+      load_topo(P.m1.topo, 0, fc1, size1);
+      load_topo(P.m2.topo, 0, fc2, size2);
       if (!obb_certainly_disjoint_f32(Rf, Tf, t_l1, n1, n2)) {
-        if (lane == 0) S.pair[0] = make_uint2(0u, 0u);
+        if (lane == 0) S.pair[0] = front_entry(0, 0, fc1, size1, fc2, size2);
         sp = 1;
       }
     }
@@ -1586,20 +1601,14 @@ __global__ void __launch_bounds__(128, 4) collide_front_kernel(CollideParams P) 
       }
       if (sp == 0) break;
 
-      // ---- BV round: entries on the stack are known to overlap ----
+      // ---- BV round: entries on the stack are known to overlap; no memory access before the expansion ----
       const bool tight = sp > kFrontStackCap - 160;  // close to the limit: one entry per round (depth-first)
       const int k = tight ? 1 : (sp < 32 ? sp : 32);
-      uint2 pr = make_uint2(0u, 0u);
-      int fc1 = 0, fc2 = 0;
-      double size1 = 0.0, size2 = 0.0;
+      uint4 pr = make_uint4(0u, 0u, 0u, 0u);
       const bool have = lane < k;
-      if (have) {
-        pr = S.pair[sp - 1 - lane];
-        load_topo(P.m1.topo, (int)pr.x, fc1, size1);
-        load_topo(P.m2.topo, (int)pr.y, fc2, size2);
-      }
-      const bool l1 = fc1 < 0, l2 = fc2 < 0;
-      const bool leafpair = have && l1 && l2;
+      if (have) pr = S.pair[sp - 1 - lane];
+      const int fc1 = (int)pr.z, fc2 = (int)pr.w;
+      const bool leafpair = have && fc1 < 0 && fc2 < 0;
       const unsigned lm = __ballot_sync(0xffffffffu, leafpair);
       if (leafpair) S.leaf[nleaf + __popc(lm & lt_mask)] = make_uint2((unsigned)(-(fc1 + 1)), (unsigned)(-(fc2 + 1)));
       nleaf += __popc(lm);
@@ -1611,12 +1620,13 @@ __global__ void __launch_bounds__(128, 4) collide_front_kernel(CollideParams P) 
       __syncwarp();  // every lane has read its popped entry before slots are overwritten
       if (internal) {
         if (rank < n_exp) {
-          if (l2 || (!l1 && (size1 > size2))) {  // firstOverSecond
-            S.expand[2 * rank] = make_uint2((unsigned)fc1, pr.y);
-            S.expand[2 * rank + 1] = make_uint2((unsigned)fc1 + 1u, pr.y);
+          const unsigned b1 = pr.x & 0x7fffffffu;
+          if (pr.x >> 31) {  // split model 1's node: children fc1, fc1 + 1 against b2 (whose first_child is carried)
+            S.expand[2 * rank] = make_uint4((unsigned)fc1, pr.y, pr.w, 1u);
+            S.expand[2 * rank + 1] = make_uint4((unsigned)fc1 + 1u, pr.y, pr.w, 1u);
           } else {
-            S.expand[2 * rank] = make_uint2(pr.x, (unsigned)fc2);
-            S.expand[2 * rank + 1] = make_uint2(pr.x, (unsigned)fc2 + 1u);
+            S.expand[2 * rank] = make_uint4(b1, (unsigned)fc2, pr.z, 0u);
+            S.expand[2 * rank + 1] = make_uint4(b1, (unsigned)fc2 + 1u, pr.z, 0u);
           }
         } else {  // not expanded this round: back on the stack
           S.pair[sp + (n_int - 1 - rank)] = pr;
@@ -1625,16 +1635,22 @@ __global__ void __launch_bounds__(128, 4) collide_front_kernel(CollideParams P) 
       sp += n_int - n_exp;
       __syncwarp();
       bool keep = false;
-      uint2 xy = make_uint2(0u, 0u);
+      uint4 entry = make_uint4(0u, 0u, 0u, 0u);
       if (lane < 2 * n_exp) {
-        xy = S.expand[lane];
+        const uint4 xy = S.expand[lane];
+        // one load phase: both box records, and {first_child, size} of both nodes for the entry to be pushed
         const ObbRec32 n1 = load_obb32(P.m1.obb32, (int)xy.x);
         const ObbRec32 n2 = load_obb32(P.m2.obb32, (int)xy.y);
+        int f1, f2;
+        double s1, s2;
+        load_topo(P.m1.topo, (int)xy.x, f1, s1);
+        load_topo(P.m2.topo, (int)xy.y, f2, s2);
         keep = !obb_certainly_disjoint_f32(Rf, Tf, t_l1, n1, n2);
+        entry = front_entry((int)xy.x, (int)xy.y, f1, s1, f2, s2);
       }
       if (kStats) bv_tests += 2 * n_exp;
       const unsigned km = __ballot_sync(0xffffffffu, keep);
-      if (keep) S.pair[sp + __popc(km & lt_mask)] = xy;
+      if (keep) S.pair[sp + __popc(km & lt_mask)] = entry;
       sp += __popc(km);
       __syncwarp();
     }
@@ -1721,6 +1737,103 @@ __global__ void __launch_bounds__(128) collide_mesh_sphere_kernel(CollideParams 
       V3 cp, nrm;
       double depth;
       if (sphere_tri_intersect(c, radius, T, cp, depth, nrm)) {
+        if (count < P.max_contacts) {
+          if (P.scratch) {
+            if (count < P.stride) {
+              fclgpu_contact* o = P.scratch + q * P.stride + count;
+              o->b1 = id;
+              o->b2 = -1;
+              if (P.enable_contact) {
+                o->normal[0] = -nrm.x; o->normal[1] = -nrm.y; o->normal[2] = -nrm.z;
+                o->pos[0] = cp.x; o->pos[1] = cp.y; o->pos[2] = cp.z;
+                o->penetration_depth = depth;
+              }
+            } else {
+              atomicMin(P.status, (int)FCLGPU_ERR_CONTACT_OVERFLOW);
+            }
+          }
+          count++;
+        }
+        if (count > 0 && P.max_contacts <= count) sp = 0;  // canStop()
+      }
+    }
+    P.num_contacts[q] = (int32_t)count;
+    if (kStats) {
+      if (P.n_bv) P.n_bv[q] = bv_tests;
+      if (P.n_leaf) P.n_leaf[q] = leaf_tests;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Mesh <-> halfspace / plane collide: fcl::collide(BVHModel<OBBRSS>, tf1, Halfspace | Plane, tf2) =
+// BVHShapeCollider<OBBRSS, Shape> -> orientedBVHShapeCollide (collision_func_matrix-inl.h:378-430; cells :841-842) with
+// the closed-form leaf tests halfspaceTriangleIntersect / planeTriangleIntersect (gjk_solver_libccd-inl.h:502-540).
+// One lane per query, depth first, left child first: one contact per intersecting triangle in the reference's order,
+// {b1 = triangle, b2 = -1, pos, -normal, depth}.
+// BV test: the reference tests the node's OBB against the shape's OBB -- for a halfspace that is the infinite box
+// (utility-inl.h:361-373: nothing is ever pruned), for a plane the slab of zero thickness (:657-669: only the plane's
+// normal can separate).  Any conservative test yields the same contacts; here: the signed distance of the box to the
+// plane along the normal, s - r > margin (halfspace) or |s| - r > margin (plane), evaluated in the mesh frame.
+// kind 0 = halfspace, 1 = plane; (n0, d0) = the shape's own normalised parameters.
+// ---------------------------------------------------------------------------------------
+template <bool kStats>
+__global__ void __launch_bounds__(128) collide_mesh_plane_kernel(CollideParams P, int kind, double n0x, double n0y, double n0z, double d0) {
+  int stk[kStackCap];
+  bool exhausted = false;
+  while (true) {
+    const long long q = fetch_work(!exhausted, P.work_counter);
+    if (__all_sync(0xffffffffu, exhausted || q >= P.n)) break;
+    if (exhausted) continue;
+    if (q >= P.n) {
+      exhausted = true;
+      continue;
+    }
+    const PoseRT tf1 = load_pose(P.tf1, q);
+    const PoseRT tf2 = load_pose(P.tf2, q);
+    // transform(shape, tf2): n' = R2 n, d' = d + n' . t2 (halfspace-inl.h:168-180)
+    const V3 nw = mulv(tf2.R, mk(n0x, n0y, n0z));
+    const double dw = d0 + dot(nw, tf2.t);
+    // the same plane in the mesh frame (steering only)
+    const V3 nm = mulTv(tf1.R, nw);
+    const double dm = dw - dot(nw, tf1.t);
+    const double base_scale = (fabs(dm) + fabs(dw)) + ((fabs(tf1.t.x) + fabs(tf1.t.y)) + fabs(tf1.t.z));
+    long long count = 0;
+    uint32_t bv_tests = 0, leaf_tests = 0;
+    int sp = 0;
+    stk[sp++] = 0;
+    while (sp > 0) {
+      const int b = stk[--sp];
+      const NodeRec nd = load_node(P.m1.obb, b);
+      const int fc = __ldg(P.m1.first_child + b);
+      if (kStats) bv_tests++;
+      {
+        const double sdist = dot(nm, nd.To) - dm;
+        const V3 pa = mulTv(nd.axis, nm);  // n . a_i
+        const double reach = (nd.e0 * fabs(pa.x) + nd.e1 * fabs(pa.y)) + nd.e2 * fabs(pa.z);
+        const double scale = (((fabs(nd.To.x) + fabs(nd.To.y)) + fabs(nd.To.z)) + ((nd.e0 + nd.e1) + nd.e2)) + base_scale;
+        const double gap = (kind == 0 ? sdist : fabs(sdist)) - reach;
+        if (gap > 1e-9 * scale) continue;  // certainly no triangle of this subtree touches the shape
+      }
+      if (fc >= 0) {
+        if (sp + 2 > kStackCap) {
+          atomicMin(P.status, (int)FCLGPU_ERR_STACK_OVERFLOW);
+          break;
+        }
+        stk[sp++] = fc + 1;
+        stk[sp++] = fc;  // left child first
+        continue;
+      }
+      const int id = -(fc + 1);
+      V3 T[3];
+      load_tri(P.m1.tri, id, T);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) T[k] = mulv(tf1.R, T[k]) + tf1.t;  // tf1 * P
+      if (kStats) leaf_tests++;
+      V3 cp, nrm;
+      double depth;
+      const bool hit = kind == 0 ? halfspace_tri_intersect(nw, dw, T, cp, depth, nrm) : plane_tri_intersect(nw, dw, T, cp, depth, nrm);
+      if (hit) {
         if (count < P.max_contacts) {
           if (P.scratch) {
             if (count < P.stride) {

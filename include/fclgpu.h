@@ -125,6 +125,14 @@ int32_t fclgpu_bvh_num_vertices(const fclgpu_bvh* bvh);
 int fclgpu_bvh_get_partition(const fclgpu_bvh* bvh, int32_t* first_primitive, int32_t* num_primitives,
                              int32_t* primitive_indices, int32_t* tri_indices3);
 
+/* Mesh files: the reference's Wavefront OBJ reader / writer, loadOBJFile / saveOBJFile
+ * (test/test_fcl_utility.h:194-309), the format of test/fcl_resources/env.obj and rob.obj.  fclgpu_load_obj allocates
+ * *vertices (num_vertices x 3) and *triangles (num_tris x 3, 0-based) with malloc: release them with fclgpu_free.
+ * A missing file returns FCLGPU_ERR_INCORRECT_DATA (the reference prints "file not exist" and leaves the arrays empty). */
+int fclgpu_load_obj(const char* path, double** vertices, int32_t* num_vertices, int32_t** triangles, int32_t* num_tris);
+int fclgpu_save_obj(const char* path, const double* vertices, int32_t num_vertices, const int32_t* triangles, int32_t num_tris);
+void fclgpu_free(void* p);
+
 /* ---------------------------------------------------------------------------------------
  * Upload: flattens BVNode<OBBRSS<double>>[] (include/fcl/geometry/bvh/BV_node.h:50-72,
  * BVH_model.h:160-203) + triangles into device records ("HBM layout").
@@ -218,6 +226,29 @@ int fclgpu_collide_mesh_sphere_batch_host(const fclgpu_model* m1, double radius,
                                           const double* tf2, const fclgpu_collision_request* request,
                                           int32_t* num_contacts, fclgpu_contact* contacts, int64_t contact_capacity,
                                           int64_t* contact_offsets, uint32_t* n_bv, uint32_t* n_leaf);
+
+/* ---------------------------------------------------------------------------------------
+ * Batched mesh <-> halfspace / plane collide: query i evaluates
+ * fcl::collide(m1, tf1[i], Halfspace(normal, d) | Plane(normal, d), tf2[i], request, result_i) =
+ * BVHShapeCollider<OBBRSS<S>, Halfspace<S> | Plane<S>> (narrowphase/detail/collision_func_matrix-inl.h:378-430, cells
+ * :841-842) with the closed-form leaf tests halfspaceTriangleIntersect (primitive_shape_algorithm/halfspace-inl.h:587-621)
+ * and planeTriangleIntersect (plane-inl.h:683-759; no GJK on these pairs, gjk_solver_libccd-inl.h:502-540).
+ * (normal, d): the halfspace { x : normal . x <= d } / the plane { normal . x = d } in the shape's frame, normalised like
+ * the reference's constructors do (geometry/shape/halfspace-inl.h:144-160).  One contact per intersecting triangle, in the
+ * reference's traversal order: b1 = triangle id, b2 = -1 (Contact::NONE); halfspace: pos = deepest vertex moved half the
+ * depth back to the boundary, normal = -n', penetration_depth >= 0; plane: pos = middle of the cut segment, normal = -/+ n'.
+ * Same buffers, capacities and error conventions as fclgpu_collide_batch.
+ * ------------------------------------------------------------------------------------- */
+#define FCLGPU_SHAPE_HALFSPACE 17 /* fcl::GEOM_HALFSPACE (geometry/collision_geometry.h:53-54) */
+#define FCLGPU_SHAPE_PLANE 16     /* fcl::GEOM_PLANE */
+int fclgpu_collide_mesh_plane_batch(const fclgpu_model* m1, int32_t shape, const double* normal3, double d, int64_t n,
+                                    const double* tf1, const double* tf2, const fclgpu_collision_request* request,
+                                    int32_t* num_contacts, fclgpu_contact* contacts, int64_t contact_capacity,
+                                    int64_t* contact_offsets, uint32_t* n_bv, uint32_t* n_leaf, void* stream);
+int fclgpu_collide_mesh_plane_batch_host(const fclgpu_model* m1, int32_t shape, const double* normal3, double d, int64_t n,
+                                         const double* tf1, const double* tf2, const fclgpu_collision_request* request,
+                                         int32_t* num_contacts, fclgpu_contact* contacts, int64_t contact_capacity,
+                                         int64_t* contact_offsets, uint32_t* n_bv, uint32_t* n_leaf);
 
 /* ---------------------------------------------------------------------------------------
  * Batched distance: query i evaluates fcl::distance(m1, tf1[i], m2, tf2[i], request, result_i)

@@ -143,6 +143,27 @@ double distance_mesh_sphere(const Model& m1, const Pose& tf1, double radius, con
                             CollideStats* stats = nullptr);
 double brute_distance_mesh_sphere(const Model& m1, const Pose& tf1, double radius, const Pose& tf2, DistanceOut& out);
 
+// ---- mesh <-> halfspace / plane (closed-form leaf tests, no GJK on these pairs) ------------------
+// Halfspace / Plane { n . x <= d / n . x = d } with the constructor's normalisation (halfspace-inl.h:144-160 unitNormalTest)
+struct PlaneShape {
+  Vec3 n;
+  double d;
+};
+PlaneShape make_plane(const Vec3& n, double d);
+// transform(Halfspace, tf) / transform(Plane, tf): n' = R n, d' = d + n' . t (halfspace-inl.h:168-180, plane-inl.h:168-180)
+PlaneShape transform_plane(const PlaneShape& a, const Pose& tf);
+// halfspaceTriangleIntersect (narrowphase/detail/primitive_shape_algorithm/halfspace-inl.h:587-621) and
+// planeTriangleIntersect (.../plane-inl.h:683-759): shape posed by tf1, triangle posed by tf2
+bool halfspace_tri_intersect(const PlaneShape& s, const Pose& tf1, const Vec3& P1, const Vec3& P2, const Vec3& P3, const Pose& tf2,
+                             Vec3* contact_point, double* penetration_depth, Vec3* normal);
+bool plane_tri_intersect(const PlaneShape& s, const Pose& tf1, const Vec3& P1, const Vec3& P2, const Vec3& P3, const Pose& tf2,
+                         Vec3* contact_point, double* penetration_depth, Vec3* normal);
+// fcl::collide(BVHModel<OBBRSS>, tf1, Halfspace | Plane, tf2): one contact per intersecting triangle, in the traversal's
+// depth-first order, {b1 = triangle, b2 = -1, pos, -normal, depth}.  kind 0 = halfspace, 1 = plane.
+size_t collide_mesh_plane(const Model& m1, const Pose& tf1, int kind, const PlaneShape& s, const Pose& tf2, size_t num_max_contacts,
+                          bool enable_contact, std::vector<Contact>& out, CollideStats* stats = nullptr);
+void brute_mesh_plane(const Model& m1, const Pose& tf1, int kind, const PlaneShape& s, const Pose& tf2, std::vector<int>& tris);
+
 // brute force over all triangle pairs (for the invariants)
 void brute_collide_pairs(const Model& m1, const Pose& tf1, const Model& m2, const Pose& tf2,
                          std::vector<std::pair<int, int>>& pairs);

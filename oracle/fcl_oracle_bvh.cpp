@@ -857,6 +857,105 @@ size_t collide_mesh_sphere(const Model& m1, const Pose& tf1, double radius, cons
   return out.size();
 }
 
+// -----------------------------------------------------------------------------
+// mesh <-> halfspace / plane: fcl::collide(BVHModel<OBBRSS>, tf1, Halfspace | Plane, tf2) =
+// BVHShapeCollider<OBBRSS, Shape> -> orientedBVHShapeCollide (collision_func_matrix-inl.h:378-430, cells :841-842).
+// BV test: the shape's OBB against the node's OBB.  computeBV<OBB>(Halfspace) is the infinite box (axis = I, To = 0,
+// extent = DBL_MAX, geometry/shape/utility-inl.h:361-373): obbDisjoint can never separate it, every node is visited.
+// computeBV<OBB>(Plane) has extent (0, DBL_MAX, DBL_MAX) around the plane (:657-669): the only axis of obbDisjoint that
+// can separate is the plane's normal, |T0| > sum_j b_j (|B0j| + 1e-6) (OBB-inl.h:409-412) -- restated directly on the
+// transformed plane (its in-plane axes come from Eigen's unitOrthogonal() and cannot matter).
+// -----------------------------------------------------------------------------
+namespace {
+struct MeshPlaneCtx {
+  const Model& m1;
+  Pose tf1, tf2;
+  int kind;  // 0 halfspace, 1 plane
+  PlaneShape shape;
+  PlaneShape world;  // transform(shape, tf2)
+  size_t max_contacts;
+  bool enable_contact;
+  std::vector<Contact>& out;
+  long long n_bv = 0, n_leaf = 0;
+
+  bool can_stop() const { return !out.empty() && max_contacts <= out.size(); }
+
+  bool bv_disjoint(int b1) {
+    n_bv++;
+    if (kind == 0) return false;
+    // the plane's normal axis: T0 = n' . (centre of the node's box in the world) - d', B0j = n' . (world axis j of the box)
+    const Node& nd = m1.nodes[b1];
+    const Vec3 cw = add(mul(tf1.R, nd.obb_To), tf1.t);
+    const double T0 = dot(world.n, cw) - world.d;
+    double reach = 0;
+    for (int j = 0; j < 3; ++j) {
+      const Vec3 aw = mul(tf1.R, col(nd.axis, j));
+      reach += nd.obb_ext[j] * (std::fabs(dot(world.n, aw)) + 1e-6);
+    }
+    return std::fabs(T0) > reach;
+  }
+
+  void leaf(int b1) {
+    n_leaf++;
+    const int id = -(m1.nodes[b1].first_child + 1);
+    const Tri& t = m1.tris[id];
+    const Vec3 &p1 = m1.verts[t.v[0]], &p2 = m1.verts[t.v[1]], &p3 = m1.verts[t.v[2]];
+    Vec3 cp{{0, 0, 0}}, nrm{{0, 0, 0}};
+    double pen = 0;
+    const bool want = enable_contact;
+    const bool hit = kind == 0 ? halfspace_tri_intersect(shape, tf2, p1, p2, p3, tf1, want ? &cp : nullptr, want ? &pen : nullptr, want ? &nrm : nullptr)
+                               : plane_tri_intersect(shape, tf2, p1, p2, p3, tf1, want ? &cp : nullptr, want ? &pen : nullptr, want ? &nrm : nullptr);
+    if (hit && max_contacts > out.size()) {
+      Contact c{};
+      c.b1 = id;
+      c.b2 = -1;
+      if (enable_contact) {
+        c.pos = cp;
+        c.normal = Vec3{{-nrm[0], -nrm[1], -nrm[2]}};
+        c.depth = pen;
+      }
+      out.push_back(c);
+    }
+  }
+
+  void recurse(int b1) {
+    const Node& n1 = m1.nodes[b1];
+    if (bv_disjoint(b1)) return;
+    if (n1.first_child < 0) {
+      leaf(b1);
+      return;
+    }
+    recurse(n1.first_child);
+    if (can_stop()) return;
+    recurse(n1.first_child + 1);
+  }
+};
+}  // namespace
+
+size_t collide_mesh_plane(const Model& m1, const Pose& tf1, int kind, const PlaneShape& s, const Pose& tf2, size_t num_max_contacts,
+                          bool enable_contact, std::vector<Contact>& out, CollideStats* stats) {
+  if (num_max_contacts == 0) return 0;
+  if (!out.empty() && num_max_contacts <= out.size()) return out.size();
+  if (m1.nodes.empty()) return out.size();
+  MeshPlaneCtx ctx{m1, tf1, tf2, kind, s, transform_plane(s, tf2), num_max_contacts, enable_contact, out};
+  ctx.recurse(0);
+  if (stats) {
+    stats->n_bv += ctx.n_bv;
+    stats->n_leaf += ctx.n_leaf;
+  }
+  return out.size();
+}
+
+void brute_mesh_plane(const Model& m1, const Pose& tf1, int kind, const PlaneShape& s, const Pose& tf2, std::vector<int>& tris) {
+  tris.clear();
+  for (int i = 0; i < (int)m1.tris.size(); ++i) {
+    const Tri& t = m1.tris[i];
+    const bool hit = kind == 0 ? halfspace_tri_intersect(s, tf2, m1.verts[t.v[0]], m1.verts[t.v[1]], m1.verts[t.v[2]], tf1, nullptr, nullptr, nullptr)
+                               : plane_tri_intersect(s, tf2, m1.verts[t.v[0]], m1.verts[t.v[1]], m1.verts[t.v[2]], tf1, nullptr, nullptr, nullptr);
+    if (hit) tris.push_back(i);
+  }
+}
+
 void brute_mesh_sphere(const Model& m1, const Pose& tf1, double radius, const Pose& tf2, std::vector<int>& tris) {
   for (int i = 0; i < (int)m1.tris.size(); ++i) {
     const Tri& t = m1.tris[i];

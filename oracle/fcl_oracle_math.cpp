@@ -912,4 +912,117 @@ bool sphere_tri_distance(const Vec3& o, double radius, const Vec3& P1, const Vec
   return false;
 }
 
+// -----------------------------------------------------------------------------
+// Halfspace / Plane vs triangle -- closed form, so these pairs can be pinned without libccd.
+// -----------------------------------------------------------------------------
+// Halfspace(n, d) / Plane(n, d) constructors -> unitNormalTest (geometry/shape/halfspace-inl.h:144-160, plane-inl.h:144-160)
+PlaneShape make_plane(const Vec3& n_in, double d_in) {
+  PlaneShape s;
+  const double l = norm(n_in);
+  if (l > 0) {
+    const double inv_l = 1.0 / l;
+    s.n = scale(n_in, inv_l);
+    s.d = d_in * inv_l;
+  } else {
+    s.n = Vec3{{1, 0, 0}};
+    s.d = 0;
+  }
+  return s;
+}
+
+// transform(): n' = tf.linear() * n, d' = d + n'.dot(tf.translation())
+PlaneShape transform_plane(const PlaneShape& a, const Pose& tf) {
+  PlaneShape r;
+  r.n = mul(tf.R, a.n);
+  r.d = a.d + dot(r.n, tf.t);
+  return r;
+}
+
+static inline double signed_distance(const PlaneShape& s, const Vec3& p) { return dot(s.n, p) - s.d; }  // halfspace-inl.h:83-86
+
+// halfspaceTriangleIntersect, narrowphase/detail/primitive_shape_algorithm/halfspace-inl.h:587-621
+bool halfspace_tri_intersect(const PlaneShape& s1, const Pose& tf1, const Vec3& P1, const Vec3& P2, const Vec3& P3, const Pose& tf2,
+                             Vec3* contact_point, double* penetration_depth, Vec3* normal) {
+  const PlaneShape new_s1 = transform_plane(s1, tf1);
+  Vec3 v = add(mul(tf2.R, P1), tf2.t);
+  double depth = signed_distance(new_s1, v);
+  Vec3 p = add(mul(tf2.R, P2), tf2.t);
+  double d = signed_distance(new_s1, p);
+  if (d < depth) {
+    depth = d;
+    v = p;
+  }
+  p = add(mul(tf2.R, P3), tf2.t);
+  d = signed_distance(new_s1, p);
+  if (d < depth) {
+    depth = d;
+    v = p;
+  }
+  if (depth <= 0) {
+    if (penetration_depth) *penetration_depth = -depth;
+    if (normal) *normal = new_s1.n;
+    if (contact_point) *contact_point = sub(v, scale(new_s1.n, 0.5 * depth));
+    return true;
+  }
+  return false;
+}
+
+// planeTriangleIntersect, narrowphase/detail/primitive_shape_algorithm/plane-inl.h:683-759
+bool plane_tri_intersect(const PlaneShape& s1, const Pose& tf1, const Vec3& P1, const Vec3& P2, const Vec3& P3, const Pose& tf2,
+                         Vec3* contact_point, double* penetration_depth, Vec3* normal) {
+  const PlaneShape new_s1 = transform_plane(s1, tf1);
+  Vec3 c[3];
+  c[0] = add(mul(tf2.R, P1), tf2.t);
+  c[1] = add(mul(tf2.R, P2), tf2.t);
+  c[2] = add(mul(tf2.R, P3), tf2.t);
+  double d[3];
+  for (int i = 0; i < 3; ++i) d[i] = signed_distance(new_s1, c[i]);
+  if ((d[0] >= 0 && d[1] >= 0 && d[2] >= 0) || (d[0] <= 0 && d[1] <= 0 && d[2] <= 0)) return false;
+  bool positive[3];
+  for (int i = 0; i < 3; ++i) positive[i] = (d[i] > 0);
+  int n_positive = 0;
+  double d_positive = 0, d_negative = 0;
+  for (int i = 0; i < 3; ++i) {
+    if (positive[i]) {
+      n_positive++;
+      if (d_positive <= d[i]) d_positive = d[i];
+    } else {
+      if (d_negative <= -d[i]) d_negative = -d[i];
+    }
+  }
+  if (penetration_depth) *penetration_depth = std::min(d_positive, d_negative);
+  if (normal) *normal = (d_positive > d_negative) ? new_s1.n : Vec3{{-new_s1.n[0], -new_s1.n[1], -new_s1.n[2]}};
+  if (contact_point) {
+    Vec3 p[2] = {Vec3{{0, 0, 0}}, Vec3{{0, 0, 0}}};
+    Vec3 q{{0, 0, 0}};
+    double p_d[2] = {0, 0};
+    double q_d = 0;
+    if (n_positive == 2) {
+      for (int i = 0, j = 0; i < 3; ++i) {
+        if (positive[i]) { p[j] = c[i]; p_d[j] = d[i]; j++; }
+        else { q = c[i]; q_d = d[i]; }
+      }
+      // t = (-p * q_d + q * p_d) / (-q_d + p_d): the unary minus applies to the vector, then the scalar product
+      Vec3 t1, t2;
+      for (int k = 0; k < 3; ++k) {
+        t1[k] = ((-p[0][k]) * q_d + q[k] * p_d[0]) / (-q_d + p_d[0]);
+        t2[k] = ((-p[1][k]) * q_d + q[k] * p_d[1]) / (-q_d + p_d[1]);
+      }
+      *contact_point = scale(add(t1, t2), 0.5);
+    } else {
+      for (int i = 0, j = 0; i < 3; ++i) {
+        if (!positive[i]) { p[j] = c[i]; p_d[j] = d[i]; j++; }
+        else { q = c[i]; q_d = d[i]; }
+      }
+      Vec3 t1, t2;
+      for (int k = 0; k < 3; ++k) {
+        t1[k] = (p[0][k] * q_d - q[k] * p_d[0]) / (q_d - p_d[0]);
+        t2[k] = (p[1][k] * q_d - q[k] * p_d[1]) / (q_d - p_d[1]);
+      }
+      *contact_point = scale(add(t1, t2), 0.5);
+    }
+  }
+  return true;
+}
+
 }  // namespace oracle

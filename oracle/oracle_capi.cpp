@@ -187,6 +187,52 @@ void* orc_collide_mesh_sphere_batch(void* h1, double radius, long long n, const 
   return b;
 }
 
+// fcl::collide(mesh, tf1, Halfspace | Plane {n, d}, tf2) over a batch; kind 0 = halfspace, 1 = plane
+void* orc_collide_mesh_plane_batch(void* h1, int kind, const double* n3, double d, long long n, const double* tf1, const double* tf2,
+                                   long long num_max_contacts, int enable_contact, int nthreads) {
+  Model* m1 = (Model*)h1;
+  const PlaneShape shape = make_plane(Vec3{{n3[0], n3[1], n3[2]}}, d);
+  CollideBatch* b = new CollideBatch;
+  b->counts.assign(n, 0);
+  b->per_pose.resize(n);
+  b->n_bv.assign(n, 0);
+  b->n_leaf.assign(n, 0);
+  auto t0 = std::chrono::steady_clock::now();
+  parallel_for(n, nthreads, [&](long long i) {
+    Pose a = pose_from(tf1 ? tf1 + 12 * i : nullptr);
+    Pose c = pose_from(tf2 ? tf2 + 12 * i : nullptr);
+    CollideStats st;
+    collide_mesh_plane(*m1, a, kind, shape, c, (size_t)num_max_contacts, enable_contact != 0, b->per_pose[i], &st);
+    b->counts[i] = (int32_t)b->per_pose[i].size();
+    b->n_bv[i] = st.n_bv;
+    b->n_leaf[i] = st.n_leaf;
+  });
+  b->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return b;
+}
+
+long long orc_brute_mesh_plane(void* h1, int kind, const double* n3, double d, const double* tf1, const double* tf2, int32_t* out, long long cap) {
+  std::vector<int> tris;
+  brute_mesh_plane(*(Model*)h1, pose_from(tf1), kind, make_plane(Vec3{{n3[0], n3[1], n3[2]}}, d), pose_from(tf2), tris);
+  for (size_t i = 0; i < tris.size() && (long long)i < cap; ++i) out[i] = tris[i];
+  return (long long)tris.size();
+}
+
+// unit kernel: shape {n, d} posed by tf_shape vs triangle (9 doubles) posed by tf_tri; out7 = contact point, depth, normal
+int orc_plane_tri_intersect(int kind, const double* n3, double d, const double* tf_shape, const double* tri9, const double* tf_tri, double* out7) {
+  const PlaneShape s = make_plane(Vec3{{n3[0], n3[1], n3[2]}}, d);
+  Vec3 cp{{0, 0, 0}}, nrm{{0, 0, 0}};
+  double pen = 0;
+  const Vec3 P1{{tri9[0], tri9[1], tri9[2]}}, P2{{tri9[3], tri9[4], tri9[5]}}, P3{{tri9[6], tri9[7], tri9[8]}};
+  const bool hit = kind == 0 ? halfspace_tri_intersect(s, pose_from(tf_shape), P1, P2, P3, pose_from(tf_tri), &cp, &pen, &nrm)
+                             : plane_tri_intersect(s, pose_from(tf_shape), P1, P2, P3, pose_from(tf_tri), &cp, &pen, &nrm);
+  if (out7 && hit) {
+    for (int k = 0; k < 3; ++k) { out7[k] = cp[k]; out7[4 + k] = nrm[k]; }
+    out7[3] = pen;
+  }
+  return hit ? 1 : 0;
+}
+
 // ids of all triangles the sphere intersects (brute force, primitive order); returns the count
 long long orc_brute_mesh_sphere(void* h1, double radius, const double* tf1, const double* tf2, int32_t* out, long long cap) {
   std::vector<int> tris;

@@ -208,6 +208,60 @@ def collide_mesh_sphere_batch(m1, radius, tf1, tf2, num_max_contacts=1, enable_c
     return dict(counts=counts, contacts=contacts, offsets=offsets, n_bv=n_bv, n_leaf=n_leaf)
 
 
+def collide_mesh_plane_batch(m1, kind, normal, d, tf1, tf2, num_max_contacts=1, enable_contact=False, nthreads=1):
+    """fcl::collide(BVHModel<OBBRSS>, tf1[i], Halfspace(normal, d) | Plane(normal, d), tf2[i]); kind 'halfspace' | 'plane'."""
+    tf1 = _poses(tf1)
+    tf2 = _poses(tf2)
+    n = len(tf1) if tf1 is not None else len(tf2)
+    L = lib()
+    L.orc_collide_mesh_plane_batch.restype = C.c_void_p
+    L.orc_collide_mesh_plane_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_double, C.c_longlong, C.POINTER(C.c_double),
+                                               C.POINTER(C.c_double), C.c_longlong, C.c_int, C.c_int]
+    nv = np.ascontiguousarray(normal, np.float64).reshape(3)
+    hb = L.orc_collide_mesh_plane_batch(m1.h, 0 if kind == "halfspace" else 1, _dp(nv), float(d), n, _dp(tf1), _dp(tf2),
+                                        int(min(num_max_contacts, 2**62)), int(enable_contact), nthreads)
+    try:
+        total = L.orc_collide_total(hb)
+        counts = np.empty(n, np.int32)
+        contacts = np.zeros(total, CONTACT_DTYPE)
+        n_bv = np.empty(n, np.int64)
+        n_leaf = np.empty(n, np.int64)
+        L.orc_collide_copy(hb, _ip(counts), contacts.ctypes.data_as(C.c_void_p), _lp(n_bv), _lp(n_leaf))
+    finally:
+        L.orc_collide_free(hb)
+    offsets = np.zeros(n + 1, np.int64)
+    np.cumsum(counts, out=offsets[1:])
+    return dict(counts=counts, contacts=contacts, offsets=offsets, n_bv=n_bv, n_leaf=n_leaf)
+
+
+def brute_mesh_plane(m1, kind, normal, d, tf1, tf2):
+    L = lib()
+    L.orc_brute_mesh_plane.restype = C.c_longlong
+    L.orc_brute_mesh_plane.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                       C.POINTER(C.c_int32), C.c_longlong]
+    nv = np.ascontiguousarray(normal, np.float64).reshape(3)
+    a = np.ascontiguousarray(tf1, dtype=np.float64).reshape(12)
+    b = np.ascontiguousarray(tf2, dtype=np.float64).reshape(12)
+    out = np.empty(m1.num_tris, np.int32)
+    k = L.orc_brute_mesh_plane(m1.h, 0 if kind == "halfspace" else 1, _dp(nv), float(d), _dp(a), _dp(b), _ip(out), len(out))
+    return out[:k]
+
+
+def plane_tri_intersect(kind, normal, d, tf_shape, tri9, tf_tri):
+    """halfspaceTriangleIntersect / planeTriangleIntersect: (hit, contact point, depth, normal)."""
+    L = lib()
+    L.orc_plane_tri_intersect.restype = C.c_int
+    L.orc_plane_tri_intersect.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                          C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    nv = np.ascontiguousarray(normal, np.float64).reshape(3)
+    a = None if tf_shape is None else np.ascontiguousarray(tf_shape, np.float64).reshape(12)
+    b = None if tf_tri is None else np.ascontiguousarray(tf_tri, np.float64).reshape(12)
+    t = np.ascontiguousarray(tri9, np.float64).reshape(9)
+    out = np.zeros(7)
+    hit = L.orc_plane_tri_intersect(0 if kind == "halfspace" else 1, _dp(nv), float(d), _dp(a), _dp(t), _dp(b), _dp(out))
+    return bool(hit), out[:3].copy(), float(out[3]), out[4:].copy()
+
+
 def brute_mesh_sphere(m1, radius, tf1, tf2):
     """Ids of every triangle of m1 (posed by tf1) the sphere (centre tf2's translation) intersects."""
     L = lib()

@@ -40,6 +40,8 @@ def lib():
         L.hm_tri_intersect.argtypes = [dp, dp, dp, C.c_int, C.POINTER(C.c_uint32), dp, dp, dp]
         L.hm_tri_distance.restype = C.c_double
         L.hm_tri_distance.argtypes = [dp, dp, dp, dp]
+        L.hm_plane_tri_intersect.restype = C.c_int
+        L.hm_plane_tri_intersect.argtypes = [C.c_int, dp, C.c_double, dp, dp]
         L.hm_sphere_tri_intersect.restype = C.c_int
         L.hm_sphere_tri_intersect.argtypes = [dp, C.c_double, dp, dp]
         L.hm_sphere_tri_distance.restype = C.c_int

@@ -61,6 +61,17 @@ double hm_tri_distance(const double* S9, const double* T9, double* P3, double* Q
   P3[0] = P.x; P3[1] = P.y; P3[2] = P.z; Q3[0] = Q.x; Q3[1] = Q.y; Q3[2] = Q.z;
   return d;
 }
+// halfspace (kind 0) / plane (kind 1) {n3, d}, already in the frame of the triangle T9; out7 = contact point, depth, normal
+int hm_plane_tri_intersect(int kind, const double* n3, double d, const double* T9, double* out7) {
+  V3 T[3] = {v3(T9), v3(T9 + 3), v3(T9 + 6)};
+  V3 cp = mk(0, 0, 0), nrm = mk(0, 0, 0);
+  double depth = 0;
+  const bool hit = kind == 0 ? halfspace_tri_intersect(v3(n3), d, T, cp, depth, nrm) : plane_tri_intersect(v3(n3), d, T, cp, depth, nrm);
+  if (hit) {
+    out7[0] = cp.x; out7[1] = cp.y; out7[2] = cp.z; out7[3] = depth; out7[4] = nrm.x; out7[5] = nrm.y; out7[6] = nrm.z;
+  }
+  return hit ? 1 : 0;
+}
 // sphere (centre c3, radius) vs triangle T9, one frame; out7 = contact point, depth, normal (as the routine writes them)
 int hm_sphere_tri_intersect(const double* c3, double radius, const double* T9, double* out7) {
   V3 T[3] = {v3(T9), v3(T9 + 3), v3(T9 + 6)};
