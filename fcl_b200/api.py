@@ -907,6 +907,127 @@ def sync_status(device=None, stream=None):
 
 
 # ------------------------------------------------------------------------------------------------
+# broadphase
+# ------------------------------------------------------------------------------------------------
+class DefaultCollisionData:
+    """fcl::DefaultCollisionData (broadphase/default_broadphase_callbacks.h:59-70)."""
+
+    def __init__(self, request=None):
+        self.request = request if request is not None else CollisionRequest()
+        self.result = CollisionResult()
+        self.done = False
+
+
+def DefaultCollisionFunction(o1, o2, data):
+    """fcl::DefaultCollisionFunction (default_broadphase_callbacks.h:84-103)."""
+    if data.done:
+        return True
+    collide(o1, o2, data.request, data.result)
+    if (not data.request.enable_cost) and data.result.isCollision() and data.result.numContacts() >= data.request.num_max_contacts:
+        data.done = True
+    return data.done
+
+
+class BatchBroadPhaseResult:
+    """pairs (m, 2): (index in this manager, index in the other manager) of every pair whose world AABBs overlap, in the
+    brute-force manager's visiting order; num_contacts[m]: fcl::collide on each pair with a fresh result (or None)."""
+
+    def __init__(self, pairs, num_contacts, aabb1, aabb2):
+        self.pairs, self.num_contacts, self.aabb1, self.aabb2 = pairs, num_contacts, aabb1, aabb2
+
+
+class NaiveCollisionManager:
+    """fcl::NaiveCollisionManager (broadphase/broadphase_bruteforce.h) over CollisionObjects whose geometries are
+    BVHModel<OBBRSS>: registerObject(s) / setup / update / clear / size / getObjects, collide(other, cdata, callback)
+    with the reference's callback protocol, and the batched form collide_batch(other, request): culling AND the
+    narrowphase of every culled pair on the GPU (fclgpu_broadphase_collide_host).  The dynamic AABB tree manager of the
+    reference reports the same set of pairs; DynamicAABBTreeCollisionManager is an alias."""
+
+    def __init__(self):
+        self.objs = []
+
+    def registerObject(self, obj):
+        self.objs.append(obj)
+
+    def registerObjects(self, objs):
+        self.objs.extend(objs)
+
+    def unregisterObject(self, obj):
+        self.objs.remove(obj)
+
+    def setup(self):
+        pass
+
+    def update(self, *args):
+        pass
+
+    def clear(self):
+        self.objs = []
+
+    def getObjects(self):
+        return list(self.objs)
+
+    def empty(self):
+        return not self.objs
+
+    def size(self):
+        return len(self.objs)
+
+    def _tables(self, other, device):
+        geoms, index = [], {}
+        for o in list(self.objs) + list(other.objs):
+            g = o.collisionGeometry()
+            if not isinstance(g, BVHModel):
+                raise FclGpuError(BVH_ERR_UNSUPPORTED_FUNCTION, "the batched broadphase handles BVHModel<OBBRSS> geometries")
+            if id(g) not in index:
+                index[id(g)] = len(geoms)
+                geoms.append(g)
+
+        def side(objs):
+            gi = np.array([index[id(o.collisionGeometry())] for o in objs], np.int32)
+            tf = np.ascontiguousarray(np.stack([_poses(o.getTransform())[0][0] for o in objs])) if objs else np.zeros((0, 12))
+            return gi, tf
+
+        handles = (C.c_void_p * len(geoms))(*[g.device_model(device) for g in geoms])
+        return geoms, handles, side(self.objs), side(other.objs)
+
+    def collide_batch(self, other, request=None, device=None, pair_capacity=None, narrowphase=True):
+        """All pairs (o1 in self, o2 in other) with overlapping AABBs, and numContacts of fcl::collide on each."""
+        n1, n2 = len(self.objs), len(other.objs)
+        if n1 == 0 or n2 == 0:
+            return BatchBroadPhaseResult(np.zeros((0, 2), np.int32), np.zeros(0, np.int32), np.zeros((n1, 6)), np.zeros((n2, 6)))
+        geoms, handles, (g1, tf1), (g2, tf2) = self._tables(other, device)
+        req = (request if request is not None else CollisionRequest())._c()
+        cap = int(pair_capacity) if pair_capacity is not None else max(1024, 4 * (n1 + n2))
+        while True:
+            pairs = np.zeros((cap, 2), np.int32)
+            counts = np.zeros(cap, np.int32) if narrowphase else None
+            a1, a2 = np.zeros((n1, 6)), np.zeros((n2, 6))
+            m = C.c_int64(0)
+            rc = _capi.lib().fclgpu_broadphase_collide_host(len(geoms), handles, n1, addr(g1), addr(tf1), n2, addr(g2), addr(tf2),
+                                                            C.byref(req), cap, addr(pairs), C.byref(m), addr(counts), addr(a1), addr(a2))
+            if rc == _capi.ERR_CONTACT_OVERFLOW and m.value > cap:
+                cap = int(m.value)
+                continue
+            check(rc)
+            k = int(m.value)
+            return BatchBroadPhaseResult(pairs[:k], counts[:k] if narrowphase else None, a1, a2)
+
+    def collide(self, other, cdata, callback):
+        """collide(other_manager, cdata, callback) (broadphase_bruteforce-inl.h:182-205): the callback sees the culled pairs
+        in the brute-force manager's order and may end the evaluation by returning True.  Culling runs on the GPU."""
+        if self.size() == 0 or other.size() == 0:
+            return
+        r = self.collide_batch(other, narrowphase=False)
+        for i, j in r.pairs:
+            if callback(self.objs[i], other.objs[j], cdata):
+                return
+
+
+DynamicAABBTreeCollisionManager = NaiveCollisionManager
+
+
+# ------------------------------------------------------------------------------------------------
 # single-query entry points with the reference's signatures
 # ------------------------------------------------------------------------------------------------
 def collide(o1, tf1, o2=None, tf2=None, request=None, result=None):

@@ -18,6 +18,7 @@
 #include "records.hpp"
 #include "traversal.cuh"
 #include "collide_ordered.cuh"
+#include "broadphase.cuh"
 #include "refit.cuh"
 
 using namespace fclgpu;
@@ -232,9 +233,39 @@ struct fclgpu_model {
   double* vert_stage = nullptr;
   int32_t* fc;
   int depth;
+  LocalAabb aabb;  // BVHModel::computeLocalAABB over the vertices the triangles reference
 };
 
 namespace {
+// BVHModel::computeLocalAABB (BVH_model-inl.h:1080-1100) over the vertices referenced by the triangles: aabb_local,
+// aabb_center = (min + max) * 0.5, aabb_radius = sqrt(max |center - v|^2).  vertex(t, k) -> pointer to 3 doubles.
+template <class VertexOf>
+void local_aabb_of(int n_tris, VertexOf vertex, LocalAabb& a) {
+  const double big = 1.7976931348623157e308;
+  for (int k = 0; k < 3; ++k) {
+    a.mn[k] = big;
+    a.mx[k] = -big;
+  }
+  for (int t = 0; t < n_tris; ++t)
+    for (int c = 0; c < 3; ++c) {
+      const double* v = vertex(t, c);
+      for (int k = 0; k < 3; ++k) {
+        a.mn[k] = std::min(a.mn[k], v[k]);
+        a.mx[k] = std::max(a.mx[k], v[k]);
+      }
+    }
+  for (int k = 0; k < 3; ++k) a.c[k] = (a.mn[k] + a.mx[k]) * 0.5;
+  double r2 = 0;
+  for (int t = 0; t < n_tris; ++t)
+    for (int c = 0; c < 3; ++c) {
+      const double* v = vertex(t, c);
+      const double dx = a.c[0] - v[0], dy = a.c[1] - v[1], dz = a.c[2] - v[2];
+      const double r = (dx * dx + dy * dy) + dz * dz;
+      if (r > r2) r2 = r;
+    }
+  a.r = std::sqrt(r2);
+}
+
 int tree_depth(const int32_t* fc, int n) {
   std::vector<std::pair<int, int>> st;
   st.emplace_back(0, 0);
@@ -345,6 +376,7 @@ extern "C" int fclgpu_model_create_obbrss(int device, int32_t n_nodes, const int
     return fail(FCLGPU_ERR_MODEL_OUT_OF_MEMORY, "first_child upload failed");
   }
   m->d = DeviceModel{m->obb, m->rss, m->fc, m->tri, m->rss32, m->obb32, m->topo, n_nodes, n_tris};
+  local_aabb_of(n_tris, [&](int t, int c) { return tri_verts9 + 9 * (size_t)t + 3 * c; }, m->aabb);
   *out = m;
   return FCLGPU_OK;
 }
@@ -563,6 +595,7 @@ extern "C" int fclgpu_model_build_obbrss(int device, const double* vertices, int
   BUILD_TRY(cudaMemcpy(m->by_size, by_size.data(), sizeof(int32_t) * nn, cudaMemcpyHostToDevice));
   m->depth = depth;
   m->d = DeviceModel{m->obb, m->rss, m->fc, m->tri, m->rss32, m->obb32, m->topo, nn, nt};
+  local_aabb_of(nt, [&](int t, int c) { return vertices + 3 * (size_t)triangles[3 * (size_t)t + c]; }, m->aabb);
 #undef BUILD_TRY
   *out = m;
   return cleanup(FCLGPU_OK);
@@ -1571,6 +1604,135 @@ extern "C" int fclgpu_collide_mesh_plane_batch_host(const fclgpu_model* m1, int3
   return mesh_shape_collide_host(m1, X, n, tf1, tf2, request, num_contacts, contacts, contact_capacity, contact_offsets, n_bv, n_leaf);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// broadphase: N x M AABB culling feeding the batched mesh-mesh kernel
+// ------------------------------------------------------------------------------------------
+extern "C" int fclgpu_model_local_aabb(const fclgpu_model* m, double center3[3], double* radius, double min3[3], double max3[3]) {
+  if (!m) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL model");
+  for (int k = 0; k < 3; ++k) {
+    if (center3) center3[k] = m->aabb.c[k];
+    if (min3) min3[k] = m->aabb.mn[k];
+    if (max3) max3[k] = m->aabb.mx[k];
+  }
+  if (radius) *radius = m->aabb.r;
+  return FCLGPU_OK;
+}
+
+extern "C" int fclgpu_broadphase_collide_host(int32_t n_geoms, const fclgpu_model* const* geoms, int64_t n1, const int32_t* geom1,
+                                              const double* tf1, int64_t n2, const int32_t* geom2, const double* tf2,
+                                              const fclgpu_collision_request* request, int64_t pair_capacity, int32_t* pairs,
+                                              int64_t* num_pairs, int32_t* num_contacts, double* aabb1_out, double* aabb2_out) {
+  if (!geoms || n_geoms <= 0 || n1 < 0 || n2 < 0 || !geom1 || !geom2 || !tf1 || !tf2 || !num_pairs || pair_capacity < 0)
+    return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL / negative argument");
+  if (n1 > 0x7fffffff || n2 > 0x7fffffff) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "too many objects");
+  if (num_contacts && !request) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "request is NULL");
+  *num_pairs = 0;
+  for (int g = 0; g < n_geoms; ++g)
+    if (!geoms[g] || geoms[g]->device != geoms[0]->device) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL geometry / mixed devices");
+  for (int64_t i = 0; i < n1; ++i)
+    if (geom1[i] < 0 || geom1[i] >= n_geoms) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "geom1[%lld] out of range", (long long)i);
+  for (int64_t j = 0; j < n2; ++j)
+    if (geom2[j] < 0 || geom2[j] >= n_geoms) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "geom2[%lld] out of range", (long long)j);
+  if (n1 == 0 || n2 == 0) return FCLGPU_OK;
+  const int device = geoms[0]->device;
+  CUDA_TRY(cudaSetDevice(device));
+  Workspace* w;
+  int rc = get_ws(device, &w);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> host_lock(w->host_mu);
+  cudaStream_t st = w->pipe[1];
+  const int64_t cap = std::max<int64_t>(pair_capacity, 1);
+  const int64_t nscan = std::max<int64_t>(std::max(n1, cap), 1);
+  const int64_t nblk = (nscan + kScanBlock - 1) / kScanBlock;
+  const size_t bytes = padded(sizeof(LocalAabb) * n_geoms) + padded(4 * n1) + padded(4 * n2) + padded(96 * n1) + padded(96 * n2) +
+                       padded(48 * n1) + padded(48 * n2) + padded(4 * nscan) + padded(8 * nscan) + padded(8 * nblk) + padded(8 * cap) +
+                       2 * padded(96 * cap) + padded(8 * cap) + 2 * padded(4 * cap) + padded(8) + 4096;
+  {
+    std::lock_guard<std::mutex> lock(w->mu);
+    rc = ensure(&w->dev_io, &w->dev_io_bytes, bytes);
+    if (rc) return rc;
+  }
+  DevBuf B{(char*)w->dev_io};
+  LocalAabb* d_loc = B.take<LocalAabb>(n_geoms);
+  int32_t* d_g1 = B.take<int32_t>(n1);
+  int32_t* d_g2 = B.take<int32_t>(n2);
+  double* d_tf1 = B.take<double>(12 * n1);
+  double* d_tf2 = B.take<double>(12 * n2);
+  double* d_a1 = B.take<double>(6 * n1);
+  double* d_a2 = B.take<double>(6 * n2);
+  int32_t* d_cnt = B.take<int32_t>(nscan);      // per-object overlap counts, later the group flags
+  long long* d_local = B.take<long long>(nscan);
+  long long* d_bsum = B.take<long long>(nblk);
+  int2* d_pairs = B.take<int2>(cap);
+  double* d_gtf1 = B.take<double>(12 * cap);
+  double* d_gtf2 = B.take<double>(12 * cap);
+  long long* d_gidx = B.take<long long>(cap);
+  int32_t* d_gcnt = B.take<int32_t>(cap);
+  int32_t* d_out = B.take<int32_t>(cap);
+  long long* d_base = B.take<long long>(1);
+
+  std::vector<LocalAabb> loc(n_geoms);
+  for (int g = 0; g < n_geoms; ++g) loc[g] = geoms[g]->aabb;
+  CUDA_TRY(cudaMemcpyAsync(d_loc, loc.data(), sizeof(LocalAabb) * n_geoms, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_g1, geom1, 4 * n1, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_g2, geom2, 4 * n2, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_tf1, tf1, 96 * n1, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_tf2, tf2, 96 * n2, cudaMemcpyHostToDevice, st));
+  world_aabb_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(d_loc, d_g1, d_tf1, n1, d_a1);
+  world_aabb_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(d_loc, d_g2, d_tf2, n2, d_a2);
+  const unsigned pair_blocks = (unsigned)((n1 * 32 + 255) / 256);
+  pair_kernel<false><<<pair_blocks, 256, 0, st>>>(d_a1, n1, d_a2, n2, d_cnt, nullptr, nullptr, kScanBlock, nullptr, 0);
+  auto scan = [&](int64_t n) {  // exclusive scan of d_cnt[0, n): offset(i) = d_bsum[i / kScanBlock] + d_local[i]; total -> d_base
+    const int nb = (int)((n + kScanBlock - 1) / kScanBlock);
+    cudaMemsetAsync(d_base, 0, sizeof(long long), st);
+    scan_block_kernel<<<nb, kScanBlock, 0, st>>>(d_cnt, n, (long long)0x7fffffff, d_local, d_bsum);
+    scan_sums_kernel<<<1, kScanBlock, 0, st>>>(d_bsum, nb, d_base, nullptr);
+    g_launches += 2;
+  };
+  scan(n1);
+  pair_kernel<true><<<pair_blocks, 256, 0, st>>>(d_a1, n1, d_a2, n2, nullptr, d_local, d_bsum, kScanBlock, d_pairs, cap);
+  g_launches += 4;
+  long long total = 0;
+  CUDA_TRY(cudaMemcpyAsync(&total, d_base, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  if (aabb1_out) CUDA_TRY(cudaMemcpyAsync(aabb1_out, d_a1, 48 * n1, cudaMemcpyDeviceToHost, st));
+  if (aabb2_out) CUDA_TRY(cudaMemcpyAsync(aabb2_out, d_a2, 48 * n2, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  *num_pairs = total;
+  if (total > pair_capacity) return fail(FCLGPU_ERR_CONTACT_OVERFLOW, "pair capacity %lld < %lld overlapping pairs", (long long)pair_capacity, total);
+  if (total == 0) return FCLGPU_OK;
+  if (pairs) CUDA_TRY(cudaMemcpyAsync(pairs, d_pairs, 8 * (size_t)total, cudaMemcpyDeviceToHost, st));
+  if (num_contacts) {
+    // narrowphase per (geometry 1, geometry 2) group: stable device compaction, pose gather, batched collide, scatter
+    std::vector<char> used1(n_geoms, 0), used2(n_geoms, 0);
+    for (int64_t i = 0; i < n1; ++i) used1[geom1[i]] = 1;
+    for (int64_t j = 0; j < n2; ++j) used2[geom2[j]] = 1;
+    const unsigned tb = (unsigned)((total + 255) / 256);
+    CUDA_TRY(cudaMemsetAsync(d_out, 0, 4 * (size_t)total, st));
+    for (int ga = 0; ga < n_geoms; ++ga) {
+      if (!used1[ga]) continue;
+      for (int gb = 0; gb < n_geoms; ++gb) {
+        if (!used2[gb]) continue;
+        group_flag_kernel<<<tb, 256, 0, st>>>(d_pairs, total, d_g1, d_g2, ga, gb, d_cnt);
+        scan(total);
+        long long m = 0;
+        CUDA_TRY(cudaMemcpyAsync(&m, d_base, sizeof(long long), cudaMemcpyDeviceToHost, st));
+        group_gather_kernel<<<tb, 256, 0, st>>>(d_pairs, total, d_cnt, d_local, d_bsum, kScanBlock, d_tf1, d_tf2, d_gtf1, d_gtf2, d_gidx);
+        g_launches += 2;
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (m == 0) continue;
+        rc = fclgpu_collide_batch(geoms[ga], geoms[gb], m, d_gtf1, d_gtf2, request, d_gcnt, nullptr, 0, nullptr, nullptr, nullptr, st);
+        if (rc) return rc;
+        group_scatter_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(d_gidx, d_gcnt, m, d_out);
+        g_launches++;
+      }
+    }
+    CUDA_TRY(cudaMemcpyAsync(num_contacts, d_out, 4 * (size_t)total, cudaMemcpyDeviceToHost, st));
+  }
+  CUDA_TRY(cudaGetLastError());
+  return fclgpu_sync_status(device, st);
+}
 
 // ------------------------------------------------------------------------------------------
 // utilities

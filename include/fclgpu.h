@@ -326,6 +326,30 @@ int fclgpu_distance_mesh_sphere_batch_host(const fclgpu_model* m1, double radius
                                            int32_t* b2, uint32_t* n_bv, uint32_t* n_leaf);
 
 /* ---------------------------------------------------------------------------------------
+ * Broadphase: N x M culling feeding the batched mesh-mesh kernel -- what
+ * NaiveCollisionManager::collide(other_manager, cdata, DefaultCollisionFunction) does
+ * (broadphase/broadphase_bruteforce-inl.h:182-205, default_broadphase_callbacks.h:84-103; the dynamic AABB tree manager
+ * reports the same set of pairs), for two sets of posed objects that share a table of geometries.
+ *   object i of set 1 = (geoms[geom1[i]], tf1[i]), object j of set 2 = (geoms[geom2[j]], tf2[j]);
+ *   world AABB of an object = CollisionObject::computeAABB (collision_object-inl.h:118-131): the local AABB translated when
+ *   the rotation is the identity, else the cube of half side aabb_radius around tf * aabb_center, with
+ *   aabb_local / aabb_center / aabb_radius = BVHModel::computeLocalAABB (BVH_model-inl.h:1080-1100, here over the vertices
+ *   the triangles reference; fclgpu_model_local_aabb reads them);
+ *   pairs[2k], pairs[2k+1] = (i, j) of the k-th pair whose AABBs overlap (AABB::overlap, AABB-inl.h:98-107), in the
+ *   brute-force manager's visiting order (i ascending, then j ascending); *num_pairs = their number (also when it
+ *   exceeds pair_capacity: FCLGPU_ERR_CONTACT_OVERFLOW, rerun with a larger list);
+ *   num_contacts[k] (optional) = fcl::collide(o1, tf1[i], o2, tf2[j], request, fresh result) for pair k: the pairs are
+ *   grouped by geometry pair ON THE DEVICE and run through fclgpu_collide_batch; neither the pair list nor the gathered
+ *   poses visit the host in between.  aabb1_out / aabb2_out (optional): the world AABBs (n x 6: min, max).
+ * Host pointers; returns when the results are in place.
+ * ------------------------------------------------------------------------------------- */
+int fclgpu_model_local_aabb(const fclgpu_model* m, double center3[3], double* radius, double min3[3], double max3[3]);
+int fclgpu_broadphase_collide_host(int32_t n_geoms, const fclgpu_model* const* geoms, int64_t n1, const int32_t* geom1,
+                                   const double* tf1, int64_t n2, const int32_t* geom2, const double* tf2,
+                                   const fclgpu_collision_request* request, int64_t pair_capacity, int32_t* pairs,
+                                   int64_t* num_pairs, int32_t* num_contacts, double* aabb1_out, double* aabb2_out);
+
+/* ---------------------------------------------------------------------------------------
  * Multi-GPU: the path shards over poses with NO exchange inside the traversal -- BVHs are replicated
  * (upload the models on every GPU), rank r owns the contiguous block fclgpu_shard_range() names, every rank runs the
  * *_batch calls above on its block, and the per-rank result arrays are gathered with NCCL's all-gather over NVLink.

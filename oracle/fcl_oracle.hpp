@@ -164,6 +164,20 @@ size_t collide_mesh_plane(const Model& m1, const Pose& tf1, int kind, const Plan
                           bool enable_contact, std::vector<Contact>& out, CollideStats* stats = nullptr);
 void brute_mesh_plane(const Model& m1, const Pose& tf1, int kind, const PlaneShape& s, const Pose& tf2, std::vector<int>& tris);
 
+// ---- broadphase: the brute-force manager -----------------------------------------------------------
+// BVHModel::computeLocalAABB (BVH_model-inl.h:1080-1100), over the vertices the triangles reference
+struct LocalAABB {
+  Vec3 center, mn, mx;
+  double radius;
+};
+LocalAABB local_aabb(const Model& m);
+// CollisionObject::computeAABB (collision_object-inl.h:118-131): out6 = min, max
+void world_aabb(const LocalAABB& a, const Pose& tf, double out6[6]);
+// NaiveCollisionManager::collide(other, ...) (broadphase_bruteforce-inl.h:182-205): every (i, j) whose AABBs overlap
+// (AABB::overlap, AABB-inl.h:98-107), i-major in registration order
+void broadphase_pairs(const std::vector<const Model*>& geoms, const std::vector<int>& geom1, const std::vector<Pose>& tf1,
+                      const std::vector<int>& geom2, const std::vector<Pose>& tf2, std::vector<std::pair<int, int>>& pairs);
+
 // brute force over all triangle pairs (for the invariants)
 void brute_collide_pairs(const Model& m1, const Pose& tf1, const Model& m2, const Pose& tf2,
                          std::vector<std::pair<int, int>>& pairs);

@@ -1076,4 +1076,78 @@ double brute_distance_mesh_sphere(const Model& m1, const Pose& tf1, double radiu
   return out.min_distance;
 }
 
+// -----------------------------------------------------------------------------
+// Broadphase: local / world AABBs and the brute-force manager's pair enumeration
+// -----------------------------------------------------------------------------
+LocalAABB local_aabb(const Model& m) {
+  LocalAABB a;
+  const double big = std::numeric_limits<double>::max();
+  a.mn = Vec3{{big, big, big}};
+  a.mx = Vec3{{-big, -big, -big}};
+  for (const Tri& t : m.tris)
+    for (int c = 0; c < 3; ++c)
+      for (int k = 0; k < 3; ++k) {
+        a.mn[k] = std::min(a.mn[k], m.verts[t.v[c]][k]);
+        a.mx[k] = std::max(a.mx[k], m.verts[t.v[c]][k]);
+      }
+  a.center = scale(add(a.mn, a.mx), 0.5);  // AABB::center()
+  double r2 = 0;
+  for (const Tri& t : m.tris)
+    for (int c = 0; c < 3; ++c) {
+      const double r = sqnorm(sub(a.center, m.verts[t.v[c]]));
+      if (r > r2) r2 = r;
+    }
+  a.radius = std::sqrt(r2);
+  return a;
+}
+
+// Eigen's MatrixBase::isIdentity(prec = NumTraits<double>::dummy_precision() = 1e-12): diagonal isApprox(x, 1, prec),
+// off-diagonal isMuchSmallerThan(x, 1, prec)  (Eigen/src/Core/CwiseNullaryOp.h; third-party, version unpinned)
+static bool is_identity(const Mat3& R) {
+  const double prec = 1e-12;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      const double x = R.m[i][j];
+      if (i == j) {
+        const double ax = std::fabs(x), one = 1.0;
+        if (!(std::fabs(x - one) <= (ax < one ? ax : one) * prec)) return false;
+      } else {
+        if (!(std::fabs(x) <= prec)) return false;
+      }
+    }
+  return true;
+}
+
+void world_aabb(const LocalAABB& a, const Pose& tf, double out6[6]) {
+  if (is_identity(tf.R)) {
+    for (int k = 0; k < 3; ++k) {
+      out6[k] = a.mn[k] + tf.t[k];
+      out6[3 + k] = a.mx[k] + tf.t[k];
+    }
+  } else {
+    const Vec3 c = add(mul(tf.R, a.center), tf.t);
+    for (int k = 0; k < 3; ++k) {
+      out6[k] = c[k] - a.radius;
+      out6[3 + k] = c[k] + a.radius;
+    }
+  }
+}
+
+void broadphase_pairs(const std::vector<const Model*>& geoms, const std::vector<int>& geom1, const std::vector<Pose>& tf1,
+                      const std::vector<int>& geom2, const std::vector<Pose>& tf2, std::vector<std::pair<int, int>>& pairs) {
+  std::vector<LocalAABB> loc;
+  for (const Model* m : geoms) loc.push_back(local_aabb(*m));
+  std::vector<double> a1(6 * geom1.size()), a2(6 * geom2.size());
+  for (size_t i = 0; i < geom1.size(); ++i) world_aabb(loc[geom1[i]], tf1[i], &a1[6 * i]);
+  for (size_t j = 0; j < geom2.size(); ++j) world_aabb(loc[geom2[j]], tf2[j], &a2[6 * j]);
+  pairs.clear();
+  for (size_t i = 0; i < geom1.size(); ++i)
+    for (size_t j = 0; j < geom2.size(); ++j) {
+      const double *a = &a1[6 * i], *b = &a2[6 * j];
+      if (a[0] > b[3] || a[1] > b[4] || a[2] > b[5]) continue;
+      if (a[3] < b[0] || a[4] < b[1] || a[5] < b[2]) continue;
+      pairs.emplace_back((int)i, (int)j);
+    }
+}
+
 }  // namespace oracle

@@ -474,4 +474,35 @@ double orc_tri_distance(const double* S9, const double* T9, double* P3, double* 
 
 int orc_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
 
-}  // extern "C"
+
+// brute-force broadphase: pairs (2 ints each, i-major) of overlapping world AABBs and, per pair, numContacts of
+// fcl::collide(o1, o2, request) with a fresh result; returns the number of pairs (pairs / counts may be NULL or too small:
+// only the first `cap` are written)
+long long orc_broadphase(int n_geoms, void** geoms, long long n1, const int32_t* geom1, const double* tf1, long long n2,
+                         const int32_t* geom2, const double* tf2, long long num_max_contacts, int enable_contact, int nthreads,
+                         int32_t* pairs, int32_t* counts, long long cap, double* aabb1_out) {
+  std::vector<const Model*> gs;
+  for (int g = 0; g < n_geoms; ++g) gs.push_back((const Model*)geoms[g]);
+  std::vector<int> g1(geom1, geom1 + n1), g2(geom2, geom2 + n2);
+  std::vector<Pose> p1(n1), p2(n2);
+  for (long long i = 0; i < n1; ++i) p1[i] = pose_from(tf1 + 12 * i);
+  for (long long j = 0; j < n2; ++j) p2[j] = pose_from(tf2 + 12 * j);
+  std::vector<std::pair<int, int>> pr;
+  broadphase_pairs(gs, g1, p1, g2, p2, pr);
+  if (aabb1_out)
+    for (long long i = 0; i < n1; ++i) world_aabb(local_aabb(*gs[g1[i]]), p1[i], aabb1_out + 6 * i);
+  const long long m = std::min<long long>((long long)pr.size(), cap);
+  if (pairs)
+    for (long long k = 0; k < m; ++k) {
+      pairs[2 * k] = pr[k].first;
+      pairs[2 * k + 1] = pr[k].second;
+    }
+  if (counts)
+    parallel_for(m, nthreads, [&](long long k) {
+      std::vector<Contact> out;
+      counts[k] = (int32_t)collide(*gs[g1[pr[k].first]], p1[pr[k].first], *gs[g2[pr[k].second]], p2[pr[k].second],
+                                   (size_t)num_max_contacts, enable_contact != 0, out);
+    });
+  return (long long)pr.size();
+}
+}

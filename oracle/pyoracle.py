@@ -417,6 +417,26 @@ def tri_distance(S, T):
     return float(d), P, Q
 
 
+def broadphase(models, geom1, tf1, geom2, tf2, num_max_contacts=1, enable_contact=False, nthreads=1, narrowphase=True):
+    """NaiveCollisionManager::collide(other) with the default callback evaluated for EVERY overlapping pair:
+    dict(pairs (m, 2) int32 in the brute-force manager's order, counts[m] = numContacts per pair, aabb1 (n1, 6))."""
+    L = lib()
+    L.orc_broadphase.restype = C.c_longlong
+    L.orc_broadphase.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_longlong, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_longlong,
+                                 C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_int32),
+                                 C.POINTER(C.c_int32), C.c_longlong, C.POINTER(C.c_double)]
+    hs = (C.c_void_p * len(models))(*[m.h for m in models])
+    g1, g2 = np.ascontiguousarray(geom1, np.int32), np.ascontiguousarray(geom2, np.int32)
+    t1, t2 = _poses(tf1), _poses(tf2)
+    aabb1 = np.zeros((len(g1), 6))
+    total = L.orc_broadphase(len(models), hs, len(g1), _ip(g1), _dp(t1), len(g2), _ip(g2), _dp(t2), 1, 0, 1, None, None, 0, _dp(aabb1))
+    pairs = np.zeros((total, 2), np.int32)
+    counts = np.zeros(total, np.int32) if narrowphase else None
+    L.orc_broadphase(len(models), hs, len(g1), _ip(g1), _dp(t1), len(g2), _ip(g2), _dp(t2), int(min(num_max_contacts, 2**62)),
+                     int(enable_contact), int(nthreads), _ip(pairs), _ip(counts), total, None)
+    return dict(pairs=pairs, counts=counts, aabb1=aabb1)
+
+
 # ------------------------------------------------------------------------------------------------
 # executed-operation counters (fcl_oracle_counted.cpp): the oracle recompiled over a counting scalar
 # ------------------------------------------------------------------------------------------------
