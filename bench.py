@@ -702,7 +702,7 @@ def main():
     ap.add_argument("--workload", default="all", choices=["all"] + sorted(WORKLOADS))
     ap.add_argument("--poses", type=int, default=1_000_000, help="poses per GPU per step (cfg4: robot configurations)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="cfg4 / cfg5: weak = --poses per GPU, strong = --poses in total, split across the GPUs")
+                    help="weak = --poses per GPU (default), strong = --poses in total, split across the GPUs")
     ap.add_argument("--cpu-sample", type=int, default=20000)
     ap.add_argument("--traversal", type=int, default=3, help="kernel variant (fclgpu option 'traversal', see DESIGN.md)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -767,7 +767,7 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     for wl in names:
-        n = 10_000 if wl == "cfg1" else args.poses
+        n = 10_000 if wl == "cfg1" else (args.poses // world if args.scaling == "strong" else args.poses)
         steps = args.steps if wl == head else max(3, min(args.steps, 10))
         results[wl] = run_env_rob(ctx, wl, n, steps, args.warmup, (env, rob), meshes, with_cpu)
     clocks = sampler.stop()
@@ -775,7 +775,7 @@ def main():
         h = results[head]
         line = {
             "metric": METRIC, "value": h["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": h["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": h["ms_per_step"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOADS[head], "poses_per_gpu": h["poses_per_gpu"], "global_poses": world * h["poses_per_gpu"],
                        "pose_seed": 1, "models": "env.obj (2180 tris, 4359 nodes) posed vs rob.obj (216 tris, 431 nodes) at identity",

@@ -307,9 +307,11 @@ __global__ void __launch_bounds__(kOrdWarps * 32, FCLGPU_ORD_MINBLOCKS) collide_
           if (lane == 0) atomicMin(P.status, (int)FCLGPU_ERR_CONTACT_OVERFLOW);
           stored = Q.pool_capacity > (long long)off ? Q.pool_capacity - (long long)off : 0;
         }
+        // the pool is written once and never read by this kernel: streaming stores (evict first), so that the 2 GB
+        // passing through do not push the staging lines -- which ARE re-read and overwritten -- out of the L2
         const int4* src = reinterpret_cast<const int4*>(stage);
         int4* dst = reinterpret_cast<int4*>(Q.pool + off);
-        for (long long i = lane; i < stored * 4; i += 32) dst[i] = src[i];
+        for (long long i = lane; i < stored * 4; i += 32) __stcs(dst + i, src[i]);
       }
     }
     __syncwarp();

@@ -1153,7 +1153,15 @@ int distance_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, 
   }
   const long long trav = opt("traversal");
   const size_t front_smem = sizeof(WarpFront) * kDistWarps;
-  if (trav >= 2 && P.spill_pair) {
+  const bool tol = within != nullptr || stop_below >= 0;
+  if (trav >= 1 && tol) {  // tolerance verdicts: FP32-steered front with the early exit (also for traversal 1)
+    if (P.spill_pair)
+      rc = stats ? launch_persistent(distance_warp_kernel<true, true, true, true>, P, w, kDistWarps * 32, st, front_smem)
+                 : launch_persistent(distance_warp_kernel<false, true, true, true>, P, w, kDistWarps * 32, st, front_smem);
+    else
+      rc = stats ? launch_persistent(distance_warp_kernel<true, true, false, true>, P, w, kDistWarps * 32, st, front_smem)
+                 : launch_persistent(distance_warp_kernel<false, true, false, true>, P, w, kDistWarps * 32, st, front_smem);
+  } else if (trav >= 2 && P.spill_pair) {
     rc = stats ? launch_persistent(distance_warp_kernel<true, true, true>, P, w, kDistWarps * 32, st, front_smem)
                : launch_persistent(distance_warp_kernel<false, true, true>, P, w, kDistWarps * 32, st, front_smem);
   } else if (trav >= 2) {
