@@ -57,7 +57,7 @@ SYMBOLS = [
     "fclgpu_distance_mesh_sphere_batch", "fclgpu_distance_mesh_sphere_batch_host",
     "fclgpu_distance_cutoff_batch", "fclgpu_distance_cutoff_batch_host",
     "fclgpu_within_tolerance_batch", "fclgpu_within_tolerance_batch_host",
-    "fclgpu_load_obj", "fclgpu_save_obj", "fclgpu_free", "fclgpu_model_local_aabb", "fclgpu_broadphase_collide_host",
+    "fclgpu_load_obj", "fclgpu_save_obj", "fclgpu_free", "fclgpu_model_create_obbrss2", "fclgpu_model_local_aabb", "fclgpu_broadphase_collide_host",
     "fclgpu_collide_mesh_plane_batch", "fclgpu_collide_mesh_plane_batch_host",
     "fclgpu_shard_range", "fclgpu_comm_unique_id", "fclgpu_comm_init", "fclgpu_comm_rank", "fclgpu_comm_world",
     "fclgpu_comm_allgather", "fclgpu_comm_allgather_ragged", "fclgpu_comm_destroy", "fclgpu_comm_last_error",
@@ -129,6 +129,7 @@ def lib():
                                                   vp, C.c_int64, vp, up, up, vp]
     L.fclgpu_collide_mesh_plane_batch_host.argtypes = [vp, C.c_int32, dp, C.c_double, C.c_int64, dp, dp, C.POINTER(CollisionRequestC),
                                                        ip, vp, C.c_int64, vp, up, up]
+    L.fclgpu_model_create_obbrss2.argtypes = [C.c_int, C.c_int32, ip, dp, dp, dp, dp, dp, dp, dp, C.c_int32, dp, C.POINTER(vp)]
     L.fclgpu_model_local_aabb.argtypes = [vp, dp, dp, dp, dp]
     L.fclgpu_broadphase_collide_host.argtypes = [C.c_int32, C.POINTER(vp), C.c_int64, ip, dp, C.c_int64, ip, dp,
                                                  C.POINTER(CollisionRequestC), C.c_int64, ip, C.POINTER(C.c_int64), ip, dp, dp]

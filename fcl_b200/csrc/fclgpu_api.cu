@@ -289,6 +289,17 @@ extern "C" int fclgpu_model_create_obbrss(int device, int32_t n_nodes, const int
                                           const double* obb_extent3, const double* rss_To3,
                                           const double* rss_l2, const double* rss_r, int32_t n_tris,
                                           const double* tri_verts9, fclgpu_model** out) {
+  return fclgpu_model_create_obbrss2(device, n_nodes, first_child, axis9, obb_To3, obb_extent3, nullptr, rss_To3, rss_l2, rss_r,
+                                     n_tris, tri_verts9, out);
+}
+
+// rss_axis9 == NULL: the RSS shares the OBB's axes (true for every tree built by endModel() or refitted top-down,
+// BV_fitter-inl.h:464).  After the reference's BOTTOM-UP refit the two differ (OBBRSS::operator+ merges the OBB and
+// the RSS separately, OBBRSS-inl.h:95-101): such a model must be uploaded with both.
+extern "C" int fclgpu_model_create_obbrss2(int device, int32_t n_nodes, const int32_t* first_child, const double* axis9,
+                                           const double* obb_To3, const double* obb_extent3, const double* rss_axis9,
+                                           const double* rss_To3, const double* rss_l2, const double* rss_r, int32_t n_tris,
+                                           const double* tri_verts9, fclgpu_model** out) {
   if (!out) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "out is NULL");
   *out = nullptr;
   if (n_nodes <= 0 || n_tris <= 0) return fail(FCLGPU_ERR_BUILD_EMPTY_MODEL, "empty model");
@@ -313,7 +324,10 @@ extern "C" int fclgpu_model_create_obbrss(int device, int32_t n_nodes, const int
   for (int i = 0; i < n_nodes; ++i) {
     double* o = &obb[(size_t)i * kNodeDoubles];
     double* r = &rss[(size_t)i * kNodeDoubles];
-    for (int k = 0; k < 9; ++k) o[k] = r[k] = axis9[9 * (size_t)i + k];
+    for (int k = 0; k < 9; ++k) {
+      o[k] = axis9[9 * (size_t)i + k];
+      r[k] = (rss_axis9 ? rss_axis9 : axis9)[9 * (size_t)i + k];
+    }
     for (int k = 0; k < 3; ++k) {
       o[9 + k] = obb_To3[3 * (size_t)i + k];
       o[12 + k] = obb_extent3[3 * (size_t)i + k];
@@ -346,7 +360,7 @@ extern "C" int fclgpu_model_create_obbrss(int device, int32_t n_nodes, const int
   {
     std::vector<RssRec32> r32(n_nodes);
     for (int i = 0; i < n_nodes; ++i)
-      pack_rss32(axis9 + 9 * (size_t)i, rss_To3 + 3 * (size_t)i, rss_l2 + 2 * (size_t)i, rss_r[i], r32[i]);
+      pack_rss32((rss_axis9 ? rss_axis9 : axis9) + 9 * (size_t)i, rss_To3 + 3 * (size_t)i, rss_l2 + 2 * (size_t)i, rss_r[i], r32[i]);
     if (cudaMalloc((void**)&m->rss32, sizeof(RssRec32) * n_nodes) != cudaSuccess ||
         cudaMemcpy(m->rss32, r32.data(), sizeof(RssRec32) * n_nodes, cudaMemcpyHostToDevice) != cudaSuccess) {
       fclgpu_model_destroy(m);

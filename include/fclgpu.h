@@ -146,6 +146,13 @@ int fclgpu_model_create_obbrss(int device, int32_t n_nodes, const int32_t* first
                                const double* axis9, const double* obb_To3, const double* obb_extent3,
                                const double* rss_To3, const double* rss_l2, const double* rss_r,
                                int32_t n_tris, const double* tri_verts9, fclgpu_model** out);
+/* The same with separate RSS axes (rss_axis9 == NULL: shared).  endModel() and the top-down refit give both volumes
+ * the same axes; the reference's BOTTOM-UP refit (BVHModel::refitTree_bottomup, BVH_model-inl.h:952-1025) merges the
+ * children's OBBs and RSSs separately (OBBRSS::operator+, OBBRSS-inl.h:95-101), after which they differ. */
+int fclgpu_model_create_obbrss2(int device, int32_t n_nodes, const int32_t* first_child, const double* axis9,
+                                const double* obb_To3, const double* obb_extent3, const double* rss_axis9,
+                                const double* rss_To3, const double* rss_l2, const double* rss_r, int32_t n_tris,
+                                const double* tri_verts9, fclgpu_model** out);
 int fclgpu_model_from_bvh(int device, const fclgpu_bvh* bvh, fclgpu_model** out);
 /* On-device build: BVHModel::endModel() for BVH_MODEL_TRIANGLES + OBBRSS
  * (BVH_model-inl.h:450-517, 833-938) executed level by level on the GPU from the host arrays

@@ -52,12 +52,15 @@ class DeviceModel {
   DeviceModel(const BVH& m, int device = 0) : host_(&m) {
     const int n = m.getNumBVs(), nt = m.num_tris;
     std::vector<int32_t> fc(n);
-    std::vector<double> axis(9 * n), oT(3 * n), oe(3 * n), rT(3 * n), rl(2 * n), rr(n), tv(9 * nt);
+    std::vector<double> axis(9 * n), raxis(9 * n), oT(3 * n), oe(3 * n), rT(3 * n), rl(2 * n), rr(n), tv(9 * nt);
     for (int i = 0; i < n; ++i) {
       const auto& node = m.getBV(i);
       fc[i] = node.first_child;
       for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) axis[9 * i + 3 * r + c] = node.bv.obb.axis(r, c);  // rss.axis is identical
+        for (int c = 0; c < 3; ++c) {
+          axis[9 * i + 3 * r + c] = node.bv.obb.axis(r, c);
+          raxis[9 * i + 3 * r + c] = node.bv.rss.axis(r, c);  // equal to obb.axis unless FCL refitted the model bottom-up
+        }
       for (int k = 0; k < 3; ++k) {
         oT[3 * i + k] = node.bv.obb.To[k];
         oe[3 * i + k] = node.bv.obb.extent[k];
@@ -70,8 +73,8 @@ class DeviceModel {
     for (int t = 0; t < nt; ++t)
       for (int k = 0; k < 3; ++k)
         for (int c = 0; c < 3; ++c) tv[9 * t + 3 * k + c] = m.vertices[m.tri_indices[t][k]][c];
-    check(fclgpu_model_create_obbrss(device, n, fc.data(), axis.data(), oT.data(), oe.data(), rT.data(), rl.data(),
-                                     rr.data(), nt, tv.data(), &h_));
+    check(fclgpu_model_create_obbrss2(device, n, fc.data(), axis.data(), oT.data(), oe.data(), raxis.data(), rT.data(), rl.data(),
+                                      rr.data(), nt, tv.data(), &h_));
     // Refit topology.  BVHModel::primitive_indices is private (BVH_model.h:191), but the public node fields give it
     // back: node i owns primitive_indices[first_primitive .. first_primitive + num_primitives), a leaf owns exactly one
     // slot and names its triangle in first_child, so every slot is written by exactly one leaf.

@@ -595,3 +595,47 @@ def test_distance_front_survives_unprunable_fronts(oracle):
         finally:
             _capi.set_option("traversal", 3)
         assert np.all(np.abs(gd.min_distance - rd["min_distance"]) <= 1e-14 * np.abs(rd["min_distance"])), trav
+
+
+def test_upload_with_separate_rss_axes(models, oracle):
+    """fclgpu_model_create_obbrss2: after the reference's bottom-up refit the RSS of a node no longer shares the OBB's axes
+    (OBBRSS::operator+ merges the two volumes separately, OBBRSS-inl.h:95-101).  Here every RSS is re-expressed in another
+    frame -- same rectangle, corner moved to the opposite vertex, both in-plane axes negated -- and uploaded next to the
+    untouched OBBs: collide (OBB side) is unchanged byte for byte and distance returns the same minima (box tests only
+    steer; results come from the triangles)."""
+    import ctypes as C
+
+    (env, rob), (oenv, orob) = models
+    L = _capi.lib()
+    a = env.node_arrays()
+    nn, nt = len(a["first_child"]), env.num_tris
+    tv = np.zeros((nt, 9))
+    check = _capi.check
+    h = env._bvh
+    fc = np.zeros(nn, np.int32)
+    check(L.fclgpu_bvh_get(h, _capi.addr(fc), None, None, None, None, None, None, _capi.addr(tv)))
+    axis = np.ascontiguousarray(a["axis"]).reshape(nn, 3, 3)
+    rax = axis.copy()
+    rax[:, :, 0] *= -1.0
+    rax[:, :, 1] *= -1.0
+    rTo = a["rss_To"] + axis[:, :, 0] * a["rss_l"][:, :1] + axis[:, :, 1] * a["rss_l"][:, 1:2]
+    m2 = C.c_void_p()
+    check(L.fclgpu_model_create_obbrss2(0, nn, _capi.addr(fc), _capi.addr(np.ascontiguousarray(axis)), _capi.addr(np.ascontiguousarray(a["obb_To"])),
+                                        _capi.addr(np.ascontiguousarray(a["obb_ext"])), _capi.addr(np.ascontiguousarray(rax)),
+                                        _capi.addr(np.ascontiguousarray(rTo)), _capi.addr(np.ascontiguousarray(a["rss_l"])),
+                                        _capi.addr(np.ascontiguousarray(a["rss_r"])), nt, _capi.addr(tv), C.byref(m2)))
+    try:
+        n = 4000
+        P = random_poses(n, seed=31)
+        ref = oracle.distance_batch(oenv, orob, P, None, True, 2, nthreads=8)
+        dist = np.zeros(n)
+        rq = F.DistanceRequest(False)._c()
+        check(L.fclgpu_distance_batch_host(m2, rob.device_model(0), n, _capi.addr(P), None, C.byref(rq), _capi.addr(dist), None, None, None,
+                                           None, None, None))
+        assert np.array_equal(dist, ref["min_distance"])
+        cnt = np.zeros(n, np.int32)
+        cq = F.CollisionRequest()._c()
+        check(L.fclgpu_collide_batch_host(m2, rob.device_model(0), n, _capi.addr(P), None, C.byref(cq), _capi.addr(cnt), None, 0, None, None, None))
+        assert np.array_equal(cnt, oracle.collide_batch(oenv, orob, P, None, 1, False, nthreads=8)["counts"])
+    finally:
+        L.fclgpu_model_destroy(m2)
