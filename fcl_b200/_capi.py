@@ -65,7 +65,7 @@ SYMBOLS = [
     "fclgpu_model_num_tris", "fclgpu_model_device", "fclgpu_collide_batch", "fclgpu_collide_batch_host",
     "fclgpu_distance_batch", "fclgpu_distance_batch_host", "fclgpu_abi_version", "fclgpu_device_count",
     "fclgpu_last_error", "fclgpu_pose_from_colmajor4x4", "fclgpu_sync_status", "fclgpu_set_option",
-    "fclgpu_get_option", "fclgpu_launch_count", "fclgpu_microbench",
+    "fclgpu_get_option", "fclgpu_launch_count", "fclgpu_debug_counters", "fclgpu_microbench",
 ]
 
 _lib = None
@@ -156,6 +156,7 @@ def lib():
     L.fclgpu_get_option.argtypes = [C.c_char_p]
     L.fclgpu_get_option.restype = C.c_int64
     L.fclgpu_launch_count.restype = C.c_int64
+    L.fclgpu_debug_counters.argtypes = [C.c_int, C.POINTER(C.c_uint64), C.c_int]
     L.fclgpu_microbench.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
     _lib = L
     return L

@@ -44,6 +44,14 @@ FD float f32_rsqrt(float x) {
   return 1.0f / sqrtf(x);
 #endif
 }
+// approximate reciprocal (MUFU.RCP): only used where the result's accuracy cannot invalidate a bound
+FD float f32_rcp(float x) {
+#ifdef __CUDA_ARCH__
+  return __fdividef(1.0f, x);
+#else
+  return 1.0f / x;
+#endif
+}
 
 // lower bound on the distance between two RSS; R0 (row-major), T0: pose of model2 in model1's
 // frame, t0_l1 >= |T0|_1.  Valid for any inputs: every candidate is the support-function gap
@@ -324,6 +332,123 @@ FD float tri_lower_bound_dirs_f32(const float* s1, const float* s2, const float*
   const float Lsum = fmaxf(fmaxf(l1(s1), l1(s2)), fmaxf(l1(t0), fmaxf(l1(t1), l1(t2))));
   const float lb = fmaf(best, 0.999999f, -(1.9073486328125e-06f * Lsum));  // 32 * 2^-24 * Lsum
   return fmaxf(lb, 0.0f);
+}
+
+// Two-sided single-precision bounds on the distance between two triangles: lo <= d <= hi.
+// Same local coordinates as tri_lower_bound_f32 (S = {0, s1, s2}, T = {t0, t1, t2}, translated in FP64, rounded once).
+//   * Fifteen candidate point pairs (X on S, Y on T), each an ACTUAL pair of points of the two (rounded) triangles
+//     whatever the rounding of its parameters: the nine edge / edge pairs (clamped closed form) and the six
+//     vertex / face pairs (barycentric coordinates of the projection, clamped into the triangle).
+//   * hi = the smallest candidate length, plus slack: an upper bound because the two points exist.
+//   * lo = the support-function gap along V = Y - X of that candidate, minus slack: a lower bound along ANY
+//     direction, and tight along this one (in exact arithmetic V of the true closest pair gives gap = d).
+// Error budget (u = 2^-24, L = largest |coordinate| <= Lsum): a candidate point is evaluated with <= 2 u L per
+// coordinate, V and its length with <= 3 u |V|, rounding the inputs moves every point by <= sqrt(3) u L:
+// |hi_computed - d(X, Y)| <= 11 u L + 3 u |V|; the projections of lo as in tri_lower_bound_f32 (<= 13 u L + 3 u gap).
+// Slack: 64 u Lsum + 2e-6 relative on hi (covers the 2-ulp rsqrt), 32 u Lsum + 1e-6 relative on lo.
+// `trust_hi` is false when a face normal is so short that the reference's triDistance skips its vertex / face stage
+// (|N|^2 <= 1e-15, triangle_distance-inl.h:262,318) and may return MORE than the true distance: hi bounds the true
+// distance only, so the caller must not prune with it then.
+FD void tri_closest_bounds_f32(const float* s1, const float* s2, const float* t0, const float* t1, const float* t2,
+                               float& lo, float& hi, bool& trust_hi) {
+  const float P[3][3] = {{0.0f, 0.0f, 0.0f}, {s1[0], s1[1], s1[2]}, {s2[0], s2[1], s2[2]}};
+  const float Q[3][3] = {{t0[0], t0[1], t0[2]}, {t1[0], t1[1], t1[2]}, {t2[0], t2[1], t2[2]}};
+  float E[3][3], Fv[3][3], a[3], e[3], ra[3], re[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int n = (i + 1) % 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      E[i][c] = P[n][c] - P[i][c];
+      Fv[i][c] = Q[n][c] - Q[i][c];
+    }
+    a[i] = fmaf(E[i][2], E[i][2], fmaf(E[i][1], E[i][1], E[i][0] * E[i][0]));
+    e[i] = fmaf(Fv[i][2], Fv[i][2], fmaf(Fv[i][1], Fv[i][1], Fv[i][0] * Fv[i][0]));
+    ra[i] = f32_rcp(fmaxf(a[i], 1e-30f));
+    re[i] = f32_rcp(fmaxf(e[i], 1e-30f));
+  }
+  float best = 3.0e38f, V[3] = {0.0f, 0.0f, 0.0f};
+  auto take = [&](float vx, float vy, float vz) {
+    const float dd = fmaf(vz, vz, fmaf(vy, vy, vx * vx));
+    const bool better = dd < best;
+    best = better ? dd : best;
+    V[0] = better ? vx : V[0];
+    V[1] = better ? vy : V[1];
+    V[2] = better ? vz : V[2];
+  };
+  auto clamp01 = [](float x) { return fminf(fmaxf(x, 0.0f), 1.0f); };
+  // edge i of S against edge j of T
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float r0 = P[i][0] - Q[j][0], r1 = P[i][1] - Q[j][1], r2 = P[i][2] - Q[j][2];
+      const float b = fmaf(E[i][2], Fv[j][2], fmaf(E[i][1], Fv[j][1], E[i][0] * Fv[j][0]));
+      const float c = fmaf(E[i][2], r2, fmaf(E[i][1], r1, E[i][0] * r0));
+      const float f = fmaf(Fv[j][2], r2, fmaf(Fv[j][1], r1, Fv[j][0] * r0));
+      const float denom = fmaf(a[i], e[j], -(b * b));
+      float s = clamp01(fmaf(b, f, -(c * e[j])) * f32_rcp(fmaxf(denom, 1e-30f)));
+      s = denom > 1e-6f * (a[i] * e[j]) ? s : 0.0f;  // nearly parallel: any s is a valid point
+      float t = fmaf(b, s, f) * re[j];
+      const float s_lo = clamp01(-c * ra[i]), s_hi = clamp01((b - c) * ra[i]);
+      s = t < 0.0f ? s_lo : (t > 1.0f ? s_hi : s);
+      t = clamp01(t);
+      // V = Y - X = (Q_j + t F_j) - (P_i + s E_i) = -r + t F_j - s E_i
+      take(fmaf(-s, E[i][0], fmaf(t, Fv[j][0], -r0)), fmaf(-s, E[i][1], fmaf(t, Fv[j][1], -r1)),
+           fmaf(-s, E[i][2], fmaf(t, Fv[j][2], -r2)));
+    }
+  }
+  // vertex of one triangle against the face of the other: barycentric coordinates (u, v) of the projection with respect
+  // to origin O and edge vectors g1, g2, clamped into the triangle; sign = +1 when the vertex belongs to T (V = Y - X)
+  auto vertex_face = [&](const float* O, const float* g1, const float* g2, float d11, float d12, float d22, float rdet,
+                         const float* Y, float sign) {
+    const float w0 = Y[0] - O[0], w1 = Y[1] - O[1], w2 = Y[2] - O[2];
+    const float p1 = fmaf(g1[2], w2, fmaf(g1[1], w1, g1[0] * w0));
+    const float p2 = fmaf(g2[2], w2, fmaf(g2[1], w1, g2[0] * w0));
+    float uu = fmaf(d22, p1, -(d12 * p2)) * rdet;
+    float vv = fmaf(d11, p2, -(d12 * p1)) * rdet;
+    uu = fminf(fmaxf(uu, 0.0f), 1.0f);
+    vv = fminf(fmaxf(vv, 0.0f), 1.0f - uu);
+    take(sign * fmaf(-vv, g2[0], fmaf(-uu, g1[0], w0)), sign * fmaf(-vv, g2[1], fmaf(-uu, g1[1], w1)),
+         sign * fmaf(-vv, g2[2], fmaf(-uu, g1[2], w2)));
+  };
+  float gS2[3], gT2[3];  // second edge vector from the first vertex: S2 - S0, T2 - T0
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    gS2[c] = P[2][c];
+    gT2[c] = Q[2][c] - Q[0][c];
+  }
+  const float dS12 = fmaf(E[0][2], gS2[2], fmaf(E[0][1], gS2[1], E[0][0] * gS2[0]));
+  const float dT12 = fmaf(Fv[0][2], gT2[2], fmaf(Fv[0][1], gT2[1], Fv[0][0] * gT2[0]));
+  float nS[3], nT[3];
+  nS[0] = fmaf(E[0][1], gS2[2], -(E[0][2] * gS2[1])); nS[1] = fmaf(E[0][2], gS2[0], -(E[0][0] * gS2[2])); nS[2] = fmaf(E[0][0], gS2[1], -(E[0][1] * gS2[0]));
+  nT[0] = fmaf(Fv[0][1], gT2[2], -(Fv[0][2] * gT2[1])); nT[1] = fmaf(Fv[0][2], gT2[0], -(Fv[0][0] * gT2[2])); nT[2] = fmaf(Fv[0][0], gT2[1], -(Fv[0][1] * gT2[0]));
+  const float nlS = fmaf(nS[2], nS[2], fmaf(nS[1], nS[1], nS[0] * nS[0]));
+  const float nlT = fmaf(nT[2], nT[2], fmaf(nT[1], nT[1], nT[0] * nT[0]));
+  const float rdS = f32_rcp(fmaxf(nlS, 1e-30f)), rdT = f32_rcp(fmaxf(nlT, 1e-30f));  // |g1 x g2|^2 = d11 d22 - d12^2
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    vertex_face(P[0], E[0], gS2, a[0], dS12, a[2], rdS, Q[k], 1.0f);
+    vertex_face(Q[0], Fv[0], gT2, e[0], dT12, e[2], rdT, P[k], -1.0f);
+  }
+  auto l1 = [](const float* p) { return fabsf(p[0]) + fabsf(p[1]) + fabsf(p[2]); };
+  const float Lsum = fmaxf(fmaxf(l1(s1), l1(s2)), fmaxf(l1(t0), fmaxf(l1(t1), l1(t2))));
+  const bool ok = (best > 1e-30f) && (best < 1e30f);
+  const float rlen = f32_rsqrt(ok ? best : 1.0f);
+  const float len = ok ? best * rlen : (best < 1.0f ? 1e-15f : 3.0e38f);
+  hi = fmaf(len, 1.000002f, 3.814697265625e-06f * Lsum);  // 64 * 2^-24 * Lsum
+  // support-function gap along V
+  const float a1 = fmaf(V[2], s1[2], fmaf(V[1], s1[1], V[0] * s1[0]));
+  const float a2 = fmaf(V[2], s2[2], fmaf(V[1], s2[1], V[0] * s2[0]));
+  const float b0 = fmaf(V[2], t0[2], fmaf(V[1], t0[1], V[0] * t0[0]));
+  const float b1 = fmaf(V[2], t1[2], fmaf(V[1], t1[1], V[0] * t1[0]));
+  const float b2 = fmaf(V[2], t2[2], fmaf(V[1], t2[1], V[0] * t2[0]));
+  const float g = fminf(b0, fminf(b1, b2)) - fmaxf(0.0f, fmaxf(a1, a2));
+  const float v = ok ? g * rlen : 0.0f;
+  lo = fmaxf(fmaf(v, 0.999999f, -(1.9073486328125e-06f * Lsum)), 0.0f);  // 32 * 2^-24 * Lsum
+  // |N| computed with <= 8 u |g1| |g2| absolute error; the reference compares |N|^2 with 1e-15 (|N| > 3.17e-8)
+  const float limS = 3.2e-8f + 5e-7f * sqrtf(a[0] * a[2]), limT = 3.2e-8f + 5e-7f * sqrtf(e[0] * e[2]);
+  trust_hi = (nlS > limS * limS) && (nlT > limT * limT) && (best < 1e30f);
 }
 
 // Single-precision classification of a triangle pair for the collide leaf test:

@@ -1786,6 +1786,18 @@ extern "C" int fclgpu_set_option(const char* name, int64_t value) {
 }
 extern "C" int64_t fclgpu_get_option(const char* name) { return name ? opt(name) : 0; }
 extern "C" int64_t fclgpu_launch_count(void) { return g_launches.load(); }
+// development counters (all zero unless the library was built with an instrumentation flag such as -DFCLGPU_DIST_PROF=1)
+extern "C" int fclgpu_debug_counters(int device, uint64_t* out16, int reset) {
+  if (!out16) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "out16 is NULL");
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpyFromSymbol(out16, g_debug_counters, sizeof(uint64_t) * 16));
+  if (reset) {
+    uint64_t z[16] = {0};
+    CUDA_TRY(cudaMemcpyToSymbol(g_debug_counters, z, sizeof(z)));
+  }
+  return 0;
+}
 
 // ------------------------------------------------------------------------------------------
 // micro-benchmarks for the roofline denominators

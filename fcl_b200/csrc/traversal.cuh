@@ -582,6 +582,27 @@ __device__ __forceinline__ unsigned warp_sort_keys(unsigned key, int lane) {
 #ifndef FCLGPU_DIST_MINBLOCKS
 #define FCLGPU_DIST_MINBLOCKS 5
 #endif
+#ifndef FCLGPU_DIST_SEED
+#define FCLGPU_DIST_SEED 0
+#endif
+// Development build (-DFCLGPU_DIST_PROF=1): per-phase SM cycles of the sorted-front kernel, summed over warps
+// (0 prologue / epilogue, 1 BV rounds, 2 screening rounds, 3 exact rounds, 4 refill; 8.. = round counts), read with
+// fclgpu_debug_counters().  Compiled out of the product build.
+#ifndef FCLGPU_DIST_PROF
+#define FCLGPU_DIST_PROF 0
+#endif
+__device__ unsigned long long g_debug_counters[16];
+#if FCLGPU_DIST_PROF
+#define DPROF_MARK(k)                      \
+  {                                        \
+    const long long t_now = clock64();     \
+    prof_acc[k] += t_now - prof_t0;        \
+    prof_cnt[k] += 1;                      \
+    prof_t0 = t_now;                       \
+  }
+#else
+#define DPROF_MARK(k)
+#endif
 // kSpill: instantiation with the global overflow area for deep trees (kept out of the default instantiation:
 // the extra live state costs the hot loop 10 %)
 // kTol: tolerance verdicts (stop_below / within) -- a separate instantiation as well: the early-exit test inside the leaf
@@ -596,12 +617,64 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
   // box tests dominate and the later minimum update costs more than the saved tests (cfg5: 48 -> 56 ms)
   constexpr bool kScreen = kScreenLeaves && !kSpill;
 
+  // Seed front (FCLGPU_DIST_SEED levels): while nothing is known about the minimum every pair of the first BVTT levels
+  // is expanded whatever the pose, and which node of a pair is split depends on the two trees only (firstOverSecond).
+  // Warp 0 therefore expands the root pair level by level once per block (leaf pairs stay as they are, at most 32
+  // entries), and every query starts with ONE full round that bounds and sorts those pairs instead of the 1-, 2-, 4-,
+  // 8- and 16-lane rounds that lead there.  Same BVTT coverage, so the same minimum.
+  constexpr bool kSeed = FCLGPU_DIST_SEED > 0;
+  __shared__ uint2 s_seed[32];
+  __shared__ int s_nseed;
+  if (kSeed) {
+    if (threadIdx.x < 32) {
+      if (lane == 0) s_seed[0] = make_uint2(0u, 0u);
+      __syncwarp();
+      int n = 1;
+      for (int lv = 0; lv < FCLGPU_DIST_SEED; ++lv) {
+        const bool have = lane < n;
+        uint2 e = make_uint2(0u, 0u);
+        int fc1 = -1, fc2 = -1;
+        double size1 = 0.0, size2 = 0.0;
+        if (have) {
+          e = s_seed[lane];
+          load_topo(P.m1.topo, (int)e.x, fc1, size1);
+          load_topo(P.m2.topo, (int)e.y, fc2, size2);
+        }
+        const bool l1 = fc1 < 0, l2 = fc2 < 0;
+        const bool exp = have && !(l1 && l2);
+        const unsigned em = __ballot_sync(0xffffffffu, exp);
+        const int add = __popc(em);
+        if (add == 0 || n + add > 32) break;
+        __syncwarp();
+        if (have) {
+          const int pos = lane + __popc(em & lt_mask);
+          if (!exp) {
+            s_seed[pos] = e;
+          } else if (l2 || (!l1 && (size1 > size2))) {  // firstOverSecond
+            s_seed[pos] = make_uint2((unsigned)fc1, e.y);
+            s_seed[pos + 1] = make_uint2((unsigned)fc1 + 1u, e.y);
+          } else {
+            s_seed[pos] = make_uint2(e.x, (unsigned)fc2);
+            s_seed[pos + 1] = make_uint2(e.x, (unsigned)fc2 + 1u);
+          }
+        }
+        n += add;
+        __syncwarp();
+      }
+      if (lane == 0) s_nseed = n;
+    }
+    __syncthreads();
+  }
+
   while (true) {
     long long q = 0;
     if (lane == 0) q = (long long)atomicAdd(P.work_counter, 1ull);
     q = __shfl_sync(0xffffffffu, q, 0);
     if (q >= P.n) break;
 
+#if FCLGPU_DIST_PROF
+    long long prof_t0 = clock64();
+#endif
     M3 R;
     V3 T;
     {
@@ -619,11 +692,17 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
       t_l1 = __double2float_ru((fabs(T.x) + fabs(T.y)) + fabs(T.z));
     }
 
+#if FCLGPU_DIST_PROF
+    long long prof_acc[5] = {0, 0, 0, 0, 0};
+    unsigned prof_cnt[5] = {0, 0, 0, 0, 0};
+    DPROF_MARK(0)
+#endif
     double min_d = P.cutoff;  // DBL_MAX for fcl::distance
     // bounds are floats: (double)b < min_d  <=>  b < min_f with min_f = min_d rounded up (the smallest float >= min_d;
     // +inf for DBL_MAX)
     float min_f = __double2float_ru(min_d);
-    int sp = 1, nleaf = 1, nraw = 0;
+    int sp = kSeed ? 0 : 1, nleaf = 1, nraw = 0;
+    bool seed_pending = kSeed;
     uint32_t bv_tests = 0, leaf_tests = 0;
     if (lane == 0) {
       S.pair[0] = make_uint2(0u, 0u);
@@ -667,6 +746,7 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
           sp += __popc(m);
         }
         __syncwarp();
+        DPROF_MARK(4)
         continue;
       }
       // the screening round may add up to min(nraw, 32) pairs to the exact queue: only run it when they fit
@@ -712,9 +792,10 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
         }
         nleaf += __popc(km);
         __syncwarp();
+        DPROF_MARK(2)
         continue;
       }
-      const bool do_leaf = (nleaf >= kLeafTrigger) || (sp == 0 && nleaf > 0);
+      const bool do_leaf = (nleaf >= kLeafTrigger) || (sp == 0 && nleaf > 0 && !seed_pending);
       if (do_leaf) {
         const int k = nleaf < 32 ? nleaf : 32;
         nleaf -= k;
@@ -765,9 +846,10 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
           }
         }
         __syncwarp();
+        DPROF_MARK(3)
         continue;
       }
-      if (sp == 0) break;
+      if (sp == 0 && !seed_pending) break;
 
       // ---- BV round ----
       // every lane pops one entry; dead entries (bound no longer beats the minimum) vanish, leaf
@@ -776,103 +858,112 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
       // Close to the stack limit (a front that nothing prunes, e.g. coincident meshes before the first zero distance
       // is found) a warp without (room in) an overflow area pops and expands ONE entry per round: plain
       // nearest-first depth first, whose growth is bounded by the tree depths (checked on the host).
+      int n_test;  // lanes that bound a child pair in this round
+      if (kSeed && seed_pending) {
+        seed_pending = false;
+        n_test = s_nseed;
+        if (lane < n_test) S.expand[lane] = s_seed[lane];
+        __syncwarp();
+      } else {
 #ifndef FCLGPU_DIST_TIGHT
 #define FCLGPU_DIST_TIGHT 1
 #endif
-      const bool tight = FCLGPU_DIST_TIGHT && sp > kDistStackCap - 160 &&
-                         (!kSpill || g_pair == nullptr || gsp + kSpillBlock > P.spill_cap);  // ... or the overflow area is full
-      const int k = tight ? 1 : (sp < 32 ? sp : 32);
-      uint2 pr = make_uint2(0u, 0u);
-      float bd = 0.0f;
-      bool alive = lane < k;
-      if (alive) {
-        pr = S.pair[sp - 1 - lane];
-        bd = S.bound[sp - 1 - lane];
-        alive = bd < min_f;  // canStop(c): bound >= min_distance -> skip
-      }
-      int fc1 = 0, fc2 = 0;
-      double size1 = 0.0, size2 = 0.0;
-      if (alive) {  // {first_child, size} of both nodes: one 16-byte load each
-        load_topo(P.m1.topo, (int)pr.x, fc1, size1);
-        load_topo(P.m2.topo, (int)pr.y, fc2, size2);
-      }
-      const bool l1 = fc1 < 0, l2 = fc2 < 0;
-      const bool leafpair = alive && l1 && l2;
-      const unsigned lm = __ballot_sync(0xffffffffu, leafpair);
-      if (leafpair) {
-        const uint2 tri_ids = make_uint2((unsigned)(-(fc1 + 1)), (unsigned)(-(fc2 + 1)));
-        if (kBound32 && kScreen) {
-          const int pos = nraw + __popc(lm & lt_mask);
-          S.raw_pair[pos] = tri_ids;
-          S.raw_bound[pos] = bd;
-        } else {
-          const int pos = nleaf + __popc(lm & lt_mask);
-          S.leaf_pair[pos] = tri_ids;
-          S.leaf_bound[pos] = bd;
+        const bool tight = FCLGPU_DIST_TIGHT && sp > kDistStackCap - 160 &&
+                           (!kSpill || g_pair == nullptr || gsp + kSpillBlock > P.spill_cap);  // ... or the overflow area is full
+        const int k = tight ? 1 : (sp < 32 ? sp : 32);
+        uint2 pr = make_uint2(0u, 0u);
+        float bd = 0.0f;
+        bool alive = lane < k;
+        if (alive) {
+          pr = S.pair[sp - 1 - lane];
+          bd = S.bound[sp - 1 - lane];
+          alive = bd < min_f;  // canStop(c): bound >= min_distance -> skip
         }
-      }
-      if (kBound32 && kScreen) nraw += __popc(lm);
-      else nleaf += __popc(lm);
-      const bool internal = alive && !leafpair;
-      const unsigned im = __ballot_sync(0xffffffffu, internal);
-      const int n_int = __popc(im), rank = __popc(im & lt_mask);
-      sp -= k;
-      if (kSpill && kDistStackCap - sp - n_int < kDistPop && g_pair != nullptr && sp >= kSpillBlock && gsp + kSpillBlock <= P.spill_cap) {
-        // The front no longer fits (deep trees): park the bottom of the stack -- the farthest, oldest candidates --
-        // in the warp's global overflow area and slide the rest down.
-        for (int base = 0; base < kSpillBlock; base += 32) {
-          g_pair[gsp + base + lane] = S.pair[base + lane];
-          g_bound[gsp + base + lane] = S.bound[base + lane];
+        int fc1 = 0, fc2 = 0;
+        double size1 = 0.0, size2 = 0.0;
+        if (alive) {  // {first_child, size} of both nodes: one 16-byte load each
+          load_topo(P.m1.topo, (int)pr.x, fc1, size1);
+          load_topo(P.m2.topo, (int)pr.y, fc2, size2);
         }
-        gsp += kSpillBlock;
-        __syncwarp();
-        for (int base = kSpillBlock; base < sp; base += 32) {
-          const int i = base + lane;
-          uint2 pr2 = make_uint2(0u, 0u);
-          float bd2 = 0.0f;
-          if (i < sp) {
-            pr2 = S.pair[i];
-            bd2 = S.bound[i];
-          }
-          __syncwarp();
-          if (i < sp) {
-            S.pair[i - kSpillBlock] = pr2;
-            S.bound[i - kSpillBlock] = bd2;
-          }
-        }
-        sp -= kSpillBlock;
-        __syncwarp();
-      }
-      int n_exp = n_int < kDistPop ? n_int : kDistPop;
-      const int room = kDistStackCap - sp - n_int;  // after re-pushing the leftovers, 2*n_exp children minus n_exp must fit
-      if (n_exp > room) n_exp = room;
-      if (n_int > 0 && n_exp <= 0) {
-        if (lane == 0) atomicMin(P.status, (int)FCLGPU_ERR_STACK_OVERFLOW);
-        sp = 0;
-        gsp = 0;
-        nleaf = 0;
-        nraw = 0;
-        break;
-      }
-      __syncwarp();  // every lane has read its popped entry before slots are overwritten
-      if (internal) {
-        if (rank < n_exp) {
-          if (l2 || (!l1 && (size1 > size2))) {  // firstOverSecond
-            S.expand[2 * rank] = make_uint2((unsigned)fc1, pr.y);
-            S.expand[2 * rank + 1] = make_uint2((unsigned)fc1 + 1u, pr.y);
+        const bool l1 = fc1 < 0, l2 = fc2 < 0;
+        const bool leafpair = alive && l1 && l2;
+        const unsigned lm = __ballot_sync(0xffffffffu, leafpair);
+        if (leafpair) {
+          const uint2 tri_ids = make_uint2((unsigned)(-(fc1 + 1)), (unsigned)(-(fc2 + 1)));
+          if (kBound32 && kScreen) {
+            const int pos = nraw + __popc(lm & lt_mask);
+            S.raw_pair[pos] = tri_ids;
+            S.raw_bound[pos] = bd;
           } else {
-            S.expand[2 * rank] = make_uint2(pr.x, (unsigned)fc2);
-            S.expand[2 * rank + 1] = make_uint2(pr.x, (unsigned)fc2 + 1u);
+            const int pos = nleaf + __popc(lm & lt_mask);
+            S.leaf_pair[pos] = tri_ids;
+            S.leaf_bound[pos] = bd;
           }
-        } else {  // leftover: back on the stack, order preserved (rank n_exp nearest -> top)
-          const int pos = sp + (n_int - 1 - rank);
-          S.pair[pos] = pr;
-          S.bound[pos] = bd;
         }
+        if (kBound32 && kScreen) nraw += __popc(lm);
+        else nleaf += __popc(lm);
+        const bool internal = alive && !leafpair;
+        const unsigned im = __ballot_sync(0xffffffffu, internal);
+        const int n_int = __popc(im), rank = __popc(im & lt_mask);
+        sp -= k;
+        if (kSpill && kDistStackCap - sp - n_int < kDistPop && g_pair != nullptr && sp >= kSpillBlock && gsp + kSpillBlock <= P.spill_cap) {
+          // The front no longer fits (deep trees): park the bottom of the stack -- the farthest, oldest candidates --
+          // in the warp's global overflow area and slide the rest down.
+          for (int base = 0; base < kSpillBlock; base += 32) {
+            g_pair[gsp + base + lane] = S.pair[base + lane];
+            g_bound[gsp + base + lane] = S.bound[base + lane];
+          }
+          gsp += kSpillBlock;
+          __syncwarp();
+          for (int base = kSpillBlock; base < sp; base += 32) {
+            const int i = base + lane;
+            uint2 pr2 = make_uint2(0u, 0u);
+            float bd2 = 0.0f;
+            if (i < sp) {
+              pr2 = S.pair[i];
+              bd2 = S.bound[i];
+            }
+            __syncwarp();
+            if (i < sp) {
+              S.pair[i - kSpillBlock] = pr2;
+              S.bound[i - kSpillBlock] = bd2;
+            }
+          }
+          sp -= kSpillBlock;
+          __syncwarp();
+        }
+        int n_exp = n_int < kDistPop ? n_int : kDistPop;
+        const int room = kDistStackCap - sp - n_int;  // after re-pushing the leftovers, 2*n_exp children minus n_exp must fit
+        if (n_exp > room) n_exp = room;
+        if (n_int > 0 && n_exp <= 0) {
+          if (lane == 0) atomicMin(P.status, (int)FCLGPU_ERR_STACK_OVERFLOW);
+          sp = 0;
+          gsp = 0;
+          nleaf = 0;
+          nraw = 0;
+          break;
+        }
+        __syncwarp();  // every lane has read its popped entry before slots are overwritten
+        if (internal) {
+          if (rank < n_exp) {
+            if (l2 || (!l1 && (size1 > size2))) {  // firstOverSecond
+              S.expand[2 * rank] = make_uint2((unsigned)fc1, pr.y);
+              S.expand[2 * rank + 1] = make_uint2((unsigned)fc1 + 1u, pr.y);
+            } else {
+              S.expand[2 * rank] = make_uint2(pr.x, (unsigned)fc2);
+              S.expand[2 * rank + 1] = make_uint2(pr.x, (unsigned)fc2 + 1u);
+            }
+          } else {  // leftover: back on the stack, order preserved (rank n_exp nearest -> top)
+            const int pos = sp + (n_int - 1 - rank);
+            S.pair[pos] = pr;
+            S.bound[pos] = bd;
+          }
+        }
+        sp += n_int - n_exp;
+        __syncwarp();
+        n_test = 2 * n_exp;
       }
-      sp += n_int - n_exp;
-      __syncwarp();
-      const bool expand = lane < 2 * n_exp;
+      const bool expand = lane < n_test;
       unsigned key = 0xffffffffu;
       uint2 xy = make_uint2(0u, 0u);
       float d = 0.0f;  // lower bound on the distance between the two child BVs
@@ -890,7 +981,7 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
         }
         if (d < min_f) key = (__float_as_uint(d) & ~31u) | (unsigned)lane;
       }
-      if (kStats) bv_tests += 2 * n_exp;
+      if (kStats) bv_tests += n_test;
       const int nkeep = __popc(__ballot_sync(0xffffffffu, key != 0xffffffffu));
       if (nkeep > 0) {
         // full 32-key sort: ordering only the two children of each parent instead (one shuffle) was measured at
@@ -907,6 +998,7 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
         sp += nkeep;
       }
       __syncwarp();
+      DPROF_MARK(1)
     }
 
     // postprocess: nearest points (model1 frame) -> world with tf1
@@ -928,6 +1020,16 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
       }
     }
     __syncwarp();
+#if FCLGPU_DIST_PROF
+    DPROF_MARK(0)
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        atomicAdd(&g_debug_counters[k], (unsigned long long)prof_acc[k]);
+        atomicAdd(&g_debug_counters[8 + k], (unsigned long long)prof_cnt[k]);
+      }
+    }
+#endif
   }
 }
 

@@ -399,6 +399,9 @@ int fclgpu_set_option(const char* name, int64_t value);
 int64_t fclgpu_get_option(const char* name);
 /* Kernel launches issued by this library since process start (bench.py's gpu_launches). */
 int64_t fclgpu_launch_count(void);
+/* Development counters of instrumented builds (-DFCLGPU_DIST_PROF=1: per-phase cycles of the distance kernel); a product
+ * build returns zeros. */
+int fclgpu_debug_counters(int device, uint64_t* out16, int reset);
 /* FP64 pipe / L2 micro-benchmarks used for the roofline denominators:
  * kind 0: unfused DMUL+DADD ops/s, 1: DFMA ops/s (counted as 1 op), 2: L2-resident read GB/s */
 int fclgpu_microbench(int device, int kind, double* result);

@@ -49,8 +49,9 @@ def test_tolerance_verification_matches_oracle(oracle, env_rob_npz, trav):
             assert (wres.min_distance[~within] == cutoff).all()
             within2, full_tol = F.within_tolerance_batch(env, P, rob, None, tol, stats=True, early_exit=False)
             assert np.array_equal(within2, within)
-            assert wres.n_bv.astype(np.int64).sum() <= full_tol.n_bv.astype(np.int64).sum()
-            assert wres.n_leaf.astype(np.int64).sum() <= full_tol.n_leaf.astype(np.int64).sum()
+            if trav != 1:  # (traversal 1: the early-exit verdict runs the FP32-steered kernel, the plain query the FP64-bound one)
+                assert wres.n_bv.astype(np.int64).sum() <= full_tol.n_bv.astype(np.int64).sum()
+                assert wres.n_leaf.astype(np.int64).sum() <= full_tol.n_leaf.astype(np.int64).sum()
     finally:
         _capi.set_option("traversal", 3)
 
