@@ -583,7 +583,7 @@ __device__ __forceinline__ unsigned warp_sort_keys(unsigned key, int lane) {
 #define FCLGPU_DIST_MINBLOCKS 5
 #endif
 #ifndef FCLGPU_DIST_SEED
-#define FCLGPU_DIST_SEED 0
+#define FCLGPU_DIST_SEED 5
 #endif
 // Development build (-DFCLGPU_DIST_PROF=1): per-phase SM cycles of the sorted-front kernel, summed over warps
 // (0 prologue / epilogue, 1 BV rounds, 2 screening rounds, 3 exact rounds, 4 refill; 8.. = round counts), read with
@@ -701,8 +701,9 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
     // bounds are floats: (double)b < min_d  <=>  b < min_f with min_f = min_d rounded up (the smallest float >= min_d;
     // +inf for DBL_MAX)
     float min_f = __double2float_ru(min_d);
-    int sp = kSeed ? 0 : 1, nleaf = 1, nraw = 0;
-    bool seed_pending = kSeed;
+    // (a finite start value prunes from the root pair on: far queries end after one box test, so no seed front then)
+    bool seed_pending = kSeed && !(min_d < DBL_MAX);
+    int sp = seed_pending ? 0 : 1, nleaf = 1, nraw = 0;
     uint32_t bv_tests = 0, leaf_tests = 0;
     if (lane == 0) {
       S.pair[0] = make_uint2(0u, 0u);
