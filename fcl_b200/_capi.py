@@ -52,6 +52,7 @@ class FclGpuError(RuntimeError):
 SYMBOLS = [
     "fclgpu_bvh_build_obbrss", "fclgpu_bvh_destroy", "fclgpu_bvh_num_nodes", "fclgpu_bvh_num_tris", "fclgpu_bvh_get",
     "fclgpu_bvh_refit_topdown", "fclgpu_bvh_num_vertices", "fclgpu_bvh_get_partition", "fclgpu_model_set_partition",
+    "fclgpu_bvh_refit_bottomup", "fclgpu_bvh_get_rss_axis", "fclgpu_model_refit_bottomup", "fclgpu_model_download_rss_axis",
     "fclgpu_model_refit_topdown", "fclgpu_model_download", "fclgpu_model_build_obbrss", "fclgpu_model_get_topology",
     "fclgpu_collide_mesh_sphere_batch", "fclgpu_collide_mesh_sphere_batch_host",
     "fclgpu_distance_mesh_sphere_batch", "fclgpu_distance_mesh_sphere_batch_host",
@@ -94,6 +95,10 @@ def lib():
     L.fclgpu_model_set_partition.argtypes = [vp, C.c_int32, vp, vp, vp, vp]
     L.fclgpu_model_refit_topdown.argtypes = [vp, vp, C.c_int32, C.c_int32, vp]
     L.fclgpu_model_download.argtypes = [vp] * 8
+    L.fclgpu_bvh_refit_bottomup.argtypes = [vp, vp, C.c_int32]
+    L.fclgpu_bvh_get_rss_axis.argtypes = [vp, vp]
+    L.fclgpu_model_refit_bottomup.argtypes = [vp, vp, C.c_int32, C.c_int32, vp]
+    L.fclgpu_model_download_rss_axis.argtypes = [vp, vp]
     L.fclgpu_model_build_obbrss.argtypes = [C.c_int, vp, C.c_int32, vp, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
     L.fclgpu_model_get_topology.argtypes = [vp] * 5
     L.fclgpu_model_create_obbrss.argtypes = [C.c_int, C.c_int32, vp, vp, vp, vp, vp, vp, vp, C.c_int32, vp,

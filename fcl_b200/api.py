@@ -235,9 +235,11 @@ class BVHModel:
         return self.replaceSubModel(np.array([p1, p2, p3], dtype=np.float64))
 
     def endReplaceModel(self, refit=True, bottomup=True):
-        """refit=True, bottomup=False: top-down refit (refitTree_topdown) on the host copy AND, by a kernel,
-        on every uploaded device copy (bit-identical BVs).  refit=False: rebuild the tree (buildTree) and
-        re-upload.  The bottom-up refit (fit3 + BV merging, BVH_model-inl.h:961-1037) is not on this path."""
+        """refit=True, bottomup=True (the reference's default, BVH_model.h:128): bottom-up refit (refitTree_bottomup,
+        BVH_model-inl.h:952-1037: triangle fit at the leaves, OBB / RSS merging above) on the host copy AND, by a kernel,
+        on every uploaded device copy (bit-identical BVs, the reference's merge quirks included).
+        refit=True, bottomup=False: top-down refit (refitTree_topdown), likewise.
+        refit=False: rebuild the tree (buildTree) and re-upload."""
         if self.build_state != BVH_BUILD_STATE_REPLACE_BEGUN:
             sys.stderr.write("BVH Warning! Call endReplaceModel() in a wrong order. endReplaceModel() was ignored. \n")
             return BVH_ERR_BUILD_OUT_OF_SEQUENCE
@@ -245,22 +247,22 @@ class BVHModel:
             sys.stderr.write("BVH Error! The replaced model should have the same number of vertices as the old model.\n")
             return BVH_ERR_INCORRECT_DATA
         new_v = np.ascontiguousarray(np.concatenate(self._replace), dtype=np.float64)
-        if refit and bottomup:
-            sys.stderr.write("BVH Error! bottom-up refit is not supported on the OBBRSS mesh-mesh GPU path; use "
-                             "endReplaceModel(True, False) or endReplaceModel(False).\n")
-            return BVH_ERR_UNSUPPORTED_FUNCTION
         self.vertices = new_v
         L = _capi.lib()
         if refit:
+            host_refit = L.fclgpu_bvh_refit_bottomup if bottomup else L.fclgpu_bvh_refit_topdown
+            dev_refit = L.fclgpu_model_refit_bottomup if bottomup else L.fclgpu_model_refit_topdown
             if self._bvh is not None:
-                rc = L.fclgpu_bvh_refit_topdown(self._bvh, addr(new_v), self.num_vertices)
+                rc = host_refit(self._bvh, addr(new_v), self.num_vertices)
                 if rc != 0:
                     return rc
             for dev, h in self._dev.items():
-                check(L.fclgpu_model_refit_topdown(h, addr(new_v), self.num_vertices, 0, None))
+                check(dev_refit(h, addr(new_v), self.num_vertices, 0, None))
                 check(L.fclgpu_sync_status(int(dev), None))
+            self._bottomup = bool(bottomup)
         else:
             self._release()
+            self._bottomup = False
             if not self.build_on_device:
                 h = C.c_void_p()
                 rc = L.fclgpu_bvh_build_obbrss(addr(self.vertices), self.num_vertices, addr(self.tri_indices),
@@ -271,13 +273,15 @@ class BVHModel:
         self.build_state = BVH_BUILD_STATE_PROCESSED
         return BVH_OK
 
-    def refit_device(self, vertices, device=None, stream=None):
+    def refit_device(self, vertices, device=None, stream=None, bottomup=False):
         """Device-resident update: `vertices` is a CUDA float64 tensor (num_vertices, 3); only the device copy
         on that GPU is refitted (asynchronous on `stream`); the host copy is left untouched."""
         torch = _torch()
         dev = vertices.device.index if device is None else device
         st = (stream or torch.cuda.current_stream(dev)).cuda_stream
-        check(_capi.lib().fclgpu_model_refit_topdown(self.device_model(dev), addr(vertices), self.num_vertices, 1, st))
+        L = _capi.lib()
+        fn = L.fclgpu_model_refit_bottomup if bottomup else L.fclgpu_model_refit_topdown
+        check(fn(self.device_model(dev), addr(vertices), self.num_vertices, 1, st))
 
     def download_device_arrays(self, device=None):
         """FP64 node records as they currently are in HBM (for tests / inspection)."""
@@ -288,6 +292,8 @@ class BVHModel:
         check(_capi.lib().fclgpu_model_download(h, addr(out["axis"]), addr(out["obb_To"]), addr(out["obb_ext"]),
                                                 addr(out["rss_To"]), addr(out["rss_l"]), addr(out["rss_r"]),
                                                 addr(out["tri_verts"])))
+        out["rss_axis"] = np.empty((n, 9))
+        check(_capi.lib().fclgpu_model_download_rss_axis(h, addr(out["rss_axis"])))
         return out
 
     def partition(self):
@@ -334,6 +340,10 @@ class BVHModel:
         check(_capi.lib().fclgpu_bvh_get(self._bvh, addr(out["first_child"]), addr(out["axis"]), addr(out["obb_To"]),
                                          addr(out["obb_ext"]), addr(out["rss_To"]), addr(out["rss_l"]),
                                          addr(out["rss_r"]), addr(out["tri_verts"])))
+        out["rss_axis"] = np.empty((n, 9))  # = axis unless the model was refitted bottom-up
+        rc = _capi.lib().fclgpu_bvh_get_rss_axis(self._bvh, addr(out["rss_axis"]))
+        if rc < 0:
+            check(rc)
         return out
 
     def device_model(self, device=None):
@@ -349,6 +359,9 @@ class BVHModel:
                 check(_capi.lib().fclgpu_model_build_obbrss(int(device), addr(self.vertices), self.num_vertices,
                                                             addr(self.tri_indices), self.num_tris, self.split_method,
                                                             C.byref(h)))
+                if getattr(self, "_bottomup", False):  # a copy made after a bottom-up refit of a device-built model
+                    check(_capi.lib().fclgpu_model_refit_bottomup(h, addr(self.vertices), self.num_vertices, 0, None))
+                    check(_capi.lib().fclgpu_sync_status(int(device), None))
             else:
                 check(_capi.lib().fclgpu_model_from_bvh(int(device), self._bvh, C.byref(h)))
             self._dev[device] = h

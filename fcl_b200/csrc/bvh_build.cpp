@@ -14,6 +14,7 @@
 // -ffp-contract=off), like the device code.
 #include "bvh_build.hpp"
 #include "bvh_fit.cuh"
+#include "bvh_merge.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -167,6 +168,7 @@ extern "C" int fclgpu_bvh_refit_topdown(fclgpu_bvh* b, const double* vertices, i
   if (!b || !vertices) return FCLGPU_ERR_INVALID_ARGUMENT;
   if (num_vertices != b->num_vertices) return FCLGPU_ERR_INCORRECT_DATA;  // :602-606
   deindex(b, vertices);
+  b->rss_axis.clear();  // FitImpl<OBBRSS>: both volumes share the fitted axes again
   const int nn = 2 * b->num_tris - 1;
   for (int i = 0; i < nn; ++i) {
     NodeFit f;
@@ -174,6 +176,47 @@ extern "C" int fclgpu_bvh_refit_topdown(fclgpu_bvh* b, const double* vertices, i
     store_fit(b, i, f);
   }
   return FCLGPU_OK;
+}
+
+// endReplaceModel(refit = true, bottomup = true), the reference's default (BVH_model-inl.h:952-1037): children before
+// parents, leaves by the closed-form triangle fit, inner nodes by merging the children's volumes (bvh_merge.cuh).
+// Children always have larger ids than their parent (pre-order pair allocation), so one pass from the last node to the
+// first visits every child before its parent.
+extern "C" int fclgpu_bvh_refit_bottomup(fclgpu_bvh* b, const double* vertices, int32_t num_vertices) {
+  if (!b || !vertices) return FCLGPU_ERR_INVALID_ARGUMENT;
+  if (num_vertices != b->num_vertices) return FCLGPU_ERR_INCORRECT_DATA;  // :602-606
+  deindex(b, vertices);
+  const int nn = 2 * b->num_tris - 1;
+  std::vector<fclgpu::NodeBV> bv((size_t)nn);
+  for (int i = nn - 1; i >= 0; --i) {
+    const int fc = b->first_child[i];
+    if (fc < 0) fclgpu::fit3_obbrss(&b->tri_verts[9 * (size_t)(-(fc + 1))], bv[i]);
+    else fclgpu::merge_obbrss(bv[fc], bv[fc + 1], bv[i]);
+  }
+  b->rss_axis.resize(9 * (size_t)nn);
+  for (int i = 0; i < nn; ++i) {
+    const fclgpu::NodeBV& f = bv[i];
+    std::memcpy(&b->axis[9 * (size_t)i], f.axis, sizeof f.axis);
+    std::memcpy(&b->rss_axis[9 * (size_t)i], f.rss_axis, sizeof f.rss_axis);
+    for (int k = 0; k < 3; ++k) {
+      b->obb_To[3 * (size_t)i + k] = f.obb_To[k];
+      b->obb_ext[3 * (size_t)i + k] = f.obb_ext[k];
+      b->rss_To[3 * (size_t)i + k] = f.rss_To[k];
+    }
+    b->rss_l[2 * (size_t)i] = f.rss_l[0];
+    b->rss_l[2 * (size_t)i + 1] = f.rss_l[1];
+    b->rss_r[i] = f.rss_r;
+  }
+  return FCLGPU_OK;
+}
+
+// rss.axis per node (9 doubles, row-major); returns 1 when the model has separate RSS axes (after a bottom-up refit),
+// 0 when the RSS shares the OBB's axes (rss_axis9 is then filled with those)
+extern "C" int fclgpu_bvh_get_rss_axis(const fclgpu_bvh* b, double* rss_axis9) {
+  if (!b) return FCLGPU_ERR_INVALID_ARGUMENT;
+  const std::vector<double>& src = b->rss_axis.empty() ? b->axis : b->rss_axis;
+  if (rss_axis9) std::memcpy(rss_axis9, src.data(), src.size() * sizeof(double));
+  return b->rss_axis.empty() ? 0 : 1;
 }
 
 extern "C" int fclgpu_bvh_get_partition(const fclgpu_bvh* b, int32_t* first_primitive, int32_t* num_primitives,

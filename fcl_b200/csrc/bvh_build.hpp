@@ -11,6 +11,7 @@ struct fclgpu_bvh {
   std::vector<double> obb_To, obb_ext, rss_To;  // 3 per node
   std::vector<double> rss_l;         // 2 per node
   std::vector<double> rss_r;         // 1 per node
+  std::vector<double> rss_axis;      // 9 per node after a bottom-up refit (the RSS no longer shares the OBB's axes); else empty
   std::vector<double> tri_verts;     // 9 per triangle (de-indexed)
   // what a top-down refit needs (BVHModel::primitive_indices, BVNodeBase::first_primitive / num_primitives)
   std::vector<int32_t> tri_index;        // 3 per triangle (vertex ids)

@@ -92,72 +92,44 @@ __host__ __device__ inline void jacobi3(const double M[3][3], double d[3], doubl
   }
 }
 
-// tv: de-indexed triangle vertices, 9 doubles per triangle with stride `tri_stride` doubles.
-// idx[0..n): the node's primitives in the order the sums must run.
-__host__ __device__ inline void fit_obbrss(const double* tv, int tri_stride, const uint32_t* idx, int n, NodeFit& f) {
-  // --- covariance of the 3n vertices ---
-  double S1[3] = {0, 0, 0}, S2[6] = {0, 0, 0, 0, 0, 0};  // xx yy zz xy xz yz
-  for (int i = 0; i < n; ++i) {
-    const double* p1 = tv + (size_t)idx[i] * tri_stride;
-    const double* p2 = p1 + 3;
-    const double* p3 = p1 + 6;
-    for (int k = 0; k < 3; ++k) S1[k] += ((p1[k] + p2[k]) + p3[k]);
-    S2[0] += (p1[0] * p1[0] + p2[0] * p2[0] + p3[0] * p3[0]);
-    S2[1] += (p1[1] * p1[1] + p2[1] * p2[1] + p3[1] * p3[1]);
-    S2[2] += (p1[2] * p1[2] + p2[2] * p2[2] + p3[2] * p3[2]);
-    S2[3] += (p1[0] * p1[1] + p2[0] * p2[1] + p3[0] * p3[1]);
-    S2[4] += (p1[0] * p1[2] + p2[0] * p2[2] + p3[0] * p3[2]);
-    S2[5] += (p1[1] * p1[2] + p2[1] * p2[2] + p3[1] * p3[2]);
-  }
-  const int np = 3 * n;
-  f.vsum[0] = S1[0];
-  f.vsum[1] = S1[1];
-  f.vsum[2] = S1[2];
-  double M[3][3];
-  M[0][0] = S2[0] - S1[0] * S1[0] / np;
-  M[1][1] = S2[1] - S1[1] * S1[1] / np;
-  M[2][2] = S2[2] - S1[2] * S1[2] / np;
-  M[0][1] = M[1][0] = S2[3] - S1[0] * S1[1] / np;
-  M[1][2] = M[2][1] = S2[5] - S1[1] * S1[2] / np;
-  M[0][2] = M[2][0] = S2[4] - S1[0] * S1[2] / np;
-
-  // --- principal axes: largest, middle eigenvector, then their cross product ---
-  double ev[3], V[3][3];
-  jacobi3(M, ev, V);
-  int lo, mid, hi;
-  if (ev[0] > ev[1]) { hi = 0; lo = 1; } else { lo = 0; hi = 1; }
-  if (ev[2] < ev[lo]) { mid = lo; lo = 2; }
-  else if (ev[2] > ev[hi]) { mid = hi; hi = 2; }
-  else mid = 2;
-  double* A = f.axis;
-  for (int r = 0; r < 3; ++r) {
-    A[3 * r + 0] = V[r][hi];
-    A[3 * r + 1] = V[r][mid];
-  }
-  A[2] = A[3] * A[7] - A[6] * A[4];
-  A[5] = A[6] * A[1] - A[0] * A[7];
-  A[8] = A[0] * A[4] - A[3] * A[1];
+// Centre and half extents of the box with the given axes around m points (getExtentAndCenter_mesh /
+// _pointcloud: identical arithmetic once the points are enumerated in the same order).  pt(j) -> pointer to 3 doubles.
+template <class PointOf>
+__host__ __device__ inline void extent_center_from_points(PointOf pt, int m, const double* A, double To[3], double ext[3]) {
   const double a00 = A[0], a10 = A[3], a20 = A[6], a01 = A[1], a11 = A[4], a21 = A[7], a02 = A[2], a12 = A[5], a22 = A[8];
-
-  const int m = 3 * n;
-  // projection of point j (vertex j%3 of the node's (j/3)-th primitive) on box axis c
-#define FCLGPU_PT(j) (tv + (size_t)idx[(j) / 3] * tri_stride + 3 * ((j) % 3))
-#define FCLGPU_PX(p) ((a00 * (p)[0] + a10 * (p)[1]) + a20 * (p)[2])
-#define FCLGPU_PY(p) ((a01 * (p)[0] + a11 * (p)[1]) + a21 * (p)[2])
-#define FCLGPU_PZ(p) ((a02 * (p)[0] + a12 * (p)[1]) + a22 * (p)[2])
-
-  // --- OBB centre and half extents; RSS thin-direction extent ---
   double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
-  double minz = 0, maxz = 0;
   for (int j = 0; j < m; ++j) {
-    const double* p = FCLGPU_PT(j);
-    const double c0 = FCLGPU_PX(p), c1 = FCLGPU_PY(p), c2 = FCLGPU_PZ(p);
+    const double* p = pt(j);
+    const double c0 = (a00 * p[0] + a10 * p[1]) + a20 * p[2];
+    const double c1 = (a01 * p[0] + a11 * p[1]) + a21 * p[2];
+    const double c2 = (a02 * p[0] + a12 * p[1]) + a22 * p[2];
     if (c0 > mx[0]) mx[0] = c0;
     if (c0 < mn[0]) mn[0] = c0;
     if (c1 > mx[1]) mx[1] = c1;
     if (c1 < mn[1]) mn[1] = c1;
     if (c2 > mx[2]) mx[2] = c2;
     if (c2 < mn[2]) mn[2] = c2;
+  }
+  const double o[3] = {(mx[0] + mn[0]) / 2, (mx[1] + mn[1]) / 2, (mx[2] + mn[2]) / 2};
+  for (int r = 0; r < 3; ++r) {
+    To[r] = (A[3 * r] * o[0] + A[3 * r + 1] * o[1]) + A[3 * r + 2] * o[2];
+    ext[r] = (mx[r] - mn[r]) / 2;
+  }
+}
+
+// Rectangle-swept-sphere with the given axes around m points (getRadiusAndOriginAndRectangleSize after the projections
+// have been gathered, math/geometry-inl.h:782-988): radius from the thin direction, rectangle grown to cover.  The
+// reference keeps the projections in a temporary vector; every pass here recomputes them (same expression, same bits).
+template <class PointOf>
+__host__ __device__ inline void rss_from_points(PointOf pt, int m, const double* A, double To[3], double l[2], double& rad) {
+  const double a00 = A[0], a10 = A[3], a20 = A[6], a01 = A[1], a11 = A[4], a21 = A[7], a02 = A[2], a12 = A[5], a22 = A[8];
+#define FCLGPU_PX(p) ((a00 * (p)[0] + a10 * (p)[1]) + a20 * (p)[2])
+#define FCLGPU_PY(p) ((a01 * (p)[0] + a11 * (p)[1]) + a21 * (p)[2])
+#define FCLGPU_PZ(p) ((a02 * (p)[0] + a12 * (p)[1]) + a22 * (p)[2])
+  double minz = 0, maxz = 0;
+  for (int j = 0; j < m; ++j) {
+    const double* p = pt(j);
+    const double c2 = FCLGPU_PZ(p);
     if (j == 0) {
       minz = maxz = c2;
     } else {
@@ -165,40 +137,32 @@ __host__ __device__ inline void fit_obbrss(const double* tv, int tri_stride, con
       else if (c2 > maxz) maxz = c2;
     }
   }
-  const double o[3] = {(mx[0] + mn[0]) / 2, (mx[1] + mn[1]) / 2, (mx[2] + mn[2]) / 2};
-  for (int r = 0; r < 3; ++r) {
-    f.obb_To[r] = (A[3 * r] * o[0] + A[3 * r + 1] * o[1]) + A[3 * r + 2] * o[2];
-    f.obb_ext[r] = (mx[r] - mn[r]) / 2;
-  }
-
-  // --- RSS: radius from the thin direction, rectangle grown to cover ---
   const double r = 0.5 * (maxz - minz), radsqr = r * r, cz = 0.5 * (maxz + minz);
-#define FCLGPU_REACH(pz) sqrt(fmax(radsqr - ((pz)-cz) * ((pz)-cz), 0.0))
   double lo2[2], hi2[2];
   for (int c = 0; c < 2; ++c) {
     int imin = 0, imax = 0;
     double vmin, vmax;
     {
-      const double* p = FCLGPU_PT(0);
+      const double* p = pt(0);
       vmin = vmax = (c == 0) ? FCLGPU_PX(p) : FCLGPU_PY(p);
     }
     for (int j = 1; j < m; ++j) {
-      const double* p = FCLGPU_PT(j);
+      const double* p = pt(j);
       const double val = (c == 0) ? FCLGPU_PX(p) : FCLGPU_PY(p);
       if (val < vmin) { imin = j; vmin = val; }
       else if (val > vmax) { imax = j; vmax = val; }
     }
     double lo_c, hi_c;
     {
-      const double* p = FCLGPU_PT(imin);
+      const double* p = pt(imin);
       const double dz = FCLGPU_PZ(p) - cz;
       lo_c = ((c == 0) ? FCLGPU_PX(p) : FCLGPU_PY(p)) + sqrt(fmax(radsqr - dz * dz, 0.0));
-      const double* q = FCLGPU_PT(imax);
+      const double* q = pt(imax);
       const double dz2 = FCLGPU_PZ(q) - cz;
       hi_c = ((c == 0) ? FCLGPU_PX(q) : FCLGPU_PY(q)) - sqrt(fmax(radsqr - dz2 * dz2, 0.0));
     }
     for (int j = 0; j < m; ++j) {
-      const double* p = FCLGPU_PT(j);
+      const double* p = pt(j);
       const double val = (c == 0) ? FCLGPU_PX(p) : FCLGPU_PY(p);
       if (val < lo_c) {
         const double dz = FCLGPU_PZ(p) - cz;
@@ -207,7 +171,7 @@ __host__ __device__ inline void fit_obbrss(const double* tv, int tri_stride, con
       }
     }
     for (int j = 0; j < m; ++j) {
-      const double* p = FCLGPU_PT(j);
+      const double* p = pt(j);
       const double val = (c == 0) ? FCLGPU_PX(p) : FCLGPU_PY(p);
       if (val > hi_c) {
         const double dz = FCLGPU_PZ(p) - cz;
@@ -221,7 +185,7 @@ __host__ __device__ inline void fit_obbrss(const double* tv, int tri_stride, con
   double minx = lo2[0], maxx = hi2[0], miny = lo2[1], maxy = hi2[1];
   const double a = sqrt(0.5);
   for (int j = 0; j < m; ++j) {
-    const double* p = FCLGPU_PT(j);
+    const double* p = pt(j);
     const double px = FCLGPU_PX(p), py = FCLGPU_PY(p), pz = FCLGPU_PZ(p);
     double dx, dy, u, t;
     if (px > maxx) {
@@ -254,17 +218,69 @@ __host__ __device__ inline void fit_obbrss(const double* tv, int tri_stride, con
       }
     }
   }
-  for (int k = 0; k < 3; ++k) f.rss_To[k] = (A[3 * k] * minx + A[3 * k + 1] * miny) + A[3 * k + 2] * cz;
-  f.rss_l[0] = maxx - minx;
-  if (f.rss_l[0] < 0) f.rss_l[0] = 0;
-  f.rss_l[1] = maxy - miny;
-  if (f.rss_l[1] < 0) f.rss_l[1] = 0;
-  f.rss_r = r;
-#undef FCLGPU_REACH
-#undef FCLGPU_PT
+  for (int k = 0; k < 3; ++k) To[k] = (A[3 * k] * minx + A[3 * k + 1] * miny) + A[3 * k + 2] * cz;
+  l[0] = maxx - minx;
+  if (l[0] < 0) l[0] = 0;
+  l[1] = maxy - miny;
+  if (l[1] < 0) l[1] = 0;
+  rad = r;
 #undef FCLGPU_PX
 #undef FCLGPU_PY
 #undef FCLGPU_PZ
+}
+
+// principal axes from a covariance matrix: largest, middle eigenvector (eigen_old + axisFromEigen), then their cross
+// product.  A row-major, column c = c-th axis.
+__host__ __device__ inline void axes_from_covariance(const double M[3][3], double* A) {
+  double ev[3], V[3][3];
+  jacobi3(M, ev, V);
+  int lo, mid, hi;
+  if (ev[0] > ev[1]) { hi = 0; lo = 1; } else { lo = 0; hi = 1; }
+  if (ev[2] < ev[lo]) { mid = lo; lo = 2; }
+  else if (ev[2] > ev[hi]) { mid = hi; hi = 2; }
+  else mid = 2;
+  for (int r = 0; r < 3; ++r) {
+    A[3 * r + 0] = V[r][hi];
+    A[3 * r + 1] = V[r][mid];
+  }
+  A[2] = A[3] * A[7] - A[6] * A[4];
+  A[5] = A[6] * A[1] - A[0] * A[7];
+  A[8] = A[0] * A[4] - A[3] * A[1];
+}
+
+// tv: de-indexed triangle vertices, 9 doubles per triangle with stride `tri_stride` doubles.
+// idx[0..n): the node's primitives in the order the sums must run.
+__host__ __device__ inline void fit_obbrss(const double* tv, int tri_stride, const uint32_t* idx, int n, NodeFit& f) {
+  // --- covariance of the 3n vertices ---
+  double S1[3] = {0, 0, 0}, S2[6] = {0, 0, 0, 0, 0, 0};  // xx yy zz xy xz yz
+  for (int i = 0; i < n; ++i) {
+    const double* p1 = tv + (size_t)idx[i] * tri_stride;
+    const double* p2 = p1 + 3;
+    const double* p3 = p1 + 6;
+    for (int k = 0; k < 3; ++k) S1[k] += ((p1[k] + p2[k]) + p3[k]);
+    S2[0] += (p1[0] * p1[0] + p2[0] * p2[0] + p3[0] * p3[0]);
+    S2[1] += (p1[1] * p1[1] + p2[1] * p2[1] + p3[1] * p3[1]);
+    S2[2] += (p1[2] * p1[2] + p2[2] * p2[2] + p3[2] * p3[2]);
+    S2[3] += (p1[0] * p1[1] + p2[0] * p2[1] + p3[0] * p3[1]);
+    S2[4] += (p1[0] * p1[2] + p2[0] * p2[2] + p3[0] * p3[2]);
+    S2[5] += (p1[1] * p1[2] + p2[1] * p2[2] + p3[1] * p3[2]);
+  }
+  const int np = 3 * n;
+  f.vsum[0] = S1[0];
+  f.vsum[1] = S1[1];
+  f.vsum[2] = S1[2];
+  double M[3][3];
+  M[0][0] = S2[0] - S1[0] * S1[0] / np;
+  M[1][1] = S2[1] - S1[1] * S1[1] / np;
+  M[2][2] = S2[2] - S1[2] * S1[2] / np;
+  M[0][1] = M[1][0] = S2[3] - S1[0] * S1[1] / np;
+  M[1][2] = M[2][1] = S2[5] - S1[1] * S1[2] / np;
+  M[0][2] = M[2][0] = S2[4] - S1[0] * S1[2] / np;
+  axes_from_covariance(M, f.axis);
+  // point j = vertex j % 3 of the node's (j / 3)-th primitive
+  auto pt = [&](int j) { return tv + (size_t)idx[j / 3] * tri_stride + 3 * (j % 3); };
+  extent_center_from_points(pt, 3 * n, f.axis, f.obb_To, f.obb_ext);
+  rss_from_points(pt, 3 * n, f.axis, f.rss_To, f.rss_l, f.rss_r);
 }
 
 }  // namespace fclgpu

@@ -233,6 +233,9 @@ struct fclgpu_model {
   double* vert_stage = nullptr;
   int32_t* fc;
   int depth;
+  // bottom-up refit schedule (built on first use): node ids grouped by tree height, leaves first
+  int32_t* by_height = nullptr;
+  std::vector<int32_t> height_start;  // group h = by_height[height_start[h] .. height_start[h + 1])
   LocalAabb aabb;  // BVHModel::computeLocalAABB over the vertices the triangles reference
 };
 
@@ -457,8 +460,10 @@ extern "C" int fclgpu_model_from_bvh(int device, const fclgpu_bvh* bvh, fclgpu_m
   std::vector<double> axis(9 * (size_t)nn), oT(3 * (size_t)nn), oe(3 * (size_t)nn), rT(3 * (size_t)nn), rl(2 * (size_t)nn),
       rr(nn), tv(9 * (size_t)nt);
   fclgpu_bvh_get(bvh, fc.data(), axis.data(), oT.data(), oe.data(), rT.data(), rl.data(), rr.data(), tv.data());
-  int rc = fclgpu_model_create_obbrss(device, nn, fc.data(), axis.data(), oT.data(), oe.data(), rT.data(), rl.data(),
-                                      rr.data(), nt, tv.data(), out);
+  std::vector<double> raxis(9 * (size_t)nn);
+  const bool separate = fclgpu_bvh_get_rss_axis(bvh, raxis.data()) == 1;  // host model refitted bottom-up
+  int rc = fclgpu_model_create_obbrss2(device, nn, fc.data(), axis.data(), oT.data(), oe.data(), separate ? raxis.data() : nullptr,
+                                       rT.data(), rl.data(), rr.data(), nt, tv.data(), out);
   if (rc) return rc;
   std::vector<int32_t> nf(nn), nc(nn), po(nt), ti(3 * (size_t)nt);
   fclgpu_bvh_get_partition(bvh, nf.data(), nc.data(), po.data(), ti.data());
@@ -498,6 +503,65 @@ extern "C" int fclgpu_model_refit_topdown(fclgpu_model* m, const double* vertice
     g_launches += 2;
   }
   CUDA_TRY(cudaGetLastError());
+  return FCLGPU_OK;
+}
+
+// On-device bottom-up refit: BVHModel::endReplaceModel(refit = true, bottomup = true), the reference's default
+// (BVH_model-inl.h:952-1037).  One launch per tree height (refit.cuh), the same merge routines as the host model.
+extern "C" int fclgpu_model_refit_bottomup(fclgpu_model* m, const double* vertices, int32_t num_vertices,
+                                           int32_t vertices_on_device, void* stream) {
+  if (!m || !vertices) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL model/vertices");
+  if (!m->tri_index) return fail(FCLGPU_ERR_UNSUPPORTED_FUNCTION, "model has no refit topology (fclgpu_model_set_partition)");
+  if (num_vertices != m->num_vertices)  // BVH_model-inl.h:602-606
+    return fail(FCLGPU_ERR_INCORRECT_DATA, "the replaced model must have the same number of vertices (%d != %d)", num_vertices, m->num_vertices);
+  CUDA_TRY(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nn = m->d.n_nodes;
+  if (!m->by_height) {
+    // height of a node = 1 + max height of its children; children have larger ids than their parent
+    std::vector<int32_t> fc(nn), height(nn), ids(nn);
+    CUDA_TRY(cudaMemcpy(fc.data(), m->fc, sizeof(int32_t) * nn, cudaMemcpyDeviceToHost));
+    int hmax = 0;
+    for (int i = nn - 1; i >= 0; --i) {
+      height[i] = fc[i] < 0 ? 0 : 1 + std::max(height[fc[i]], height[fc[i] + 1]);
+      hmax = std::max(hmax, height[i]);
+    }
+    m->height_start.assign(hmax + 2, 0);
+    for (int i = 0; i < nn; ++i) m->height_start[height[i] + 1]++;
+    for (int h = 0; h <= hmax; ++h) m->height_start[h + 1] += m->height_start[h];
+    std::vector<int32_t> cur(m->height_start.begin(), m->height_start.end() - 1);
+    for (int i = 0; i < nn; ++i) ids[cur[height[i]]++] = i;
+    CUDA_TRY(cudaMalloc((void**)&m->by_height, sizeof(int32_t) * nn));
+    CUDA_TRY(cudaMemcpy(m->by_height, ids.data(), sizeof(int32_t) * nn, cudaMemcpyHostToDevice));
+  }
+  const double* dv = vertices;
+  if (!vertices_on_device) {
+    CUDA_TRY(cudaMemcpyAsync(m->vert_stage, vertices, 3 * (size_t)num_vertices * sizeof(double), cudaMemcpyHostToDevice, st));
+    dv = m->vert_stage;
+  }
+  RefitParams P{m->obb, m->rss, m->tri, m->rss32, m->obb32, m->topo, m->tri_index, m->node_first, m->node_count,
+                m->prim_order, m->by_size, m->d.n_nodes, m->d.n_tris};
+  gather_tris_kernel<<<(P.n_tris + 255) / 256, 256, 0, st>>>(P, dv);
+  const int levels = (int)m->height_start.size() - 1;
+  for (int h = 0; h < levels; ++h) {
+    const int first = m->height_start[h], count = m->height_start[h + 1] - first;
+    refit_bottomup_level_kernel<<<(count + 63) / 64, 64, 0, st>>>(P, m->fc, m->by_height + first, count);
+  }
+  g_launches += 1 + levels;
+  CUDA_TRY(cudaGetLastError());
+  return FCLGPU_OK;
+}
+
+// rss.axis of every node as it is in HBM (equal to the OBB's axes unless the model was refitted bottom-up)
+extern "C" int fclgpu_model_download_rss_axis(const fclgpu_model* m, double* rss_axis9) {
+  if (!m || !rss_axis9) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL model/array");
+  CUDA_TRY(cudaSetDevice(m->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  const int nn = m->d.n_nodes;
+  std::vector<double> rss((size_t)nn * kNodeDoubles);
+  CUDA_TRY(cudaMemcpy(rss.data(), m->rss, rss.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < nn; ++i)
+    for (int k = 0; k < 9; ++k) rss_axis9[9 * (size_t)i + k] = rss[(size_t)i * kNodeDoubles + k];
   return FCLGPU_OK;
 }
 
@@ -674,6 +738,7 @@ extern "C" int fclgpu_model_destroy(fclgpu_model* m) {
   cudaFree(m->node_first);
   cudaFree(m->node_count);
   cudaFree(m->by_size);
+  cudaFree(m->by_height);
   cudaFree(m->prim_order);
   cudaFree(m->vert_stage);
   delete m;

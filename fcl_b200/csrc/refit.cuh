@@ -14,6 +14,7 @@
 // times faster than the host refit and needs no PCIe round trip.
 #pragma once
 #include "bvh_fit.cuh"
+#include "bvh_merge.cuh"
 #include "records.hpp"
 #include "traversal.cuh"
 
@@ -615,6 +616,79 @@ __device__ __forceinline__ void store_node_records(const RefitParams& P, int nod
   double2 t = P.topo[node];
   t.y = size;
   P.topo[node] = t;
+}
+
+// ---------------------------------------------------------------------------------------
+// Bottom-up refit (the reference's default endReplaceModel(), BVH_model-inl.h:952-1037): one launch per tree HEIGHT.
+// ids[] lists the nodes of one height (0 = leaves: closed-form triangle fit; h > 0: merge of the two children, both of
+// smaller height and therefore finished by an earlier launch on the same stream), one thread per node running the very
+// routines of bvh_merge.cuh the host model runs.  OBB and RSS get their own axes from here on.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_node_bv(const RefitParams& P, int node, NodeBV& f) {
+  const double* o = P.obb + (size_t)node * kNodeDoubles;
+  const double* r = P.rss + (size_t)node * kNodeDoubles;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    f.axis[i] = o[i];
+    f.rss_axis[i] = r[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    f.obb_To[i] = o[9 + i];
+    f.obb_ext[i] = o[12 + i];
+    f.rss_To[i] = r[9 + i];
+  }
+  f.rss_l[0] = r[12];
+  f.rss_l[1] = r[13];
+  f.rss_r = r[14];
+}
+
+__device__ __forceinline__ void store_node_bv(const RefitParams& P, int node, const NodeBV& f) {
+  double* o = P.obb + (size_t)node * kNodeDoubles;
+  double* r = P.rss + (size_t)node * kNodeDoubles;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    o[i] = f.axis[i];
+    r[i] = f.rss_axis[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    o[9 + i] = f.obb_To[i];
+    o[12 + i] = f.obb_ext[i];
+    r[9 + i] = f.rss_To[i];
+  }
+  r[12] = f.rss_l[0];
+  r[13] = f.rss_l[1];
+  r[14] = f.rss_r;
+  const double size = (f.obb_ext[0] * f.obb_ext[0] + f.obb_ext[1] * f.obb_ext[1]) + f.obb_ext[2] * f.obb_ext[2];
+  o[15] = r[15] = size;
+  RssRec32 r32;
+  pack_rss32(f.rss_axis, f.rss_To, f.rss_l, f.rss_r, r32);
+  P.rss32[node] = r32;
+  ObbRec32 o32;
+  pack_obb32(f.axis, f.obb_To, f.obb_ext, o32);
+  P.obb32[node] = o32;
+  double2 t = P.topo[node];
+  t.y = size;
+  P.topo[node] = t;
+}
+
+__global__ void __launch_bounds__(64) refit_bottomup_level_kernel(RefitParams P, const int32_t* __restrict__ first_child,
+                                                                  const int32_t* __restrict__ ids, int count) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const int node = ids[k];
+  const int fc = first_child[node];
+  NodeBV f;
+  if (fc < 0) {
+    fit3_obbrss(P.tri + (size_t)(-(fc + 1)) * kTriDoubles, f);
+  } else {
+    NodeBV a, b;
+    load_node_bv(P, fc, a);
+    load_node_bv(P, fc + 1, b);
+    merge_obbrss(a, b, f);
+  }
+  store_node_bv(P, node, f);
 }
 
 // one warp per node for the next largest nodes (by_size[n_huge .. n_big))

@@ -119,6 +119,17 @@ int fclgpu_bvh_get(const fclgpu_bvh* bvh, int32_t* first_child, double* axis9, d
  * refit = true, bottomup = false) (BVH_model-inl.h:521-620, refitTree_topdown :1064-1076): new vertex
  * positions (same count), same tree, every BV refitted over its stored primitive range. */
 int fclgpu_bvh_refit_topdown(fclgpu_bvh* bvh, const double* vertices, int32_t num_vertices);
+/* Bottom-up refit on the host: endReplaceModel(refit = true, bottomup = true), the reference's DEFAULT
+ * (BVH_model.h:128, BVH_model-inl.h:952-1037): a leaf gets the closed-form fit of its triangle (fit3,
+ * math/bv/utility-inl.h:92-117, 208-230), an inner node the merge of its children's volumes (OBB::operator+,
+ * OBB-inl.h:161-369; RSS::operator+, RSS-inl.h:313-371).  The reference's quirks are kept bit for bit (the `else if`
+ * of merge_smalldist, the transposed eigenvector matrix and the stale third axis of RSS::operator+), so -- as in
+ * the reference -- a volume refitted this way need not contain its subtree.  Afterwards the RSS of a node no longer
+ * shares the OBB's axes (fclgpu_bvh_get_rss_axis). */
+int fclgpu_bvh_refit_bottomup(fclgpu_bvh* bvh, const double* vertices, int32_t num_vertices);
+/* rss.axis per node (row-major 9).  Returns 1 when they are separate from the OBB's (after a bottom-up refit), 0 when
+ * shared (the array then receives the OBB's axes); < 0 on error. */
+int fclgpu_bvh_get_rss_axis(const fclgpu_bvh* bvh, double* rss_axis9);
 int32_t fclgpu_bvh_num_vertices(const fclgpu_bvh* bvh);
 /* BVNodeBase::first_primitive / num_primitives per node, BVHModel::primitive_indices, tri_indices
  * (any pointer may be NULL). */
@@ -178,6 +189,13 @@ int fclgpu_model_set_partition(fclgpu_model* m, int32_t num_vertices, const int3
  * vertices_on_device != 0, else a host pointer.  Asynchronous on `stream`. */
 int fclgpu_model_refit_topdown(fclgpu_model* m, const double* vertices, int32_t num_vertices,
                                int32_t vertices_on_device, void* stream);
+/* On-device bottom-up refit: same semantics and bits as fclgpu_bvh_refit_bottomup, one launch per tree height (every
+ * node of a height in parallel).  Needs the triangle indices (fclgpu_model_set_partition / fclgpu_model_from_bvh /
+ * fclgpu_model_build_obbrss).  Asynchronous on `stream`. */
+int fclgpu_model_refit_bottomup(fclgpu_model* m, const double* vertices, int32_t num_vertices,
+                                int32_t vertices_on_device, void* stream);
+/* rss.axis of every node as stored in HBM (row-major 9 per node). */
+int fclgpu_model_download_rss_axis(const fclgpu_model* m, double* rss_axis9);
 /* Copies the FP64 node records back to the host (testing / inspection; any pointer may be NULL). */
 int fclgpu_model_download(const fclgpu_model* m, double* axis9, double* obb_To3, double* obb_extent3,
                           double* rss_To3, double* rss_l2, double* rss_r, double* tri_verts9);

@@ -52,7 +52,8 @@ struct Node {
   int first_child;      // <0 => leaf holding primitive -(first_child+1)
   int first_primitive;  // build bookkeeping
   int num_primitives;
-  Mat3 axis;            // shared by obb and rss (BV_fitter-inl.h:464)
+  Mat3 axis;            // obb.axis; also rss.axis after endModel() / a top-down refit (BV_fitter-inl.h:464)
+  Mat3 rss_axis;        // rss.axis: differs from `axis` only after a bottom-up refit (OBBRSS-inl.h:95-101 merges separately)
   Vec3 obb_To, obb_ext;
   Vec3 rss_To;
   double rss_l[2], rss_r;
@@ -98,6 +99,13 @@ void build_model(Model& m, const std::vector<Vec3>& pts, const std::vector<Tri>&
 // endReplaceModel(refit=true, bottomup=false): new vertex positions, same topology; every node is
 // refitted over its stored primitive range (BVH_model-inl.h:594-620, refitTree_topdown :1064-1076)
 void refit_topdown(Model& m, const std::vector<Vec3>& new_verts);
+// endReplaceModel(refit=true, bottomup=true) -- the reference's default: leaves get the closed-form fit of their
+// triangle (fit3), inner nodes the merge of their children's volumes (BVH_model-inl.h:952-1037, OBB-inl.h:161-357,
+// RSS-inl.h:313-371).  OBB and RSS are merged separately, so the two no longer share axes.
+void refit_bottomup(Model& m, const std::vector<Vec3>& new_verts);
+// the two merges on their own (tests): out.{axis, obb_To, obb_ext} = a.obb + b.obb, out.{rss_*} = a.rss + b.rss
+void merge_obbrss(const Node& a, const Node& b, Node& out);
+void fit3_obbrss(const Vec3 ps[3], Node& out);
 
 // ---- BV / leaf kernels -------------------------------------------------------
 bool obb_disjoint(const Mat3& B, const Vec3& T, const Vec3& a, const Vec3& b);

@@ -206,6 +206,13 @@ struct Builder {
         id++;
       }
     }
+    rss_from_projections(P, axis, origin, l, r);
+  }
+
+  // the part of getRadiusAndOriginAndRectangleSize after the projections P have been gathered (:782-988); the point
+  // branch (:757-779) builds P from plain points and continues the same way
+  static void rss_from_projections(const std::vector<Vec3>& P, const Mat3& axis, Vec3& origin, double l[2], double& r) {
+    const int size_P = (int)P.size();
     double minx, maxx, miny, maxy, minz, maxz, cz, radsqr;
     minz = maxz = P[0][2];
     for (int i = 1; i < size_P; ++i) {
@@ -291,6 +298,7 @@ struct Builder {
     covariance(idx, n, M);
     jacobi(M, s, E);
     axis_from_eigen(E, s, nd.axis);
+    nd.rss_axis = nd.axis;  // bv.rss.axis = bv.obb.axis (BV_fitter-inl.h:464)
     extent_and_center(idx, n, nd.axis, nd.obb_To, nd.obb_ext);
     rss_fit(idx, n, nd.axis, nd.rss_To, nd.rss_l, nd.rss_r);
   }
@@ -405,6 +413,7 @@ void sphere_obb_impl(double radius, const Pose& tf, Node& bv) {
   double sv[3], E[3][3];
   Builder::jacobi(M, sv, E);
   Builder::axis_from_eigen(E, sv, bv.axis);
+  bv.rss_axis = bv.axis;
   const double real_max = std::numeric_limits<double>::max();
   double mn[3] = {real_max, real_max, real_max}, mx[3] = {-real_max, -real_max, -real_max};
   for (int i = 0; i < 12; ++i)
@@ -456,6 +465,319 @@ void refit_topdown(Model& m, const std::vector<Vec3>& new_verts) {
   for (size_t i = 0; i < m.nodes.size(); ++i) {
     Node& nd = m.nodes[i];
     b.fit(b.prim.data() + nd.first_primitive, nd.num_primitives, nd);
+  }
+}
+
+// -----------------------------------------------------------------------------
+// Bottom-up refit — BVHModel::refitTree_bottomup / recursiveRefitTree_bottomup, BVH_model-inl.h:952-1037.
+// prev_vertices == nullptr after beginReplaceModel (:530-534), so a leaf is fit(v, 3, bv) = fit3 and an inner node is
+// bvs[left].bv + bvs[right].bv, children first.
+//
+// Eigen pieces restated from Eigen 3.3's published algorithms (Eigen itself is not on this image; the 4-term quaternion
+// sums are evaluated left to right in coefficient order x, y, z, w -- same "association order unpinned" caveat as
+// fcl_oracle_vec.hpp):
+//   Vector3::normalize()            z = squaredNorm(); if (z > 0) v /= sqrt(z)          (Core/Dot.h)
+//   Quaternion(Matrix3)             trace branch / largest-diagonal branch              (Geometry/Quaternion.h)
+//   Quaternion::toRotationMatrix()  tx = 2x ... res(0,0) = 1 - (tyy + tzz) ...          (Geometry/Quaternion.h)
+// -----------------------------------------------------------------------------
+namespace {
+
+inline void normalize_in_place(Vec3& v) {
+  const double z = sqnorm(v);
+  if (z > 0) {
+    const double n = std::sqrt(z);
+    v = Vec3{{v[0] / n, v[1] / n, v[2] / n}};
+  }
+}
+inline void set_col(Mat3& A, int j, const Vec3& v) {
+  for (int r = 0; r < 3; ++r) A.m[r][j] = v[r];
+}
+
+// getCovariance, point branch without indices — math/geometry-inl.h:1383-1425
+void covariance_points(const Vec3* ps, int n, double M[3][3]) {
+  double S1[3] = {0, 0, 0}, S2[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int i = 0; i < n; ++i) {
+    const Vec3& p = ps[i];
+    for (int k = 0; k < 3; ++k) S1[k] += p[k];
+    S2[0][0] += (p[0] * p[0]);
+    S2[1][1] += (p[1] * p[1]);
+    S2[2][2] += (p[2] * p[2]);
+    S2[0][1] += (p[0] * p[1]);
+    S2[0][2] += (p[0] * p[2]);
+    S2[1][2] += (p[1] * p[2]);
+  }
+  const int n_points = n;
+  M[0][0] = S2[0][0] - S1[0] * S1[0] / n_points;
+  M[1][1] = S2[1][1] - S1[1] * S1[1] / n_points;
+  M[2][2] = S2[2][2] - S1[2] * S1[2] / n_points;
+  M[0][1] = S2[0][1] - S1[0] * S1[1] / n_points;
+  M[1][2] = S2[1][2] - S1[1] * S1[2] / n_points;
+  M[0][2] = S2[0][2] - S1[0] * S1[2] / n_points;
+  M[1][0] = M[0][1];
+  M[2][0] = M[0][2];
+  M[2][1] = M[1][2];
+}
+
+// getExtentAndCenter_pointcloud without indices / second frame — math/geometry-inl.h:229-292
+void extent_and_center_points(const Vec3* ps, int n, const Mat3& axis, Vec3& center, Vec3& extent) {
+  const double real_max = std::numeric_limits<double>::max();
+  double mn[3] = {real_max, real_max, real_max}, mx[3] = {-real_max, -real_max, -real_max};
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < 3; ++k) {
+      const double proj = dot(col(axis, k), ps[i]);
+      if (proj > mx[k]) mx[k] = proj;
+      if (proj < mn[k]) mn[k] = proj;
+    }
+  const Vec3 o{{(mx[0] + mn[0]) / 2, (mx[1] + mn[1]) / 2, (mx[2] + mn[2]) / 2}};
+  center = mul(axis, o);
+  extent = Vec3{{(mx[0] - mn[0]) * 0.5, (mx[1] - mn[1]) * 0.5, (mx[2] - mn[2]) * 0.5}};
+}
+
+// getRadiusAndOriginAndRectangleSize, point branch — math/geometry-inl.h:757-779, then :782-988
+void rss_fit_points(const Vec3* ps, int n, const Mat3& axis, Vec3& origin, double l[2], double& r) {
+  std::vector<Vec3> P(n);
+  for (int i = 0; i < n; ++i) {
+    P[i][0] = dot(col(axis, 0), ps[i]);
+    P[i][1] = dot(col(axis, 1), ps[i]);
+    P[i][2] = dot(col(axis, 2), ps[i]);
+  }
+  Builder::rss_from_projections(P, axis, origin, l, r);
+}
+
+// eigenvalue order of axisFromEigen / merge_largedist / RSS::operator+ (same if-chain in all three)
+inline void order3(const double s[3], int& mn, int& mid, int& mx) {
+  if (s[0] > s[1]) { mx = 0; mn = 1; } else { mn = 0; mx = 1; }
+  if (s[2] < s[mn]) { mid = mn; mn = 2; }
+  else if (s[2] > s[mx]) { mid = mx; mx = 2; }
+  else { mid = 2; }
+}
+
+// computeVertices — math/bv/OBB-inl.h:233-250
+void obb_vertices(const Mat3& axis, const Vec3& To, const Vec3& extent, Vec3 v[8]) {
+  const Vec3 e0 = scale(col(axis, 0), extent[0]), e1 = scale(col(axis, 1), extent[1]), e2 = scale(col(axis, 2), extent[2]);
+  v[0] = sub(sub(sub(To, e0), e1), e2);
+  v[1] = sub(sub(add(To, e0), e1), e2);
+  v[2] = sub(add(add(To, e0), e1), e2);
+  v[3] = sub(add(sub(To, e0), e1), e2);
+  v[4] = add(sub(sub(To, e0), e1), e2);
+  v[5] = add(sub(add(To, e0), e1), e2);
+  v[6] = add(add(add(To, e0), e1), e2);
+  v[7] = add(add(sub(To, e0), e1), e2);
+}
+
+// merge_largedist — math/bv/OBB-inl.h:254-312
+void obb_merge_largedist(const Node& b1, const Node& b2, Node& b) {
+  Vec3 vertex[16];
+  obb_vertices(b1.axis, b1.obb_To, b1.obb_ext, vertex);
+  obb_vertices(b2.axis, b2.obb_To, b2.obb_ext, vertex + 8);
+  Vec3 a0 = sub(b1.obb_To, b2.obb_To);
+  normalize_in_place(a0);
+  Vec3 proj[16];
+  for (int i = 0; i < 16; ++i) proj[i] = sub(vertex[i], scale(a0, dot(vertex[i], a0)));
+  double M[3][3], s[3], v[3][3];
+  covariance_points(proj, 16, M);
+  Builder::jacobi(M, s, v);
+  int mn, mid, mx;
+  order3(s, mn, mid, mx);
+  // E = vout with vout.col(k) = (v[k][0], v[k][1], v[k][2]) (eigen_old, :503-505), i.e. E(r, c) = v[c][r];
+  // axis.col(1) << E.col(0)[max], E.col(1)[max], E.col(2)[max] = (E(max,0), E(max,1), E(max,2)) = (v[0][max], v[1][max], v[2][max])
+  set_col(b.axis, 0, a0);
+  set_col(b.axis, 1, Vec3{{v[0][mx], v[1][mx], v[2][mx]}});
+  set_col(b.axis, 2, Vec3{{v[0][mid], v[1][mid], v[2][mid]}});
+  extent_and_center_points(vertex, 16, b.axis, b.obb_To, b.obb_ext);
+}
+
+// merge_smalldist — math/bv/OBB-inl.h:316-369
+struct Quat {
+  double x, y, z, w;
+};
+Quat quat_from(const Mat3& A) {  // Eigen quaternionbase_assign_impl<Matrix3>
+  Quat q;
+  double t = (A.m[0][0] + A.m[1][1]) + A.m[2][2];
+  if (t > 0) {
+    t = std::sqrt(t + 1.0);
+    q.w = 0.5 * t;
+    t = 0.5 / t;
+    q.x = (A.m[2][1] - A.m[1][2]) * t;
+    q.y = (A.m[0][2] - A.m[2][0]) * t;
+    q.z = (A.m[1][0] - A.m[0][1]) * t;
+  } else {
+    int i = 0;
+    if (A.m[1][1] > A.m[0][0]) i = 1;
+    if (A.m[2][2] > A.m[i][i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = std::sqrt(((A.m[i][i] - A.m[j][j]) - A.m[k][k]) + 1.0);
+    double c[3];
+    c[i] = 0.5 * t;
+    t = 0.5 / t;
+    q.w = (A.m[k][j] - A.m[j][k]) * t;
+    c[j] = (A.m[j][i] + A.m[i][j]) * t;
+    c[k] = (A.m[k][i] + A.m[i][k]) * t;
+    q.x = c[0];
+    q.y = c[1];
+    q.z = c[2];
+  }
+  return q;
+}
+Mat3 quat_to_matrix(const Quat& q) {  // Eigen QuaternionBase::toRotationMatrix
+  const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+  const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+  const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+  const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+  Mat3 R;
+  R.m[0][0] = 1 - (tyy + tzz);
+  R.m[0][1] = txy - twz;
+  R.m[0][2] = txz + twy;
+  R.m[1][0] = txy + twz;
+  R.m[1][1] = 1 - (txx + tzz);
+  R.m[1][2] = tyz - twx;
+  R.m[2][0] = txz - twy;
+  R.m[2][1] = tyz + twx;
+  R.m[2][2] = 1 - (txx + tyy);
+  return R;
+}
+void obb_merge_smalldist(const Node& b1, const Node& b2, Node& b) {
+  Vec3 To = scale(add(b1.obb_To, b2.obb_To), 0.5);
+  const Quat q0 = quat_from(b1.axis);
+  Quat q1 = quat_from(b2.axis);
+  if ((((q0.x * q1.x + q0.y * q1.y) + q0.z * q1.z) + q0.w * q1.w) < 0) q1 = Quat{-q1.x, -q1.y, -q1.z, -q1.w};
+  Quat q{q0.x + q1.x, q0.y + q1.y, q0.z + q1.z, q0.w + q1.w};
+  {
+    const double z = ((q.x * q.x + q.y * q.y) + q.z * q.z) + q.w * q.w;
+    if (z > 0) {
+      const double n = std::sqrt(z);
+      q = Quat{q.x / n, q.y / n, q.z / n, q.w / n};
+    }
+  }
+  b.axis = quat_to_matrix(q);
+  const double real_max = std::numeric_limits<double>::max();
+  double pmin[3] = {real_max, real_max, real_max}, pmax[3] = {-real_max, -real_max, -real_max};
+  Vec3 vertex[8];
+  for (int which = 0; which < 2; ++which) {
+    const Node& s = which == 0 ? b1 : b2;
+    obb_vertices(s.axis, s.obb_To, s.obb_ext, vertex);
+    for (int i = 0; i < 8; ++i) {
+      const Vec3 diff = sub(vertex[i], To);
+      for (int j = 0; j < 3; ++j) {
+        const double d = dot(diff, col(b.axis, j));
+        if (d > pmax[j]) pmax[j] = d;
+        else if (d < pmin[j]) pmin[j] = d;   // `else if`, like the reference (:339-342)
+      }
+    }
+  }
+  for (int j = 0; j < 3; ++j) {
+    To = add(To, scale(col(b.axis, j), 0.5 * (pmax[j] + pmin[j])));
+    b.obb_ext[j] = 0.5 * (pmax[j] - pmin[j]);
+  }
+  b.obb_To = To;
+}
+
+// OBB::operator+ — math/bv/OBB-inl.h:161-174
+void obb_merge(const Node& a, const Node& o, Node& out) {
+  const Vec3 center_diff = sub(a.obb_To, o.obb_To);
+  const double max_extent = std::max(std::max(a.obb_ext[0], a.obb_ext[1]), a.obb_ext[2]);
+  const double max_extent2 = std::max(std::max(o.obb_ext[0], o.obb_ext[1]), o.obb_ext[2]);
+  if (norm(center_diff) > 2 * (max_extent + max_extent2)) obb_merge_largedist(a, o, out);
+  else obb_merge_smalldist(a, o, out);
+}
+
+// RSS::operator+ — math/bv/RSS-inl.h:313-371.  Two things are kept exactly as the reference has them: the new in-plane
+// axes are E.col(max) / E.col(mid) of eigen_old's output (E(r, c) = v[c][r], so E.col(k) = ROW k of the Jacobi
+// eigenvector matrix, not the eigenvector axisFromEigen would pick), and the third axis is the cross product of
+// *this*'s first two axes (`axis.col(0).cross(axis.col(1))`, :364), not of the new ones.
+void rss_merge(const Node& a, const Node& o, Node& out) {
+  Vec3 v[16];
+  auto corners = [](const Node& s, Vec3* dst) {
+    const Vec3 d0_pos = scale(col(s.rss_axis, 0), s.rss_l[0] + s.rss_r);
+    const Vec3 d1_pos = scale(col(s.rss_axis, 1), s.rss_l[1] + s.rss_r);
+    const Vec3 d0_neg = scale(col(s.rss_axis, 0), -s.rss_r);
+    const Vec3 d1_neg = scale(col(s.rss_axis, 1), -s.rss_r);
+    const Vec3 d2_pos = scale(col(s.rss_axis, 2), s.rss_r);
+    const Vec3 d2_neg = scale(col(s.rss_axis, 2), -s.rss_r);
+    dst[0] = add(add(add(s.rss_To, d0_pos), d1_pos), d2_pos);
+    dst[1] = add(add(add(s.rss_To, d0_pos), d1_pos), d2_neg);
+    dst[2] = add(add(add(s.rss_To, d0_pos), d1_neg), d2_pos);
+    dst[3] = add(add(add(s.rss_To, d0_pos), d1_neg), d2_neg);
+    dst[4] = add(add(add(s.rss_To, d0_neg), d1_pos), d2_pos);
+    dst[5] = add(add(add(s.rss_To, d0_neg), d1_pos), d2_neg);
+    dst[6] = add(add(add(s.rss_To, d0_neg), d1_neg), d2_pos);
+    dst[7] = add(add(add(s.rss_To, d0_neg), d1_neg), d2_neg);
+  };
+  corners(o, v);      // v[0..7]: other
+  corners(a, v + 8);  // v[8..15]: *this
+  double M[3][3], s[3], e[3][3];
+  covariance_points(v, 16, M);
+  Builder::jacobi(M, s, e);
+  int mn, mid, mx;
+  order3(s, mn, mid, mx);
+  Mat3 A;
+  set_col(A, 0, Vec3{{e[mx][0], e[mx][1], e[mx][2]}});     // E.col(max)
+  set_col(A, 1, Vec3{{e[mid][0], e[mid][1], e[mid][2]}});  // E.col(mid)
+  set_col(A, 2, cross(col(a.rss_axis, 0), col(a.rss_axis, 1)));
+  out.rss_axis = A;
+  rss_fit_points(v, 16, A, out.rss_To, out.rss_l, out.rss_r);
+}
+
+}  // namespace
+
+// OBBRSS_fit_functions::fit3 — math/bv/utility-inl.h:92-117 (OBB), :208-230 (RSS), :507-511
+void fit3_obbrss(const Vec3 ps[3], Node& out) {
+  Vec3 e[3] = {sub(ps[0], ps[1]), sub(ps[1], ps[2]), sub(ps[2], ps[0])};
+  const double len[3] = {sqnorm(e[0]), sqnorm(e[1]), sqnorm(e[2])};
+  int imax = 0;
+  if (len[1] > len[0]) imax = 1;
+  if (len[2] > len[imax]) imax = 2;
+  Vec3 c2 = cross(e[0], e[1]);
+  normalize_in_place(c2);
+  Vec3 c0 = e[imax];
+  normalize_in_place(c0);
+  set_col(out.axis, 2, c2);
+  set_col(out.axis, 0, c0);
+  set_col(out.axis, 1, cross(c2, c0));
+  extent_and_center_points(ps, 3, out.axis, out.obb_To, out.obb_ext);
+  // RSS: e[0].cross(e[1]).normalized(), e[imax].normalized() -- the same values (normalized() = copy + normalize())
+  out.rss_axis = out.axis;
+  rss_fit_points(ps, 3, out.rss_axis, out.rss_To, out.rss_l, out.rss_r);
+}
+
+// OBBRSS::operator+ — math/bv/OBBRSS-inl.h:95-101
+void merge_obbrss(const Node& a, const Node& b, Node& out) {
+  Node r = out;
+  obb_merge(a, b, r);
+  rss_merge(a, b, r);
+  out.axis = r.axis;
+  out.obb_To = r.obb_To;
+  out.obb_ext = r.obb_ext;
+  out.rss_axis = r.rss_axis;
+  out.rss_To = r.rss_To;
+  out.rss_l[0] = r.rss_l[0];
+  out.rss_l[1] = r.rss_l[1];
+  out.rss_r = r.rss_r;
+}
+
+void refit_bottomup(Model& m, const std::vector<Vec3>& new_verts) {
+  m.verts = new_verts;
+  // recursiveRefitTree_bottomup(0): post-order; iterative with an explicit stack (trees can be 10^6 nodes deep in the
+  // worst case)
+  if (m.nodes.empty()) return;
+  std::vector<std::pair<int, int>> st;  // (node, state)
+  st.push_back({0, 0});
+  while (!st.empty()) {
+    auto [id, state] = st.back();
+    Node& nd = m.nodes[id];
+    if (nd.first_child < 0) {
+      const Tri& t = m.tris[-(nd.first_child + 1)];
+      const Vec3 ps[3] = {m.verts[t.v[0]], m.verts[t.v[1]], m.verts[t.v[2]]};
+      fit3_obbrss(ps, nd);
+      st.pop_back();
+    } else if (state == 0) {
+      st.back().second = 1;
+      st.push_back({nd.first_child + 1, 0});  // right is pushed first so that left is processed first
+      st.push_back({nd.first_child, 0});
+    } else {
+      merge_obbrss(m.nodes[nd.first_child], m.nodes[nd.first_child + 1], nd);
+      st.pop_back();
+    }
   }
 }
 

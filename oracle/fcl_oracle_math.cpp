@@ -398,10 +398,10 @@ double rect_distance(const Mat3& Rab, const Vec3& Tab, const double a[2], const 
 
 // distance(R0,T0,RSS,RSS) — RSS-inl.h:1957-1974 (via OBBRSS-inl.h:164-171).
 double rss_distance(const Mat3& R0, const Vec3& T0, const Node& n1, const Node& n2) {
-  Mat3 R0b2 = mul(R0, n2.axis);
-  Mat3 R = mulTN(n1.axis, R0b2);
+  Mat3 R0b2 = mul(R0, n2.rss_axis);
+  Mat3 R = mulTN(n1.rss_axis, R0b2);
   Vec3 Ttemp = sub(add(mul(R0, n2.rss_To), T0), n1.rss_To);
-  Vec3 T = mulTv(n1.axis, Ttemp);
+  Vec3 T = mulTv(n1.rss_axis, Ttemp);
   double dist = rect_distance(R, T, n1.rss_l, n2.rss_l);
   dist -= (n1.rss_r + n2.rss_r);
   return (dist < 0.0) ? 0.0 : dist;

@@ -97,6 +97,71 @@ int orc_model_refit_topdown(void* h, const double* verts, int nv) {
   return 0;
 }
 
+// endReplaceModel(refit=true, bottomup=true), the reference's default
+int orc_model_refit_bottomup(void* h, const double* verts, int nv) {
+  Model* m = (Model*)h;
+  if ((size_t)nv != m->verts.size()) return -7;
+  std::vector<Vec3> pts(nv);
+  for (int i = 0; i < nv; ++i) pts[i] = Vec3{{verts[3 * i], verts[3 * i + 1], verts[3 * i + 2]}};
+  refit_bottomup(*m, pts);
+  return 0;
+}
+
+// rss.axis per node, row-major 9 (equal to the obb's unless the model was refitted bottom-up)
+void orc_model_get_rss_axis(void* h, double* axis9) {
+  Model* m = (Model*)h;
+  for (size_t i = 0; i < m->nodes.size(); ++i)
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) axis9[9 * i + 3 * r + c] = m->nodes[i].rss_axis.m[r][c];
+}
+
+// OBBRSS::operator+ on two volumes given as arrays (axis9, obb_To3, obb_ext3, rss_axis9, rss_To3, rss_l2, rss_r = 29 doubles)
+static Node node_from29(const double* a) {
+  Node n{};
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      n.axis.m[r][c] = a[3 * r + c];
+      n.rss_axis.m[r][c] = a[15 + 3 * r + c];
+    }
+  for (int k = 0; k < 3; ++k) {
+    n.obb_To[k] = a[9 + k];
+    n.obb_ext[k] = a[12 + k];
+    n.rss_To[k] = a[24 + k];
+  }
+  n.rss_l[0] = a[27];
+  n.rss_l[1] = a[28];
+  return n;
+}
+static void node_to30(const Node& n, double* a) {
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      a[3 * r + c] = n.axis.m[r][c];
+      a[15 + 3 * r + c] = n.rss_axis.m[r][c];
+    }
+  for (int k = 0; k < 3; ++k) {
+    a[9 + k] = n.obb_To[k];
+    a[12 + k] = n.obb_ext[k];
+    a[24 + k] = n.rss_To[k];
+  }
+  a[27] = n.rss_l[0];
+  a[28] = n.rss_l[1];
+  a[29] = n.rss_r;
+}
+// volumes as 30 doubles: axis9, obb_To3, obb_ext3, rss_axis9, rss_To3, rss_l2, rss_r
+void orc_merge_obbrss(const double* a30, const double* b30, double* out30) {
+  Node a = node_from29(a30), b = node_from29(b30), o{};
+  a.rss_r = a30[29];
+  b.rss_r = b30[29];
+  merge_obbrss(a, b, o);
+  node_to30(o, out30);
+}
+void orc_fit3_obbrss(const double* pts9, double* out30) {
+  const Vec3 ps[3] = {Vec3{{pts9[0], pts9[1], pts9[2]}}, Vec3{{pts9[3], pts9[4], pts9[5]}}, Vec3{{pts9[6], pts9[7], pts9[8]}}};
+  Node o{};
+  fit3_obbrss(ps, o);
+  node_to30(o, out30);
+}
+
 void orc_model_partition(void* h, int32_t* first_primitive, int32_t* num_primitives, int32_t* primitive_indices) {
   Model* m = (Model*)h;
   for (size_t i = 0; i < m->nodes.size(); ++i) {
@@ -407,6 +472,7 @@ int orc_obb_disjoint(const double* B9, const double* T3, const double* a3, const
 static Node node_from(const double* axis9, const double* To, const double* ext_or_l, double r, bool rss) {
   Node n{};
   n.axis = mat_from(axis9);
+  n.rss_axis = n.axis;
   if (rss) {
     n.rss_To = vec_from(To);
     n.rss_l[0] = ext_or_l[0];

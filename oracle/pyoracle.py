@@ -48,6 +48,11 @@ def lib():
         L.orc_model_free.argtypes = [vp]
         L.orc_model_refit_topdown.restype = C.c_int
         L.orc_model_refit_topdown.argtypes = [vp, dp, C.c_int]
+        L.orc_model_refit_bottomup.restype = C.c_int
+        L.orc_model_refit_bottomup.argtypes = [vp, dp, C.c_int]
+        L.orc_model_get_rss_axis.argtypes = [vp, dp]
+        L.orc_merge_obbrss.argtypes = [dp, dp, dp]
+        L.orc_fit3_obbrss.argtypes = [dp, dp]
         L.orc_model_partition.argtypes = [vp, ip, ip, ip]
         L.orc_model_counts.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.orc_model_get.argtypes = [vp, dp, ip, ip, dp, dp, dp, dp, dp, dp]
@@ -138,6 +143,14 @@ class Model:
             self.verts = v
         return rc
 
+    def refit_bottomup(self, new_verts):
+        """endReplaceModel(refit=True, bottomup=True), the reference's default (BVH_model-inl.h:952-1037)."""
+        v = np.ascontiguousarray(new_verts, dtype=np.float64).reshape(-1, 3)
+        rc = lib().orc_model_refit_bottomup(self.h, _dp(v), len(v))
+        if rc == 0:
+            self.verts = v
+        return rc
+
     def partition(self):
         fp, npr, pi = np.empty(self.num_bvs, np.int32), np.empty(self.num_bvs, np.int32), np.empty(self.num_tris, np.int32)
         lib().orc_model_partition(self.h, _ip(fp), _ip(npr), _ip(pi))
@@ -152,6 +165,8 @@ class Model:
         )
         lib().orc_model_get(self.h, None, None, _ip(out["first_child"]), _dp(out["axis"]), _dp(out["obb_To"]),
                             _dp(out["obb_ext"]), _dp(out["rss_To"]), _dp(out["rss_l"]), _dp(out["rss_r"]))
+        out["rss_axis"] = np.empty((n, 9))
+        lib().orc_model_get_rss_axis(self.h, _dp(out["rss_axis"]))
         return out
 
 
@@ -502,3 +517,19 @@ def counted_query(kind, m1, m2, tf1, tf2=None, num_max_contacts=1, enable_contac
         L.orcc_distance(m1._h, m2._h, _dp(tf1), _dp(tf2), n, int(enable_nearest_points), int(nthreads), _lp(ops),
                         _lp(nbv), _lp(nleaf), _dp(val))
     return {"ops": ops, "n_bv": nbv, "n_leaf": nleaf, "value": val}
+
+
+def merge_obbrss(a30, b30):
+    """OBBRSS::operator+ on two volumes (30 doubles each: axis9, obb_To3, obb_ext3, rss_axis9, rss_To3, rss_l2, rss_r)."""
+    a, b = np.ascontiguousarray(a30, dtype=np.float64), np.ascontiguousarray(b30, dtype=np.float64)
+    out = np.empty(30)
+    lib().orc_merge_obbrss(_dp(a), _dp(b), _dp(out))
+    return out
+
+
+def fit3_obbrss(pts):
+    """OBBRSS_fit_functions::fit3 over three points -> 30 doubles."""
+    p = np.ascontiguousarray(pts, dtype=np.float64).reshape(9)
+    out = np.empty(30)
+    lib().orc_fit3_obbrss(_dp(p), _dp(out))
+    return out
