@@ -150,7 +150,6 @@ def test_replace_model_topdown_refit_matches_oracle(oracle, env_rob_npz, capfd):
         assert m.replaceSubModel(v2[: len(v2) // 2]) == F.BVH_OK
         assert m.endReplaceModel(True, False) == F.BVH_ERR_INCORRECT_DATA  # vertex count mismatch (:602-606)
         assert m.replaceSubModel(v2[len(v2) // 2:]) == F.BVH_OK
-        assert m.endReplaceModel(True, True) == F.BVH_ERR_UNSUPPORTED_FUNCTION  # bottom-up refit: not on this path
         assert m.endReplaceModel(True, False) == F.BVH_OK
         assert o.refit_topdown(v2) == 0
         got, ref = m.node_arrays(), o.arrays()
