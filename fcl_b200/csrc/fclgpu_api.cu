@@ -575,8 +575,8 @@ extern "C" int fclgpu_model_build_obbrss(int device, const double* vertices, int
   *out = nullptr;
   if (num_tris <= 0 || num_vertices <= 0) return fail(FCLGPU_ERR_BUILD_EMPTY_MODEL, "empty model");
   if (!vertices || !triangles) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL vertices/triangles");
-  if (split_method != FCLGPU_SPLIT_METHOD_MEAN && split_method != FCLGPU_SPLIT_METHOD_BV_CENTER)
-    return fail(FCLGPU_ERR_UNSUPPORTED_FUNCTION, "the on-device build supports the mean and BV-centre split rules");
+  if (split_method != FCLGPU_SPLIT_METHOD_MEAN && split_method != FCLGPU_SPLIT_METHOD_BV_CENTER && split_method != FCLGPU_SPLIT_METHOD_MEDIAN)
+    return fail(FCLGPU_ERR_INVALID_ARGUMENT, "unknown split method %d", split_method);
   for (int64_t i = 0; i < 3 * (int64_t)num_tris; ++i)
     if (triangles[i] < 0 || triangles[i] >= num_vertices) return fail(FCLGPU_ERR_INCORRECT_DATA, "triangle index out of range");
   int ndev = 0;

@@ -757,6 +757,109 @@ struct BuildParams {
   int32_t split;          // FCLGPU_SPLIT_METHOD_MEAN or _BV_CENTER
 };
 
+// ---------------------------------------------------------------------------------------
+// Median split rule (computeSplitValue_median, BV_splitter-inl.h:603-657): the reference sorts the projections of the
+// node's triangle centroids on the split axis and takes the middle one (odd count) or the mean of the two middle ones
+// (even).  Only those one or two order statistics matter, so nothing is sorted here: the projections go to the node's
+// slice of the queue scratch as order-preserving 64-bit keys and the k-th smallest is found bit by bit -- the answer is
+// the largest t with |{key < t}| <= k, built from the most significant bit down, one cooperative counting pass per bit.
+// kMode 0: one thread (n <= 24: insertion sort of a local array instead), 1: one warp, 2: one block of kFitBlock threads.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ordered_key_of(double x) {
+  const long long b = __double_as_longlong(x);
+  return b < 0 ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double double_of_ordered_key(unsigned long long k) {
+  return __longlong_as_double((long long)((k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k));
+}
+__device__ __forceinline__ double centroid_projection(const double* __restrict__ tri, uint32_t prim, double sv0, double sv1, double sv2) {
+  const double* p1 = tri + (size_t)prim * kTriDoubles;
+  const double* p2 = p1 + 3;
+  const double* p3 = p1 + 6;
+  const double c0 = (p1[0] + p2[0]) + p3[0], c1 = (p1[1] + p2[1]) + p3[1], c2 = (p1[2] + p2[2]) + p3[2];
+  return ((c0 * sv0 + c1 * sv1) + c2 * sv2) / 3;
+}
+
+template <int kMode>
+__device__ inline long long group_sum(long long v, int* wcnt) {
+  if constexpr (kMode == 0) {
+    return v;
+  } else {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if constexpr (kMode == 2) {
+      __syncthreads();  // the previous round's readers are done with wcnt
+      if ((threadIdx.x & 31) == 0) wcnt[threadIdx.x >> 5] = (int)v;
+      __syncthreads();
+      v = 0;
+      for (int w = 0; w < kFitBlock / 32; ++w) v += wcnt[w];
+    }
+    return v;
+  }
+}
+
+template <int kMode>
+__device__ inline double median_split_value(const BuildParams& B, const BuildNode nd, double sv0, double sv1, double sv2, int* wcnt) {
+  const RefitParams& P = B.R;
+  const uint32_t* idx = B.prim_order + nd.first;
+  const int n = nd.count;
+  if constexpr (kMode == 0) {  // n <= 24
+    double proj[24];
+    for (int i = 0; i < n; ++i) {
+      const double v = centroid_projection(P.tri, idx[i], sv0, sv1, sv2);
+      int j = i;
+      while (j > 0 && v < proj[j - 1]) {
+        proj[j] = proj[j - 1];
+        --j;
+      }
+      proj[j] = v;
+    }
+    return (n % 2 == 1) ? proj[(n - 1) / 2] : (proj[n / 2] + proj[n / 2 - 1]) / 2;
+  } else {
+  const int tid = (kMode == 1) ? (threadIdx.x & 31) : threadIdx.x;
+  const int stride = (kMode == 1) ? 32 : kFitBlock;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(B.queue + 2 * (size_t)nd.first);
+  for (int i = tid; i < n; i += stride) keys[i] = ordered_key_of(centroid_projection(P.tri, idx[i], sv0, sv1, sv2));
+  if (kMode == 1) __syncwarp();
+  else __syncthreads();
+  const long long k = (n % 2 == 1) ? (n - 1) / 2 : n / 2 - 1;  // lower middle (0-based rank)
+  unsigned long long ans = 0;
+  for (int bit = 63; bit >= 0; --bit) {
+    const unsigned long long t = ans | (1ull << bit);
+    long long c = 0;
+    for (int i = tid; i < n; i += stride) c += keys[i] < t ? 1 : 0;
+    c = group_sum<kMode>(c, wcnt);
+    if (c <= k) ans = t;
+  }
+  double lo = double_of_ordered_key(ans);
+  if (n % 2 == 1) return lo;
+  // upper middle: the same value when it occurs more than once past rank k, else the smallest key above it
+  long long le = 0;
+  unsigned long long above = ~0ull;
+  for (int i = tid; i < n; i += stride) {
+    const unsigned long long x = keys[i];
+    le += x <= ans ? 1 : 0;
+    if (x > ans && x < above) above = x;
+  }
+  le = group_sum<kMode>(le, wcnt);
+  // min over the group, as two 32-bit halves through the same sum-free path: shuffles inside a warp, wcnt across warps
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = shfl_u64(above, (threadIdx.x & 31) ^ o);
+    above = other < above ? other : above;
+  }
+  if (kMode == 2) {
+    __shared__ unsigned long long s_above[kFitBlock / 32];
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_above[threadIdx.x >> 5] = above;
+    __syncthreads();
+    for (int w = 0; w < kFitBlock / 32; ++w) above = s_above[w] < above ? s_above[w] : above;
+  }
+  const double hi = (le > k + 1) ? lo : double_of_ordered_key(above);
+  return (hi + lo) / 2;
+  }
+}
+
 __device__ inline void build_finish_node(const BuildParams& B, const BuildNode nd, const NodeFit& f, int lane, bool warp_mode) {
   const RefitParams& P = B.R;
   uint32_t* idx = B.prim_order + nd.first;
@@ -778,9 +881,12 @@ __device__ inline void build_finish_node(const BuildParams& B, const BuildNode n
     return;
   }
   const double sv0 = f.axis[0], sv1 = f.axis[3], sv2 = f.axis[6];
-  const double thr = (B.split == FCLGPU_SPLIT_METHOD_BV_CENTER)
-                         ? f.obb_To[0]
-                         : (f.vsum[0] * sv0 + f.vsum[1] * sv1 + f.vsum[2] * sv2) / (3 * n);
+  double thr;
+  if (B.split == FCLGPU_SPLIT_METHOD_BV_CENTER) thr = f.obb_To[0];
+  else if (B.split == FCLGPU_SPLIT_METHOD_MEDIAN)
+    thr = warp_mode ? median_split_value<1>(B, nd, sv0, sv1, sv2, nullptr) : median_split_value<0>(B, nd, sv0, sv1, sv2, nullptr);
+  else thr = (f.vsum[0] * sv0 + f.vsum[1] * sv1 + f.vsum[2] * sv2) / (3 * n);
+  if (warp_mode) __syncwarp();  // (median) every lane is done with the key scratch before it is reused below
   // side flags
   for (int i = warp_mode ? lane : 0; i < n; i += warp_mode ? 32 : 1) {
     const double* p1 = P.tri + (size_t)idx[i] * kTriDoubles;
@@ -878,9 +984,12 @@ __device__ inline void build_finish_node_block(const BuildParams& B, const Build
     B.node_count[nd.id] = n;
   }
   const double sv0 = f.axis[0], sv1 = f.axis[3], sv2 = f.axis[6];
-  const double thr = (B.split == FCLGPU_SPLIT_METHOD_BV_CENTER)
-                         ? f.obb_To[0]
-                         : (f.vsum[0] * sv0 + f.vsum[1] * sv1 + f.vsum[2] * sv2) / (3 * n);
+  double thr;
+  if (B.split == FCLGPU_SPLIT_METHOD_BV_CENTER) thr = f.obb_To[0];
+  else if (B.split == FCLGPU_SPLIT_METHOD_MEDIAN) {
+    thr = median_split_value<2>(B, nd, sv0, sv1, sv2, sm.wcnt);
+    __syncthreads();  // every thread is done with the key scratch before it is reused below
+  } else thr = (f.vsum[0] * sv0 + f.vsum[1] * sv1 + f.vsum[2] * sv2) / (3 * n);
   uint32_t* old = B.queue + 2 * (size_t)nd.first;
   uint32_t* lrank = old + n;
   uint8_t* fl = B.flag + nd.first;

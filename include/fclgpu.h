@@ -169,8 +169,8 @@ int fclgpu_model_from_bvh(int device, const fclgpu_bvh* bvh, fclgpu_model** out)
  * (BVH_model-inl.h:450-517, 833-938) executed level by level on the GPU from the host arrays
  * `vertices` (num_vertices x 3) and `triangles` (num_tris x 3).  Same tree, node numbering,
  * primitive order and volumes as fclgpu_bvh_build_obbrss + fclgpu_model_from_bvh, bit for bit.
- * split_method: FCLGPU_SPLIT_METHOD_MEAN or FCLGPU_SPLIT_METHOD_BV_CENTER (the median rule sorts per node;
- * use the host builder for it -> FCLGPU_ERR_UNSUPPORTED_FUNCTION here). Synchronous. */
+ * split_method: any of the three rules; the median rule (BV_splitter-inl.h:603-657) finds the one or two middle
+ * projections by a cooperative bitwise selection instead of sorting.  Synchronous. */
 int fclgpu_model_build_obbrss(int device, const double* vertices, int32_t num_vertices,
                               const int32_t* triangles, int32_t num_tris, int32_t split_method,
                               fclgpu_model** out);

@@ -363,7 +363,7 @@ def test_device_refit_thread_and_warp_variants_agree(oracle):
     _capi.set_option("refit_warp", 2)
 
 
-@pytest.mark.parametrize("split", [F.SPLIT_METHOD_MEAN, F.SPLIT_METHOD_BV_CENTER])
+@pytest.mark.parametrize("split", [F.SPLIT_METHOD_MEAN, F.SPLIT_METHOD_MEDIAN, F.SPLIT_METHOD_BV_CENTER])
 def test_device_build_equals_host_build(oracle, env_rob_npz, split):
     """SURVEY 8f rank 1: BVHModel::endModel() on the device (level-by-level fit / split / swap-partition replay).
     Tree, node numbering, primitive order and every BV equal the host builder's and the oracle's bit for bit;
@@ -421,7 +421,7 @@ def test_device_build_rejects_what_the_reference_rejects():
     assert L.fclgpu_model_build_obbrss(0, v.ctypes.data, 3, t.ctypes.data, 1, 0, C.byref(h)) == F.BVH_ERR_INCORRECT_DATA
     assert L.fclgpu_model_build_obbrss(0, v.ctypes.data, 3, t.ctypes.data, 0, 0, C.byref(h)) == F.BVH_ERR_BUILD_EMPTY_MODEL
     t[0, 2] = 2
-    assert L.fclgpu_model_build_obbrss(0, v.ctypes.data, 3, t.ctypes.data, 1, 1, C.byref(h)) == F.BVH_ERR_UNSUPPORTED_FUNCTION
+    assert L.fclgpu_model_build_obbrss(0, v.ctypes.data, 3, t.ctypes.data, 1, 7, C.byref(h)) == _capi.ERR_INVALID_ARGUMENT  # no such split rule
 
 
 @pytest.mark.parametrize("host_chunk", [4096, 1 << 17])
