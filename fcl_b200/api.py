@@ -185,7 +185,7 @@ class BVHModel:
         self.vertices = np.ascontiguousarray(np.concatenate(self._verts), dtype=np.float64)
         self.tri_indices = np.ascontiguousarray(np.concatenate(self._tris), dtype=np.int32)
         if self.build_on_device:
-            if self.split_method not in (SPLIT_METHOD_MEAN, SPLIT_METHOD_BV_CENTER):
+            if self.split_method not in (SPLIT_METHOD_MEAN, SPLIT_METHOD_MEDIAN, SPLIT_METHOD_BV_CENTER):
                 return BVH_ERR_UNSUPPORTED_FUNCTION
             if self.tri_indices.min() < 0 or self.tri_indices.max() >= self.num_vertices:
                 return BVH_ERR_INCORRECT_DATA
