@@ -32,6 +32,11 @@ CONTACT_DTYPE = np.dtype(
 assert CONTACT_DTYPE.itemsize == 64
 
 
+class ContinuousRequestC(C.Structure):  # fclgpu_continuous_request
+    _fields_ = [("num_max_iterations", C.c_int64), ("toc_err", C.c_double), ("ccd_motion_type", C.c_int32),
+                ("gjk_solver_type", C.c_int32), ("ccd_solver_type", C.c_int32)]
+
+
 class CollisionRequestC(C.Structure):
     _fields_ = [("num_max_contacts", C.c_int64), ("enable_contact", C.c_int32), ("enable_cost", C.c_int32),
                 ("stage_capacity", C.c_int64)]
@@ -52,6 +57,7 @@ class FclGpuError(RuntimeError):
 SYMBOLS = [
     "fclgpu_bvh_build_obbrss", "fclgpu_bvh_destroy", "fclgpu_bvh_num_nodes", "fclgpu_bvh_num_tris", "fclgpu_bvh_get",
     "fclgpu_bvh_refit_topdown", "fclgpu_bvh_num_vertices", "fclgpu_bvh_get_partition", "fclgpu_model_set_partition",
+    "fclgpu_continuous_collide_batch", "fclgpu_continuous_collide_batch_host",
     "fclgpu_bvh_refit_bottomup", "fclgpu_bvh_get_rss_axis", "fclgpu_model_refit_bottomup", "fclgpu_model_download_rss_axis",
     "fclgpu_model_refit_topdown", "fclgpu_model_download", "fclgpu_model_build_obbrss", "fclgpu_model_get_topology",
     "fclgpu_collide_mesh_sphere_batch", "fclgpu_collide_mesh_sphere_batch_host",
@@ -96,6 +102,10 @@ def lib():
     L.fclgpu_model_refit_topdown.argtypes = [vp, vp, C.c_int32, C.c_int32, vp]
     L.fclgpu_model_download.argtypes = [vp] * 8
     L.fclgpu_bvh_refit_bottomup.argtypes = [vp, vp, C.c_int32]
+    L.fclgpu_continuous_collide_batch.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, C.POINTER(ContinuousRequestC), vp, vp, vp, vp, vp,
+                                                  vp, vp, vp]
+    L.fclgpu_continuous_collide_batch_host.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, C.POINTER(ContinuousRequestC), vp, vp, vp,
+                                                       vp, vp]
     L.fclgpu_bvh_get_rss_axis.argtypes = [vp, vp]
     L.fclgpu_model_refit_bottomup.argtypes = [vp, vp, C.c_int32, C.c_int32, vp]
     L.fclgpu_model_download_rss_axis.argtypes = [vp, vp]

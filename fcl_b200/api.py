@@ -1117,3 +1117,83 @@ def distance(o1, tf1, o2=None, tf2=None, request=None, result=None):
     else:
         result.update(float(r.min_distance[0]), o1, o2, int(r.b1[0]), int(r.b2[0]))
     return result.min_distance
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Continuous collision: narrowphase/continuous_collision.h, continuous_collision_request.h:48-80,
+# continuous_collision_result.h.  Built: CCDM_TRANS motions with the conservative-advancement solver on two
+# BVHModel<OBBRSS> (csrc/continuous.cuh); everything else answers like the reference's "not supported" branch.
+# ---------------------------------------------------------------------------------------------------------------------
+CCDM_TRANS, CCDM_LINEAR, CCDM_SCREW, CCDM_SPLINE = 0, 1, 2, 3
+CCDC_NAIVE, CCDC_CONSERVATIVE_ADVANCEMENT, CCDC_RAY_SHOOTING, CCDC_POLYNOMIAL_SOLVER = 0, 1, 2, 3
+
+
+class ContinuousCollisionRequest:
+    def __init__(self, num_max_iterations=10, toc_err=0.0001, ccd_motion_type=CCDM_TRANS, gjk_solver_type="GST_LIBCCD",
+                 ccd_solver_type=CCDC_NAIVE):
+        self.num_max_iterations = num_max_iterations
+        self.toc_err = toc_err
+        self.ccd_motion_type = ccd_motion_type
+        self.gjk_solver_type = gjk_solver_type
+        self.ccd_solver_type = ccd_solver_type
+
+    def _c(self):
+        return _capi.ContinuousRequestC(int(self.num_max_iterations), float(self.toc_err), int(self.ccd_motion_type), 0,
+                                        int(self.ccd_solver_type))
+
+
+class ContinuousCollisionResult:
+    def __init__(self):
+        self.is_collide = False
+        self.time_of_contact = 1.0
+        self.contact_tf1 = Transform3()
+        self.contact_tf2 = Transform3()
+
+
+class BatchContinuousResult:
+    def __init__(self, is_collide, time_of_contact, contact_tf1, contact_tf2, iterations):
+        self.is_collide = is_collide
+        self.time_of_contact = time_of_contact
+        self.contact_tf1 = contact_tf1
+        self.contact_tf2 = contact_tf2
+        self.iterations = iterations
+
+
+def continuous_collide_batch(o1, tf1_beg, tf1_end, o2, tf2_beg, tf2_end, request, device=None):
+    """n independent fcl::continuousCollide(o1, tf1_beg[i], tf1_end[i], o2, tf2_beg[i], tf2_end[i], request, result_i)
+    calls (host arrays in and out).  Any pose argument may be None (identity)."""
+    arrs, ns = zip(*[_poses(t) for t in (tf1_beg, tf1_end, tf2_beg, tf2_end)])
+    ns = [k for k in ns if k is not None]
+    if not ns:
+        raise ValueError("at least one pose array must be given")
+    if len(set(ns)) != 1:
+        raise ValueError("the pose arrays must have the same length")
+    n = ns[0]
+    m1, m2 = o1.device_model(device), o2.device_model(device)
+    req = request._c()
+    hit, toc, it = np.zeros(n, np.int32), np.zeros(n), np.zeros(n, np.int32)
+    c1, c2 = np.zeros((n, 12)), np.zeros((n, 12))
+    check(_capi.lib().fclgpu_continuous_collide_batch_host(m1, m2, n, addr(arrs[0]), addr(arrs[1]), addr(arrs[2]), addr(arrs[3]),
+                                                           C.byref(req), addr(hit), addr(toc), addr(c1), addr(c2), addr(it)))
+    return BatchContinuousResult(hit.astype(bool), toc, c1, c2, it)
+
+
+def continuousCollide(o1, tf1_beg, tf1_end, o2=None, tf2_beg=None, tf2_end=None, request=None, result=None):
+    """fcl::continuousCollide(o1, tf1_beg, tf1_end, o2, tf2_beg, tf2_end, request, result)
+    (continuous_collision-inl.h:441-452), or the CollisionObject overload continuousCollide(obj1, tf1_end, obj2, tf2_end,
+    request, result) (:455-470); returns the time of contact (-1 for unsupported settings, like the reference)."""
+    if isinstance(o1, CollisionObject):
+        obj1, end1, obj2, end2, request, result = o1, tf1_beg, tf1_end, o2, tf2_beg, tf2_end
+        return continuousCollide(obj1.collisionGeometry(), obj1.getTransform(), end1, obj2.collisionGeometry(),
+                                 obj2.getTransform(), end2, request, result)
+    if request.ccd_solver_type != CCDC_CONSERVATIVE_ADVANCEMENT or request.ccd_motion_type != CCDM_TRANS or not (
+            isinstance(o1, BVHModel) and isinstance(o2, BVHModel)):
+        sys.stderr.write("Warning! Invalid continuous collision setting\n")
+        return -1.0
+    r = continuous_collide_batch(o1, tf1_beg, tf1_end, o2, tf2_beg, tf2_end, request)
+    result.is_collide = bool(r.is_collide[0])
+    result.time_of_contact = float(r.time_of_contact[0])
+    if result.is_collide:
+        result.contact_tf1 = Transform3.from_pose12(r.contact_tf1[0])
+        result.contact_tf2 = Transform3.from_pose12(r.contact_tf2[0])
+    return result.time_of_contact

@@ -20,6 +20,7 @@
 #include "collide_ordered.cuh"
 #include "broadphase.cuh"
 #include "refit.cuh"
+#include "continuous.cuh"
 
 using namespace fclgpu;
 
@@ -1300,6 +1301,56 @@ extern "C" int fclgpu_distance_mesh_sphere_batch(const fclgpu_model* m1, double 
 // ------------------------------------------------------------------------------------------
 // status / host-pointer wrappers
 // ------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------
+// continuous collision (conservative advancement, translating bodies) -- continuous.cuh
+// ------------------------------------------------------------------------------------------
+extern "C" int fclgpu_continuous_collide_batch(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1_beg,
+                                               const double* tf1_end, const double* tf2_beg, const double* tf2_end,
+                                               const fclgpu_continuous_request* request, int32_t* is_collide,
+                                               double* time_of_contact, double* contact_tf1, double* contact_tf2,
+                                               int32_t* iterations, uint32_t* n_bv, uint32_t* n_leaf, void* stream) {
+  if (!m1 || !m2 || !request || n < 0) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL model/request or n<0");
+  if (!is_collide) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "is_collide is NULL (it also holds the start-configuration verdicts)");
+  if (request->ccd_motion_type != FCLGPU_CCDM_TRANS)
+    return fail(FCLGPU_ERR_UNSUPPORTED_FUNCTION, "only CCDM_TRANS motions are built (the others need sin / cos / atan2: no bit parity)");
+  if (request->ccd_solver_type != FCLGPU_CCDC_CONSERVATIVE_ADVANCEMENT)
+    return fail(FCLGPU_ERR_UNSUPPORTED_FUNCTION, "only CCDC_CONSERVATIVE_ADVANCEMENT is built");
+  if (m1->device != m2->device) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "models live on different devices");
+  if (m1->depth + m2->depth + 2 > kStackCap)
+    return fail(FCLGPU_ERR_STACK_OVERFLOW, "tree depths %d+%d exceed the traversal stack", m1->depth, m2->depth);
+  if (n == 0) return FCLGPU_OK;
+  // conservativeAdvancementMeshOriented starts with collide() at the start configuration (default CollisionRequest)
+  fclgpu_collision_request cr{1, 0, 0, 0};
+  int rc = collide_enqueue(m1, m2, n, tf1_beg, tf2_beg, &cr, is_collide, nullptr, 0, nullptr, nullptr, nullptr, stream, CollideExtra{});
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaSetDevice(m1->device));
+  Workspace* w;
+  rc = get_ws(m1->device, &w);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lock(w->mu);
+  ContinuousParams P;
+  P.m1 = m1->d;
+  P.m2 = m2->d;
+  P.tf1_beg = tf1_beg;
+  P.tf1_end = tf1_end;
+  P.tf2_beg = tf2_beg;
+  P.tf2_end = tf2_end;
+  P.n = n;
+  P.start_hits = is_collide;
+  P.is_collide = is_collide;
+  P.toc = time_of_contact;
+  P.contact_tf1 = contact_tf1;
+  P.contact_tf2 = contact_tf2;
+  P.iterations = iterations;
+  P.n_bv = n_bv;
+  P.n_leaf = n_leaf;
+  P.work_counter = next_counter(w, st);
+  P.status = stream_state(w, st).status;
+  return (n_bv || n_leaf) ? launch_persistent(ca_translation_kernel<true>, P, w, 128, st)
+                          : launch_persistent(ca_translation_kernel<false>, P, w, 128, st);
+}
+
 extern "C" int fclgpu_sync_status(int device, void* stream) {
   Workspace* w;
   int rc = get_ws(device, &w);
@@ -1695,6 +1746,57 @@ extern "C" int fclgpu_collide_mesh_plane_batch_host(const fclgpu_model* m1, int3
 // ------------------------------------------------------------------------------------------
 // broadphase: N x M AABB culling feeding the batched mesh-mesh kernel
 // ------------------------------------------------------------------------------------------
+extern "C" int fclgpu_continuous_collide_batch_host(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1_beg,
+                                                    const double* tf1_end, const double* tf2_beg, const double* tf2_end,
+                                                    const fclgpu_continuous_request* request, int32_t* is_collide,
+                                                    double* time_of_contact, double* contact_tf1, double* contact_tf2,
+                                                    int32_t* iterations) {
+  if (!m1 || !m2 || !request || n < 0) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL model/request or n<0");
+  if (n == 0) return FCLGPU_OK;
+  CUDA_TRY(cudaSetDevice(m1->device));
+  Workspace* w;
+  int rc = get_ws(m1->device, &w);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> host_lock(w->host_mu);
+  // one staging block: 4 pose arrays in, verdict / toc / 2 contact poses / iterations out
+  const size_t N = (size_t)n;
+  char* dev = nullptr;
+  const size_t bytes = 4 * padded(96 * N) + padded(4 * N) + padded(8 * N) + 2 * padded(96 * N) + padded(4 * N) + 256;
+  CUDA_TRY(cudaMalloc((void**)&dev, bytes));
+  DevBuf B{dev};
+  double* d_in[4];
+  const double* h_in[4] = {tf1_beg, tf1_end, tf2_beg, tf2_end};
+  cudaStream_t st = w->pipe[0];
+  auto bail = [&](int code) {
+    cudaStreamSynchronize(st);
+    cudaFree(dev);
+    return code;
+  };
+  for (int k = 0; k < 4; ++k) {
+    d_in[k] = h_in[k] ? B.take<double>(12 * N) : nullptr;
+    if (h_in[k] && cudaMemcpyAsync(d_in[k], h_in[k], 96 * N, cudaMemcpyHostToDevice, st) != cudaSuccess)
+      return bail(fail(FCLGPU_ERR_UNKNOWN, "pose upload failed"));
+  }
+  int32_t* d_hit = B.take<int32_t>(N);
+  double* d_toc = B.take<double>(N);
+  double* d_c1 = contact_tf1 ? B.take<double>(12 * N) : nullptr;
+  double* d_c2 = contact_tf2 ? B.take<double>(12 * N) : nullptr;
+  int32_t* d_it = iterations ? B.take<int32_t>(N) : nullptr;
+  rc = fclgpu_continuous_collide_batch(m1, m2, n, d_in[0], d_in[1], d_in[2], d_in[3], request, d_hit, d_toc, d_c1, d_c2, d_it, nullptr,
+                                       nullptr, st);
+  if (rc) return bail(rc);
+  cudaError_t e = cudaSuccess;
+  if (is_collide) e = cudaMemcpyAsync(is_collide, d_hit, 4 * N, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && time_of_contact) e = cudaMemcpyAsync(time_of_contact, d_toc, 8 * N, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && d_c1) e = cudaMemcpyAsync(contact_tf1, d_c1, 96 * N, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && d_c2) e = cudaMemcpyAsync(contact_tf2, d_c2, 96 * N, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && d_it) e = cudaMemcpyAsync(iterations, d_it, 4 * N, cudaMemcpyDeviceToHost, st);
+  if (e != cudaSuccess) return bail(fail(FCLGPU_ERR_UNKNOWN, "result download failed: %s", cudaGetErrorString(e)));
+  rc = fclgpu_sync_status(m1->device, st);
+  cudaFree(dev);
+  return rc;
+}
+
 extern "C" int fclgpu_model_local_aabb(const fclgpu_model* m, double center3[3], double* radius, double min3[3], double max3[3]) {
   if (!m) return fail(FCLGPU_ERR_INVALID_ARGUMENT, "NULL model");
   for (int k = 0; k < 3; ++k) {

@@ -234,6 +234,41 @@ int fclgpu_collide_batch_host(const fclgpu_model* m1, const fclgpu_model* m2, in
                               int64_t* contact_offsets, uint32_t* n_bv, uint32_t* n_leaf);
 
 /* ---------------------------------------------------------------------------------------
+ * Batched continuous collision: query i evaluates
+ *   fcl::continuousCollide(m1, tf1_beg[i], tf1_end[i], m2, tf2_beg[i], tf2_end[i], request, result_i)
+ * (narrowphase/continuous_collision-inl.h:441-452) for request.ccd_motion_type = CCDM_TRANS (both bodies translate from
+ * tf_beg to tf_end's translation with tf_beg's rotation: TranslationMotion, math/motion/translation_motion-inl.h:47-84)
+ * and request.ccd_solver_type = CCDC_CONSERVATIVE_ADVANCEMENT: BVHConservativeAdvancement<OBBRSS> ->
+ * conservativeAdvancementMeshOriented (detail/conservative_advancement_func_matrix-inl.h:149-219, 692-712) with
+ * MeshConservativeAdvancementTraversalNodeOBBRSS (detail/traversal/distance/mesh_conservative_advancement_traversal_node.h
+ * :163-215, -inl.h:432-713).  Outputs mirror ContinuousCollisionResult: is_collide, time_of_contact (1 when there is
+ * no contact), contact_tf1 / contact_tf2 (12 doubles each; the start poses when there is no contact -- the reference
+ * leaves them unset).  The other motion types return FCLGPU_ERR_UNSUPPORTED_FUNCTION (see csrc/continuous.cuh), the
+ * other solvers as well.  num_max_iterations / toc_err are accepted and ignored, as the reference ignores them on this
+ * path (the traversal node's own t_err = 1e-5 ends the advancement).
+ * is_collide must not be NULL (it doubles as scratch for the start-configuration verdicts).
+ * ------------------------------------------------------------------------------------- */
+enum { FCLGPU_CCDM_TRANS = 0, FCLGPU_CCDM_LINEAR = 1, FCLGPU_CCDM_SCREW = 2, FCLGPU_CCDM_SPLINE = 3 };
+enum { FCLGPU_CCDC_NAIVE = 0, FCLGPU_CCDC_CONSERVATIVE_ADVANCEMENT = 1, FCLGPU_CCDC_RAY_SHOOTING = 2, FCLGPU_CCDC_POLYNOMIAL_SOLVER = 3 };
+typedef struct fclgpu_continuous_request { /* fcl::ContinuousCollisionRequest, continuous_collision_request.h:54-80 */
+  int64_t num_max_iterations; /* default 10 (ignored on this path) */
+  double toc_err;             /* default 0.0001 (ignored on this path) */
+  int32_t ccd_motion_type;    /* FCLGPU_CCDM_* (default CCDM_TRANS) */
+  int32_t gjk_solver_type;    /* unused for mesh pairs */
+  int32_t ccd_solver_type;    /* FCLGPU_CCDC_* (the reference's default is CCDC_NAIVE: not built) */
+} fclgpu_continuous_request;
+
+int fclgpu_continuous_collide_batch(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1_beg,
+                                    const double* tf1_end, const double* tf2_beg, const double* tf2_end,
+                                    const fclgpu_continuous_request* request, int32_t* is_collide, double* time_of_contact,
+                                    double* contact_tf1, double* contact_tf2, int32_t* iterations, uint32_t* n_bv,
+                                    uint32_t* n_leaf, void* stream);
+int fclgpu_continuous_collide_batch_host(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1_beg,
+                                         const double* tf1_end, const double* tf2_beg, const double* tf2_end,
+                                         const fclgpu_continuous_request* request, int32_t* is_collide, double* time_of_contact,
+                                         double* contact_tf1, double* contact_tf2, int32_t* iterations);
+
+/* ---------------------------------------------------------------------------------------
  * Batched mesh <-> sphere collide: query i evaluates
  * fcl::collide(m1, tf1[i], Sphere(radius), tf2[i], request, result_i) =
  * BVHShapeCollider<OBBRSS<S>, Sphere<S>> -> orientedBVHShapeCollide

@@ -107,6 +107,17 @@ void refit_bottomup(Model& m, const std::vector<Vec3>& new_verts);
 void merge_obbrss(const Node& a, const Node& b, Node& out);
 void fit3_obbrss(const Vec3 ps[3], Node& out);
 
+// continuousCollide() with ccd_motion_type = CCDM_TRANS and ccd_solver_type = CCDC_CONSERVATIVE_ADVANCEMENT on two
+// BVHModel<OBBRSS> (only the translations of tf*_end are used: TranslationMotion keeps tf*_beg's rotation)
+struct ContinuousOut {
+  bool is_collide;
+  double time_of_contact;
+  Pose contact_tf1, contact_tf2;  // ContinuousCollisionResult::contact_tf1/2 (the start poses when there is no contact)
+  int iterations;                 // distance traversals run (diagnostic)
+};
+double continuous_collide_translation(const Model& m1, const Pose& tf1_beg, const Pose& tf1_end, const Model& m2,
+                                      const Pose& tf2_beg, const Pose& tf2_end, ContinuousOut& out);
+
 // ---- BV / leaf kernels -------------------------------------------------------
 bool obb_disjoint(const Mat3& B, const Vec3& T, const Vec3& a, const Vec3& b);
 bool obb_overlap(const Mat3& R0, const Vec3& T0, const Node& n1, const Node& n2);

@@ -1087,6 +1087,187 @@ double brute_distance(const Model& m1, const Pose& tf1, const Model& m2, const P
 }
 
 // ---------------------------------------------------------------------------------------
+// Continuous collision by conservative advancement, both bodies translating (CCDM_TRANS):
+//   continuousCollide(o1, tf1_beg, tf1_end, o2, tf2_beg, tf2_end, request{CCDM_TRANS, CCDC_CONSERVATIVE_ADVANCEMENT})
+//     narrowphase/continuous_collision-inl.h:441-452 (getMotionBase :93-117 -> TranslationMotion), :355-377, :302-352
+//   -> conservative_advancement_matrix[BV_OBBRSS][BV_OBBRSS] = BVHConservativeAdvancement<OBBRSS>
+//     detail/conservative_advancement_func_matrix-inl.h:692-712, 675-690
+//   -> conservativeAdvancementMeshOriented<OBBRSS, MeshConservativeAdvancementTraversalNodeOBBRSS>   :149-219
+//   traversal node: detail/traversal/distance/mesh_conservative_advancement_traversal_node.h:163-215 (BVTesting),
+//     -inl.h:432-470 (OBBRSS leafTesting / canStop), :641-713 (meshConservativeAdvancementOrientedNodeLeafTesting),
+//     :566-637 (meshConservativeAdvancementOrientedNodeCanStop)
+//   TranslationMotion: math/motion/translation_motion-inl.h:47-134; bounds: triangle_motion_bound_visitor-inl.h:218-227,
+//     tbv_motion_bound_visitor-inl.h:52-62 -- TBVMotionBoundVisitorVisitImpl is specialised for RSS only, so for
+//     BV = OBBRSS the generic template answers 0: a pruned node pair never shortens the step (bound 0 <= c gives
+//     cur_delta_t = 1) and only the triangle pairs actually visited do.  Kept as the reference has it.
+// Eigen pieces (published algorithms, restated above for the bottom-up refit): Quaternion(Matrix3), toRotationMatrix,
+// Quaternion * Vector3 (_transformVector: uv = 2 (vec x v); v + w uv + vec x uv), Vector3::normalize.
+// ---------------------------------------------------------------------------------------
+namespace {
+
+struct TransMotion {  // TranslationMotion<S>
+  Quat rot;
+  Vec3 trans_start, trans_range;
+  Pose tf;  // current transform
+  TransMotion(const Pose& tf1, const Pose& tf2) : rot(quat_from(tf1.R)), trans_start(tf1.t), trans_range(sub(tf2.t, tf1.t)), tf(tf1) {}
+  void integrate(double dt) {
+    if (dt > 1) dt = 1;
+    tf.R = quat_to_matrix(rot);
+    tf.t = add(trans_start, scale(trans_range, dt));
+  }
+};
+
+inline Vec3 quat_rotate(const Quat& q, const Vec3& v) {  // Eigen QuaternionBase::_transformVector
+  const Vec3 qv{{q.x, q.y, q.z}};
+  Vec3 uv = cross(qv, v);
+  uv = add(uv, uv);
+  return add(add(v, scale(uv, q.w)), cross(qv, uv));
+}
+
+struct CaStackData {  // ConservativeAdvancementStackData (P1, P2 of the box pair are never read for OBBRSS: bound = 0)
+  int c1, c2;
+  double d;
+};
+
+struct CaCtx {
+  const Model& m1;
+  const Model& m2;
+  const TransMotion* motion1;
+  const TransMotion* motion2;
+  Mat3 R{};
+  Vec3 T{};
+  double min_distance = std::numeric_limits<double>::max();
+  double delta_t = 1, toc = 0, t_err = 0.00001, w = 1;  // constructor defaults, -inl.h:84-97
+  CaCtx(const Model& a, const Model& b, const TransMotion* x, const TransMotion* y) : m1(a), m2(b), motion1(x), motion2(y) {}
+  std::vector<CaStackData> stack;
+  long long n_bv = 0, n_leaf = 0;
+
+  double bv(int b1, int b2) {  // BVTesting, mesh_conservative_advancement_traversal_node.h:172-189
+    n_bv++;
+    const double d = rss_distance(R, T, m1.nodes[b1], m2.nodes[b2]);
+    stack.push_back({b1, b2, d});
+    return d;
+  }
+
+  void leaf(int b1, int b2) {  // meshConservativeAdvancementOrientedNodeLeafTesting
+    n_leaf++;
+    const Tri& t1 = m1.tris[-(m1.nodes[b1].first_child + 1)];
+    const Tri& t2 = m2.tris[-(m2.nodes[b2].first_child + 1)];
+    const Vec3 S[3] = {m1.verts[t1.v[0]], m1.verts[t1.v[1]], m1.verts[t1.v[2]]};
+    Vec3 Tt[3];
+    for (int k = 0; k < 3; ++k) Tt[k] = add(mul(R, m2.verts[t2.v[k]]), T);  // triDistance(..., R, T, P, Q)
+    Vec3 P1, P2;
+    const double d = tri_distance(S, Tt, P1, P2);
+    if (d < min_distance) min_distance = d;
+    const Vec3 n = sub(P2, P1);
+    const Quat R0 = quat_from(motion1->tf.R);  // getCurrentRotation(Quaternion&): Q = tf.linear()
+    Vec3 nt = quat_rotate(R0, n);
+    normalize_in_place(nt);
+    const Vec3 neg{{-nt[0], -nt[1], -nt[2]}};
+    const double bound1 = dot(motion1->trans_range, nt);   // TriangleMotionBoundVisitor / TranslationMotion: velocity . n
+    const double bound2 = dot(motion2->trans_range, neg);
+    const double bound = bound1 + bound2;
+    double cur_delta_t;
+    if (bound <= d) cur_delta_t = 1;
+    else cur_delta_t = d / bound;
+    if (cur_delta_t < delta_t) delta_t = cur_delta_t;
+  }
+
+  bool can_stop(double c) {  // meshConservativeAdvancementOrientedNodeCanStop with abs_err = rel_err = 0
+    if ((c >= w * (min_distance - 0.0)) && (c * (1 + 0.0) >= w * min_distance)) {
+      const CaStackData& data = stack.back();
+      if (data.d > c) stack[stack.size() - 2] = stack[stack.size() - 1];
+      // bound1 = bound2 = 0 (generic TBVMotionBoundVisitorVisitImpl for OBBRSS): bound <= c, cur_delta_t = 1
+      const double bound = 0.0 + 0.0;
+      double cur_delta_t;
+      if (bound <= c) cur_delta_t = 1;
+      else cur_delta_t = c / bound;
+      if (cur_delta_t < delta_t) delta_t = cur_delta_t;
+      stack.pop_back();
+      return true;
+    }
+    const CaStackData& data = stack.back();
+    if (data.d > c) stack[stack.size() - 2] = stack[stack.size() - 1];
+    stack.pop_back();
+    return false;
+  }
+
+  void recurse(int b1, int b2) {  // distanceRecurse, traversal_recurse-inl.h:259-316
+    const Node& n1 = m1.nodes[b1];
+    const Node& n2 = m2.nodes[b2];
+    const bool l1 = n1.first_child < 0, l2 = n2.first_child < 0;
+    if (l1 && l2) {
+      leaf(b1, b2);
+      return;
+    }
+    int a1, a2, c1, c2;
+    if (first_over_second(n1, n2)) {
+      a1 = n1.first_child; a2 = b2; c1 = n1.first_child + 1; c2 = b2;
+    } else {
+      a1 = b1; a2 = n2.first_child; c1 = b1; c2 = n2.first_child + 1;
+    }
+    const double d1 = bv(a1, a2);
+    const double d2 = bv(c1, c2);
+    if (d2 < d1) {
+      if (!can_stop(d2)) recurse(c1, c2);
+      if (!can_stop(d1)) recurse(a1, a2);
+    } else {
+      if (!can_stop(d1)) recurse(a1, a2);
+      if (!can_stop(d2)) recurse(c1, c2);
+    }
+  }
+};
+
+}  // namespace
+
+double continuous_collide_translation(const Model& m1, const Pose& tf1_beg, const Pose& tf1_end, const Model& m2,
+                                      const Pose& tf2_beg, const Pose& tf2_end, ContinuousOut& out) {
+  TransMotion motion1(tf1_beg, tf1_end), motion2(tf2_beg, tf2_end);
+  out.is_collide = false;
+  out.time_of_contact = 1.0;  // ContinuousCollisionResult()
+  out.iterations = 0;
+  out.contact_tf1 = tf1_beg;
+  out.contact_tf2 = tf2_beg;
+  double toc;
+  bool is_collide;
+  // conservativeAdvancementMeshOriented: collision at the start configuration?
+  std::vector<Contact> contacts;
+  if (collide(m1, motion1.tf, m2, motion2.tf, 1, false, contacts) > 0) {
+    toc = 0;
+    is_collide = true;
+  } else {
+    CaCtx node(m1, m2, &motion1, &motion2);
+    do {
+      relative_for_distance(motion1.tf, motion2.tf, node.R, node.T);  // tf1.inverse(Isometry) * tf2
+      node.delta_t = 1;
+      node.min_distance = std::numeric_limits<double>::max();
+      node.stack.clear();
+      node.recurse(0, 0);
+      out.iterations++;
+      if (node.delta_t <= node.t_err) break;
+      node.toc += node.delta_t;
+      if (node.toc > 1) {
+        node.toc = 1;
+        break;
+      }
+      motion1.integrate(node.toc);
+      motion2.integrate(node.toc);
+    } while (1);
+    toc = node.toc;
+    is_collide = node.toc < 1;
+  }
+  out.is_collide = is_collide;
+  out.time_of_contact = toc;
+  if (is_collide) {  // continuousCollideConservativeAdvancement, continuous_collision-inl.h:339-350
+    motion1.integrate(toc);
+    motion2.integrate(toc);
+    out.contact_tf1 = motion1.tf;
+    out.contact_tf2 = motion2.tf;
+  }
+  return toc;
+}
+
+// ---------------------------------------------------------------------------------------
 // Mesh <-> sphere collide: BVHShapeCollider<OBBRSS, Sphere>::collide -> orientedBVHShapeCollide
 // (detail/collision_func_matrix-inl.h:378-430) -> initialize / setupMeshShapeCollisionOrientedNode
 // (computeBV(model2, tf2, model2_bv)) -> collisionRecurse with a leaf second node.

@@ -432,6 +432,33 @@ double orc_distance_batch(void* h1, void* h2, long long n, const double* tf1, co
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
+// continuousCollide (CCDM_TRANS, conservative advancement) over a batch; tf*_beg / tf*_end: 12 doubles per query
+// (NULL = identity).  Outputs (any may be NULL): is_collide[n], toc[n], contact_tf1/2[12 n], iterations[n].
+double orc_continuous_collide_translation_batch(void* h1, void* h2, long long n, const double* tf1_beg, const double* tf1_end,
+                                                const double* tf2_beg, const double* tf2_end, int nthreads, int32_t* is_collide,
+                                                double* toc, double* contact_tf1, double* contact_tf2, int32_t* iterations) {
+  Model* m1 = (Model*)h1;
+  Model* m2 = (Model*)h2;
+  auto t0 = std::chrono::steady_clock::now();
+  auto put = [](double* dst, const Pose& p) {
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) dst[3 * r + c] = p.R.m[r][c];
+    for (int k = 0; k < 3; ++k) dst[9 + k] = p.t[k];
+  };
+  parallel_for(n, nthreads, [&](long long i) {
+    const Pose a0 = pose_from(tf1_beg ? tf1_beg + 12 * i : nullptr), a1 = pose_from(tf1_end ? tf1_end + 12 * i : nullptr);
+    const Pose b0 = pose_from(tf2_beg ? tf2_beg + 12 * i : nullptr), b1 = pose_from(tf2_end ? tf2_end + 12 * i : nullptr);
+    ContinuousOut o;
+    continuous_collide_translation(*m1, a0, a1, *m2, b0, b1, o);
+    if (is_collide) is_collide[i] = o.is_collide ? 1 : 0;
+    if (toc) toc[i] = o.time_of_contact;
+    if (contact_tf1) put(contact_tf1 + 12 * i, o.contact_tf1);
+    if (contact_tf2) put(contact_tf2 + 12 * i, o.contact_tf2);
+    if (iterations) iterations[i] = o.iterations;
+  });
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
 // ---- brute force --------------------------------------------------------------
 long long orc_brute_collide(void* h1, void* h2, const double* tf1, const double* tf2, int32_t* pairs,
                             long long cap_pairs) {

@@ -316,6 +316,22 @@ def distance_batch(m1, m2, tf1, tf2=None, enable_nearest_points=True, qsize=2, n
     return dict(min_distance=dist, p1=p1, p2=p2, b1=b1, b2=b2, n_bv=n_bv, n_leaf=n_leaf, seconds=secs)
 
 
+def continuous_collide_translation_batch(m1, m2, tf1_beg, tf1_end, tf2_beg=None, tf2_end=None, nthreads=1):
+    """fcl::continuousCollide(o1, tf1_beg, tf1_end, o2, tf2_beg, tf2_end, request) with ccd_motion_type = CCDM_TRANS and
+    ccd_solver_type = CCDC_CONSERVATIVE_ADVANCEMENT, one call per row."""
+    L = lib()
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    L.orc_continuous_collide_translation_batch.restype = C.c_double
+    L.orc_continuous_collide_translation_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, dp, dp, dp, dp, C.c_int, ip, dp, dp, dp, ip]
+    a0, a1, b0, b1 = _poses(tf1_beg), _poses(tf1_end), _poses(tf2_beg), _poses(tf2_end)
+    n = max(len(x) for x in (a0, a1, b0, b1) if x is not None)
+    hit, toc, it = np.empty(n, np.int32), np.empty(n), np.empty(n, np.int32)
+    c1, c2 = np.empty((n, 12)), np.empty((n, 12))
+    secs = L.orc_continuous_collide_translation_batch(m1.h, m2.h, n, _dp(a0), _dp(a1), _dp(b0), _dp(b1), nthreads, _ip(hit), _dp(toc),
+                                                      _dp(c1), _dp(c2), _ip(it))
+    return dict(is_collide=hit.astype(bool), time_of_contact=toc, contact_tf1=c1, contact_tf2=c2, iterations=it, seconds=secs)
+
+
 def brute_collide(m1, m2, tf1, tf2=None):
     tf1 = None if tf1 is None else np.ascontiguousarray(tf1, dtype=np.float64).reshape(12)
     tf2 = None if tf2 is None else np.ascontiguousarray(tf2, dtype=np.float64).reshape(12)
