@@ -112,7 +112,7 @@ def test_gpu_continuous_collide_matches_oracle_bitwise(oracle, env_rob_npz, orac
         assert np.array_equal(got.iterations, ref["iterations"])
         assert got.contact_tf1.tobytes() == ref["contact_tf1"].tobytes()
         assert got.contact_tf2.tobytes() == ref["contact_tf2"].tobytes()
-        assert 0.05 * n < (ref["is_collide"] & (ref["time_of_contact"] > 0)).sum()
+        assert 0.02 * n < (ref["is_collide"] & (ref["time_of_contact"] > 0)).sum()
     # the single-query entry point reads like the reference's
     res = F.ContinuousCollisionResult()
     k = int(np.where(ref["is_collide"] & (ref["time_of_contact"] > 0))[0][0])
