@@ -118,8 +118,9 @@ FD void mesh_sphere_leaf(const Acc& acc, int id, const M3& R1, const V3& t1, con
 }
 
 // Depth first, nearer child first.  Acc: int first_child(b); void box(b, axis, To, e0, e1, e2); void tri(id, T[3]).
-// Every bound is >= -margin > -1, so after a triangle within the radius nothing else is visited -- exactly
-// where canStop() ends the reference's traversal.
+// The bounds (distance of the centre to a box, minus the radius, minus a margin) go down to about -radius, so after a
+// triangle within the radius (minimum -1: nothing can update it any more) the loop is left explicitly instead of
+// descending every box within radius - 1 of the centre.
 #pragma nv_exec_check_disable
 template <class Acc>
 FD void mesh_sphere_distance_query(const Acc& acc, const M3& R1, const V3& t1, const V3& c, double radius, int* stk,
@@ -146,6 +147,7 @@ FD void mesh_sphere_distance_query(const Acc& acc, const M3& R1, const V3& t1, c
     if (fc < 0) {
       if (b >= 0) s.leaf_tests++;
       mesh_sphere_leaf(acc, -(fc + 1), R1, t1, c, radius, s);
+      if (s.min_d == -1.0) break;  // a triangle within the radius: the result is final
       continue;
     }
     double d1, d2;

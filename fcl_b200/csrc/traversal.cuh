@@ -2158,6 +2158,7 @@ __global__ void __launch_bounds__(128, kMinBlocks) distance_mesh_sphere_rounds_k
       if (pend >= 0) {
         mesh_sphere_leaf(acc, pend, tf1.R, tf1.t, tf2.t, radius, s);
         pend = -1;
+        if (s.min_d == -1.0) sp = 0;  // a triangle within the radius: final, drop the rest of the stack
       }
     }
   }
