@@ -585,6 +585,14 @@ __device__ __forceinline__ unsigned warp_sort_keys(unsigned key, int lane) {
 #ifndef FCLGPU_DIST_SEED
 #define FCLGPU_DIST_SEED 5
 #endif
+// Pre-expanded front entries (FCLGPU_DIST_PREX): the lane that bounds a child pair also reads the two topology records
+// and stores the entry in the form the NEXT expansion needs -- a leaf pair as its two triangle ids, an internal pair as
+// (first child of the node firstOverSecond splits, which model that is, the other node) -- so that a popped entry is
+// expanded without a dependent global load (pop -> topology -> ballot was the longest chain of a BV round); the loads
+// now overlap the key sort.  Encoding: leaf pair {t1 | 1<<31, t2}; internal {fc | side<<30, other}, side 1 = model 1 splits.
+#ifndef FCLGPU_DIST_PREX
+#define FCLGPU_DIST_PREX 1
+#endif
 // Development build (-DFCLGPU_DIST_PROF=1): per-phase SM cycles of the sorted-front kernel, summed over warps
 // (0 prologue / epilogue, 1 BV rounds, 2 screening rounds, 3 exact rounds, 4 refill; 8.. = round counts), read with
 // fclgpu_debug_counters().  Compiled out of the product build.
@@ -603,6 +611,13 @@ __device__ unsigned long long g_debug_counters[16];
 #else
 #define DPROF_MARK(k)
 #endif
+// front entry of the node pair (x, y) in the pre-expanded form (FCLGPU_DIST_PREX)
+__device__ __forceinline__ uint2 prex_entry(unsigned x, unsigned y, int fc1, double size1, int fc2, double size2) {
+  const bool l1 = fc1 < 0, l2 = fc2 < 0;
+  if (l1 && l2) return make_uint2((unsigned)(-(fc1 + 1)) | 0x80000000u, (unsigned)(-(fc2 + 1)));
+  if (l2 || (!l1 && (size1 > size2))) return make_uint2((unsigned)fc1 | 0x40000000u, y);  // firstOverSecond: model 1 splits
+  return make_uint2((unsigned)fc2, x);
+}
 // kSpill: instantiation with the global overflow area for deep trees (kept out of the default instantiation:
 // the extra live state costs the hot loop 10 %)
 // kTol: tolerance verdicts (stop_below / within) -- a separate instantiation as well: the early-exit test inside the leaf
@@ -623,8 +638,21 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
   // entries), and every query starts with ONE full round that bounds and sorts those pairs instead of the 1-, 2-, 4-,
   // 8- and 16-lane rounds that lead there.  Same BVTT coverage, so the same minimum.
   constexpr bool kSeed = FCLGPU_DIST_SEED > 0;
+  constexpr bool kPrex = FCLGPU_DIST_PREX != 0;
   __shared__ uint2 s_seed[32];
   __shared__ int s_nseed;
+  __shared__ uint2 s_root;  // the root pair as a front entry
+  if (threadIdx.x == 0) {
+    s_root = make_uint2(0u, 0u);
+    if (kPrex) {
+      int fc1, fc2;
+      double size1, size2;
+      load_topo(P.m1.topo, 0, fc1, size1);
+      load_topo(P.m2.topo, 0, fc2, size2);
+      s_root = prex_entry(0u, 0u, fc1, size1, fc2, size2);
+    }
+  }
+  if (!kSeed) __syncthreads();
   if (kSeed) {
     if (threadIdx.x < 32) {
       if (lane == 0) s_seed[0] = make_uint2(0u, 0u);
@@ -706,7 +734,7 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
     int sp = seed_pending ? 0 : 1, nleaf = 1, nraw = 0;
     uint32_t bv_tests = 0, leaf_tests = 0;
     if (lane == 0) {
-      S.pair[0] = make_uint2(0u, 0u);
+      S.pair[0] = s_root;
       S.bound[0] = -1.0f;                   // the root pair is never bound-tested
       S.leaf_pair[0] = make_uint2(0u, 0u);  // preprocess: triangle 0 / triangle 0 seeds the result
       S.leaf_bound[0] = -1.0f;
@@ -882,15 +910,16 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
         }
         int fc1 = 0, fc2 = 0;
         double size1 = 0.0, size2 = 0.0;
-        if (alive) {  // {first_child, size} of both nodes: one 16-byte load each
+        if (!kPrex && alive) {  // {first_child, size} of both nodes: one 16-byte load each
           load_topo(P.m1.topo, (int)pr.x, fc1, size1);
           load_topo(P.m2.topo, (int)pr.y, fc2, size2);
         }
         const bool l1 = fc1 < 0, l2 = fc2 < 0;
-        const bool leafpair = alive && l1 && l2;
+        const bool leafpair = alive && (kPrex ? (pr.x >> 31) != 0u : (l1 && l2));
         const unsigned lm = __ballot_sync(0xffffffffu, leafpair);
         if (leafpair) {
-          const uint2 tri_ids = make_uint2((unsigned)(-(fc1 + 1)), (unsigned)(-(fc2 + 1)));
+          const uint2 tri_ids = kPrex ? make_uint2(pr.x & 0x7fffffffu, pr.y)
+                                      : make_uint2((unsigned)(-(fc1 + 1)), (unsigned)(-(fc2 + 1)));
           if (kBound32 && kScreen) {
             const int pos = nraw + __popc(lm & lt_mask);
             S.raw_pair[pos] = tri_ids;
@@ -947,7 +976,16 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
         __syncwarp();  // every lane has read its popped entry before slots are overwritten
         if (internal) {
           if (rank < n_exp) {
-            if (l2 || (!l1 && (size1 > size2))) {  // firstOverSecond
+            if (kPrex) {
+              const unsigned fc = pr.x & 0x3fffffffu;
+              if (pr.x & 0x40000000u) {  // model 1's node splits
+                S.expand[2 * rank] = make_uint2(fc, pr.y);
+                S.expand[2 * rank + 1] = make_uint2(fc + 1u, pr.y);
+              } else {
+                S.expand[2 * rank] = make_uint2(pr.y, fc);
+                S.expand[2 * rank + 1] = make_uint2(pr.y, fc + 1u);
+              }
+            } else if (l2 || (!l1 && (size1 > size2))) {  // firstOverSecond
               S.expand[2 * rank] = make_uint2((unsigned)fc1, pr.y);
               S.expand[2 * rank + 1] = make_uint2((unsigned)fc1 + 1u, pr.y);
             } else {
@@ -982,6 +1020,12 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
         }
         if (d < min_f) key = (__float_as_uint(d) & ~31u) | (unsigned)lane;
       }
+      int tfc1 = 0, tfc2 = 0;
+      double tsz1 = 0.0, tsz2 = 0.0;
+      if (kPrex && key != 0xffffffffu) {  // the survivor's topology: in flight during the sort below
+        load_topo(P.m1.topo, (int)xy.x, tfc1, tsz1);
+        load_topo(P.m2.topo, (int)xy.y, tfc2, tsz2);
+      }
       if (kStats) bv_tests += n_test;
       const int nkeep = __popc(__ballot_sync(0xffffffffu, key != 0xffffffffu));
       if (nkeep > 0) {
@@ -989,6 +1033,7 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
         // 83 ms vs 44 ms -- the nearest-first order is what keeps the front small
         key = warp_sort_keys(key, lane);  // ascending: lane 0 = nearest
         const int src = (int)(key & 31u);
+        if (kPrex) xy = prex_entry(xy.x, xy.y, tfc1, tsz1, tfc2, tsz2);
         const unsigned long long v = shfl_u64(((unsigned long long)xy.x << 32) | xy.y, src);
         const float dv = __shfl_sync(0xffffffffu, d, src);
         if (lane < nkeep) {  // nearest ends on top of the stack
