@@ -83,6 +83,9 @@ struct OrderedParams {
   unsigned long long* cursor;  // running number of contacts appended to the pool
   long long* starts;           // [n] start of query i's block in the pool (or nullptr)
   int depth_sum;               // depth(model1) + depth(model2)
+  int discard_stage;           // drop the staging lines from the L2 after the copy to the pool (global staging only)
+  int smem_stage;              // > 0: contacts are staged in shared memory (that many slots per warp, >= C.stride) instead
+                               // of the global per-warp scratch: the staged list never leaves the SM before it reaches the pool
 };
 
 template <bool kStats>
@@ -93,7 +96,9 @@ __global__ void __launch_bounds__(kOrdWarps * 32, FCLGPU_ORD_MINBLOCKS) collide_
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   const long long gwarp = (long long)blockIdx.x * kOrdWarps + (threadIdx.x >> 5);
-  fclgpu_contact* const stage = P.scratch ? P.scratch + gwarp * P.stride : nullptr;
+  fclgpu_contact* const stage =
+      Q.smem_stage > 0 ? reinterpret_cast<fclgpu_contact*>(smem_raw + sizeof(OrderedFront) * kOrdWarps) + (size_t)(threadIdx.x >> 5) * Q.smem_stage
+                       : (P.scratch ? P.scratch + gwarp * P.stride : nullptr);
   // a normal round adds at most 16 entries; the depth-first fallback at most depth_sum + 1 in total
   const int normal_limit = kOrdCap - (Q.depth_sum + 2) - 16;
   const bool coherent = P.ready != nullptr;
@@ -312,6 +317,14 @@ __global__ void __launch_bounds__(kOrdWarps * 32, FCLGPU_ORD_MINBLOCKS) collide_
         const int4* src = reinterpret_cast<const int4*>(stage);
         int4* dst = reinterpret_cast<int4*>(Q.pool + off);
         for (long long i = lane; i < stored * 4; i += 32) __stcs(dst + i, src[i]);
+        if (Q.discard_stage && Q.smem_stage == 0) {
+          // the staged copy is dead now: drop its L2 lines instead of letting them be written back to HBM some day
+          // (discard.global.L2 leaves the contents undetermined; the warp's next query rewrites them before reading)
+          __syncwarp();
+          const char* base = reinterpret_cast<const char*>(stage);
+          const long long lines = (stored * (long long)sizeof(fclgpu_contact)) / 128;  // whole 128-byte lines only
+          for (long long l = lane; l < lines; l += 32) asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + 128 * l) : "memory");
+        }
       }
     }
     __syncwarp();

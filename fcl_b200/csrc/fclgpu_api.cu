@@ -77,6 +77,11 @@ std::map<std::string, long long> g_opts = {
     // (contact_offsets[i] = start of query i's block); 1 = blocks in query order (contact_offsets = exclusive prefix sum
     // of num_contacts): per-query scratch + scan + compaction passes around the lane-per-query kernels
     {"contact_order", 0},
+    // ordered-front path, both measured and left off: discard the L2 lines of the contact staging once a
+    // query's list is in the pool (DRAM writes 2.11 -> 2.05 GB per 1M queries, time unchanged); stage short lists in
+    // shared memory instead of the global per-warp scratch (DRAM writes 2.04 GB, but the smaller L1 costs 1.7 %)
+    {"contact_discard", 0},
+    {"contact_smem_stage", 0},
     {"scratch_bytes", 2ll << 30},
     {"blocks_per_sm", 0},      // 0 = occupancy query
     {"stats", 1},
@@ -950,12 +955,24 @@ int collide_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, c
     // Contact list, default path: ONE launch of the warp-per-query ordered-front kernel (collide_ordered.cuh).
     // Contacts are staged per RESIDENT WARP (L2-resident) and appended to the caller's pool when a query retires.
     const long long stride = std::min<long long>(request->num_max_contacts, stage_capacity(request));
-    const size_t smem = sizeof(OrderedFront) * kOrdWarps;
+    size_t smem = sizeof(OrderedFront) * kOrdWarps;
     auto kern = stats ? collide_ordered_kernel<true> : collide_ordered_kernel<false>;
+    // short lists (the usual num_max_contacts <= ~100) are staged in shared memory when that does not cost a resident block
+    int smem_stage = 0;
     int per_sm = (int)opt("blocks_per_sm");
     if (per_sm <= 0) {
       CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kOrdWarps * 32, smem));
       if (per_sm < 1) per_sm = 1;
+      const size_t with_stage = smem + (size_t)kOrdWarps * (size_t)stride * sizeof(fclgpu_contact);
+      if (opt("contact_smem_stage") && contacts != nullptr && with_stage <= 100 * 1024) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_stage));
+        int per_sm2 = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, kern, kOrdWarps * 32, with_stage));
+        if (per_sm2 >= per_sm) {
+          smem = with_stage;
+          smem_stage = (int)stride;
+        }
+      }
     }
     const long long warps = (long long)w->sm_count * per_sm * kOrdWarps;
     rc = ensure(&w->scratch, &w->scratch_bytes, (size_t)(warps * stride) * sizeof(fclgpu_contact));
@@ -986,6 +1003,9 @@ int collide_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, c
     Q.cursor = (unsigned long long*)ss.cursor;
     Q.starts = (long long*)contact_offsets;
     Q.depth_sum = m1->depth + m2->depth;
+    Q.smem_stage = smem_stage;
+    // (the per-warp staging block must start on a 128-byte line: stride * 64 bytes per warp)
+    Q.discard_stage = (opt("contact_discard") && stride % 2 == 0) ? 1 : 0;
     kern<<<(unsigned)(w->sm_count * per_sm), kOrdWarps * 32, smem, st>>>(Q);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
