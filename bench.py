@@ -9,7 +9,8 @@ line rank 0 prints) is BASELINE configs[1]: env.obj vs rob.obj distance() with n
 With the default --workload all the same line carries, under "workloads", the other env/rob configurations measured
 the same way: cfg1 (collide, binary verdict, at its real size of 10k poses and at 1M), cfg3 (contacts, max 100).
 cfg4 (7-link arm vs 200k-triangle scene) and cfg5 (two 1M-triangle meshes: collide, distance, tolerance
-verification) are separate invocations (--workload cfg4 | cfg5, --scaling weak|strong).
+verification) ride along at reduced sizes (250k configurations / 100k poses per GPU; --no-big skips them) and are
+separate invocations at any size (--workload cfg4 | cfg5 --poses N, --scaling weak|strong).
 
 Roofline: per workload, the bound is the SLOWER of
   fp64 : executed mul+add+cmp of the reference's sequential traversal (instrumented oracle, oracle/fcl_oracle_counted.cpp)
@@ -707,6 +708,7 @@ def main():
     ap.add_argument("--traversal", type=int, default=3, help="kernel variant (fclgpu option 'traversal', see DESIGN.md)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-big", action="store_true", help="--workload all: skip the reduced cfg4 / cfg5 legs")
     ap.add_argument("--opt", action="append", default=[], help="name=value library option (A/B runs; recorded in config)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -771,6 +773,23 @@ def main():
         steps = args.steps if wl == head else max(3, min(args.steps, 10))
         results[wl] = run_env_rob(ctx, wl, n, steps, args.warmup, (env, rob), meshes, with_cpu)
     clocks = sampler.stop()
+    if args.workload == "all" and not args.no_big:
+        # BASELINE configs[3] and [4] in the same line, at sizes that keep the default run short (their own invocations,
+        # --workload cfg4 | cfg5, take --poses): 250k robot configurations (1.75M link queries) / 100k poses per GPU
+        import copy
+
+        import bench_big
+
+        keep = ("value", "unit", "ms_per_step", "e2e", "roofline", "cpu_baseline", "gpu_launches", "config", "workloads", "clocks")
+        for which, poses in (("cfg4", 250_000), ("cfg5", 100_000)):
+            a2 = copy.copy(args)
+            a2.poses = poses // world if args.scaling == "strong" else poses
+            a2.steps = max(3, min(args.steps, 5))
+            ctx.args = a2
+            big = bench_big.run(ctx, which)
+            ctx.args = args
+            if rank == 0 and big is not None:
+                results[which] = {k: big[k] for k in keep if k in big}
     if rank == 0:
         h = results[head]
         line = {
