@@ -34,7 +34,7 @@ def make_mesh():
 while time.time() < t_end:
     (v1, t1), (v2, t2) = make_mesh(), make_mesh()
     split = int(rng.integers(0, 3))
-    on_dev = bool(rng.integers(0, 2)) and split != 1
+    on_dev = bool(rng.integers(0, 2))  # all three split rules build on the device
     m1 = F.BVHModel.from_arrays(v1, t1, split, build_on_device=on_dev)
     m2 = F.BVHModel.from_arrays(v2, t2, split)
     o1, o2 = O.Model(v1, t1, split), O.Model(v2, t2, split)
@@ -113,6 +113,45 @@ while time.time() < t_end:
     sep = bs["min_distance"] > 0
     if sep.any():
         ok = ok and bool((np.abs(ds.nearest_p1[sep] - bs["p1"][sep]) <= 1e-6 * (np.abs(bs["p1"][sep]).max() + 1.0)).all())
+    # continuous collision (translating bodies, conservative advancement): verdict, time of contact, traversal count and
+    # contact poses bit-identical
+    if rng.integers(0, 2) == 0:
+        nc = min(n, 1500)
+        E1 = P1[:nc].copy()
+        E1[:, 9:] += rng.normal(0, 0.5 * ext, size=(nc, 3))
+        B0 = P2[:nc] if P2 is not None else None
+        B1 = None
+        if B0 is not None:
+            B1 = B0.copy()
+            B1[:, 9:] += rng.normal(0, 0.2 * ext, size=(nc, 3))
+        rc_ = O.continuous_collide_translation_batch(o1, o2, P1[:nc], E1, B0, B1, nthreads=8)
+        gc_ = F.continuous_collide_batch(m1, P1[:nc], E1, m2, B0, B1, F.ContinuousCollisionRequest(ccd_solver_type=F.CCDC_CONSERVATIVE_ADVANCEMENT))
+        ok = ok and np.array_equal(gc_.is_collide, rc_["is_collide"]) and gc_.time_of_contact.tobytes() == rc_["time_of_contact"].tobytes()
+        ok = ok and np.array_equal(gc_.iterations, rc_["iterations"]) and gc_.contact_tf1.tobytes() == rc_["contact_tf1"].tobytes()
+        ok = ok and gc_.contact_tf2.tobytes() == rc_["contact_tf2"].tobytes()
+        checks += nc
+    # bottom-up refit (the reference's default endReplaceModel()): device records = oracle's, then collide with the
+    # exact box test (the merged boxes need not contain their subtrees, so only the same test visits the same nodes)
+    if ok and rng.integers(0, 3) == 0:
+        vn = v1 + rng.normal(0, 0.02, size=v1.shape)
+        o1.refit_bottomup(vn)
+        m1.device_model()
+        if not (m1.beginReplaceModel() == 0 and m1.replaceSubModel(vn) == 0 and m1.endReplaceModel() == 0):
+            print("REFIT PROTOCOL ERROR", tag)
+            sys.exit(4)
+        a, b = m1.download_device_arrays(), o1.arrays()
+        bad = [k for k in ("axis", "obb_To", "obb_ext", "rss_axis", "rss_To", "rss_l", "rss_r") if a[k].tobytes() != b[k].tobytes()]
+        if bad:
+            print("BOTTOM-UP REFIT MISMATCH", tag, bad)
+            np.savez("gpurun_out/stress_fail_refit.npz", v=v1, t=t1, vn=vn, split=split)
+            sys.exit(5)
+        _capi.set_option("traversal", 1)
+        nr = min(n, 2000)
+        ref2 = O.collide_batch(o1, o2, P1[:nr], None if P2 is None else P2[:nr], mx, True, nthreads=8)
+        got2 = F.collide_batch(m1, P1[:nr], m2, None if P2 is None else P2[:nr], F.CollisionRequest(mx, True), contact_capacity=max(64 * nr, 1024),
+                               grow_on_overflow=True)
+        ok = ok and np.array_equal(got2.num_contacts, ref2["counts"]) and got2.contacts.tobytes() == ref2["contacts"].tobytes()
+        checks += nr
     rounds += 1
     checks += 5 * n
     if not ok:
