@@ -567,6 +567,20 @@ def run_env_rob(ctx, wl, n, steps, warmup, models, meshes, with_cpu):
             d2h = n * 4
         e2e = {"value": world * n * steps / dt, "unit": UNIT, "h2d_bytes_per_step": n * 96, "d2h_bytes_per_step": d2h,
                "note": "per-rank host buffers; at N > 1 every rank runs its shard through the host API concurrently"}
+        if wl == "contacts" and world == 1:
+            # the same lists in the compact record formats (extension, include/fclgpu.h): the copy back is the long pole
+            for name, fmt, rec in (("ids", F.CONTACT_IDS, 8), ("f32", F.CONTACT_F32, 40)):
+                def step_c():
+                    return F.collide_batch(env, hp, rob, None, creq, contact_capacity=40 * n, device=local, pinned=True, contact_format=fmt).num_contacts
+                step_c()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                reps = max(2, steps // 2)
+                for _ in range(reps):
+                    step_c()
+                torch.cuda.synchronize()
+                e2e["compact_" + name] = {"value": n * reps / (time.perf_counter() - t0), "unit": UNIT, "record_bytes": rec,
+                                          "d2h_bytes_per_step": n * 4 + (n + 1) * 8 + int(ncon.sum()) * rec}
     if rank != 0:
         return None
 

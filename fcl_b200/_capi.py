@@ -30,6 +30,11 @@ CONTACT_DTYPE = np.dtype(
     [("b1", "<i4"), ("b2", "<i4"), ("normal", "<f8", (3,)), ("pos", "<f8", (3,)), ("penetration_depth", "<f8")]
 )
 assert CONTACT_DTYPE.itemsize == 64
+# compact records (include/fclgpu.h: fclgpu_contact_ids, fclgpu_contact_f32)
+CONTACT_IDS_DTYPE = np.dtype([("b1", np.int32), ("b2", np.int32)])
+CONTACT_F32_DTYPE = np.dtype([("b1", np.int32), ("b2", np.int32), ("normal", np.float32, 3), ("pos", np.float32, 3),
+                              ("penetration_depth", np.float32), ("reserved", np.float32)])
+assert CONTACT_IDS_DTYPE.itemsize == 8 and CONTACT_F32_DTYPE.itemsize == 40
 
 
 class ContinuousRequestC(C.Structure):  # fclgpu_continuous_request
@@ -39,7 +44,7 @@ class ContinuousRequestC(C.Structure):  # fclgpu_continuous_request
 
 class CollisionRequestC(C.Structure):
     _fields_ = [("num_max_contacts", C.c_int64), ("enable_contact", C.c_int32), ("enable_cost", C.c_int32),
-                ("stage_capacity", C.c_int64)]
+                ("stage_capacity", C.c_int64), ("contact_format", C.c_int32), ("reserved", C.c_int32)]
 
 
 class DistanceRequestC(C.Structure):

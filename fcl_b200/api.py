@@ -18,7 +18,10 @@ import sys
 import numpy as np
 
 from . import _capi
-from ._capi import CONTACT_DTYPE, FclGpuError, check, addr
+from ._capi import CONTACT_DTYPE, CONTACT_F32_DTYPE, CONTACT_IDS_DTYPE, FclGpuError, check, addr
+
+CONTACT_FULL, CONTACT_IDS, CONTACT_F32 = 0, 1, 2
+CONTACT_DTYPES = {CONTACT_FULL: CONTACT_DTYPE, CONTACT_IDS: CONTACT_IDS_DTYPE, CONTACT_F32: CONTACT_F32_DTYPE}
 
 # BVHReturnCode (geometry/bvh/BVH_internal.h:61-72)
 BVH_OK = 0
@@ -509,9 +512,9 @@ class CollisionRequest:
     def isSatisfied(self, result):
         return (not self.enable_cost) and result.isCollision() and self.num_max_contacts <= result.numContacts()
 
-    def _c(self, stage_capacity=0):
+    def _c(self, stage_capacity=0, contact_format=0):
         return _capi.CollisionRequestC(int(min(self.num_max_contacts, 2**62)), int(bool(self.enable_contact)),
-                                       int(bool(self.enable_cost)), int(stage_capacity))
+                                       int(bool(self.enable_cost)), int(stage_capacity), int(contact_format), 0)
 
 
 class Contact:
@@ -688,10 +691,12 @@ class BatchDistanceResult:
 
 
 def collide_batch(o1, tf1, o2, tf2, request, contact_capacity=None, want_contacts=True, stats=False, device=None,
-                  grow_on_overflow=False, pinned=False, stage_capacity=0):
+                  grow_on_overflow=False, pinned=False, stage_capacity=0, contact_format=CONTACT_FULL):
     """Host arrays in, host arrays out (copies inside): n independent fcl::collide() calls.
 
-    tf1 / tf2: (n,12) float64 pose records, a Transform3, or None (identity)."""
+    tf1 / tf2: (n,12) float64 pose records, a Transform3, or None (identity).
+    contact_format (extension): CONTACT_FULL = the reference's 64-byte contacts; CONTACT_IDS = the two primitive ids only
+    (8 bytes); CONTACT_F32 = ids + single-precision normal / position / depth (40 bytes) -- same lists, same order."""
     tf1, n1 = _poses(tf1)
     tf2, n2 = _poses(tf2)
     n = n1 if n1 is not None else n2
@@ -700,7 +705,7 @@ def collide_batch(o1, tf1, o2, tf2, request, contact_capacity=None, want_contact
     if n1 is not None and n2 is not None and n1 != n2:
         raise ValueError("tf1 and tf2 must have the same length")
     m1, m2 = o1.device_model(device), o2.device_model(device)
-    req = request._c(stage_capacity)
+    req = request._c(stage_capacity, contact_format)
     keep = []
     counts, k = _out(n, np.int32, pinned, "counts")
     keep.append(k)
@@ -708,7 +713,7 @@ def collide_batch(o1, tf1, o2, tf2, request, contact_capacity=None, want_contact
         if contact_capacity is None:
             contact_capacity = int(min(max(request.num_max_contacts, 0), 64)) * n
         contact_capacity = max(int(contact_capacity), 1)
-        contacts, k = _out(contact_capacity, CONTACT_DTYPE, pinned, "contacts")
+        contacts, k = _out(contact_capacity, CONTACT_DTYPES[contact_format], pinned, "contacts%d" % contact_format)
         keep.append(k)
         offsets = np.zeros(n + 1, np.int64)
     else:
@@ -722,7 +727,7 @@ def collide_batch(o1, tf1, o2, tf2, request, contact_capacity=None, want_contact
         # counts are exact even when the pool / the per-query staging was too small: size both (per call) and rerun
         return collide_batch(o1, tf1, o2, tf2, request, contact_capacity=int(counts.sum(dtype=np.int64)),
                              want_contacts=True, stats=stats, device=device, grow_on_overflow=False,
-                             stage_capacity=max(int(counts.max()), 1))
+                             stage_capacity=max(int(counts.max()), 1), contact_format=contact_format)
     check(rc)
     if want_contacts:
         contacts = contacts[: offsets[n]]

@@ -83,6 +83,7 @@ struct OrderedParams {
   unsigned long long* cursor;  // running number of contacts appended to the pool
   long long* starts;           // [n] start of query i's block in the pool (or nullptr)
   int depth_sum;               // depth(model1) + depth(model2)
+  int format;                  // FCLGPU_CONTACT_*: layout of the pool records (the staging always holds full records)
   int discard_stage;           // drop the staging lines from the L2 after the copy to the pool (global staging only)
   int smem_stage;              // > 0: contacts are staged in shared memory (that many slots per warp, >= C.stride) instead
                                // of the global per-warp scratch: the staged list never leaves the SM before it reaches the pool
@@ -314,9 +315,26 @@ __global__ void __launch_bounds__(kOrdWarps * 32, FCLGPU_ORD_MINBLOCKS) collide_
         }
         // the pool is written once and never read by this kernel: streaming stores (evict first), so that the 2 GB
         // passing through do not push the staging lines -- which ARE re-read and overwritten -- out of the L2
+        if (Q.format == FCLGPU_CONTACT_IDS) {
+          uint2* dst = reinterpret_cast<uint2*>(Q.pool) + off;
+          for (long long i = lane; i < stored; i += 32) __stcs(dst + i, make_uint2((unsigned)stage[i].b1, (unsigned)stage[i].b2));
+        } else if (Q.format == FCLGPU_CONTACT_F32) {
+          // 40-byte records = 5 x 8 bytes; one lane per record
+          float2* dst = reinterpret_cast<float2*>(reinterpret_cast<fclgpu_contact_f32*>(Q.pool) + off);
+          for (long long i = lane; i < stored; i += 32) {
+            const fclgpu_contact c = stage[i];
+            float2* o = dst + 5 * i;
+            __stcs(o + 0, make_float2(__int_as_float(c.b1), __int_as_float(c.b2)));
+            __stcs(o + 1, make_float2((float)c.normal[0], (float)c.normal[1]));
+            __stcs(o + 2, make_float2((float)c.normal[2], (float)c.pos[0]));
+            __stcs(o + 3, make_float2((float)c.pos[1], (float)c.pos[2]));
+            __stcs(o + 4, make_float2((float)c.penetration_depth, 0.0f));
+          }
+        } else {
         const int4* src = reinterpret_cast<const int4*>(stage);
         int4* dst = reinterpret_cast<int4*>(Q.pool + off);
         for (long long i = lane; i < stored * 4; i += 32) __stcs(dst + i, src[i]);
+        }
         if (Q.discard_stage && Q.smem_stage == 0) {
           // the staged copy is dead now: drop its L2 lines instead of letting them be written back to HBM some day
           // (discard.global.L2 leaves the contents undetermined; the warp's next query rewrites them before reading)

@@ -891,6 +891,10 @@ unsigned long long* next_counter(Workspace* w, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------
 namespace {
 // Hidden knobs of the host wrappers around collide_enqueue.
+size_t contact_record_bytes(const fclgpu_collision_request* r) {
+  return r->contact_format == FCLGPU_CONTACT_IDS ? sizeof(fclgpu_contact_ids)
+         : r->contact_format == FCLGPU_CONTACT_F32 ? sizeof(fclgpu_contact_f32) : sizeof(fclgpu_contact);
+}
 long long stage_capacity(const fclgpu_collision_request* r) {
   return r->stage_capacity > 0 ? (long long)r->stage_capacity : std::max<long long>(1, opt("contact_stride"));
 }
@@ -950,6 +954,10 @@ int collide_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, c
   const bool stats = (n_bv || n_leaf);
   const StreamState ss = stream_state(w, st);
   const long long trav0 = opt("traversal");
+  if (request->contact_format < FCLGPU_CONTACT_FULL || request->contact_format > FCLGPU_CONTACT_F32)
+    return fail(FCLGPU_ERR_INVALID_ARGUMENT, "unknown contact_format %d", request->contact_format);
+  if (request->contact_format != FCLGPU_CONTACT_FULL && contacts != nullptr && !(trav0 >= 3 && !opt("contact_order") && !shape2))
+    return fail(FCLGPU_ERR_UNSUPPORTED_FUNCTION, "compact contact records are written by the default mesh-mesh contact path only");
 
   if (want_contacts && trav0 >= 3 && !opt("contact_order") && !shape2) {
     // Contact list, default path: ONE launch of the warp-per-query ordered-front kernel (collide_ordered.cuh).
@@ -1004,6 +1012,7 @@ int collide_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, c
     Q.starts = (long long*)contact_offsets;
     Q.depth_sum = m1->depth + m2->depth;
     Q.smem_stage = smem_stage;
+    Q.format = request->contact_format;
     // (the per-warp staging block must start on a 128-byte line: stride * 64 bytes per warp)
     Q.discard_stage = (opt("contact_discard") && stride % 2 == 0) ? 1 : 0;
     kern<<<(unsigned)(w->sm_count * per_sm), kOrdWarps * 32, smem, st>>>(Q);
@@ -1340,7 +1349,7 @@ extern "C" int fclgpu_continuous_collide_batch(const fclgpu_model* m1, const fcl
     return fail(FCLGPU_ERR_STACK_OVERFLOW, "tree depths %d+%d exceed the traversal stack", m1->depth, m2->depth);
   if (n == 0) return FCLGPU_OK;
   // conservativeAdvancementMeshOriented starts with collide() at the start configuration (default CollisionRequest)
-  fclgpu_collision_request cr{1, 0, 0, 0};
+  fclgpu_collision_request cr{1, 0, 0, 0, 0, 0};
   int rc = collide_enqueue(m1, m2, n, tf1_beg, tf2_beg, &cr, is_collide, nullptr, 0, nullptr, nullptr, nullptr, stream, CollideExtra{});
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1432,6 +1441,7 @@ extern "C" int fclgpu_collide_batch_host(const fclgpu_model* m1, const fclgpu_mo
   std::lock_guard<std::mutex> host_lock(w->host_mu);
   const bool want = contacts != nullptr || contact_offsets != nullptr;
   if (contacts == nullptr) contact_capacity = 0;
+  const size_t rec = contact_record_bytes(request);  // bytes per record of `contacts` (fclgpu_collision_request::contact_format)
   if (!want && n > 0) {
     // Counts / verdicts only.  ONE persistent launch over the whole batch on the compute stream while the copy
     // stream brings the poses up chunk by chunk; behind every chunk it writes ready[c] (a 4-byte DMA from a pinned
@@ -1492,7 +1502,7 @@ extern "C" int fclgpu_collide_batch_host(const fclgpu_model* m1, const fclgpu_mo
     const int64_t C = 1ll << shift;
     const int nsub = (int)((n + C - 1) / C);
     const size_t bytes = (tf1 ? padded(96 * (size_t)n) : 0) + (tf2 ? padded(96 * (size_t)n) : 0) + padded(4 * (size_t)n) +
-                         padded(8 * (size_t)(n + 1)) + padded(64 * (size_t)contact_capacity) +
+                         padded(8 * (size_t)(n + 1)) + padded(rec * (size_t)contact_capacity) +
                          (n_bv ? padded(4 * (size_t)n) : 0) + (n_leaf ? padded(4 * (size_t)n) : 0) + 256;
     {
       std::lock_guard<std::mutex> lock(w->mu);
@@ -1504,7 +1514,7 @@ extern "C" int fclgpu_collide_batch_host(const fclgpu_model* m1, const fclgpu_mo
     double* d_tf2 = tf2 ? B.take<double>(12 * (size_t)n) : nullptr;
     int32_t* d_cnt = B.take<int32_t>((size_t)n);
     int64_t* d_off = B.take<int64_t>((size_t)n + 1);
-    fclgpu_contact* d_con = contact_capacity > 0 ? B.take<fclgpu_contact>((size_t)contact_capacity) : nullptr;
+    fclgpu_contact* d_con = contact_capacity > 0 ? reinterpret_cast<fclgpu_contact*>(B.take<char>(rec * (size_t)contact_capacity)) : nullptr;
     uint32_t* d_bv = n_bv ? B.take<uint32_t>((size_t)n) : nullptr;
     uint32_t* d_leaf = n_leaf ? B.take<uint32_t>((size_t)n) : nullptr;
     cudaStream_t copy = w->pipe[0], compute = w->pipe[1];
@@ -1528,7 +1538,8 @@ extern "C" int fclgpu_collide_batch_host(const fclgpu_model* m1, const fclgpu_mo
       CUDA_TRY(cudaEventSynchronize(w->ev[k & 1]));
       const int64_t upto = std::min<int64_t>(w->host_totals[k], contact_capacity);
       if (contacts && upto > done)
-        CUDA_TRY(cudaMemcpyAsync(contacts + done, d_con + done, 64 * (size_t)(upto - done), cudaMemcpyDeviceToHost, copy));
+        CUDA_TRY(cudaMemcpyAsync((char*)contacts + rec * (size_t)done, (const char*)d_con + rec * (size_t)done, rec * (size_t)(upto - done),
+                                 cudaMemcpyDeviceToHost, copy));
       done = std::max(done, upto);
       return 0;
     };
@@ -1560,7 +1571,7 @@ extern "C" int fclgpu_collide_batch_host(const fclgpu_model* m1, const fclgpu_mo
     return finish_pipeline(w, m1->device);
   }
   size_t bytes = (tf1 ? padded(96 * (size_t)n) : 0) + (tf2 ? padded(96 * (size_t)n) : 0) + padded(4 * (size_t)n) +
-                 (want ? padded(8 * (size_t)(n + 1)) + padded(64 * (size_t)contact_capacity) : 0) +
+                 (want ? padded(8 * (size_t)(n + 1)) + padded(rec * (size_t)contact_capacity) : 0) +
                  (n_bv ? padded(4 * (size_t)n) : 0) + (n_leaf ? padded(4 * (size_t)n) : 0) + 256;
   {
     std::lock_guard<std::mutex> lock(w->mu);
@@ -1572,7 +1583,7 @@ extern "C" int fclgpu_collide_batch_host(const fclgpu_model* m1, const fclgpu_mo
   double* d_tf2 = tf2 ? B.take<double>(12 * (size_t)n) : nullptr;
   int32_t* d_cnt = B.take<int32_t>((size_t)n);
   int64_t* d_off = want ? B.take<int64_t>((size_t)n + 1) : nullptr;
-  fclgpu_contact* d_con = (want && contact_capacity > 0) ? B.take<fclgpu_contact>((size_t)contact_capacity) : nullptr;
+  fclgpu_contact* d_con = (want && contact_capacity > 0) ? reinterpret_cast<fclgpu_contact*>(B.take<char>(rec * (size_t)contact_capacity)) : nullptr;
   uint32_t* d_bv = n_bv ? B.take<uint32_t>((size_t)n) : nullptr;
   uint32_t* d_leaf = n_leaf ? B.take<uint32_t>((size_t)n) : nullptr;
   cudaStream_t st = 0;
@@ -1588,7 +1599,7 @@ extern "C" int fclgpu_collide_batch_host(const fclgpu_model* m1, const fclgpu_mo
     if (contact_offsets) CUDA_TRY(cudaMemcpyAsync(contact_offsets, d_off, 8 * (size_t)(n + 1), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpy(&total, d_off + n, 8, cudaMemcpyDeviceToHost));
     if (contacts && total > 0)
-      CUDA_TRY(cudaMemcpyAsync(contacts, d_con, 64 * (size_t)std::min<int64_t>(total, contact_capacity),
+      CUDA_TRY(cudaMemcpyAsync(contacts, d_con, rec * (size_t)std::min<int64_t>(total, contact_capacity),
                                cudaMemcpyDeviceToHost, st));
   } else if (contact_offsets) {
     std::memset(contact_offsets, 0, 8 * (size_t)(n + 1));

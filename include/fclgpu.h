@@ -33,7 +33,8 @@
 extern "C" {
 #endif
 
-#define FCLGPU_ABI_VERSION 2 /* 2: contact_offsets[i] = start of query i's block (order of the blocks: see below) */
+#define FCLGPU_ABI_VERSION 3 /* 2: contact_offsets[i] = start of query i's block (order of the blocks: see below);
+                               * 3: fclgpu_collision_request::contact_format (compact contact records) */
 
 /* Status codes.  -1..-8 mirror the reference's BVHReturnCode
  * (include/fcl/geometry/bvh/BVH_internal.h:61-72). */
@@ -73,6 +74,25 @@ typedef struct fclgpu_contact {
   double penetration_depth;
 } fclgpu_contact;
 
+/* Compact contact records (not in the reference; fclgpu_collision_request::contact_format).  A contact list of the
+ * full 64-byte records is 2 GB per million queries at 32 contacts each, and the copy to the host then takes twice as
+ * long as the traversal; a caller that only needs WHICH triangles touch, or single-precision geometry, asks for these:
+ *   FCLGPU_CONTACT_IDS  8 bytes: the two primitive ids;
+ *   FCLGPU_CONTACT_F32 40 bytes: ids + normal, position and depth rounded to nearest float from the same FP64 values.
+ * Same lists, same order, same truncation as the full records.  Supported by fclgpu_collide_batch[_host] on its default
+ * (one-launch) contact path; elsewhere a format other than FULL returns FCLGPU_ERR_UNSUPPORTED_FUNCTION. */
+enum { FCLGPU_CONTACT_FULL = 0, FCLGPU_CONTACT_IDS = 1, FCLGPU_CONTACT_F32 = 2 };
+typedef struct fclgpu_contact_ids {
+  int32_t b1, b2;
+} fclgpu_contact_ids;
+typedef struct fclgpu_contact_f32 {
+  int32_t b1, b2;
+  float normal[3];
+  float pos[3];
+  float penetration_depth;
+  float reserved;
+} fclgpu_contact_f32;
+
 /* Honoured fields of fcl::CollisionRequest (include/fcl/narrowphase/collision_request.h:52-106).
  * enable_cost must be 0 (cost sources are not on this path: FCLGPU_ERR_UNSUPPORTED_FUNCTION). */
 typedef struct fclgpu_collision_request {
@@ -84,6 +104,10 @@ typedef struct fclgpu_collision_request {
    * min(num_max_contacts, stage_capacity) reports FCLGPU_ERR_CONTACT_OVERFLOW (counts stay exact): rerun with
    * stage_capacity = max(num_contacts).  Per call, so concurrent callers do not share a setting. */
   int64_t stage_capacity;
+  /* Not an fcl::CollisionRequest field either: layout of the records written to `contacts` (FCLGPU_CONTACT_*; 0 = the
+   * full fclgpu_contact).  `contacts` then points to contact_capacity records of that format. */
+  int32_t contact_format;
+  int32_t reserved;
 } fclgpu_collision_request;
 
 /* Honoured fields of fcl::DistanceRequest (include/fcl/narrowphase/distance_request.h:52-113).

@@ -68,6 +68,36 @@ def test_cfg3_contacts_max100(models, oracle, traversal):
     assert (got.num_contacts == 100).sum() > 100  # truncation is exercised
 
 
+def test_compact_contact_records(models, oracle):
+    """fclgpu_collision_request::contact_format (extension): the same contact lists -- same order, same truncation -- as
+    8-byte id records or 40-byte single-precision records (the FP64 values rounded to nearest float)."""
+    (env, rob), (oenv, orob) = models
+    P = random_poses(6000, seed=17)
+    ref = oracle.collide_batch(oenv, orob, P, None, 100, True, nthreads=8)
+    full = F.collide_batch(env, P, rob, None, F.CollisionRequest(100, True), contact_capacity=100 * len(P))
+    assert full.contacts.tobytes() == ref["contacts"].tobytes()
+    for pinned in (False, True):
+        ids = F.collide_batch(env, P, rob, None, F.CollisionRequest(100, True), contact_capacity=100 * len(P), contact_format=F.CONTACT_IDS,
+                              pinned=pinned)
+        assert np.array_equal(ids.num_contacts, ref["counts"]) and np.array_equal(ids.offsets, ref["offsets"])
+        assert ids.contacts.dtype.itemsize == 8
+        assert np.array_equal(ids.contacts["b1"], ref["contacts"]["b1"]) and np.array_equal(ids.contacts["b2"], ref["contacts"]["b2"])
+        f32 = F.collide_batch(env, P, rob, None, F.CollisionRequest(100, True), contact_capacity=100 * len(P), contact_format=F.CONTACT_F32,
+                              pinned=pinned)
+        c = f32.contacts
+        assert c.dtype.itemsize == 40 and np.array_equal(f32.num_contacts, ref["counts"])
+        assert np.array_equal(c["b1"], ref["contacts"]["b1"]) and np.array_equal(c["b2"], ref["contacts"]["b2"])
+        for k, rk in (("normal", "normal"), ("pos", "pos"), ("penetration_depth", "depth")):
+            assert c[k].tobytes() == ref["contacts"][rk].astype(np.float32).tobytes(), k
+    # the other contact paths do not write compact records
+    _capi.set_option("contact_order", 1)
+    try:
+        with pytest.raises(F.FclGpuError):
+            F.collide_batch(env, P[:10], rob, None, F.CollisionRequest(100, True), contact_capacity=1000, contact_format=F.CONTACT_IDS)
+    finally:
+        _capi.set_option("contact_order", 0)
+
+
 def test_exhaustive_contact_pair_sets(models, oracle, traversal):
     (env, rob), (oenv, orob) = models
     P = random_poses(4000, seed=8)

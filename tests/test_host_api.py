@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for s in sorted(declared):
         assert hasattr(L, s), f"libfclgpu.so does not export {s}"
     assert declared == set(_capi.SYMBOLS)
-    assert L.fclgpu_abi_version() == 2
+    assert L.fclgpu_abi_version() == 3
 
 
 def test_build_protocol_and_return_codes(capfd):
