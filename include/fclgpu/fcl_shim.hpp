@@ -109,6 +109,14 @@ class DeviceModel {
     check(fclgpu_model_refit_topdown(h_, v.data(), host_->num_vertices, 0, nullptr));
     check(fclgpu_sync_status(fclgpu_model_device(h_), nullptr));
   }
+  // endReplaceModel() with its default arguments (refit = true, bottomup = true) on the device copy
+  void refit_bottomup() {
+    std::vector<double> v(3 * (std::size_t)host_->num_vertices);
+    for (int i = 0; i < host_->num_vertices; ++i)
+      for (int c = 0; c < 3; ++c) v[3 * (std::size_t)i + c] = host_->vertices[i][c];
+    check(fclgpu_model_refit_bottomup(h_, v.data(), host_->num_vertices, 0, nullptr));
+    check(fclgpu_sync_status(fclgpu_model_device(h_), nullptr));
+  }
 
  private:
   const BVH* host_;
@@ -290,6 +298,48 @@ inline void distance(const DeviceModel& o1, const std::vector<fcl::Transform3<do
 // unmodified single-query callers work.  Device copies of the models come from a process-wide cache keyed by the host
 // model's address (upload on first use; evict() when a model is rebuilt or destroyed).
 // ---------------------------------------------------------------------------------------------------------------------
+// n independent fcl::continuousCollide(o1, tf1_beg[i], tf1_end[i], o2, tf2_beg[i], tf2_end[i], request, results[i]) calls
+// (narrowphase/continuous_collision-inl.h:441-452).  Built: ccd_motion_type = CCDM_TRANS with ccd_solver_type =
+// CCDC_CONSERVATIVE_ADVANCEMENT; other settings throw (the C ABI answers FCLGPU_ERR_UNSUPPORTED_FUNCTION).
+inline void from_pose(const double* p, fcl::Transform3<double>& tf) {
+  tf = fcl::Transform3<double>::Identity();
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) tf.linear()(r, c) = p[3 * r + c];
+    tf.translation()[r] = p[9 + r];
+  }
+}
+inline void continuous_collide(const DeviceModel& o1, const std::vector<fcl::Transform3<double>>& tf1_beg,
+                               const std::vector<fcl::Transform3<double>>& tf1_end, const DeviceModel& o2,
+                               const std::vector<fcl::Transform3<double>>& tf2_beg, const std::vector<fcl::Transform3<double>>& tf2_end,
+                               const fcl::ContinuousCollisionRequest<double>& request,
+                               std::vector<fcl::ContinuousCollisionResult<double>>& results) {
+  const std::size_t n = tf1_beg.size();
+  same_size(n, tf1_end.size());
+  same_size(n, tf2_beg.size());
+  same_size(n, tf2_end.size());
+  std::vector<double> p(4 * 12 * n), toc(n), c1(12 * n), c2(12 * n);
+  std::vector<int32_t> hit(n);
+  for (std::size_t i = 0; i < n; ++i) {
+    to_pose(tf1_beg[i], &p[12 * i]);
+    to_pose(tf1_end[i], &p[12 * (n + i)]);
+    to_pose(tf2_beg[i], &p[12 * (2 * n + i)]);
+    to_pose(tf2_end[i], &p[12 * (3 * n + i)]);
+  }
+  fclgpu_continuous_request req{(int64_t)request.num_max_iterations, request.toc_err, (int32_t)request.ccd_motion_type,
+                                (int32_t)request.gjk_solver_type, (int32_t)request.ccd_solver_type};
+  check(fclgpu_continuous_collide_batch_host(o1.handle(), o2.handle(), (int64_t)n, &p[0], &p[12 * n], &p[24 * n], &p[36 * n], &req,
+                                             hit.data(), toc.data(), c1.data(), c2.data(), nullptr));
+  results.assign(n, fcl::ContinuousCollisionResult<double>());
+  for (std::size_t i = 0; i < n; ++i) {
+    results[i].is_collide = hit[i] != 0;
+    results[i].time_of_contact = toc[i];
+    if (hit[i]) {  // the reference sets the contact transforms only when there is a contact
+      from_pose(&c1[12 * i], results[i].contact_tf1);
+      from_pose(&c2[12 * i], results[i].contact_tf2);
+    }
+  }
+}
+
 class ModelCache {
  public:
   DeviceModel& get(const BVH* m, int device = 0) {

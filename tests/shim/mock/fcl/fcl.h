@@ -55,6 +55,17 @@ struct Transform3 {
       for (int c = 0; c < 3; ++c) m16[4 * c + r] = row_major9[3 * r + c];
   }
   void setTranslation(S x, S y, S z) { m16[12] = x; m16[13] = y; m16[14] = z; }
+  // writable views like Eigen's tf.linear()(r, c) and tf.translation()[k] (column-major 4x4 storage)
+  struct LinearRef {
+    S* p;
+    S& operator()(int r, int c) { return p[4 * c + r]; }
+  };
+  struct TranslationRef {
+    S* p;
+    S& operator[](int k) { return p[12 + k]; }
+  };
+  LinearRef linear() { return LinearRef{m16}; }
+  TranslationRef translation() { return TranslationRef{m16}; }
 };
 
 template <typename S>
@@ -164,6 +175,28 @@ template <typename S>
 bool CollisionRequest<S>::isSatisfied(const CollisionResult<S>& result) const {
   return (!enable_cost) && result.isCollision() && (num_max_contacts <= result.numContacts());
 }
+
+// narrowphase/continuous_collision_request.h:48-80, continuous_collision_result.h
+enum CCDMotionType { CCDM_TRANS, CCDM_LINEAR, CCDM_SCREW, CCDM_SPLINE };
+enum CCDSolverType { CCDC_NAIVE, CCDC_CONSERVATIVE_ADVANCEMENT, CCDC_RAY_SHOOTING, CCDC_POLYNOMIAL_SOLVER };
+enum GJKSolverType { GST_LIBCCD, GST_INDEP };
+template <typename S>
+struct ContinuousCollisionRequest {
+  std::size_t num_max_iterations;
+  S toc_err;
+  CCDMotionType ccd_motion_type;
+  GJKSolverType gjk_solver_type;
+  CCDSolverType ccd_solver_type;
+  ContinuousCollisionRequest(std::size_t it = 10, S err = 0.0001, CCDMotionType m = CCDM_TRANS, GJKSolverType g = GST_LIBCCD,
+                             CCDSolverType c = CCDC_NAIVE)
+      : num_max_iterations(it), toc_err(err), ccd_motion_type(m), gjk_solver_type(g), ccd_solver_type(c) {}
+};
+template <typename S>
+struct ContinuousCollisionResult {
+  bool is_collide = false;
+  S time_of_contact = 1.0;
+  Transform3<S> contact_tf1, contact_tf2;
+};
 
 template <typename S>
 struct DistanceResult;

@@ -117,6 +117,46 @@ int main(int argc, char** argv) {
   std::vector<int32_t> i1(n), i2(n);
   fclgpu::check(fclgpu_distance_batch_host(g1, g2, n, nullptr, p2.data(), &dreq, dist.data(), q1.data(), q2.data(), i1.data(), i2.data(), nullptr, nullptr));
 
+  // continuous collision (both bodies translating): shim against the C ABI
+  {
+    std::vector<fcl::Transform3<double>> end1(tf1), end2(tf2);
+    std::vector<double> pe1(12 * (size_t)n), pe2(12 * (size_t)n), pb1(12 * (size_t)n);
+    for (int i = 0; i < n; ++i) {
+      end1[i].setTranslation(0.3 * (rnd() - 0.5), 0.3 * (rnd() - 0.5), 0.3 * (rnd() - 0.5));
+      end2[i].setTranslation(tf2[i].m16[12] + 2.0 * (rnd() - 0.5), tf2[i].m16[13] + 2.0 * (rnd() - 0.5), tf2[i].m16[14] + 2.0 * (rnd() - 0.5));
+      fclgpu_pose_from_colmajor4x4(tf1[i].m16, &pb1[12 * (size_t)i]);
+      fclgpu_pose_from_colmajor4x4(end1[i].m16, &pe1[12 * (size_t)i]);
+      fclgpu_pose_from_colmajor4x4(end2[i].m16, &pe2[12 * (size_t)i]);
+    }
+    fclgpu_continuous_request rq{10, 0.0001, FCLGPU_CCDM_TRANS, 0, FCLGPU_CCDC_CONSERVATIVE_ADVANCEMENT};
+    std::vector<int32_t> hit(n);
+    std::vector<double> toc(n), c2(12 * (size_t)n);
+    fclgpu::check(fclgpu_continuous_collide_batch_host(g1, g2, n, pb1.data(), pe1.data(), p2.data(), pe2.data(), &rq, hit.data(), toc.data(),
+                                                       nullptr, c2.data(), nullptr));
+    std::vector<fcl::ContinuousCollisionResult<double>> cc;
+    fclgpu::continuous_collide(d1, tf1, end1, d2, tf2, end2,
+                               fcl::ContinuousCollisionRequest<double>(10, 0.0001, fcl::CCDM_TRANS, fcl::GST_LIBCCD, fcl::CCDC_CONSERVATIVE_ADVANCEMENT), cc);
+    long long moving_hits = 0;
+    for (int i = 0; i < n; ++i) {
+      if (cc[i].is_collide != (hit[i] != 0) || cc[i].time_of_contact != toc[i]) { std::printf("FAIL continuous %d\n", i); return 1; }
+      if (hit[i] && toc[i] > 0) {
+        ++moving_hits;
+        double q[12];
+        fclgpu_pose_from_colmajor4x4(cc[i].contact_tf2.m16, q);
+        if (std::memcmp(q, &c2[12 * (size_t)i], sizeof q)) { std::printf("FAIL continuous contact pose %d\n", i); return 1; }
+      }
+    }
+    if (moving_hits == 0) { std::printf("FAIL: no contact found in motion\n"); return 1; }
+    bool threw = false;
+    try {
+      fclgpu::continuous_collide(d1, tf1, end1, d2, tf2, end2, fcl::ContinuousCollisionRequest<double>(), cc);  // CCDC_NAIVE: not built
+    } catch (const std::exception&) {
+      threw = true;
+    }
+    if (!threw) { std::printf("FAIL: unsupported continuous setting accepted\n"); return 1; }
+    std::printf("shim continuous collide OK: %lld contacts found in motion\n", moving_hits);
+  }
+
   // the same through the shim
   std::vector<fcl::CollisionResult<double>> cres;
   fclgpu::collide(d1, tf1, d2, tf2, fcl::CollisionRequest<double>(20, true), cres);
@@ -267,6 +307,19 @@ int main(int argc, char** argv) {
     fclgpu::check(fclgpu_bvh_get(b1, nullptr, nullptr, hostT.data(), nullptr, nullptr, nullptr, nullptr, nullptr));
     if (std::memcmp(devT.data(), hostT.data(), devT.size() * 8)) { std::printf("FAIL: shim refit differs from the host refit\n"); return 1; }
     std::printf("shim refit OK\n");
+    // bottom-up refit (FCL's default endReplaceModel()) through the shim against the host model's
+    d1.refit_bottomup();
+    fclgpu::check(fclgpu_bvh_refit_bottomup(b1, &m1.verts_[0].v[0], m1.num_vertices));
+    std::vector<double> devA(9 * (size_t)m1.getNumBVs()), hostA(9 * (size_t)m1.getNumBVs());
+    fclgpu::check(fclgpu_model_download_rss_axis(d1.handle(), devA.data()));
+    if (fclgpu_bvh_get_rss_axis(b1, hostA.data()) != 1) { std::printf("FAIL: host model has no separate RSS axes after the bottom-up refit\n"); return 1; }
+    fclgpu::check(fclgpu_model_download(d1.handle(), nullptr, devT.data(), nullptr, nullptr, nullptr, nullptr, nullptr));
+    fclgpu::check(fclgpu_bvh_get(b1, nullptr, nullptr, hostT.data(), nullptr, nullptr, nullptr, nullptr, nullptr));
+    if (std::memcmp(devA.data(), hostA.data(), devA.size() * 8) || std::memcmp(devT.data(), hostT.data(), devT.size() * 8)) {
+      std::printf("FAIL: shim bottom-up refit differs from the host refit\n");
+      return 1;
+    }
+    std::printf("shim bottom-up refit OK\n");
     fclgpu::uninstall<Solver>();
     if (fcl::getCollisionFunctionLookTable<Solver>().collision_matrix[fcl::BV_OBBRSS][fcl::BV_OBBRSS] != nullptr) { std::printf("FAIL: uninstall\n"); return 1; }
   }
