@@ -42,3 +42,26 @@ Q = F.random_poses(300, seed=6, extents=(-4, 4, -4, 4, 0.2, 1.5)) if "extents" i
 dd = F.distance_batch(big, None, rob, Q, F.DistanceRequest(True))
 cc = F.collide_batch(big, None, rob, Q, F.CollisionRequest(), want_contacts=False)
 print("big", float(np.nansum(dd.min_distance)), int(cc.num_contacts.sum()))
+# round 2: median split on the device, bottom-up refit, compact contact records, continuous collision, plane / halfspace,
+# tolerance verdicts, broadphase
+m = F.BVHModel.from_arrays(v, t, F.SPLIT_METHOD_MEDIAN, build_on_device=True)
+m.device_model()
+assert m.beginReplaceModel() == 0 and m.replaceSubModel(v * 1.01) == 0 and m.endReplaceModel() == 0  # bottom-up
+for fmt in (F.CONTACT_IDS, F.CONTACT_F32):
+    cf = F.collide_batch(env, P, rob, None, F.CollisionRequest(50, True), contact_capacity=50 * n, contact_format=fmt)
+    print("compact", fmt, int(cf.num_contacts.sum()))
+P1 = P.copy()
+P1[:, 9:] += 200.0
+cc2 = F.continuous_collide_batch(env, None, None, rob, P, P1, F.ContinuousCollisionRequest(ccd_solver_type=F.CCDC_CONSERVATIVE_ADVANCEMENT))
+print("continuous", int(cc2.is_collide.sum()), float(cc2.time_of_contact.sum()))
+hp = F.collide_mesh_plane_batch(env, None, F.Halfspace([0, 0, 1.0], 100.0), P, F.CollisionRequest(50, True), contact_capacity=50 * n)
+pp = F.collide_mesh_plane_batch(env, None, F.Plane([0, 0, 1.0], 100.0), P, F.CollisionRequest(50, True), contact_capacity=50 * n)
+print("halfspace / plane", int(hp.num_contacts.sum()), int(pp.num_contacts.sum()))
+w, _ = F.within_tolerance_batch(env, P, rob, None, 50.0)
+print("within tolerance", int(w.sum()))
+mgr1, mgr2 = F.NaiveCollisionManager(), F.NaiveCollisionManager()
+for i in range(40):
+    mgr1.registerObject(F.CollisionObject(env if i % 2 else rob, F.Transform3.from_pose12(P[i])))
+    mgr2.registerObject(F.CollisionObject(rob, F.Transform3.from_pose12(P[100 + i])))
+bp = mgr1.collide_batch(mgr2)
+print("broadphase pairs", len(bp.pairs))
