@@ -21,6 +21,7 @@
 #include "broadphase.cuh"
 #include "refit.cuh"
 #include "continuous.cuh"
+#include "query_order.cuh"
 
 using namespace fclgpu;
 
@@ -77,6 +78,10 @@ std::map<std::string, long long> g_opts = {
     // (contact_offsets[i] = start of query i's block); 1 = blocks in query order (contact_offsets = exclusive prefix sum
     // of num_contacts): per-query scratch + scan + compaction passes around the lane-per-query kernels
     {"contact_order", 0},
+    // evaluate the queries of a device-resident batch in a locality order (query_order.cuh) on the lane-per-query collide
+    // path: 0 never (default), else for batches of at least this many queries.  Measured on 1M random poses:
+    // slower -- a million random 6-DOF poses are too sparse to be coherent, and coherent stretches have correlated cost
+    {"order_queries", 0},
     // ordered-front path, both measured and left off: discard the L2 lines of the contact staging once a
     // query's list is in the pool (DRAM writes 2.11 -> 2.05 GB per 1M queries, time unchanged); stage short lists in
     // shared memory instead of the global per-warp scratch (DRAM writes 2.04 GB, but the smaller L1 costs 1.7 %)
@@ -118,9 +123,11 @@ struct Workspace {
   std::map<cudaStream_t, int> stream_slot;
   // The contact scratch and the distance front's overflow area are one allocation per device: launches that use them
   // on DIFFERENT streams are ordered with an event (same-stream launches are ordered anyway).
-  cudaEvent_t scratch_ev = nullptr, spill_ev = nullptr;
-  cudaStream_t scratch_stream = nullptr, spill_stream = nullptr;
-  bool scratch_used = false, spill_used = false;
+  cudaEvent_t scratch_ev = nullptr, spill_ev = nullptr, order_ev = nullptr;
+  cudaStream_t scratch_stream = nullptr, spill_stream = nullptr, order_stream = nullptr;
+  bool scratch_used = false, spill_used = false, order_used = false;
+  void* order_buf = nullptr;  // locality order of a batch (query_order.cuh): keys, bucket counters, the order itself
+  size_t order_bytes = 0;
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
   void* scan_tmp = nullptr;
@@ -168,6 +175,7 @@ int get_ws(int device, Workspace** out) {
   CUDA_TRY(cudaMemset(w->cursor_pool, 0, sizeof(long long) * kStreamSlots));
   CUDA_TRY(cudaEventCreateWithFlags(&w->scratch_ev, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&w->spill_ev, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&w->order_ev, cudaEventDisableTiming));
   CUDA_TRY(cudaMalloc(&w->ready, sizeof(unsigned) * kReadySlots));
   CUDA_TRY(cudaMemset(w->ready, 0, sizeof(unsigned) * kReadySlots));
   CUDA_TRY(cudaHostAlloc((void**)&w->host_one, sizeof(unsigned), cudaHostAllocDefault));
@@ -208,6 +216,7 @@ void mark_use(cudaStream_t st, cudaEvent_t ev, bool& used, cudaStream_t& last) {
   last = st;
 }
 
+size_t padded_up(size_t bytes) { return (bytes + 255) & ~size_t(255); }
 int ensure(void** p, size_t* have, size_t want) {
   if (*have >= want) return 0;
   if (*p) CUDA_TRY(cudaFree(*p));
@@ -922,6 +931,40 @@ extern "C" int fclgpu_collide_batch(const fclgpu_model* m1, const fclgpu_model* 
 }
 
 namespace {
+// Locality order of queries [0, n) of a resident batch into the workspace's order buffer (three small launches).
+int enqueue_query_order(Workspace* w, const fclgpu_model* m1, const fclgpu_model* m2, long long n, const double* tf1, const double* tf2,
+                        cudaStream_t st, const int32_t** order) {
+  const size_t bytes = padded_up(2 * (size_t)n) + 2 * sizeof(uint32_t) * kOrderBuckets + padded_up(4 * (size_t)n);
+  int rc = ensure(&w->order_buf, &w->order_bytes, bytes);
+  if (rc) return rc;
+  order_after(st, w->order_ev, w->order_used, w->order_stream);
+  char* base = (char*)w->order_buf;
+  OrderParams O;
+  O.tf1 = tf1;
+  O.tf2 = tf2;
+  O.n = n;
+  for (int k = 0; k < 3; ++k) {
+    O.c1[k] = m1->aabb.c[k];
+    O.c2[k] = m2->aabb.c[k];
+  }
+  O.reach = m1->aabb.r + m2->aabb.r;
+  O.hist = (uint32_t*)base;
+  O.cursor = O.hist + kOrderBuckets;
+  O.key = (uint16_t*)(base + 2 * sizeof(uint32_t) * kOrderBuckets);
+  O.order = (int32_t*)(base + 2 * sizeof(uint32_t) * kOrderBuckets + padded_up(2 * (size_t)n));
+  CUDA_TRY(cudaMemsetAsync(O.hist, 0, sizeof(uint32_t) * kOrderBuckets, st));
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  order_key_kernel<<<blocks, 256, 0, st>>>(O);
+  order_scan_kernel<<<1, 1024, 0, st>>>(O);
+  order_scatter_kernel<<<blocks, 256, 0, st>>>(O);
+  g_launches += 3;
+  CUDA_TRY(cudaGetLastError());
+  *order = O.order;
+  return 0;
+}
+}  // namespace
+
+namespace {
 int collide_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, const double* tf1, const double* tf2,
                     const fclgpu_collision_request* request, int32_t* num_contacts, fclgpu_contact* contacts,
                     int64_t contact_capacity, int64_t* contact_offsets, uint32_t* n_bv, uint32_t* n_leaf, void* stream,
@@ -1061,6 +1104,7 @@ int collide_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, c
     P.ready = X.ready;
     P.ready_shift = X.ready_shift;
     P.ready_q0 = X.ready_q0 + s;
+    P.order = nullptr;
     const long long trav = trav0;
     const int trig = (int)opt("leaf_trigger");
     const long long front = opt("collide_front");  // 0 never, 1 (default) for BVHs beyond the caches, 2 always
@@ -1087,6 +1131,13 @@ int collide_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, c
     } else if (trav >= 3) {  // pooled leaf rounds
       const int ptrig = (int)opt("pool_trigger");
       const size_t psm = sizeof(PoolWarp) * 4;
+      const long long min_order = opt("order_queries");
+      bool ordered = false;
+      if (min_order > 0 && cn >= min_order && X.ready == nullptr && cn < (1ll << 31)) {
+        rc = enqueue_query_order(w, m1, m2, cn, P.tf1, P.tf2, st, &P.order);
+        if (rc) return rc;
+        ordered = true;
+      }
       if (!P.enable_contact && opt("binary_pooled") >= 2)
         rc = stats ? launch_persistent(collide_pooled_kernel<true, true>, P, w, 128, st, psm, ptrig)
                    : launch_persistent(collide_pooled_kernel<false, true>, P, w, 128, st, psm, ptrig);
@@ -1098,6 +1149,7 @@ int collide_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, c
       else
         rc = stats ? launch_persistent(collide_pooled_kernel<true, false>, P, w, 128, st, psm, ptrig)
                    : launch_persistent(collide_pooled_kernel<false, false>, P, w, 128, st, psm, ptrig);
+      if (ordered) mark_use(st, w->order_ev, w->order_used, w->order_stream);
     } else if (trav >= 2) {
       rc = stats ? launch_persistent(collide_deferred_kernel<true, true, false>, P, w, 128, st, 0, trig)
                  : launch_persistent(collide_deferred_kernel<false, true, false>, P, w, 128, st, 0, trig);

@@ -150,6 +150,31 @@ __device__ __forceinline__ long long fetch_work(bool need, unsigned long long* c
   return need ? (long long)(base + __popc(mask & ((1u << lane) - 1u))) : -1;
 }
 
+// The same for kernels whose lanes should stay on NEIGHBOURING units of work (a batch sorted for locality): a warp draws
+// kWorkBlock consecutive units at a time and hands them to its lanes as they become free, so the 32 queries in flight in
+// a warp always come from one stretch of kWorkBlock units.  next / end: the warp's current stretch (uniform across the
+// warp).  Returns the unit, -1 for lanes that did not ask, -2 for a lane that has to ask again (stretch used up).
+constexpr int kWorkBlock = 64;
+__device__ __forceinline__ long long fetch_work_blocked(bool need, unsigned long long* counter, long long& next, long long& end) {
+  const unsigned mask = __ballot_sync(0xffffffffu, need);
+  if (mask == 0) return -1;
+  const int lane = threadIdx.x & 31;
+  if (next >= end) {
+    const int leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(counter, (unsigned long long)kWorkBlock);
+    base = __shfl_sync(0xffffffffu, base, leader);
+    next = (long long)base;
+    end = next + kWorkBlock;
+  }
+  const long long rem = end - next;
+  const int rank = __popc(mask & ((1u << lane) - 1u));
+  const int cnt = __popc(mask);
+  const long long mine = (need && rank < rem) ? next + rank : (need ? -2 : -1);
+  next += cnt < rem ? cnt : rem;
+  return mine;
+}
+
 struct CollideParams {
   DeviceModel m1, m2;
   const double* tf1;
@@ -169,6 +194,9 @@ struct CollideParams {
   const unsigned* ready;
   int ready_shift;
   long long ready_q0;  // index of query 0 of this launch in the flagged batch
+  // locality order (query_order.cuh): the i-th unit of work is query order[i]; nullptr = batch order.  Results are
+  // written at the query's own index, so the order never shows in an output.
+  const int32_t* order;
 };
 
 // Spin until the chunk that holds query q has landed.  Acquire load: the pose loads that follow cannot be
@@ -1372,6 +1400,7 @@ __global__ void __launch_bounds__(128, FCLGPU_POOLED_MINBLOCKS) collide_pooled_k
   long long count = 0;
   uint32_t bv_tests = 0, leaf_tests = 0;
   bool exhausted = false;
+  long long blk_next = 0, blk_end = 0;  // the warp's current stretch of an ordered batch (fetch_work_blocked)
 
   while (true) {
     const bool need = (sp == 0) && (qcount == 0) && !exhausted;
@@ -1383,11 +1412,12 @@ __global__ void __launch_bounds__(128, FCLGPU_POOLED_MINBLOCKS) collide_pooled_k
       }
       q = -1;
     }
-    const long long nq = fetch_work(need, P.work_counter);
+    // a batch ordered for locality is handed out in warp-sized stretches, so that the lanes of a warp stay on neighbours
+    const long long nq = P.order ? fetch_work_blocked(need, P.work_counter, blk_next, blk_end) : fetch_work(need, P.work_counter);
     if (nq >= 0 && nq < P.n && !wait_ready(P.ready, P.ready_shift, nq + P.ready_q0)) atomicMin(P.status, (int)FCLGPU_ERR_INPUT_STALLED);
-    if (need) {
+    if (need && nq != -2) {
       if (nq < P.n) {
-        q = nq;
+        q = P.order ? (long long)__ldg(P.order + nq) : nq;
         const PoseRT tf1 = load_pose(P.tf1, q, P.ready != nullptr);
         const PoseRT tf2 = load_pose(P.tf2, q, P.ready != nullptr);
         R = mulTM(tf1.R, tf2.R);
