@@ -142,7 +142,7 @@ inline void collide(const DeviceModel& o1, const std::vector<fcl::Transform3<dou
     to_pose(tf2[i], &p2[12 * i]);
   }
   fclgpu_collision_request req{(int64_t)std::min<std::size_t>(request.num_max_contacts, (std::size_t)1 << 62),
-                               request.enable_contact ? 1 : 0, request.enable_cost ? 1 : 0, 0};
+                               request.enable_contact ? 1 : 0, request.enable_cost ? 1 : 0, 0, FCLGPU_CONTACT_FULL, 0};
   std::vector<int32_t> counts(n);
   std::vector<int64_t> off(n + 1);
   int64_t cap = std::max<int64_t>(64 * n, 1024);
@@ -187,7 +187,7 @@ inline void collide(const DeviceModel& o1, const std::vector<fcl::Transform3<dou
     to_pose(tf2[i], &p2[12 * i]);
   }
   fclgpu_collision_request req{(int64_t)std::min<std::size_t>(request.num_max_contacts, (std::size_t)1 << 62),
-                               request.enable_contact ? 1 : 0, request.enable_cost ? 1 : 0, 0};
+                               request.enable_contact ? 1 : 0, request.enable_cost ? 1 : 0, 0, FCLGPU_CONTACT_FULL, 0};
   std::vector<int32_t> counts(n);
   std::vector<int64_t> off(n + 1);
   int64_t cap = std::max<int64_t>(64 * n, 1024);

@@ -35,7 +35,7 @@ int main(void) {
     printf("no device: upload refused with %d (%s)\n", rc, fclgpu_last_error());
   } else {
     if (rc != FCLGPU_OK) { printf("upload failed %d (%s)\n", rc, fclgpu_last_error()); return 1; }
-    fclgpu_collision_request req = {1, 0, 0, 0};
+    fclgpu_collision_request req = {1, 0, 0, 0, FCLGPU_CONTACT_FULL, 0};
     double tf[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0.5, 0, 0};
     int32_t n = -1;
     rc = fclgpu_collide_batch_host(m, m, 1, tf, NULL, &req, &n, NULL, 0, NULL, NULL, NULL);

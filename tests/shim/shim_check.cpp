@@ -107,7 +107,7 @@ int main(int argc, char** argv) {
   fclgpu_model *g1 = nullptr, *g2 = nullptr;
   fclgpu::check(fclgpu_model_from_bvh(0, b1, &g1));
   fclgpu::check(fclgpu_model_from_bvh(0, b2, &g2));
-  fclgpu_collision_request creq{20, 1, 0, 0};
+  fclgpu_collision_request creq{20, 1, 0, 0, FCLGPU_CONTACT_FULL, 0};
   std::vector<int32_t> cnt(n);
   std::vector<int64_t> off(n + 1);
   std::vector<fclgpu_contact> pool(20 * (size_t)n);
