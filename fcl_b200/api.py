@@ -1031,15 +1031,29 @@ class NaiveCollisionManager:
             k = int(m.value)
             return BatchBroadPhaseResult(pairs[:k], counts[:k] if narrowphase else None, a1, a2)
 
-    def collide(self, other, cdata, callback):
+    def collide(self, other, cdata, callback=None):
         """collide(other_manager, cdata, callback) (broadphase_bruteforce-inl.h:182-205): the callback sees the culled pairs
-        in the brute-force manager's order and may end the evaluation by returning True.  Culling runs on the GPU."""
+        in the brute-force manager's order and may end the evaluation by returning True.  Culling runs on the GPU.
+        collide(cdata, callback) -- or the same manager on both sides, :188-192 -- is the self-collision form (:140-160):
+        every unordered pair of this manager's objects once, it1 before it2 in registration order."""
+        if callback is None:  # collide(cdata, callback)
+            other, cdata, callback = self, other, cdata
         if self.size() == 0 or other.size() == 0:
             return
         r = self.collide_batch(other, narrowphase=False)
+        own = other is self
         for i, j in r.pairs:
+            if own and j <= i:
+                continue
             if callback(self.objs[i], other.objs[j], cdata):
                 return
+
+    def self_pairs(self, request=None, device=None, narrowphase=True):
+        """Batched self-collision: the pairs (i < j) of this manager's objects whose AABBs overlap, in the brute-force
+        manager's order, with numContacts of fcl::collide on each."""
+        r = self.collide_batch(self, request, device, narrowphase=narrowphase)
+        keep = r.pairs[:, 0] < r.pairs[:, 1]
+        return BatchBroadPhaseResult(r.pairs[keep], None if r.num_contacts is None else r.num_contacts[keep], r.aabb1, r.aabb2)
 
 
 DynamicAABBTreeCollisionManager = NaiveCollisionManager

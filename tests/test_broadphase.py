@@ -94,3 +94,15 @@ def test_gpu_broadphase_pairs_and_counts_equal_the_brute_force_manager(oracle):
     # empty managers
     E = F.NaiveCollisionManager()
     assert len(E.collide_batch(B).pairs) == 0 and len(A.collide_batch(E).pairs) == 0
+    # self-collision (collide(cdata, callback), broadphase_bruteforce-inl.h:140-160): every unordered pair once, in order
+    sp = A.self_pairs(F.CollisionRequest(6, False))
+    aabb = got.aabb1
+    ov = np.all((aabb[:, None, :3] <= aabb[None, :, 3:]) & (aabb[None, :, :3] <= aabb[:, None, 3:]), axis=2)
+    iu, ju = np.nonzero(np.triu(ov, 1))
+    assert np.array_equal(sp.pairs, np.stack([iu, ju], axis=1).astype(np.int32)) and len(sp.pairs) > 50
+    visited = []
+    A.collide(visited, lambda o1, o2, data: data.append((A.objs.index(o1), A.objs.index(o2))) or False)
+    assert visited == [tuple(p) for p in sp.pairs.tolist()]
+    visited2 = []
+    A.collide(A, visited2, lambda o1, o2, data: data.append(1) or len(data) >= 7)  # same manager on both sides; early stop
+    assert len(visited2) == 7
