@@ -946,6 +946,48 @@ def DefaultCollisionFunction(o1, o2, data):
     return data.done
 
 
+class DefaultDistanceData:
+    """fcl::DefaultDistanceData (broadphase/default_broadphase_callbacks.h:160-167)."""
+
+    def __init__(self, request=None):
+        self.request = request if request is not None else DistanceRequest()
+        self.result = DistanceResult()
+        self.done = False
+
+
+def DefaultDistanceFunction(o1, o2, data, dist):
+    """fcl::DefaultDistanceFunction (default_broadphase_callbacks.h:190-211).  `dist` stands for the reference's `S& dist`:
+    a one-element list the callback writes the current minimum into."""
+    if data.done:
+        dist[0] = data.result.min_distance
+        return True
+    distance(o1, o2, data.request, data.result)
+    dist[0] = data.result.min_distance
+    if dist[0] <= 0:
+        return True  # in collision or in touch
+    return data.done
+
+
+def _aabb_distance_matrix(a, b):
+    """AABB::distance (math/bv/AABB-inl.h:292-315) for every pair of rows of a (n1, 6) and b (n2, 6): {min3, max3}."""
+    res = np.zeros((len(a), len(b)))
+    for k in range(3):
+        amin, amax = a[:, None, k], a[:, None, 3 + k]
+        bmin, bmax = b[None, :, k], b[None, :, 3 + k]
+        d1 = bmax - amin
+        d2 = amax - bmin
+        res = res + np.where(amin > bmax, d1 * d1, np.where(bmin > amax, d2 * d2, 0.0))
+    return np.sqrt(res)
+
+
+class BatchBroadPhaseDistance:
+    """min_distance over all pairs (o1 in this manager, o2 in the other), the pair (i, j) that attains it, its nearest points
+    (world frame) and closest primitive ids, and how many of the n1 x n2 pairs needed an exact query."""
+
+    def __init__(self, min_distance, pair, nearest_points, ids, evaluated):
+        self.min_distance, self.pair, self.nearest_points, self.ids, self.evaluated = min_distance, pair, nearest_points, ids, evaluated
+
+
 class BatchBroadPhaseResult:
     """pairs (m, 2): (index in this manager, index in the other manager) of every pair whose world AABBs overlap, in the
     brute-force manager's visiting order; num_contacts[m]: fcl::collide on each pair with a fresh result (or None)."""
@@ -1047,6 +1089,63 @@ class NaiveCollisionManager:
                 continue
             if callback(self.objs[i], other.objs[j], cdata):
                 return
+
+    def distance(self, other, cdata, callback=None):
+        """distance(other_manager, cdata, callback) (broadphase_bruteforce-inl.h:208-233): pairs in registration order, a
+        pair is handed to the callback only while the distance of its AABBs is below the running minimum the callback
+        reports; distance(cdata, callback) is the self form (:163-178)."""
+        if callback is None:
+            other, cdata, callback = self, other, cdata
+        if self.size() == 0 or other.size() == 0:
+            return
+        r = self.collide_batch(other, narrowphase=False)  # world AABBs as CollisionObject::computeAABB builds them
+        D = _aabb_distance_matrix(r.aabb1, r.aabb2)
+        own = other is self
+        min_dist = [DBL_MAX]
+        for i, o1 in enumerate(self.objs):
+            for j, o2 in enumerate(other.objs):
+                if own and j <= i:
+                    continue
+                if D[i, j] < min_dist[0]:
+                    if callback(o1, o2, cdata, min_dist):
+                        return
+
+    def distance_batch(self, other, request=None, device=None, chunk=4096):
+        """The minimum distance between any object of this manager and any object of the other one, batched: pairs in the
+        order of their AABB distance (a lower bound), exact distance() queries on the GPU a chunk at a time (grouped by
+        geometry pair), until the next AABB distance is no smaller than the minimum found.  The value is what
+        distance(other, DefaultDistanceData, DefaultDistanceFunction) ends with; among exact ties another pair may be named."""
+        n1, n2 = len(self.objs), len(other.objs)
+        if n1 == 0 or n2 == 0:
+            return BatchBroadPhaseDistance(DBL_MAX, (-1, -1), None, (-1, -1), 0)
+        r = self.collide_batch(other, narrowphase=False, device=device)
+        D = _aabb_distance_matrix(r.aabb1, r.aabb2)
+        own = other is self
+        if own:
+            D[np.tril_indices(n1)] = np.inf
+        flat = np.argsort(D, axis=None, kind="stable")
+        req = request if request is not None else DistanceRequest(True)
+        geoms, _, (g1, tf1), (g2, tf2) = self._tables(other, device)
+        best = (DBL_MAX, (-1, -1), None, (-1, -1))
+        pos = evaluated = 0
+        while pos < len(flat):
+            take = flat[pos:pos + chunk]
+            take = take[D.ravel()[take] < best[0]]
+            if len(take) == 0:
+                break
+            pos += chunk
+            ii, jj = np.unravel_index(take, D.shape)
+            key = g1[ii].astype(np.int64) * len(geoms) + g2[jj]
+            for k in np.unique(key):
+                sel = np.nonzero(key == k)[0]
+                a, b = geoms[int(k) // len(geoms)], geoms[int(k) % len(geoms)]
+                res = distance_batch(a, np.ascontiguousarray(tf1[ii[sel]]), b, np.ascontiguousarray(tf2[jj[sel]]), req, device=device)
+                m = int(np.argmin(res.min_distance))
+                evaluated += len(sel)
+                if res.min_distance[m] < best[0]:
+                    pts = (res.nearest_p1[m].copy(), res.nearest_p2[m].copy()) if req.enable_nearest_points else None
+                    best = (float(res.min_distance[m]), (int(ii[sel[m]]), int(jj[sel[m]])), pts, (int(res.b1[m]), int(res.b2[m])))
+        return BatchBroadPhaseDistance(best[0], best[1], best[2], best[3], evaluated)
 
     def self_pairs(self, request=None, device=None, narrowphase=True):
         """Batched self-collision: the pairs (i < j) of this manager's objects whose AABBs overlap, in the brute-force

@@ -106,3 +106,42 @@ def test_gpu_broadphase_pairs_and_counts_equal_the_brute_force_manager(oracle):
     visited2 = []
     A.collide(A, visited2, lambda o1, o2, data: data.append(1) or len(data) >= 7)  # same manager on both sides; early stop
     assert len(visited2) == 7
+
+
+@pytest.mark.gpu
+def test_gpu_manager_distance_equals_all_pairs_minimum(oracle):
+    """NaiveCollisionManager::distance(other, cdata, DefaultDistanceFunction) (broadphase_bruteforce-inl.h:208-233,
+    default_broadphase_callbacks.h:190-211) and its batched form against the oracle's distance over ALL pairs."""
+    meshes, g1, P1, g2, P2 = _scene(9, 40, 30)
+    P2[:, 9:] += 8.0  # apart: a positive minimum
+    omodels = [oracle.Model(v, t) for v, t in meshes]
+    geoms = [F.BVHModel.from_arrays(v, t) for v, t in meshes]
+    A, B = F.NaiveCollisionManager(), F.NaiveCollisionManager()
+    A.registerObjects([F.CollisionObject(geoms[g], F.Transform3.from_pose12(p)) for g, p in zip(g1, P1)])
+    B.registerObjects([F.CollisionObject(geoms[g], F.Transform3.from_pose12(p)) for g, p in zip(g2, P2)])
+    want = np.inf
+    for ga in np.unique(g1):
+        for gb in np.unique(g2):
+            ia, ib = np.nonzero(g1 == ga)[0], np.nonzero(g2 == gb)[0]
+            t1 = np.repeat(P1[ia], len(ib), axis=0)
+            t2 = np.tile(P2[ib], (len(ia), 1))
+            want = min(want, oracle.distance_batch(omodels[ga], omodels[gb], t1, t2, True, 2, nthreads=8)["min_distance"].min())
+    assert want > 0
+    got = A.distance_batch(B, chunk=64)  # small chunks: the AABB lower bounds end the evaluation early
+    assert got.min_distance == want and got.evaluated < len(g1) * len(g2) // 2
+    assert A.distance_batch(B).min_distance == want
+    i, j = got.pair
+    d = F.DistanceResult()
+    assert F.distance(A.objs[i], B.objs[j], F.DistanceRequest(True), d) == want
+    assert abs(np.linalg.norm(got.nearest_points[0] - got.nearest_points[1]) - want) <= 1e-9 * max(1.0, want)
+    data = F.DefaultDistanceData(F.DistanceRequest(True))
+    A.distance(B, data, F.DefaultDistanceFunction)
+    assert data.result.min_distance == want
+    # touching / colliding sets: the callback protocol stops at the first pair with distance <= 0
+    P2[:, 9:] -= 8.0
+    B2 = F.NaiveCollisionManager()
+    B2.registerObjects([F.CollisionObject(geoms[g], F.Transform3.from_pose12(p)) for g, p in zip(g2, P2)])
+    assert A.distance_batch(B2).min_distance == 0.0
+    data = F.DefaultDistanceData()
+    A.distance(B2, data, F.DefaultDistanceFunction)
+    assert data.result.min_distance == 0.0
