@@ -217,6 +217,63 @@ inline void collide(const DeviceModel& o1, const std::vector<fcl::Transform3<dou
     }
 }
 
+// n independent fcl::collide(mesh, tf1[i], Halfspace | Plane, tf2[i], request, results[i]) calls
+// (collision_matrix[BV_OBBRSS][GEOM_HALFSPACE] / [GEOM_PLANE], collision_func_matrix-inl.h:841-842; contacts carry b2 = NONE).
+// Shape: fcl::Halfspace<double> or fcl::Plane<double> (public members n, d; geometry/shape/halfspace.h, plane.h).
+template <typename Shape>
+inline void collide_plane_like(const DeviceModel& o1, const std::vector<fcl::Transform3<double>>& tf1, const Shape& shape, int32_t kind,
+                               const std::vector<fcl::Transform3<double>>& tf2, const fcl::CollisionRequest<double>& request,
+                               std::vector<fcl::CollisionResult<double>>& results) {
+  const int64_t n = (int64_t)tf1.size();
+  same_size(tf1.size(), tf2.size());
+  results.assign(n, fcl::CollisionResult<double>());
+  if (request.num_max_contacts == 0 || n == 0) return;
+  std::vector<double> p1(12 * n), p2(12 * n);
+  for (int64_t i = 0; i < n; ++i) {
+    to_pose(tf1[i], &p1[12 * i]);
+    to_pose(tf2[i], &p2[12 * i]);
+  }
+  const double nrm[3] = {shape.n[0], shape.n[1], shape.n[2]};
+  fclgpu_collision_request req{(int64_t)std::min<std::size_t>(request.num_max_contacts, (std::size_t)1 << 62),
+                               request.enable_contact ? 1 : 0, request.enable_cost ? 1 : 0, 0, FCLGPU_CONTACT_FULL, 0};
+  std::vector<int32_t> counts(n);
+  std::vector<int64_t> off(n + 1);
+  int64_t cap = std::max<int64_t>(64 * n, 1024);
+  std::vector<fclgpu_contact> pool(cap);
+  int rc = fclgpu_collide_mesh_plane_batch_host(o1.handle(), kind, nrm, shape.d, n, p1.data(), p2.data(), &req, counts.data(), pool.data(),
+                                                cap, off.data(), nullptr, nullptr);
+  if (rc == FCLGPU_ERR_CONTACT_OVERFLOW) {  // counts are exact: size the pool and rerun
+    cap = 0;
+    int32_t mx = 1;
+    for (int32_t c : counts) { cap += c; mx = std::max(mx, c); }
+    req.stage_capacity = mx;
+    pool.resize(cap);
+    rc = fclgpu_collide_mesh_plane_batch_host(o1.handle(), kind, nrm, shape.d, n, p1.data(), p2.data(), &req, counts.data(), pool.data(), cap,
+                                              off.data(), nullptr, nullptr);
+  }
+  check(rc);
+  for (int64_t i = 0; i < n; ++i)
+    for (int64_t k = off[i]; k < off[i] + counts[i]; ++k) {
+      const fclgpu_contact& c = pool[k];
+      if (request.enable_contact)
+        results[i].addContact(fcl::Contact<double>(o1.host(), &shape, c.b1, fcl::Contact<double>::NONE,
+                                                   fcl::Vector3<double>(c.pos[0], c.pos[1], c.pos[2]),
+                                                   fcl::Vector3<double>(c.normal[0], c.normal[1], c.normal[2]), c.penetration_depth));
+      else
+        results[i].addContact(fcl::Contact<double>(o1.host(), &shape, c.b1, fcl::Contact<double>::NONE));
+    }
+}
+inline void collide(const DeviceModel& o1, const std::vector<fcl::Transform3<double>>& tf1, const fcl::Halfspace<double>& hs,
+                    const std::vector<fcl::Transform3<double>>& tf2, const fcl::CollisionRequest<double>& request,
+                    std::vector<fcl::CollisionResult<double>>& results) {
+  collide_plane_like(o1, tf1, hs, FCLGPU_SHAPE_HALFSPACE, tf2, request, results);
+}
+inline void collide(const DeviceModel& o1, const std::vector<fcl::Transform3<double>>& tf1, const fcl::Plane<double>& pl,
+                    const std::vector<fcl::Transform3<double>>& tf2, const fcl::CollisionRequest<double>& request,
+                    std::vector<fcl::CollisionResult<double>>& results) {
+  collide_plane_like(o1, tf1, pl, FCLGPU_SHAPE_PLANE, tf2, request, results);
+}
+
 inline void distance(const DeviceModel& o1, const std::vector<fcl::Transform3<double>>& tf1, const DeviceModel& o2,
                      const std::vector<fcl::Transform3<double>>& tf2, const fcl::DistanceRequest<double>& request,
                      std::vector<fcl::DistanceResult<double>>& results) {
@@ -408,6 +465,32 @@ std::size_t collide_sphere_cell(const fcl::CollisionGeometry<double>* o1, const 
   return result.numContacts();
 }
 
+// collision_matrix[BV_OBBRSS][GEOM_HALFSPACE] and [GEOM_PLANE] (BVHShapeCollider<OBBRSS, Halfspace | Plane>)
+template <typename Solver, typename Shape>
+std::size_t collide_plane_like_cell(const fcl::CollisionGeometry<double>* o1, const fcl::Transform3<double>& tf1,
+                                    const fcl::CollisionGeometry<double>* o2, const fcl::Transform3<double>& tf2, const Solver*,
+                                    const fcl::CollisionRequest<double>& request, fcl::CollisionResult<double>& result) {
+  if (request.isSatisfied(result)) return result.numContacts();  // collision_func_matrix-inl.h:389
+  if (request.num_max_contacts <= result.numContacts()) return result.numContacts();
+  const DeviceModel& m1 = model_cache().get(static_cast<const BVH*>(o1));
+  std::vector<fcl::CollisionResult<double>> r;
+  collide(m1, {tf1}, *static_cast<const Shape*>(o2), {tf2}, detail::remaining(request, result), r);
+  detail::append(r[0], result);
+  return result.numContacts();
+}
+template <typename Solver>
+std::size_t collide_halfspace_cell(const fcl::CollisionGeometry<double>* o1, const fcl::Transform3<double>& tf1,
+                                   const fcl::CollisionGeometry<double>* o2, const fcl::Transform3<double>& tf2, const Solver* s,
+                                   const fcl::CollisionRequest<double>& request, fcl::CollisionResult<double>& result) {
+  return collide_plane_like_cell<Solver, fcl::Halfspace<double>>(o1, tf1, o2, tf2, s, request, result);
+}
+template <typename Solver>
+std::size_t collide_plane_cell(const fcl::CollisionGeometry<double>* o1, const fcl::Transform3<double>& tf1,
+                               const fcl::CollisionGeometry<double>* o2, const fcl::Transform3<double>& tf2, const Solver* s,
+                               const fcl::CollisionRequest<double>& request, fcl::CollisionResult<double>& result) {
+  return collide_plane_like_cell<Solver, fcl::Plane<double>>(o1, tf1, o2, tf2, s, request, result);
+}
+
 // distance_matrix[BV_OBBRSS][BV_OBBRSS]
 template <typename Solver>
 double distance_cell(const fcl::CollisionGeometry<double>* o1, const fcl::Transform3<double>& tf1,
@@ -441,7 +524,8 @@ double distance_sphere_cell(const fcl::CollisionGeometry<double>* o1, const fcl:
 // What install() replaced, so that uninstall() can put it back.
 template <typename Solver>
 struct InstalledCells {
-  typename fcl::detail::CollisionFunctionMatrix<Solver>::CollisionFunc collide_mesh = nullptr, collide_sphere = nullptr;
+  typename fcl::detail::CollisionFunctionMatrix<Solver>::CollisionFunc collide_mesh = nullptr, collide_sphere = nullptr,
+                                                                       collide_halfspace = nullptr, collide_plane = nullptr;
   typename fcl::detail::DistanceFunctionMatrix<Solver>::DistanceFunc distance_mesh = nullptr, distance_sphere = nullptr;
   bool installed = false;
   static InstalledCells& saved() {
@@ -450,7 +534,7 @@ struct InstalledCells {
   }
 };
 
-// Overwrites the four cells of the look-up tables of `Solver` (the public, non-const array members of the function-
+// Overwrites the six cells of the look-up tables of `Solver` (the public, non-const array members of the function-
 // local statics behind fcl::getCollisionFunctionLookTable / getDistanceFunctionLookTable).  Call once at start-up,
 // before other threads issue queries.  In a shared-library build of FCL with hidden visibility the library keeps its
 // own copy of the tables for the extern-template collide<double>(o1, tf1, o2, tf2, request, result); the overwrite then
@@ -463,12 +547,16 @@ void install() {
   if (!s.installed) {
     s.collide_mesh = c.collision_matrix[fcl::BV_OBBRSS][fcl::BV_OBBRSS];
     s.collide_sphere = c.collision_matrix[fcl::BV_OBBRSS][fcl::GEOM_SPHERE];
+    s.collide_halfspace = c.collision_matrix[fcl::BV_OBBRSS][fcl::GEOM_HALFSPACE];
+    s.collide_plane = c.collision_matrix[fcl::BV_OBBRSS][fcl::GEOM_PLANE];
     s.distance_mesh = d.distance_matrix[fcl::BV_OBBRSS][fcl::BV_OBBRSS];
     s.distance_sphere = d.distance_matrix[fcl::BV_OBBRSS][fcl::GEOM_SPHERE];
     s.installed = true;
   }
   c.collision_matrix[fcl::BV_OBBRSS][fcl::BV_OBBRSS] = &collide_cell<Solver>;
   c.collision_matrix[fcl::BV_OBBRSS][fcl::GEOM_SPHERE] = &collide_sphere_cell<Solver>;
+  c.collision_matrix[fcl::BV_OBBRSS][fcl::GEOM_HALFSPACE] = &collide_halfspace_cell<Solver>;
+  c.collision_matrix[fcl::BV_OBBRSS][fcl::GEOM_PLANE] = &collide_plane_cell<Solver>;
   d.distance_matrix[fcl::BV_OBBRSS][fcl::BV_OBBRSS] = &distance_cell<Solver>;
   d.distance_matrix[fcl::BV_OBBRSS][fcl::GEOM_SPHERE] = &distance_sphere_cell<Solver>;
 }
@@ -481,6 +569,8 @@ void uninstall() {
   auto& d = fcl::getDistanceFunctionLookTable<Solver>();
   c.collision_matrix[fcl::BV_OBBRSS][fcl::BV_OBBRSS] = s.collide_mesh;
   c.collision_matrix[fcl::BV_OBBRSS][fcl::GEOM_SPHERE] = s.collide_sphere;
+  c.collision_matrix[fcl::BV_OBBRSS][fcl::GEOM_HALFSPACE] = s.collide_halfspace;
+  c.collision_matrix[fcl::BV_OBBRSS][fcl::GEOM_PLANE] = s.collide_plane;
   d.distance_matrix[fcl::BV_OBBRSS][fcl::BV_OBBRSS] = s.distance_mesh;
   d.distance_matrix[fcl::BV_OBBRSS][fcl::GEOM_SPHERE] = s.distance_sphere;
   s.installed = false;

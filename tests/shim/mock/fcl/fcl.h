@@ -134,6 +134,24 @@ struct Sphere : CollisionGeometry<S> {
   OBJECT_TYPE getObjectType() const override { return OT_GEOM; }
 };
 
+// geometry/shape/halfspace.h, plane.h: public members n (unit normal) and d
+template <typename S>
+struct Halfspace : CollisionGeometry<S> {
+  Vector3<S> n;
+  S d;
+  Halfspace(const Vector3<S>& n_, S d_) : n(n_), d(d_) {}
+  NODE_TYPE getNodeType() const override { return GEOM_HALFSPACE; }
+  OBJECT_TYPE getObjectType() const override { return OT_GEOM; }
+};
+template <typename S>
+struct Plane : CollisionGeometry<S> {
+  Vector3<S> n;
+  S d;
+  Plane(const Vector3<S>& n_, S d_) : n(n_), d(d_) {}
+  NODE_TYPE getNodeType() const override { return GEOM_PLANE; }
+  OBJECT_TYPE getObjectType() const override { return OT_GEOM; }
+};
+
 template <typename S>
 struct Contact {
   static const int NONE = -1;  // contact.h: id of "no primitive" (shape side)

@@ -295,6 +295,29 @@ int main(int argc, char** argv) {
       const double b = fcl::distance(sp, tf2[far], g1p, tf1[far], &solver, fcl::DistanceRequest<double>(true), s2);
       if (a != b || s1.b1 != s2.b1 || s1.b2 != fcl::DistanceResult<double>::NONE) { std::printf("FAIL sphere cells\n"); return 1; }
     }
+    {  // halfspace / plane cells against the C ABI (single query each)
+      const fcl::CollisionGeometry<double>* g1p = &m1;
+      fcl::Halfspace<double> hs(fcl::Vector3<double>(0.0, 0.0, 1.0), 0.3);
+      fcl::Plane<double> pl(fcl::Vector3<double>(0.0, 1.0, 0.0), -0.2);
+      const double nh[3] = {0, 0, 1}, np_[3] = {0, 1, 0};
+      fclgpu_collision_request rq{1000, 1, 0, 0, FCLGPU_CONTACT_FULL, 0};
+      for (int which = 0; which < 2; ++which) {
+        int32_t c = 0;
+        std::vector<fclgpu_contact> pc(4000);
+        int64_t o2[2];
+        double idp[12];
+        fclgpu_pose_from_colmajor4x4(tf1[0].m16, idp);
+        fclgpu::check(fclgpu_collide_mesh_plane_batch_host(g1, which ? FCLGPU_SHAPE_PLANE : FCLGPU_SHAPE_HALFSPACE, which ? np_ : nh, which ? -0.2 : 0.3,
+                                                           1, idp, idp, &rq, &c, pc.data(), (int64_t)pc.size(), o2, nullptr, nullptr));
+        fcl::CollisionResult<double> res;
+        const fcl::CollisionGeometry<double>* sh = which ? (const fcl::CollisionGeometry<double>*)&pl : (const fcl::CollisionGeometry<double>*)&hs;
+        const std::size_t got = fcl::collide(g1p, tf1[0], sh, tf1[0], &solver, fcl::CollisionRequest<double>(1000, true), res);
+        if ((int)got != c || c == 0) { std::printf("FAIL plane-like cell %d: %zu vs %d\n", which, got, c); return 1; }
+        for (int k = 0; k < c; ++k)
+          if (res.getContact(k).b1 != pc[k].b1 || res.getContact(k).penetration_depth != pc[k].penetration_depth) { std::printf("FAIL plane-like contact %d\n", k); return 1; }
+      }
+      std::printf("shim halfspace / plane cells OK\n");
+    }
     if (cells == 0) { std::printf("FAIL: no multi-contact query for the cell check\n"); return 1; }
     std::printf("shim cells OK: %lld single queries through the look-up table, %lld accumulations, %lld early returns\n", cells, accumulated, early);
     // refit through the shim: the partition was derived from the public node fields
