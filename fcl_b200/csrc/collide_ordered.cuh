@@ -41,6 +41,15 @@ constexpr int kOrdWarps = 4;      // warps per block
 #ifndef FCLGPU_ORD_OUTOFLINE
 #define FCLGPU_ORD_OUTOFLINE 3   // bit 0: triangle SAT out of line, bit 1: contact computation out of line
 #endif
+// Seed front (FCLGPU_ORD_SEED levels, like the distance kernel's): the first levels of the BVTT are expanded whatever the pose --
+// which node of a pair splits depends on the two trees only -- so one warp per block expands the root pair that many
+// levels once (in depth-first order, at most 32 pairs) and every query starts with ONE round that box-tests those pairs,
+// instead of the 1-, 2-, 4-, ... lane rounds that lead there.  A pair whose boxes overlap although an ancestor's are
+// disjoint cannot hold an intersecting triangle pair (both ancestors' boxes would contain the intersection point), so
+// skipping the ancestors' tests never adds a contact.
+#ifndef FCLGPU_ORD_SEED
+#define FCLGPU_ORD_SEED 5
+#endif
 #ifndef FCLGPU_ORD_ROLLED
 #define FCLGPU_ORD_ROLLED 1      // rolled-loop triangle SAT (compact code)
 #endif
@@ -104,6 +113,50 @@ __global__ void __launch_bounds__(kOrdWarps * 32, FCLGPU_ORD_MINBLOCKS) collide_
   const int normal_limit = kOrdCap - (Q.depth_sum + 2) - 16;
   const bool coherent = P.ready != nullptr;
 
+  constexpr bool kSeed = FCLGPU_ORD_SEED > 0;
+  __shared__ uint2 s_seed[32];
+  __shared__ int s_nseed;
+  if (kSeed) {
+    if (threadIdx.x < 32) {
+      if (lane == 0) s_seed[0] = make_uint2(0u, 0u);
+      __syncwarp();
+      int n = 1;
+      for (int lv = 0; lv < FCLGPU_ORD_SEED; ++lv) {
+        const bool have = lane < n;
+        uint2 e = make_uint2(0u, 0u);
+        int fc1 = -1, fc2 = -1;
+        double size1 = 0.0, size2 = 0.0;
+        if (have) {
+          e = s_seed[lane];
+          load_topo(P.m1.topo, (int)e.x, fc1, size1);
+          load_topo(P.m2.topo, (int)e.y, fc2, size2);
+        }
+        const bool l1 = fc1 < 0, l2 = fc2 < 0;
+        const bool exp = have && !(l1 && l2);
+        const unsigned em = __ballot_sync(0xffffffffu, exp);
+        const int add = __popc(em);
+        if (add == 0 || n + add > 32) break;
+        __syncwarp();
+        if (have) {
+          const int pos = lane + __popc(em & lt_mask);  // every expanded entry ahead of this one takes one more slot
+          if (!exp) {
+            s_seed[pos] = e;
+          } else if (l2 || (!l1 && (size1 > size2))) {  // firstOverSecond; left child first = depth-first order
+            s_seed[pos] = make_uint2((unsigned)fc1, e.y);
+            s_seed[pos + 1] = make_uint2((unsigned)fc1 + 1u, e.y);
+          } else {
+            s_seed[pos] = make_uint2(e.x, (unsigned)fc2);
+            s_seed[pos + 1] = make_uint2(e.x, (unsigned)fc2 + 1u);
+          }
+        }
+        n += add;
+        __syncwarp();
+      }
+      if (lane == 0) s_nseed = n;
+    }
+    __syncthreads();
+  }
+
   while (true) {
     long long q = 0;
     if (lane == 0) q = (long long)atomicAdd(P.work_counter, 1ull);
@@ -135,7 +188,20 @@ __global__ void __launch_bounds__(kOrdWarps * 32, FCLGPU_ORD_MINBLOCKS) collide_
     long long count = 0;
     int sp = 0, nleaf = 0, head = 0;
     uint32_t bv_tests = 1, leaf_tests = 0;
-    {  // root pair
+    if (kSeed) {  // one round over the pose-independent seed pairs (depth-first order: the first survivor ends on top)
+      const int n_test = s_nseed;
+      bool keep = false;
+      uint2 xy = make_uint2(0u, 0u);
+      if (lane < n_test) {
+        xy = s_seed[lane];
+        const ObbRec32 n1 = load_obb32(P.m1.obb32, (int)xy.x), n2 = load_obb32(P.m2.obb32, (int)xy.y);
+        keep = !obb_certainly_disjoint_f32(Rf, Tf, t_l1, n1, n2);
+      }
+      const unsigned km = __ballot_sync(0xffffffffu, keep);
+      sp = __popc(km);
+      if (keep) S.pair[sp - 1 - __popc(km & lt_mask)] = xy;
+      bv_tests = (uint32_t)n_test;
+    } else {  // root pair
       const ObbRec32 n1 = load_obb32(P.m1.obb32, 0), n2 = load_obb32(P.m2.obb32, 0);
       if (!obb_certainly_disjoint_f32(Rf, Tf, t_l1, n1, n2)) {
         if (lane == 0) S.pair[0] = make_uint2(0u, 0u);

@@ -1691,6 +1691,9 @@ namespace fclgpu {
 // once the BVH no longer fits the caches (cfg5: 1M-triangle meshes).  Near the stack limit the
 // warp falls back to one expansion per round (plain DFS, depth-bounded), so it never overflows.
 // ---------------------------------------------------------------------------------------
+#ifndef FCLGPU_FRONT_SEED
+#define FCLGPU_FRONT_SEED 5
+#endif
 constexpr int kFrontStackCap = 512;
 constexpr int kFrontLeafCap = 64;
 
@@ -1718,6 +1721,57 @@ __global__ void __launch_bounds__(128, 4) collide_front_kernel(CollideParams P) 
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
 
+  // Seed front (FCLGPU_FRONT_SEED levels, see the distance kernel): the pose-independent first levels of the BVTT, expanded
+  // once per block; every query starts with one full round over them.  A pair whose boxes overlap although an ancestor's
+  // are disjoint holds no intersecting triangles, so skipping the ancestors' tests never changes a count.
+  constexpr bool kSeed = FCLGPU_FRONT_SEED > 0;
+  __shared__ uint2 s_seed[32];
+  __shared__ uint4 s_seed_entry[32];
+  __shared__ int s_nseed;
+  if (kSeed) {
+    if (threadIdx.x < 32) {
+      if (lane == 0) s_seed[0] = make_uint2(0u, 0u);
+      __syncwarp();
+      int n = 1;
+      for (int lv = 0; lv <= FCLGPU_FRONT_SEED; ++lv) {
+        const bool have = lane < n;
+        uint2 e = make_uint2(0u, 0u);
+        int fc1 = -1, fc2 = -1;
+        double size1 = 0.0, size2 = 0.0;
+        if (have) {
+          e = s_seed[lane];
+          load_topo(P.m1.topo, (int)e.x, fc1, size1);
+          load_topo(P.m2.topo, (int)e.y, fc2, size2);
+        }
+        const bool l1 = fc1 < 0, l2 = fc2 < 0;
+        const bool exp = have && !(l1 && l2);
+        const unsigned em = __ballot_sync(0xffffffffu, exp);
+        const int add = __popc(em);
+        if (lv == FCLGPU_FRONT_SEED || add == 0 || n + add > 32) {  // final pairs: keep them as ready-to-expand entries
+          if (have) s_seed_entry[lane] = front_entry((int)e.x, (int)e.y, fc1, size1, fc2, size2);
+          break;
+        }
+        __syncwarp();
+        if (have) {
+          const int pos = lane + __popc(em & lt_mask);
+          if (!exp) {
+            s_seed[pos] = e;
+          } else if (l2 || (!l1 && (size1 > size2))) {  // firstOverSecond
+            s_seed[pos] = make_uint2((unsigned)fc1, e.y);
+            s_seed[pos + 1] = make_uint2((unsigned)fc1 + 1u, e.y);
+          } else {
+            s_seed[pos] = make_uint2(e.x, (unsigned)fc2);
+            s_seed[pos + 1] = make_uint2(e.x, (unsigned)fc2 + 1u);
+          }
+        }
+        n += add;
+        __syncwarp();
+      }
+      if (lane == 0) s_nseed = n;
+    }
+    __syncthreads();
+  }
+
   while (true) {
     long long q = 0;
     if (lane == 0) q = (long long)atomicAdd(P.work_counter, 1ull);
@@ -1742,7 +1796,19 @@ __global__ void __launch_bounds__(128, 4) collide_front_kernel(CollideParams P) 
     long long count = 0;
     int sp = 0, nleaf = 0;
     uint32_t bv_tests = 1, leaf_tests = 0;
-    {  // root pair
+    if (kSeed) {  // one round over the seed pairs
+      const int n_test = s_nseed;
+      bool keep = false;
+      if (lane < n_test) {
+        const uint2 xy = s_seed[lane];
+        const ObbRec32 n1 = load_obb32(P.m1.obb32, (int)xy.x), n2 = load_obb32(P.m2.obb32, (int)xy.y);
+        keep = !obb_certainly_disjoint_f32(Rf, Tf, t_l1, n1, n2);
+      }
+      const unsigned km = __ballot_sync(0xffffffffu, keep);
+      if (keep) S.pair[__popc(km & lt_mask)] = s_seed_entry[lane];
+      sp = __popc(km);
+      bv_tests = (uint32_t)n_test;
+    } else {  // root pair
       const ObbRec32 n1 = load_obb32(P.m1.obb32, 0), n2 = load_obb32(P.m2.obb32, 0);
       int fc1, fc2;
       double size1, size2;
