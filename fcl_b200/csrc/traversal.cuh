@@ -757,8 +757,11 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
     // bounds are floats: (double)b < min_d  <=>  b < min_f with min_f = min_d rounded up (the smallest float >= min_d;
     // +inf for DBL_MAX)
     float min_f = __double2float_ru(min_d);
-    // (a finite start value prunes from the root pair on: far queries end after one box test, so no seed front then)
-    bool seed_pending = kSeed && !(min_d < DBL_MAX);
+    // (with a finite start value far queries end in their first round either way: root -> two children, or the seed pairs)
+#ifndef FCLGPU_DIST_SEED_CUTOFF
+#define FCLGPU_DIST_SEED_CUTOFF 1
+#endif
+    bool seed_pending = kSeed && (FCLGPU_DIST_SEED_CUTOFF || !(min_d < DBL_MAX));
     int sp = seed_pending ? 0 : 1, nleaf = 1, nraw = 0;
     uint32_t bv_tests = 0, leaf_tests = 0;
     if (lane == 0) {
