@@ -209,7 +209,7 @@ static double run_query(const SimModel& m1, const SimModel& m2, const double* po
     // ---- screening rounds
     if (o.mode == 0) {
       const bool can_screen = !raw.empty() && (exq.size() + std::min<size_t>(raw.size(), 32) <= 64);
-      if (can_screen && ((int)raw.size() >= o.raw_trigger || stack.empty())) {
+      if (can_screen && ((int)raw.size() >= o.raw_trigger || stack.empty() || (o.eager0 >= 2 && (int)raw.size() >= o.eager0 && !(min_f < 3.0e38f)))) {
         const int k = (int)std::min<size_t>(32, raw.size());
         int lanes = 0;
         float round_hi0 = 3.4e38f;
