@@ -106,3 +106,35 @@ def test_cfg5_full_size_one_million_triangles(oracle):
                          grow_on_overflow=True)
     rc = oracle.collide_batch(OA, OB, identity_poses(60), P[sub], INT_MAX, True, nthreads=8)
     assert np.array_equal(gc.num_contacts, rc["counts"]) and gc.contacts.tobytes() == rc["contacts"].tobytes()
+
+
+def test_distance_overflow_area_with_several_host_chunks(oracle):
+    """The distance front's HBM overflow area is one allocation per device while fclgpu_distance_batch_host alternates its
+    chunks on two streams: with a BVH pair of >= 2^17 nodes (the kSpill instantiation), a SMALL overflow area and small
+    host chunks, consecutive chunks' launches overlap in time and must still not disturb each other's parked entries
+    (launches that use the area on different streams are ordered by an event).  Distances = the oracle's, bit for bit."""
+    from fcl_b200 import _capi
+
+    va, ta = noisy_sphere(1.0, 190, 181, seed=31)  # ~68k triangles -> 137k nodes: >= 2^17 together with the second mesh
+    vb, tb = noisy_sphere(1.0, 60, 61, seed=32)
+    A, B = F.BVHModel.from_arrays(va, ta), F.BVHModel.from_arrays(vb, tb)
+    assert A.getNumBVs() + B.getNumBVs() >= (1 << 17)
+    OA, OB = oracle.Model(va, ta), oracle.Model(vb, tb)
+    rng = np.random.default_rng(8)
+    n = 6000
+    ang = rng.uniform(0, 2 * np.pi, size=(n, 3))
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    P = np.empty((n, 12))
+    P[:, :9] = euler_to_matrix(ang[:, 0], ang[:, 1], ang[:, 2]).reshape(n, 9)
+    P[:, 9:] = d * rng.uniform(0.0, 2.6, size=(n, 1))  # from coincident centres (wide, unprunable fronts) to apart
+    ref = oracle.distance_batch(OA, OB, identity_poses(n), P, True, 2, nthreads=8)
+    try:
+        _capi.set_option("dist_spill_entries", 256)  # one block of parked entries per warp: refills happen all the time
+        _capi.set_option("host_chunk", 1024)          # six chunks alternating on the two pipeline streams
+        for pinned in (False, True):
+            got = F.distance_batch(A, identity_poses(n), B, P, F.DistanceRequest(True), pinned=pinned)
+            assert np.array_equal(got.min_distance, ref["min_distance"]), pinned
+    finally:
+        _capi.set_option("dist_spill_entries", 4096)
+        _capi.set_option("host_chunk", 1 << 17)
