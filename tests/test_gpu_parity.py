@@ -688,3 +688,45 @@ def test_upload_with_separate_rss_axes(models, oracle):
         assert np.array_equal(cnt, oracle.collide_batch(oenv, orob, P, None, 1, False, nthreads=8)["counts"])
     finally:
         L.fclgpu_model_destroy(m2)
+
+
+def test_concurrent_contact_queries_on_two_streams(models, oracle):
+    """Two contact-generating fclgpu_collide_batch calls in flight on DIFFERENT streams of one device (and two distance
+    calls): the contact staging is one allocation per device, so the library orders such launches with an event; running
+    totals, offsets and the sticky status are per stream.  Both results equal the oracle's; an overflow on one stream is
+    reported on that stream only."""
+    import torch
+
+    (env, rob), (oenv, orob) = models
+    dev = torch.device("cuda", 0)
+    n = 6000
+    sets = [random_poses(n, seed=61), random_poses(n, seed=62)]
+    refs = [oracle.collide_batch(oenv, orob, P, None, 20, True, nthreads=8) for P in sets]
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    outs = []
+    for rep in range(3):  # several rounds back to back: the second call is enqueued while the first is running
+        outs = []
+        for P, st in zip(sets, streams):
+            dP = torch.from_numpy(P).to(dev)
+            cnt = torch.zeros(n, dtype=torch.int32, device=dev)
+            con = torch.zeros(20 * n * 64, dtype=torch.uint8, device=dev)
+            off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+            st.wait_stream(torch.cuda.current_stream(dev))
+            F.collide_batch_device(env, dP, rob, None, F.CollisionRequest(20, True), cnt, con, off, stream=st)
+            outs.append((dP, cnt, con, off))
+        for st in streams:
+            F.sync_status(0, st)
+    for (dP, cnt, con, off), ref in zip(outs, refs):
+        res = F.BatchCollisionResult(cnt.cpu().numpy(), np.frombuffer(con.cpu().numpy().tobytes(), dtype=F.api.CONTACT_DTYPE), off.cpu().numpy())
+        assert np.array_equal(res.num_contacts, ref["counts"])
+        assert res.contacts[: ref["offsets"][-1]].tobytes() == ref["contacts"].tobytes()
+    # an overflow on one stream does not show on the other
+    small = torch.zeros(10 * 64, dtype=torch.uint8, device=dev)
+    dP, cnt, con, off = outs[0]
+    F.collide_batch_device(env, dP, rob, None, F.CollisionRequest(20, True), cnt, small, off, stream=streams[0])
+    dP1, cnt1, con1, off1 = outs[1]
+    F.collide_batch_device(env, dP1, rob, None, F.CollisionRequest(20, True), cnt1, con1, off1, stream=streams[1])
+    F.sync_status(0, streams[1])  # clean
+    with pytest.raises(F.FclGpuError):
+        F.sync_status(0, streams[0])
+    F.sync_status(0, streams[0])  # the sticky word was cleared by the read
