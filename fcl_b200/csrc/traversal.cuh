@@ -763,6 +763,7 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
 #endif
     bool seed_pending = kSeed && (FCLGPU_DIST_SEED_CUTOFF || !(min_d < DBL_MAX));
     int sp = seed_pending ? 0 : 1, nleaf = 1, nraw = 0;
+    bool had_exact = false;
     uint32_t bv_tests = 0, leaf_tests = 0;
     if (lane == 0) {
       S.pair[0] = s_root;
@@ -812,7 +813,15 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
       // the screening round may add up to min(nraw, 32) pairs to the exact queue: only run it when they fit
       // (otherwise the exact queue is at least half full and the exact round below drains it first)
       const bool can_screen = kBound32 && kScreen && nraw > 0 && (nleaf + (nraw < 32 ? nraw : 32) <= kLeafCap);
-      if (can_screen && (nraw >= 32 || sp == 0)) {
+      // Early first minimum (FCLGPU_DIST_EAGER > 0): until an exact round has run nothing is pruned, so the first one is
+      // not held back until 32 pairs are queued -- a screening round starts at FCLGPU_DIST_EAGER raw pairs and the exact round
+      // follows at once.
+#ifndef FCLGPU_DIST_EAGER
+#define FCLGPU_DIST_EAGER 16
+#endif
+      // (only with the screening round, i.e. cache-resident models: on cfg5 the early round costs 4 %)
+      const bool eager = FCLGPU_DIST_EAGER > 0 && kBound32 && kScreen && !had_exact;
+      if (can_screen && (nraw >= 32 || sp == 0 || (eager && nraw >= FCLGPU_DIST_EAGER))) {
         // ---- screening round: triangle-level lower bound (FP32, branch-free) on up to 32 raw leaf pairs;
         // only pairs that can still beat the minimum go on to the exact queue
         const int k = nraw < 32 ? nraw : 32;
@@ -855,8 +864,9 @@ __global__ void __launch_bounds__(kDistWarps * 32, FCLGPU_DIST_MINBLOCKS) distan
         DPROF_MARK(2)
         continue;
       }
-      const bool do_leaf = (nleaf >= kLeafTrigger) || (sp == 0 && nleaf > 0 && !seed_pending);
+      const bool do_leaf = (nleaf >= kLeafTrigger) || (sp == 0 && nleaf > 0 && !seed_pending) || (eager && nleaf > 1);
       if (do_leaf) {
+        had_exact = true;
         const int k = nleaf < 32 ? nleaf : 32;
         nleaf -= k;
         double d = 1.7976931348623157e308;
