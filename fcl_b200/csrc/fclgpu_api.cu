@@ -72,6 +72,8 @@ std::map<std::string, long long> g_opts = {
     {"dist_spill_entries", 4096},  // per-warp global overflow entries of the distance front (allocated for big models)
     {"collide_front", 1},      // counts-only collide: warp-per-query front kernel (0 never, 1 big BVHs and small batches, 2 always)
     {"front_small_batch", 131072},  // ... batches of at most this many queries count as small
+    {"front_leaf_trigger", 0},  // front kernel: triangle pairs queued before a leaf round while the query can still saturate (0 = 8 for BVHs beyond the caches, else 32)
+    {"front_cap", 0},          // front kernel: stack entries per warp (0 = default, 384; measured 256 .. 2048)
     {"host_chunk", 1 << 17},   // queries per stage of the host API's two-stream copy/compute pipeline
     {"contact_stride", 1024},  // contact staging slots per query (per resident warp on the ordered-front path) when num_max_contacts is larger
     // layout of a contact list: 0 (default) = blocks appended in completion order by the one-launch ordered-front kernel
@@ -1105,6 +1107,7 @@ int collide_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, c
     P.ready_shift = X.ready_shift;
     P.ready_q0 = X.ready_q0 + s;
     P.order = nullptr;
+    P.front_cap = P.front_reserve = P.front_leaf_trigger = 0;
     const long long trav = trav0;
     const int trig = (int)opt("leaf_trigger");
     const long long front = opt("collide_front");  // 0 never, 1 (default) for BVHs beyond the caches, 2 always
@@ -1122,7 +1125,16 @@ int collide_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, c
       // beyond the caches (memory-level parallelism) and for SMALL batches: a lane-per-query launch cannot end before
       // its longest query (~0.8 ms on env/rob), a warp-per-query launch spreads every query over 32 lanes
       // (BASELINE cfg1 at its real size, 10k poses: 0.83 ms -> 0.11 ms)
-      const size_t fsm = sizeof(CollideFront) * 4;
+      P.front_reserve = m1->depth + m2->depth + 2 + 32;
+      const long long cap_opt = opt("front_cap");
+      P.front_cap = (int)std::min<long long>(std::max<long long>(cap_opt > 0 ? cap_opt : 384, P.front_reserve + 64), 3072);
+      // A query whose count is within 32 of num_max_contacts (every verdict query) may end at its next leaf round.  With the
+      // BVH in L2 / HBM a BV round costs its load latency, an early, partly filled leaf round is cheap next to the rounds it
+      // saves (cfg4 21.6 -> 19.9 ms, cfg5 5.44 -> 4.84 ms); with cache-resident models (env/rob) it is not (0.087 -> 0.102 ms).
+      const bool beyond_caches = (long long)m1->d.n_nodes + m2->d.n_nodes >= (1 << 17);
+      const long long trig_opt = opt("front_leaf_trigger");
+      P.front_leaf_trigger = (int)std::min<long long>(trig_opt > 0 ? trig_opt : (beyond_caches ? 8 : 32), 32);
+      const size_t fsm = front_bytes_per_warp(P.front_cap) * 4;
       rc = stats ? launch_persistent(collide_front_kernel<true>, P, w, 128, st, fsm)
                  : launch_persistent(collide_front_kernel<false>, P, w, 128, st, fsm);
     } else if (trav >= 2 && !P.enable_contact && (trav == 2 || !opt("binary_pooled"))) {

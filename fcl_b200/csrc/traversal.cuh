@@ -197,6 +197,11 @@ struct CollideParams {
   // locality order (query_order.cuh): the i-th unit of work is query order[i]; nullptr = batch order.  Results are
   // written at the query's own index, so the order never shows in an output.
   const int32_t* order;
+  // collide_front_kernel: stack entries per warp and the head room kept for the depth-first mode
+  // (depth1 + depth2 + 2 for the descent, + 32 for the wide round that crossed the limit)
+  int front_cap;
+  int front_reserve;
+  int front_leaf_trigger;  // queued triangle pairs that start a leaf round while fewer than 32 more contacts end the query
 };
 
 // Spin until the chunk that holds query q has landed.  Acquire load: the pose loads that follow cannot be
@@ -1707,19 +1712,59 @@ namespace fclgpu {
 #ifndef FCLGPU_FRONT_SEED
 #define FCLGPU_FRONT_SEED 5
 #endif
-constexpr int kFrontStackCap = 512;
+// FCLGPU_FRONT_STAGE (measured and rejected; kept compiled out): the box records of a BV round fetched by FOUR
+// lanes per record (16 bytes each, one 64-byte request per record) into a shared-memory staging area and read back by the
+// lanes that test them, instead of every lane fetching its two 64-byte records with eight divergent 16-byte loads.  A
+// third of the L1 wavefronts, but global load -> shared store -> barrier -> shared load is a longer dependent chain per round
+// and the kernel is latency bound: cfg1 0.087 -> 0.111 ms, cfg4 21.8 -> 27.1 ms per 1M configurations.
+#ifndef FCLGPU_FRONT_STAGE
+#define FCLGPU_FRONT_STAGE 0
+#endif
+// Stack entries per warp: a launch parameter (CollideParams::front_cap, dynamic shared memory).  Rounds are 32 wide while the
+// stack is below cap - front_reserve and depth first (one entry per round, growth bounded by the two tree depths) above it;
+// on BVHs beyond the caches the width of the rounds is what hides the HBM latency, so big models get the larger stack.
+// FCLGPU_FRONT_DUAL = n > 0 (measured and rejected; compiled out): a round that popped more than n internal pairs
+// expands ALL of them, one lane per pair and both children per lane, instead of 16 of them with two lanes per pair.  Half
+// the rounds on wide fronts, but the traversal becomes breadth first and a colliding query reaches its first intersecting
+// triangle pair much later: cfg4 21.4 -> 30.8 ms, cfg5 verdicts 5.4 -> 8.9 ms.
+#ifndef FCLGPU_FRONT_DUAL
+#define FCLGPU_FRONT_DUAL 0
+#endif
+#ifndef FCLGPU_FRONT_NEXP
+#define FCLGPU_FRONT_NEXP 16  // pairs expanded per round (two lanes each)
+#endif
+#ifndef FCLGPU_FRONT_MINBLOCKS
+#define FCLGPU_FRONT_MINBLOCKS 4
+#endif
 constexpr int kFrontLeafCap = 64;
-
+constexpr int kFrontStageRecs = FCLGPU_FRONT_STAGE ? 48 : 0;
 // A front entry carries everything the NEXT round needs to expand it without touching memory: both node ids, both
 // first_child fields (fetched, together with the box records, when the pair was tested) and the firstOverSecond decision
 // (bit 31 of b1).  A round is then pop -> expand -> ONE dependent global-load phase (records + topo of the two children)
 // -> test -> push, instead of two phases (topo of the popped pair, then the children's records): the kernel is latency
 // bound once the BVH leaves the caches (ncu on cfg5: 55 % of the stall samples were long_scoreboard).
-struct __align__(16) CollideFront {
-  uint4 pair[kFrontStackCap];  // {b1 | split-first flag, b2, first_child1, first_child2}
-  uint2 leaf[kFrontLeafCap];
-  uint4 expand[32];            // {node1, node2, first_child of the node that was NOT split (carried), which side was split}
+struct CollideFront {
+  uint4* pair;    // [cap] {b1 | split-first flag, b2, first_child1, first_child2}
+  uint2* leaf;    // [kFrontLeafCap]
+  uint4* expand;  // [32] {node1, node2, first_child of the node that was NOT split (carried), which side was split}
+  float4* stage;  // [kFrontStageRecs * 4] staged box records: slot s, 16-byte piece p at [4 s + (p ^ ((s >> 1) & 3))] (no bank conflicts)
 };
+inline __host__ __device__ size_t front_bytes_per_warp(int cap) {
+  return (size_t)cap * sizeof(uint4) + kFrontLeafCap * sizeof(uint2) + 32 * sizeof(uint4) + (size_t)kFrontStageRecs * 4 * sizeof(float4);
+}
+
+// piece p of staged record `slot`
+__device__ __forceinline__ int front_stage_index(int slot, int p) { return 4 * slot + (p ^ ((slot >> 1) & 3)); }
+__device__ __forceinline__ ObbRec32 front_staged_obb32(const float4* stage, int slot) {
+  const float4 v0 = stage[front_stage_index(slot, 0)], v1 = stage[front_stage_index(slot, 1)];
+  const float4 v2 = stage[front_stage_index(slot, 2)], v3 = stage[front_stage_index(slot, 3)];
+  ObbRec32 n;
+  n.a[0] = v0.x; n.a[1] = v0.y; n.a[2] = v0.z; n.a[3] = v0.w;
+  n.a[4] = v1.x; n.a[5] = v1.y; n.a[6] = v1.z; n.a[7] = v1.w;
+  n.a[8] = v2.x; n.c[0] = v2.y; n.c[1] = v2.z; n.c[2] = v2.w;
+  n.e[0] = v3.x; n.e[1] = v3.y; n.e[2] = v3.z; n.s = v3.w;
+  return n;
+}
 
 __device__ __forceinline__ uint4 front_entry(int b1, int b2, int fc1, double size1, int fc2, double size2) {
   const bool l1 = fc1 < 0, l2 = fc2 < 0;
@@ -1728,9 +1773,14 @@ __device__ __forceinline__ uint4 front_entry(int b1, int b2, int fc1, double siz
 }
 
 template <bool kStats>
-__global__ void __launch_bounds__(128, 4) collide_front_kernel(CollideParams P) {
+__global__ void __launch_bounds__(128, FCLGPU_FRONT_MINBLOCKS) collide_front_kernel(CollideParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  CollideFront& S = reinterpret_cast<CollideFront*>(smem_raw)[threadIdx.x >> 5];
+  CollideFront S;
+  S.pair = reinterpret_cast<uint4*>(smem_raw + (size_t)(threadIdx.x >> 5) * front_bytes_per_warp(P.front_cap));
+  S.leaf = reinterpret_cast<uint2*>(S.pair + P.front_cap);
+  S.expand = reinterpret_cast<uint4*>(S.leaf + kFrontLeafCap);
+  S.stage = reinterpret_cast<float4*>(S.expand + 32);
+  const int wide_limit = P.front_cap - P.front_reserve;  // above it: one entry per round
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -1835,7 +1885,7 @@ __global__ void __launch_bounds__(128, 4) collide_front_kernel(CollideParams P) 
     __syncwarp();
 
     while (true) {
-      const bool do_leaf = (nleaf >= 32) || (sp == 0 && nleaf > 0);
+      const bool do_leaf = (nleaf >= (P.max_contacts - count < 32 ? P.front_leaf_trigger : 32)) || (sp == 0 && nleaf > 0);
       if (do_leaf) {
         const int k = nleaf < 32 ? nleaf : 32;
         nleaf -= k;
@@ -1861,7 +1911,7 @@ __global__ void __launch_bounds__(128, 4) collide_front_kernel(CollideParams P) 
       if (sp == 0) break;
 
       // ---- BV round: entries on the stack are known to overlap; no memory access before the expansion ----
-      const bool tight = sp > kFrontStackCap - 160;  // close to the limit: one entry per round (depth-first)
+      const bool tight = sp > wide_limit;  // close to the limit: one entry per round (depth-first)
       const int k = tight ? 1 : (sp < 32 ? sp : 32);
       uint4 pr = make_uint4(0u, 0u, 0u, 0u);
       const bool have = lane < k;
@@ -1875,8 +1925,36 @@ __global__ void __launch_bounds__(128, 4) collide_front_kernel(CollideParams P) 
       const unsigned im = __ballot_sync(0xffffffffu, internal);
       const int n_int = __popc(im), rank = __popc(im & lt_mask);
       sp -= k;
-      const int n_exp = n_int < 16 ? n_int : 16;
+      const int n_exp = n_int < FCLGPU_FRONT_NEXP ? n_int : FCLGPU_FRONT_NEXP;
       __syncwarp();  // every lane has read its popped entry before slots are overwritten
+      if (FCLGPU_FRONT_DUAL && n_int > FCLGPU_FRONT_DUAL) {
+        // wide front: every lane expands the entry it popped and tests BOTH children (no hand-over through shared memory, no
+        // entry pushed back): the same loads per expanded entry as below, all in flight at once, and half as many rounds --
+        // with the BVH in HBM a round costs its load latency however many tests follow it
+        bool keep_a = false, keep_b = false;
+        uint4 ent_a = make_uint4(0u, 0u, 0u, 0u), ent_b = ent_a;
+        if (internal) {
+          const unsigned b1 = pr.x & 0x7fffffffu, b2 = pr.y;
+          const bool split1 = (pr.x >> 31) != 0u;
+          const unsigned x_a = split1 ? (unsigned)fc1 : b1, x_b = split1 ? (unsigned)fc1 + 1u : b1;
+          const unsigned y_a = split1 ? b2 : (unsigned)fc2, y_b = split1 ? b2 : (unsigned)fc2 + 1u;
+          const ObbRec32 n1a = load_obb32(P.m1.obb32, (int)x_a), n2a = load_obb32(P.m2.obb32, (int)y_a);
+          const ObbRec32 n1b = load_obb32(P.m1.obb32, (int)x_b), n2b = load_obb32(P.m2.obb32, (int)y_b);
+          const double2 t1a = __ldg(P.m1.topo + x_a), t2a = __ldg(P.m2.topo + y_a);
+          const double2 t1b = __ldg(P.m1.topo + x_b), t2b = __ldg(P.m2.topo + y_b);
+          keep_a = !obb_certainly_disjoint_f32(Rf, Tf, t_l1, n1a, n2a);
+          ent_a = front_entry((int)x_a, (int)y_a, __double2loint(t1a.x), t1a.y, __double2loint(t2a.x), t2a.y);
+          keep_b = !obb_certainly_disjoint_f32(Rf, Tf, t_l1, n1b, n2b);
+          ent_b = front_entry((int)x_b, (int)y_b, __double2loint(t1b.x), t1b.y, __double2loint(t2b.x), t2b.y);
+        }
+        if (kStats) bv_tests += 2 * n_int;
+        const unsigned ka = __ballot_sync(0xffffffffu, keep_a), kb = __ballot_sync(0xffffffffu, keep_b);
+        if (keep_a) S.pair[sp + __popc(ka & lt_mask)] = ent_a;
+        if (keep_b) S.pair[sp + __popc(ka) + __popc(kb & lt_mask)] = ent_b;
+        sp += __popc(ka) + __popc(kb);
+        __syncwarp();
+        continue;
+      }
       if (internal) {
         if (rank < n_exp) {
           const unsigned b1 = pr.x & 0x7fffffffu;
@@ -1895,7 +1973,45 @@ __global__ void __launch_bounds__(128, 4) collide_front_kernel(CollideParams P) 
       __syncwarp();
       bool keep = false;
       uint4 entry = make_uint4(0u, 0u, 0u, 0u);
-      if (lane < 2 * n_exp) {
+      if (FCLGPU_FRONT_STAGE) {
+        // one load phase: the records by four lanes each (slots 0..31: the children, in expand[] order; slots 32..47: the node
+        // of the other model, one per expansion), and {first_child, size} of both nodes for the entry to be pushed
+        const int sub = lane >> 2, piece = lane & 3;
+        float4 v[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const bool child = i < 4;
+          const int t = child ? 8 * i + sub : 8 * (i - 4) + sub;  // child: expand[] index, other: expansion index
+          if (child ? (t < 2 * n_exp) : (t < n_exp)) {
+            const uint4 e = S.expand[child ? t : 2 * t];
+            const bool from1 = child ? (e.w != 0u) : (e.w == 0u);
+            const float4* p = reinterpret_cast<const float4*>(from1 ? P.m1.obb32 + e.x : P.m2.obb32 + e.y) + piece;
+            v[i] = __ldg(p);
+          }
+        }
+        uint4 xy = make_uint4(0u, 0u, 0u, 0u);
+        double2 t1 = make_double2(0.0, 0.0), t2 = t1;
+        if (lane < 2 * n_exp) {
+          xy = S.expand[lane];
+          t1 = __ldg(P.m1.topo + xy.x);
+          t2 = __ldg(P.m2.topo + xy.y);
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const bool child = i < 4;
+          const int t = child ? 8 * i + sub : 8 * (i - 4) + sub;
+          if (child ? (t < 2 * n_exp) : (t < n_exp)) S.stage[front_stage_index(child ? t : 32 + t, piece)] = v[i];
+        }
+        __syncwarp();
+        if (lane < 2 * n_exp) {
+          const int child_slot = lane, other_slot = 32 + (lane >> 1);
+          const bool split1 = xy.w != 0u;
+          const ObbRec32 n1 = front_staged_obb32(S.stage, split1 ? child_slot : other_slot);
+          const ObbRec32 n2 = front_staged_obb32(S.stage, split1 ? other_slot : child_slot);
+          keep = !obb_certainly_disjoint_f32(Rf, Tf, t_l1, n1, n2);
+          entry = front_entry((int)xy.x, (int)xy.y, __double2loint(t1.x), t1.y, __double2loint(t2.x), t2.y);
+        }
+      } else if (lane < 2 * n_exp) {
         const uint4 xy = S.expand[lane];
         // one load phase: both box records, and {first_child, size} of both nodes for the entry to be pushed
         const ObbRec32 n1 = load_obb32(P.m1.obb32, (int)xy.x);
