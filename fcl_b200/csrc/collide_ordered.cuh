@@ -50,6 +50,13 @@ constexpr int kOrdWarps = 4;      // warps per block
 #ifndef FCLGPU_ORD_SEED
 #define FCLGPU_ORD_SEED 5
 #endif
+// Pre-expanded entries (like the distance kernel's FCLGPU_DIST_PREX): the lane that tests a child pair also reads the two
+// topology records -- in the same load phase as the box records -- and stores the pair in the form the next round needs:
+// {triangle ids} for a leaf pair, {first child of the node firstOverSecond splits | side, other node} otherwise.  A BV round
+// is then pop -> expand -> ONE dependent load phase -> test -> push instead of two (topology of the popped pairs first).
+#ifndef FCLGPU_ORD_PREX
+#define FCLGPU_ORD_PREX 1
+#endif
 #ifndef FCLGPU_ORD_ROLLED
 #define FCLGPU_ORD_ROLLED 1      // rolled-loop triangle SAT (compact code)
 #endif
@@ -114,7 +121,9 @@ __global__ void __launch_bounds__(kOrdWarps * 32, FCLGPU_ORD_MINBLOCKS) collide_
   const bool coherent = P.ready != nullptr;
 
   constexpr bool kSeed = FCLGPU_ORD_SEED > 0;
+  constexpr bool kPrex = FCLGPU_ORD_PREX != 0;
   __shared__ uint2 s_seed[32];
+  __shared__ uint2 s_seed_entry[32];
   __shared__ int s_nseed;
   if (kSeed) {
     if (threadIdx.x < 32) {
@@ -151,6 +160,14 @@ __global__ void __launch_bounds__(kOrdWarps * 32, FCLGPU_ORD_MINBLOCKS) collide_
         }
         n += add;
         __syncwarp();
+      }
+      if (kPrex && lane < n) {
+        const uint2 e = s_seed[lane];
+        int fc1, fc2;
+        double size1, size2;
+        load_topo(P.m1.topo, (int)e.x, fc1, size1);
+        load_topo(P.m2.topo, (int)e.y, fc2, size2);
+        s_seed_entry[lane] = prex_entry(e.x, e.y, fc1, size1, fc2, size2);
       }
       if (lane == 0) s_nseed = n;
     }
@@ -199,12 +216,20 @@ __global__ void __launch_bounds__(kOrdWarps * 32, FCLGPU_ORD_MINBLOCKS) collide_
       }
       const unsigned km = __ballot_sync(0xffffffffu, keep);
       sp = __popc(km);
-      if (keep) S.pair[sp - 1 - __popc(km & lt_mask)] = xy;
+      if (keep) S.pair[sp - 1 - __popc(km & lt_mask)] = kPrex ? s_seed_entry[lane] : xy;
       bv_tests = (uint32_t)n_test;
     } else {  // root pair
       const ObbRec32 n1 = load_obb32(P.m1.obb32, 0), n2 = load_obb32(P.m2.obb32, 0);
       if (!obb_certainly_disjoint_f32(Rf, Tf, t_l1, n1, n2)) {
-        if (lane == 0) S.pair[0] = make_uint2(0u, 0u);
+        uint2 root = make_uint2(0u, 0u);
+        if (kPrex) {
+          int fc1, fc2;
+          double size1, size2;
+          load_topo(P.m1.topo, 0, fc1, size1);
+          load_topo(P.m2.topo, 0, fc2, size2);
+          root = prex_entry(0u, 0u, fc1, size1, fc2, size2);
+        }
+        if (lane == 0) S.pair[0] = root;
         sp = 1;
       }
     }
@@ -308,22 +333,35 @@ __global__ void __launch_bounds__(kOrdWarps * 32, FCLGPU_ORD_MINBLOCKS) collide_
       const bool have = lane < k;
       if (have) {
         pr = S.pair[sp - 1 - lane];
-        load_topo(P.m1.topo, (int)pr.x, fc1, size1);
-        load_topo(P.m2.topo, (int)pr.y, fc2, size2);
+        if (!kPrex) {
+          load_topo(P.m1.topo, (int)pr.x, fc1, size1);
+          load_topo(P.m2.topo, (int)pr.y, fc2, size2);
+        }
       }
       const bool l1 = fc1 < 0, l2 = fc2 < 0;
-      const bool leafpair = have && l1 && l2;
+      const bool leafpair = have && (kPrex ? (pr.x >> 31) != 0u : (l1 && l2));
       const bool internal = have && !leafpair;
       const unsigned im = __ballot_sync(0xffffffffu, internal);
       const int lead = im ? (__ffs(im) - 1) : k;  // leaf pairs ahead of every internal entry: next in DFS order
-      if (lane < lead) S.leaf[(head + nleaf + lane) & (kOrdLeafCap - 1)] = make_uint2((unsigned)(-(fc1 + 1)), (unsigned)(-(fc2 + 1)));
+      if (lane < lead)
+        S.leaf[(head + nleaf + lane) & (kOrdLeafCap - 1)] =
+            kPrex ? make_uint2(pr.x & 0x7fffffffu, pr.y) : make_uint2((unsigned)(-(fc1 + 1)), (unsigned)(-(fc2 + 1)));
       nleaf += lead;
       const int n_int = __popc(im), rank = __popc(im & lt_mask);
       const int n_exp = n_int < 16 ? n_int : 16;
       const bool expanded = internal && rank < n_exp;
       __syncwarp();  // every lane holds its popped entry before slots are overwritten
       if (expanded) {
-        if (l2 || (!l1 && (size1 > size2))) {  // firstOverSecond
+        if (kPrex) {
+          const unsigned fc = pr.x & 0x3fffffffu;
+          if (pr.x & 0x40000000u) {  // model 1's node is split
+            S.expand[2 * rank] = make_uint2(fc, pr.y);
+            S.expand[2 * rank + 1] = make_uint2(fc + 1u, pr.y);
+          } else {
+            S.expand[2 * rank] = make_uint2(pr.y, fc);
+            S.expand[2 * rank + 1] = make_uint2(pr.y, fc + 1u);
+          }
+        } else if (l2 || (!l1 && (size1 > size2))) {  // firstOverSecond
           S.expand[2 * rank] = make_uint2((unsigned)fc1, pr.y);
           S.expand[2 * rank + 1] = make_uint2((unsigned)fc1 + 1u, pr.y);
         } else {
@@ -338,7 +376,16 @@ __global__ void __launch_bounds__(kOrdWarps * 32, FCLGPU_ORD_MINBLOCKS) collide_
         xy = S.expand[lane];
         const ObbRec32 n1 = load_obb32(P.m1.obb32, (int)xy.x);
         const ObbRec32 n2 = load_obb32(P.m2.obb32, (int)xy.y);
-        keep = !obb_certainly_disjoint_f32(Rf, Tf, t_l1, n1, n2);
+        if (kPrex) {
+          int tfc1, tfc2;
+          double tsz1, tsz2;
+          load_topo(P.m1.topo, (int)xy.x, tfc1, tsz1);
+          load_topo(P.m2.topo, (int)xy.y, tfc2, tsz2);
+          keep = !obb_certainly_disjoint_f32(Rf, Tf, t_l1, n1, n2);
+          xy = prex_entry(xy.x, xy.y, tfc1, tsz1, tfc2, tsz2);
+        } else {
+          keep = !obb_certainly_disjoint_f32(Rf, Tf, t_l1, n1, n2);
+        }
       }
       if (kStats) bv_tests += 2 * n_exp;
       const unsigned km = __ballot_sync(0xffffffffu, keep);
