@@ -524,6 +524,27 @@ def test_counts_only_front_kernel_matches_oracle(models, oracle):
         _capi.set_option("collide_front", 1)
 
 
+def test_front_kernel_stack_and_leaf_trigger_settings_do_not_change_counts(models, oracle):
+    """The front kernel's schedule knobs only move work around: with the smallest stack the library accepts (the rounds are
+    depth first almost all the time), with a large one, and with leaf rounds started at 1 / 8 / 32 queued triangle pairs the
+    counts equal the oracle's for every budget."""
+    (env, rob), (oenv, orob) = models
+    P = random_poses(6000, seed=77)
+    refs = {m: oracle.collide_batch(oenv, orob, P, None, m, False, nthreads=8)["counts"] for m in (1, 40, 100000)}
+    _capi.set_option("collide_front", 2)
+    try:
+        for cap, trig in ((1, 32), (1, 1), (384, 8), (2048, 1), (100000, 32)):  # the library clamps cap to [depths + 98, 3072]
+            _capi.set_option("front_cap", cap)
+            _capi.set_option("front_leaf_trigger", trig)
+            for max_contacts, ref in refs.items():
+                got = F.collide_batch(env, P, rob, None, F.CollisionRequest(max_contacts, False), want_contacts=False)
+                assert np.array_equal(got.num_contacts, ref), (cap, trig, max_contacts)
+    finally:
+        _capi.set_option("collide_front", 1)
+        _capi.set_option("front_cap", 0)
+        _capi.set_option("front_leaf_trigger", 0)
+
+
 def test_tiny_and_coincident_models_all_variants(oracle):
     """Edge cases of the traversals: models of 1..9 triangles (single-node trees, leaf-vs-internal pairs), identical
     poses (coincident meshes: every tie-break and touching rule is exercised), far-apart poses (root boxes disjoint).
