@@ -7,6 +7,8 @@ cp $O/launches_bench.csv profiles/r02_launches_bench.csv
 cp $O/full_distance.summary.txt profiles/r02_ncu_distance.txt
 cp $O/full_contacts.summary.txt profiles/r02_ncu_contacts.txt
 cp $O/full_collide.summary.txt profiles/r02_ncu_collide.txt
+cp $O/full_cfg4.summary.txt profiles/r02_ncu_cfg4_front.txt
+cp $O/full_cfg5_distance.summary.txt profiles/r02_ncu_cfg5_distance.txt
 cp $O/pytest_gpu.log profiles/r02_pytest_gpu.log
 cp $O/sanitizer_memcheck.log profiles/r02_sanitizer_memcheck.log
 python - <<'PY'
