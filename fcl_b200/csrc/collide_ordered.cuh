@@ -57,6 +57,12 @@ constexpr int kOrdWarps = 4;      // warps per block
 #ifndef FCLGPU_ORD_PREX
 #define FCLGPU_ORD_PREX 1
 #endif
+#ifndef FCLGPU_ORD_NEXP
+#define FCLGPU_ORD_NEXP 16          // entries expanded per BV round (two lanes each)
+#endif
+#ifndef FCLGPU_ORD_LEAF_TRIGGER
+#define FCLGPU_ORD_LEAF_TRIGGER 32  // queued triangle pairs that start a leaf round
+#endif
 #ifndef FCLGPU_ORD_ROLLED
 #define FCLGPU_ORD_ROLLED 1      // rolled-loop triangle SAT (compact code)
 #endif
@@ -236,7 +242,7 @@ __global__ void __launch_bounds__(kOrdWarps * 32, FCLGPU_ORD_MINBLOCKS) collide_
     __syncwarp();
 
     while (true) {
-      if (nleaf >= 32 || (sp == 0 && nleaf > 0)) {
+      if (nleaf >= FCLGPU_ORD_LEAF_TRIGGER || (sp == 0 && nleaf > 0)) {
         // ---- leaf round: the next <= 32 triangle pairs of the depth-first order ----
         const int k = nleaf < 32 ? nleaf : 32;
         const bool mine = lane < k;
@@ -348,7 +354,7 @@ __global__ void __launch_bounds__(kOrdWarps * 32, FCLGPU_ORD_MINBLOCKS) collide_
             kPrex ? make_uint2(pr.x & 0x7fffffffu, pr.y) : make_uint2((unsigned)(-(fc1 + 1)), (unsigned)(-(fc2 + 1)));
       nleaf += lead;
       const int n_int = __popc(im), rank = __popc(im & lt_mask);
-      const int n_exp = n_int < 16 ? n_int : 16;
+      const int n_exp = n_int < FCLGPU_ORD_NEXP ? n_int : FCLGPU_ORD_NEXP;
       const bool expanded = internal && rank < n_exp;
       __syncwarp();  // every lane holds its popped entry before slots are overwritten
       if (expanded) {

@@ -25,5 +25,6 @@ for w in cfg4 cfg5_distance; do
   python tools/ncu_by_function.py $O/full_$w.ncu-rep >> $O/full_$w.summary.txt 2>&1
   grep -E "::|gpu__time_duration|dram__bytes" $O/full_$w.summary.txt | head -4
 done
+rm -f $O/full_collide.ncu-rep $O/full_cfg4.ncu-rep $O/full_cfg5_distance.ncu-rep  # gpurun_out is limited to 64 MiB; the summaries stay
 timeout 1500 python -m pytest tests -m gpu -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_gpu.log
 timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_run.py > $O/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 $O/sanitizer_memcheck.log
