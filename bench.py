@@ -332,17 +332,38 @@ class Ctx:
                 ms += e0.elapsed_time(e1)
             torch.cuda.synchronize()
             return ms
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for k in range(steps):
-            self.flush.fill_(1)
-            fn(k)
-        if drain:
-            drain()
-        e1.record()
-        e1.synchronize()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
+        # N > 1: the K steps are enqueued back to back (no host synchronisation inside, so the gather of step k overlaps step
+        # k + 1); like at N = 1 the L2 flush between steps is outside the events, and the part of the last gather that is
+        # still running when the last step ends is timed by its own pair of events
+        if os.environ.get("FCLGPU_BENCH_TIMING") == "loop":  # diagnosis: one pair of events around the loop, flushes included
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for k in range(steps):
+                self.flush.fill_(1)
+                fn(k)
+            if drain:
+                drain()
+            e1.record()
+            e1.synchronize()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+        else:
+            evs = []
+            for k in range(steps):
+                self.flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn(k)
+                e1.record()
+                evs.append((e0, e1))
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            d0.record()
+            if drain:
+                drain()
+            d1.record()
+            d1.synchronize()
+            torch.cuda.synchronize()
+            ms = sum(a.elapsed_time(b) for a, b in evs) + d0.elapsed_time(d1)
         dist.barrier()
         t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -367,7 +388,7 @@ class Ctx:
     # ---- results of step k leave over NVLink while step k+1 computes (one packed record buffer per step) ----
     def gather_async(self, local_buf, out_buf):
         torch, dist = self.torch, self.dist
-        if self.world == 1:
+        if self.world == 1 or os.environ.get("FCLGPU_BENCH_NO_GATHER"):  # (the switch is for diagnosis only)
             return
         ev = torch.cuda.Event()
         ev.record()
@@ -377,6 +398,12 @@ class Ctx:
         rc = _capi.lib().fclgpu_comm_allgather(self.comm, local_buf.data_ptr(), out_buf.data_ptr(), local_buf.numel() * local_buf.element_size(),
                                                self.comm_stream.cuda_stream)
         assert rc == 0, _capi.lib().fclgpu_comm_last_error()
+        # the step after the next one reuses local_buf: it may not start before this gather has read it
+        done = torch.cuda.Event()
+        done.record(self.comm_stream)
+        prev, self._gather_done = getattr(self, "_gather_done", None), done
+        if prev is not None:
+            torch.cuda.current_stream().wait_event(prev)
 
     def drain(self):
         if self.world > 1:
@@ -788,14 +815,17 @@ def main():
         results[wl] = run_env_rob(ctx, wl, n, steps, args.warmup, (env, rob), meshes, with_cpu)
     clocks = sampler.stop()
     if args.workload == "all" and not args.no_big:
-        # BASELINE configs[3] and [4] in the same line, at sizes that keep the default run short (their own invocations,
-        # --workload cfg4 | cfg5, take --poses): 250k robot configurations (1.75M link queries) / 100k poses per GPU
+        # BASELINE configs[3] and [4] in the same line (their own invocations, --workload cfg4 | cfg5, take --poses): cfg4 at
+        # 250k robot configurations (1.75M link queries) per GPU, which keeps the default run short (the rate does not depend
+        # on the batch there: 21.4 ms per 1M), cfg5 at BASELINE's full 1M poses per GPU: its launches are tail-sensitive --
+        # single queries take up to ~2 ms and a 100k-pose launch is only 2.3 .. 24 ms long, so the longest query of a shard
+        # decides up to 40 % of such a launch (shards of the same distribution: 2.34 .. 4.02 ms), at 1M poses a few per cent
         import copy
 
         import bench_big
 
         keep = ("value", "unit", "ms_per_step", "e2e", "roofline", "cpu_baseline", "gpu_launches", "config", "workloads", "clocks")
-        for which, poses in (("cfg4", 250_000), ("cfg5", 100_000)):
+        for which, poses in (("cfg4", 250_000), ("cfg5", 1_000_000)):
             a2 = copy.copy(args)
             a2.poses = poses // world if args.scaling == "strong" else poses
             a2.steps = max(3, min(args.steps, 5))

@@ -9,6 +9,7 @@ cfg5: two 999,680-triangle meshes; a step = collide() verdicts, distance() with 
 --scaling weak: --poses per GPU; --scaling strong: --poses in total (split across the GPUs).
 Meshes are built ON the device (fclgpu_model_build_obbrss); BVHs are replicated on every GPU.
 """
+import os
 import time
 
 import numpy as np
@@ -159,6 +160,7 @@ def run(ctx, which):
     B = F.BVHModel.from_arrays(vb, tb, build_on_device=True)
     A.device_model(local)
     B.device_model(local)
+    start += int(os.environ.get("FCLGPU_BENCH_SHARD_SHIFT", "0")) * n  # diagnosis: time another rank's shard on one GPU
     P = W.shell_poses(n, 1.5, 3.0, seed=6, start=start)  # centre distance 1.5 .. 3 radii: about half collide
     hP = torch.from_numpy(P).pin_memory()
     dP = hP.to(dev)

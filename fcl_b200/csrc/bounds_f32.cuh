@@ -145,7 +145,10 @@ FD float rss_lower_bound_f32(const float* R0, const float* T0, float t0_l1, cons
     best = fmaxf(best, ok ? g : 0.0f);
   }
   const float slack = 9.1552734375e-05f * M;  // 1536 * 2^-24 * M
-  const float lb = fmaf(best, 0.999f, -slack) - (n1.r + n2.r) * 1.000001f;
+#ifndef FCLGPU_RSS_REL
+#define FCLGPU_RSS_REL 0.999f
+#endif
+  const float lb = fmaf(best, FCLGPU_RSS_REL, -slack) - (n1.r + n2.r) * 1.000001f;
   return fmaxf(lb, 0.0f);
 }
 
