@@ -125,9 +125,9 @@ struct Workspace {
   std::map<cudaStream_t, int> stream_slot;
   // The contact scratch and the distance front's overflow area are one allocation per device: launches that use them
   // on DIFFERENT streams are ordered with an event (same-stream launches are ordered anyway).
-  cudaEvent_t scratch_ev = nullptr, spill_ev = nullptr, order_ev = nullptr;
-  cudaStream_t scratch_stream = nullptr, spill_stream = nullptr, order_stream = nullptr;
-  bool scratch_used = false, spill_used = false, order_used = false;
+  cudaEvent_t scratch_ev = nullptr, order_ev = nullptr;
+  cudaStream_t scratch_stream = nullptr, order_stream = nullptr;
+  bool scratch_used = false, order_used = false;
   void* order_buf = nullptr;  // locality order of a batch (query_order.cuh): keys, bucket counters, the order itself
   size_t order_bytes = 0;
   void* scratch = nullptr;
@@ -138,9 +138,18 @@ struct Workspace {
   void* dev_io = nullptr;
   size_t dev_io_bytes = 0;
   cudaStream_t pipe[2] = {nullptr, nullptr};
-  uint2* spill_pair = nullptr;    // distance kernel: per-warp overflow area of the sorted front (deep trees)
-  float* spill_bound = nullptr;
-  int spill_cap = 0;
+  // distance kernel: per-warp overflow areas of the sorted front (deep trees).  An area is indexed by the launch-local warp
+  // id, so two launches may share one only one after the other; there are two, so that the launches of the host API's two
+  // pipeline streams overlap (the tail of a launch -- its longest queries -- runs next to the start of the following one)
+  struct SpillArea {
+    uint2* pair = nullptr;
+    float* bound = nullptr;
+    int cap = 0;
+    cudaEvent_t ev = nullptr;
+    bool used = false;
+    cudaStream_t stream = nullptr;
+  } spill[2];
+  unsigned spill_next = 0;
   unsigned* ready = nullptr;      // device: per-chunk "input has landed" flags of the streamed host path
   unsigned* host_one = nullptr;   // pinned host word (= 1) the copy stream writes into ready[c]
   long long* host_totals = nullptr;  // pinned: running contact totals read back per sub-batch
@@ -176,7 +185,7 @@ int get_ws(int device, Workspace** out) {
   CUDA_TRY(cudaMalloc(&w->cursor_pool, sizeof(long long) * kStreamSlots));
   CUDA_TRY(cudaMemset(w->cursor_pool, 0, sizeof(long long) * kStreamSlots));
   CUDA_TRY(cudaEventCreateWithFlags(&w->scratch_ev, cudaEventDisableTiming));
-  CUDA_TRY(cudaEventCreateWithFlags(&w->spill_ev, cudaEventDisableTiming));
+  for (auto& a : w->spill) CUDA_TRY(cudaEventCreateWithFlags(&a.ev, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&w->order_ev, cudaEventDisableTiming));
   CUDA_TRY(cudaMalloc(&w->ready, sizeof(unsigned) * kReadySlots));
   CUDA_TRY(cudaMemset(w->ready, 0, sizeof(unsigned) * kReadySlots));
@@ -1288,27 +1297,37 @@ int distance_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, 
   P.cutoff = cutoff;
   P.stop_below = stop_below;
   P.within = within;
+  Workspace::SpillArea* area = nullptr;
   if ((long long)m1->d.n_nodes + m2->d.n_nodes >= (1 << 17) && opt("dist_spill_entries") >= kSpillBlock) {
     // big models: the sorted front may outgrow its shared-memory stack; give every warp of the largest
     // possible grid an overflow area in HBM (12 bytes per entry)
     const int cap = (int)opt("dist_spill_entries");
-    if (w->spill_cap != cap) {
-      if (w->spill_pair) CUDA_TRY(cudaFree(w->spill_pair));
-      if (w->spill_bound) CUDA_TRY(cudaFree(w->spill_bound));
-      w->spill_pair = nullptr;
-      w->spill_bound = nullptr;
-      w->spill_cap = 0;
+    for (auto& a : w->spill)
+      if (a.used && a.stream == st) area = &a;  // the area this stream used last
+    if (!area)
+      for (auto& a : w->spill)
+        if (!a.used) {
+          area = &a;
+          break;
+        }
+    if (!area) area = &w->spill[w->spill_next++ & 1u];  // more streams than areas: share one, ordered by its event
+    if (area->cap != cap) {
+      if (area->pair) CUDA_TRY(cudaFree(area->pair));
+      if (area->bound) CUDA_TRY(cudaFree(area->bound));
+      area->pair = nullptr;
+      area->bound = nullptr;
+      area->cap = 0;
       const size_t warps = (size_t)w->sm_count * 8 * kDistWarps;  // up to 8 resident blocks per SM
-      CUDA_TRY(cudaMalloc((void**)&w->spill_pair, warps * cap * sizeof(uint2)));
-      CUDA_TRY(cudaMalloc((void**)&w->spill_bound, warps * cap * sizeof(float)));
-      w->spill_cap = cap;
+      CUDA_TRY(cudaMalloc((void**)&area->pair, warps * cap * sizeof(uint2)));
+      CUDA_TRY(cudaMalloc((void**)&area->bound, warps * cap * sizeof(float)));
+      area->cap = cap;
     }
-    P.spill_pair = w->spill_pair;
-    P.spill_bound = w->spill_bound;
+    P.spill_pair = area->pair;
+    P.spill_bound = area->bound;
     P.spill_cap = cap;
     P.spill_warps = w->sm_count * 8 * kDistWarps;
-    // the area is indexed by the launch-local warp id: a launch on another stream must not overlap this one
-    order_after(st, w->spill_ev, w->spill_used, w->spill_stream);
+    // the area is indexed by the launch-local warp id: a launch on another stream must not overlap its previous user
+    order_after(st, area->ev, area->used, area->stream);
   }
   const bool stats = (n_bv || n_leaf);
   if (sphere_radius >= 0) {
@@ -1347,7 +1366,7 @@ int distance_enqueue(const fclgpu_model* m1, const fclgpu_model* m2, int64_t n, 
     rc = stats ? launch_persistent(distance_thread_kernel<true>, P, w, 128, st)
                : launch_persistent(distance_thread_kernel<false>, P, w, 128, st);
   }
-  if (P.spill_pair) mark_use(st, w->spill_ev, w->spill_used, w->spill_stream);
+  if (area) mark_use(st, area->ev, area->used, area->stream);
   return rc;
 }
 }  // namespace
