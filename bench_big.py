@@ -235,7 +235,7 @@ def run(ctx, which):
                     return F.collide_batch(A, ident, B, hp, creq, want_contacts=False, device=local, pinned=True)
                 if kind == "distance":
                     return F.distance_batch(A, ident, B, hp, dreq, device=local, pinned=True)
-                return F.within_tolerance_batch(A, ident, B, hp, tol, device=local)
+                return F.within_tolerance_batch(A, ident, B, hp, tol, device=local, pinned=True)
             one()
             torch.cuda.synchronize()
             if world > 1:

@@ -839,14 +839,14 @@ def distance_batch(o1, tf1, o2, tf2, request, stats=False, device=None, pinned=F
     return res
 
 
-def within_tolerance_batch(o1, tf1, o2, tf2, tolerance, stats=False, device=None, early_exit=True):
+def within_tolerance_batch(o1, tf1, o2, tf2, tolerance, stats=False, device=None, early_exit=True, pinned=False):
     """Tolerance verification (extension; BASELINE cfg5): bool[n], query i is True iff fcl::distance(o1, tf1[i], o2,
     tf2[i]) <= tolerance.  Node pairs farther apart than the tolerance are pruned from the first round on and (with
     early_exit, the default: fclgpu_within_tolerance_batch) a query ends at the first triangle pair found within the
     tolerance.  Returns (within, BatchDistanceResult); with early_exit the result's min_distance is the witness pair's
     distance (an upper bound of the true distance), without it min(fcl::distance, nextafter(tolerance))."""
     if not early_exit:
-        r = distance_batch(o1, tf1, o2, tf2, DistanceRequest(False), stats=stats, device=device,
+        r = distance_batch(o1, tf1, o2, tf2, DistanceRequest(False), stats=stats, device=device, pinned=pinned,
                            cutoff=float(np.nextafter(float(tolerance), np.inf)))
         return r.min_distance <= float(tolerance), r
     tf1, n1 = _poses(tf1)
@@ -857,12 +857,14 @@ def within_tolerance_batch(o1, tf1, o2, tf2, tolerance, stats=False, device=None
     if n1 is not None and n2 is not None and n1 != n2:
         raise ValueError("tf1 and tf2 must have the same length")
     m1, m2 = o1.device_model(device), o2.device_model(device)
-    within, dist = np.zeros(n, np.uint8), np.zeros(n, np.float64)
+    (within, k0), (dist, k1) = _out(n, np.uint8, pinned, "within"), _out(n, np.float64, pinned, "wdist")  # pinned: see _out
     n_bv = np.zeros(n, np.uint32) if stats else None
     n_leaf = np.zeros(n, np.uint32) if stats else None
     check(_capi.lib().fclgpu_within_tolerance_batch_host(m1, m2, n, addr(tf1), addr(tf2), float(tolerance), addr(within),
                                                          addr(dist), addr(n_bv), addr(n_leaf)))
-    return within.astype(bool), BatchDistanceResult(dist, None, None, None, None, n_bv, n_leaf)
+    res = BatchDistanceResult(dist, None, None, None, None, n_bv, n_leaf)
+    res._keepalive = (k0, k1)
+    return within.astype(bool), res
 
 
 def distance_mesh_sphere_batch(o1, tf1, sphere, tf2, request, stats=False, device=None, pinned=False):
