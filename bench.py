@@ -842,7 +842,8 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOADS[head], "poses_per_gpu": h["poses_per_gpu"], "global_poses": world * h["poses_per_gpu"],
                        "pose_seed": 1, "models": "env.obj (2180 tris, 4359 nodes) posed vs rob.obj (216 tris, 431 nodes) at identity",
-                       "l2_flush_between_steps": True, "l2_flush_inside_timed_region": world > 1,
+                       "l2_flush_between_steps": True, "l2_flush_inside_timed_region": os.environ.get("FCLGPU_BENCH_TIMING") == "loop" and world > 1,
+                       "timing": "per-step CUDA events on the launching stream, summed" + (" + exposed tail of the last gather" if world > 1 else ""),
                        "traversal": _capi.get_option("traversal"), **({"options": args.opt} if args.opt else {}),
                        "multi_gpu": ("BVHs replicated, poses partitioned, one packed 64 B/query result record all-gathered per step with "
                                      "fclgpu_comm_allgather (C ABI, raw NCCL) on a second stream, overlapped with the next step's traversal")
