@@ -749,7 +749,7 @@ def main():
     ap.add_argument("--traversal", type=int, default=3, help="kernel variant (fclgpu option 'traversal', see DESIGN.md)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-big", action="store_true", help="--workload all: skip the reduced cfg4 / cfg5 legs")
+    ap.add_argument("--no-big", action="store_true", help="--workload all: skip the cfg4 / cfg5 legs")
     ap.add_argument("--opt", action="append", default=[], help="name=value library option (A/B runs; recorded in config)")
     args = ap.parse_args()
     if args.warmup < 3:
