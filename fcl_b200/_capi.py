@@ -77,7 +77,7 @@ SYMBOLS = [
     "fclgpu_model_num_tris", "fclgpu_model_device", "fclgpu_collide_batch", "fclgpu_collide_batch_host",
     "fclgpu_distance_batch", "fclgpu_distance_batch_host", "fclgpu_abi_version", "fclgpu_device_count",
     "fclgpu_last_error", "fclgpu_pose_from_colmajor4x4", "fclgpu_sync_status", "fclgpu_set_option",
-    "fclgpu_get_option", "fclgpu_launch_count", "fclgpu_debug_counters", "fclgpu_microbench",
+    "fclgpu_get_option", "fclgpu_launch_count", "fclgpu_debug_counters", "fclgpu_microbench", "fclgpu_device_trim",
 ]
 
 _lib = None
@@ -172,6 +172,7 @@ def lib():
     L.fclgpu_pose_from_colmajor4x4.argtypes = [vp, vp]
     L.fclgpu_pose_from_colmajor4x4.restype = None
     L.fclgpu_sync_status.argtypes = [C.c_int, vp]
+    L.fclgpu_device_trim.argtypes = [C.c_int, C.POINTER(C.c_int64)]
     L.fclgpu_set_option.argtypes = [C.c_char_p, C.c_int64]
     L.fclgpu_get_option.argtypes = [C.c_char_p]
     L.fclgpu_get_option.restype = C.c_int64

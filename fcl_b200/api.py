@@ -926,6 +926,16 @@ def sync_status(device=None, stream=None):
     check(_capi.lib().fclgpu_sync_status(dev, st))
 
 
+def trim_device(device=None):
+    """Give the per-device workspace buffers (contact staging, host-API staging, overflow areas of the distance front) back to
+    the device after it has gone idle; models stay.  Returns the number of bytes released (fclgpu_device_trim)."""
+    dev = _current_device() if device is None else device
+    n = C.c_int64(0)
+    check(_capi.lib().fclgpu_device_trim(dev, C.byref(n)))
+    _PINNED_POOL.clear()  # the page-locked result buffers of the pinned=True calls go as well
+    return int(n.value)
+
+
 # ------------------------------------------------------------------------------------------------
 # broadphase (SURVEY 8f rank 3)
 # ------------------------------------------------------------------------------------------------

@@ -1463,6 +1463,48 @@ extern "C" int fclgpu_continuous_collide_batch(const fclgpu_model* m1, const fcl
                           : launch_persistent(ca_translation_kernel<false>, P, w, 128, st);
 }
 
+extern "C" int fclgpu_device_trim(int device, int64_t* released) {
+  if (released) *released = 0;
+  Workspace* w = nullptr;
+  {
+    std::lock_guard<std::mutex> g(g_ws_mu);
+    auto it = g_ws.find(device);
+    if (it == g_ws.end()) return FCLGPU_OK;  // nothing was ever allocated on this device
+    w = it->second;
+  }
+  std::lock_guard<std::mutex> host_lock(w->host_mu);
+  std::lock_guard<std::mutex> lock(w->mu);
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaDeviceSynchronize());  // nothing in flight may still use the buffers
+  int64_t bytes = 0;
+  auto drop = [&](void** p, size_t* have) {
+    if (*p) cudaFree(*p);
+    bytes += (int64_t)*have;
+    *p = nullptr;
+    *have = 0;
+  };
+  drop(&w->scratch, &w->scratch_bytes);
+  drop(&w->scan_tmp, &w->scan_bytes);
+  drop(&w->dev_io, &w->dev_io_bytes);
+  drop(&w->order_buf, &w->order_bytes);
+  const size_t spill_warps = (size_t)w->sm_count * 8 * kDistWarps;
+  for (auto& a : w->spill) {
+    if (a.pair) cudaFree(a.pair);
+    if (a.bound) cudaFree(a.bound);
+    if (a.pair) bytes += (int64_t)(spill_warps * (size_t)a.cap * (sizeof(uint2) + sizeof(float)));
+    a.pair = nullptr;
+    a.bound = nullptr;
+    a.cap = 0;
+    a.used = false;
+    a.stream = nullptr;
+  }
+  w->scratch_used = w->order_used = false;
+  w->scratch_stream = w->order_stream = nullptr;
+  if (released) *released = bytes;
+  CUDA_TRY(cudaGetLastError());
+  return FCLGPU_OK;
+}
+
 extern "C" int fclgpu_sync_status(int device, void* stream) {
   Workspace* w;
   int rc = get_ws(device, &w);

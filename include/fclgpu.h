@@ -471,6 +471,13 @@ void fclgpu_pose_from_colmajor4x4(const double* m16, double* pose12);
  * capacity, traversal stack) are sticky.  This synchronises `stream` and returns and clears
  * that status. */
 int fclgpu_sync_status(int device, void* stream);
+/* The reference allocates nothing persistent (its traversal nodes live on the stack, SURVEY 8b "Ownership"); this library
+ * keeps a per-device workspace that grows with the largest batch seen (contact staging, host-API staging buffers, the
+ * distance front's overflow areas, scan temporaries).  fclgpu_device_trim waits for the device to go idle and gives those
+ * buffers back; the next call allocates what it needs again.  Models are not touched.  Returns the number of bytes released
+ * through *released (may be NULL).  Must not run concurrently with *_batch calls that are still being ENQUEUED on the same
+ * device from other threads (it takes the same locks, so it is safe, but it would stall them). */
+int fclgpu_device_trim(int device, int64_t* released);
 /* Tuning knob: select the traversal kernel variant (0 = default).  See DESIGN.md. */
 int fclgpu_set_option(const char* name, int64_t value);
 int64_t fclgpu_get_option(const char* name);

@@ -751,3 +751,26 @@ def test_concurrent_contact_queries_on_two_streams(models, oracle):
     with pytest.raises(F.FclGpuError):
         F.sync_status(0, streams[0])
     F.sync_status(0, streams[0])  # the sticky word was cleared by the read
+
+
+def test_device_trim_releases_the_workspace_and_the_next_call_regrows_it(models, oracle):
+    """fclgpu_device_trim: the growable per-device buffers go back to the device (the reference keeps nothing between calls,
+    SURVEY 8b "Ownership"); models survive and the next query allocates what it needs and returns the same results."""
+    torch = pytest.importorskip("torch")
+    (env, rob), (oenv, orob) = models
+    P = random_poses(3000, seed=91)
+    req = F.CollisionRequest(50, True)
+    a = F.collide_batch(env, P, rob, None, req)
+    da = F.distance_batch(env, P, rob, None, F.DistanceRequest(True))
+    free0 = torch.cuda.mem_get_info(0)[0]
+    released = F.trim_device(0)
+    assert released > 0
+    assert torch.cuda.mem_get_info(0)[0] >= free0 + released // 2  # the driver really got (most of) it back
+    assert F.trim_device(0) == 0  # nothing left to release
+    b = F.collide_batch(env, P, rob, None, req)
+    db = F.distance_batch(env, P, rob, None, F.DistanceRequest(True))
+    assert np.array_equal(a.num_contacts, b.num_contacts) and np.array_equal(a.contacts, b.contacts)
+    assert np.array_equal(da.min_distance, db.min_distance)
+    ref = oracle.collide_batch(oenv, orob, P, None, 50, True, nthreads=8)
+    assert np.array_equal(b.num_contacts, ref["counts"])
+
