@@ -422,6 +422,14 @@ inline ModelCache& model_cache() {
   static ModelCache c;
   return c;
 }
+// Give back what the library keeps between calls on `device`: the growable workspace buffers (fclgpu_device_trim) and,
+// with models = true, the cached device copies of every BVHModel as well.  Returns the workspace bytes released.
+inline std::int64_t release_device_memory(int device = 0, bool models = false) {
+  if (models) model_cache().clear();
+  std::int64_t released = 0;
+  check(fclgpu_device_trim(device, &released));
+  return released;
+}
 
 namespace detail {
 // the budget a non-empty result leaves (mesh_collision_traversal_node-inl.h:553-556, 594-600: addContact only while

@@ -348,6 +348,11 @@ int main(int argc, char** argv) {
   }
   if (colliding < n / 20 || colliding > n - n / 20) { std::printf("FAIL: degenerate pose sample (%lld colliding)\n", colliding); return 1; }
   std::printf("shim OK: %d queries, %lld colliding, %lld contacts compared, distances identical\n", n, colliding, contacts);
+  {  // what the library kept between the calls goes back to the driver; a second call has nothing left to release
+    const std::int64_t released = fclgpu::release_device_memory(0, /*models=*/true);
+    if (released <= 0 || fclgpu::release_device_memory(0) != 0) { std::printf("FAIL: release_device_memory (%lld)\n", (long long)released); return 1; }
+    std::printf("shim release OK: %lld workspace bytes\n", (long long)released);
+  }
   fclgpu_model_destroy(g1);
   fclgpu_model_destroy(g2);
   fclgpu_bvh_destroy(b1);
