@@ -114,6 +114,15 @@ def test_no_cpu_fallback_without_device():
         F.collide_mesh_sphere_batch(m, random_poses(4), F.Sphere(1.0), random_poses(4, seed=2), F.CollisionRequest())
 
 
+def test_device_trim_on_an_untouched_device_is_a_no_op():
+    """fclgpu_device_trim before anything ran on the device: nothing to release, no CUDA call, no error (also without a GPU)."""
+    import ctypes as C
+
+    n = C.c_int64(-1)
+    assert _capi.lib().fclgpu_device_trim(7, C.byref(n)) == 0 and n.value == 0
+    assert _capi.lib().fclgpu_device_trim(7, None) == 0
+
+
 def test_pose_generator_is_reproducible_and_shardable():
     a = random_poses(1000, seed=1)
     b = np.concatenate([random_poses(400, seed=1, start=0), random_poses(600, seed=1, start=400)])
