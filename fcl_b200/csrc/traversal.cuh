@@ -1712,24 +1712,13 @@ namespace fclgpu {
 #ifndef FCLGPU_FRONT_SEED
 #define FCLGPU_FRONT_SEED 5
 #endif
-// FCLGPU_FRONT_STAGE (measured and rejected; kept compiled out): the box records of a BV round fetched by FOUR
-// lanes per record (16 bytes each, one 64-byte request per record) into a shared-memory staging area and read back by the
-// lanes that test them, instead of every lane fetching its two 64-byte records with eight divergent 16-byte loads.  A
-// third of the L1 wavefronts, but global load -> shared store -> barrier -> shared load is a longer dependent chain per round
-// and the kernel is latency bound: cfg1 0.087 -> 0.111 ms, cfg4 21.8 -> 27.1 ms per 1M configurations.
-#ifndef FCLGPU_FRONT_STAGE
-#define FCLGPU_FRONT_STAGE 0
-#endif
 // Stack entries per warp: a launch parameter (CollideParams::front_cap, dynamic shared memory).  Rounds are 32 wide while the
 // stack is below cap - front_reserve and depth first (one entry per round, growth bounded by the two tree depths) above it;
 // on BVHs beyond the caches the width of the rounds is what hides the HBM latency, so big models get the larger stack.
-// FCLGPU_FRONT_DUAL = n > 0 (measured and rejected; compiled out): a round that popped more than n internal pairs
-// expands ALL of them, one lane per pair and both children per lane, instead of 16 of them with two lanes per pair.  Half
-// the rounds on wide fronts, but the traversal becomes breadth first and a colliding query reaches its first intersecting
-// triangle pair much later: cfg4 21.4 -> 30.8 ms, cfg5 verdicts 5.4 -> 8.9 ms.
-#ifndef FCLGPU_FRONT_DUAL
-#define FCLGPU_FRONT_DUAL 0
-#endif
+// Measured and rejected for this kernel (the code is in the history): box records fetched by four lanes per
+// record through a shared-memory staging area (a third of the L1 wavefronts, 25 % slower: a longer dependent chain per round),
+// and wide rounds that expand every popped pair with both children per lane (breadth first: a colliding query reaches its
+// first intersecting triangle pair much later).
 #ifndef FCLGPU_FRONT_NEXP
 #define FCLGPU_FRONT_NEXP 16  // pairs expanded per round (two lanes each)
 #endif
@@ -1737,7 +1726,6 @@ namespace fclgpu {
 #define FCLGPU_FRONT_MINBLOCKS 4
 #endif
 constexpr int kFrontLeafCap = 64;
-constexpr int kFrontStageRecs = FCLGPU_FRONT_STAGE ? 48 : 0;
 // A front entry carries everything the NEXT round needs to expand it without touching memory: both node ids, both
 // first_child fields (fetched, together with the box records, when the pair was tested) and the firstOverSecond decision
 // (bit 31 of b1).  A round is then pop -> expand -> ONE dependent global-load phase (records + topo of the two children)
@@ -1747,23 +1735,9 @@ struct CollideFront {
   uint4* pair;    // [cap] {b1 | split-first flag, b2, first_child1, first_child2}
   uint2* leaf;    // [kFrontLeafCap]
   uint4* expand;  // [32] {node1, node2, first_child of the node that was NOT split (carried), which side was split}
-  float4* stage;  // [kFrontStageRecs * 4] staged box records: slot s, 16-byte piece p at [4 s + (p ^ ((s >> 1) & 3))] (no bank conflicts)
 };
 inline __host__ __device__ size_t front_bytes_per_warp(int cap) {
-  return (size_t)cap * sizeof(uint4) + kFrontLeafCap * sizeof(uint2) + 32 * sizeof(uint4) + (size_t)kFrontStageRecs * 4 * sizeof(float4);
-}
-
-// piece p of staged record `slot`
-__device__ __forceinline__ int front_stage_index(int slot, int p) { return 4 * slot + (p ^ ((slot >> 1) & 3)); }
-__device__ __forceinline__ ObbRec32 front_staged_obb32(const float4* stage, int slot) {
-  const float4 v0 = stage[front_stage_index(slot, 0)], v1 = stage[front_stage_index(slot, 1)];
-  const float4 v2 = stage[front_stage_index(slot, 2)], v3 = stage[front_stage_index(slot, 3)];
-  ObbRec32 n;
-  n.a[0] = v0.x; n.a[1] = v0.y; n.a[2] = v0.z; n.a[3] = v0.w;
-  n.a[4] = v1.x; n.a[5] = v1.y; n.a[6] = v1.z; n.a[7] = v1.w;
-  n.a[8] = v2.x; n.c[0] = v2.y; n.c[1] = v2.z; n.c[2] = v2.w;
-  n.e[0] = v3.x; n.e[1] = v3.y; n.e[2] = v3.z; n.s = v3.w;
-  return n;
+  return (size_t)cap * sizeof(uint4) + kFrontLeafCap * sizeof(uint2) + 32 * sizeof(uint4);
 }
 
 __device__ __forceinline__ uint4 front_entry(int b1, int b2, int fc1, double size1, int fc2, double size2) {
@@ -1779,7 +1753,6 @@ __global__ void __launch_bounds__(128, FCLGPU_FRONT_MINBLOCKS) collide_front_ker
   S.pair = reinterpret_cast<uint4*>(smem_raw + (size_t)(threadIdx.x >> 5) * front_bytes_per_warp(P.front_cap));
   S.leaf = reinterpret_cast<uint2*>(S.pair + P.front_cap);
   S.expand = reinterpret_cast<uint4*>(S.leaf + kFrontLeafCap);
-  S.stage = reinterpret_cast<float4*>(S.expand + 32);
   const int wide_limit = P.front_cap - P.front_reserve;  // above it: one entry per round
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -1927,34 +1900,6 @@ __global__ void __launch_bounds__(128, FCLGPU_FRONT_MINBLOCKS) collide_front_ker
       sp -= k;
       const int n_exp = n_int < FCLGPU_FRONT_NEXP ? n_int : FCLGPU_FRONT_NEXP;
       __syncwarp();  // every lane has read its popped entry before slots are overwritten
-      if (FCLGPU_FRONT_DUAL && n_int > FCLGPU_FRONT_DUAL) {
-        // wide front: every lane expands the entry it popped and tests BOTH children (no hand-over through shared memory, no
-        // entry pushed back): the same loads per expanded entry as below, all in flight at once, and half as many rounds --
-        // with the BVH in HBM a round costs its load latency however many tests follow it
-        bool keep_a = false, keep_b = false;
-        uint4 ent_a = make_uint4(0u, 0u, 0u, 0u), ent_b = ent_a;
-        if (internal) {
-          const unsigned b1 = pr.x & 0x7fffffffu, b2 = pr.y;
-          const bool split1 = (pr.x >> 31) != 0u;
-          const unsigned x_a = split1 ? (unsigned)fc1 : b1, x_b = split1 ? (unsigned)fc1 + 1u : b1;
-          const unsigned y_a = split1 ? b2 : (unsigned)fc2, y_b = split1 ? b2 : (unsigned)fc2 + 1u;
-          const ObbRec32 n1a = load_obb32(P.m1.obb32, (int)x_a), n2a = load_obb32(P.m2.obb32, (int)y_a);
-          const ObbRec32 n1b = load_obb32(P.m1.obb32, (int)x_b), n2b = load_obb32(P.m2.obb32, (int)y_b);
-          const double2 t1a = __ldg(P.m1.topo + x_a), t2a = __ldg(P.m2.topo + y_a);
-          const double2 t1b = __ldg(P.m1.topo + x_b), t2b = __ldg(P.m2.topo + y_b);
-          keep_a = !obb_certainly_disjoint_f32(Rf, Tf, t_l1, n1a, n2a);
-          ent_a = front_entry((int)x_a, (int)y_a, __double2loint(t1a.x), t1a.y, __double2loint(t2a.x), t2a.y);
-          keep_b = !obb_certainly_disjoint_f32(Rf, Tf, t_l1, n1b, n2b);
-          ent_b = front_entry((int)x_b, (int)y_b, __double2loint(t1b.x), t1b.y, __double2loint(t2b.x), t2b.y);
-        }
-        if (kStats) bv_tests += 2 * n_int;
-        const unsigned ka = __ballot_sync(0xffffffffu, keep_a), kb = __ballot_sync(0xffffffffu, keep_b);
-        if (keep_a) S.pair[sp + __popc(ka & lt_mask)] = ent_a;
-        if (keep_b) S.pair[sp + __popc(ka) + __popc(kb & lt_mask)] = ent_b;
-        sp += __popc(ka) + __popc(kb);
-        __syncwarp();
-        continue;
-      }
       if (internal) {
         if (rank < n_exp) {
           const unsigned b1 = pr.x & 0x7fffffffu;
@@ -1973,45 +1918,7 @@ __global__ void __launch_bounds__(128, FCLGPU_FRONT_MINBLOCKS) collide_front_ker
       __syncwarp();
       bool keep = false;
       uint4 entry = make_uint4(0u, 0u, 0u, 0u);
-      if (FCLGPU_FRONT_STAGE) {
-        // one load phase: the records by four lanes each (slots 0..31: the children, in expand[] order; slots 32..47: the node
-        // of the other model, one per expansion), and {first_child, size} of both nodes for the entry to be pushed
-        const int sub = lane >> 2, piece = lane & 3;
-        float4 v[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          const bool child = i < 4;
-          const int t = child ? 8 * i + sub : 8 * (i - 4) + sub;  // child: expand[] index, other: expansion index
-          if (child ? (t < 2 * n_exp) : (t < n_exp)) {
-            const uint4 e = S.expand[child ? t : 2 * t];
-            const bool from1 = child ? (e.w != 0u) : (e.w == 0u);
-            const float4* p = reinterpret_cast<const float4*>(from1 ? P.m1.obb32 + e.x : P.m2.obb32 + e.y) + piece;
-            v[i] = __ldg(p);
-          }
-        }
-        uint4 xy = make_uint4(0u, 0u, 0u, 0u);
-        double2 t1 = make_double2(0.0, 0.0), t2 = t1;
-        if (lane < 2 * n_exp) {
-          xy = S.expand[lane];
-          t1 = __ldg(P.m1.topo + xy.x);
-          t2 = __ldg(P.m2.topo + xy.y);
-        }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          const bool child = i < 4;
-          const int t = child ? 8 * i + sub : 8 * (i - 4) + sub;
-          if (child ? (t < 2 * n_exp) : (t < n_exp)) S.stage[front_stage_index(child ? t : 32 + t, piece)] = v[i];
-        }
-        __syncwarp();
-        if (lane < 2 * n_exp) {
-          const int child_slot = lane, other_slot = 32 + (lane >> 1);
-          const bool split1 = xy.w != 0u;
-          const ObbRec32 n1 = front_staged_obb32(S.stage, split1 ? child_slot : other_slot);
-          const ObbRec32 n2 = front_staged_obb32(S.stage, split1 ? other_slot : child_slot);
-          keep = !obb_certainly_disjoint_f32(Rf, Tf, t_l1, n1, n2);
-          entry = front_entry((int)xy.x, (int)xy.y, __double2loint(t1.x), t1.y, __double2loint(t2.x), t2.y);
-        }
-      } else if (lane < 2 * n_exp) {
+      if (lane < 2 * n_exp) {
         const uint4 xy = S.expand[lane];
         // one load phase: both box records, and {first_child, size} of both nodes for the entry to be pushed
         const ObbRec32 n1 = load_obb32(P.m1.obb32, (int)xy.x);
