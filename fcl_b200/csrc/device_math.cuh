@@ -16,6 +16,8 @@
 
 #include <cmath>
 
+#include "sum_order.h"
+
 namespace fclgpu {
 
 struct V3 {
@@ -28,7 +30,7 @@ FD V3 mk(double x, double y, double z) { V3 r; r.x = x; r.y = y; r.z = z; return
 FD V3 operator+(const V3& a, const V3& b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
 FD V3 operator-(const V3& a, const V3& b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
 FD V3 operator*(const V3& a, double s) { return mk(a.x * s, a.y * s, a.z * s); }
-FD double dot(const V3& a, const V3& b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+FD double dot(const V3& a, const V3& b) { return FCL_SUM3(a.x * b.x, a.y * b.y, a.z * b.z); }
 FD V3 cross(const V3& a, const V3& b) {
   return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
@@ -40,9 +42,7 @@ FD double dabs(double x) { return (x < 0.0) ? -x : x; }
 struct M3 {
   double m[9];
 };
-FD double dot3(double a0, double a1, double a2, double b0, double b1, double b2) {
-  return (a0 * b0 + a1 * b1) + a2 * b2;
-}
+FD double dot3(double a0, double a1, double a2, double b0, double b1, double b2) { return FCL_SUM3(a0 * b0, a1 * b1, a2 * b2); }
 FD V3 mulv(const M3& A, const V3& v) {  // A v
   return mk(dot3(A.m[0], A.m[1], A.m[2], v.x, v.y, v.z), dot3(A.m[3], A.m[4], A.m[5], v.x, v.y, v.z),
             dot3(A.m[6], A.m[7], A.m[8], v.x, v.y, v.z));
@@ -303,7 +303,7 @@ FD double rect_distance(const M3& Rab, const V3& Tabv, const double a[2], const 
     D0 = D0 - t;
     if (ua) D1 = D1 - ap;
   }
-  const double edge_dist = sqrt((D0 * D0 + D1 * D1) + D2 * D2);
+  const double edge_dist = sqrt(FCL_SUM3(D0 * D0, D1 * D1, D2 * D2));  // S.norm()
 
   // no edge pair: separation along the two face normals (RSS-inl.h:1152-1224)
   double sep1, sep2;
@@ -336,7 +336,7 @@ FD double rect_distance(const M3& Rab, const V3& Tabv, const double a[2], const 
 // ---------------------------------------------------------------------------------------
 FD bool axis_overlaps(const V3& ax, const V3& p2, const V3& p3, const V3& q1, const V3& q2, const V3& q3) {
   // p1 is the origin after translation; ax.dot(p1) is an exact (signed) zero
-  const double P1 = (ax.x * 0.0 + ax.y * 0.0) + ax.z * 0.0;
+  const double P1 = FCL_SUM3(ax.x * 0.0, ax.y * 0.0, ax.z * 0.0);
   const double P2 = dot(ax, p2), P3 = dot(ax, p3);
   const double Q1 = dot(ax, q1), Q2 = dot(ax, q2), Q3 = dot(ax, q3);
   const double mn1 = dmin(P1, dmin(P2, P3));
@@ -426,7 +426,7 @@ FD bool tri_intersect_rolled(const V3& P1, const V3& P2, const V3& P3, const V3&
 // triangle, deepest vertices of the other one, the shallower side wins, <= 2 points.
 FD void triangle_plane(const V3& v1, const V3& v2, const V3& v3, V3& n, double& t) {
   V3 c = cross(v2 - v1, v3 - v1);
-  const double sq = (c.x * c.x + c.y * c.y) + c.z * c.z;
+  const double sq = FCL_SUM3(c.x * c.x, c.y * c.y, c.z * c.z);  // squaredNorm()
   if (sq > 0) {
     const double len = sqrt(sq);
     n = mk(c.x / len, c.y / len, c.z / len);

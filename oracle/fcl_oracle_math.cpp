@@ -107,7 +107,7 @@ static inline bool in_voronoi(double a, double b, double Anorm_dot_B, double Ano
   return false;
 }
 
-static inline double norm3(double x, double y, double z) { return std::sqrt((x * x + y * y) + z * z); }
+static inline double norm3(double x, double y, double z) { return std::sqrt(sum3(x * x, y * y, z * z)); }  // Vector3::norm()
 
 double rect_distance(const Mat3& Rab, const Vec3& Tab, const double a[2], const double b[2]) {
   const double (*R)[3] = Rab.m;
