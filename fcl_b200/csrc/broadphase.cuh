@@ -21,6 +21,8 @@
 #pragma once
 #include <cstdint>
 
+#include "sum_order.h"
+
 namespace fclgpu {
 
 struct LocalAabb {  // BVHModel::computeLocalAABB: aabb_center, aabb_radius, aabb_local.min_, aabb_local.max_
@@ -54,7 +56,7 @@ __host__ __device__ inline void world_aabb(const LocalAabb& a, const double* tf,
     }
   } else {  // center = tf * aabb_center; min = center - radius, max = center + radius
     for (int k = 0; k < 3; ++k) {
-      const double ck = ((tf[3 * k] * a.c[0] + tf[3 * k + 1] * a.c[1]) + tf[3 * k + 2] * a.c[2]) + tf[9 + k];
+      const double ck = FCL_SUM3(tf[3 * k] * a.c[0], tf[3 * k + 1] * a.c[1], tf[3 * k + 2] * a.c[2]) + tf[9 + k];
       out6[k] = ck - a.r;
       out6[3 + k] = ck + a.r;
     }

@@ -46,7 +46,7 @@ struct Builder {
       for (int i = 0; i < n; ++i) {
         const double *p1 = vert(idx[i], 0), *p2 = vert(idx[i], 1), *p3 = vert(idx[i], 2);
         const double c0 = p1[0] + p2[0] + p3[0], c1 = p1[1] + p2[1] + p3[1], c2 = p1[2] + p2[2] + p3[2];
-        med[i] = ((c0 * sv[0] + c1 * sv[1]) + c2 * sv[2]) / 3;
+        med[i] = FCL_SUM3(c0 * sv[0], c1 * sv[1], c2 * sv[2]) / 3;
       }
       std::sort(med.begin(), med.end());
       return (n % 2 == 1) ? med[(n - 1) / 2] : (med[n / 2] + med[n / 2 - 1]) / 2;
@@ -147,7 +147,7 @@ extern "C" int fclgpu_bvh_build_obbrss(const double* vertices, int32_t num_verti
       const double *p1 = B.vert(idx[i], 0), *p2 = B.vert(idx[i], 1), *p3 = B.vert(idx[i], 2);
       const double cx = ((p1[0] + p2[0]) + p3[0]) / 3.0, cy = ((p1[1] + p2[1]) + p3[1]) / 3.0,
                    cz = ((p1[2] + p2[2]) + p3[2]) / 3.0;
-      if (!(((sv[0] * cx + sv[1] * cy) + sv[2] * cz) > thr)) {
+      if (!(FCL_SUM3(sv[0] * cx, sv[1] * cy, sv[2] * cz) > thr)) {
         std::swap(idx[i], idx[c1]);
         c1++;
       }

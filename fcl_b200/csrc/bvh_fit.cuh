@@ -18,6 +18,8 @@
 #include <cmath>
 #include <cstdint>
 
+#include "sum_order.h"
+
 namespace fclgpu {
 
 #ifndef FD
@@ -100,9 +102,9 @@ __host__ __device__ inline void extent_center_from_points(PointOf pt, int m, con
   double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
   for (int j = 0; j < m; ++j) {
     const double* p = pt(j);
-    const double c0 = (a00 * p[0] + a10 * p[1]) + a20 * p[2];
-    const double c1 = (a01 * p[0] + a11 * p[1]) + a21 * p[2];
-    const double c2 = (a02 * p[0] + a12 * p[1]) + a22 * p[2];
+    const double c0 = FCL_SUM3(a00 * p[0], a10 * p[1], a20 * p[2]);  // axis.col(0).dot(p)
+    const double c1 = FCL_SUM3(a01 * p[0], a11 * p[1], a21 * p[2]);
+    const double c2 = FCL_SUM3(a02 * p[0], a12 * p[1], a22 * p[2]);
     if (c0 > mx[0]) mx[0] = c0;
     if (c0 < mn[0]) mn[0] = c0;
     if (c1 > mx[1]) mx[1] = c1;
@@ -112,7 +114,7 @@ __host__ __device__ inline void extent_center_from_points(PointOf pt, int m, con
   }
   const double o[3] = {(mx[0] + mn[0]) / 2, (mx[1] + mn[1]) / 2, (mx[2] + mn[2]) / 2};
   for (int r = 0; r < 3; ++r) {
-    To[r] = (A[3 * r] * o[0] + A[3 * r + 1] * o[1]) + A[3 * r + 2] * o[2];
+    To[r] = FCL_SUM3(A[3 * r] * o[0], A[3 * r + 1] * o[1], A[3 * r + 2] * o[2]);  // axis * o
     ext[r] = (mx[r] - mn[r]) / 2;
   }
 }
@@ -123,9 +125,9 @@ __host__ __device__ inline void extent_center_from_points(PointOf pt, int m, con
 template <class PointOf>
 __host__ __device__ inline void rss_from_points(PointOf pt, int m, const double* A, double To[3], double l[2], double& rad) {
   const double a00 = A[0], a10 = A[3], a20 = A[6], a01 = A[1], a11 = A[4], a21 = A[7], a02 = A[2], a12 = A[5], a22 = A[8];
-#define FCLGPU_PX(p) ((a00 * (p)[0] + a10 * (p)[1]) + a20 * (p)[2])
-#define FCLGPU_PY(p) ((a01 * (p)[0] + a11 * (p)[1]) + a21 * (p)[2])
-#define FCLGPU_PZ(p) ((a02 * (p)[0] + a12 * (p)[1]) + a22 * (p)[2])
+#define FCLGPU_PX(p) FCL_SUM3(a00 * (p)[0], a10 * (p)[1], a20 * (p)[2])
+#define FCLGPU_PY(p) FCL_SUM3(a01 * (p)[0], a11 * (p)[1], a21 * (p)[2])
+#define FCLGPU_PZ(p) FCL_SUM3(a02 * (p)[0], a12 * (p)[1], a22 * (p)[2])
   double minz = 0, maxz = 0;
   for (int j = 0; j < m; ++j) {
     const double* p = pt(j);

@@ -24,7 +24,7 @@ struct NodeBV {
 
 namespace merge_detail {
 
-__host__ __device__ inline double dot3p(const double* a, const double* b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+__host__ __device__ inline double dot3p(const double* a, const double* b) { return FCL_SUM3(a[0] * b[0], a[1] * b[1], a[2] * b[2]); }
 __host__ __device__ inline void normalize3(double* v) {  // Eigen: z = squaredNorm(); if (z > 0) v /= sqrt(z)
   const double z = dot3p(v, v);
   if (z > 0) {
@@ -219,7 +219,7 @@ __host__ __device__ inline void merge_obbrss(const NodeBV& a, const NodeBV& b, N
       for (int i = 0; i < 16; ++i) {
         const double d3[3] = {v[i][0] - To[0], v[i][1] - To[1], v[i][2] - To[2]};
         for (int j = 0; j < 3; ++j) {
-          const double d = (d3[0] * out.axis[j] + d3[1] * out.axis[3 + j]) + d3[2] * out.axis[6 + j];
+          const double d = FCL_SUM3(d3[0] * out.axis[j], d3[1] * out.axis[3 + j], d3[2] * out.axis[6 + j]);
           // reference quirk (OBB-inl.h:339-342): `else if` -- a point that raises the maximum is not tried as a minimum,
           // so the very first corner never lowers pmin
           if (d > pmax[j]) pmax[j] = d;

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(64) refit_nodes_kernel(RefitParams P) {
   r[12] = f.rss_l[0];
   r[13] = f.rss_l[1];
   r[14] = f.rss_r;
-  const double size = (f.obb_ext[0] * f.obb_ext[0] + f.obb_ext[1] * f.obb_ext[1]) + f.obb_ext[2] * f.obb_ext[2];
+  const double size = FCL_SUM3(f.obb_ext[0] * f.obb_ext[0], f.obb_ext[1] * f.obb_ext[1], f.obb_ext[2] * f.obb_ext[2]);  // extent.squaredNorm()
   o[15] = r[15] = size;
   RssRec32 r32;
   pack_rss32(f.axis, f.rss_To, f.rss_l, f.rss_r, r32);
@@ -225,9 +225,9 @@ __device__ inline void fit_obbrss_warp(const double* __restrict__ tv, int tri_st
   const double a00 = A[0], a10 = A[3], a20 = A[6], a01 = A[1], a11 = A[4], a21 = A[7], a02 = A[2], a12 = A[5], a22 = A[8];
   const int m = 3 * n;
 #define W_PT(j) (tv + (size_t)idx[(j) / 3] * tri_stride + 3 * ((j) % 3))
-#define W_PX(p) ((a00 * (p)[0] + a10 * (p)[1]) + a20 * (p)[2])
-#define W_PY(p) ((a01 * (p)[0] + a11 * (p)[1]) + a21 * (p)[2])
-#define W_PZ(p) ((a02 * (p)[0] + a12 * (p)[1]) + a22 * (p)[2])
+#define W_PX(p) FCL_SUM3(a00 * (p)[0], a10 * (p)[1], a20 * (p)[2])
+#define W_PY(p) FCL_SUM3(a01 * (p)[0], a11 * (p)[1], a21 * (p)[2])
+#define W_PZ(p) FCL_SUM3(a02 * (p)[0], a12 * (p)[1], a22 * (p)[2])
   // --- extents (min / max of the projections) and extreme points along x and y (first index wins) ---
   double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
   double vminx = DBL_MAX, vmaxx = DBL_MAX, vminy = DBL_MAX, vmaxy = DBL_MAX;  // arg-max tracked on the negated value
@@ -257,7 +257,7 @@ __device__ inline void fit_obbrss_warp(const double* __restrict__ tv, int tri_st
   warp_argmin(vmaxy, imaxy);
   const double o[3] = {(mx[0] + mn[0]) / 2, (mx[1] + mn[1]) / 2, (mx[2] + mn[2]) / 2};
   for (int r = 0; r < 3; ++r) {
-    f.obb_To[r] = (A[3 * r] * o[0] + A[3 * r + 1] * o[1]) + A[3 * r + 2] * o[2];
+    f.obb_To[r] = FCL_SUM3(A[3 * r] * o[0], A[3 * r + 1] * o[1], A[3 * r + 2] * o[2]);
     f.obb_ext[r] = (mx[r] - mn[r]) / 2;
   }
   const double minz = mn[2], maxz = mx[2];
@@ -414,9 +414,9 @@ __device__ inline void fit_obbrss_block(const double* __restrict__ tv, int tri_s
   const double a00 = A[0], a10 = A[3], a20 = A[6], a01 = A[1], a11 = A[4], a21 = A[7], a02 = A[2], a12 = A[5], a22 = A[8];
   const int m = 3 * n;
 #define W_PT(j) (tv + (size_t)idx[(j) / 3] * tri_stride + 3 * ((j) % 3))
-#define W_PX(p) ((a00 * (p)[0] + a10 * (p)[1]) + a20 * (p)[2])
-#define W_PY(p) ((a01 * (p)[0] + a11 * (p)[1]) + a21 * (p)[2])
-#define W_PZ(p) ((a02 * (p)[0] + a12 * (p)[1]) + a22 * (p)[2])
+#define W_PX(p) FCL_SUM3(a00 * (p)[0], a10 * (p)[1], a20 * (p)[2])
+#define W_PY(p) FCL_SUM3(a01 * (p)[0], a11 * (p)[1], a21 * (p)[2])
+#define W_PZ(p) FCL_SUM3(a02 * (p)[0], a12 * (p)[1], a22 * (p)[2])
   // --- extents and extreme points ---
   double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
   double vminx = DBL_MAX, vmaxx = DBL_MAX, vminy = DBL_MAX, vmaxy = DBL_MAX;
@@ -480,7 +480,7 @@ __device__ inline void fit_obbrss_block(const double* __restrict__ tv, int tri_s
   iminx = ai[0]; imaxx = ai[1]; iminy = ai[2]; imaxy = ai[3];
   const double o[3] = {(mx[0] + mn[0]) / 2, (mx[1] + mn[1]) / 2, (mx[2] + mn[2]) / 2};
   for (int r = 0; r < 3; ++r) {
-    f.obb_To[r] = (A[3 * r] * o[0] + A[3 * r + 1] * o[1]) + A[3 * r + 2] * o[2];
+    f.obb_To[r] = FCL_SUM3(A[3 * r] * o[0], A[3 * r + 1] * o[1], A[3 * r + 2] * o[2]);
     f.obb_ext[r] = (mx[r] - mn[r]) / 2;
   }
   const double minz = mn[2], maxz = mx[2];
@@ -605,7 +605,7 @@ __device__ __forceinline__ void store_node_records(const RefitParams& P, int nod
   r[12] = f.rss_l[0];
   r[13] = f.rss_l[1];
   r[14] = f.rss_r;
-  const double size = (f.obb_ext[0] * f.obb_ext[0] + f.obb_ext[1] * f.obb_ext[1]) + f.obb_ext[2] * f.obb_ext[2];
+  const double size = FCL_SUM3(f.obb_ext[0] * f.obb_ext[0], f.obb_ext[1] * f.obb_ext[1], f.obb_ext[2] * f.obb_ext[2]);  // extent.squaredNorm()
   o[15] = r[15] = size;
   RssRec32 r32;
   pack_rss32(f.axis, f.rss_To, f.rss_l, f.rss_r, r32);
@@ -660,7 +660,7 @@ __device__ __forceinline__ void store_node_bv(const RefitParams& P, int node, co
   r[12] = f.rss_l[0];
   r[13] = f.rss_l[1];
   r[14] = f.rss_r;
-  const double size = (f.obb_ext[0] * f.obb_ext[0] + f.obb_ext[1] * f.obb_ext[1]) + f.obb_ext[2] * f.obb_ext[2];
+  const double size = FCL_SUM3(f.obb_ext[0] * f.obb_ext[0], f.obb_ext[1] * f.obb_ext[1], f.obb_ext[2] * f.obb_ext[2]);  // extent.squaredNorm()
   o[15] = r[15] = size;
   RssRec32 r32;
   pack_rss32(f.rss_axis, f.rss_To, f.rss_l, f.rss_r, r32);
@@ -777,7 +777,7 @@ __device__ __forceinline__ double centroid_projection(const double* __restrict__
   const double* p2 = p1 + 3;
   const double* p3 = p1 + 6;
   const double c0 = (p1[0] + p2[0]) + p3[0], c1 = (p1[1] + p2[1]) + p3[1], c2 = (p1[2] + p2[2]) + p3[2];
-  return ((c0 * sv0 + c1 * sv1) + c2 * sv2) / 3;
+  return FCL_SUM3(c0 * sv0, c1 * sv1, c2 * sv2) / 3;
 }
 
 template <int kMode>
@@ -893,7 +893,7 @@ __device__ inline void build_finish_node(const BuildParams& B, const BuildNode n
     const double* p2 = p1 + 3;
     const double* p3 = p1 + 6;
     const double cx = ((p1[0] + p2[0]) + p3[0]) / 3.0, cy = ((p1[1] + p2[1]) + p3[1]) / 3.0, cz = ((p1[2] + p2[2]) + p3[2]) / 3.0;
-    B.flag[nd.first + i] = (((sv0 * cx + sv1 * cy) + sv2 * cz) > thr) ? 0 : 1;
+    B.flag[nd.first + i] = (FCL_SUM3(sv0 * cx, sv1 * cy, sv2 * cz) > thr) ? 0 : 1;
   }
   int c1 = 0;
   if (warp_mode) {
@@ -1004,7 +1004,7 @@ __device__ inline void build_finish_node_block(const BuildParams& B, const Build
       const double* p2 = p1 + 3;
       const double* p3 = p1 + 6;
       const double cx = ((p1[0] + p2[0]) + p3[0]) / 3.0, cy = ((p1[1] + p2[1]) + p3[1]) / 3.0, cz = ((p1[2] + p2[2]) + p3[2]) / 3.0;
-      left = !(((sv0 * cx + sv1 * cy) + sv2 * cz) > thr);
+      left = !(FCL_SUM3(sv0 * cx, sv1 * cy, sv2 * cz) > thr);
       fl[i] = left ? 1 : 0;
       old[i] = pi;
       if (!left && my_i0 == n) my_i0 = i;

@@ -10,7 +10,10 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+# FCL_SUM3_ORDER=1 in the environment selects the oracle built with the other association order of the three-term sums
+# (fcl_oracle_vec.hpp `sum3`; tests/test_sum_order_hook.py re-runs the parity tests with both sides flipped)
+_SUM3 = os.environ.get("FCL_SUM3_ORDER", "0")
+_LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so" if _SUM3 == "0" else "liboracle_sum3_%s.so" % _SUM3)
 
 SPLIT_MEAN, SPLIT_MEDIAN, SPLIT_BV_CENTER = 0, 1, 2
 
@@ -26,7 +29,12 @@ def build(force=False):
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs
     )
-    if force or stale:
+    if (force or stale) and _SUM3 != "0":
+        os.makedirs(os.path.dirname(_LIB_PATH), exist_ok=True)
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-pthread", "-DFCL_SUM3_ORDER=" + _SUM3,
+                               "-shared", "-o", _LIB_PATH] +
+                              [os.path.join(_HERE, f) for f in ("fcl_oracle_math.cpp", "fcl_oracle_bvh.cpp", "oracle_capi.cpp")])
+    elif force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _LIB_PATH
 
@@ -471,7 +479,7 @@ def broadphase(models, geom1, tf1, geom2, tf2, num_max_contacts=1, enable_contac
 # ------------------------------------------------------------------------------------------------
 # executed-operation counters (fcl_oracle_counted.cpp): the oracle recompiled over a counting scalar
 # ------------------------------------------------------------------------------------------------
-_CNT_PATH = os.path.join(_HERE, "_build", "liboracle_counted.so")
+_CNT_PATH = os.path.join(_HERE, "_build", "liboracle_counted.so" if _SUM3 == "0" else "liboracle_counted_sum3_%s.so" % _SUM3)
 _cnt = None
 OP_NAMES = ("mul", "add", "cmp", "div", "sqrt")
 
@@ -480,7 +488,10 @@ def counted_lib():
     global _cnt
     if _cnt is None:
         build()
-        if not os.path.exists(_CNT_PATH):
+        if not os.path.exists(_CNT_PATH) and _SUM3 != "0":
+            subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-pthread", "-Wno-unused-function",
+                                   "-DFCL_SUM3_ORDER=" + _SUM3, "-shared", "-o", _CNT_PATH, os.path.join(_HERE, "fcl_oracle_counted.cpp")])
+        elif not os.path.exists(_CNT_PATH):
             subprocess.check_call(["make", "-C", _HERE, "-s", "_build/liboracle_counted.so"])
         L = C.CDLL(_CNT_PATH)
         vp, dp, ip, lp = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_longlong)

@@ -9,8 +9,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "devmath_host.cu")
 _CSRC = os.path.join(_HERE, "..", "..", "fcl_b200", "csrc")
 _HDR = os.path.join(_CSRC, "device_math.cuh")
-_HDRS = [os.path.join(_CSRC, f) for f in ("device_math.cuh", "mesh_sphere.cuh", "bounds_f32.cuh", "records.hpp")]
-_OUT = os.path.join(_HERE, "_build", "libdevmath_host.so")
+_HDRS = [os.path.join(_CSRC, f) for f in ("device_math.cuh", "sum_order.h", "mesh_sphere.cuh", "bounds_f32.cuh", "records.hpp")]
+_SUM3 = os.environ.get("FCL_SUM3_ORDER", "0")  # see tests/test_sum_order_hook.py
+_OUT = os.path.join(_HERE, "_build", "libdevmath_host.so" if _SUM3 == "0" else "libdevmath_host_sum3_%s.so" % _SUM3)
 
 
 def build():
@@ -18,7 +19,7 @@ def build():
     if stale:
         os.makedirs(os.path.dirname(_OUT), exist_ok=True)
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler",
-                               "-fPIC,-ffp-contract=off", "-shared", "-o", _OUT, _SRC])
+                               "-fPIC,-ffp-contract=off", "-DFCL_SUM3_ORDER=" + _SUM3, "-shared", "-o", _OUT, _SRC])
     return _OUT
 
 

@@ -3,6 +3,8 @@ in the reference (gjk_solver_libccd-inl.h:502-540 -> halfspace-inl.h:587-621, pl
 without libccd.  CPU part: the oracle against the reference's own known answers (test_fcl_geometric_shapes.cpp:1295-1394)
 and against brute force; the product's device math (host build) against the oracle, bit for bit.  GPU part: the batched
 entry point against the oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -11,6 +13,14 @@ from fcl_b200.poses import identity_poses, random_poses
 from tests import hostcheck as H
 
 IDENT = identity_poses(1)[0]
+
+
+_FLIP = os.environ.get("FCL_SUM3_ORDER", "0") != "0"  # tests/test_sum_order_hook.py re-runs this file with both sides flipped
+
+
+def _sum3(a, b, c):
+    """The kernel prologue restated below uses the same association order as the library it is compared with."""
+    return a + (b + c) if _FLIP else (a + b) + c
 
 
 def _random_tf(seed):
@@ -61,15 +71,14 @@ def test_device_math_equals_oracle_bit_for_bit(oracle):
             tf_t[9:] *= 1e-3
         hit, cp, depth, normal = oracle.plane_tri_intersect(kind, nrm, d, tf_s, tri, tf_t)
         # what the kernel does: n' = R n0, d' = d0 + n' . t ; vertices to the world
-        n0 = nrm / np.sqrt((nrm[0] * nrm[0] + nrm[1] * nrm[1]) + nrm[2] * nrm[2])  # (1 / l) * n like unitNormalTest
-        l = np.sqrt((nrm[0] * nrm[0] + nrm[1] * nrm[1]) + nrm[2] * nrm[2])
+        l = np.sqrt(_sum3(nrm[0] * nrm[0], nrm[1] * nrm[1], nrm[2] * nrm[2]))  # (1 / l) * n like unitNormalTest
         inv_l = 1.0 / l
         n0, d0 = nrm * inv_l, d * inv_l
         Rs, ts = tf_s[:9].reshape(3, 3), tf_s[9:]
-        nw = np.array([(Rs[r, 0] * n0[0] + Rs[r, 1] * n0[1]) + Rs[r, 2] * n0[2] for r in range(3)])
-        dw = d0 + ((nw[0] * ts[0] + nw[1] * ts[1]) + nw[2] * ts[2])
+        nw = np.array([_sum3(Rs[r, 0] * n0[0], Rs[r, 1] * n0[1], Rs[r, 2] * n0[2]) for r in range(3)])
+        dw = d0 + _sum3(nw[0] * ts[0], nw[1] * ts[1], nw[2] * ts[2])
         Rt, tt = tf_t[:9].reshape(3, 3), tf_t[9:]
-        V = np.array([[((Rt[r, 0] * p[0] + Rt[r, 1] * p[1]) + Rt[r, 2] * p[2]) + tt[r] for r in range(3)] for p in tri])
+        V = np.array([[_sum3(Rt[r, 0] * p[0], Rt[r, 1] * p[1], Rt[r, 2] * p[2]) + tt[r] for r in range(3)] for p in tri])
         out = np.zeros(7)
         got = L.hm_plane_tri_intersect(0 if kind == "halfspace" else 1, H.dptr(np.ascontiguousarray(nw)), float(dw),
                                        H.dptr(np.ascontiguousarray(V.reshape(-1))), H.dptr(out))

@@ -94,3 +94,23 @@ def test_the_order_switch_is_live_and_both_sides_follow_it(tmp_path):
     assert changed > 0, "FCL_SUM3_ORDER has no effect"
     rel = np.abs(res[0] - res[1]) / np.maximum(np.abs(res[0]), 1e-300)
     assert np.nanmax(np.where(np.abs(res[0]) > 1e-9, rel, 0.0)) < 1e-9  # last bits only: far inside north_star's 1e-6
+
+
+def test_the_whole_cpu_parity_suite_passes_with_both_sides_flipped(tmp_path):
+    """The product library (host BVH builder, top-down and bottom-up refit, OBJ path), the host build of its device math and
+    the oracle (plain and counting builds), all compiled with -DFCL_SUM3_ORDER=1: every CPU test that compares the two sides
+    bit for bit must still pass -- the same set of sums goes through the switch on both sides.  (The GPU kernels take the
+    macro from the same headers; with the default order their SASS is unchanged.)"""
+    import sys
+
+    csrc = os.path.join(ROOT, "fcl_b200", "csrc")
+    lib = str(tmp_path / "libfclgpu_sum3_1.so")
+    subprocess.check_call(["nvcc", "-O1", "-std=c++17", "-fmad=false", "-gencode", "arch=compute_100a,code=sm_100a",
+                           "-Xcompiler", "-fPIC,-ffp-contract=off", "-Wno-deprecated-gpu-targets", "-DFCL_SUM3_ORDER=1", "-shared", "-o", lib] +
+                          [os.path.join(csrc, f) for f in ("fclgpu_api.cu", "bvh_build.cpp", "comm.cpp", "mesh_io.cpp")] + ["-ldl"])
+    env = dict(os.environ, FCL_SUM3_ORDER="1", FCLGPU_LIB_PATH=lib)
+    files = ["test_host_api.py", "test_bottomup_refit.py", "test_device_math_host.py", "test_mesh_plane.py", "test_mesh_io.py",
+             "test_exact_golden.py", "test_oracle_counters.py", "test_oracle_known_answers.py", "test_continuous.py", "test_broadphase.py"]
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "not gpu", "-p", "no:cacheprovider"] +
+                       [os.path.join(ROOT, "tests", f) for f in files], env=env, cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
